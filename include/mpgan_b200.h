@@ -1,0 +1,119 @@
+/* mpgan_b200 -- C ABI of the B200-native MPGAN / GAPT message-passing hot path.
+ *
+ * Drop-in boundary: these are the entry points a maintainer of rkansal47/MPGAN binds (ctypes /
+ * torch custom op) to replace the aten op chains below `MPLayer.forward`
+ * (mpgan/model.py:206-282), `LinearNet.forward` (mpgan/model.py:70-85), the generator /
+ * discriminator mask + tail code (mpgan/model.py:689-699, 723-752, 810-831, 881-884),
+ * `SpectralNorm._update_u_v` (mpgan/spectral_normalization.py:21-33) and GAPT's `MAB.forward`
+ * (gapt/model.py:124-139).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer to fp32 data unless stated otherwise; tensors are row-major;
+ *    `ld*` arguments are row strides in elements, so strided views (e.g. x[:, :, :-1]) need no copy
+ *  - calls are asynchronous on `stream` (a cudaStream_t passed as void*), never allocate, keep no
+ *    global state and are safe under CUDA-graph capture; scratch memory comes from the caller
+ *  - gradient outputs named d<param> are ACCUMULATED into (+=), matching autograd's .grad semantics;
+ *    gradient outputs w.r.t. activations (dx) are overwritten unless stated otherwise
+ *  - return value: 0 = ok; non-zero = error, message via mpg_last_error() (thread-local)
+ *  - there is no CPU fallback: a missing GPU / unsupported option is an error, never a silent detour
+ *  - dropout is a counter-based Philox4x32-10 stream keyed by (seed, rng_stream, row, column), so
+ *    the backward entry points regenerate exactly the mask the forward call drew; the effective
+ *    seed is `seed + *seed_dev` when the optional device pointer seed_dev is non-NULL, so a
+ *    captured CUDA graph draws fresh masks on every replay by bumping one device word
+ *  - precision: 0 = fp32-class (3xTF32 node GEMMs, fp32 SIMT edge network), 1 = fast
+ *    (TF32 node GEMMs; bf16 tcgen05 edge network with fp32 accumulation when the edge network is
+ *    the default 96/160/192 architecture, else the fp32 SIMT kernel)
+ */
+#ifndef MPGAN_B200_H_
+#define MPGAN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPG_ACT_NONE 0
+#define MPG_ACT_LRELU 1   /* LinearNet hidden layers */
+#define MPG_ACT_TANH 1    /* mpg_unary / mpg_gen_tail: 1 = tanh, 2 = sigmoid */
+#define MPG_ACT_SIGMOID 2
+
+int mpg_version(void);
+const char* mpg_last_error(void);
+/* compiled feature flags: bit0 = tcgen05 edge forward, bit1 = tcgen05 edge backward, bit2 = GAPT */
+int mpg_features(void);
+
+/* ---- LinearNet layer (mpgan/model.py:77-83): y = dropout(act(x W^T + b)) -------------------------- */
+int mpg_linear_fwd(const float* x, int ldx, const float* w, const float* b, float* y, int M, int K, int N,
+                   int act, float alpha, float p_drop, uint64_t seed, const uint64_t* seed_dev, uint32_t rng_stream,
+                   int precision, void* stream);
+/* given dy and the layer output y: dz = dy * d(act,dropout)(y) into `dz` (scratch [M,N], may alias dy);
+ * dx = dz W (skipped if dx == NULL; accumulated if dx_accumulate); dw += dz^T x; db += colsum(dz). */
+int mpg_linear_bwd(const float* dy, const float* y, const float* x, int ldx, const float* w, float* dz,
+                   float* dx, int lddx, int dx_accumulate, float* dw, float* db, int M, int K, int N, int act,
+                   float alpha, float p_drop, uint64_t seed, const uint64_t* seed_dev, uint32_t rng_stream,
+                   int precision, void* stream);
+
+/* ---- fused edge network + neighbour aggregation (mpgan/model.py:256-267, 284-317) -----------------
+ * agg[b,i,:] = scale * sum_j mask[b,j] * fe(x_i | x_j | ef_ij),  scale = 1 (sum) or 1/N (mean).
+ * W0 is fe.net.0.weight [H0, 2F + n_ef] with column blocks (receiver | sender | [diffs] | [dist]).
+ * ef_mode: bit0 = Euclidean distance column, bit1 = difference columns; nd = number of leading
+ * features the differences are taken over.  The N^2 x H tensors never leave the SM. */
+size_t mpg_edge_workspace_bytes(int B, int N, int F, int H0, int H1, int H2);
+int mpg_edge_fwd(const float* x, int ldx, const float* mask, const float* w0, const float* b0, const float* w1,
+                 const float* b1, const float* w2, const float* b2, int B, int N, int F, int H0, int H1, int H2,
+                 int ef_mode, int nd, int mean, float alpha, float p_drop, uint64_t seed, const uint64_t* seed_dev,
+                 int precision, void* workspace, size_t workspace_bytes, float* agg, void* stream);
+/* recomputes the edge activations tile by tile; dx [B*N, F] (row stride lddx) is overwritten */
+int mpg_edge_bwd(const float* x, int ldx, const float* mask, const float* w0, const float* b0, const float* w1,
+                 const float* b1, const float* w2, const float* b2, int B, int N, int F, int H0, int H1, int H2,
+                 int ef_mode, int nd, int mean, float alpha, float p_drop, uint64_t seed, const uint64_t* seed_dev,
+                 int precision, void* workspace, size_t workspace_bytes, const float* dagg, float* dx, int lddx, float* dw0,
+                 float* db0, float* dw1, float* db1, float* dw2, float* db2, void* stream);
+
+/* ---- masks and tails ------------------------------------------------------------------------------ */
+/* mask[b,i] = rank(x[b,i,0]) <= int(labels[b]*N) - 1   (bit-exact; mpgan/model.py:692-699) */
+int mpg_rank_mask(const float* x, int ldx, const float* labels, int ldl, int B, int N, float* mask, void* stream);
+/* mask[r] = x[r, ldx-1] + 0.5   (mpgan/model.py:881) */
+int mpg_split_mask(const float* x, int ldx, int rows, float* mask, void* stream);
+/* out[r, :Fo] = act(h[r, :]); out[r, Fo] = mask[r] - 0.5 if mask   (mpgan/model.py:535-536, 752) */
+int mpg_gen_tail_fwd(const float* h, const float* mask, float* out, int rows, int Fo, int act, void* stream);
+int mpg_gen_tail_bwd(const float* dout, const float* out, float* dh, int rows, int Fo, int ldo, int act,
+                     void* stream);
+/* pooled[b,:] = sum_i h[b,i,:]*mask[b,i]  (/(sum mask + 1e-12) if mean)   (mpgan/model.py:810-822) */
+int mpg_pool_fwd(const float* h, const float* mask, float* out, int B, int N, int C, int mean, void* stream);
+int mpg_pool_bwd(const float* dout, const float* mask, float* dh, int B, int N, int C, int mean, void* stream);
+int mpg_unary_fwd(const float* x, float* y, size_t n, int act, void* stream);
+int mpg_unary_bwd(const float* dy, const float* y, float* dx, size_t n, int act, void* stream);
+
+/* ---- spectral norm (spectral_normalization.py:21-33): one power iteration, u/v updated in place --- */
+int mpg_sn_fwd(const float* w_bar, float* u, float* v, float* w_out, float* sigma, int H, int W, void* stream);
+int mpg_sn_bwd(const float* dw, const float* w_bar, const float* u, const float* v, const float* sigma,
+               float* dw_bar, int H, int W, void* stream);
+
+/* ---- optimizer: torch.optim.RMSprop(alpha, eps) on a flat buffer; g is scaled by gscale first ------ */
+int mpg_rmsprop(float* p, const float* g, float* sq, size_t n, float lr, float alpha, float eps, float gscale,
+                void* stream);
+
+/* ---- GAPT set attention (gapt/model.py:124-139; nn.MultiheadAttention with a key mask) -------------
+ * o[b,i,h*d:(h+1)*d] = softmax_j(q_i.k_j / sqrt(d) | key j not ignored) v_j, per head h (d = E/heads).
+ * q/k/v are rows [B*N, E] with row strides ld* (a packed [B*N, 3E] in_proj output needs no split).
+ * key_mask [B, Nk]: keys with mask != 1.0 are ignored (gapt/model.py:194-202: (1 - mask).bool());
+ * NULL = attend to every key.  p_saved [B, heads, Nq, Nk] keeps the probabilities for backward. */
+int mpg_attn_fwd(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, const float* key_mask,
+                 int B, int Nq, int Nk, int E, int heads, float* o, float* p_saved, void* stream);
+/* dq/dk/dv are dense [B*N, E] and overwritten */
+int mpg_attn_bwd(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, const float* key_mask,
+                 int B, int Nq, int Nk, int E, int heads, const float* p_saved, const float* dout, float* dq,
+                 float* dk, float* dv, void* stream);
+/* out = dropout(x + r) (r may be NULL): the residual + nn.Dropout steps of MAB.forward (:129-137) */
+int mpg_residual_dropout_fwd(const float* x, const float* r, float* out, size_t rows, int cols, float p_drop,
+                             uint64_t seed, const uint64_t* seed_dev, uint32_t rng_stream, void* stream);
+int mpg_residual_dropout_bwd(const float* dout, float* dx, size_t rows, int cols, float p_drop, uint64_t seed,
+                             const uint64_t* seed_dev, uint32_t rng_stream, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPGAN_B200_H_ */

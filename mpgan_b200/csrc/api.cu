@@ -1,0 +1,290 @@
+// extern "C" boundary of libmpgan_b200.so (see include/mpgan_b200.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include "../../include/mpgan_b200.h"
+#include "edge.cuh"
+#include "gapt.cuh"
+#include "gemm.cuh"
+#include "misc.cuh"
+
+namespace mpg {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+namespace {
+
+__global__ void add_strided_kernel(float* __restrict__ dst, int ldd, const float* __restrict__ src, int lds,
+                                   int rows, int cols) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < rows * cols) {
+    const int r = idx / cols, c = idx % cols;
+    dst[(size_t)r * ldd + c] += src[(size_t)r * lds + c];
+  }
+}
+
+struct EdgeWs {
+  float *P, *Q, *W1t, *W2t, *dP, *dQ, *dxef;
+  void* tc;
+  size_t total;
+};
+
+size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+
+EdgeWs carve_edge_ws(void* base, int B, int N, int F, int H0, int H1, int H2) {
+  EdgeWs w;
+  size_t off = 0;
+  char* p = reinterpret_cast<char*>(base);
+  auto take = [&](size_t floats) {
+    float* r = reinterpret_cast<float*>(p + off);
+    off += align_up(floats * sizeof(float));
+    return r;
+  };
+  const size_t BN = (size_t)B * N;
+  w.P = take(BN * H0);
+  w.Q = take(BN * H0);
+  w.W1t = take((size_t)H0 * H1);
+  w.W2t = take((size_t)H1 * H2);
+  w.dP = take(BN * H0);
+  w.dQ = take(BN * H0);
+  w.dxef = take(BN * F);
+  w.tc = p + off;
+  off += align_up(edge_tc_workspace_bytes(B, N, H0, H1, H2));
+  w.total = off;
+  return w;
+}
+
+int edge_common(EdgeArgs& a, EdgeWs& w, const float* x, int ldx, const float* mask, const float* w0,
+                const float* b0, const float* w1, const float* b1, const float* w2, const float* b2, int B, int N,
+                int F, int H0, int H1, int H2, int ef_mode, int nd, int mean, float alpha, float p_drop,
+                uint64_t seed, const uint64_t* seed_dev, int precision, void* workspace, size_t workspace_bytes, bool* use_tc,
+                cudaStream_t s) {
+  MPG_CHECK(B > 0 && N > 0 && F > 0, "bad edge problem size B=%d N=%d F=%d", B, N, F);
+  MPG_CHECK(ef_mode >= 0 && ef_mode <= 3 && (ef_mode == 0 || (nd > 0 && nd <= F)), "bad ef_mode/nd");
+  MPG_CHECK(p_drop >= 0.f && p_drop < 1.f, "dropout p must be in [0,1)");
+  w = carve_edge_ws(workspace, B, N, F, H0, H1, H2);
+  MPG_CHECK(workspace != nullptr && workspace_bytes >= w.total, "edge workspace too small: need %zu bytes, got %zu",
+            w.total, workspace_bytes);
+  memset(&a, 0, sizeof(a));
+  a.B = B; a.N = N; a.F = F; a.H0 = H0; a.H1 = H1; a.H2 = H2;
+  a.n_ef = ((ef_mode & 2) ? nd : 0) + (ef_mode & 1);
+  a.nd = ef_mode ? nd : 0;
+  a.ef_mode = ef_mode;
+  a.ldwef = 2 * F + a.n_ef;
+  a.Wef = w0 + 2 * F;
+  a.x = x; a.ldx = ldx;
+  a.P = w.P; a.Q = w.Q;
+  a.W1 = w1; a.W2 = w2; a.W1t = w.W1t; a.W2t = w.W2t; a.b1 = b1; a.b2 = b2;
+  a.mask = mask;
+  a.alpha = alpha;
+  a.out_scale = mean ? 1.f / (float)N : 1.f;
+  a.drop = make_drop(p_drop, seed, seed_dev);
+  const bool precise = precision == 0;
+  *use_tc = !precise && edge_tc_supported(a);
+  // factorised first layer: W0 [x_i ; x_j ; ef] = Wa x_i + Wb x_j + Wef ef   (node-level GEMMs)
+  GemmEpi e;
+  e.bias = b0;
+  if (launch_gemm(true, true, true, x, ldx, w0, a.ldwef, w.P, H0, B * N, H0, F, e, 1, s)) return 1;
+  GemmEpi e2;
+  if (launch_gemm(true, true, true, x, ldx, w0 + F, a.ldwef, w.Q, H0, B * N, H0, F, e2, 1, s)) return 1;
+  if (!*use_tc) {
+    if (launch_transpose(w1, H1, H0, w.W1t, s)) return 1;
+    if (launch_transpose(w2, H2, H1, w.W2t, s)) return 1;
+  }
+  return 0;
+}
+
+}  // namespace
+}  // namespace mpg
+
+using namespace mpg;
+
+extern "C" {
+
+int mpg_version(void) { return 100; }
+const char* mpg_last_error(void) { return g_err; }
+int mpg_features(void) { return edge_tc_features() | 4; }
+
+int mpg_linear_fwd(const float* x, int ldx, const float* w, const float* b, float* y, int M, int K, int N, int act,
+                   float alpha, float p_drop, uint64_t seed, const uint64_t* seed_dev, uint32_t rng_stream, int precision,
+                   void* stream) {
+  MPG_CHECK(M >= 0 && K > 0 && N > 0, "bad linear size M=%d K=%d N=%d", M, K, N);
+  MPG_CHECK(p_drop >= 0.f && p_drop < 1.f, "dropout p must be in [0,1)");
+  GemmEpi e;
+  e.bias = b;
+  e.act = act;
+  e.alpha = alpha;
+  e.drop = p_drop > 0.f;
+  e.dc = make_drop(p_drop, seed, seed_dev);
+  e.stream = rng_stream;
+  return launch_gemm(true, true, precision == 0, x, ldx, w, K, y, N, M, N, K, e, 1, (cudaStream_t)stream);
+}
+
+int mpg_linear_bwd(const float* dy, const float* y, const float* x, int ldx, const float* w, float* dz, float* dx,
+                   int lddx, int dx_accumulate, float* dw, float* db, int M, int K, int N, int act, float alpha,
+                   float p_drop, uint64_t seed, const uint64_t* seed_dev, uint32_t rng_stream, int precision,
+                   void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  MPG_CHECK(M >= 0 && K > 0 && N > 0, "bad linear size M=%d K=%d N=%d", M, K, N);
+  const bool precise = precision == 0;
+  const float* g = dy;
+  if (act || p_drop > 0.f) {
+    MPG_CHECK(dz != nullptr && y != nullptr, "linear_bwd needs y and a dz scratch buffer");
+    if (launch_act_bwd(dy, y, dz, M, N, act, alpha, make_drop(p_drop, seed, seed_dev), rng_stream, s)) return 1;
+    g = dz;
+  }
+  if (dx != nullptr) {
+    GemmEpi e;
+    e.accumulate = dx_accumulate;
+    if (launch_gemm(true, false, precise, g, N, w, K, dx, lddx, M, K, N, e, 1, s)) return 1;
+  }
+  if (dw != nullptr) {
+    GemmEpi e;
+    e.accumulate = 1;
+    const int tiles = cdiv(N, 64) * cdiv(K, 64);
+    int split = tiles >= 148 ? 1 : (2 * 148) / tiles;
+    if (split > cdiv(M, 128)) split = cdiv(M, 128);
+    if (launch_gemm(false, false, precise, g, N, x, ldx, dw, K, N, K, M, e, split < 1 ? 1 : split, s)) return 1;
+  }
+  if (db != nullptr)
+    if (launch_colsum(g, N, M, N, db, s)) return 1;
+  return 0;
+}
+
+size_t mpg_edge_workspace_bytes(int B, int N, int F, int H0, int H1, int H2) {
+  return carve_edge_ws(nullptr, B, N, F, H0, H1, H2).total;
+}
+
+int mpg_edge_fwd(const float* x, int ldx, const float* mask, const float* w0, const float* b0, const float* w1,
+                 const float* b1, const float* w2, const float* b2, int B, int N, int F, int H0, int H1, int H2,
+                 int ef_mode, int nd, int mean, float alpha, float p_drop, uint64_t seed, const uint64_t* seed_dev,
+                 int precision, void* workspace, size_t workspace_bytes, float* agg, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  EdgeArgs a;
+  EdgeWs w;
+  bool use_tc = false;
+  if (edge_common(a, w, x, ldx, mask, w0, b0, w1, b1, w2, b2, B, N, F, H0, H1, H2, ef_mode, nd, mean, alpha,
+                  p_drop, seed, seed_dev, precision, workspace, workspace_bytes, &use_tc, s))
+    return 1;
+  a.agg = agg;
+  if (use_tc) return launch_edge_tc_fwd(a, w.tc, s);
+  return launch_edge_generic(a, false, s);
+}
+
+int mpg_edge_bwd(const float* x, int ldx, const float* mask, const float* w0, const float* b0, const float* w1,
+                 const float* b1, const float* w2, const float* b2, int B, int N, int F, int H0, int H1, int H2,
+                 int ef_mode, int nd, int mean, float alpha, float p_drop, uint64_t seed, const uint64_t* seed_dev,
+                 int precision, void* workspace, size_t workspace_bytes, const float* dagg, float* dx, int lddx, float* dw0,
+                 float* db0, float* dw1, float* db1, float* dw2, float* db2, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  EdgeArgs a;
+  EdgeWs w;
+  bool use_tc = false;
+  if (edge_common(a, w, x, ldx, mask, w0, b0, w1, b1, w2, b2, B, N, F, H0, H1, H2, ef_mode, nd, mean, alpha,
+                  p_drop, seed, seed_dev, precision, workspace, workspace_bytes, &use_tc, s))
+    return 1;
+  MPG_CHECK(dagg && dx && dw0 && db0 && dw1 && db1 && dw2 && db2, "edge_bwd: null gradient pointer");
+  const size_t BN = (size_t)B * N;
+  a.dagg = dagg;
+  a.dW1 = dw1; a.db1 = db1; a.dW2 = dw2; a.db2 = db2;
+  a.dP = w.dP; a.dQ = w.dQ; a.dx_ef = w.dxef;
+  a.dWef = dw0 + 2 * F;
+  MPG_CUDA(cudaMemsetAsync(w.dQ, 0, BN * H0 * sizeof(float), s));
+  if (a.n_ef) MPG_CUDA(cudaMemsetAsync(w.dxef, 0, BN * F * sizeof(float), s));
+  const bool tc_bwd = use_tc && (edge_tc_features() & 2);
+  if (tc_bwd) {
+    if (launch_edge_tc_bwd(a, w.tc, s)) return 1;
+  } else {
+    if (use_tc) {  // forward ran on tensor cores, backward kernel not built: generic needs W^T copies
+      if (launch_transpose(w1, H1, H0, w.W1t, s)) return 1;
+      if (launch_transpose(w2, H2, H1, w.W2t, s)) return 1;
+    }
+    if (launch_edge_generic(a, true, s)) return 1;
+  }
+  const bool precise = precision == 0;
+  // node-level tail of the factorised first layer
+  if (launch_colsum(w.dP, H0, (int)BN, H0, db0, s)) return 1;
+  int split = cdiv((long long)BN, 256);
+  if (split > 64) split = 64;
+  GemmEpi acc;
+  acc.accumulate = 1;
+  if (launch_gemm(false, false, precise, w.dP, H0, x, ldx, dw0, a.ldwef, H0, F, (int)BN, acc, split, s)) return 1;
+  if (launch_gemm(false, false, precise, w.dQ, H0, x, ldx, dw0 + F, a.ldwef, H0, F, (int)BN, acc, split, s)) return 1;
+  GemmEpi e0;
+  if (launch_gemm(true, false, precise, w.dP, H0, w0, a.ldwef, dx, lddx, (int)BN, F, H0, e0, 1, s)) return 1;
+  if (launch_gemm(true, false, precise, w.dQ, H0, w0 + F, a.ldwef, dx, lddx, (int)BN, F, H0, acc, 1, s)) return 1;
+  if (a.n_ef) {
+    add_strided_kernel<<<cdiv((long long)BN * F, 256), 256, 0, s>>>(dx, lddx, w.dxef, F, (int)BN, F);
+    MPG_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+int mpg_rank_mask(const float* x, int ldx, const float* labels, int ldl, int B, int N, float* mask, void* stream) {
+  MPG_CHECK(N > 0 && N <= 8192, "rank_mask: N out of range");
+  return launch_rank_mask(x, ldx, labels, ldl, B, N, mask, (cudaStream_t)stream);
+}
+int mpg_split_mask(const float* x, int ldx, int rows, float* mask, void* stream) {
+  return launch_split_mask(x, ldx, rows, mask, (cudaStream_t)stream);
+}
+int mpg_gen_tail_fwd(const float* h, const float* mask, float* out, int rows, int Fo, int act, void* stream) {
+  return launch_gen_tail_fwd(h, mask, out, rows, Fo, act, (cudaStream_t)stream);
+}
+int mpg_gen_tail_bwd(const float* dout, const float* out, float* dh, int rows, int Fo, int ldo, int act,
+                     void* stream) {
+  return launch_gen_tail_bwd(dout, out, dh, rows, Fo, ldo, act, (cudaStream_t)stream);
+}
+int mpg_pool_fwd(const float* h, const float* mask, float* out, int B, int N, int C, int mean, void* stream) {
+  return launch_pool_fwd(h, mask, out, B, N, C, mean, (cudaStream_t)stream);
+}
+int mpg_pool_bwd(const float* dout, const float* mask, float* dh, int B, int N, int C, int mean, void* stream) {
+  return launch_pool_bwd(dout, mask, dh, B, N, C, mean, (cudaStream_t)stream);
+}
+int mpg_unary_fwd(const float* x, float* y, size_t n, int act, void* stream) {
+  return launch_unary(x, nullptr, y, n, act, false, (cudaStream_t)stream);
+}
+int mpg_unary_bwd(const float* dy, const float* y, float* dx, size_t n, int act, void* stream) {
+  return launch_unary(y, dy, dx, n, act, true, (cudaStream_t)stream);
+}
+int mpg_sn_fwd(const float* w_bar, float* u, float* v, float* w_out, float* sigma, int H, int W, void* stream) {
+  MPG_CHECK((size_t)(H + W + 32) * 4 <= 48 * 1024, "spectral norm: weight too large");
+  return launch_sn_fwd(w_bar, u, v, w_out, sigma, H, W, (cudaStream_t)stream);
+}
+int mpg_sn_bwd(const float* dw, const float* w_bar, const float* u, const float* v, const float* sigma,
+               float* dw_bar, int H, int W, void* stream) {
+  return launch_sn_bwd(dw, w_bar, u, v, sigma, dw_bar, H, W, (cudaStream_t)stream);
+}
+int mpg_rmsprop(float* p, const float* g, float* sq, size_t n, float lr, float alpha, float eps, float gscale,
+                void* stream) {
+  return launch_rmsprop(p, g, sq, n, lr, alpha, eps, gscale, (cudaStream_t)stream);
+}
+
+int mpg_attn_fwd(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, const float* key_mask,
+                 int B, int Nq, int Nk, int E, int heads, float* o, float* p_saved, void* stream) {
+  AttnArgs a{q, ldq, k, ldk, v, ldv, key_mask, B, Nq, Nk, E, heads};
+  return launch_attn_fwd(a, o, p_saved, (cudaStream_t)stream);
+}
+int mpg_attn_bwd(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, const float* key_mask,
+                 int B, int Nq, int Nk, int E, int heads, const float* p_saved, const float* dout, float* dq,
+                 float* dk, float* dv, void* stream) {
+  AttnArgs a{q, ldq, k, ldk, v, ldv, key_mask, B, Nq, Nk, E, heads};
+  return launch_attn_bwd(a, p_saved, dout, dq, dk, dv, (cudaStream_t)stream);
+}
+int mpg_residual_dropout_fwd(const float* x, const float* r, float* out, size_t rows, int cols, float p_drop,
+                             uint64_t seed, const uint64_t* seed_dev, uint32_t rng_stream, void* stream) {
+  MPG_CHECK(p_drop >= 0.f && p_drop < 1.f, "dropout p must be in [0,1)");
+  return launch_resdrop(x, r, out, rows, cols, make_drop(p_drop, seed, seed_dev), rng_stream, false,
+                        (cudaStream_t)stream);
+}
+int mpg_residual_dropout_bwd(const float* dout, float* dx, size_t rows, int cols, float p_drop, uint64_t seed,
+                             const uint64_t* seed_dev, uint32_t rng_stream, void* stream) {
+  return launch_resdrop(dout, nullptr, dx, rows, cols, make_drop(p_drop, seed, seed_dev), rng_stream, true,
+                        (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,46 @@
+// Argument block shared by the edge-network kernels (generic SIMT and tcgen05).
+#pragma once
+#include "common.cuh"
+
+namespace mpg {
+
+struct EdgeArgs {
+  int B, N, F, H0, H1, H2;
+  // factorised first layer (node level): P = x*Wa^T + b0, Q = x*Wb^T   [B*N, H0]
+  const float* P;
+  const float* Q;
+  // optional pair features (pos_diffs): ef_mode bit0 = distance column, bit1 = difference columns
+  const float* x;        // [B*N, F] node features, row stride ldx
+  int ldx;
+  const float* Wef;      // &W0[0][2F], row stride ldwef
+  int ldwef, n_ef, nd, ef_mode;
+  const float* W1;       // [H1, H0]  (reference layout)
+  const float* W2;       // [H2, H1]
+  const float* W1t;      // [H0, H1]  (transposed copy, workspace)
+  const float* W2t;      // [H1, H2]
+  const float* b1;
+  const float* b2;
+  const float* mask;     // [B*N] multiplier on the sender axis, or null
+  float* agg;            // [B*N, H2]
+  float alpha, out_scale;
+  DropCfg drop;
+  // backward
+  const float* dagg;     // [B*N, H2]
+  float *dW1, *db1, *dW2, *db2;   // accumulated (atomics)
+  float *dP, *dQ;        // [B*N, H0]; dQ must be zeroed by the caller
+  float* dWef;           // &dW0[0][2F], row stride ldwef (accumulated)
+  float* dx_ef;          // [B*N, F] zeroed by the caller
+};
+
+size_t edge_generic_smem(const EdgeArgs& a, bool bwd);
+int launch_edge_generic(const EdgeArgs& a, bool bwd, cudaStream_t stream);
+int launch_transpose(const float* in, int rows, int cols, float* out, cudaStream_t stream);
+
+// tcgen05 path (edge_tc.cu): default architecture only
+int edge_tc_features();
+bool edge_tc_supported(const EdgeArgs& a);
+size_t edge_tc_workspace_bytes(int B, int N, int H0, int H1, int H2);
+int launch_edge_tc_fwd(const EdgeArgs& a, void* ws, cudaStream_t stream);
+int launch_edge_tc_bwd(const EdgeArgs& a, void* ws, cudaStream_t stream);
+
+}  // namespace mpg

@@ -1,0 +1,273 @@
+// TF32 mma.sync GEMM for node-level (O(B*N) rows) matrices.  See gemm.cuh.
+#include "gemm.cuh"
+
+namespace mpg {
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 32, NT = 128;
+constexpr int KS = BK + 4;   // stride of a [rows][k] tile  (conflict-free fragment reads)
+constexpr int MS = BM + 8;   // stride of a [k][rows] tile
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// Loads one BMxBK (or BNxBK) operand tile into registers: 16 floats per thread.
+// KMAJ: source element (r, k) at src[r*ld + k]; else at src[k*ld + r].
+template <bool KMAJ>
+__device__ __forceinline__ void load_tile(float (&reg)[16], const float* __restrict__ src, int ld, int r0,
+                                          int k0, int R, int K, int tid, bool vec_ok) {
+  if (KMAJ) {
+    // thread -> (row = tid/8 + 16*i, k = (tid%8)*4 .. +3)
+    const int kk = k0 + (tid & 7) * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = r0 + (tid >> 3) + 16 * i;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < R) {
+        const float* p = src + (size_t)r * ld + kk;
+        if (vec_ok && kk + 3 < K) {
+          v = *reinterpret_cast<const float4*>(p);
+        } else {
+          if (kk + 0 < K) v.x = p[0];
+          if (kk + 1 < K) v.y = p[1];
+          if (kk + 2 < K) v.z = p[2];
+          if (kk + 3 < K) v.w = p[3];
+        }
+      }
+      reg[4 * i + 0] = v.x; reg[4 * i + 1] = v.y; reg[4 * i + 2] = v.z; reg[4 * i + 3] = v.w;
+    }
+  } else {
+    // thread -> (k = tid/16 + 8*i, row = (tid%16)*4 .. +3)
+    const int rr = r0 + (tid & 15) * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = k0 + (tid >> 4) + 8 * i;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k < K) {
+        const float* p = src + (size_t)k * ld + rr;
+        if (vec_ok && rr + 3 < R) {
+          v = *reinterpret_cast<const float4*>(p);
+        } else {
+          if (rr + 0 < R) v.x = p[0];
+          if (rr + 1 < R) v.y = p[1];
+          if (rr + 2 < R) v.z = p[2];
+          if (rr + 3 < R) v.w = p[3];
+        }
+      }
+      reg[4 * i + 0] = v.x; reg[4 * i + 1] = v.y; reg[4 * i + 2] = v.z; reg[4 * i + 3] = v.w;
+    }
+  }
+}
+
+template <bool KMAJ>
+__device__ __forceinline__ void store_tile(float* __restrict__ s, const float (&reg)[16], int tid) {
+  if (KMAJ) {  // s[row][k], stride KS
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float* p = s + ((tid >> 3) + 16 * i) * KS + (tid & 7) * 4;
+      *reinterpret_cast<float4*>(p) = make_float4(reg[4 * i], reg[4 * i + 1], reg[4 * i + 2], reg[4 * i + 3]);
+    }
+  } else {     // s[k][row], stride MS
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float* p = s + ((tid >> 4) + 8 * i) * MS + (tid & 15) * 4;
+      *reinterpret_cast<float4*>(p) = make_float4(reg[4 * i], reg[4 * i + 1], reg[4 * i + 2], reg[4 * i + 3]);
+    }
+  }
+}
+
+template <bool KMAJ>
+__device__ __forceinline__ float tile_at(const float* __restrict__ s, int r, int k) {
+  return KMAJ ? s[r * KS + k] : s[k * MS + r];
+}
+
+constexpr int TILE_FLOATS = (BM * KS > BK * MS) ? BM * KS : BK * MS;
+
+template <bool A_K, bool B_K, bool PRECISE>
+__global__ void __launch_bounds__(NT) gemm_kernel(const float* __restrict__ A, int lda,
+                                                  const float* __restrict__ B, int ldb,
+                                                  float* __restrict__ C, int ldc, int M, int N, int K,
+                                                  int k_per_split, GemmEpi epi, bool vecA, bool vecB) {
+  if (epi.drop) resolve_seed(epi.dc);
+  if (epi.g_drop) resolve_seed(epi.gdc);
+  __shared__ __align__(16) float As[2][TILE_FLOATS];
+  __shared__ __align__(16) float Bs[2][TILE_FLOATS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kbeg = blockIdx.z * k_per_split;
+  const int kend = min(K, kbeg + k_per_split);
+
+  float acc[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
+
+  float ra[16], rb[16];
+  const int nchunks = (kend - kbeg + BK - 1) / BK;
+  if (nchunks > 0) {
+    load_tile<A_K>(ra, A, lda, m0, kbeg, M, kend, tid, vecA);
+    load_tile<B_K>(rb, B, ldb, n0, kbeg, N, kend, tid, vecB);
+    store_tile<A_K>(As[0], ra, tid);
+    store_tile<B_K>(Bs[0], rb, tid);
+  }
+  __syncthreads();
+  for (int c = 0; c < nchunks; ++c) {
+    const int cur = c & 1;
+    if (c + 1 < nchunks) {
+      load_tile<A_K>(ra, A, lda, m0, kbeg + (c + 1) * BK, M, kend, tid, vecA);
+      load_tile<B_K>(rb, B, ldb, n0, kbeg + (c + 1) * BK, N, kend, tid, vecB);
+    }
+    const float* as = As[cur];
+    const float* bs = Bs[cur];
+#pragma unroll
+    for (int kk = 0; kk < BK; kk += 8) {
+      uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        const int r = wm + mi * 16 + g;
+        const float v[4] = {tile_at<A_K>(as, r, kk + t), tile_at<A_K>(as, r + 8, kk + t),
+                            tile_at<A_K>(as, r, kk + t + 4), tile_at<A_K>(as, r + 8, kk + t + 4)};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          ah[mi][q] = to_tf32(v[q]);
+          if (PRECISE) al[mi][q] = to_tf32(v[q] - __uint_as_float(ah[mi][q]));
+        }
+      }
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const int r = wn + ni * 8 + g;
+        const float v[2] = {tile_at<B_K>(bs, r, kk + t), tile_at<B_K>(bs, r, kk + t + 4)};
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          bh[ni][q] = to_tf32(v[q]);
+          if (PRECISE) bl[ni][q] = to_tf32(v[q] - __uint_as_float(bh[ni][q]));
+        }
+      }
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+          if (PRECISE) {
+            mma_tf32(acc[mi][ni], al[mi], bh[ni]);
+            mma_tf32(acc[mi][ni], ah[mi], bl[ni]);
+          }
+          mma_tf32(acc[mi][ni], ah[mi], bh[ni]);
+        }
+    }
+    if (c + 1 < nchunks) {
+      store_tile<A_K>(As[cur ^ 1], ra, tid);
+      store_tile<B_K>(Bs[cur ^ 1], rb, tid);
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue ---------------------------------------------------------------------------------
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int m = m0 + wm + mi * 16 + g + ((q & 2) ? 8 : 0);
+        const int n = n0 + wn + ni * 8 + 2 * t + (q & 1);
+        if (m >= M || n >= N) continue;
+        float v = acc[mi][ni][q] * epi.scale;
+        if (epi.bias != nullptr && blockIdx.z == 0) v += epi.bias[n];
+        if (epi.act) v = lrelu(v, epi.alpha);
+        if (epi.drop) v = drop_keep(epi.dc, epi.stream, (uint64_t)m, (uint32_t)n) ? v * epi.dc.scale : 0.f;
+        if (epi.gy != nullptr) {
+          const float y = epi.gy[(size_t)m * epi.ldgy + n];
+          float gfac = epi.g_act ? lrelu_grad_from_out(y, epi.alpha) : 1.f;
+          if (epi.g_drop)
+            gfac = drop_keep(epi.gdc, epi.gstream, (uint64_t)m, (uint32_t)n) ? gfac * epi.gdc.scale : 0.f;
+          v *= gfac;
+        }
+        float* dst = C + (size_t)m * ldc + n;
+        if (epi.atomic) atomicAdd(dst, v);
+        else if (epi.accumulate) *dst += v;
+        else *dst = v;
+      }
+}
+
+__global__ void colsum_kernel(const float* __restrict__ X, int ldx, int M, int N, float* __restrict__ out,
+                              int rows_per_block) {
+  // block (32 x 8): 32 consecutive columns, 8 row lanes
+  __shared__ float red[8][33];
+  const int n = blockIdx.x * 32 + threadIdx.x;
+  const int mbeg = blockIdx.y * rows_per_block;
+  const int mend = min(M, mbeg + rows_per_block);
+  float s = 0.f;
+  if (n < N)
+    for (int m = mbeg + threadIdx.y; m < mend; m += 8) s += X[(size_t)m * ldx + n];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && n < N) {
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += red[i][threadIdx.x];
+    atomicAdd(out + n, tot);
+  }
+}
+
+}  // namespace
+
+int launch_gemm(bool a_k, bool b_k, bool precise, const float* A, int lda, const float* B, int ldb, float* C,
+                int ldc, int M, int N, int K, const GemmEpi& epi_in, int split_k, cudaStream_t stream) {
+  if (M <= 0 || N <= 0) return 0;
+  GemmEpi epi = epi_in;
+  if (split_k < 1) split_k = 1;
+  int k_per_split = ((K + split_k - 1) / split_k + BK - 1) / BK * BK;
+  if (k_per_split < BK) k_per_split = BK;
+  split_k = (K + k_per_split - 1) / k_per_split;
+  if (split_k < 1) split_k = 1;
+  if (split_k > 1) {
+    MPG_CHECK(epi.accumulate && !epi.act && !epi.drop && epi.gy == nullptr,
+              "split-K GEMM needs a pure accumulate epilogue");
+    epi.atomic = 1;
+  }
+  const bool vecA = (lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+  const bool vecB = (ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
+  dim3 grid(cdiv(N, BN), cdiv(M, BM), split_k), block(NT);
+#define MPG_GEMM_CASE(AK, BK_, PR)                                                                    \
+  if (a_k == AK && b_k == BK_ && precise == PR)                                                       \
+    gemm_kernel<AK, BK_, PR><<<grid, block, 0, stream>>>(A, lda, B, ldb, C, ldc, M, N, K, k_per_split, \
+                                                         epi, vecA, vecB);
+  MPG_GEMM_CASE(true, true, false)
+  MPG_GEMM_CASE(true, true, true)
+  MPG_GEMM_CASE(true, false, false)
+  MPG_GEMM_CASE(true, false, true)
+  MPG_GEMM_CASE(false, false, false)
+  MPG_GEMM_CASE(false, false, true)
+  MPG_GEMM_CASE(false, true, false)
+  MPG_GEMM_CASE(false, true, true)
+#undef MPG_GEMM_CASE
+  MPG_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_colsum(const float* X, int ldx, int M, int N, float* out, cudaStream_t stream) {
+  if (M <= 0 || N <= 0) return 0;
+  const int rows_per_block = 256;
+  dim3 grid(cdiv(N, 32), cdiv(M, rows_per_block)), block(32, 8);
+  colsum_kernel<<<grid, block, 0, stream>>>(X, ldx, M, N, out, rows_per_block);
+  MPG_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace mpg

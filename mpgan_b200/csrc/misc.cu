@@ -1,0 +1,287 @@
+// Small HBM-bound kernels of the hot path: rank mask, activation backward, generator tail,
+// discriminator pooling, spectral-norm power iteration, fused RMSprop.  All vectorised /
+// warp-shuffle, one pass over their operands.
+#include "misc.cuh"
+
+namespace mpg {
+namespace {
+
+// ---- rank mask (mpgan/model.py:692-699, gapt/model.py:255-262) -------------------------------------
+// n = int(fp32(label) * fp32(N)) - 1 (truncation toward zero); mask_i = rank(x0_i) <= n.
+// rank = position in an ascending sort = #{k : x_k < x_i or (x_k == x_i and k < i)}.
+__global__ void rank_mask_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ labels,
+                                 int ldl, int N, float* __restrict__ mask) {
+  extern __shared__ float row[];
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) row[i] = x[((size_t)b * N + i) * ldx];
+  __syncthreads();
+  const int n = (int)__fmul_rn(labels[(size_t)b * ldl], (float)N) - 1;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const float v = row[i];
+    int rank = 0;
+    for (int k = 0; k < N; ++k) {
+      const float u = row[k];
+      rank += (u < v) || (u == v && k < i);
+    }
+    mask[(size_t)b * N + i] = rank <= n ? 1.f : 0.f;
+  }
+}
+
+// ---- dz = dy * d(act, dropout)/dz evaluated from the layer OUTPUT y --------------------------------
+__global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dz,
+                               int M, int N, int act, float alpha, DropCfg dc, uint32_t stream) {
+  resolve_seed(dc);
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)M * N) return;
+  const int m = (int)(idx / N), n = (int)(idx % N);
+  float g = act ? lrelu_grad_from_out(y[idx], alpha) : 1.f;
+  if (dc.p > 0.f) g = drop_keep(dc, stream, (uint64_t)m, (uint32_t)n) ? g * dc.scale : 0.f;
+  dz[idx] = dy[idx] * g;
+}
+
+// ---- generator tail: out[..., :Fo] = act(h), out[..., Fo] = mask - 0.5 (model.py:535-536,752) ------
+__global__ void gen_tail_fwd_kernel(const float* __restrict__ h, const float* __restrict__ mask,
+                                    float* __restrict__ out, int rows, int Fo, int act) {
+  const int ldo = Fo + (mask != nullptr);
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)rows * ldo) return;
+  const int r = (int)(idx / ldo), c = (int)(idx % ldo);
+  float v;
+  if (c < Fo) {
+    v = h[(size_t)r * Fo + c];
+    if (act == 1) v = tanhf(v);
+    else if (act == 2) v = 1.f / (1.f + expf(-v));
+  } else {
+    v = mask[r] - 0.5f;
+  }
+  out[idx] = v;
+}
+
+__global__ void gen_tail_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out,
+                                    float* __restrict__ dh, int rows, int Fo, int ldo, int act) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)rows * Fo) return;
+  const int r = (int)(idx / Fo), c = (int)(idx % Fo);
+  const float y = out[(size_t)r * ldo + c];
+  float g = dout[(size_t)r * ldo + c];
+  if (act == 1) g *= 1.f - y * y;
+  else if (act == 2) g *= y * (1.f - y);
+  dh[idx] = g;
+}
+
+// ---- discriminator input split: mask = x[..., -1] + 0.5 (model.py:881) ----------------------------
+__global__ void split_mask_kernel(const float* __restrict__ x, int ldx, int rows, float* __restrict__ mask) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < rows) mask[r] = x[(size_t)r * ldx + ldx - 1] + 0.5f;
+}
+
+// ---- masked pooling over particles (model.py:810-822) ----------------------------------------------
+// pooled[b][c] = sum_i h[b,i,c]*mask[b,i]  (/ (sum_i mask + 1e-12) if mean);  no mask: sum or mean.
+__global__ void pool_fwd_kernel(const float* __restrict__ h, const float* __restrict__ mask, float* __restrict__ out,
+                                int N, int C, int mean) {
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f, ms = 0.f;
+    for (int i = 0; i < N; ++i) {
+      const float m = mask ? mask[(size_t)b * N + i] : 1.f;
+      s = fmaf(h[((size_t)b * N + i) * C + c], m, s);
+      ms += m;
+    }
+    if (mean) s = mask ? s / (ms + 1e-12f) : s / (float)N;
+    out[(size_t)b * C + c] = s;
+  }
+}
+
+__global__ void pool_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ mask,
+                                float* __restrict__ dh, int N, int C, int mean) {
+  const int b = blockIdx.x;
+  float ms = 0.f;
+  if (mean && mask)
+    for (int i = 0; i < N; ++i) ms += mask[(size_t)b * N + i];
+  const float inv = mean ? (mask ? 1.f / (ms + 1e-12f) : 1.f / (float)N) : 1.f;
+  for (int idx = threadIdx.x; idx < N * C; idx += blockDim.x) {
+    const int i = idx / C, c = idx % C;
+    const float m = mask ? mask[(size_t)b * N + i] : 1.f;
+    dh[((size_t)b * N + i) * C + c] = dout[(size_t)b * C + c] * m * inv;
+  }
+}
+
+// ---- elementwise unary with backward from output ---------------------------------------------------
+__global__ void unary_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n, int act) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const float v = x[idx];
+  y[idx] = act == 1 ? tanhf(v) : (act == 2 ? 1.f / (1.f + expf(-v)) : v);
+}
+__global__ void unary_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dx,
+                                 size_t n, int act) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const float v = y[idx];
+  dx[idx] = dy[idx] * (act == 1 ? 1.f - v * v : (act == 2 ? v * (1.f - v) : 1.f));
+}
+
+// ---- spectral norm (spectral_normalization.py:21-33) -----------------------------------------------
+// one CTA per weight: v = l2n(W^T u); u = l2n(W v); sigma = u.(W v); W_out = W / (sigma + 1e-12)
+__device__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+  return t;
+}
+
+__global__ void sn_fwd_kernel(const float* __restrict__ Wb, float* __restrict__ u, float* __restrict__ v,
+                              float* __restrict__ Wout, float* __restrict__ sigma_out, int H, int Wd) {
+  extern __shared__ float sm[];
+  float* us = sm;            // [H]
+  float* vs = us + H;        // [Wd]
+  float* red = vs + Wd;      // [32]
+  for (int i = threadIdx.x; i < H; i += blockDim.x) us[i] = u[i];
+  __syncthreads();
+  // v = W^T u
+  float part = 0.f;
+  for (int j = threadIdx.x; j < Wd; j += blockDim.x) {
+    float s = 0.f;
+    for (int i = 0; i < H; ++i) s = fmaf(Wb[(size_t)i * Wd + j], us[i], s);
+    vs[j] = s;
+    part = fmaf(s, s, part);
+  }
+  float nrm = sqrtf(block_sum(part, red));
+  for (int j = threadIdx.x; j < Wd; j += blockDim.x) vs[j] = vs[j] / (nrm + 1e-12f);
+  __syncthreads();
+  // u = W v  (one warp per row)
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int i = w; i < H; i += nw) {
+    float s = 0.f;
+    for (int j = lane; j < Wd; j += 32) s = fmaf(Wb[(size_t)i * Wd + j], vs[j], s);
+    s = warp_sum(s);
+    if (lane == 0) us[i] = s;   // holds W v
+  }
+  __syncthreads();
+  part = 0.f;
+  for (int i = threadIdx.x; i < H; i += blockDim.x) part = fmaf(us[i], us[i], part);
+  nrm = sqrtf(block_sum(part, red));
+  // u_new = Wv / (|Wv| + eps);  sigma = u_new . (W v)
+  part = 0.f;
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    const float wv = us[i];
+    const float un = wv / (nrm + 1e-12f);
+    part = fmaf(un, wv, part);
+    u[i] = un;
+  }
+  const float sigma = block_sum(part, red);
+  for (int j = threadIdx.x; j < Wd; j += blockDim.x) v[j] = vs[j];
+  if (threadIdx.x == 0) *sigma_out = sigma;
+  const float inv = 1.f / (sigma + 1e-12f);
+  for (int idx = threadIdx.x; idx < H * Wd; idx += blockDim.x) Wout[idx] = Wb[idx] * inv;
+}
+
+// dWb += dW/(s+eps) - (sum(dW*Wb)/(s+eps)^2) * u v^T      (u, v constants; sigma = u^T Wb v)
+__global__ void sn_bwd_kernel(const float* __restrict__ dW, const float* __restrict__ Wb,
+                              const float* __restrict__ u, const float* __restrict__ v,
+                              const float* __restrict__ sigma, float* __restrict__ dWb, int H, int Wd) {
+  __shared__ float red[32];
+  float part = 0.f;
+  for (int idx = threadIdx.x; idx < H * Wd; idx += blockDim.x) part = fmaf(dW[idx], Wb[idx], part);
+  const float dot = block_sum(part, red);
+  const float inv = 1.f / (*sigma + 1e-12f);
+  const float coef = dot * inv * inv;
+  for (int idx = threadIdx.x; idx < H * Wd; idx += blockDim.x) {
+    const int i = idx / Wd, j = idx % Wd;
+    dWb[idx] += dW[idx] * inv - coef * u[i] * v[j];
+  }
+}
+
+// ---- fused RMSprop over a flat parameter buffer (torch.optim.RMSprop defaults) ---------------------
+__global__ void rmsprop_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ sq, size_t n,
+                               float lr, float alpha, float eps, float gscale) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const float gr = g[idx] * gscale;
+  const float s = alpha * sq[idx] + (1.f - alpha) * gr * gr;
+  sq[idx] = s;
+  p[idx] -= lr * gr / (sqrtf(s) + eps);
+}
+
+}  // namespace
+
+int launch_rank_mask(const float* x, int ldx, const float* labels, int ldl, int B, int N, float* mask,
+                     cudaStream_t s) {
+  if (B <= 0) return 0;
+  rank_mask_kernel<<<B, 128, N * sizeof(float), s>>>(x, ldx, labels, ldl, N, mask);
+  MPG_LAUNCH_CHECK();
+  return 0;
+}
+int launch_act_bwd(const float* dy, const float* y, float* dz, int M, int N, int act, float alpha, DropCfg dc,
+                   uint32_t stream, cudaStream_t s) {
+  const size_t n = (size_t)M * N;
+  if (n == 0) return 0;
+  act_bwd_kernel<<<cdiv(n, 256), 256, 0, s>>>(dy, y, dz, M, N, act, alpha, dc, stream);
+  MPG_LAUNCH_CHECK();
+  return 0;
+}
+int launch_gen_tail_fwd(const float* h, const float* mask, float* out, int rows, int Fo, int act, cudaStream_t s) {
+  const size_t n = (size_t)rows * (Fo + (mask != nullptr));
+  if (n == 0) return 0;
+  gen_tail_fwd_kernel<<<cdiv(n, 256), 256, 0, s>>>(h, mask, out, rows, Fo, act);
+  MPG_LAUNCH_CHECK();
+  return 0;
+}
+int launch_gen_tail_bwd(const float* dout, const float* out, float* dh, int rows, int Fo, int ldo, int act,
+                        cudaStream_t s) {
+  const size_t n = (size_t)rows * Fo;
+  if (n == 0) return 0;
+  gen_tail_bwd_kernel<<<cdiv(n, 256), 256, 0, s>>>(dout, out, dh, rows, Fo, ldo, act);
+  MPG_LAUNCH_CHECK();
+  return 0;
+}
+int launch_split_mask(const float* x, int ldx, int rows, float* mask, cudaStream_t s) {
+  if (rows <= 0) return 0;
+  split_mask_kernel<<<cdiv(rows, 256), 256, 0, s>>>(x, ldx, rows, mask);
+  MPG_LAUNCH_CHECK();
+  return 0;
+}
+int launch_pool_fwd(const float* h, const float* mask, float* out, int B, int N, int C, int mean, cudaStream_t s) {
+  if (B <= 0) return 0;
+  pool_fwd_kernel<<<B, 64, 0, s>>>(h, mask, out, N, C, mean);
+  MPG_LAUNCH_CHECK();
+  return 0;
+}
+int launch_pool_bwd(const float* dout, const float* mask, float* dh, int B, int N, int C, int mean, cudaStream_t s) {
+  if (B <= 0) return 0;
+  pool_bwd_kernel<<<B, 256, 0, s>>>(dout, mask, dh, N, C, mean);
+  MPG_LAUNCH_CHECK();
+  return 0;
+}
+int launch_unary(const float* x, const float* dy, float* out, size_t n, int act, bool bwd, cudaStream_t s) {
+  if (n == 0) return 0;
+  if (bwd) unary_bwd_kernel<<<cdiv(n, 256), 256, 0, s>>>(dy, x, out, n, act);
+  else unary_fwd_kernel<<<cdiv(n, 256), 256, 0, s>>>(x, out, n, act);
+  MPG_LAUNCH_CHECK();
+  return 0;
+}
+int launch_sn_fwd(const float* Wb, float* u, float* v, float* Wout, float* sigma, int H, int Wd, cudaStream_t s) {
+  const size_t smem = (size_t)(H + Wd + 32) * sizeof(float);
+  sn_fwd_kernel<<<1, 256, smem, s>>>(Wb, u, v, Wout, sigma, H, Wd);
+  MPG_LAUNCH_CHECK();
+  return 0;
+}
+int launch_sn_bwd(const float* dW, const float* Wb, const float* u, const float* v, const float* sigma,
+                  float* dWb, int H, int Wd, cudaStream_t s) {
+  sn_bwd_kernel<<<1, 256, 0, s>>>(dW, Wb, u, v, sigma, dWb, H, Wd);
+  MPG_LAUNCH_CHECK();
+  return 0;
+}
+int launch_rmsprop(float* p, const float* g, float* sq, size_t n, float lr, float alpha, float eps, float gscale,
+                   cudaStream_t s) {
+  if (n == 0) return 0;
+  rmsprop_kernel<<<cdiv(n, 256), 256, 0, s>>>(p, g, sq, n, lr, alpha, eps, gscale);
+  MPG_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace mpg

@@ -1,0 +1,409 @@
+"""Autograd bindings of the C-ABI kernels (include/mpgan_b200.h).
+
+Each op is a ``torch.autograd.Function`` whose forward/backward call straight into
+``libmpgan_b200.so`` on the current CUDA stream.  PyTorch is used for device memory and autograd
+bookkeeping only.  Backward passes are ``once_differentiable``: double backward (WGAN-GP,
+``create_graph=True``) raises instead of silently producing wrong gradients.
+"""
+from __future__ import annotations
+
+import torch
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+
+# --------------------------------------------------------------------------------------------------
+# global knobs
+# --------------------------------------------------------------------------------------------------
+_PRECISION = 1          # 0: fp32-class (3xTF32 + fp32 SIMT edge), 1: fast (TF32 + bf16 tcgen05 edge)
+_seed_counter = 0
+_device_seed = None     # optional int64 CUDA tensor added to every dropout seed (CUDA-graph replay)
+
+
+def set_precision(p: int):
+    """0 = fp32-class reference accuracy, 1 = fast tensor-core path (default)."""
+    global _PRECISION
+    if p not in (0, 1):
+        raise ValueError("precision must be 0 or 1")
+    _PRECISION = p
+
+
+def get_precision() -> int:
+    return _PRECISION
+
+
+def set_device_seed(t):
+    """Register a 1-element int64 CUDA tensor whose value is added to every dropout seed."""
+    global _device_seed
+    if t is not None and not (t.is_cuda and t.dtype == torch.int64 and t.numel() == 1):
+        raise ValueError("device seed must be a 1-element int64 CUDA tensor")
+    _device_seed = t
+
+
+def next_seed() -> int:
+    """Fresh 64-bit dropout seed derived from torch's seed and a call counter."""
+    global _seed_counter
+    _seed_counter += 1
+    return (torch.initial_seed() * 0x9E3779B97F4A7C15 + _seed_counter * 0xD1342543DE82EF95) % (1 << 64)
+
+
+def _seed_ptr():
+    return None if _device_seed is None else _device_seed.data_ptr()
+
+
+def _rows(t):
+    """View a [..., K] tensor as rows with a constant row stride (no copy when possible)."""
+    if t.dim() == 2 and t.stride(1) == 1:
+        return t, t.stride(0)
+    if t.stride(-1) == 1 and t.dim() == 3 and t.stride(0) == t.shape[1] * t.stride(1):
+        return t, t.stride(1)
+    t = t.contiguous()
+    return t, t.shape[-1]
+
+
+# --------------------------------------------------------------------------------------------------
+# LinearNet layer
+# --------------------------------------------------------------------------------------------------
+class LinearFn(torch.autograd.Function):
+    """y = dropout(act(x W^T + b)) on rows; mpgan/model.py:77-83."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, act, alpha, p_drop, rng_stream):
+        L = _lib.lib()
+        x2, ldx = _rows(x)
+        lead = x2.shape[:-1]
+        M = int(x2.numel() // x2.shape[-1]) if x2.shape[-1] else 0
+        K, N = x2.shape[-1], w.shape[0]
+        w = w.contiguous()
+        b = b.contiguous()
+        y = torch.empty(*lead, N, device=x.device, dtype=torch.float32)
+        seed = next_seed() if p_drop > 0 else 0
+        _lib.check(L.mpg_linear_fwd(_lib.ptr(x2), ldx, _lib.ptr(w), _lib.ptr(b), _lib.ptr(y), M, K, N, int(act),
+                                    float(alpha), float(p_drop), seed, _seed_ptr(), int(rng_stream), _PRECISION,
+                                    _lib.stream()), "mpg_linear_fwd")
+        ctx.save_for_backward(x2, w, y)
+        ctx.cfg = (ldx, M, K, N, int(act), float(alpha), float(p_drop), seed, int(rng_stream), _PRECISION,
+                   _seed_ptr())
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        L = _lib.lib()
+        x2, w, y = ctx.saved_tensors
+        ldx, M, K, N, act, alpha, p, seed, rstream, prec, sptr = ctx.cfg
+        dy = dy.contiguous()
+        dz = torch.empty_like(dy) if (act or p > 0) else None
+        dx = torch.empty(*x2.shape, device=dy.device, dtype=torch.float32) if ctx.needs_input_grad[0] else None
+        dw = torch.zeros_like(w) if ctx.needs_input_grad[1] else None
+        db = torch.zeros(N, device=dy.device, dtype=torch.float32) if ctx.needs_input_grad[2] else None
+        _lib.check(L.mpg_linear_bwd(_lib.ptr(dy), _lib.ptr(y), _lib.ptr(x2), ldx, _lib.ptr(w), _lib.ptr(dz),
+                                    _lib.ptr(dx), K, 0, _lib.ptr(dw), _lib.ptr(db), M, K, N, act, alpha, p, seed,
+                                    sptr, rstream, prec, _lib.stream()), "mpg_linear_bwd")
+        return dx, dw, db, None, None, None, None
+
+
+def linear(x, w, b, act: bool, alpha: float, p_drop: float, rng_stream: int = 16):
+    return LinearFn.apply(x, w, b, act, alpha, p_drop, rng_stream)
+
+
+# --------------------------------------------------------------------------------------------------
+# fused edge network + aggregation
+# --------------------------------------------------------------------------------------------------
+class EdgeAggFn(torch.autograd.Function):
+    """agg[b,i] = scale * sum_j mask[b,j] fe(x_i | x_j | ef_ij); mpgan/model.py:256-267,284-317."""
+
+    @staticmethod
+    def forward(ctx, x, mask, w0, b0, w1, b1, w2, b2, ef_mode, nd, mean, alpha, p_drop):
+        L = _lib.lib()
+        x3, ldx = _rows(x)
+        B, N, F = x3.shape
+        H0, H1, H2 = w0.shape[0], w1.shape[0], w2.shape[0]
+        ws_bytes = L.mpg_edge_workspace_bytes(B, N, F, H0, H1, H2)
+        ws = torch.empty(ws_bytes, device=x.device, dtype=torch.uint8)
+        agg = torch.empty(B, N, H2, device=x.device, dtype=torch.float32)
+        m = None if mask is None else mask.reshape(B, N).contiguous()
+        ws_ = [t.contiguous() for t in (w0, b0, w1, b1, w2, b2)]
+        seed = next_seed() if p_drop > 0 else 0
+        _lib.check(L.mpg_edge_fwd(_lib.ptr(x3), ldx, _lib.ptr(m), *[_lib.ptr(t) for t in ws_], B, N, F, H0, H1, H2,
+                                  int(ef_mode), int(nd), int(mean), float(alpha), float(p_drop), seed, _seed_ptr(),
+                                  _PRECISION, ws.data_ptr(), ws_bytes, _lib.ptr(agg), _lib.stream()),
+                   "mpg_edge_fwd")
+        ctx.save_for_backward(x3, m, *ws_)
+        ctx.cfg = (ldx, B, N, F, H0, H1, H2, int(ef_mode), int(nd), int(mean), float(alpha), float(p_drop), seed,
+                   _PRECISION, _seed_ptr())
+        return agg
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dagg):
+        L = _lib.lib()
+        x3, m, w0, b0, w1, b1, w2, b2 = ctx.saved_tensors
+        ldx, B, N, F, H0, H1, H2, ef_mode, nd, mean, alpha, p, seed, prec, sptr = ctx.cfg
+        dagg = dagg.contiguous()
+        ws_bytes = L.mpg_edge_workspace_bytes(B, N, F, H0, H1, H2)
+        ws = torch.empty(ws_bytes, device=dagg.device, dtype=torch.uint8)
+        dx = torch.empty(B, N, F, device=dagg.device, dtype=torch.float32)
+        grads = [torch.zeros_like(t) for t in (w0, b0, w1, b1, w2, b2)]
+        _lib.check(L.mpg_edge_bwd(_lib.ptr(x3), ldx, _lib.ptr(m), *[_lib.ptr(t) for t in (w0, b0, w1, b1, w2, b2)],
+                                  B, N, F, H0, H1, H2, ef_mode, nd, mean, alpha, p, seed, sptr, prec, ws.data_ptr(),
+                                  ws_bytes, _lib.ptr(dagg), _lib.ptr(dx), F, *[_lib.ptr(g) for g in grads],
+                                  _lib.stream()), "mpg_edge_bwd")
+        return (dx, None, *grads, None, None, None, None, None)
+
+
+def edge_aggregate(x, mask, w0, b0, w1, b1, w2, b2, ef_mode=0, nd=0, mean=False, alpha=0.2, p_drop=0.0):
+    return EdgeAggFn.apply(x, mask, w0, b0, w1, b1, w2, b2, ef_mode, nd, mean, alpha, p_drop)
+
+
+# --------------------------------------------------------------------------------------------------
+# masks, tails, pooling
+# --------------------------------------------------------------------------------------------------
+def rank_mask(x, labels, num_particles: int):
+    """mask = rank(x[:, :, 0]) <= int(labels[:, -1] * N) - 1 as fp32 [B, N, 1] (bit-exact)."""
+    L = _lib.lib()
+    B, N = x.shape[0], x.shape[1]
+    x3, ldx = _rows(x.detach())
+    lab = labels.detach()[:, -1].contiguous().float()
+    mask = torch.empty(B, N, 1, device=x.device, dtype=torch.float32)
+    if N != num_particles:
+        raise RuntimeError(f"rank_mask: x has {N} particles, model was built for {num_particles}")
+    _lib.check(L.mpg_rank_mask(_lib.ptr(x3), ldx, _lib.ptr(lab), 1, B, N, _lib.ptr(mask), _lib.stream()),
+               "mpg_rank_mask")
+    return mask
+
+
+def split_mask(x):
+    """mask = x[..., -1:] + 0.5 (fp32 multiplier) for the discriminator input."""
+    L = _lib.lib()
+    x3, ldx = _rows(x.detach())
+    if ldx != x3.shape[-1]:
+        x3 = x3.contiguous()
+        ldx = x3.shape[-1]
+    B, N = x3.shape[0], x3.shape[1]
+    mask = torch.empty(B, N, 1, device=x.device, dtype=torch.float32)
+    _lib.check(L.mpg_split_mask(_lib.ptr(x3), ldx, B * N, _lib.ptr(mask), _lib.stream()), "mpg_split_mask")
+    return mask
+
+
+_ACT = {"": 0, "tanh": 1, "sigmoid": 2}
+
+
+class GenTailFn(torch.autograd.Function):
+    """cat(act(h), mask - 0.5); mpgan/model.py:535-536,752."""
+
+    @staticmethod
+    def forward(ctx, h, mask, act):
+        L = _lib.lib()
+        h = h.contiguous()
+        B, N, Fo = h.shape
+        ldo = Fo + (mask is not None)
+        out = torch.empty(B, N, ldo, device=h.device, dtype=torch.float32)
+        m = None if mask is None else mask.reshape(B, N).contiguous()
+        _lib.check(L.mpg_gen_tail_fwd(_lib.ptr(h), _lib.ptr(m), _lib.ptr(out), B * N, Fo, act, _lib.stream()),
+                   "mpg_gen_tail_fwd")
+        ctx.save_for_backward(out)
+        ctx.cfg = (B, N, Fo, ldo, act)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        L = _lib.lib()
+        (out,) = ctx.saved_tensors
+        B, N, Fo, ldo, act = ctx.cfg
+        dout = dout.contiguous()
+        dh = torch.empty(B, N, Fo, device=dout.device, dtype=torch.float32)
+        _lib.check(L.mpg_gen_tail_bwd(_lib.ptr(dout), _lib.ptr(out), _lib.ptr(dh), B * N, Fo, ldo, act,
+                                      _lib.stream()), "mpg_gen_tail_bwd")
+        return dh, None, None
+
+
+def gen_tail(h, mask, activation: str):
+    return GenTailFn.apply(h, mask, _ACT[activation])
+
+
+class PoolFn(torch.autograd.Function):
+    """sum_i h[b,i]*mask[b,i] (optionally / sum mask); mpgan/model.py:810-822."""
+
+    @staticmethod
+    def forward(ctx, h, mask, mean):
+        L = _lib.lib()
+        h = h.contiguous()
+        B, N, Cc = h.shape
+        m = None if mask is None else mask.reshape(B, N).contiguous()
+        out = torch.empty(B, Cc, device=h.device, dtype=torch.float32)
+        _lib.check(L.mpg_pool_fwd(_lib.ptr(h), _lib.ptr(m), _lib.ptr(out), B, N, Cc, int(mean), _lib.stream()),
+                   "mpg_pool_fwd")
+        ctx.save_for_backward(m) if m is not None else None
+        ctx.has_mask = m is not None
+        ctx.cfg = (B, N, Cc, int(mean))
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        L = _lib.lib()
+        m = ctx.saved_tensors[0] if ctx.has_mask else None
+        B, N, Cc, mean = ctx.cfg
+        dout = dout.contiguous()
+        dh = torch.empty(B, N, Cc, device=dout.device, dtype=torch.float32)
+        _lib.check(L.mpg_pool_bwd(_lib.ptr(dout), _lib.ptr(m), _lib.ptr(dh), B, N, Cc, mean, _lib.stream()),
+                   "mpg_pool_bwd")
+        return dh, None, None
+
+
+def masked_pool(h, mask, mean: bool):
+    return PoolFn.apply(h, mask, mean)
+
+
+class UnaryFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, act):
+        L = _lib.lib()
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        _lib.check(L.mpg_unary_fwd(_lib.ptr(x), _lib.ptr(y), x.numel(), act, _lib.stream()), "mpg_unary_fwd")
+        ctx.save_for_backward(y)
+        ctx.act = act
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        L = _lib.lib()
+        (y,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = torch.empty_like(dy)
+        _lib.check(L.mpg_unary_bwd(_lib.ptr(dy), _lib.ptr(y), _lib.ptr(dx), dy.numel(), ctx.act, _lib.stream()),
+                   "mpg_unary_bwd")
+        return dx, None
+
+
+def activation(x, name: str):
+    return x if name == "" else UnaryFn.apply(x, _ACT[name])
+
+
+# --------------------------------------------------------------------------------------------------
+# spectral norm
+# --------------------------------------------------------------------------------------------------
+class SpectralNormFn(torch.autograd.Function):
+    """One power iteration (u, v updated in place, no grad) and W = W_bar / (sigma + 1e-12)."""
+
+    @staticmethod
+    def forward(ctx, w_bar, u, v):
+        L = _lib.lib()
+        wb = w_bar.contiguous()
+        H = wb.shape[0]
+        Wd = wb.numel() // H
+        w = torch.empty_like(wb)
+        sigma = torch.empty(1, device=wb.device, dtype=torch.float32)
+        _lib.check(L.mpg_sn_fwd(_lib.ptr(wb), _lib.ptr(u), _lib.ptr(v), _lib.ptr(w), _lib.ptr(sigma), H, Wd,
+                                _lib.stream()), "mpg_sn_fwd")
+        ctx.save_for_backward(wb, u.clone(), v.clone(), sigma)
+        return w
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dw):
+        L = _lib.lib()
+        wb, u, v, sigma = ctx.saved_tensors
+        H = wb.shape[0]
+        Wd = wb.numel() // H
+        dw = dw.contiguous()
+        dwb = torch.zeros_like(wb)
+        _lib.check(L.mpg_sn_bwd(_lib.ptr(dw), _lib.ptr(wb), _lib.ptr(u), _lib.ptr(v), _lib.ptr(sigma),
+                                _lib.ptr(dwb), H, Wd, _lib.stream()), "mpg_sn_bwd")
+        return dwb, None, None
+
+
+def spectral_normalize(w_bar, u, v):
+    return SpectralNormFn.apply(w_bar, u, v)
+
+
+# --------------------------------------------------------------------------------------------------
+# optimizer
+# --------------------------------------------------------------------------------------------------
+def rmsprop_(p_flat, g_flat, sq_flat, lr, alpha=0.99, eps=1e-8, gscale=1.0):
+    L = _lib.lib()
+    _lib.check(L.mpg_rmsprop(_lib.ptr(p_flat), _lib.ptr(g_flat), _lib.ptr(sq_flat), p_flat.numel(), float(lr),
+                             float(alpha), float(eps), float(gscale), _lib.stream()), "mpg_rmsprop")
+
+
+# --------------------------------------------------------------------------------------------------
+# GAPT set attention
+# --------------------------------------------------------------------------------------------------
+class AttnFn(torch.autograd.Function):
+    """Masked multi-head softmax(q k^T / sqrt(d)) v on projected rows; gapt/model.py:129."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, key_mask, heads):
+        L = _lib.lib()
+        B, Nq, E = q.shape
+        Nk = k.shape[1]
+        q2, ldq = _rows(q)
+        k2, ldk = _rows(k)
+        v2, ldv = _rows(v)
+        km = None if key_mask is None else key_mask.reshape(B, Nk).contiguous().float()
+        o = torch.empty(B, Nq, E, device=q.device, dtype=torch.float32)
+        P = torch.empty(B, heads, Nq, Nk, device=q.device, dtype=torch.float32)
+        _lib.check(L.mpg_attn_fwd(_lib.ptr(q2), ldq, _lib.ptr(k2), ldk, _lib.ptr(v2), ldv, _lib.ptr(km), B, Nq, Nk,
+                                  E, heads, _lib.ptr(o), _lib.ptr(P), _lib.stream()), "mpg_attn_fwd")
+        ctx.save_for_backward(q2, k2, v2, km, P)
+        ctx.cfg = (ldq, ldk, ldv, B, Nq, Nk, E, heads)
+        return o
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, do):
+        L = _lib.lib()
+        q2, k2, v2, km, P = ctx.saved_tensors
+        ldq, ldk, ldv, B, Nq, Nk, E, heads = ctx.cfg
+        do = do.contiguous()
+        dq = torch.empty(B, Nq, E, device=do.device, dtype=torch.float32)
+        dk = torch.empty(B, Nk, E, device=do.device, dtype=torch.float32)
+        dv = torch.empty(B, Nk, E, device=do.device, dtype=torch.float32)
+        _lib.check(L.mpg_attn_bwd(_lib.ptr(q2), ldq, _lib.ptr(k2), ldk, _lib.ptr(v2), ldv, _lib.ptr(km), B, Nq, Nk,
+                                  E, heads, _lib.ptr(P), _lib.ptr(do), _lib.ptr(dq), _lib.ptr(dk), _lib.ptr(dv),
+                                  _lib.stream()), "mpg_attn_bwd")
+        return dq, dk, dv, None, None
+
+
+def attention(q, k, v, key_mask, heads: int):
+    return AttnFn.apply(q, k, v, key_mask, heads)
+
+
+class ResidualDropoutFn(torch.autograd.Function):
+    """out = dropout(x + r); the residual + nn.Dropout steps of MAB.forward (gapt/model.py:129-137)."""
+
+    @staticmethod
+    def forward(ctx, x, r, p_drop, rng_stream):
+        L = _lib.lib()
+        x = x.contiguous()
+        r = r.contiguous()
+        cols = x.shape[-1]
+        rows = x.numel() // cols
+        out = torch.empty_like(x)
+        seed = next_seed() if p_drop > 0 else 0
+        _lib.check(L.mpg_residual_dropout_fwd(_lib.ptr(x), _lib.ptr(r), _lib.ptr(out), rows, cols, float(p_drop),
+                                              seed, _seed_ptr(), int(rng_stream), _lib.stream()),
+                   "mpg_residual_dropout_fwd")
+        ctx.cfg = (rows, cols, float(p_drop), seed, _seed_ptr(), int(rng_stream))
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        L = _lib.lib()
+        rows, cols, p, seed, sptr, rstream = ctx.cfg
+        dout = dout.contiguous()
+        if p == 0:
+            return dout, dout, None, None
+        dx = torch.empty_like(dout)
+        _lib.check(L.mpg_residual_dropout_bwd(_lib.ptr(dout), _lib.ptr(dx), rows, cols, p, seed, sptr, rstream,
+                                              _lib.stream()), "mpg_residual_dropout_bwd")
+        return dx, dx, None, None
+
+
+def residual_dropout(x, r, p_drop: float, rng_stream: int = 48):
+    return ResidualDropoutFn.apply(x, r, p_drop, rng_stream)

@@ -1,0 +1,170 @@
+"""G+D training step and generation on top of the drop-in modules.
+
+Mirrors the reference's step functions (``train.py``: ``get_gen_noise`` :100-141, ``gen`` :144-223,
+``calc_D_loss`` :331-395, ``train_D`` :398-462, ``calc_G_loss`` :465-476, ``train_G`` :479-523) for
+the default configuration: least-squares loss, ``gp=0``, RMSprop (setup_training.py:1511-1513),
+one critic and one generator update per batch.
+
+Differences that do not change any gradient an optimizer consumes:
+  * ``train_D`` generates its fake batch under ``no_grad`` -- the reference keeps the graph and
+    back-propagates D's loss into G, then discards those gradients (train.py:428-437, 495);
+  * ``train_G`` does not compute D's weight gradients (they are discarded by the next zero_grad).
+
+Data parallel: one process per GPU; parameters and gradients live in one flat fp32 buffer per
+network, all-reduced (averaged) over NCCL after each backward; losses are batch means,
+so the averaged gradient equals the single-process gradient of the global batch.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+class FlatParams:
+    """Re-homes a module's trainable parameters and their grads into two flat fp32 buffers."""
+
+    def __init__(self, module: torch.nn.Module):
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        self.names = [n for n, p in module.named_parameters() if p.requires_grad]
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.grad = torch.zeros(n, device=dev, dtype=torch.float32)
+        off = 0
+        for p in self.params:
+            k = p.numel()
+            self.flat[off:off + k].copy_(p.data.reshape(-1))
+            p.data = self.flat[off:off + k].view_as(p)
+            p.grad = self.grad[off:off + k].view_as(p)
+            off += k
+
+    def zero_grad(self):
+        self.grad.zero_()
+        off = 0
+        for p in self.params:  # re-attach in case something replaced .grad
+            k = p.numel()
+            if p.grad is None or p.grad.data_ptr() != self.grad[off:off + k].data_ptr():
+                p.grad = self.grad[off:off + k].view_as(p)
+            off += k
+
+    def named_grads(self):
+        return {n: p.grad.detach().clone() for n, p in zip(self.names, self.params)}
+
+
+class FusedRMSprop:
+    """torch.optim.RMSprop(lr, alpha=0.99, eps=1e-8) on a flat buffer, one kernel per step."""
+
+    def __init__(self, fp: FlatParams, lr: float, alpha: float = 0.99, eps: float = 1e-8):
+        self.fp, self.lr, self.alpha, self.eps = fp, lr, alpha, eps
+        self.square_avg = torch.zeros_like(fp.flat)
+
+    def step(self, grad_scale: float = 1.0):
+        ops.rmsprop_(self.fp.flat, self.fp.grad, self.square_avg, self.lr, self.alpha, self.eps, grad_scale)
+
+
+def get_gen_noise(batch_size, num_particles, latent_node_size, sd=0.2, device="cuda", generator=None):
+    """Normal(0, sd) noise [B, N, latent] (train.py:113-127, ``--sd 0.2``)."""
+    return torch.randn(batch_size, num_particles, latent_node_size, device=device, generator=generator) * sd
+
+
+class GANTrainer:
+    def __init__(self, G, D, lr_gen=1e-5, lr_disc=3e-5, num_particles=30, latent_node_size=32, sd=0.2,
+                 process_group=None):
+        self.G, self.D = G, D
+        self.fpG, self.fpD = FlatParams(G), FlatParams(D)
+        self.optG, self.optD = FusedRMSprop(self.fpG, lr_gen), FusedRMSprop(self.fpD, lr_disc)
+        self.num_particles, self.latent, self.sd = num_particles, latent_node_size, sd
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        if self.world > 1:  # identical weights on every rank (reference: DataParallel replicate)
+            dist.broadcast(self.fpG.flat, 0, group=self.pg)
+            dist.broadcast(self.fpD.flat, 0, group=self.pg)
+
+    # -- helpers ---------------------------------------------------------------------------------
+    def _allreduce(self, fp: FlatParams) -> float:
+        """Sum gradients over ranks; returns the scale the optimizer applies (1/world = average)."""
+        if self.world == 1:
+            return 1.0
+        dist.all_reduce(fp.grad, op=dist.ReduceOp.SUM, group=self.pg)
+        return 1.0 / self.world
+
+    def named_grads(self, which):
+        return (self.fpG if which == "G" else self.fpD).named_grads()
+
+    def gen(self, batch_size, labels, noise=None):
+        if noise is None:
+            noise = get_gen_noise(batch_size, self.num_particles, self.latent, self.sd, labels.device)
+        return self.G(noise, labels)
+
+    # -- train.py:398-462 ------------------------------------------------------------------------
+    def train_D(self, data, labels, noise=None):
+        self.D.train()
+        self.fpD.zero_grad()
+        self.G.eval()
+        d_real = self.D(data, labels)
+        with torch.no_grad():
+            fake = self.gen(data.shape[0], labels, noise)
+        d_fake = self.D(fake, labels)
+        # least squares: real -> 1, fake -> 0 (train.py:357-358, 369-370, 378)
+        loss = ((d_real - 1.0) ** 2).mean() + (d_fake ** 2).mean()
+        loss.backward()
+        self.optD.step(self._allreduce(self.fpD))
+        return loss.detach()
+
+    # -- train.py:479-523 ------------------------------------------------------------------------
+    def train_G(self, labels, noise=None, batch_size=None):
+        self.G.train()
+        self.fpG.zero_grad()
+        fake = self.gen(batch_size or labels.shape[0], labels, noise)
+        for p in self.fpD.params:
+            p.requires_grad_(False)
+        try:
+            d_fake = self.D(fake, labels)  # D stays in train mode: its dropout is active (train.py:419,494)
+            loss = ((d_fake - 1.0) ** 2).mean()  # train.py:467,472
+            loss.backward()
+        finally:
+            for p in self.fpD.params:
+                p.requires_grad_(True)
+        self.optG.step(self._allreduce(self.fpG))
+        return loss.detach()
+
+    def step(self, data, labels):
+        """One critic + one generator update (train.py:841-878 with num_critic = num_gen = 1)."""
+        return self.train_D(data, labels), self.train_G(labels)
+
+
+def synthetic_jets(B, N, device="cuda", generator=None, all_real=False):
+    """SURVEY 8(d) synthetic batch: features U(-.5,.5) zeroed on padded rows, 4th channel mask-0.5;
+    labels n * fp32(1/N)."""
+    if all_real:
+        n = torch.full((B,), N, device=device)
+    else:
+        n = torch.randint(1, N + 1, (B,), device=device, generator=generator)
+    real = (torch.arange(N, device=device)[None, :] < n[:, None]).float().unsqueeze(2)
+    feats = (torch.rand(B, N, 3, device=device, generator=generator) - 0.5) * real
+    x = torch.cat((feats, real - 0.5), dim=2)
+    labels = (n.float() * torch.tensor(1.0 / N, dtype=torch.float32, device=device)).unsqueeze(1)
+    return x, labels, n
+
+
+@torch.no_grad()
+def gen_multi_batch(G, num_samples, batch_size, num_particles, labels=None, latent_node_size=32, sd=0.2,
+                    out_device="cpu", pin=True):
+    """Generates ``num_samples`` jets in batches into ONE pre-allocated output (train.py:226-282
+    without its O(n^2) ``torch.cat`` and without the duplicated last batch when
+    ``num_samples % batch_size == 0``)."""
+    G.eval()
+    dev = next(G.parameters()).device
+    out_feats = G.output_node_size + 1
+    out = torch.empty(num_samples, num_particles, out_feats, device=out_device,
+                      pin_memory=(pin and out_device == "cpu"))
+    for start in range(0, num_samples, batch_size):
+        n = min(batch_size, num_samples - start)
+        lab = None if labels is None else labels[start:start + n].to(dev, non_blocking=True)
+        noise = get_gen_noise(n, num_particles, latent_node_size, sd, dev)
+        out[start:start + n].copy_(G(noise, lab), non_blocking=True)
+    if dev.type == "cuda":
+        torch.cuda.current_stream().synchronize()
+    return out

@@ -1,0 +1,266 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle and the golden vectors minted
+from the unmodified reference.  precision 0 (fp32-class) is held to fp32 tolerances; precision 1
+(TF32 node GEMMs + bf16 tcgen05 edge network) to the stated fast-path tolerance.
+
+Tolerances (max abs error / max abs of the reference tensor):
+  precision 0: 1e-4 forward, 1e-3 gradients        (fp32 with a different summation order / atomics)
+  precision 1: 3e-2 forward, 8e-2 gradients        (bf16 operands, fp32 accumulate)
+Masks / ranks: bit-exact (torch.equal).
+"""
+import pytest
+import torch
+
+from oracle import gapt_oracle as go
+from oracle import mpgan_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+TOL = {0: (1e-4, 1e-3), 1: (3e-2, 8e-2)}
+
+
+def rel(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return float((a - b).abs().max()) / max(float(b.abs().max()), 1e-6)
+
+
+def close(a, b, tol, what=""):
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    r = rel(a, b)
+    assert r <= tol, f"{what}: rel err {r:.3e} > {tol:.1e}"
+
+
+@pytest.fixture(autouse=True)
+def _precision():
+    from mpgan_b200 import ops
+    ops.set_precision(0)
+    yield
+    ops.set_precision(1)
+
+
+def dev(t):
+    return t.cuda() if isinstance(t, torch.Tensor) else t
+
+
+def test_library_loaded():
+    from mpgan_b200 import _lib
+    assert _lib.lib().mpg_version() >= 100
+
+
+@pytest.mark.parametrize("prec", [0, 1])
+def test_linear_fwd_bwd(prec):
+    from mpgan_b200 import ops
+    ops.set_precision(prec)
+    g = torch.Generator().manual_seed(3)
+    for (M, K, N, act) in [(37, 6, 96, True), (450, 224, 256, True), (450, 256, 3, False), (16, 195, 256, True),
+                           (5, 32, 1, False), (300, 64, 192, False)]:
+        x = torch.randn(M, K, generator=g).requires_grad_(True)
+        w = (torch.randn(N, K, generator=g) / K ** 0.5).requires_grad_(True)
+        b = torch.randn(N, generator=g).requires_grad_(True)
+        dy = torch.randn(M, N, generator=g)
+        y = torch.nn.functional.linear(x, w, b)
+        if prec == 1:
+            act = False  # TF32 rounding flips leaky-relu signs of near-zero pre-activations: test the GEMMs alone
+        y = torch.nn.functional.leaky_relu(y, 0.2) if act else y
+        y.backward(dy)
+        xc, wc, bc = (t.detach().cuda().requires_grad_(True) for t in (x, w, b))
+        yc = ops.linear(xc, wc, bc, act, 0.2, 0.0)
+        yc.backward(dy.cuda())
+        ft, gt = (2e-5, 1e-4) if prec == 0 else (3e-3, 6e-3)
+        close(yc, y, ft, f"y {M,K,N}")
+        close(xc.grad, x.grad, gt, "dx")
+        close(wc.grad, w.grad, gt, "dw")
+        close(bc.grad, b.grad, gt, "db")
+
+
+def test_rank_mask_bit_exact(golden):
+    from mpgan_b200 import ops
+    for name, c in golden("rank_mask.pt").items():
+        N = c["x0"].shape[1]
+        x = torch.zeros(N, N, 32)
+        x[:, :, 0] = c["x0"]
+        m = ops.rank_mask(x.cuda(), c["labels"].cuda(), N)
+        assert torch.equal(m.cpu().squeeze(2).to(torch.uint8), c["mask"].squeeze(2)), name
+
+
+def test_mplayer_variants(golden):
+    from mpgan_b200 import MPLayer
+    for name, c in golden("mplayer_variants.pt").items():
+        sd = c["sd"]
+        F_in = c["x"].shape[2]
+        fe = [sd["fe.net.0.weight"].shape[0], sd["fe.net.1.weight"].shape[0], sd["fe.net.2.weight"].shape[0]]
+        fn = [sd["fn.net.0.weight"].shape[0], sd["fn.net.1.weight"].shape[0]]
+        layer = MPLayer(F_in, fe, fn, sd["fn.net.2.weight"].shape[0], **c["kw"]).cuda()
+        layer.load_state_dict(sd, strict=True)
+        x = c["x"].cuda().requires_grad_(True)
+        mask = dev(c["mask"])
+        out = layer(x, mask is not None, mask)
+        close(out, c["out"], 1e-4, name)
+        (out * c["w"].cuda()).sum().backward()
+        close(x.grad, c["dx"], 1e-3, name + " dx")
+        for k, g in c["grads"].items():
+            close(dict(layer.named_parameters())[k].grad, g, 1e-3, f"{name} {k}")
+
+
+@pytest.mark.parametrize("prec", [0, 1])
+def test_generator_golden(golden, prec):
+    from mpgan_b200 import ops, presets
+    ops.set_precision(prec)
+    sd = golden("mp_g_weights.pt")
+    cases = golden("gen_forward.pt")
+    for name, N in (("survey4", 30), ("b64", 30), ("n100", 100), ("n150", 150)):
+        c = cases[name]
+        G = presets.mp_generator(num_hits=N).cuda().eval()
+        G.load_state_dict(sd, strict=True)
+        with torch.no_grad():
+            out = G(c["noise"].cuda(), c["labels"].cuda())
+        assert torch.equal(out[..., 3].cpu(), c["out"][..., 3]), name  # mask channel bit-exact
+        close(out, c["out"], TOL[prec][0], name)
+
+
+@pytest.mark.parametrize("prec", [0, 1])
+def test_discriminator_fwd_bwd_golden(golden, prec):
+    from mpgan_b200 import ops, presets
+    ops.set_precision(prec)
+    cases = golden("disc_fwd_bwd.pt")
+    for name, N in (("n30", 30), ("n150", 150)):
+        c = cases[name]
+        D = presets.mp_discriminator(num_hits=N, disc_dropout=0.0).cuda().train()
+        D.load_state_dict(golden("mp_d_seed4_weights.pt"), strict=True)
+        x = c["x"].cuda().requires_grad_(True)
+        out = D(x, c["labels"].cuda())
+        close(out, c["out"], TOL[prec][0], name)
+        loss = ((out - 1) ** 2).mean()
+        loss.backward()
+        # the kernels do not differentiate w.r.t. the mask channel (only WGAN-GP needs it)
+        close(x.grad[..., :3], c["dx"][..., :3], TOL[prec][1], name + " dx")
+        for k, g in c["grads"].items():
+            close(dict(D.named_parameters())[k].grad, g, TOL[prec][1], f"{name} {k}")
+
+
+@pytest.mark.parametrize("prec", [0, 1])
+def test_g_through_d_golden(golden, prec):
+    from mpgan_b200 import ops, presets
+    ops.set_precision(prec)
+    c = golden("disc_fwd_bwd.pt")["g_through_d"]
+    G = presets.mp_generator().cuda().train()
+    G.load_state_dict(golden("mp_g_weights.pt"), strict=True)
+    D = presets.mp_discriminator(disc_dropout=0.0).cuda().train()
+    D.load_state_dict(golden("mp_d_seed4_weights.pt"), strict=True)
+    labels = c["labels"].cuda()
+    loss = ((D(G(c["noise"].cuda(), labels), labels) - 1) ** 2).mean()
+    close(loss, c["loss"], TOL[prec][0], "loss")
+    loss.backward()
+    for k, g in c["grads"].items():
+        close(dict(G.named_parameters())[k].grad, g, TOL[prec][1], k)
+
+
+def test_spectral_norm_golden(golden):
+    from mpgan_b200 import LinearNet
+    c = golden("spectral_norm.pt")
+    net = LinearNet([24, 16], input_size=10, output_size=4, final_linear=True, spectral_norm=True).cuda()
+    net.load_state_dict(c["sd0"], strict=True)
+    x = c["x"].cuda().requires_grad_(True)
+    out = net(x)
+    close(out, c["out"], 2e-5, "out")
+    (out * c["w"].cuda()).sum().backward()
+    close(x.grad, c["dx"], 2e-4, "dx")
+    params = dict(net.named_parameters())
+    for k, g in c["grads"].items():
+        close(params[k].grad, g, 2e-4, k)
+    for k, v in net.state_dict().items():  # u, v advanced by exactly one power iteration
+        close(v, c["sd1"][k], 2e-5, k)
+
+
+@pytest.mark.parametrize("prec", [0, 1])
+def test_gapt_golden(golden, prec):
+    from mpgan_b200 import ops, presets
+    ops.set_precision(prec)
+    ft, gt = (1e-4, 1e-3) if prec == 0 else (5e-3, 8e-2)
+    for name, c in golden("gapt.pt").items():
+        isab = name == "isab"
+        GG = presets.gapt_generator(use_isab=isab).cuda().train()
+        GD = presets.gapt_discriminator(use_isab=isab, disc_dropout=0.0).cuda().train()
+        GG.load_state_dict(c["sdG"], strict=True)
+        GD.load_state_dict(c["sdD"], strict=True)
+        noise = c["noise"].cuda().requires_grad_(True)
+        labels = c["labels"].cuda()
+        fake = GG(noise, labels)
+        assert torch.equal(fake[..., 3].cpu(), c["fake"][..., 3])
+        close(fake, c["fake"], ft, name + " fake")
+        dout = GD(fake, labels)
+        close(dout, c["dout"], ft, name + " dout")
+        ((dout - 1) ** 2).mean().backward()
+        close(noise.grad, c["dnoise"], gt, name + " dnoise")
+        pG = dict(GG.named_parameters())
+        for k, g in c["gradsG"].items():
+            close(pG[k].grad, g, gt, f"{name} G {k}")
+        GD.zero_grad()
+        x = c["x"].cuda().requires_grad_(True)
+        rout = GD(x, c["xlabels"].cuda())
+        close(rout, c["rout"], ft, name + " rout")
+        ((rout - 1) ** 2).mean().backward()
+        close(x.grad[..., :3], c["dx"][..., :3], gt, name + " dx")
+        pD = dict(GD.named_parameters())
+        for k, g in c["gradsD"].items():
+            close(pD[k].grad, g, gt, f"{name} D {k}")
+
+
+def test_dropout_statistics_and_determinism():
+    """Dropout cannot match torch's RNG stream; check keep-rate, 1/(1-p) scaling and that backward
+    regenerates the forward mask (grad is non-zero exactly where the output is)."""
+    from mpgan_b200 import ops
+    torch.manual_seed(0)
+    for p in (0.5, 0.3):
+        x = torch.ones(512, 64, device="cuda", requires_grad=True)
+        w = torch.eye(64, device="cuda").repeat(3, 1).requires_grad_(True)   # [192, 64]
+        b = torch.zeros(192, device="cuda", requires_grad=True)
+        y = ops.linear(x, w, b, True, 0.2, p)
+        keep = (y != 0).float().mean().item()
+        assert abs(keep - (1 - p)) < 0.01, keep
+        assert torch.allclose(y[y != 0], torch.full_like(y[y != 0], 1 / (1 - p)), rtol=1e-6)
+        y.sum().backward()
+        # dL/db[n] = scale * #kept rows in column n  -> equals column sums of y
+        assert torch.allclose(b.grad, y.sum(0), rtol=1e-5)
+    # edge network: D-style dropout in the fused kernel, fwd/bwd consistency via finite differences
+    from mpgan_b200 import MPLayer
+    torch.manual_seed(1)
+    layer = MPLayer(3, [16, 24, 32], [40, 40], 6, dropout_p=0.5).cuda().train()
+    x = (torch.randn(2, 7, 3, device="cuda") * 0.5).requires_grad_(True)
+    import mpgan_b200.ops as O
+    cnt = O._seed_counter
+    out = layer(x)
+    out.sum().backward()
+    g = x.grad.clone()
+    eps = 1e-3
+    xp = x.detach().clone()
+    xp[0, 2, 1] += eps
+    O._seed_counter = cnt  # replay the same dropout streams
+    outp = layer(xp)
+    fd = (outp.sum() - out.sum()).item() / eps
+    assert abs(fd - g[0, 2, 1].item()) < 5e-2 * max(1.0, abs(fd)), (fd, g[0, 2, 1].item())
+
+
+def test_train_step_golden(golden):
+    """One train_D + train_G (LS loss, RMSprop) against the reference's own train.py step."""
+    from mpgan_b200 import presets, train
+    c = golden("train_step.pt")
+    G = presets.mp_generator().cuda()
+    D = presets.mp_discriminator(disc_dropout=0.0).cuda()
+    G.load_state_dict(golden("mp_g_weights.pt"), strict=True)
+    D.load_state_dict(golden("mp_d_seed4_weights.pt"), strict=True)
+    tr = train.GANTrainer(G, D, lr_gen=c["lr_g"], lr_disc=c["lr_d"], num_particles=30)
+    labels = c["labels"].cuda()
+    ld = tr.train_D(c["data"].cuda(), labels, noise=c["noise_d"].cuda())
+    gradsD = tr.named_grads("D")
+    lg = tr.train_G(labels, noise=c["noise_g"].cuda())
+    gradsG = tr.named_grads("G")
+    assert abs(float(ld) - c["loss_d"]) < 1e-5 and abs(float(lg) - c["loss_g"]) < 1e-5
+    for k, g in c["gradsD"].items():
+        close(gradsD[k], g, 1e-3, "D " + k)
+    for k, g in c["gradsG"].items():
+        close(gradsG[k], g, 3e-3, "G " + k)  # four MP layers deep, atomically-ordered fp32 sums
+    sdD = D.state_dict()
+    for k, v in c["sdD_after"].items():
+        g = c["gradsD"][k]
+        ok = g.abs() > 1e-3 * g.abs().max()
+        assert float((sdD[k].cpu() - v)[ok].abs().max()) < 2e-6, k
