@@ -1,0 +1,340 @@
+"""Benchmark of the MPGAN hot path (BASELINE.json metric: jets/s per G+D train step).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+Workloads (config.workload):
+  train_n30_b256   MPGAN G+D training step, 30-particle jets, batch 256 per GPU  (BASELINE configs[1];
+                   the default: the configuration the metric is quoted on)
+  train_n150_b32   same at 150 particles, batch 32 per GPU (configs[2], reference default batch)
+  gen_n30_b1024    generator inference from the mp_g weights, batch 1024 (configs[0])
+
+A "step" is one train_D + train_G on one synthetic batch (train.py:841-878, num_critic=num_gen=1,
+LS loss, RMSprop, D dropout 0.5).  `value` times K steps on the device with the batch resident in
+HBM (per-step CUDA events, L2 flushed between steps, max over ranks); `e2e` times the same K steps
+through the public API starting from pinned HOST buffers, host->device copies and the device->host
+read of the two losses inside the timed region.  `--impl reference` times the CPU oracle port of the
+same step (oracle/mpgan_oracle.gd_step) on the host cores, on a bounded sample of the batch.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "train_n30_b256": dict(kind="train", N=30, B=256),
+    "train_n150_b32": dict(kind="train", N=150, B=32),
+    "train_n150_b256": dict(kind="train", N=150, B=256),
+    "gen_n30_b1024": dict(kind="gen", N=30, B=1024),
+    "gen_n150_b1024": dict(kind="gen", N=150, B=1024),
+}
+H = (96, 160, 192)
+FN = (256, 256)
+
+
+def layer_flops(N, F, Fout):
+    """Algorithmic forward FLOPs of one MPLayer per jet (first fe layer factorised)."""
+    return 4.0 * N * F * H[0] + 2.0 * N * N * (H[0] * H[1] + H[1] * H[2]) + \
+        2.0 * N * ((H[2] + F) * FN[0] + FN[0] * FN[1] + FN[1] * Fout)
+
+
+def net_flops(N):
+    fg = layer_flops(N, 32, 32) + layer_flops(N, 32, 3)
+    fd = layer_flops(N, 3, 32) + layer_flops(N, 32, 32) + 2.0 * 32
+    return fg, fd
+
+
+def step_flops(N):
+    """Minimal G+D step: D 3 fwd + 2 full bwd + 1 dX bwd, G 2 fwd + 1 bwd = 8 F_D + 4 F_G."""
+    fg, fd = net_flops(N)
+    return 8.0 * fd + 4.0 * fg
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(tflops=d["bf16_tflops_sustained"], tflops_burst=d["bf16_tflops"], hbm=d["hbm_gbs"], src="measured")
+    return dict(tflops=1400.0, tflops_burst=1590.0, hbm=6650.0, src="fallback")
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU oracle arm
+# ----------------------------------------------------------------------------------------------------
+def cpu_step_time(N, B_sample, reps, warm=1, kind="train"):
+    """Times the CPU oracle port (oracle/mpgan_oracle.py) on B_sample jets; returns seconds/step."""
+    import torch
+    from oracle import mpgan_oracle as mo
+    torch.set_num_threads(os.cpu_count() or 1)
+    gold = os.path.join(ROOT, "tests", "golden")
+    sdG = torch.load(os.path.join(gold, "mp_g_weights.pt"), map_location="cpu")
+    sdD = torch.load(os.path.join(gold, "mp_d_seed4_weights.pt"), map_location="cpu")
+    cfgG = mo.NetCfg(num_particles=N, final_activation="tanh")
+    cfgD = mo.NetCfg(num_particles=N, final_activation="sigmoid", dropout_p=0.5,
+                     layers=[mo.EdgeCfg(all_ef=False), mo.EdgeCfg()])
+    g = torch.Generator().manual_seed(4)
+    data, labels, _ = mo.synthetic_jets(B_sample, N, g)
+    times = []
+    if kind == "gen":
+        for i in range(warm + reps):
+            noise = torch.randn(B_sample, N, 32, generator=g) * 0.2
+            t0 = time.perf_counter()
+            with torch.no_grad():
+                mo.generator(sdG, noise, labels, cfgG)
+            times.append(time.perf_counter() - t0)
+        return min(times[warm:]), torch.get_num_threads()
+    pG = {k: v.clone().requires_grad_(True) for k, v in sdG.items()}
+    pD = {k: v.clone().requires_grad_(True) for k, v in sdD.items()}
+    stD, stG = {}, {}
+    for i in range(warm + reps):
+        nd = torch.randn(B_sample, N, 32, generator=g) * 0.2
+        ng = torch.randn(B_sample, N, 32, generator=g) * 0.2
+        t0 = time.perf_counter()
+        mo.gd_step(pG, pD, cfgG, cfgD, data, labels, nd, ng, stateD=stD, stateG=stG)
+        times.append(time.perf_counter() - t0)
+    return sum(times[warm:]) / reps, torch.get_num_threads()
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    N, kind = wl["N"], wl["kind"]
+    # bounded sample: sized so one step is ~1-2 s on a few cores
+    B_sample = {30: 32, 150: 2}.get(N, 4) if kind == "train" else {30: 256, 150: 16}.get(N, 16)
+    reps = max(1, min(args.steps, 8))
+    sec, cores = cpu_step_time(N, B_sample, reps, warm=min(args.warmup, 1), kind=kind)
+    val = B_sample / sec
+    line = {
+        "impl": "reference", "metric": metric_name(wl), "value": val, "unit": "jets/s", "n_gpus": args.gpus,
+        "steps": reps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "sample_jets_per_step": B_sample, "particles": N},
+        "cpu_baseline": {"value": val, "unit": "jets/s", "cores": cores, "kind": "port",
+                         "sample": f"{B_sample} jets/step x {reps} steps of the same workload (oracle port of the "
+                                   "reference fp32 PyTorch path)"},
+        "e2e": {"value": val, "unit": "jets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def metric_name(wl):
+    return "jets/sec per G+D train step" if wl["kind"] == "train" else "generated jets/sec"
+
+
+# ----------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+    from mpgan_b200 import _lib, ops, presets, train
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    N, B, kind = wl["N"], wl["B"], wl["kind"]
+    L = _lib.lib()
+    ops.set_precision(1)
+    torch.manual_seed(4 + rank)
+
+    G = presets.mp_generator(num_hits=N).to(dev)
+    D = presets.mp_discriminator(num_hits=N).to(dev)
+    torch.manual_seed(4)  # identical initial weights on every rank
+    gold = os.path.join(ROOT, "tests", "golden")
+    G.load_state_dict(torch.load(os.path.join(gold, "mp_g_weights.pt"), map_location=dev))
+    D.load_state_dict(torch.load(os.path.join(gold, "mp_d_seed4_weights.pt"), map_location=dev))
+    gen = torch.Generator(device=dev).manual_seed(4 + rank)
+    data, labels, _ = train.synthetic_jets(B, N, dev, gen)
+    flush_buf = torch.empty(256 * 1024 * 1024 // 4, device=dev)  # > 126 MB L2
+
+    if kind == "train":
+        tr = train.GANTrainer(G, D, lr_gen=1e-5, lr_disc=3e-5, num_particles=N)
+
+        def one_step(d, l):
+            return tr.step(d, l)
+    else:
+        G.eval()
+
+        def one_step(d, l):
+            with torch.no_grad():
+                return G(train.get_gen_noise(B, N, 32, 0.2, dev), l)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        one_step(data, labels)
+    barrier()
+
+    # ---- device-resident timed region ---------------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    prof = ops.profile_start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = L.mpg_launch_count()
+    barrier()
+    for i in range(args.steps):
+        flush_buf.zero_()  # evict L2 between timed steps (untimed)
+        ev[i][0].record()
+        one_step(data, labels)
+        ev[i][1].record()
+    barrier()
+    launches = L.mpg_launch_count() - launches0
+    prof = ops.profile_stop()
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = torch.tensor([sum(step_ms)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms)
+    value = B * world * args.steps / (total_ms * 1e-3)
+
+    # ---- end-to-end through the public API from pinned host buffers -------------------------------
+    h_data, h_labels = data.cpu().pin_memory(), labels.cpu().pin_memory()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    sink = 0.0
+    for i in range(args.steps):
+        d = h_data.to(dev, non_blocking=True)
+        l = h_labels.to(dev, non_blocking=True)
+        out = one_step(d, l)
+        if kind == "train":
+            sink += float(out[0]) + float(out[1])   # D2H read of both losses (train.py:390-393,523)
+        else:
+            sink += float(out[0, 0, 0].cpu())
+    e1.record()
+    barrier()
+    e2e_ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_val = B * world * args.steps / (float(e2e_ms) * 1e-3)
+    h2d = h_data.numel() * 4 + h_labels.numel() * 4
+    d2h = 8 if kind == "train" else 4
+
+    if rank == 0:
+        pk = peaks()
+        # dominant kernel class by device time
+        by = {}
+        for name, a, b, fl in prof:
+            t = by.setdefault(name, [0.0, 0, 0.0])
+            t[0] += a.elapsed_time(b)
+            t[1] += 1
+            t[2] += fl
+        dom = max(by, key=lambda k: by[k][0]) if by else None
+        roof = None
+        if dom:
+            ms, cnt, fl = by[dom]
+            ach = fl / (ms * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s",
+                    "frac": ach / pk["tflops"], "traffic": None, "peak_source": pk["src"] + " bf16 sustained",
+                    "launches": cnt, "avg_launch_ms": ms / cnt,
+                    "share_of_step": ms / sum(step_ms),
+                    "all": {k: {"ms_total": v[0], "launches": v[1], "tflops": v[2] / (v[0] * 1e-3) / 1e12}
+                            for k, v in by.items()}}
+        alg = step_flops(N) if kind == "train" else net_flops(N)[0]
+        # CPU baseline: bounded sample of the same workload on the host cores
+        try:
+            bs = {30: 32, 150: 2}.get(N, 4) if kind == "train" else {30: 256, 150: 16}.get(N, 16)
+            sec, cores = cpu_step_time(N, bs, reps=2, warm=1, kind=kind)
+            cpu = {"value": bs / sec, "unit": "jets/s", "cores": cores, "kind": "port",
+                   "sample": f"{bs} jets/step x 2 steps (oracle port of the reference fp32 PyTorch path)"}
+        except Exception as e:  # pragma: no cover
+            cpu = {"value": None, "unit": "jets/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+        line = {
+            "metric": metric_name(wl), "value": value, "unit": "jets/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": args.workload, "particles": N, "batch_per_gpu": B, "global_batch": B * world,
+                       "l2": "flushed between timed steps (256 MiB write)", "precision": "bf16 tcgen05 edge network, "
+                       "TF32 node GEMMs, fp32 accumulate", "parallelism": f"dp{world}"},
+            "e2e": {"value": e2e_val, "unit": "jets/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "roofline": roof,
+            "step_roofline": {"algorithmic_gflop_per_jet": alg / 1e9,
+                              "achieved_tflops": value / world * alg / 1e12,
+                              "frac_of_peak": value / world * alg / 1e12 / pk["tflops"]},
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="train_n30_b256", choices=sorted(WORKLOADS))
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -43,6 +43,8 @@ int mpg_version(void);
 const char* mpg_last_error(void);
 /* compiled feature flags: bit0 = tcgen05 edge forward, bit1 = tcgen05 edge backward, bit2 = GAPT */
 int mpg_features(void);
+/* number of kernel launches this library has issued so far in this process */
+unsigned long long mpg_launch_count(void);
 
 /* ---- LinearNet layer (mpgan/model.py:77-83): y = dropout(act(x W^T + b)) -------------------------- */
 int mpg_linear_fwd(const float* x, int ldx, const float* w, const float* b, float* y, int M, int K, int N,

@@ -10,6 +10,7 @@
 
 namespace mpg {
 static thread_local char g_err[512] = "";
+unsigned long long g_launch_count = 0;
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -109,6 +110,7 @@ extern "C" {
 int mpg_version(void) { return 100; }
 const char* mpg_last_error(void) { return g_err; }
 int mpg_features(void) { return edge_tc_features() | 4; }
+unsigned long long mpg_launch_count(void) { return g_launch_count; }
 
 int mpg_linear_fwd(const float* x, int ldx, const float* w, const float* b, float* y, int M, int K, int N, int act,
                    float alpha, float p_drop, uint64_t seed, const uint64_t* seed_dev, uint32_t rng_stream, int precision,
@@ -198,6 +200,7 @@ int mpg_edge_bwd(const float* x, int ldx, const float* mask, const float* w0, co
   if (a.n_ef) MPG_CUDA(cudaMemsetAsync(w.dxef, 0, BN * F * sizeof(float), s));
   const bool tc_bwd = use_tc && (edge_tc_features() & 2);
   if (tc_bwd) {
+    MPG_CUDA(cudaMemsetAsync(w.dP, 0, BN * H0 * sizeof(float), s));
     if (launch_edge_tc_bwd(a, w.tc, s)) return 1;
   } else {
     if (use_tc) {  // forward ran on tensor cores, backward kernel not built: generic needs W^T copies

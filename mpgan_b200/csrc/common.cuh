@@ -25,7 +25,13 @@ void set_error(const char* fmt, ...);
       return 2;                                                                     \
     }                                                                               \
   } while (0)
-#define MPG_LAUNCH_CHECK() MPG_CUDA(cudaGetLastError())
+// every kernel launch goes through here: the counter backs bench.py's "gpu_launches" claim
+extern unsigned long long g_launch_count;
+#define MPG_LAUNCH_CHECK()          \
+  do {                              \
+    ++::mpg::g_launch_count;        \
+    MPG_CUDA(cudaGetLastError());   \
+  } while (0)
 
 // ---- Philox4x32-10 counter-based RNG -----------------------------------------------------------
 // Dropout masks must be regenerated bit-identically in forward, recompute and backward, so they

@@ -417,9 +417,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_fwd_kernel(TcArgs t) {
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
 }
 
+#include "edge_tc_bwd.cuh"
+
 }  // namespace
 
-int edge_tc_features() { return 1; }
+int edge_tc_features() { return 3; }
 
 bool edge_tc_supported(const EdgeArgs& a) {
   return a.H0 == K0 && a.H1 == N1 && a.H2 == N2 && a.n_ef == 0 && a.N >= 2 &&
@@ -461,9 +463,41 @@ int launch_edge_tc_fwd(const EdgeArgs& a, void* ws, cudaStream_t stream) {
   return 0;
 }
 
+template <int MODE, bool DROP>
+static int launch_bwd_one(const TcArgs& t, int grid, uint32_t smem, cudaStream_t stream) {
+  MPG_CUDA(cudaFuncSetAttribute(edge_tc_bwd_kernel<MODE, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  edge_tc_bwd_kernel<MODE, DROP><<<grid, NTHREADS, smem, stream>>>(t);
+  MPG_LAUNCH_CHECK();
+  return 0;
+}
+
+// dP and dQ must be zeroed by the caller (both are accumulated with atomics here)
 int launch_edge_tc_bwd(const EdgeArgs& a, void* ws, cudaStream_t stream) {
-  MPG_CHECK(false, "tcgen05 edge backward kernel not built");
-  return 1;
+  MPG_CHECK(edge_tc_supported(a), "edge_tc: unsupported configuration");
+  uint8_t* img = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  TcArgs t;
+  t.a = a;
+  t.w1img = img;
+  t.w2img = img + W1_BYTES;
+  const float s = a.drop.p > 0.f ? 2.f : 1.f;
+  weight_image_kernel<<<cdiv(N1 * 128, 256), 256, 0, stream>>>(a.W1, a.b1, N1, K0, 128, s, img);
+  weight_image_kernel<<<cdiv(N2 * 192, 256), 256, 0, stream>>>(a.W2, a.b2, N2, N1, 192, s, img + W1_BYTES);
+  MPG_LAUNCH_CHECK();
+  const long long BN = (long long)a.B * a.N;
+  t.num_tiles = (int)((BN + TILE - 1) / TILE);
+  t.total_steps = (long long)t.num_tiles * a.N;
+  int dev = 0, sms = 148;
+  MPG_CUDA(cudaGetDevice(&dev));
+  MPG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int grid = (int)(t.total_steps < sms ? t.total_steps : sms);
+  if (a.drop.p > 0.f) {
+    if (launch_bwd_one<BWD_CHAIN, true>(t, grid, BW_SMEM_CHAIN, stream)) return 1;
+    if (launch_bwd_one<BWD_DW2, true>(t, grid, BW_SMEM_DW2, stream)) return 1;
+  } else {
+    if (launch_bwd_one<BWD_CHAIN, false>(t, grid, BW_SMEM_CHAIN, stream)) return 1;
+    if (launch_bwd_one<BWD_DW2, false>(t, grid, BW_SMEM_DW2, stream)) return 1;
+  }
+  return 0;
 }
 
 }  // namespace mpg

@@ -1,0 +1,437 @@
+// tcgen05 backward of the edge network (included by edge_tc.cu inside its anonymous namespace).
+//
+// The backward recomputes H0/H1/D2 per (tile, sender) step exactly as the forward does and never
+// stores an N^2 x hidden tensor.  All fp32 weight-gradient accumulators cannot be TMEM-resident at
+// once (dW2: 2x160 columns, dW1^T: 160 columns, plus >= 192 streaming columns > 512), so the work is
+// split into two kernels that share the recompute code:
+//
+//   CHAIN  G2 = dAgg*m*f'(D2) -> dH1 = G2 W2 -> G1 = dH1 f'(D1) -> dH0 = G1 W1 -> G0 = dH0 f'(pre0)
+//          dP[r] += G0 (registers), dQ[jet,s] += G0 (red.global), dW1^T += H0^T G1 (TMEM accumulator;
+//          the constant-1 bias columns of the H0 tile make row 96 of it db1).
+//   DW2    recompute -> G2, dW2 += G2^T H1 (two M=128 TMEM accumulators), db2 = column sums of G2.
+//
+// The transposed products reuse the SAME swizzled shared-memory tiles through MN-major UMMA
+// descriptors (a K-major [rows x cols] SW128 tile read as MN-major is its transpose), and the
+// weight images serve both W (K-major B operand) and W^T (MN-major B operand).
+//
+// Scale convention with dropout p = 0.5 (s = 2): tiles hold activations / pre-activation gradients
+// divided by s and the weight images hold s*W, so every MMA sees the true product; the factors are
+// restored at the flush (dW: s^2, db: s) and in G0 (s).
+
+enum { BWD_CHAIN = 0, BWD_DW2 = 1 };
+
+// MN-major view of a SW128 tile: 64-element blocks along M/N are lbo_bytes apart, 8-row groups along
+// K are 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | (64ull << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+__host__ __device__ constexpr uint32_t umma_idesc_t(int N, int a_mn, int b_mn) {
+  return umma_idesc(N) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16);
+}
+
+constexpr uint32_t BW_OFF_A0_CHAIN = OFF_W2 + W2_BYTES;            // 114688: H0 tile (32 KB)
+constexpr uint32_t BW_OFF_A1_CHAIN = BW_OFF_A0_CHAIN + H0_BYTES;   // 147456: H1 / G2 / G1 tile (48 KB)
+constexpr uint32_t BW_OFF_G2_DW2 = OFF_W2 + W2_BYTES;              // 114688: H0 then G2 tile (48 KB)
+constexpr uint32_t BW_OFF_A1_DW2 = BW_OFF_G2_DW2 + H1_BYTES;       // 163840: H1 tile (48 KB)
+constexpr uint32_t BW_OFF_BAR_CHAIN = BW_OFF_A1_CHAIN + H1_BYTES;  // 196608
+constexpr uint32_t BW_OFF_BAR_DW2 = BW_OFF_A1_DW2 + H1_BYTES;      // 212992
+constexpr uint32_t BW_SMEM_CHAIN = BW_OFF_BAR_CHAIN + 128 + 1024;
+constexpr uint32_t BW_SMEM_DW2 = BW_OFF_BAR_DW2 + 128 + 1024;
+constexpr uint32_t RS_COL = 0, RW1_COL = 256, RW2A_COL = 192, RW2B_COL = 352;
+
+__device__ __forceinline__ void st_chunk(uint32_t addr, const float (&v)[16], int o) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(pack_bf16(v[o], v[o + 1])),
+               "r"(pack_bf16(v[o + 2], v[o + 3])), "r"(pack_bf16(v[o + 4], v[o + 5])),
+               "r"(pack_bf16(v[o + 6], v[o + 7])));
+}
+__device__ __forceinline__ uint32_t word_of(const u4& b, int w) {
+  return w == 0 ? b.x : (w == 1 ? b.y : (w == 2 ? b.z : b.w));
+}
+
+template <int MODE, bool DROP>
+__global__ void __launch_bounds__(NTHREADS, 1) edge_tc_bwd_kernel(TcArgs t) {
+  extern __shared__ uint8_t smem_raw[];
+  const EdgeArgs& a = t.a;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sW1 = base + OFF_W1, sW2 = base + OFF_W2;
+  const uint32_t sA0 = base + (MODE == BWD_CHAIN ? BW_OFF_A0_CHAIN : BW_OFF_G2_DW2);
+  const uint32_t sA1 = base + (MODE == BWD_CHAIN ? BW_OFF_A1_CHAIN : BW_OFF_A1_DW2);
+  const uint32_t sG2 = MODE == BWD_CHAIN ? sA1 : base + BW_OFF_G2_DW2;   // G2 tile (CHAIN: over H1; DW2: over H0)
+  const uint32_t off_bar = MODE == BWD_CHAIN ? BW_OFF_BAR_CHAIN : BW_OFF_BAR_DW2;
+  const uint32_t bar_w = base + off_bar, bar_rdy = bar_w + 8, bar_done = bar_w + 16;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + off_bar + 64);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  DropCfg drop = a.drop;
+  if (DROP) resolve_seed(drop);
+  const float sdrop = DROP ? 2.f : 1.f;
+
+  const long long g0 = t.total_steps * blockIdx.x / gridDim.x;
+  const long long g1 = t.total_steps * (blockIdx.x + 1) / gridDim.x;
+  const int nsteps = (int)(g1 - g0);
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(bar_rdy, NTHREADS);
+    mbar_init(bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const bool issuer = threadIdx.x == 0;
+  if (issuer && nsteps > 0) {
+    mbar_expect_tx(bar_w, W1_BYTES + W2_BYTES);
+    bulk_g2s(sW1, t.w1img, W1_BYTES, bar_w);
+    bulk_g2s(sW2, t.w2img, W2_BYTES, bar_w);
+  }
+
+  const int wg = warp >> 2;
+  const int row = (warp & 3) * 32 + lane;
+  const uint32_t tlane = (uint32_t)((warp & 3) * 32) << 16;
+  const int BN = a.B * a.N;
+  uint32_t prdy = 0, pdone = 0;
+
+  // publish this thread's smem writes + TMEM reads, let thread 0 issue a batch of MMAs, wait for them
+  auto sync_issue = [&](auto&& issue_fn) {
+    fence_async_smem();
+    tc_fence_before();
+    mbar_arrive(bar_rdy);
+    if (issuer) {
+      mbar_wait(bar_rdy, prdy);
+      tc_fence_after();
+      issue_fn();
+      umma_commit(bar_done);
+    }
+    prdy ^= 1;
+    mbar_wait(bar_done, pdone);
+    pdone ^= 1;
+    tc_fence_after();
+  };
+
+  // constant 1.0 bias columns (H0 cols 96,97 / H1 cols 160,161), zeros up to the end of the K step
+  if (nsteps > 0) {
+    const uint32_t one2 = 0x3F803F80u;
+    if (MODE == BWD_CHAIN) {
+      if (wg == 0) {
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%2,%2};" ::"r"(sA0 + swz_chunk(row, 96, A_BLK)), "r"(one2), "r"(0u));
+        asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(sA0 + swz_chunk(row, 104, A_BLK)), "r"(0u));
+        // columns 112..127 of the H0 tile are read (as unused rows) by the transposed dW1 product
+        asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(sA0 + swz_chunk(row, 112, A_BLK)), "r"(0u));
+        asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(sA0 + swz_chunk(row, 120, A_BLK)), "r"(0u));
+      }
+    }
+  }
+
+  float Preg[48];
+  uint32_t dAggp[48];           // bf16x2: dAgg[r][wg*96 + 2i], [.. + 2i + 1]
+  float dPacc[MODE == BWD_CHAIN ? 48 : 1];
+  float db2acc0 = 0.f, db2acc1 = 0.f;
+  int cur_tile = -1, r = 0, jet = 0;
+  bool valid = false;
+  bool first_mma = true;
+
+  auto flush_dP = [&]() {
+    if constexpr (MODE == BWD_CHAIN) if (cur_tile >= 0 && valid) {
+      float* dst = a.dP + (size_t)r * K0 + wg * 48;
+#pragma unroll
+      for (int c = 0; c < 48; ++c) atomicAdd(dst + c, dPacc[c]);
+    }
+  };
+  auto load_tile = [&](int tile) {
+    flush_dP();
+    cur_tile = tile;
+    r = tile * TILE + row;
+    valid = r < BN;
+    const int rc = valid ? r : BN - 1;
+    jet = rc / a.N;
+    const float4* p = reinterpret_cast<const float4*>(a.P + (size_t)rc * K0 + wg * 48);
+#pragma unroll
+    for (int c = 0; c < 12; ++c) {
+      const float4 v = __ldg(p + c);
+      Preg[4 * c] = v.x; Preg[4 * c + 1] = v.y; Preg[4 * c + 2] = v.z; Preg[4 * c + 3] = v.w;
+    }
+    const float4* dg = reinterpret_cast<const float4*>(a.dagg + (size_t)rc * N2 + wg * 96);
+#pragma unroll
+    for (int c = 0; c < 24; ++c) {
+      const float4 v = __ldg(dg + c);
+      dAggp[2 * c] = pack_bf16(v.x, v.y);
+      dAggp[2 * c + 1] = pack_bf16(v.z, v.w);
+    }
+    if constexpr (MODE == BWD_CHAIN) {
+#pragma unroll
+      for (int c = 0; c < 48; ++c) dPacc[c] = 0.f;
+    }
+  };
+
+  if (issuer && nsteps > 0) mbar_wait(bar_w, 0);
+
+  for (int it = 0; it < nsteps; ++it) {
+    const long long g = g0 + it;
+    const int tile = (int)(g / a.N), s = (int)(g % a.N);
+    if (tile != cur_tile) load_tile(tile);
+    const uint64_t pair = (uint64_t)(valid ? r : 0) * a.N + s;
+    const float mfac = valid ? (a.mask ? a.mask[(size_t)jet * a.N + s] : 1.f) * a.out_scale : 0.f;
+
+    // ---- H0 tile; remember sign / keep bits of the 48 columns this thread owns ------------------------
+    uint32_t pos0[2] = {0, 0}, keep0[2] = {~0u, ~0u};
+    {
+      const float4* q = reinterpret_cast<const float4*>(a.Q + ((size_t)jet * a.N + s) * K0 + wg * 48);
+      u4 bits{0, 0, 0, 0};
+      if (DROP) bits = drop_bits128(drop.seed, 0, pair, 0);
+#pragma unroll
+      for (int c8 = 0; c8 < 6; ++c8) {
+        const float4 q0 = __ldg(q + 2 * c8), q1 = __ldg(q + 2 * c8 + 1);
+        float v[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int le = c8 * 8 + e;               // 0..47
+          float x = v[e] + Preg[le];
+          if (x > 0.f) pos0[le >> 5] |= 1u << (le & 31);
+          x = fmaxf(x, a.alpha * x);
+          if (DROP) {
+            const int col = wg * 48 + le;
+            if (!((word_of(bits, col >> 5) >> (col & 31)) & 1u)) {
+              x = 0.f;
+              keep0[le >> 5] &= ~(1u << (le & 31));
+            }
+          }
+          v[e] = x;
+        }
+        st_chunk(sA0 + swz_chunk(row, wg * 48 + c8 * 8, A_BLK), v, 0);
+      }
+      if (MODE == BWD_DW2 && wg == 0) {   // DW2 builds H0 inside the G2 region: bias columns every step
+        const uint32_t one2 = 0x3F803F80u;
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%2,%2};" ::"r"(sA0 + swz_chunk(row, 96, A_BLK)), "r"(one2), "r"(0u));
+        asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(sA0 + swz_chunk(row, 104, A_BLK)), "r"(0u));
+      }
+    }
+    sync_issue([&]() {   // D1 = H0 * W1^T
+#pragma unroll
+      for (int ks = 0; ks < KSTEPS1; ++ks) {
+        const uint32_t blk = ks >> 2, j = ks & 3;
+        umma_bf16(tmem + RS_COL, umma_desc(sA0 + blk * A_BLK + j * 32), umma_desc(sW1 + blk * W1_BLK + j * 32),
+                  umma_idesc(N1), ks > 0);
+      }
+    });
+    // ---- e1: H1 tile, sign / keep bits of this thread's 80 columns ------------------------------------
+    uint32_t pos1[3] = {0, 0, 0}, keep1[3] = {~0u, ~0u, ~0u};
+    {
+      u4 b0{0, 0, 0, 0}, b1{0, 0, 0, 0};
+      if (DROP) {
+        b0 = drop_bits128(drop.seed, 1, pair, 0);
+        if (wg == 1) b1 = drop_bits128(drop.seed, 1, pair, 1);
+      }
+#pragma unroll
+      for (int c16 = 0; c16 < 5; ++c16) {
+        const int col0 = wg * 80 + c16 * 16;
+        float v[16];
+        tmem_ld16(tmem + tlane + RS_COL + col0, v);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int le = c16 * 16 + e;             // 0..79
+          float x = v[e];
+          if (x > 0.f) pos1[le >> 5] |= 1u << (le & 31);
+          x = fmaxf(x, a.alpha * x);
+          if (DROP) {
+            const int col = col0 + e;
+            const u4& bb = (col >> 7) ? b1 : b0;
+            if (!((word_of(bb, (col >> 5) & 3) >> (col & 31)) & 1u)) {
+              x = 0.f;
+              keep1[le >> 5] &= ~(1u << (le & 31));
+            }
+          }
+          v[e] = x;
+        }
+        st_chunk(sA1 + swz_chunk(row, col0, A_BLK), v, 0);
+        st_chunk(sA1 + swz_chunk(row, col0 + 8, A_BLK), v, 8);
+      }
+      if (MODE == BWD_DW2 && it == 0) {   // constant bias columns of the H1 tile (never overwritten in DW2)
+        if (wg == 1) {
+          const uint32_t one2 = 0x3F803F80u;
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%2,%2};" ::"r"(sA1 + swz_chunk(row, 160, A_BLK)), "r"(one2), "r"(0u));
+          asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(sA1 + swz_chunk(row, 168, A_BLK)), "r"(0u));
+        }
+      }
+      if (MODE == BWD_CHAIN) {            // CHAIN reuses the H1 region for G2/G1: rewrite them every step
+        if (wg == 1) {
+          const uint32_t one2 = 0x3F803F80u;
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%2,%2};" ::"r"(sA1 + swz_chunk(row, 160, A_BLK)), "r"(one2), "r"(0u));
+          asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(sA1 + swz_chunk(row, 168, A_BLK)), "r"(0u));
+        }
+      }
+    }
+    sync_issue([&]() {   // D2 = H1 * W2^T
+#pragma unroll
+      for (int ks = 0; ks < KSTEPS2; ++ks) {
+        const uint32_t blk = ks >> 2, j = ks & 3;
+        umma_bf16(tmem + RS_COL, umma_desc(sA1 + blk * A_BLK + j * 32), umma_desc(sW2 + blk * W2_BLK + j * 32),
+                  umma_idesc(N2), ks > 0);
+      }
+    });
+    // ---- e2': G2 = dAgg * m * f'(D2) * keep2  (divided by s, see header) -> bf16 tile --------------------
+    {
+      u4 b0{0, 0, 0, 0}, b1{0, 0, 0, 0};
+      if (DROP) {
+        b0 = drop_bits128(drop.seed, 2, pair, 0);
+        if (wg == 1) b1 = drop_bits128(drop.seed, 2, pair, 1);
+      }
+#pragma unroll
+      for (int c16 = 0; c16 < 6; ++c16) {
+        const int col0 = wg * 96 + c16 * 16;
+        float v[16];
+        tmem_ld16(tmem + tlane + RS_COL + col0, v);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int le = c16 * 16 + e;             // 0..95
+          const uint32_t pk = dAggp[le >> 1];
+          const float dg = __uint_as_float((le & 1) ? (pk & 0xFFFF0000u) : (pk << 16));
+          float gval = dg * mfac * (v[e] > 0.f ? 1.f : a.alpha);
+          if (DROP) {
+            const int col = col0 + e;
+            const u4& bb = (col >> 7) ? b1 : b0;
+            if (!((word_of(bb, (col >> 5) & 3) >> (col & 31)) & 1u)) gval = 0.f;
+          }
+          v[e] = gval;
+        }
+        st_chunk(sG2 + swz_chunk(row, col0, A_BLK), v, 0);
+        st_chunk(sG2 + swz_chunk(row, col0 + 8, A_BLK), v, 8);
+      }
+    }
+
+    if constexpr (MODE == BWD_DW2) {
+      // db2 partial column sums straight from the bf16 G2 tile (thread -> 2 columns x 64 rows)
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (threadIdx.x < 192) {
+        const int cp = threadIdx.x % 96, rh = threadIdx.x / 96;
+        const uint32_t col = 2 * cp;
+#pragma unroll 8
+        for (int rr = 0; rr < 64; ++rr) {
+          const uint32_t rw = rh * 64 + rr;
+          uint32_t w;
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(sG2 + swz_chunk(rw, col, A_BLK) + (col & 7) * 2));
+          db2acc0 += __uint_as_float(w << 16);
+          db2acc1 += __uint_as_float(w & 0xFFFF0000u);
+        }
+      }
+      const bool acc_flag = !first_mma;
+      sync_issue([&]() {   // dW2[n2][n1] += G2^T H1 : two M=128 blocks over G2 columns, N = 160, K = 128 rows
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+          for (int ks = 0; ks < TILE / 16; ++ks)
+            umma_bf16(tmem + (mb == 0 ? RW2A_COL : RW2B_COL), umma_desc_mn(sG2 + mb * 2 * A_BLK + ks * 2048, A_BLK),
+                      umma_desc_mn(sA1 + ks * 2048, A_BLK), umma_idesc_t(N1, 1, 1), (acc_flag || ks > 0) ? 1u : 0u);
+      });
+      first_mma = false;
+    } else {
+      sync_issue([&]() {   // dH1 = G2 * W2   (B = W2 image read MN-major: N = 160 inputs, K = 192 outputs)
+#pragma unroll
+        for (int ks = 0; ks < N2 / 16; ++ks) {
+          const uint32_t blk = ks >> 2, j = ks & 3;
+          umma_bf16(tmem + RS_COL, umma_desc(sG2 + blk * A_BLK + j * 32), umma_desc_mn(sW2 + ks * 2048, W2_BLK),
+                    umma_idesc_t(N1, 0, 1), ks > 0);
+        }
+      });
+      // ---- e3: G1 = dH1 * f'(D1) * keep1 (divided by s) -> bf16 tile over the G2 tile --------------------
+#pragma unroll
+      for (int c16 = 0; c16 < 5; ++c16) {
+        const int col0 = wg * 80 + c16 * 16;
+        float v[16];
+        tmem_ld16(tmem + tlane + RS_COL + col0, v);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int le = c16 * 16 + e;
+          float gval = v[e] * (((pos1[le >> 5] >> (le & 31)) & 1u) ? 1.f : a.alpha);
+          if (DROP && !((keep1[le >> 5] >> (le & 31)) & 1u)) gval = 0.f;
+          v[e] = gval;
+        }
+        st_chunk(sA1 + swz_chunk(row, col0, A_BLK), v, 0);
+        st_chunk(sA1 + swz_chunk(row, col0 + 8, A_BLK), v, 8);
+      }
+      const bool acc_flag = !first_mma;
+      sync_issue([&]() {
+        // dH0 = G1 * W1   (B = W1 image read MN-major: N = 96 inputs, K = 160 outputs)
+#pragma unroll
+        for (int ks = 0; ks < N1 / 16; ++ks) {
+          const uint32_t blk = ks >> 2, j = ks & 3;
+          umma_bf16(tmem + RS_COL, umma_desc(sA1 + blk * A_BLK + j * 32), umma_desc_mn(sW1 + ks * 2048, W1_BLK),
+                    umma_idesc_t(K0, 0, 1), ks > 0);
+        }
+        // dW1^T[k0][n1] += H0^T G1   (M = 128 columns of the H0 tile incl. the constant-1 columns, K = 128 rows)
+#pragma unroll
+        for (int ks = 0; ks < TILE / 16; ++ks)
+          umma_bf16(tmem + RW1_COL, umma_desc_mn(sA0 + ks * 2048, A_BLK), umma_desc_mn(sA1 + ks * 2048, A_BLK),
+                    umma_idesc_t(N1, 1, 1), (acc_flag || ks > 0) ? 1u : 0u);
+      });
+      first_mma = false;
+      // ---- e4: G0 = dH0 * s * f'(pre0) * keep0 -> dP (registers), dQ (red.global) ---------------------------
+      {
+        float* dq = a.dQ + ((size_t)jet * a.N + s) * K0 + wg * 48;
+#pragma unroll
+        for (int c16 = 0; c16 < 3; ++c16) {
+          float v[16];
+          tmem_ld16(tmem + tlane + RS_COL + wg * 48 + c16 * 16, v);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const int le = c16 * 16 + e;
+            float gval = v[e] * sdrop * (((pos0[le >> 5] >> (le & 31)) & 1u) ? 1.f : a.alpha);
+            if (DROP && !((keep0[le >> 5] >> (le & 31)) & 1u)) gval = 0.f;
+            if (valid) {
+              dPacc[le] += gval;
+              if (gval != 0.f) atomicAdd(dq + le, gval);
+            }
+          }
+        }
+      }
+    }
+  }
+  flush_dP();
+
+  // ---- flush the TMEM weight-gradient accumulators ----------------------------------------------------
+  if (nsteps > 0) {
+    tc_fence_after();
+    if constexpr (MODE == BWD_CHAIN) {
+      // accumulator row m' = H0-tile column (k0 < 96: dW1[:, k0]; 96: db1), column n1
+#pragma unroll 1
+      for (int c16 = 0; c16 < 5; ++c16) {
+        const int col0 = wg * 80 + c16 * 16;
+        float v[16];
+        tmem_ld16(tmem + tlane + RW1_COL + col0, v);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int n1 = col0 + e;
+          if (row < K0) atomicAdd(a.dW1 + (size_t)n1 * K0 + row, v[e] * sdrop * sdrop);
+          else if (row == K0) atomicAdd(a.db1 + n1, v[e] * sdrop);
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int mb = 0; mb < 2; ++mb) {
+        const int n2 = mb * 128 + row;
+#pragma unroll 1
+        for (int c16 = 0; c16 < 5; ++c16) {
+          const int col0 = wg * 80 + c16 * 16;
+          float v[16];
+          tmem_ld16(tmem + tlane + (mb == 0 ? RW2A_COL : RW2B_COL) + col0, v);
+          if (n2 < N2) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) atomicAdd(a.dW2 + (size_t)n2 * N1 + col0 + e, v[e] * sdrop * sdrop);
+          }
+        }
+      }
+      if (threadIdx.x < 192) {
+        const int cp = threadIdx.x % 96;
+        atomicAdd(a.db2 + 2 * cp, db2acc0 * sdrop);
+        atomicAdd(a.db2 + 2 * cp + 1, db2acc1 * sdrop);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
+}

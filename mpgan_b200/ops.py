@@ -51,6 +51,46 @@ def _seed_ptr():
     return None if _device_seed is None else _device_seed.data_ptr()
 
 
+# optional per-call device timing of the edge-network launches (bench.py's roofline leg): a list of
+# (name, start_event, end_event, algorithmic_flops) filled while profiling is on
+_profile = None
+
+
+def profile_start():
+    global _profile
+    _profile = []
+    return _profile
+
+
+def profile_stop():
+    global _profile
+    p, _profile = _profile, None
+    return p
+
+
+class _Timed:
+    def __init__(self, name, flops):
+        self.name, self.flops = name, flops
+
+    def __enter__(self):
+        if _profile is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _profile is not None:
+            self.e1.record()
+            _profile.append((self.name, self.e0, self.e1, self.flops))
+        return False
+
+
+def edge_flops(B, N, F, H0, H1, H2):
+    """Algorithmic forward FLOPs of one fused edge call (first layer factorised)."""
+    return 4.0 * B * N * F * H0 + 2.0 * B * N * N * (H0 * H1 + H1 * H2)
+
+
 def _rows(t):
     """View a [..., K] tensor as rows with a constant row stride (no copy when possible)."""
     if t.dim() == 2 and t.stride(1) == 1:
@@ -125,10 +165,11 @@ class EdgeAggFn(torch.autograd.Function):
         m = None if mask is None else mask.reshape(B, N).contiguous()
         ws_ = [t.contiguous() for t in (w0, b0, w1, b1, w2, b2)]
         seed = next_seed() if p_drop > 0 else 0
-        _lib.check(L.mpg_edge_fwd(_lib.ptr(x3), ldx, _lib.ptr(m), *[_lib.ptr(t) for t in ws_], B, N, F, H0, H1, H2,
-                                  int(ef_mode), int(nd), int(mean), float(alpha), float(p_drop), seed, _seed_ptr(),
-                                  _PRECISION, ws.data_ptr(), ws_bytes, _lib.ptr(agg), _lib.stream()),
-                   "mpg_edge_fwd")
+        with _Timed("edge_fwd", edge_flops(B, N, F, H0, H1, H2)):
+            _lib.check(L.mpg_edge_fwd(_lib.ptr(x3), ldx, _lib.ptr(m), *[_lib.ptr(t) for t in ws_], B, N, F, H0, H1,
+                                      H2, int(ef_mode), int(nd), int(mean), float(alpha), float(p_drop), seed,
+                                      _seed_ptr(), _PRECISION, ws.data_ptr(), ws_bytes, _lib.ptr(agg),
+                                      _lib.stream()), "mpg_edge_fwd")
         ctx.save_for_backward(x3, m, *ws_)
         ctx.cfg = (ldx, B, N, F, H0, H1, H2, int(ef_mode), int(nd), int(mean), float(alpha), float(p_drop), seed,
                    _PRECISION, _seed_ptr())
@@ -145,10 +186,12 @@ class EdgeAggFn(torch.autograd.Function):
         ws = torch.empty(ws_bytes, device=dagg.device, dtype=torch.uint8)
         dx = torch.empty(B, N, F, device=dagg.device, dtype=torch.float32)
         grads = [torch.zeros_like(t) for t in (w0, b0, w1, b1, w2, b2)]
-        _lib.check(L.mpg_edge_bwd(_lib.ptr(x3), ldx, _lib.ptr(m), *[_lib.ptr(t) for t in (w0, b0, w1, b1, w2, b2)],
-                                  B, N, F, H0, H1, H2, ef_mode, nd, mean, alpha, p, seed, sptr, prec, ws.data_ptr(),
-                                  ws_bytes, _lib.ptr(dagg), _lib.ptr(dx), F, *[_lib.ptr(g) for g in grads],
-                                  _lib.stream()), "mpg_edge_bwd")
+        with _Timed("edge_bwd", 2.0 * edge_flops(B, N, F, H0, H1, H2)):
+            _lib.check(L.mpg_edge_bwd(_lib.ptr(x3), ldx, _lib.ptr(m),
+                                      *[_lib.ptr(t) for t in (w0, b0, w1, b1, w2, b2)], B, N, F, H0, H1, H2, ef_mode,
+                                      nd, mean, alpha, p, seed, sptr, prec, ws.data_ptr(), ws_bytes, _lib.ptr(dagg),
+                                      _lib.ptr(dx), F, *[_lib.ptr(g) for g in grads], _lib.stream()),
+                       "mpg_edge_bwd")
         return (dx, None, *grads, None, None, None, None, None)
 
 

@@ -240,6 +240,22 @@ def test_dropout_statistics_and_determinism():
     assert abs(fd - g[0, 2, 1].item()) < 5e-2 * max(1.0, abs(fd)), (fd, g[0, 2, 1].item())
 
 
+def test_tc_dropout_matches_generic(golden):
+    """Same seed => the tcgen05 kernel and the fp32 SIMT kernel draw identical Philox masks."""
+    import mpgan_b200.ops as O
+    from mpgan_b200 import presets, train
+    D = presets.mp_discriminator(disc_dropout=0.5).cuda().train()
+    D.load_state_dict(golden("mp_d_seed4_weights.pt"), strict=True)
+    x, labels, _ = train.synthetic_jets(16, 30, "cuda", torch.Generator(device="cuda").manual_seed(9))
+    outs = []
+    for prec in (0, 1):
+        O.set_precision(prec)
+        O._seed_counter = 1000
+        with torch.no_grad():
+            outs.append(D.mp_layers[1].fe is not None and D(x, labels))
+    close(outs[1], outs[0], 2e-2, "dropout D forward, tcgen05 vs fp32")
+
+
 def test_train_step_golden(golden):
     """One train_D + train_G (LS loss, RMSprop) against the reference's own train.py step."""
     from mpgan_b200 import presets, train
