@@ -45,6 +45,9 @@ const char* mpg_last_error(void);
 int mpg_features(void);
 /* number of kernel launches this library has issued so far in this process */
 unsigned long long mpg_launch_count(void);
+/* measurement hook: brackets the NEXT launch of one tcgen05 edge kernel (1 = forward, 2 = backward
+ * chain, 3 = backward dW2) with the two cudaEvent_t handles; one-shot, calling thread only */
+void mpg_probe(int kernel_id, void* ev_start, void* ev_stop);
 
 /* ---- LinearNet layer (mpgan/model.py:77-83): y = dropout(act(x W^T + b)) -------------------------- */
 int mpg_linear_fwd(const float* x, int ldx, const float* w, const float* b, float* y, int M, int K, int N,

@@ -20,6 +20,7 @@ _SIGS = {
     "mpg_last_error": (C.c_char_p, []),
     "mpg_features": (C.c_int, []),
     "mpg_launch_count": (C.c_ulonglong, []),
+    "mpg_probe": (None, [_i, _f, _f]),
     "mpg_linear_fwd": (C.c_int, [_f, _i, _f, _f, _f, _i, _i, _i, _i, _fl, _fl, _u64, _f, _u32, _i, _f]),
     "mpg_linear_bwd": (C.c_int, [_f, _f, _f, _i, _f, _f, _f, _i, _i, _f, _f, _i, _i, _i, _i, _fl, _fl, _u64, _f,
                                  _u32, _i, _f]),

@@ -111,6 +111,9 @@ int mpg_version(void) { return 100; }
 const char* mpg_last_error(void) { return g_err; }
 int mpg_features(void) { return edge_tc_features() | 4; }
 unsigned long long mpg_launch_count(void) { return g_launch_count; }
+void mpg_probe(int kernel_id, void* ev_start, void* ev_stop) {
+  edge_tc_arm_probe(kernel_id, (cudaEvent_t)ev_start, (cudaEvent_t)ev_stop);
+}
 
 int mpg_linear_fwd(const float* x, int ldx, const float* w, const float* b, float* y, int M, int K, int N, int act,
                    float alpha, float p_drop, uint64_t seed, const uint64_t* seed_dev, uint32_t rng_stream, int precision,

@@ -96,6 +96,29 @@ __host__ __device__ __forceinline__ bool drop_keep(const DropCfg& d, uint32_t st
   return h >= d.thr16;
 }
 
+// ---- edge-network dropout, p == 0.5 ---------------------------------------------------------------
+// One Philox draw (128 bits) covers one quarter of the columns of ALL three fe layers of a pair row:
+// layer l (width H_l) column c lies in quarter q = c / (H_l/4) at index i = c % (H_l/4); its keep bit is
+// bit (off_l + i) of draw(pair, q), off = (0, H0/4, H0/4 + H1/4).  This is the layout the tcgen05
+// kernels consume (thread = one row x one column quarter => one draw per thread and step); the generic
+// kernel evaluates the same function element-wise.  Needs H_l % 4 == 0 and (H0+H1+H2)/4 <= 128.
+__host__ __device__ __forceinline__ bool edge_drop_packed_ok(int H0, int H1, int H2) {
+  return (H0 % 4 == 0) && (H1 % 4 == 0) && (H2 % 4 == 0) && (H0 + H1 + H2) / 4 <= 128;
+}
+__host__ __device__ __forceinline__ u4 edge_drop_bits(uint64_t seed, uint64_t pair, uint32_t quarter) {
+  return philox4x32_10((uint32_t)pair, (uint32_t)(pair >> 32), 0xED6E0000u | quarter, 0u, (uint32_t)seed,
+                       (uint32_t)(seed >> 32));
+}
+__host__ __device__ __forceinline__ bool edge_drop_keep(uint64_t seed, uint64_t pair, int layer, int col, int H0,
+                                                        int H1, int H2) {
+  const int w = (layer == 0 ? H0 : (layer == 1 ? H1 : H2)) / 4;
+  const int off = layer == 0 ? 0 : (layer == 1 ? H0 / 4 : (H0 + H1) / 4);
+  const int b = off + col % w;
+  const u4 r = edge_drop_bits(seed, pair, (uint32_t)(col / w));
+  const uint32_t word = (b >> 5) == 0 ? r.x : ((b >> 5) == 1 ? r.y : ((b >> 5) == 2 ? r.z : r.w));
+  return (word >> (b & 31)) & 1u;
+}
+
 __device__ __forceinline__ float lrelu(float x, float a) { return x > 0.f ? x : a * x; }
 __device__ __forceinline__ float lrelu_grad_from_out(float y, float a) { return y > 0.f ? 1.f : a; }
 

@@ -38,6 +38,7 @@ int launch_transpose(const float* in, int rows, int cols, float* out, cudaStream
 
 // tcgen05 path (edge_tc.cu): default architecture only
 int edge_tc_features();
+void edge_tc_arm_probe(int id, cudaEvent_t e0, cudaEvent_t e1);
 bool edge_tc_supported(const EdgeArgs& a);
 size_t edge_tc_workspace_bytes(int B, int N, int H0, int H1, int H2);
 int launch_edge_tc_fwd(const EdgeArgs& a, void* ws, cudaStream_t stream);

@@ -42,6 +42,14 @@ __device__ __forceinline__ void tile_matmul(float (&acc)[8][U], const float* __r
   }
 }
 
+// keep decision of pair-row element (layer, col): the packed one-draw-per-quarter-row layout the tcgen05
+// kernels use when it applies (p == 0.5), else the generic per-element stream
+__device__ __forceinline__ bool edge_keep(const EdgeArgs& a, uint32_t layer, uint64_t pair, int col) {
+  if (a.drop.half && edge_drop_packed_ok(a.H0, a.H1, a.H2))
+    return edge_drop_keep(a.drop.seed, pair, (int)layer, col, a.H0, a.H1, a.H2);
+  return drop_keep(a.drop, layer, pair, (uint32_t)col);
+}
+
 struct ChunkCtx {
   int b, i, j0, nvalid;   // senders j0 .. j0+nvalid-1
   uint64_t pair0;         // (b*N + i)*N
@@ -77,7 +85,7 @@ __device__ __forceinline__ void build_h0(const EdgeArgs& a, const ChunkCtx& c, c
       v = Pi[k] + a.Q[((size_t)c.b * a.N + c.j0 + r) * a.H0 + k];
       for (int e = 0; e < a.n_ef; ++e) v = fmaf(efs[e * RS + r], a.Wef[(size_t)k * a.ldwef + e], v);
       v = lrelu(v, a.alpha);
-      if (a.drop.p > 0.f) v = drop_keep(a.drop, 0, c.pair0 + c.j0 + r, k) ? v * a.drop.scale : 0.f;
+      if (a.drop.p > 0.f) v = edge_keep(a, 0, c.pair0 + c.j0 + r, k) ? v * a.drop.scale : 0.f;
     }
     H0s[k * RS + r] = v;
   }
@@ -99,7 +107,7 @@ __device__ __forceinline__ void layer_fwd(const EdgeArgs& a, const ChunkCtx& c, 
     for (int r = 0; r < 8; ++r) {
       const int row = tr * 8 + r;
       float v = lrelu(acc[r][u] + bv, a.alpha);
-      if (a.drop.p > 0.f) v = drop_keep(a.drop, stream, c.pair0 + c.j0 + row, col) ? v * a.drop.scale : 0.f;
+      if (a.drop.p > 0.f) v = edge_keep(a, stream, c.pair0 + c.j0 + row, col) ? v * a.drop.scale : 0.f;
       out[col * RS + row] = row < c.nvalid ? v : 0.f;
     }
   }
@@ -156,7 +164,7 @@ __global__ void __launch_bounds__(NTHR) edge_fwd_generic(EdgeArgs a) {
 // d(act+dropout)/dz given the stored output y (see common.cuh) for pair-row elements
 __device__ __forceinline__ float act_grad(const EdgeArgs& a, float y, uint32_t stream, uint64_t row, int col) {
   float gfac = lrelu_grad_from_out(y, a.alpha);
-  if (a.drop.p > 0.f) gfac = drop_keep(a.drop, stream, row, col) ? gfac * a.drop.scale : 0.f;
+  if (a.drop.p > 0.f) gfac = edge_keep(a, stream, row, col) ? gfac * a.drop.scale : 0.f;
   return gfac;
 }
 

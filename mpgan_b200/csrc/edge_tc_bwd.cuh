@@ -17,6 +17,8 @@
 // Scale convention with dropout p = 0.5 (s = 2): tiles hold activations / pre-activation gradients
 // divided by s and the weight images hold s*W, so every MMA sees the true product; the factors are
 // restored at the flush (dW: s^2, db: s) and in G0 (s).
+//
+// Thread layout as in the forward kernel: 16 warps, thread <-> (tile row, column quarter).
 
 enum { BWD_CHAIN = 0, BWD_DW2 = 1 };
 
@@ -39,15 +41,6 @@ constexpr uint32_t BW_OFF_BAR_DW2 = BW_OFF_A1_DW2 + H1_BYTES;      // 212992
 constexpr uint32_t BW_SMEM_CHAIN = BW_OFF_BAR_CHAIN + 128 + 1024;
 constexpr uint32_t BW_SMEM_DW2 = BW_OFF_BAR_DW2 + 128 + 1024;
 constexpr uint32_t RS_COL = 0, RW1_COL = 256, RW2A_COL = 192, RW2B_COL = 352;
-
-__device__ __forceinline__ void st_chunk(uint32_t addr, const float (&v)[16], int o) {
-  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(pack_bf16(v[o], v[o + 1])),
-               "r"(pack_bf16(v[o + 2], v[o + 3])), "r"(pack_bf16(v[o + 4], v[o + 5])),
-               "r"(pack_bf16(v[o + 6], v[o + 7])));
-}
-__device__ __forceinline__ uint32_t word_of(const u4& b, int w) {
-  return w == 0 ? b.x : (w == 1 ? b.y : (w == 2 ? b.z : b.w));
-}
 
 template <int MODE, bool DROP>
 __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_bwd_kernel(TcArgs t) {
@@ -90,7 +83,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_bwd_kernel(TcArgs t) {
     bulk_g2s(sW2, t.w2img, W2_BYTES, bar_w);
   }
 
-  const int wg = warp >> 2;
+  const int q = warp >> 2;
   const int row = (warp & 3) * 32 + lane;
   const uint32_t tlane = (uint32_t)((warp & 3) * 32) << 16;
   const int BN = a.B * a.N;
@@ -113,33 +106,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_bwd_kernel(TcArgs t) {
     tc_fence_after();
   };
 
-  // constant 1.0 bias columns (H0 cols 96,97 / H1 cols 160,161), zeros up to the end of the K step
-  if (nsteps > 0) {
-    const uint32_t one2 = 0x3F803F80u;
-    if (MODE == BWD_CHAIN) {
-      if (wg == 0) {
-        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%2,%2};" ::"r"(sA0 + swz_chunk(row, 96, A_BLK)), "r"(one2), "r"(0u));
-        asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(sA0 + swz_chunk(row, 104, A_BLK)), "r"(0u));
-        // columns 112..127 of the H0 tile are read (as unused rows) by the transposed dW1 product
-        asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(sA0 + swz_chunk(row, 112, A_BLK)), "r"(0u));
-        asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(sA0 + swz_chunk(row, 120, A_BLK)), "r"(0u));
-      }
-    }
+  // CHAIN: the H0 tile is private to H0; its bias columns (96,97 = 1) and the never-written columns
+  // 98..127 (read as unused rows by the transposed dW1 product) are initialised once
+  if (MODE == BWD_CHAIN && nsteps > 0 && q == 0) {
+    st_ones_chunk(sA0 + swz_chunk(row, 96, A_BLK));
+    st_zero_chunk(sA0 + swz_chunk(row, 104, A_BLK));
+    st_zero_chunk(sA0 + swz_chunk(row, 112, A_BLK));
+    st_zero_chunk(sA0 + swz_chunk(row, 120, A_BLK));
   }
 
-  float Preg[48];
-  uint32_t dAggp[48];           // bf16x2: dAgg[r][wg*96 + 2i], [.. + 2i + 1]
-  float dPacc[MODE == BWD_CHAIN ? 48 : 1];
+  float Preg[Q0];
+  uint32_t dAggp[Q2 / 2];       // bf16x2: dAgg[r][q*48 + 2i], [.. + 2i + 1]
+  float dPacc[MODE == BWD_CHAIN ? Q0 : 1];
   float db2acc0 = 0.f, db2acc1 = 0.f;
   int cur_tile = -1, r = 0, jet = 0;
   bool valid = false;
   bool first_mma = true;
 
   auto flush_dP = [&]() {
-    if constexpr (MODE == BWD_CHAIN) if (cur_tile >= 0 && valid) {
-      float* dst = a.dP + (size_t)r * K0 + wg * 48;
+    if constexpr (MODE == BWD_CHAIN) {
+      if (cur_tile >= 0 && valid) {
+        float* dst = a.dP + (size_t)r * K0 + q * Q0;
 #pragma unroll
-      for (int c = 0; c < 48; ++c) atomicAdd(dst + c, dPacc[c]);
+        for (int c = 0; c < Q0; ++c) atomicAdd(dst + c, dPacc[c]);
+      }
     }
   };
   auto load_tile = [&](int tile) {
@@ -149,22 +139,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_bwd_kernel(TcArgs t) {
     valid = r < BN;
     const int rc = valid ? r : BN - 1;
     jet = rc / a.N;
-    const float4* p = reinterpret_cast<const float4*>(a.P + (size_t)rc * K0 + wg * 48);
+    const float4* p = reinterpret_cast<const float4*>(a.P + (size_t)rc * K0 + q * Q0);
 #pragma unroll
-    for (int c = 0; c < 12; ++c) {
+    for (int c = 0; c < Q0 / 4; ++c) {
       const float4 v = __ldg(p + c);
       Preg[4 * c] = v.x; Preg[4 * c + 1] = v.y; Preg[4 * c + 2] = v.z; Preg[4 * c + 3] = v.w;
     }
-    const float4* dg = reinterpret_cast<const float4*>(a.dagg + (size_t)rc * N2 + wg * 96);
+    const float4* dg = reinterpret_cast<const float4*>(a.dagg + (size_t)rc * N2 + q * Q2);
 #pragma unroll
-    for (int c = 0; c < 24; ++c) {
+    for (int c = 0; c < Q2 / 4; ++c) {
       const float4 v = __ldg(dg + c);
       dAggp[2 * c] = pack_bf16(v.x, v.y);
       dAggp[2 * c + 1] = pack_bf16(v.z, v.w);
     }
     if constexpr (MODE == BWD_CHAIN) {
 #pragma unroll
-      for (int c = 0; c < 48; ++c) dPacc[c] = 0.f;
+      for (int c = 0; c < Q0; ++c) dPacc[c] = 0.f;
     }
   };
 
@@ -176,38 +166,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_bwd_kernel(TcArgs t) {
     if (tile != cur_tile) load_tile(tile);
     const uint64_t pair = (uint64_t)(valid ? r : 0) * a.N + s;
     const float mfac = valid ? (a.mask ? a.mask[(size_t)jet * a.N + s] : 1.f) * a.out_scale : 0.f;
+    u4 bits{0, 0, 0, 0};
+    if (DROP) bits = edge_drop_bits(drop.seed, pair, q);
 
-    // ---- H0 tile; remember sign / keep bits of the 48 columns this thread owns ------------------------
-    uint32_t pos0[2] = {0, 0}, keep0[2] = {~0u, ~0u};
+    // ---- H0 tile; remember the sign bits of the 24 columns this thread owns -----------------------------
+    uint32_t pos0 = 0;
     {
-      const float4* q = reinterpret_cast<const float4*>(a.Q + ((size_t)jet * a.N + s) * K0 + wg * 48);
-      u4 bits{0, 0, 0, 0};
-      if (DROP) bits = drop_bits128(drop.seed, 0, pair, 0);
+      const float4* qp = reinterpret_cast<const float4*>(a.Q + ((size_t)jet * a.N + s) * K0 + q * Q0);
 #pragma unroll
-      for (int c8 = 0; c8 < 6; ++c8) {
-        const float4 q0 = __ldg(q + 2 * c8), q1 = __ldg(q + 2 * c8 + 1);
-        float v[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, 0, 0, 0, 0, 0, 0, 0, 0};
+      for (int c8 = 0; c8 < Q0 / 8; ++c8) {
+        const float4 q0 = __ldg(qp + 2 * c8), q1 = __ldg(qp + 2 * c8 + 1);
+        float v[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          const int le = c8 * 8 + e;               // 0..47
+          const int le = c8 * 8 + e;
           float x = v[e] + Preg[le];
-          if (x > 0.f) pos0[le >> 5] |= 1u << (le & 31);
+          if (x > 0.f) pos0 |= 1u << le;
           x = fmaxf(x, a.alpha * x);
-          if (DROP) {
-            const int col = wg * 48 + le;
-            if (!((word_of(bits, col >> 5) >> (col & 31)) & 1u)) {
-              x = 0.f;
-              keep0[le >> 5] &= ~(1u << (le & 31));
-            }
-          }
+          if (DROP) x = apply_keep(x, keep_mask(bits, le));
           v[e] = x;
         }
-        st_chunk(sA0 + swz_chunk(row, wg * 48 + c8 * 8, A_BLK), v, 0);
+        st_chunk(sA0 + swz_chunk(row, q * Q0 + c8 * 8, A_BLK), v);
       }
-      if (MODE == BWD_DW2 && wg == 0) {   // DW2 builds H0 inside the G2 region: bias columns every step
-        const uint32_t one2 = 0x3F803F80u;
-        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%2,%2};" ::"r"(sA0 + swz_chunk(row, 96, A_BLK)), "r"(one2), "r"(0u));
-        asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(sA0 + swz_chunk(row, 104, A_BLK)), "r"(0u));
+      if (MODE == BWD_DW2 && q == 0) {   // DW2 builds H0 inside the G2 region: bias columns every step
+        st_ones_chunk(sA0 + swz_chunk(row, 96, A_BLK));
+        st_zero_chunk(sA0 + swz_chunk(row, 104, A_BLK));
       }
     }
     sync_issue([&]() {   // D1 = H0 * W1^T
@@ -218,51 +201,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_bwd_kernel(TcArgs t) {
                   umma_idesc(N1), ks > 0);
       }
     });
-    // ---- e1: H1 tile, sign / keep bits of this thread's 80 columns ------------------------------------
-    uint32_t pos1[3] = {0, 0, 0}, keep1[3] = {~0u, ~0u, ~0u};
+    // ---- e1: H1 tile, sign bits of this thread's 40 columns ----------------------------------------------
+    uint32_t pos1[2] = {0, 0};
     {
-      u4 b0{0, 0, 0, 0}, b1{0, 0, 0, 0};
-      if (DROP) {
-        b0 = drop_bits128(drop.seed, 1, pair, 0);
-        if (wg == 1) b1 = drop_bits128(drop.seed, 1, pair, 1);
-      }
 #pragma unroll
-      for (int c16 = 0; c16 < 5; ++c16) {
-        const int col0 = wg * 80 + c16 * 16;
+      for (int c0 = 0; c0 < Q1; c0 += 16) {
+        const int n = (Q1 - c0) >= 16 ? 16 : 8;   // static after unrolling
         float v[16];
-        tmem_ld16(tmem + tlane + RS_COL + col0, v);
+        if (n == 16) tmem_ld16(tmem + tlane + RS_COL + q * Q1 + c0, v);
+        else tmem_ld8(tmem + tlane + RS_COL + q * Q1 + c0, v);
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
-          const int le = c16 * 16 + e;             // 0..79
-          float x = v[e];
-          if (x > 0.f) pos1[le >> 5] |= 1u << (le & 31);
-          x = fmaxf(x, a.alpha * x);
-          if (DROP) {
-            const int col = col0 + e;
-            const u4& bb = (col >> 7) ? b1 : b0;
-            if (!((word_of(bb, (col >> 5) & 3) >> (col & 31)) & 1u)) {
-              x = 0.f;
-              keep1[le >> 5] &= ~(1u << (le & 31));
-            }
+          if (e < n) {
+            const int le = c0 + e;
+            float x = v[e];
+            if (x > 0.f) pos1[le >> 5] |= 1u << (le & 31);
+            x = fmaxf(x, a.alpha * x);
+            if (DROP) x = apply_keep(x, keep_mask(bits, Q0 + le));
+            v[e] = x;
           }
-          v[e] = x;
         }
-        st_chunk(sA1 + swz_chunk(row, col0, A_BLK), v, 0);
-        st_chunk(sA1 + swz_chunk(row, col0 + 8, A_BLK), v, 8);
+        st_chunk(sA1 + swz_chunk(row, q * Q1 + c0, A_BLK), v);
+        if (n == 16) st_chunk(sA1 + swz_chunk(row, q * Q1 + c0 + 8, A_BLK), v + 8);
       }
-      if (MODE == BWD_DW2 && it == 0) {   // constant bias columns of the H1 tile (never overwritten in DW2)
-        if (wg == 1) {
-          const uint32_t one2 = 0x3F803F80u;
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%2,%2};" ::"r"(sA1 + swz_chunk(row, 160, A_BLK)), "r"(one2), "r"(0u));
-          asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(sA1 + swz_chunk(row, 168, A_BLK)), "r"(0u));
-        }
-      }
-      if (MODE == BWD_CHAIN) {            // CHAIN reuses the H1 region for G2/G1: rewrite them every step
-        if (wg == 1) {
-          const uint32_t one2 = 0x3F803F80u;
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%2,%2};" ::"r"(sA1 + swz_chunk(row, 160, A_BLK)), "r"(one2), "r"(0u));
-          asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(sA1 + swz_chunk(row, 168, A_BLK)), "r"(0u));
-        }
+      // constant bias columns of the H1 tile: DW2 never overwrites them, CHAIN reuses the region for G2/G1
+      if ((MODE == BWD_CHAIN || it == 0) && q == 1) {
+        st_ones_chunk(sA1 + swz_chunk(row, 160, A_BLK));
+        st_zero_chunk(sA1 + swz_chunk(row, 168, A_BLK));
       }
     }
     sync_issue([&]() {   // D2 = H1 * W2^T
@@ -274,44 +239,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_bwd_kernel(TcArgs t) {
       }
     });
     // ---- e2': G2 = dAgg * m * f'(D2) * keep2  (divided by s, see header) -> bf16 tile --------------------
-    {
-      u4 b0{0, 0, 0, 0}, b1{0, 0, 0, 0};
-      if (DROP) {
-        b0 = drop_bits128(drop.seed, 2, pair, 0);
-        if (wg == 1) b1 = drop_bits128(drop.seed, 2, pair, 1);
-      }
 #pragma unroll
-      for (int c16 = 0; c16 < 6; ++c16) {
-        const int col0 = wg * 96 + c16 * 16;
-        float v[16];
-        tmem_ld16(tmem + tlane + RS_COL + col0, v);
+    for (int c16 = 0; c16 < Q2 / 16; ++c16) {
+      float v[16];
+      tmem_ld16(tmem + tlane + RS_COL + q * Q2 + c16 * 16, v);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const int le = c16 * 16 + e;             // 0..95
-          const uint32_t pk = dAggp[le >> 1];
-          const float dg = __uint_as_float((le & 1) ? (pk & 0xFFFF0000u) : (pk << 16));
-          float gval = dg * mfac * (v[e] > 0.f ? 1.f : a.alpha);
-          if (DROP) {
-            const int col = col0 + e;
-            const u4& bb = (col >> 7) ? b1 : b0;
-            if (!((word_of(bb, (col >> 5) & 3) >> (col & 31)) & 1u)) gval = 0.f;
-          }
-          v[e] = gval;
-        }
-        st_chunk(sG2 + swz_chunk(row, col0, A_BLK), v, 0);
-        st_chunk(sG2 + swz_chunk(row, col0 + 8, A_BLK), v, 8);
+      for (int e = 0; e < 16; ++e) {
+        const int le = c16 * 16 + e;
+        const uint32_t pk = dAggp[le >> 1];
+        const float dg = __uint_as_float((le & 1) ? (pk & 0xFFFF0000u) : (pk << 16));
+        float gval = dg * mfac * (v[e] > 0.f ? 1.f : a.alpha);
+        if (DROP) gval = apply_keep(gval, keep_mask(bits, Q0 + Q1 + le));
+        v[e] = gval;
       }
+      st_chunk(sG2 + swz_chunk(row, q * Q2 + c16 * 16, A_BLK), v);
+      st_chunk(sG2 + swz_chunk(row, q * Q2 + c16 * 16 + 8, A_BLK), v + 8);
     }
 
     if constexpr (MODE == BWD_DW2) {
-      // db2 partial column sums straight from the bf16 G2 tile (thread -> 2 columns x 64 rows)
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (threadIdx.x < 192) {
-        const int cp = threadIdx.x % 96, rh = threadIdx.x / 96;
+      // db2 partial column sums straight from the bf16 G2 tile (thread -> 2 columns x 32 rows)
+      asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory");
+      if (threadIdx.x < 384) {
+        const int cp = threadIdx.x % 96, rq = threadIdx.x / 96;
         const uint32_t col = 2 * cp;
 #pragma unroll 8
-        for (int rr = 0; rr < 64; ++rr) {
-          const uint32_t rw = rh * 64 + rr;
+        for (int rr = 0; rr < 32; ++rr) {
+          const uint32_t rw = rq * 32 + rr;
           uint32_t w;
           asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(sG2 + swz_chunk(rw, col, A_BLK) + (col & 7) * 2));
           db2acc0 += __uint_as_float(w << 16);
@@ -339,19 +292,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_bwd_kernel(TcArgs t) {
       });
       // ---- e3: G1 = dH1 * f'(D1) * keep1 (divided by s) -> bf16 tile over the G2 tile --------------------
 #pragma unroll
-      for (int c16 = 0; c16 < 5; ++c16) {
-        const int col0 = wg * 80 + c16 * 16;
+      for (int c0 = 0; c0 < Q1; c0 += 16) {
+        const int n = (Q1 - c0) >= 16 ? 16 : 8;   // static after unrolling
         float v[16];
-        tmem_ld16(tmem + tlane + RS_COL + col0, v);
+        if (n == 16) tmem_ld16(tmem + tlane + RS_COL + q * Q1 + c0, v);
+        else tmem_ld8(tmem + tlane + RS_COL + q * Q1 + c0, v);
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
-          const int le = c16 * 16 + e;
-          float gval = v[e] * (((pos1[le >> 5] >> (le & 31)) & 1u) ? 1.f : a.alpha);
-          if (DROP && !((keep1[le >> 5] >> (le & 31)) & 1u)) gval = 0.f;
-          v[e] = gval;
+          if (e < n) {
+            const int le = c0 + e;
+            float gval = v[e] * (((pos1[le >> 5] >> (le & 31)) & 1u) ? 1.f : a.alpha);
+            if (DROP) gval = apply_keep(gval, keep_mask(bits, Q0 + le));
+            v[e] = gval;
+          }
         }
-        st_chunk(sA1 + swz_chunk(row, col0, A_BLK), v, 0);
-        st_chunk(sA1 + swz_chunk(row, col0 + 8, A_BLK), v, 8);
+        st_chunk(sA1 + swz_chunk(row, q * Q1 + c0, A_BLK), v);
+        if (n == 16) st_chunk(sA1 + swz_chunk(row, q * Q1 + c0 + 8, A_BLK), v + 8);
       }
       const bool acc_flag = !first_mma;
       sync_issue([&]() {
@@ -371,20 +327,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_bwd_kernel(TcArgs t) {
       first_mma = false;
       // ---- e4: G0 = dH0 * s * f'(pre0) * keep0 -> dP (registers), dQ (red.global) ---------------------------
       {
-        float* dq = a.dQ + ((size_t)jet * a.N + s) * K0 + wg * 48;
+        float* dq = a.dQ + ((size_t)jet * a.N + s) * K0 + q * Q0;
+        float v[Q0];
+        tmem_ld_cols<Q0>(tmem + tlane + RS_COL + q * Q0, v);
 #pragma unroll
-        for (int c16 = 0; c16 < 3; ++c16) {
-          float v[16];
-          tmem_ld16(tmem + tlane + RS_COL + wg * 48 + c16 * 16, v);
-#pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const int le = c16 * 16 + e;
-            float gval = v[e] * sdrop * (((pos0[le >> 5] >> (le & 31)) & 1u) ? 1.f : a.alpha);
-            if (DROP && !((keep0[le >> 5] >> (le & 31)) & 1u)) gval = 0.f;
-            if (valid) {
-              dPacc[le] += gval;
-              if (gval != 0.f) atomicAdd(dq + le, gval);
-            }
+        for (int e = 0; e < Q0; ++e) {
+          float gval = v[e] * sdrop * (((pos0 >> e) & 1u) ? 1.f : a.alpha);
+          if (DROP) gval = apply_keep(gval, keep_mask(bits, e));
+          if (valid) {
+            dPacc[e] += gval;
+            if (gval != 0.f) atomicAdd(dq + e, gval);
           }
         }
       }
@@ -397,34 +349,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_bwd_kernel(TcArgs t) {
     tc_fence_after();
     if constexpr (MODE == BWD_CHAIN) {
       // accumulator row m' = H0-tile column (k0 < 96: dW1[:, k0]; 96: db1), column n1
-#pragma unroll 1
-      for (int c16 = 0; c16 < 5; ++c16) {
-        const int col0 = wg * 80 + c16 * 16;
-        float v[16];
-        tmem_ld16(tmem + tlane + RW1_COL + col0, v);
+      float v[Q1];
+      tmem_ld_cols<Q1>(tmem + tlane + RW1_COL + q * Q1, v);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const int n1 = col0 + e;
-          if (row < K0) atomicAdd(a.dW1 + (size_t)n1 * K0 + row, v[e] * sdrop * sdrop);
-          else if (row == K0) atomicAdd(a.db1 + n1, v[e] * sdrop);
-        }
+      for (int e = 0; e < Q1; ++e) {
+        const int n1 = q * Q1 + e;
+        if (row < K0) atomicAdd(a.dW1 + (size_t)n1 * K0 + row, v[e] * sdrop * sdrop);
+        else if (row == K0) atomicAdd(a.db1 + n1, v[e] * sdrop);
       }
     } else {
 #pragma unroll 1
       for (int mb = 0; mb < 2; ++mb) {
         const int n2 = mb * 128 + row;
-#pragma unroll 1
-        for (int c16 = 0; c16 < 5; ++c16) {
-          const int col0 = wg * 80 + c16 * 16;
-          float v[16];
-          tmem_ld16(tmem + tlane + (mb == 0 ? RW2A_COL : RW2B_COL) + col0, v);
-          if (n2 < N2) {
+        float v[Q1];
+        tmem_ld_cols<Q1>(tmem + tlane + (mb == 0 ? RW2A_COL : RW2B_COL) + q * Q1, v);
+        if (n2 < N2) {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) atomicAdd(a.dW2 + (size_t)n2 * N1 + col0 + e, v[e] * sdrop * sdrop);
-          }
+          for (int e = 0; e < Q1; ++e) atomicAdd(a.dW2 + (size_t)n2 * N1 + q * Q1 + e, v[e] * sdrop * sdrop);
         }
       }
-      if (threadIdx.x < 192) {
+      if (threadIdx.x < 384) {
         const int cp = threadIdx.x % 96;
         atomicAdd(a.db2 + 2 * cp, db2acc0 * sdrop);
         atomicAdd(a.db2 + 2 * cp + 1, db2acc1 * sdrop);

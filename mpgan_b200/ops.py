@@ -69,13 +69,24 @@ def profile_stop():
 
 
 class _Timed:
-    def __init__(self, name, flops):
-        self.name, self.flops = name, flops
+    """Brackets one C-ABI edge call with events; additionally arms the library's one-shot probes so
+    the tcgen05 kernels inside the call are timed on their own (kernel ids: include/mpgan_b200.h)."""
+
+    def __init__(self, name, flops, probes=()):
+        self.name, self.flops, self.probes = name, flops, probes
 
     def __enter__(self):
         if _profile is not None:
             self.e0 = torch.cuda.Event(enable_timing=True)
             self.e1 = torch.cuda.Event(enable_timing=True)
+            self.pe = []
+            L = _lib.lib()
+            for kid, kname, kflops in self.probes:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()  # materialise the cudaEvent_t handles
+                b.record()
+                L.mpg_probe(kid, a.cuda_event, b.cuda_event)
+                self.pe.append((kname, a, b, kflops))
             self.e0.record()
         return self
 
@@ -83,12 +94,17 @@ class _Timed:
         if _profile is not None:
             self.e1.record()
             _profile.append((self.name, self.e0, self.e1, self.flops))
+            _profile.extend(self.pe)
         return False
 
 
 def edge_flops(B, N, F, H0, H1, H2):
     """Algorithmic forward FLOPs of one fused edge call (first layer factorised)."""
     return 4.0 * B * N * F * H0 + 2.0 * B * N * N * (H0 * H1 + H1 * H2)
+
+
+def _pair_flops(B, N, Ha, Hb):
+    return 2.0 * B * N * N * Ha * Hb
 
 
 def _rows(t):
@@ -165,7 +181,8 @@ class EdgeAggFn(torch.autograd.Function):
         m = None if mask is None else mask.reshape(B, N).contiguous()
         ws_ = [t.contiguous() for t in (w0, b0, w1, b1, w2, b2)]
         seed = next_seed() if p_drop > 0 else 0
-        with _Timed("edge_fwd", edge_flops(B, N, F, H0, H1, H2)):
+        with _Timed("edge_fwd", edge_flops(B, N, F, H0, H1, H2),
+                    [(1, "edge_tc_fwd_kernel", _pair_flops(B, N, H0, H1) + _pair_flops(B, N, H1, H2))]):
             _lib.check(L.mpg_edge_fwd(_lib.ptr(x3), ldx, _lib.ptr(m), *[_lib.ptr(t) for t in ws_], B, N, F, H0, H1,
                                       H2, int(ef_mode), int(nd), int(mean), float(alpha), float(p_drop), seed,
                                       _seed_ptr(), _PRECISION, ws.data_ptr(), ws_bytes, _lib.ptr(agg),
@@ -186,7 +203,9 @@ class EdgeAggFn(torch.autograd.Function):
         ws = torch.empty(ws_bytes, device=dagg.device, dtype=torch.uint8)
         dx = torch.empty(B, N, F, device=dagg.device, dtype=torch.float32)
         grads = [torch.zeros_like(t) for t in (w0, b0, w1, b1, w2, b2)]
-        with _Timed("edge_bwd", 2.0 * edge_flops(B, N, F, H0, H1, H2)):
+        with _Timed("edge_bwd", 2.0 * edge_flops(B, N, F, H0, H1, H2),
+                    [(2, "edge_tc_bwd_chain_kernel", 2 * _pair_flops(B, N, H0, H1) + _pair_flops(B, N, H1, H2)),
+                     (3, "edge_tc_bwd_dw2_kernel", _pair_flops(B, N, H1, H2))]):
             _lib.check(L.mpg_edge_bwd(_lib.ptr(x3), ldx, _lib.ptr(m),
                                       *[_lib.ptr(t) for t in (w0, b0, w1, b1, w2, b2)], B, N, F, H0, H1, H2, ef_mode,
                                       nd, mean, alpha, p, seed, sptr, prec, ws.data_ptr(), ws_bytes, _lib.ptr(dagg),

@@ -134,6 +134,49 @@ class GANTrainer:
         """One critic + one generator update (train.py:841-878 with num_critic = num_gen = 1)."""
         return self.train_D(data, labels), self.train_G(labels)
 
+    # -- whole-step CUDA graph (SURVEY 8f rank 1) ---------------------------------------------------
+    def capture(self, data, labels, warmup=3):
+        """Captures train_D + train_G (kernels, NCCL all-reduces, RMSprop) into one CUDA graph.
+
+        Noise is drawn inside the graph (torch's graph-safe Philox state); dropout masks change on
+        every replay because the kernels add a device-resident counter, bumped in-graph, to their
+        seeds.  Returns self; afterwards ``step_graphed`` replays the graph on new batches.
+        """
+        dev = data.device
+        self._static_data = data.clone()
+        self._static_labels = labels.clone()
+        self._seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        ops.set_device_seed(self._seed_dev)
+
+        def body():
+            self._seed_dev.add_(0x9E3779B97F4A7C15 >> 1)
+            return self.step(self._static_data, self._static_labels)
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        from . import _lib
+        n0 = _lib.lib().mpg_launch_count()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._static_losses = body()
+        self.launches_per_step = int(_lib.lib().mpg_launch_count() - n0)  # our kernels inside one replay
+        return self
+
+    def step_graphed(self, data=None, labels=None):
+        """Replays the captured step; ``data``/``labels`` (host or device) are copied into the graph's
+        static input buffers first (``non_blocking`` so pinned host batches stream in)."""
+        if data is not None:
+            self._static_data.copy_(data, non_blocking=True)
+        if labels is not None:
+            self._static_labels.copy_(labels, non_blocking=True)
+        self._graph.replay()
+        return self._static_losses
+
 
 def synthetic_jets(B, N, device="cuda", generator=None, all_real=False):
     """SURVEY 8(d) synthetic batch: features U(-.5,.5) zeroed on padded rows, 4th channel mask-0.5;
