@@ -1,0 +1,141 @@
+"""CPU-side checks (no GPU): the C-ABI library builds/loads and exports every symbol the public header
+declares, the drop-in modules keep the reference's constructor surface and state_dict layout, and
+nothing silently falls back to PyTorch on CPU."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "mpgan_b200.h")
+
+
+def _declared():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mpg_[a-z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def libpath():
+    from mpgan_b200 import build
+    return build.build()
+
+
+def test_header_symbols_exported(libpath):
+    lib = ctypes.CDLL(libpath)
+    names = _declared()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/mpgan_b200.h but not exported"
+    lib.mpg_version.restype = ctypes.c_int
+    assert lib.mpg_version() >= 100
+    lib.mpg_features.restype = ctypes.c_int
+    assert lib.mpg_features() & 1, "tcgen05 edge forward must be compiled in"
+    assert lib.mpg_features() & 2, "tcgen05 edge backward must be compiled in"
+
+
+def test_binding_table_matches_header(libpath):
+    from mpgan_b200 import _lib
+    assert sorted(_lib.exported_symbols()) == _declared()
+
+
+def test_library_has_no_torch_dependency(libpath):
+    out = subprocess.run(["ldd", libpath], capture_output=True, text=True).stdout
+    assert "torch" not in out and "c10" not in out, out
+
+
+def test_sass_is_blackwell_native(libpath):
+    """The edge kernels must be tcgen05 / TMEM / bulk-async code, not recompiled mma.sync."""
+    cuobjdump = "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", libpath], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in sass, "no tcgen05.mma in SASS"
+    assert "LDTM" in sass, "no tcgen05.ld in SASS"
+    assert "UBLKCP" in sass, "no bulk-async (TMA) copy in SASS"
+
+
+def test_state_dict_layout_matches_reference(golden):
+    from mpgan_b200 import presets
+    man = golden("mp_state_manifest.pt")
+    G, D = presets.mp_generator(), presets.mp_discriminator()
+    assert {k: tuple(v.shape) for k, v in G.state_dict().items()} == man["G"]
+    assert {k: tuple(v.shape) for k, v in D.state_dict().items()} == man["D"]
+    assert sum(p.numel() for p in G.parameters()) == 361123
+    assert sum(p.numel() for p in D.parameters()) == 355617
+    G.load_state_dict(golden("mp_g_weights.pt"), strict=True)
+    D.load_state_dict(golden("mp_d_seed4_weights.pt"), strict=True)
+
+
+def test_gapt_and_spectral_norm_layouts(golden):
+    from mpgan_b200 import LinearNet, presets
+    g = golden("gapt.pt")
+    for name in ("sab", "isab"):
+        GG = presets.gapt_generator(use_isab=name == "isab")
+        GD = presets.gapt_discriminator(use_isab=name == "isab")
+        GG.load_state_dict(g[name]["sdG"], strict=True)
+        GD.load_state_dict(g[name]["sdD"], strict=True)
+    sn = golden("spectral_norm.pt")
+    net = LinearNet([24, 16], input_size=10, output_size=4, final_linear=True, spectral_norm=True)
+    net.load_state_dict(sn["sd0"], strict=True)
+    assert not net.net[0].module.weight_u.requires_grad and net.net[0].module.weight_bar.requires_grad
+    assert "net.2.weight" in net.state_dict()  # final linear layer is not wrapped (reference :65-68)
+
+
+def test_same_seed_same_init_as_reference_layout():
+    """nn.Linear containers consume the RNG like the reference, so equal seeds give equal weights."""
+    from mpgan_b200 import presets
+    torch.manual_seed(4)
+    a = presets.mp_discriminator().state_dict()
+    torch.manual_seed(4)
+    b = presets.mp_discriminator().state_dict()
+    assert all(torch.equal(a[k], b[k]) for k in a)
+
+
+def test_no_cpu_fallback():
+    from mpgan_b200 import presets
+    G = presets.mp_generator()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        G(torch.zeros(2, 30, 32), torch.ones(2, 1))
+    D = presets.gapt_discriminator()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        D(torch.zeros(2, 30, 4))
+    from mpgan_b200 import ops
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.linear(torch.zeros(4, 8), torch.zeros(3, 8), torch.zeros(3), True, 0.2, 0.0)
+
+
+def test_unsupported_options_fail_loudly():
+    from mpgan_b200 import LinearNet, MPLayer, presets
+    with pytest.raises(NotImplementedError):
+        LinearNet([8], input_size=4, batch_norm=True)
+    with pytest.raises(NotImplementedError):
+        MPLayer(3, [96, 160, 192], [256, 256], 32, fully_connected=False)
+    with pytest.raises(NotImplementedError):
+        MPLayer(3, [96, 160, 192], [256, 256], 32, clabels=1)
+    with pytest.raises(NotImplementedError):
+        presets.mp_generator(mask_learn=True)
+    with pytest.raises(NotImplementedError):
+        presets.gapt_generator(layer_norm_gen=True)
+
+
+def test_pair_feature_modes():
+    from mpgan_b200 import MPLayer
+    assert MPLayer(5, [16, 24, 32], [40], 6)._ef_mode == 0
+    l = MPLayer(5, [16, 24, 32], [40], 6, pos_diffs=True, all_ef=True, delta_r=False)
+    assert (l._ef_mode, l._nd, l.num_ef) == (1, 5, 1)
+    l = MPLayer(5, [16, 24, 32], [40], 6, pos_diffs=True, all_ef=False, delta_r=True, delta_coords=True)
+    assert (l._ef_mode, l._nd, l.num_ef) == (3, 2, 3)
+    assert l.fe.net[0].weight.shape == (16, 13)
+
+
+def test_flops_model_matches_survey():
+    import bench
+    fg, fd = bench.net_flops(30)
+    assert abs(fg / 1e6 - 181.9) < 0.1 and abs(fd / 1e6 - 181.6) < 0.1
+    assert abs(bench.step_flops(30) / 1e9 - 2.180) < 0.001
+    assert abs(bench.step_flops(150) / 1e9 - 50.71) < 0.01
