@@ -97,26 +97,35 @@ __host__ __device__ __forceinline__ bool drop_keep(const DropCfg& d, uint32_t st
 }
 
 // ---- edge-network dropout, p == 0.5 ---------------------------------------------------------------
-// One Philox draw (128 bits) covers one quarter of the columns of ALL three fe layers of a pair row:
-// layer l (width H_l) column c lies in quarter q = c / (H_l/4) at index i = c % (H_l/4); its keep bit is
-// bit (off_l + i) of draw(pair, q), off = (0, H0/4, H0/4 + H1/4).  This is the layout the tcgen05
-// kernels consume (thread = one row x one column quarter => one draw per thread and step); the generic
-// kernel evaluates the same function element-wise.  Needs H_l % 4 == 0 and (H0+H1+H2)/4 <= 128.
+// The tcgen05 kernels give one thread one pair row x one column "quarter" q of every fe layer, where
+// quarter q is the set of 8-column chunks 4c + q (columns 32c + 8q + [0, 8), c = 0, 1, ...); layer 2 is
+// handled as two halves of H2/2 columns with the same chunking inside each half.  Element i = 8c + e of
+// a thread's slice is column 32c + 8q + e.  Two Philox draws per (pair, quarter) cover the slices:
+// draw 0 -> layer 0 (consumed when the H0 tile is built, two pipeline steps before the rest), draw 1 ->
+// words x,y: layer 1; word z: layer 2 low half; word w: high half.  Inside a 32-bit word, element i
+// uses bit edge_drop_bitpos(i & 31): the order in which byte-permutes with sign replication (PRMT)
+// turn a word into packed bf16x2 / fp32 keep masks.  The generic kernel evaluates the same function
+// element-wise.
 __host__ __device__ __forceinline__ bool edge_drop_packed_ok(int H0, int H1, int H2) {
-  return (H0 % 4 == 0) && (H1 % 4 == 0) && (H2 % 4 == 0) && (H0 + H1 + H2) / 4 <= 128;
+  return (H0 % 32 == 0) && (H1 % 32 == 0) && (H2 % 64 == 0) && H0 / 4 <= 128 && H1 / 4 <= 64 && H2 / 8 <= 32;
 }
-__host__ __device__ __forceinline__ u4 edge_drop_bits(uint64_t seed, uint64_t pair, uint32_t quarter) {
-  return philox4x32_10((uint32_t)pair, (uint32_t)(pair >> 32), 0xED6E0000u | quarter, 0u, (uint32_t)seed,
+__host__ __device__ __forceinline__ u4 edge_drop_bits(uint64_t seed, uint64_t pair, uint32_t quarter, uint32_t draw) {
+  return philox4x32_10((uint32_t)pair, (uint32_t)(pair >> 32), 0xED6E0000u | quarter, draw, (uint32_t)seed,
                        (uint32_t)(seed >> 32));
+}
+__host__ __device__ __forceinline__ uint32_t edge_drop_bitpos(int e) {   // e in [0, 32)
+  return 8u * (2u * ((uint32_t)(e >> 1) & 1u) + ((uint32_t)e & 1u)) + 7u - (uint32_t)(e >> 2);
 }
 __host__ __device__ __forceinline__ bool edge_drop_keep(uint64_t seed, uint64_t pair, int layer, int col, int H0,
                                                         int H1, int H2) {
-  const int w = (layer == 0 ? H0 : (layer == 1 ? H1 : H2)) / 4;
-  const int off = layer == 0 ? 0 : (layer == 1 ? H0 / 4 : (H0 + H1) / 4);
-  const int b = off + col % w;
-  const u4 r = edge_drop_bits(seed, pair, (uint32_t)(col / w));
-  const uint32_t word = (b >> 5) == 0 ? r.x : ((b >> 5) == 1 ? r.y : ((b >> 5) == 2 ? r.z : r.w));
-  return (word >> (b & 31)) & 1u;
+  const int cc = layer == 2 ? col % (H2 / 2) : col;      // column inside the slice's tile (half)
+  const int q = (cc >> 3) & 3;
+  const int i = 8 * (cc >> 5) + (cc & 7);
+  const uint32_t draw = layer == 0 ? 0u : 1u;
+  const int wsel = layer == 2 ? 2 + col / (H2 / 2) : (i >> 5);
+  const u4 r = edge_drop_bits(seed, pair, (uint32_t)q, draw);
+  const uint32_t word = wsel == 0 ? r.x : (wsel == 1 ? r.y : (wsel == 2 ? r.z : r.w));
+  return (word >> edge_drop_bitpos(i & 31)) & 1u;
 }
 
 __device__ __forceinline__ float lrelu(float x, float a) { return x > 0.f ? x : a * x; }

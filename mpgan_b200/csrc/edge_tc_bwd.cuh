@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_bwd_kernel(TcArgs t) {
   }
 
   float Preg[Q0];
-  uint32_t dAggp[Q2 / 2];       // bf16x2: dAgg[r][q*48 + 2i], [.. + 2i + 1]
+  uint32_t dAggp[Q2 / 2];       // bf16x2 pairs of dAgg[r][h*96 + q*24 + ..], h = 0, 1
   float dPacc[MODE == BWD_CHAIN ? Q0 : 1];
   float db2acc0 = 0.f, db2acc1 = 0.f;
   int cur_tile = -1, r = 0, jet = 0;
@@ -126,9 +126,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_bwd_kernel(TcArgs t) {
   auto flush_dP = [&]() {
     if constexpr (MODE == BWD_CHAIN) {
       if (cur_tile >= 0 && valid) {
-        float* dst = a.dP + (size_t)r * K0 + q * Q0;
+        float* dst = a.dP + (size_t)r * K0 + q * 8;
 #pragma unroll
-        for (int c = 0; c < Q0; ++c) atomicAdd(dst + c, dPacc[c]);
+        for (int c = 0; c < Q0; ++c) atomicAdd(dst + 32 * (c >> 3) + (c & 7), dPacc[c]);
       }
     }
   };
@@ -139,18 +139,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_bwd_kernel(TcArgs t) {
     valid = r < BN;
     const int rc = valid ? r : BN - 1;
     jet = rc / a.N;
-    const float4* p = reinterpret_cast<const float4*>(a.P + (size_t)rc * K0 + q * Q0);
+    // column ownership: chunks 4c + q, i.e. columns 32c + 8q + [0, 8) (edge_tc_common.cuh)
 #pragma unroll
     for (int c = 0; c < Q0 / 4; ++c) {
-      const float4 v = __ldg(p + c);
+      const float4 v = __ldg(reinterpret_cast<const float4*>(a.P + (size_t)rc * K0 + q * 8 + 32 * (c >> 1) + 4 * (c & 1)));
       Preg[4 * c] = v.x; Preg[4 * c + 1] = v.y; Preg[4 * c + 2] = v.z; Preg[4 * c + 3] = v.w;
     }
-    const float4* dg = reinterpret_cast<const float4*>(a.dagg + (size_t)rc * N2 + q * Q2);
 #pragma unroll
-    for (int c = 0; c < Q2 / 4; ++c) {
-      const float4 v = __ldg(dg + c);
-      dAggp[2 * c] = pack_bf16(v.x, v.y);
-      dAggp[2 * c + 1] = pack_bf16(v.z, v.w);
+    for (int h = 0; h < 2; ++h) {   // this thread's layer-2 columns: h*96 + 32c + 8q + [0, 8)
+      const float* dg = a.dagg + (size_t)rc * N2 + h * NH2 + q * 8;
+#pragma unroll
+      for (int c = 0; c < QH / 4; ++c) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(dg + 32 * (c >> 1) + 4 * (c & 1)));
+        dAggp[h * (QH / 2) + 2 * c] = pack_bf16(v.x, v.y);
+        dAggp[h * (QH / 2) + 2 * c + 1] = pack_bf16(v.z, v.w);
+      }
     }
     if constexpr (MODE == BWD_CHAIN) {
 #pragma unroll
@@ -166,16 +169,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_bwd_kernel(TcArgs t) {
     if (tile != cur_tile) load_tile(tile);
     const uint64_t pair = (uint64_t)(valid ? r : 0) * a.N + s;
     const float mfac = valid ? (a.mask ? a.mask[(size_t)jet * a.N + s] : 1.f) * a.out_scale : 0.f;
-    u4 bits{0, 0, 0, 0};
-    if (DROP) bits = edge_drop_bits(drop.seed, pair, q);
+    uint32_t k0w = 0;           // keep words (common.cuh edge_drop_*): layer 0
+    u4 bits{0, 0, 0, 0};        // x,y: layer 1; z / w: layer 2 low / high half
+    if (DROP) {
+      k0w = edge_drop_bits(drop.seed, pair, q, 0).x;
+      bits = edge_drop_bits(drop.seed, pair, q, 1);
+    }
 
     // ---- H0 tile; remember the sign bits of the 24 columns this thread owns -----------------------------
     uint32_t pos0 = 0;
     {
-      const float4* qp = reinterpret_cast<const float4*>(a.Q + ((size_t)jet * a.N + s) * K0 + q * Q0);
+      const float4* qp = reinterpret_cast<const float4*>(a.Q + ((size_t)jet * a.N + s) * K0 + q * 8);
 #pragma unroll
       for (int c8 = 0; c8 < Q0 / 8; ++c8) {
-        const float4 q0 = __ldg(qp + 2 * c8), q1 = __ldg(qp + 2 * c8 + 1);
+        const float4 q0 = __ldg(qp + 8 * c8), q1 = __ldg(qp + 8 * c8 + 1);
         float v[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -183,10 +190,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_bwd_kernel(TcArgs t) {
           float x = v[e] + Preg[le];
           if (x > 0.f) pos0 |= 1u << le;
           x = fmaxf(x, a.alpha * x);
-          if (DROP) x = apply_keep(x, keep_mask(bits, le));
+          if (DROP) x = apply_keep(x, keep_one(k0w, le));
           v[e] = x;
         }
-        st_chunk(sA0 + swz_chunk(row, q * Q0 + c8 * 8, A_BLK), v);
+        st_chunk(sA0 + swz_chunk(row, 32 * c8 + 8 * q, A_BLK), v);
       }
       if (MODE == BWD_DW2 && q == 0) {   // DW2 builds H0 inside the G2 region: bias columns every step
         st_ones_chunk(sA0 + swz_chunk(row, 96, A_BLK));
@@ -204,26 +211,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_bwd_kernel(TcArgs t) {
     // ---- e1: H1 tile, sign bits of this thread's 40 columns ----------------------------------------------
     uint32_t pos1[2] = {0, 0};
     {
+      float v[Q1];
+      tmem_ld8x5(tmem + tlane + RS_COL + q * 8, v);
 #pragma unroll
-      for (int c0 = 0; c0 < Q1; c0 += 16) {
-        const int n = (Q1 - c0) >= 16 ? 16 : 8;   // static after unrolling
-        float v[16];
-        if (n == 16) tmem_ld16(tmem + tlane + RS_COL + q * Q1 + c0, v);
-        else tmem_ld8(tmem + tlane + RS_COL + q * Q1 + c0, v);
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          if (e < n) {
-            const int le = c0 + e;
-            float x = v[e];
-            if (x > 0.f) pos1[le >> 5] |= 1u << (le & 31);
-            x = fmaxf(x, a.alpha * x);
-            if (DROP) x = apply_keep(x, keep_mask(bits, Q0 + le));
-            v[e] = x;
-          }
-        }
-        st_chunk(sA1 + swz_chunk(row, q * Q1 + c0, A_BLK), v);
-        if (n == 16) st_chunk(sA1 + swz_chunk(row, q * Q1 + c0 + 8, A_BLK), v + 8);
+      for (int le = 0; le < Q1; ++le) {
+        float x = v[le];
+        if (x > 0.f) pos1[le >> 5] |= 1u << (le & 31);
+        x = fmaxf(x, a.alpha * x);
+        if (DROP) x = apply_keep(x, keep_one(le < 32 ? bits.x : bits.y, le & 31));
+        v[le] = x;
       }
+#pragma unroll
+      for (int c = 0; c < Q1 / 8; ++c) st_chunk(sA1 + swz_chunk(row, 32 * c + 8 * q, A_BLK), v + 8 * c);
       // constant bias columns of the H1 tile: DW2 never overwrites them, CHAIN reuses the region for G2/G1
       if ((MODE == BWD_CHAIN || it == 0) && q == 1) {
         st_ones_chunk(sA1 + swz_chunk(row, 160, A_BLK));
@@ -240,20 +239,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_bwd_kernel(TcArgs t) {
     });
     // ---- e2': G2 = dAgg * m * f'(D2) * keep2  (divided by s, see header) -> bf16 tile --------------------
 #pragma unroll
-    for (int c16 = 0; c16 < Q2 / 16; ++c16) {
-      float v[16];
-      tmem_ld16(tmem + tlane + RS_COL + q * Q2 + c16 * 16, v);
+    for (int h = 0; h < 2; ++h) {
+      float v[QH];
+      tmem_ld8x3(tmem + tlane + RS_COL + h * NH2 + q * 8, v);
 #pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const int le = c16 * 16 + e;
-        const uint32_t pk = dAggp[le >> 1];
-        const float dg = __uint_as_float((le & 1) ? (pk & 0xFFFF0000u) : (pk << 16));
+      for (int e = 0; e < QH; ++e) {
+        const uint32_t pk = dAggp[h * (QH / 2) + (e >> 1)];
+        const float dg = __uint_as_float((e & 1) ? (pk & 0xFFFF0000u) : (pk << 16));
         float gval = dg * mfac * (v[e] > 0.f ? 1.f : a.alpha);
-        if (DROP) gval = apply_keep(gval, keep_mask(bits, Q0 + Q1 + le));
+        if (DROP) gval = apply_keep(gval, keep_one(h ? bits.w : bits.z, e));
         v[e] = gval;
       }
-      st_chunk(sG2 + swz_chunk(row, q * Q2 + c16 * 16, A_BLK), v);
-      st_chunk(sG2 + swz_chunk(row, q * Q2 + c16 * 16 + 8, A_BLK), v + 8);
+#pragma unroll
+      for (int c8 = 0; c8 < QH / 8; ++c8) st_chunk(sG2 + swz_chunk(row, h * NH2 + 32 * c8 + 8 * q, A_BLK), v + c8 * 8);
     }
 
     if constexpr (MODE == BWD_DW2) {
@@ -291,23 +289,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_bwd_kernel(TcArgs t) {
         }
       });
       // ---- e3: G1 = dH1 * f'(D1) * keep1 (divided by s) -> bf16 tile over the G2 tile --------------------
+      {
+        float v[Q1];
+        tmem_ld8x5(tmem + tlane + RS_COL + q * 8, v);
 #pragma unroll
-      for (int c0 = 0; c0 < Q1; c0 += 16) {
-        const int n = (Q1 - c0) >= 16 ? 16 : 8;   // static after unrolling
-        float v[16];
-        if (n == 16) tmem_ld16(tmem + tlane + RS_COL + q * Q1 + c0, v);
-        else tmem_ld8(tmem + tlane + RS_COL + q * Q1 + c0, v);
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          if (e < n) {
-            const int le = c0 + e;
-            float gval = v[e] * (((pos1[le >> 5] >> (le & 31)) & 1u) ? 1.f : a.alpha);
-            if (DROP) gval = apply_keep(gval, keep_mask(bits, Q0 + le));
-            v[e] = gval;
-          }
+        for (int le = 0; le < Q1; ++le) {
+          float gval = v[le] * (((pos1[le >> 5] >> (le & 31)) & 1u) ? 1.f : a.alpha);
+          if (DROP) gval = apply_keep(gval, keep_one(le < 32 ? bits.x : bits.y, le & 31));
+          v[le] = gval;
         }
-        st_chunk(sA1 + swz_chunk(row, q * Q1 + c0, A_BLK), v);
-        if (n == 16) st_chunk(sA1 + swz_chunk(row, q * Q1 + c0 + 8, A_BLK), v + 8);
+#pragma unroll
+        for (int c = 0; c < Q1 / 8; ++c) st_chunk(sA1 + swz_chunk(row, 32 * c + 8 * q, A_BLK), v + 8 * c);
       }
       const bool acc_flag = !first_mma;
       sync_issue([&]() {
@@ -327,16 +319,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_bwd_kernel(TcArgs t) {
       first_mma = false;
       // ---- e4: G0 = dH0 * s * f'(pre0) * keep0 -> dP (registers), dQ (red.global) ---------------------------
       {
-        float* dq = a.dQ + ((size_t)jet * a.N + s) * K0 + q * Q0;
+        float* dq = a.dQ + ((size_t)jet * a.N + s) * K0 + q * 8;
         float v[Q0];
-        tmem_ld_cols<Q0>(tmem + tlane + RS_COL + q * Q0, v);
+        tmem_ld8x3(tmem + tlane + RS_COL + q * 8, v);
 #pragma unroll
         for (int e = 0; e < Q0; ++e) {
           float gval = v[e] * sdrop * (((pos0 >> e) & 1u) ? 1.f : a.alpha);
-          if (DROP) gval = apply_keep(gval, keep_mask(bits, e));
+          if (DROP) gval = apply_keep(gval, keep_one(k0w, e));
           if (valid) {
             dPacc[e] += gval;
-            if (gval != 0.f) atomicAdd(dq + e, gval);
+            if (gval != 0.f) atomicAdd(dq + 32 * (e >> 3) + (e & 7), gval);
           }
         }
       }

@@ -1,0 +1,262 @@
+// Shared pieces of the tcgen05 / TMEM edge-network kernels (sm_100a): problem constants, shared-memory
+// layout of the swizzled bf16 tiles, PTX wrappers (mbarrier, bulk-async copies, tcgen05 alloc / mma /
+// commit / ld), UMMA descriptors and the weight-image kernel.  Included by edge_tc.cu inside its
+// anonymous namespace.
+#pragma once
+
+constexpr int K0 = 96, N1 = 160, N2 = 192;
+constexpr int TILE = 128;
+constexpr int NQ = 4;                            // column quarters (warps sharing a TMEM lane group)
+constexpr int Q0 = K0 / NQ, Q1 = N1 / NQ, Q2 = N2 / NQ;   // 24, 40, 48 columns per thread
+constexpr int KSTEPS1 = K0 / 16 + 1;             // + bias step
+constexpr int KSTEPS2 = N1 / 16 + 1;
+constexpr uint32_t W1_BLK = N1 * 128;            // bytes of one 64-wide K block of W1 (rows = out features)
+constexpr uint32_t W2_BLK = N2 * 128;
+constexpr uint32_t A_BLK = TILE * 128;           // one 64-wide K block of an activation tile
+constexpr uint32_t W1_BYTES = 2 * W1_BLK;        // K = 128 (96 + bias step, padded)
+constexpr uint32_t W2_BYTES = 3 * W2_BLK;        // K = 192 (160 + bias step, padded)
+constexpr uint32_t H0_BYTES = 2 * A_BLK;
+constexpr uint32_t H1_BYTES = 3 * A_BLK;
+constexpr uint32_t OFF_W1 = 0;
+constexpr uint32_t OFF_W2 = OFF_W1 + W1_BYTES;   // 40960
+constexpr uint32_t OFF_H0 = OFF_W2 + W2_BYTES;   // 114688
+constexpr uint32_t OFF_H1 = OFF_H0 + H0_BYTES;   // 147456
+constexpr uint32_t OFF_BAR = OFF_H1 + H1_BYTES;  // 196608
+constexpr uint32_t SMEM_BYTES = OFF_BAR + 128 + 1024;   // + barriers + alignment slack
+constexpr int NTHREADS = 128 * NQ;
+constexpr uint32_t TMEM_COLS = 512, D1_COL = 0, D2_COL = 256;
+
+// ---------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded spin: a protocol bug must trap, never hang the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 22)) {
+#ifdef MPG_DEBUG_BARRIERS
+      printf("mbarrier timeout: block %d thread %d barrier +%u parity %u\n", blockIdx.x, threadIdx.x, bar & 0xFFu, parity);
+#endif
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 operands, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, 128-byte swizzle: 8-row groups 1024 B apart, descriptor version 1 (sm_100)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// the same descriptor split in two words: the high word is a constant, the low word carries the address
+constexpr uint32_t UMMA_DESC_HI = 64u | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+// Warp-collective forms: executed by ALL lanes of a converged warp; one elected lane (always the same
+// one for a full mask) issues.  tcgen05.mma / commit / bulk copies take warp-uniform operands, and from a
+// `lane == 0` branch ptxas wraps each of them in an elect-and-loop sequence that costs ~100 cycles per MMA.
+__device__ __forceinline__ void umma_bf16_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(UMMA_DESC_HI)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_elect(uint32_t bar, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_elect(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+// hides a value from loop-invariant code motion
+__device__ __forceinline__ void opaque(uint32_t& v) { asm volatile("" : "+r"(v)); }
+__host__ __device__ constexpr uint32_t umma_idesc(int N) {
+  // c = f32 (1 << 4), a = b = bf16 (1 << 7, 1 << 10), K-major A and B, N >> 3 at bit 17, M >> 4 at bit 24
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
+}
+// 16 / 8 consecutive fp32 columns of this thread's TMEM lane, into v[o..]
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+// NC (multiple of 8) columns starting at taddr
+template <int NC>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float* v) {
+#pragma unroll
+  for (int c = 0; c + 16 <= NC; c += 16) tmem_ld16(taddr + c, v + c);
+  if (NC % 16) tmem_ld8(taddr + (NC / 16) * 16, v + (NC / 16) * 16);
+}
+
+// Column ownership inside the tcgen05 kernels: thread (tile row, quarter q) owns the 8-column chunks
+// 4c + q, c = 0, 1, ... of every tile / accumulator (columns 32c + 8q + [0, 8)).  A chunk is one 16-byte
+// unit of the 128-byte-swizzled bf16 tiles, so all of a thread's tile stores are [x0 | x1] + constant.
+// tmem_ld8xK: K such chunks (fp32) from TMEM with ONE wait; every destination register is an output of
+// the asm statement that also holds the wait, so no consumer can be scheduled ahead of it.
+__device__ __forceinline__ void tmem_ld8x5(uint32_t taddr, float* v) {
+  uint32_t r[40];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%40];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%8,%9,%10,%11,%12,%13,%14,%15}, [%41];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%16,%17,%18,%19,%20,%21,%22,%23}, [%42];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%24,%25,%26,%27,%28,%29,%30,%31}, [%43];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%32,%33,%34,%35,%36,%37,%38,%39}, [%44];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39])
+      : "r"(taddr + 0), "r"(taddr + 32), "r"(taddr + 64), "r"(taddr + 96), "r"(taddr + 128)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 40; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld8x3(uint32_t taddr, float* v) {
+  uint32_t r[24];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%24];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%8,%9,%10,%11,%12,%13,%14,%15}, [%25];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%16,%17,%18,%19,%20,%21,%22,%23}, [%26];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23])
+      : "r"(taddr + 0), "r"(taddr + 32), "r"(taddr + 64)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 24; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+// byte offset of the 16-byte chunk holding columns [k, k+8) of `row` inside a swizzled tile whose
+// 64-wide K blocks are blk_bytes apart
+__device__ __forceinline__ uint32_t swz_chunk(uint32_t row, uint32_t k, uint32_t blk_bytes) {
+  const uint32_t blk = k >> 6, chunk = (k & 63) >> 3;
+  return blk * blk_bytes + row * 128 + ((chunk ^ (row & 7)) << 4);
+}
+// store 8 consecutive columns (one 16-byte chunk) of a row as bf16
+__device__ __forceinline__ void st_chunk(uint32_t addr, const float* v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(pack_bf16(v[0], v[1])),
+               "r"(pack_bf16(v[2], v[3])), "r"(pack_bf16(v[4], v[5])), "r"(pack_bf16(v[6], v[7])));
+}
+__device__ __forceinline__ void st_ones_chunk(uint32_t addr) {   // {1, 1, 0, 0, 0, 0, 0, 0}
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%2,%2};" ::"r"(addr), "r"(0x3F803F80u), "r"(0u));
+}
+__device__ __forceinline__ void st_zero_chunk(uint32_t addr) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(addr), "r"(0u));
+}
+// keep bit `b` (0..127) of a 128-bit Philox draw as an all-ones / all-zeros word
+__device__ __forceinline__ uint32_t keep_mask(const u4& bits, int b) {
+  const uint32_t w = (b >> 5) == 0 ? bits.x : ((b >> 5) == 1 ? bits.y : ((b >> 5) == 2 ? bits.z : bits.w));
+  int32_t m;
+  asm("bfe.s32 %0, %1, %2, 1;" : "=r"(m) : "r"(w), "r"(b & 31));
+  return (uint32_t)m;
+}
+__device__ __forceinline__ float apply_keep(float x, uint32_t mask) { return __uint_as_float(__float_as_uint(x) & mask); }
+
+struct TcArgs {
+  EdgeArgs a;
+  const uint8_t* w1img;   // pre-swizzled bf16 images (weight_image_kernel)
+  const uint8_t* w2img;
+  int num_tiles;
+  long long total_steps;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// weight image: img[n][k] (K-major, SW128) = bf16(scale * W[n][k]) for k < K, bias_hi / bias_lo at
+// k = K, K+1, zero elsewhere.
+// ---------------------------------------------------------------------------------------------------
+__global__ void weight_image_kernel(const float* __restrict__ W, const float* __restrict__ bias, int Nout, int K,
+                                    int Kpad, float scale, uint8_t* __restrict__ img) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Nout * Kpad) return;
+  const int n = idx / Kpad, k = idx % Kpad;
+  float v = 0.f;
+  if (k < K) v = W[(size_t)n * K + k] * scale;
+  else if (k == K) v = bias[n];
+  else if (k == K + 1) v = bias[n] - __bfloat162float(__float2bfloat16_rn(bias[n]));
+  const uint32_t off = (uint32_t)(k >> 6) * (uint32_t)Nout * 128u + (uint32_t)n * 128u +
+                       ((((uint32_t)(k & 63) >> 3) ^ ((uint32_t)n & 7u)) << 4) + (uint32_t)(k & 7) * 2u;
+  *reinterpret_cast<__nv_bfloat16*>(img + off) = __float2bfloat16_rn(v);
+}
+

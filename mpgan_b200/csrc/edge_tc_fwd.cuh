@@ -1,0 +1,376 @@
+// tcgen05 forward of the edge network (included by edge_tc.cu inside its anonymous namespace).
+//
+// Work unit ("step"): 128 receivers (rows r = b*N + i of the flattened node list) x one sender
+// index s of each row's own jet.  A CTA owns a contiguous range of (tile, s) steps and keeps the
+// running neighbour sum of its 128 receivers in registers, so the reduction over senders is a
+// plain in-thread add and the [B*N*N, hidden] tensors exist only as bf16 tiles in shared memory:
+//
+//   H0'[r,:] = g(P[r,:] + Q[jet(r)*N + s,:])                    g(v) = v + c|v| = lrelu(v) / sl
+//   D1       = H0' * (sl W1)^T  (tcgen05.mma, M=128 N=160 K=96+16)   fp32, TMEM, double buffered
+//   H1'      = g(D1)                                             bf16 tile (A operand)
+//   D2       = H1' * (sl W2)^T  (two N=96 halves, K=160+16)       fp32, TMEM
+//   acc[r,:] += mask[jet(r), s] * g(D2)                          fp32 registers; x sl at the flush
+//
+// c = (1-alpha)/(1+alpha), sl = (1+alpha)/2: leaky-relu costs ONE fma per element (|v| is a free
+// operand modifier) and its scale rides in the next layer's weight image.  The biases ride in an
+// extra K=16 step (constant-1 columns of the A tiles x bias_hi/bias_lo rows of the weight images).
+//
+// Pipeline.  16 epilogue warps (thread <-> TMEM lane = tile row, column quarter) plus one control
+// warpgroup: one lane issues every tcgen05.mma, another the bulk-async (TMA) copies of the weight
+// images and of the Q rows (a 4-stage shared-memory ring, so no thread waits on global memory per
+// step).  Registers are re-split with setmaxnreg (epilogue 120, control 32 per thread).  The tensor pipe executes   ... M2hi(s-1) | M1(s+1) | M2lo(s) | M2hi(s) | M1(s+2) ...  :
+// layer 1 runs one step ahead into a double-buffered D1, so the only serial dependency on the
+// epilogue warps -- E1(s): D1 -> H1' -- overlaps M1(s+1); E2lo/E2hi(s-1) and the H0' tile of step s+2
+// are produced under M2(s).  TMEM: D1a [0,160) D1b [160,320) D2lo [320,416) D2hi [416,512).
+//
+// Dropout (p = 0.5): Philox bits as laid out in common.cuh (edge_drop_*), applied to the packed bf16
+// words (layers 0/1) or to the mask multiplier (layer 2) through PRMT sign-replication masks; the 2x
+// scale of layers 0/1 is folded into the next weight image, the last one into the flush.
+
+constexpr int F_NEPI = 512;                  // epilogue threads
+constexpr int F_NTHR = F_NEPI + 128;         // + control warpgroup (warp 16: MMA issuer, warp 17: TMA loader)
+constexpr int F_REGS_EPI = 112, F_REGS_CTL = 32;   // setmaxnreg split of the 64K register file
+constexpr int F_QS = 4;                      // Q ring stages
+constexpr int F_QJ = 10;                     // jets a 128-row tile can span (N >= 15)
+constexpr uint32_t F_QROW = K0 * 4;          // bytes of one Q row
+constexpr uint32_t F_QSTAGE = F_QJ * F_QROW;
+constexpr uint32_t F_OFF_Q = OFF_H1 + H1_BYTES;            // 196608
+constexpr uint32_t F_OFF_BAR = F_OFF_Q + F_QS * F_QSTAGE;  // 211968
+constexpr uint32_t F_SMEM = F_OFF_BAR + 256 + 1024;
+constexpr uint32_t F_D1_COL = 0, F_D2LO_COL = 320, F_D2HI_COL = 416;
+constexpr int NH2 = N2 / 2;                  // 96: columns of one D2 half
+constexpr int QH = NH2 / NQ;                 // 24: columns of a D2 half owned by one thread
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+// keep mask (0xFFFF per kept bf16 lane) of the element pair (e, e+1), e even, of a 32-element slice
+__device__ __forceinline__ uint32_t keep_pair(uint32_t word, int e) {
+  return prmt(word << (e >> 2), 0u, ((e >> 1) & 1) ? 0xbbaau : 0x9988u);
+}
+// keep mask (all ones / zero) of element e of a 32-element slice
+__device__ __forceinline__ uint32_t keep_one(uint32_t word, int e) {
+  const int byte = 2 * ((e >> 1) & 1) + (e & 1);
+  return prmt(word << (e >> 2), 0u, 0x8888u + 0x1111u * (uint32_t)byte);
+}
+// g(v) = v + c|v|
+__device__ __forceinline__ float lrelu_g(float v, float c) { return fmaf(fabsf(v), c, v); }
+
+template <bool DROP>
+__global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
+  extern __shared__ uint8_t smem_raw[];
+  const EdgeArgs& a = t.a;
+  uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SW128 tiles need 1024-byte alignment
+  uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+  opaque(base);   // keep it in a register: every barrier / tile address below is base + constant
+  const uint32_t sW1 = base + OFF_W1, sW2 = base + OFF_W2, sH0 = base + OFF_H0, sH1 = base + OFF_H1,
+                 sQ = base + F_OFF_Q;
+  const uint32_t bar0 = base + F_OFF_BAR;
+  const uint32_t bar_w = bar0, bar_h0 = bar0 + 8, bar_d1 = bar0 + 16 /* [2] */, bar_h1 = bar0 + 32,
+                 bar_d2lo = bar0 + 40, bar_d2hi = bar0 + 48, bar_f2lo = bar0 + 56, bar_f2hi = bar0 + 64,
+                 bar_q = bar0 + 72 /* [F_QS] */, bar_qe = bar0 + 72 + 8 * F_QS /* [F_QS] */;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + F_OFF_BAR + 192);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long g0 = t.total_steps * blockIdx.x / gridDim.x;
+  const long long g1 = t.total_steps * (blockIdx.x + 1) / gridDim.x;
+  const int nsteps = (int)(g1 - g0);
+  const int N = a.N, BN = a.B * a.N;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(bar_h0, F_NEPI);
+    mbar_init(bar_d1, 1);
+    mbar_init(bar_d1 + 8, 1);
+    mbar_init(bar_h1, F_NEPI);
+    mbar_init(bar_d2lo, 1);
+    mbar_init(bar_d2hi, 1);
+    mbar_init(bar_f2lo, F_NEPI);
+    mbar_init(bar_f2hi, F_NEPI);
+    for (int i = 0; i < F_QS; ++i) {
+      mbar_init(bar_q + 8 * i, 1);
+      mbar_init(bar_qe + 8 * i, F_NEPI);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 16) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp >= 16) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(F_REGS_CTL));
+    // both roles run with all 32 lanes converged; single-thread instructions are elect-predicated
+    if (warp == 17 && nsteps > 0) {
+      // =============================== TMA loader ================================================
+      mbar_expect_tx_elect(bar_w, W1_BYTES + W2_BYTES);
+      bulk_g2s_elect(sW1, t.w1img, W1_BYTES, bar_w);
+      bulk_g2s_elect(sW2, t.w2img, W2_BYTES, bar_w);
+      int q_tile = (int)(g0 / N), q_s = (int)(g0 % N);   // step whose Q rows are loaded next
+      for (int it = 0; it < nsteps; ++it) {
+        // stage it % F_QS is free once every builder thread has read the rows of step it - F_QS
+        if (it >= F_QS) mbar_wait(bar_qe + 8 * (it & (F_QS - 1)), (it / F_QS - 1) & 1);
+        const int j0 = (q_tile * TILE) / N;
+        const int rl = min(q_tile * TILE + TILE - 1, BN - 1);
+        const int nj = rl / N - j0 + 1;
+        const uint32_t bar = bar_q + 8 * (it & (F_QS - 1));
+        const uint32_t dst = sQ + (uint32_t)(it & (F_QS - 1)) * F_QSTAGE;
+        mbar_expect_tx_elect(bar, (uint32_t)nj * F_QROW);
+        for (int j = 0; j < nj; ++j)
+          bulk_g2s_elect(dst + (uint32_t)j * F_QROW, a.Q + ((size_t)(j0 + j) * N + q_s) * K0, F_QROW, bar);
+        if (++q_s == N) { q_s = 0; ++q_tile; }
+      }
+    } else if (warp == 16 && nsteps > 0) {
+      // =============================== MMA issuer ================================================
+      // operand descriptors = per-tile base (low word) + compile-time offset, rebuilt at every use: the
+      // control warps run on 32 registers, so nothing may be hoisted out of the step loop (opaque())
+      constexpr uint32_t idesc1 = umma_idesc(N1), idesc2h = umma_idesc(NH2);
+      uint32_t lH0 = umma_desc_lo(sH0), lW1 = umma_desc_lo(sW1), lH1 = umma_desc_lo(sH1), lW2 = umma_desc_lo(sW2);
+      auto issue_m1 = [&](int it) {   // D1[it&1] = H0' * W1'^T
+        const uint32_t d = tmem + F_D1_COL + (uint32_t)(it & 1) * N1;
+        opaque(lH0); opaque(lW1);
+#pragma unroll
+        for (uint32_t ks = 0; ks < KSTEPS1; ++ks) {
+          const uint32_t blk = ks >> 2, j = ks & 3;
+          umma_bf16_lo(d, lH0 + ((blk * A_BLK + j * 32) >> 4), lW1 + ((blk * W1_BLK + j * 32) >> 4), idesc1, ks);
+        }
+        umma_commit_elect(bar_d1 + 8 * (it & 1));
+      };
+      auto issue_m2 = [&](uint32_t dcol, uint32_t wrow_off, uint32_t bar) {   // one N=96 half of D2
+        opaque(lH1); opaque(lW2);
+#pragma unroll
+        for (uint32_t ks = 0; ks < KSTEPS2; ++ks) {
+          const uint32_t blk = ks >> 2, j = ks & 3;
+          umma_bf16_lo(tmem + dcol, lH1 + ((blk * A_BLK + j * 32) >> 4),
+                       lW2 + ((blk * W2_BLK + wrow_off + j * 32) >> 4), idesc2h, ks);
+        }
+        umma_commit_elect(bar);
+      };
+
+      mbar_wait(bar_w, 0);
+      mbar_wait(bar_h0, 0);
+      tc_fence_after();
+      issue_m1(0);
+      for (int it = 0; it < nsteps; ++it) {
+        if (it + 1 < nsteps) {
+          mbar_wait(bar_h0, (it + 1) & 1);
+          tc_fence_after();
+          issue_m1(it + 1);
+        }
+        mbar_wait(bar_h1, it & 1);
+        if (it >= 1) mbar_wait(bar_f2lo, (it - 1) & 1);
+        tc_fence_after();
+        issue_m2(F_D2LO_COL, 0, bar_d2lo);
+        if (it >= 1) {
+          mbar_wait(bar_f2hi, (it - 1) & 1);
+          tc_fence_after();
+        }
+        issue_m2(F_D2HI_COL, NH2 * 128, bar_d2hi);
+      }
+    }
+  } else {
+    // =============================== epilogue warps ==============================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(F_REGS_EPI));
+    if (nsteps > 0) {
+    const int q = warp >> 2;                        // column quarter: chunks 4c + q (edge_tc_common.cuh)
+    const int row = (warp & 3) * 32 + lane;         // tile row == TMEM lane
+    const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)q * 8;
+    const float cg = (1.f - a.alpha) / (1.f + a.alpha);
+    DropCfg drop = a.drop;
+    if (DROP) resolve_seed(drop);
+    // this thread's two 16-byte positions inside a swizzled 128-byte tile row: chunk 4c + q of a tile
+    // lives at xs[c & 1] + (c >> 1) * A_BLK + <tile offset>
+    uint32_t xs[2];
+    xs[0] = base + (uint32_t)row * 128u + ((uint32_t)(q ^ (row & 7)) << 4);
+    xs[1] = base + (uint32_t)row * 128u + ((uint32_t)((4 + q) ^ (row & 7)) << 4);
+    opaque(xs[0]);
+    opaque(xs[1]);
+
+    // constant 1.0 columns of the bias K-step (cols 96,97 of H0'; 160,161 of H1'), zeros after them
+    if (q == 0) {
+      st_ones_chunk(sH0 + swz_chunk(row, 96, A_BLK));
+      st_zero_chunk(sH0 + swz_chunk(row, 104, A_BLK));
+    } else if (q == 1) {
+      st_ones_chunk(sH1 + swz_chunk(row, 160, A_BLK));
+      st_zero_chunk(sH1 + swz_chunk(row, 168, A_BLK));
+    }
+
+    float acc[2 * QH];
+#pragma unroll
+    for (int c = 0; c < 2 * QH; ++c) acc[c] = 0.f;
+    float Preg[Q0];
+
+    // ---- state of the H0' builder (step it+2) -----------------------------------------------------
+    int h_tile = (int)(g0 / N), h_s = (int)(g0 % N);
+    int h_loaded = -1, h_r = 0;
+    uint32_t h_qoff = 0;
+    auto build_h0 = [&](int it) {
+      if (h_tile != h_loaded) {
+        h_loaded = h_tile;
+        const int r = h_tile * TILE + row;
+        const int rc = r < BN ? r : BN - 1;
+        h_r = rc;
+        h_qoff = (uint32_t)(rc / N - (h_tile * TILE) / N) * F_QROW + (uint32_t)q * 32u;
+        const float* p = a.P + (size_t)rc * K0 + q * 8;
+#pragma unroll
+        for (int c = 0; c < Q0 / 8; ++c) {
+          const float4 v0 = __ldg(reinterpret_cast<const float4*>(p + 32 * c));
+          const float4 v1 = __ldg(reinterpret_cast<const float4*>(p + 32 * c + 4));
+          Preg[8 * c] = v0.x; Preg[8 * c + 1] = v0.y; Preg[8 * c + 2] = v0.z; Preg[8 * c + 3] = v0.w;
+          Preg[8 * c + 4] = v1.x; Preg[8 * c + 5] = v1.y; Preg[8 * c + 6] = v1.z; Preg[8 * c + 7] = v1.w;
+        }
+      }
+      uint32_t kw = 0;
+      if (DROP) kw = edge_drop_bits(drop.seed, (uint64_t)h_r * N + h_s, q, 0).x;
+      mbar_wait(bar_q + 8 * (it & (F_QS - 1)), (it / F_QS) & 1);
+      const uint32_t qa = sQ + (uint32_t)(it & (F_QS - 1)) * F_QSTAGE + h_qoff;
+#pragma unroll
+      for (int c = 0; c < Q0 / 8; ++c) {
+        float v[8];
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(qa + c * 128));
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(qa + c * 128 + 16));
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+          const float x0 = lrelu_g(v[e] + Preg[8 * c + e], cg), x1 = lrelu_g(v[e + 1] + Preg[8 * c + e + 1], cg);
+          w[e >> 1] = pack_bf16(x0, x1);
+          if (DROP) w[e >> 1] &= keep_pair(kw, 8 * c + e);
+        }
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(xs[c & 1] + OFF_H0 + (c >> 1) * A_BLK),
+                     "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]));
+      }
+      mbar_arrive(bar_qe + 8 * (it & (F_QS - 1)));   // Q rows consumed (generic-proxy reads are complete)
+      fence_async_smem();
+      mbar_arrive(bar_h0);
+      if (++h_s == N) { h_s = 0; ++h_tile; }
+    };
+
+    // ---- state of the accumulating epilogue (step it-1) -------------------------------------------
+    int e_tile = h_tile, e_s = h_s, e_row = 0, e_jet = 0;
+    bool e_valid = false;
+    float e_m = 0.f;
+    auto e_enter_tile = [&]() {
+      const int r = e_tile * TILE + row;
+      e_valid = r < BN;
+      e_row = e_valid ? r : BN - 1;
+      e_jet = e_row / N;
+    };
+    auto e_load_mask = [&]() { e_m = e_valid ? (a.mask ? __ldg(a.mask + (size_t)e_jet * N + e_s) : 1.f) : 0.f; };
+    const float fl_scale = a.out_scale * (DROP ? 2.f : 1.f) * 0.5f * (1.f + a.alpha);
+    auto flush = [&]() {
+      if (e_valid) {
+        float* dst = a.agg + (size_t)e_row * N2 + q * 8;
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int c = 0; c < QH / 8; ++c)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) atomicAdd(dst + h * NH2 + 32 * c + e, acc[h * QH + 8 * c + e] * fl_scale);
+      }
+#pragma unroll
+      for (int c = 0; c < 2 * QH; ++c) acc[c] = 0.f;
+    };
+    // one D2 half (this thread's 3 chunks): acc += m * keep * g(D2)
+    auto e2_half = [&](uint32_t dcol, float* ac, uint32_t kw) {
+      float v[QH];
+      tmem_ld8x3(tl + dcol, v);
+#pragma unroll
+      for (int e = 0; e < QH; ++e) {
+        float m = e_m;
+        if (DROP) m = __uint_as_float(__float_as_uint(m) & keep_one(kw, e));
+        ac[e] = fmaf(lrelu_g(v[e], cg), m, ac[e]);
+      }
+    };
+    uint32_t kz = 0, kwd = 0;   // layer-2 keep words of the step whose E1 ran last (consumed one iteration later)
+
+    e_enter_tile();
+    e_load_mask();
+    build_h0(0);
+    if (nsteps > 1) {
+      mbar_wait(bar_d1, 0);   // M1(0) done: the H0' tile may be overwritten
+      build_h0(1);
+    }
+
+    // pair row of the step whose E1 runs in iteration `it` (for the dropout draw)
+    int d_tile = e_tile, d_s = e_s;
+
+    for (int it = 0; it < nsteps; ++it) {
+      // ---- E2lo(it-1) ----------------------------------------------------------------------------
+      if (it >= 1) {
+        mbar_wait(bar_d2lo, (it - 1) & 1);
+        tc_fence_after();
+        e2_half(F_D2LO_COL, acc, kz);
+        tc_fence_before();
+        mbar_arrive(bar_f2lo);
+        mbar_wait(bar_d2hi, (it - 1) & 1);   // M2hi(it-1) done: D2hi readable, H1' tile free
+      }
+      // ---- E1(it): D1 -> H1' ---------------------------------------------------------------------
+      uint32_t kx = 0, ky = 0, kz_n = 0, kw_n = 0;
+      if (DROP) {
+        const int r = d_tile * TILE + row;
+        const u4 b = edge_drop_bits(drop.seed, (uint64_t)(r < BN ? r : BN - 1) * N + d_s, q, 1);
+        kx = b.x; ky = b.y; kz_n = b.z; kw_n = b.w;
+        if (++d_s == N) { d_s = 0; ++d_tile; }
+      }
+      mbar_wait(bar_d1 + 8 * (it & 1), (it >> 1) & 1);
+      tc_fence_after();
+      {
+        float v[Q1];
+        tmem_ld8x5(tl + F_D1_COL + (uint32_t)(it & 1) * N1, v);
+#pragma unroll
+        for (int c = 0; c < Q1 / 8; ++c) {
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) {
+            const int i = c * 8 + e;
+            w[e >> 1] = pack_bf16(lrelu_g(v[i], cg), lrelu_g(v[i + 1], cg));
+            if (DROP) w[e >> 1] &= keep_pair(i < 32 ? kx : ky, i & 31);
+          }
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(xs[c & 1] + OFF_H1 + (c >> 1) * A_BLK),
+                       "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]));
+        }
+      }
+      fence_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_h1);
+      // ---- E2hi(it-1) ----------------------------------------------------------------------------
+      if (it >= 1) {
+        tc_fence_after();
+        e2_half(F_D2HI_COL, acc + QH, kwd);
+        tc_fence_before();
+        mbar_arrive(bar_f2hi);
+        if (++e_s == N) {   // step it-1 was the tile's last sender
+          flush();
+          e_s = 0;
+          ++e_tile;
+          e_enter_tile();
+        }
+        e_load_mask();      // multiplier of step `it` (used in the next iteration)
+      }
+      kz = kz_n;
+      kwd = kw_n;
+      // ---- H0'(it+2) -----------------------------------------------------------------------------
+      if (it + 2 < nsteps) {
+        mbar_wait(bar_d1 + 8 * ((it + 1) & 1), ((it + 1) >> 1) & 1);   // M1(it+1) done: H0' tile free
+        build_h0(it + 2);
+      }
+    }
+    // ---- drain: E2 of the last step ------------------------------------------------------------------
+    mbar_wait(bar_d2lo, (nsteps - 1) & 1);
+    mbar_wait(bar_d2hi, (nsteps - 1) & 1);
+    tc_fence_after();
+    e2_half(F_D2LO_COL, acc, kz);
+    e2_half(F_D2HI_COL, acc + QH, kwd);
+    flush();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 16) tmem_dealloc(tmem, TMEM_COLS);
+}

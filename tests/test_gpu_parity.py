@@ -280,3 +280,33 @@ def test_train_step_golden(golden):
         g = c["gradsD"][k]
         ok = g.abs() > 1e-3 * g.abs().max()
         assert float((sdD[k].cpu() - v)[ok].abs().max()) < 2e-6, k
+
+
+@pytest.mark.parametrize("B,N,p", [(5, 30, 0.0), (3, 150, 0.0), (40, 30, 0.5), (2, 150, 0.5), (7, 17, 0.0),
+                                   (300, 30, 0.0)])
+def test_edge_tc_vs_fp32_kernel(B, N, p):
+    """The tcgen05 edge kernels (bf16 operands) against the fp32 SIMT kernels on the same inputs and --
+    with dropout -- the same Philox masks: forward, input gradient and all six weight gradients.
+    Shapes cover ragged last tiles, tiles spanning several jets (N=17, 30) and jets spanning tiles (N=150)."""
+    import mpgan_b200.ops as O
+    torch.manual_seed(B * 1000 + N)
+    F = 32
+    x0 = torch.randn(B, N, F, device="cuda") * 0.5
+    n = torch.randint(1, N + 1, (B,), device="cuda")
+    mask = (torch.arange(N, device="cuda")[None, :] < n[:, None]).float().unsqueeze(2)
+    ws0 = []
+    for i, o in ((2 * F, 96), (96, 160), (160, 192)):
+        ws0 += [torch.randn(o, i, device="cuda") / i ** 0.5, torch.randn(o, device="cuda") * 0.1]
+    dagg = torch.randn(B, N, 192, device="cuda")
+    res = []
+    for prec in (0, 1):
+        O.set_precision(prec)
+        O._seed_counter = 4242
+        x = x0.clone().requires_grad_(True)
+        ws = [w.clone().requires_grad_(True) for w in ws0]
+        agg = O.edge_aggregate(x, mask, *ws, p_drop=p)
+        agg.backward(dagg)
+        res.append([agg.detach(), x.grad] + [w.grad for w in ws])
+    names = ["agg", "dx", "dW0", "db0", "dW1", "db1", "dW2", "db2"]
+    for name, r0, r1 in zip(names, res[0], res[1]):
+        close(r1, r0, 2e-2 if name == "agg" else 6e-2, f"edge {name} B={B} N={N} p={p}")
