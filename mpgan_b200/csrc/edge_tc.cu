@@ -14,6 +14,12 @@ namespace {
 
 int edge_tc_features() { return 3; }
 
+#ifdef MPG_TRACE
+extern "C" int mpg_debug_set_trace(void* p) {
+  return (int)cudaMemcpyToSymbol(g_trace, &p, sizeof(p));
+}
+#endif
+
 // one-shot timing probes: bench.py arms a pair of CUDA events per kernel id (1 = forward,
 // 2 = backward CHAIN, 3 = backward DW2); the next launch of that kernel is bracketed by them
 static thread_local cudaEvent_t g_probe[4][2] = {};

@@ -98,6 +98,31 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
 // the same descriptor split in two words: the high word is a constant, the low word carries the address
 constexpr uint32_t UMMA_DESC_HI = 64u | (1u << 14) | (2u << 29);
 __device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+// D[tmem] (+)= A[tmem] * B[smem]^T: A is a bf16 [128 x 16] slice held in TMEM (lane = row, two K
+// elements per 32-bit column => 8 columns per K = 16 step)
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 4 / 8 consecutive 32-bit TMEM columns of this thread's lane
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, uint32_t a, uint32_t b) {   // {a, b, b, b, b, b, b, b}
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%2,%2,%2,%2,%2,%2};" ::"r"(taddr), "r"(a), "r"(b)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // Warp-collective forms: executed by ALL lanes of a converged warp; one elected lane (always the same
 // one for a full mask) issues.  tcgen05.mma / commit / bulk copies take warp-uniform operands, and from a
 // `lane == 0` branch ptxas wraps each of them in an elect-and-loop sequence that costs ~100 cycles per MMA.
@@ -135,8 +160,20 @@ __device__ __forceinline__ void bulk_g2s_elect(uint32_t dst, const void* src, ui
       "l"(src), "r"(bytes), "r"(bar)
       : "memory");
 }
+// CUTLASS-style leader election: ptxas knows the guarded region runs on exactly one lane, so its
+// values are trivially warp-uniform and the single-thread instructions need no per-lane loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 // hides a value from loop-invariant code motion
 __device__ __forceinline__ void opaque(uint32_t& v) { asm volatile("" : "+r"(v)); }
+__device__ __forceinline__ void opaque(uint64_t& v) { asm volatile("" : "+l"(v)); }
 __host__ __device__ constexpr uint32_t umma_idesc(int N) {
   // c = f32 (1 << 4), a = b = bf16 (1 << 7, 1 << 10), K-major A and B, N >> 3 at bit 17, M >> 4 at bit 24
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);

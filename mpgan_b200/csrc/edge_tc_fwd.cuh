@@ -7,8 +7,8 @@
 //
 //   H0'[r,:] = g(P[r,:] + Q[jet(r)*N + s,:])                    g(v) = v + c|v| = lrelu(v) / sl
 //   D1       = H0' * (sl W1)^T  (tcgen05.mma, M=128 N=160 K=96+16)   fp32, TMEM, double buffered
-//   H1'      = g(D1)                                             bf16 tile (A operand)
-//   D2       = H1' * (sl W2)^T  (two N=96 halves, K=160+16)       fp32, TMEM
+//   H1'      = g(D1)                                             bf16, written back IN PLACE into TMEM
+//   D2       = H1' * (sl W2)^T  (A operand from TMEM; two N=96 halves, K=160+16)   fp32, TMEM
 //   acc[r,:] += mask[jet(r), s] * g(D2)                          fp32 registers; x sl at the flush
 //
 // c = (1-alpha)/(1+alpha), sl = (1+alpha)/2: leaky-relu costs ONE fma per element (|v| is a free
@@ -19,9 +19,14 @@
 // warpgroup: one lane issues every tcgen05.mma, another the bulk-async (TMA) copies of the weight
 // images and of the Q rows (a 4-stage shared-memory ring, so no thread waits on global memory per
 // step).  Registers are re-split with setmaxnreg (epilogue 120, control 32 per thread).  The tensor pipe executes   ... M2hi(s-1) | M1(s+1) | M2lo(s) | M2hi(s) | M1(s+2) ...  :
-// layer 1 runs one step ahead into a double-buffered D1, so the only serial dependency on the
-// epilogue warps -- E1(s): D1 -> H1' -- overlaps M1(s+1); E2lo/E2hi(s-1) and the H0' tile of step s+2
-// are produced under M2(s).  TMEM: D1a [0,160) D1b [160,320) D2lo [320,416) D2hi [416,512).
+// layer 1 runs one step ahead into a double-buffered D1.  H1' never touches shared memory: the
+// epilogue warps pack it to bf16 and store it over the first 88 columns of the D1 buffer they read
+// (the four warps sharing a TMEM lane quarter meet at a named barrier between the loads and the
+// stores), and M2 takes its A operand from there.  Shared-memory bandwidth (128 B/clk) is what bounds
+// an SS-mode MMA of this shape: with H1' in TMEM a step moves ~150 KB instead of ~320 KB through it.
+// Every epilogue phase then has ~1000 cycles of slack: E1(s) needs only D1(s) (ready one step early),
+// E2lo/E2hi(s-1) and H0'(s+2) are produced under M2(s) / M1(s+1).
+// TMEM: D1a [0,160) D1b [160,320) D2lo [320,416) D2hi [416,512).
 //
 // Dropout (p = 0.5): Philox bits as laid out in common.cuh (edge_drop_*), applied to the packed bf16
 // words (layers 0/1) or to the mask multiplier (layer 2) through PRMT sign-replication masks; the 2x
@@ -34,7 +39,7 @@ constexpr int F_QS = 4;                      // Q ring stages
 constexpr int F_QJ = 10;                     // jets a 128-row tile can span (N >= 15)
 constexpr uint32_t F_QROW = K0 * 4;          // bytes of one Q row
 constexpr uint32_t F_QSTAGE = F_QJ * F_QROW;
-constexpr uint32_t F_OFF_Q = OFF_H1 + H1_BYTES;            // 196608
+constexpr uint32_t F_OFF_Q = OFF_H1;                       // 147456 (no H1 tile in shared memory)
 constexpr uint32_t F_OFF_BAR = F_OFF_Q + F_QS * F_QSTAGE;  // 211968
 constexpr uint32_t F_SMEM = F_OFF_BAR + 256 + 1024;
 constexpr uint32_t F_D1_COL = 0, F_D2LO_COL = 320, F_D2HI_COL = 416;
@@ -58,6 +63,17 @@ __device__ __forceinline__ uint32_t keep_one(uint32_t word, int e) {
 // g(v) = v + c|v|
 __device__ __forceinline__ float lrelu_g(float v, float c) { return fmaf(fabsf(v), c, v); }
 
+// optional event trace (build with -DMPG_TRACE): clock64 stamps of block 0, lane 0 of warps 0 and 16
+#ifdef MPG_TRACE
+__device__ long long* g_trace = nullptr;
+#define MPG_TR(it, slot)                                                                        \
+  do {                                                                                           \
+    if (g_trace && blockIdx.x == 0 && lane == 0 && (it) < 256) g_trace[(it) * 16 + (slot)] = clock64(); \
+  } while (0)
+#else
+#define MPG_TR(it, slot) do { } while (0)
+#endif
+
 template <bool DROP>
 __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
   extern __shared__ uint8_t smem_raw[];
@@ -65,8 +81,7 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
   uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SW128 tiles need 1024-byte alignment
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
   opaque(base);   // keep it in a register: every barrier / tile address below is base + constant
-  const uint32_t sW1 = base + OFF_W1, sW2 = base + OFF_W2, sH0 = base + OFF_H0, sH1 = base + OFF_H1,
-                 sQ = base + F_OFF_Q;
+  const uint32_t sW1 = base + OFF_W1, sW2 = base + OFF_W2, sH0 = base + OFF_H0, sQ = base + F_OFF_Q;
   const uint32_t bar0 = base + F_OFF_BAR;
   const uint32_t bar_w = bar0, bar_h0 = bar0 + 8, bar_d1 = bar0 + 16 /* [2] */, bar_h1 = bar0 + 32,
                  bar_d2lo = bar0 + 40, bar_d2hi = bar0 + 48, bar_f2lo = bar0 + 56, bar_f2hi = bar0 + 64,
@@ -125,29 +140,37 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
       }
     } else if (warp == 16 && nsteps > 0) {
       // =============================== MMA issuer ================================================
-      // operand descriptors = per-tile base (low word) + compile-time offset, rebuilt at every use: the
-      // control warps run on 32 registers, so nothing may be hoisted out of the step loop (opaque())
+      // operand descriptors = tile base (low word) + compile-time offset.  Everything here derives from
+      // warp-uniform values (no opaque()/per-thread registers), so ptxas keeps it in uniform registers
       constexpr uint32_t idesc1 = umma_idesc(N1), idesc2h = umma_idesc(NH2);
-      uint32_t lH0 = umma_desc_lo(sH0), lW1 = umma_desc_lo(sW1), lH1 = umma_desc_lo(sH1), lW2 = umma_desc_lo(sW2);
+      const uint32_t ub = (smem_u32(smem_raw) + 1023u) & ~1023u;
+      uint64_t dH0 = umma_desc(ub + OFF_H0), dW1 = umma_desc(ub + OFF_W1), dW2 = umma_desc(ub + OFF_W2);
       auto issue_m1 = [&](int it) {   // D1[it&1] = H0' * W1'^T
         const uint32_t d = tmem + F_D1_COL + (uint32_t)(it & 1) * N1;
-        opaque(lH0); opaque(lW1);
+        if (elect_one()) {
+          opaque(dH0); opaque(dW1);   // no hoisting of the 14 descriptors out of the step loop (32 registers)
 #pragma unroll
-        for (uint32_t ks = 0; ks < KSTEPS1; ++ks) {
-          const uint32_t blk = ks >> 2, j = ks & 3;
-          umma_bf16_lo(d, lH0 + ((blk * A_BLK + j * 32) >> 4), lW1 + ((blk * W1_BLK + j * 32) >> 4), idesc1, ks);
+          for (uint32_t ks = 0; ks < KSTEPS1; ++ks) {
+            const uint32_t blk = ks >> 2, j = ks & 3;
+            umma_bf16(d, dH0 + ((blk * A_BLK + j * 32) >> 4), dW1 + ((blk * W1_BLK + j * 32) >> 4), idesc1, ks);
+          }
+          umma_commit(bar_d1 + 8 * (it & 1));
         }
-        umma_commit_elect(bar_d1 + 8 * (it & 1));
+        __syncwarp();
       };
-      auto issue_m2 = [&](uint32_t dcol, uint32_t wrow_off, uint32_t bar) {   // one N=96 half of D2
-        opaque(lH1); opaque(lW2);
+      // one N=96 half of D2; A = H1' (bf16) in the first 88 columns of D1[it&1]
+      auto issue_m2 = [&](int it, uint32_t dcol, uint32_t wrow_off, uint32_t bar) {
+        const uint32_t at = tmem + F_D1_COL + (uint32_t)(it & 1) * N1;
+        if (elect_one()) {
+          opaque(dW2);
 #pragma unroll
-        for (uint32_t ks = 0; ks < KSTEPS2; ++ks) {
-          const uint32_t blk = ks >> 2, j = ks & 3;
-          umma_bf16_lo(tmem + dcol, lH1 + ((blk * A_BLK + j * 32) >> 4),
-                       lW2 + ((blk * W2_BLK + wrow_off + j * 32) >> 4), idesc2h, ks);
+          for (uint32_t ks = 0; ks < KSTEPS2; ++ks) {
+            const uint32_t blk = ks >> 2, j = ks & 3;
+            umma_bf16_ts(tmem + dcol, at + ks * 8, dW2 + ((blk * W2_BLK + wrow_off + j * 32) >> 4), idesc2h, ks);
+          }
+          umma_commit(bar);
         }
-        umma_commit_elect(bar);
+        __syncwarp();
       };
 
       mbar_wait(bar_w, 0);
@@ -158,17 +181,24 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
         if (it + 1 < nsteps) {
           mbar_wait(bar_h0, (it + 1) & 1);
           tc_fence_after();
+          MPG_TR(it, 8);
           issue_m1(it + 1);
+          MPG_TR(it, 9);
         }
         mbar_wait(bar_h1, it & 1);
+        MPG_TR(it, 10);
         if (it >= 1) mbar_wait(bar_f2lo, (it - 1) & 1);
         tc_fence_after();
-        issue_m2(F_D2LO_COL, 0, bar_d2lo);
+        MPG_TR(it, 11);
+        issue_m2(it, F_D2LO_COL, 0, bar_d2lo);
+        MPG_TR(it, 12);
         if (it >= 1) {
           mbar_wait(bar_f2hi, (it - 1) & 1);
           tc_fence_after();
         }
-        issue_m2(F_D2HI_COL, NH2 * 128, bar_d2hi);
+        MPG_TR(it, 13);
+        issue_m2(it, F_D2HI_COL, NH2 * 128, bar_d2hi);
+        MPG_TR(it, 14);
       }
     }
   } else {
@@ -193,9 +223,6 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
     if (q == 0) {
       st_ones_chunk(sH0 + swz_chunk(row, 96, A_BLK));
       st_zero_chunk(sH0 + swz_chunk(row, 104, A_BLK));
-    } else if (q == 1) {
-      st_ones_chunk(sH1 + swz_chunk(row, 160, A_BLK));
-      st_zero_chunk(sH1 + swz_chunk(row, 168, A_BLK));
     }
 
     float acc[2 * QH];
@@ -303,11 +330,12 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
       // ---- E2lo(it-1) ----------------------------------------------------------------------------
       if (it >= 1) {
         mbar_wait(bar_d2lo, (it - 1) & 1);
+        MPG_TR(it, 0);
         tc_fence_after();
         e2_half(F_D2LO_COL, acc, kz);
         tc_fence_before();
         mbar_arrive(bar_f2lo);
-        mbar_wait(bar_d2hi, (it - 1) & 1);   // M2hi(it-1) done: D2hi readable, H1' tile free
+        MPG_TR(it, 1);
       }
       // ---- E1(it): D1 -> H1' ---------------------------------------------------------------------
       uint32_t kx = 0, ky = 0, kz_n = 0, kw_n = 0;
@@ -318,32 +346,39 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
         if (++d_s == N) { d_s = 0; ++d_tile; }
       }
       mbar_wait(bar_d1 + 8 * (it & 1), (it >> 1) & 1);
+      MPG_TR(it, 3);
       tc_fence_after();
       {
+        const uint32_t d1 = tl + F_D1_COL + (uint32_t)(it & 1) * N1;   // column of chunk q of D1[it&1]
         float v[Q1];
-        tmem_ld8x5(tl + F_D1_COL + (uint32_t)(it & 1) * N1, v);
+        tmem_ld8x5(d1, v);
+        uint32_t w[Q1 / 2];
 #pragma unroll
-        for (int c = 0; c < Q1 / 8; ++c) {
-          uint32_t w[4];
-#pragma unroll
-          for (int e = 0; e < 8; e += 2) {
-            const int i = c * 8 + e;
-            w[e >> 1] = pack_bf16(lrelu_g(v[i], cg), lrelu_g(v[i + 1], cg));
-            if (DROP) w[e >> 1] &= keep_pair(i < 32 ? kx : ky, i & 31);
-          }
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(xs[c & 1] + OFF_H1 + (c >> 1) * A_BLK),
-                       "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]));
+        for (int i = 0; i < Q1; i += 2) {
+          w[i >> 1] = pack_bf16(lrelu_g(v[i], cg), lrelu_g(v[i + 1], cg));
+          if (DROP) w[i >> 1] &= keep_pair(i < 32 ? kx : ky, i & 31);
         }
+        // H1' goes back into D1[it&1]: element column 32c + 8q + e -> packed column 16c + 4q + e/2.  Those
+        // columns hold fp32 values other warps of this lane quarter are still reading: meet them first
+        named_bar_sync(1 + (warp & 3), 128);
+        const uint32_t h1 = d1 - (uint32_t)q * 4;                      // packed column 4q
+#pragma unroll
+        for (int c = 0; c < Q1 / 8; ++c) tmem_st4(h1 + 16 * c, w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+        if (q == 0) tmem_st8(d1 + N1 / 2, 0x3F803F80u, 0u);            // bias K-step: columns 160,161 = 1.0
+        tmem_st_wait();
       }
-      fence_async_smem();
       tc_fence_before();
       mbar_arrive(bar_h1);
+      MPG_TR(it, 4);
       // ---- E2hi(it-1) ----------------------------------------------------------------------------
       if (it >= 1) {
+        mbar_wait(bar_d2hi, (it - 1) & 1);
+        MPG_TR(it, 2);
         tc_fence_after();
         e2_half(F_D2HI_COL, acc + QH, kwd);
         tc_fence_before();
         mbar_arrive(bar_f2hi);
+        MPG_TR(it, 5);
         if (++e_s == N) {   // step it-1 was the tile's last sender
           flush();
           e_s = 0;
@@ -357,7 +392,9 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
       // ---- H0'(it+2) -----------------------------------------------------------------------------
       if (it + 2 < nsteps) {
         mbar_wait(bar_d1 + 8 * ((it + 1) & 1), ((it + 1) >> 1) & 1);   // M1(it+1) done: H0' tile free
+        MPG_TR(it, 6);
         build_h0(it + 2);
+        MPG_TR(it, 7);
       }
     }
     // ---- drain: E2 of the last step ------------------------------------------------------------------
