@@ -1,5 +1,7 @@
 // Argument block shared by the edge-network kernels (generic SIMT and tcgen05).
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace mpg {

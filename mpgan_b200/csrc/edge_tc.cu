@@ -42,20 +42,25 @@ bool edge_tc_supported(const EdgeArgs& a) {
          (a.drop.p == 0.f || a.drop.p == 0.5f) && a.alpha > 0.f && a.alpha < 1.f;
 }
 
-size_t edge_tc_workspace_bytes(int B, int N, int H0, int H1, int H2) {
-  if (H0 != K0 || H1 != N1 || H2 != N2) return 0;
-  return W1_BYTES + W2_BYTES + 1024;
+static size_t tc_sbits_bytes(int B, int N) {   // backward: one uint2 per (step, epilogue thread)
+  const long long tiles = ((long long)B * N + TILE - 1) / TILE;
+  return (size_t)tiles * N * F_NEPI * sizeof(uint2);
 }
 
-// fwd: the forward kernel's activation tiles hold lrelu(v) / sl, so its weight images carry sl
-static int tc_prepare(const EdgeArgs& a, void* ws, TcArgs& t, int* grid, bool fwd, cudaStream_t stream) {
+size_t edge_tc_workspace_bytes(int B, int N, int H0, int H1, int H2) {
+  if (H0 != K0 || H1 != N1 || H2 != N2) return 0;
+  return W1_BYTES + W2_BYTES + 1024 + tc_sbits_bytes(B, N);
+}
+
+// the activation / gradient tiles hold X / (sd * sl) (dropout and leaky-relu scales), the weight images sd * sl * W
+static int tc_prepare(const EdgeArgs& a, void* ws, TcArgs& t, int* grid, cudaStream_t stream) {
   MPG_CHECK(edge_tc_supported(a), "edge_tc: unsupported configuration");
   uint8_t* img = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
   t.a = a;
   t.w1img = img;
   t.w2img = img + W1_BYTES;
-  // dropout scale (and, forward, leaky-relu scale) of the previous layer folded into the weights
-  const float s = (a.drop.p > 0.f ? 2.f : 1.f) * (fwd ? 0.5f * (1.f + a.alpha) : 1.f);
+  t.sbits = reinterpret_cast<uint2*>(img + W1_BYTES + W2_BYTES);
+  const float s = (a.drop.p > 0.f ? 2.f : 1.f) * 0.5f * (1.f + a.alpha);
   weight_image_kernel<<<cdiv(N1 * 128, 256), 256, 0, stream>>>(a.W1, a.b1, N1, K0, 128, s, img);
   MPG_LAUNCH_CHECK();
   weight_image_kernel<<<cdiv(N2 * 192, 256), 256, 0, stream>>>(a.W2, a.b2, N2, N1, 192, s, img + W1_BYTES);
@@ -73,7 +78,7 @@ static int tc_prepare(const EdgeArgs& a, void* ws, TcArgs& t, int* grid, bool fw
 int launch_edge_tc_fwd(const EdgeArgs& a, void* ws, cudaStream_t stream) {
   TcArgs t;
   int grid = 1;
-  if (tc_prepare(a, ws, t, &grid, true, stream)) return 1;
+  if (tc_prepare(a, ws, t, &grid, stream)) return 1;
   MPG_CUDA(cudaMemsetAsync(a.agg, 0, (size_t)a.B * a.N * N2 * sizeof(float), stream));
   if (a.drop.p > 0.f) {
     MPG_CUDA(cudaFuncSetAttribute(edge_tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
@@ -93,7 +98,7 @@ static int launch_bwd_one(const TcArgs& t, int grid, uint32_t smem, cudaStream_t
   MPG_CUDA(cudaFuncSetAttribute(edge_tc_bwd_kernel<MODE, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
     ProbeScope probe(MODE == BWD_CHAIN ? 2 : 3, stream);
-    edge_tc_bwd_kernel<MODE, DROP><<<grid, NTHREADS, smem, stream>>>(t);
+    edge_tc_bwd_kernel<MODE, DROP><<<grid, F_NTHR, smem, stream>>>(t);
   }
   MPG_LAUNCH_CHECK();
   return 0;
@@ -103,13 +108,13 @@ static int launch_bwd_one(const TcArgs& t, int grid, uint32_t smem, cudaStream_t
 int launch_edge_tc_bwd(const EdgeArgs& a, void* ws, cudaStream_t stream) {
   TcArgs t;
   int grid = 1;
-  if (tc_prepare(a, ws, t, &grid, false, stream)) return 1;
+  if (tc_prepare(a, ws, t, &grid, stream)) return 1;
   if (a.drop.p > 0.f) {
-    if (launch_bwd_one<BWD_CHAIN, true>(t, grid, BW_SMEM_CHAIN, stream)) return 1;
-    if (launch_bwd_one<BWD_DW2, true>(t, grid, BW_SMEM_DW2, stream)) return 1;
+    if (launch_bwd_one<BWD_CHAIN, true>(t, grid, C_SMEM, stream)) return 1;
+    if (launch_bwd_one<BWD_DW2, true>(t, grid, D_SMEM, stream)) return 1;
   } else {
-    if (launch_bwd_one<BWD_CHAIN, false>(t, grid, BW_SMEM_CHAIN, stream)) return 1;
-    if (launch_bwd_one<BWD_DW2, false>(t, grid, BW_SMEM_DW2, stream)) return 1;
+    if (launch_bwd_one<BWD_CHAIN, false>(t, grid, C_SMEM, stream)) return 1;
+    if (launch_bwd_one<BWD_DW2, false>(t, grid, D_SMEM, stream)) return 1;
   }
   return 0;
 }

@@ -1,24 +1,35 @@
 // tcgen05 backward of the edge network (included by edge_tc.cu inside its anonymous namespace).
 //
-// The backward recomputes H0/H1/D2 per (tile, sender) step exactly as the forward does and never
-// stores an N^2 x hidden tensor.  All fp32 weight-gradient accumulators cannot be TMEM-resident at
-// once (dW2: 2x160 columns, dW1^T: 160 columns, plus >= 192 streaming columns > 512), so the work is
-// split into two kernels that share the recompute code:
+// The backward recomputes H0'/H1'/D2 per (tile, sender) step exactly as the forward does and never
+// stores an N^2 x hidden tensor.  All fp32 weight-gradient accumulators cannot be TMEM-resident next
+// to the streaming tiles, so the work is split into two kernels over the SAME step partition:
 //
-//   CHAIN  G2 = dAgg*m*f'(D2) -> dH1 = G2 W2 -> G1 = dH1 f'(D1) -> dH0 = G1 W1 -> G0 = dH0 f'(pre0)
-//          dP[r] += G0 (registers), dQ[jet,s] += G0 (red.global), dW1^T += H0^T G1 (TMEM accumulator;
-//          the constant-1 bias columns of the H0 tile make row 96 of it db1).
-//   DW2    recompute -> G2, dW2 += G2^T H1 (two M=128 TMEM accumulators), db2 = column sums of G2.
+//   CHAIN  H0' -> D1 -> H1' -> D2 -> G2' -> dH1 = G2' W2 -> G1' -> dH0 = G1' W1 -> G0'
+//          dP[r] += G0' (registers); dW1^T += H0'^T G1' (TMEM accumulator, the constant-1 column of
+//          the H0' tile makes row 96 of it db1); dQ[jet,s] = sum over the jet's rows of G0': one more
+//          MMA, H0'^T G0', whose rows 98+j come from one-hot "row belongs to jet j" columns parked in
+//          the unused columns of the H0' tile (no per-element atomics, no shuffles).
+//          It also dumps the sign bits of D2 (one uint2 per thread and step) for the second kernel.
+//   DW2    H0' -> D1 -> H1' (recompute of layer 1 only), G2' rebuilt from the dumped sign bits,
+//          dW2 += G2'^T H1' in two M=128 TMEM accumulators; the constant-1 column of the H1' tile
+//          (N = 176) makes column 160 of them db2.  No W2 image, no second-layer MMA.
 //
-// The transposed products reuse the SAME swizzled shared-memory tiles through MN-major UMMA
-// descriptors (a K-major [rows x cols] SW128 tile read as MN-major is its transpose), and the
-// weight images serve both W (K-major B operand) and W^T (MN-major B operand).
+// Primed tiles are scaled: X' = X / (sd*sl) with sd = dropout scale (2 or 1) and sl = (1+alpha)/2, and
+// the weight images carry sd*sl (forward convention, edge_tc_fwd.cuh), so every MMA sees true products:
+//   g(v) = v + cg|v| = lrelu(v)/sl,  lrelu'(v) = sl*(1 + cg*sgn v).
+//   G2' = dAgg*m*keep2*(1 + cg sgn D2),  G1' = dH1*keep1*(1 + cg sgn D1),  G0' = dH0*keep0*(1 + cg sgn pre0)
+//   dW = (sd*sl)^2 * acc,  db = sd*sl * acc,  dP/dQ = sd*sl * G0'.
+// Gradient tiles are produced in packed bf16x2 arithmetic: pack two fp32 values, multiply by a factor
+// pair selected per lane from the sign bits (PRMT sign-replication mask + one LOP3).  Sign bits are kept
+// one word per 32 elements (sign_put / neg_pair_mask).
 //
-// Scale convention with dropout p = 0.5 (s = 2): tiles hold activations / pre-activation gradients
-// divided by s and the weight images hold s*W, so every MMA sees the true product; the factors are
-// restored at the flush (dW: s^2, db: s) and in G0 (s).
-//
-// Thread layout as in the forward kernel: 16 warps, thread <-> (tile row, column quarter).
+// Structure as in the forward kernel: 16 epilogue warps (thread <-> tile row x column chunks 4c+q), a
+// control warpgroup (warp 16 issues every MMA through an elected lane, warp 17 runs the TMA Q ring),
+// setmaxnreg 112/32.  Operands that only feed an MMA as A live in TMEM (H1', G2', G1': written back in
+// place over the fp32 accumulator they were computed from); tiles that feed an MMA as B or transposed
+// (H0', G1', G0', H1', G2') are swizzled bf16 tiles in shared memory.  CHAIN is serial per step (TMEM
+// holds one step) with H0'(s+1) built under M4(s), E4(s) under M1(s+1) and E1(s+1) under the dQ MMA of
+// step s; in DW2 layer 1 runs one step ahead of the dW2 MMA, which keeps the tensor pipe busy.
 
 enum { BWD_CHAIN = 0, BWD_DW2 = 1 };
 
@@ -32,342 +43,639 @@ __host__ __device__ constexpr uint32_t umma_idesc_t(int N, int a_mn, int b_mn) {
   return umma_idesc(N) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16);
 }
 
-constexpr uint32_t BW_OFF_A0_CHAIN = OFF_W2 + W2_BYTES;            // 114688: H0 tile (32 KB)
-constexpr uint32_t BW_OFF_A1_CHAIN = BW_OFF_A0_CHAIN + H0_BYTES;   // 147456: H1 / G2 / G1 tile (48 KB)
-constexpr uint32_t BW_OFF_G2_DW2 = OFF_W2 + W2_BYTES;              // 114688: H0 then G2 tile (48 KB)
-constexpr uint32_t BW_OFF_A1_DW2 = BW_OFF_G2_DW2 + H1_BYTES;       // 163840: H1 tile (48 KB)
-constexpr uint32_t BW_OFF_BAR_CHAIN = BW_OFF_A1_CHAIN + H1_BYTES;  // 196608
-constexpr uint32_t BW_OFF_BAR_DW2 = BW_OFF_A1_DW2 + H1_BYTES;      // 212992
-constexpr uint32_t BW_SMEM_CHAIN = BW_OFF_BAR_CHAIN + 128 + 1024;
-constexpr uint32_t BW_SMEM_DW2 = BW_OFF_BAR_DW2 + 128 + 1024;
-constexpr uint32_t RS_COL = 0, RW1_COL = 256, RW2A_COL = 192, RW2B_COL = 352;
+// ---- shared-memory maps ------------------------------------------------------------------------------
+// CHAIN: W1 | W2 | H0' (2 blocks) | X (3 blocks: G1', later G0') | Q ring (4 stages) | barriers
+constexpr uint32_t C_OFF_H0 = OFF_W2 + W2_BYTES;            // 114688
+constexpr uint32_t C_OFF_X = C_OFF_H0 + H0_BYTES;           // 147456
+constexpr uint32_t C_OFF_Q = C_OFF_X + H1_BYTES;            // 196608
+constexpr int C_QS = 4;
+constexpr uint32_t C_OFF_BAR = C_OFF_Q + C_QS * F_QSTAGE;   // 211968
+constexpr uint32_t C_SMEM = C_OFF_BAR + 256 + 1024;
+// DW2: W1 | H0' | G2' (3 blocks; the 4th one the second M block reads is H1' buffer 0) | H1' x2 | Q ring (2)
+constexpr uint32_t D_OFF_H0 = W1_BYTES;                     // 40960
+constexpr uint32_t D_OFF_G2 = D_OFF_H0 + H0_BYTES;          // 73728
+constexpr uint32_t D_OFF_H1 = D_OFF_G2 + H1_BYTES;          // 122880 (+ 49152 per buffer)
+constexpr uint32_t D_OFF_Q = D_OFF_H1 + 2 * H1_BYTES;       // 221184
+constexpr int D_QS = 2;
+constexpr uint32_t D_OFF_BAR = D_OFF_Q + D_QS * F_QSTAGE;   // 228864
+constexpr uint32_t D_SMEM = D_OFF_BAR + 256 + 1024;
+// ---- TMEM maps -------------------------------------------------------------------------------------------
+constexpr uint32_t C_RA = 0, C_RB = 160, C_PW1 = 352;       // CHAIN: D1/H1'/dH1/G1' | D2/G2'/dQ + dH0 | dW1^T
+constexpr uint32_t D_R = 0, D_PW2A = 160, D_PW2B = 336;     // DW2: D1 | dW2 rows 0..127 | rows 128..191
+constexpr int NDW = N1 + 16;                                 // 176: dW2 accumulator width incl. the db2 column
+
+__device__ __forceinline__ uint32_t mul_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+// sign bits of the bf16 pair `w` (bits 15 and 31) into slot p (0..15) of a 32-bit sign word:
+// slots 0..7 use bits (15-p, 31-p), slots 8..15 bits (15-p, 31-p) of the low bytes, i.e. (7-(p-8), 23-(p-8))
+__device__ __forceinline__ void sign_put(uint32_t& acc, uint32_t w, int p) {
+  if (p < 8) acc |= (w >> p) & (0x80008000u >> p);
+  else acc |= (w >> p) & (0x00800080u >> (p - 8));
+}
+// 0xFFFF per negative lane of pair p
+__device__ __forceinline__ uint32_t neg_pair_mask(uint32_t sw, int p) {
+  return p < 8 ? prmt(sw << p, 0u, 0xbb99u) : prmt(sw << (p - 8), 0u, 0xaa88u);
+}
+// per-lane select: negative lanes take `neg`, the others `pos`
+__device__ __forceinline__ uint32_t sel_pair(uint32_t mask, uint32_t neg, uint32_t pos) {
+  return (mask & neg) | (~mask & pos);
+}
+__device__ __forceinline__ uint32_t bf16x2_dup(float v) {
+  const uint32_t h = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v));
+  return h | (h << 16);
+}
+
+struct BwdBars {   // byte offsets from the barrier block
+  static constexpr uint32_t w = 0, rdyA = 8, rdyB = 16, rdyC = 24, rdyD = 32, rdyE = 40, doneA = 48, doneB = 56,
+                            doneC = 64, doneD5 = 72, doneD4 = 80, doneE = 88, q = 96 /* [4] */, qe = 128 /* [4] */;
+};
 
 template <int MODE, bool DROP>
-__global__ void __launch_bounds__(NTHREADS, 1) edge_tc_bwd_kernel(TcArgs t) {
+__global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
   extern __shared__ uint8_t smem_raw[];
   const EdgeArgs& a = t.a;
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  constexpr bool CH = MODE == BWD_CHAIN;
+  constexpr uint32_t OFF_H0T = CH ? C_OFF_H0 : D_OFF_H0, OFF_QR = CH ? C_OFF_Q : D_OFF_Q,
+                     OFF_BARS = CH ? C_OFF_BAR : D_OFF_BAR;
+  constexpr int QS = CH ? C_QS : D_QS;
+  uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t sW1 = base + OFF_W1, sW2 = base + OFF_W2;
-  const uint32_t sA0 = base + (MODE == BWD_CHAIN ? BW_OFF_A0_CHAIN : BW_OFF_G2_DW2);
-  const uint32_t sA1 = base + (MODE == BWD_CHAIN ? BW_OFF_A1_CHAIN : BW_OFF_A1_DW2);
-  const uint32_t sG2 = MODE == BWD_CHAIN ? sA1 : base + BW_OFF_G2_DW2;   // G2 tile (CHAIN: over H1; DW2: over H0)
-  const uint32_t off_bar = MODE == BWD_CHAIN ? BW_OFF_BAR_CHAIN : BW_OFF_BAR_DW2;
-  const uint32_t bar_w = base + off_bar, bar_rdy = bar_w + 8, bar_done = bar_w + 16;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + off_bar + 64);
+  opaque(base);
+  const uint32_t sQ = base + OFF_QR, bar0 = base + OFF_BARS;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + OFF_BARS + 192);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  DropCfg drop = a.drop;
-  if (DROP) resolve_seed(drop);
-  const float sdrop = DROP ? 2.f : 1.f;
-
   const long long g0 = t.total_steps * blockIdx.x / gridDim.x;
   const long long g1 = t.total_steps * (blockIdx.x + 1) / gridDim.x;
   const int nsteps = (int)(g1 - g0);
+  const int N = a.N, BN = a.B * a.N;
 
   if (threadIdx.x == 0) {
-    mbar_init(bar_w, 1);
-    mbar_init(bar_rdy, NTHREADS);
-    mbar_init(bar_done, 1);
+    mbar_init(bar0 + BwdBars::w, 1);
+    for (uint32_t b = BwdBars::rdyA; b <= BwdBars::rdyE; b += 8) mbar_init(bar0 + b, F_NEPI);
+    for (uint32_t b = BwdBars::doneA; b <= BwdBars::doneE; b += 8) mbar_init(bar0 + b, 1);
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(bar0 + BwdBars::q + 8 * i, 1);
+      mbar_init(bar0 + BwdBars::qe + 8 * i, F_NEPI);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), TMEM_COLS);
+  if (warp == 16) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const bool issuer = threadIdx.x == 0;
-  if (issuer && nsteps > 0) {
-    mbar_expect_tx(bar_w, W1_BYTES + W2_BYTES);
-    bulk_g2s(sW1, t.w1img, W1_BYTES, bar_w);
-    bulk_g2s(sW2, t.w2img, W2_BYTES, bar_w);
-  }
 
-  const int q = warp >> 2;
-  const int row = (warp & 3) * 32 + lane;
-  const uint32_t tlane = (uint32_t)((warp & 3) * 32) << 16;
-  const int BN = a.B * a.N;
-  uint32_t prdy = 0, pdone = 0;
-
-  // publish this thread's smem writes + TMEM reads, let thread 0 issue a batch of MMAs, wait for them
-  auto sync_issue = [&](auto&& issue_fn) {
-    fence_async_smem();
-    tc_fence_before();
-    mbar_arrive(bar_rdy);
-    if (issuer) {
-      mbar_wait(bar_rdy, prdy);
+  if (warp >= 16) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(F_REGS_CTL));
+    const uint32_t ub = (smem_u32(smem_raw) + 1023u) & ~1023u;   // warp-uniform copy of `base`
+    const uint32_t ubar = ub + OFF_BARS;
+    if (warp == 17 && nsteps > 0) {
+      // =============================== TMA loader: weight images, Q ring =============================
+      if (CH) {
+        mbar_expect_tx_elect(ubar + BwdBars::w, W1_BYTES + W2_BYTES);
+        bulk_g2s_elect(ub + OFF_W1, t.w1img, W1_BYTES, ubar + BwdBars::w);
+        bulk_g2s_elect(ub + OFF_W2, t.w2img, W2_BYTES, ubar + BwdBars::w);
+      } else {
+        mbar_expect_tx_elect(ubar + BwdBars::w, W1_BYTES);
+        bulk_g2s_elect(ub + OFF_W1, t.w1img, W1_BYTES, ubar + BwdBars::w);
+      }
+      int q_tile = (int)(g0 / N), q_s = (int)(g0 % N);
+      for (int it = 0; it < nsteps; ++it) {
+        const int st = it % QS;
+        if (it >= QS) mbar_wait(ubar + BwdBars::qe + 8 * st, (it / QS - 1) & 1);
+        const int j0 = (q_tile * TILE) / N;
+        const int rl = min(q_tile * TILE + TILE - 1, BN - 1);
+        const int nj = rl / N - j0 + 1;
+        const uint32_t bar = ubar + BwdBars::q + 8 * st;
+        const uint32_t dst = ub + OFF_QR + (uint32_t)st * F_QSTAGE;
+        mbar_expect_tx_elect(bar, (uint32_t)nj * F_QROW);
+        for (int j = 0; j < nj; ++j)
+          bulk_g2s_elect(dst + (uint32_t)j * F_QROW, a.Q + ((size_t)(j0 + j) * N + q_s) * K0, F_QROW, bar);
+        if (++q_s == N) { q_s = 0; ++q_tile; }
+      }
+    } else if (warp == 16 && nsteps > 0) {
+      // =============================== MMA issuer ======================================================
+      uint64_t dH0 = umma_desc(ub + OFF_H0T), dW1 = umma_desc(ub + OFF_W1);
+      auto m1 = [&]() {   // D1 = H0' W1'^T  -> CHAIN: RA, DW2: R (both column 0)
+        if (elect_one()) {
+          opaque(dH0); opaque(dW1);
+#pragma unroll
+          for (uint32_t ks = 0; ks < KSTEPS1; ++ks) {
+            const uint32_t blk = ks >> 2, j = ks & 3;
+            umma_bf16(tmem, dH0 + ((blk * A_BLK + j * 32) >> 4), dW1 + ((blk * W1_BLK + j * 32) >> 4),
+                      umma_idesc(N1), ks);
+          }
+          umma_commit(ubar + BwdBars::doneA);
+        }
+        __syncwarp();
+      };
+      mbar_wait(ubar + BwdBars::w, 0);
+      mbar_wait(ubar + BwdBars::rdyA, 0);
       tc_fence_after();
-      issue_fn();
-      umma_commit(bar_done);
-    }
-    prdy ^= 1;
-    mbar_wait(bar_done, pdone);
-    pdone ^= 1;
-    tc_fence_after();
-  };
-
-  // CHAIN: the H0 tile is private to H0; its bias columns (96,97 = 1) and the never-written columns
-  // 98..127 (read as unused rows by the transposed dW1 product) are initialised once
-  if (MODE == BWD_CHAIN && nsteps > 0 && q == 0) {
-    st_ones_chunk(sA0 + swz_chunk(row, 96, A_BLK));
-    st_zero_chunk(sA0 + swz_chunk(row, 104, A_BLK));
-    st_zero_chunk(sA0 + swz_chunk(row, 112, A_BLK));
-    st_zero_chunk(sA0 + swz_chunk(row, 120, A_BLK));
-  }
-
-  float Preg[Q0];
-  uint32_t dAggp[Q2 / 2];       // bf16x2 pairs of dAgg[r][h*96 + q*24 + ..], h = 0, 1
-  float dPacc[MODE == BWD_CHAIN ? Q0 : 1];
-  float db2acc0 = 0.f, db2acc1 = 0.f;
-  int cur_tile = -1, r = 0, jet = 0;
-  bool valid = false;
-  bool first_mma = true;
-
-  auto flush_dP = [&]() {
-    if constexpr (MODE == BWD_CHAIN) {
-      if (cur_tile >= 0 && valid) {
-        float* dst = a.dP + (size_t)r * K0 + q * 8;
+      m1();
+      if constexpr (CH) {
+        uint64_t dW2 = umma_desc(ub + OFF_W2);
+        for (int it = 0; it < nsteps; ++it) {
+          const uint32_t par = it & 1;
+          // ---- M2: D2 = H1'(TMEM RA) W2'^T -> RB ---------------------------------------------------------
+          mbar_wait(ubar + BwdBars::rdyB, par);
+          tc_fence_after();
+          if (elect_one()) {
+            opaque(dW2);
 #pragma unroll
-        for (int c = 0; c < Q0; ++c) atomicAdd(dst + 32 * (c >> 3) + (c & 7), dPacc[c]);
-      }
-    }
-  };
-  auto load_tile = [&](int tile) {
-    flush_dP();
-    cur_tile = tile;
-    r = tile * TILE + row;
-    valid = r < BN;
-    const int rc = valid ? r : BN - 1;
-    jet = rc / a.N;
-    // column ownership: chunks 4c + q, i.e. columns 32c + 8q + [0, 8) (edge_tc_common.cuh)
+            for (uint32_t ks = 0; ks < KSTEPS2; ++ks) {
+              const uint32_t blk = ks >> 2, j = ks & 3;
+              umma_bf16_ts(tmem + C_RB, tmem + C_RA + ks * 8, dW2 + ((blk * W2_BLK + j * 32) >> 4), umma_idesc(N2), ks);
+            }
+            umma_commit(ubar + BwdBars::doneB);
+          }
+          __syncwarp();
+          // ---- M3: dH1 = G2'(TMEM RB) W2' (B = W2 image read MN-major: N = 160 inputs, K = 192 outputs) -> RA
+          mbar_wait(ubar + BwdBars::rdyC, par);
+          tc_fence_after();
+          if (elect_one()) {
+            uint64_t dB = umma_desc_mn(ub + OFF_W2, W2_BLK);
+            opaque(dB);
 #pragma unroll
-    for (int c = 0; c < Q0 / 4; ++c) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(a.P + (size_t)rc * K0 + q * 8 + 32 * (c >> 1) + 4 * (c & 1)));
-      Preg[4 * c] = v.x; Preg[4 * c + 1] = v.y; Preg[4 * c + 2] = v.z; Preg[4 * c + 3] = v.w;
-    }
+            for (uint32_t ks = 0; ks < N2 / 16; ++ks)
+              umma_bf16_ts(tmem + C_RA, tmem + C_RB + ks * 8, dB + ((ks * 2048) >> 4), umma_idesc_t(N1, 0, 1), ks);
+            umma_commit(ubar + BwdBars::doneC);
+          }
+          __syncwarp();
+          // ---- M5: dW1^T += H0'^T G1' (both MN-major from shared memory); M4: dH0 = G1'(TMEM RA) W1' -> RB+96
+          mbar_wait(ubar + BwdBars::rdyD, par);
+          tc_fence_after();
+          if (elect_one()) {
+            uint64_t dA = umma_desc_mn(ub + C_OFF_H0, A_BLK), dB = umma_desc_mn(ub + C_OFF_X, A_BLK);
+            opaque(dA); opaque(dB);
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {   // this thread's layer-2 columns: h*96 + 32c + 8q + [0, 8)
-      const float* dg = a.dagg + (size_t)rc * N2 + h * NH2 + q * 8;
+            for (uint32_t ks = 0; ks < TILE / 16; ++ks)
+              umma_bf16(tmem + C_PW1, dA + ((ks * 2048) >> 4), dB + ((ks * 2048) >> 4), umma_idesc_t(N1, 1, 1),
+                        (it > 0 || ks > 0) ? 1u : 0u);
+            umma_commit(ubar + BwdBars::doneD5);
+            uint64_t dW = umma_desc_mn(ub + OFF_W1, W1_BLK);
+            opaque(dW);
 #pragma unroll
-      for (int c = 0; c < QH / 4; ++c) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(dg + 32 * (c >> 1) + 4 * (c & 1)));
-        dAggp[h * (QH / 2) + 2 * c] = pack_bf16(v.x, v.y);
-        dAggp[h * (QH / 2) + 2 * c + 1] = pack_bf16(v.z, v.w);
-      }
-    }
-    if constexpr (MODE == BWD_CHAIN) {
+            for (uint32_t ks = 0; ks < N1 / 16; ++ks)
+              umma_bf16_ts(tmem + C_RB + NH2, tmem + C_RA + ks * 8, dW + ((ks * 2048) >> 4), umma_idesc_t(K0, 0, 1), ks);
+            umma_commit(ubar + BwdBars::doneD4);
+          }
+          __syncwarp();
+          // ---- M1 of the next step (its H0' tile is built under M4) ---------------------------------------------
+          if (it + 1 < nsteps) {
+            mbar_wait(ubar + BwdBars::rdyA, (it + 1) & 1);
+            tc_fence_after();
+            m1();
+          }
+          // ---- M7: per-jet column sums of G0' = rows 98+j of H0'^T G0' -> RB[0,96) --------------------------------
+          mbar_wait(ubar + BwdBars::rdyE, par);
+          tc_fence_after();
+          if (elect_one()) {
+            uint64_t dA = umma_desc_mn(ub + C_OFF_H0, A_BLK), dB = umma_desc_mn(ub + C_OFF_X, A_BLK);
+            opaque(dA); opaque(dB);
 #pragma unroll
-      for (int c = 0; c < Q0; ++c) dPacc[c] = 0.f;
-    }
-  };
-
-  if (issuer && nsteps > 0) mbar_wait(bar_w, 0);
-
-  for (int it = 0; it < nsteps; ++it) {
-    const long long g = g0 + it;
-    const int tile = (int)(g / a.N), s = (int)(g % a.N);
-    if (tile != cur_tile) load_tile(tile);
-    const uint64_t pair = (uint64_t)(valid ? r : 0) * a.N + s;
-    const float mfac = valid ? (a.mask ? a.mask[(size_t)jet * a.N + s] : 1.f) * a.out_scale : 0.f;
-    uint32_t k0w = 0;           // keep words (common.cuh edge_drop_*): layer 0
-    u4 bits{0, 0, 0, 0};        // x,y: layer 1; z / w: layer 2 low / high half
-    if (DROP) {
-      k0w = edge_drop_bits(drop.seed, pair, q, 0).x;
-      bits = edge_drop_bits(drop.seed, pair, q, 1);
-    }
-
-    // ---- H0 tile; remember the sign bits of the 24 columns this thread owns -----------------------------
-    uint32_t pos0 = 0;
-    {
-      const float4* qp = reinterpret_cast<const float4*>(a.Q + ((size_t)jet * a.N + s) * K0 + q * 8);
-#pragma unroll
-      for (int c8 = 0; c8 < Q0 / 8; ++c8) {
-        const float4 q0 = __ldg(qp + 8 * c8), q1 = __ldg(qp + 8 * c8 + 1);
-        float v[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int le = c8 * 8 + e;
-          float x = v[e] + Preg[le];
-          if (x > 0.f) pos0 |= 1u << le;
-          x = fmaxf(x, a.alpha * x);
-          if (DROP) x = apply_keep(x, keep_one(k0w, le));
-          v[e] = x;
+            for (uint32_t ks = 0; ks < TILE / 16; ++ks)
+              umma_bf16(tmem + C_RB, dA + ((ks * 2048) >> 4), dB + ((ks * 2048) >> 4), umma_idesc_t(K0, 1, 1), ks);
+            umma_commit(ubar + BwdBars::doneE);
+          }
+          __syncwarp();
         }
-        st_chunk(sA0 + swz_chunk(row, 32 * c8 + 8 * q, A_BLK), v);
-      }
-      if (MODE == BWD_DW2 && q == 0) {   // DW2 builds H0 inside the G2 region: bias columns every step
-        st_ones_chunk(sA0 + swz_chunk(row, 96, A_BLK));
-        st_zero_chunk(sA0 + swz_chunk(row, 104, A_BLK));
-      }
-    }
-    sync_issue([&]() {   // D1 = H0 * W1^T
+      } else {
+        for (int it = 0; it < nsteps; ++it) {
+          const uint32_t par = it & 1;
+          mbar_wait(ubar + BwdBars::rdyB, par);          // E1(it) done: H1'(it) in shared memory, D1 free
+          if (it + 1 < nsteps) {                          // layer 1 runs one step ahead
+            mbar_wait(ubar + BwdBars::rdyA, (it + 1) & 1);
+            tc_fence_after();
+            m1();
+          }
+          // ---- M6: dW2 += G2'^T H1' (two M blocks over the G2' columns, N = 176, K = 128 rows) ----------------------
+          mbar_wait(ubar + BwdBars::rdyC, par);          // G2'(it) built
+          tc_fence_after();
+          if (elect_one()) {
+            uint64_t dA = umma_desc_mn(ub + D_OFF_G2, A_BLK), dB = umma_desc_mn(ub + D_OFF_H1 + par * H1_BYTES, A_BLK);
+            opaque(dA); opaque(dB);
 #pragma unroll
-      for (int ks = 0; ks < KSTEPS1; ++ks) {
-        const uint32_t blk = ks >> 2, j = ks & 3;
-        umma_bf16(tmem + RS_COL, umma_desc(sA0 + blk * A_BLK + j * 32), umma_desc(sW1 + blk * W1_BLK + j * 32),
-                  umma_idesc(N1), ks > 0);
-      }
-    });
-    // ---- e1: H1 tile, sign bits of this thread's 40 columns ----------------------------------------------
-    uint32_t pos1[2] = {0, 0};
-    {
-      float v[Q1];
-      tmem_ld8x5(tmem + tlane + RS_COL + q * 8, v);
+            for (uint32_t mb = 0; mb < 2; ++mb)
 #pragma unroll
-      for (int le = 0; le < Q1; ++le) {
-        float x = v[le];
-        if (x > 0.f) pos1[le >> 5] |= 1u << (le & 31);
-        x = fmaxf(x, a.alpha * x);
-        if (DROP) x = apply_keep(x, keep_one(le < 32 ? bits.x : bits.y, le & 31));
-        v[le] = x;
-      }
-#pragma unroll
-      for (int c = 0; c < Q1 / 8; ++c) st_chunk(sA1 + swz_chunk(row, 32 * c + 8 * q, A_BLK), v + 8 * c);
-      // constant bias columns of the H1 tile: DW2 never overwrites them, CHAIN reuses the region for G2/G1
-      if ((MODE == BWD_CHAIN || it == 0) && q == 1) {
-        st_ones_chunk(sA1 + swz_chunk(row, 160, A_BLK));
-        st_zero_chunk(sA1 + swz_chunk(row, 168, A_BLK));
-      }
-    }
-    sync_issue([&]() {   // D2 = H1 * W2^T
-#pragma unroll
-      for (int ks = 0; ks < KSTEPS2; ++ks) {
-        const uint32_t blk = ks >> 2, j = ks & 3;
-        umma_bf16(tmem + RS_COL, umma_desc(sA1 + blk * A_BLK + j * 32), umma_desc(sW2 + blk * W2_BLK + j * 32),
-                  umma_idesc(N2), ks > 0);
-      }
-    });
-    // ---- e2': G2 = dAgg * m * f'(D2) * keep2  (divided by s, see header) -> bf16 tile --------------------
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      float v[QH];
-      tmem_ld8x3(tmem + tlane + RS_COL + h * NH2 + q * 8, v);
-#pragma unroll
-      for (int e = 0; e < QH; ++e) {
-        const uint32_t pk = dAggp[h * (QH / 2) + (e >> 1)];
-        const float dg = __uint_as_float((e & 1) ? (pk & 0xFFFF0000u) : (pk << 16));
-        float gval = dg * mfac * (v[e] > 0.f ? 1.f : a.alpha);
-        if (DROP) gval = apply_keep(gval, keep_one(h ? bits.w : bits.z, e));
-        v[e] = gval;
-      }
-#pragma unroll
-      for (int c8 = 0; c8 < QH / 8; ++c8) st_chunk(sG2 + swz_chunk(row, h * NH2 + 32 * c8 + 8 * q, A_BLK), v + c8 * 8);
-    }
-
-    if constexpr (MODE == BWD_DW2) {
-      // db2 partial column sums straight from the bf16 G2 tile (thread -> 2 columns x 32 rows)
-      asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory");
-      if (threadIdx.x < 384) {
-        const int cp = threadIdx.x % 96, rq = threadIdx.x / 96;
-        const uint32_t col = 2 * cp;
-#pragma unroll 8
-        for (int rr = 0; rr < 32; ++rr) {
-          const uint32_t rw = rq * 32 + rr;
-          uint32_t w;
-          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(sG2 + swz_chunk(rw, col, A_BLK) + (col & 7) * 2));
-          db2acc0 += __uint_as_float(w << 16);
-          db2acc1 += __uint_as_float(w & 0xFFFF0000u);
+              for (uint32_t ks = 0; ks < TILE / 16; ++ks)
+                umma_bf16(tmem + (mb ? D_PW2B : D_PW2A), dA + ((mb * 2 * A_BLK + ks * 2048) >> 4),
+                          dB + ((ks * 2048) >> 4), umma_idesc_t(NDW, 1, 1), (it > 0 || ks > 0) ? 1u : 0u);
+            umma_commit(ubar + BwdBars::doneC);
+          }
+          __syncwarp();
         }
       }
-      const bool acc_flag = !first_mma;
-      sync_issue([&]() {   // dW2[n2][n1] += G2^T H1 : two M=128 blocks over G2 columns, N = 160, K = 128 rows
+    }
+  } else {
+    // =============================== epilogue warps ====================================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(F_REGS_EPI));
+    if (nsteps > 0) {
+      const int q = warp >> 2;
+      const int row = (warp & 3) * 32 + lane;
+      const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)q * 8;   // chunk q of this lane
+      const uint32_t tp = tl - (uint32_t)q * 4;                                            // packed column 4q
+      const float cg = (1.f - a.alpha) / (1.f + a.alpha);
+      const float ssl = (DROP ? 2.f : 1.f) * 0.5f * (1.f + a.alpha);                      // sd * sl
+      DropCfg drop = a.drop;
+      if (DROP) resolve_seed(drop);
+      const uint32_t F_NEG = bf16x2_dup(1.f - cg), F_POS = bf16x2_dup(1.f + cg);
+      // this thread's two 16-byte positions inside a swizzled 128-byte tile row (chunk 4c+q -> xs{c&1} + (c>>1)*A_BLK)
+      uint32_t xs0 = base + (uint32_t)row * 128u + ((uint32_t)(q ^ (row & 7)) << 4);
+      uint32_t xs1 = base + (uint32_t)row * 128u + ((uint32_t)((4 + q) ^ (row & 7)) << 4);
+      opaque(xs0);
+      opaque(xs1);
+      const uint32_t sH0 = base + OFF_H0T;
+      const int bar_id = 1 + (warp & 3);      // named barrier of the four warps sharing this TMEM lane quarter
+
+      float Preg[Q0];
+      uint32_t dAggp[Q2 / 2];                 // bf16x2 pairs of dAgg[r][h*96 + 32c + 8q + ..]
+      float dPacc[CH ? Q0 : 1];
+      uint32_t s0 = 0, k0w = 0;               // CHAIN: pre0 sign word / layer-0 keep word of the current step
+      uint32_t s0_next = 0, k0w_next = 0;     // ... of the step whose H0' was built last
+
+      // ---- H0' builder state -------------------------------------------------------------------------------
+      int h_tile = (int)(g0 / N), h_s = (int)(g0 % N), h_loaded = -1, h_r = 0;
+      uint32_t h_qoff = 0;
+      auto write_onehot = [&](int tile) {   // CHAIN: constant-1 columns 96,97 and one-hot jet columns 98+j of the H0' tile
+        if (q == 0) {
+          const int r = tile * TILE + row;
+          const int js = (r < BN ? r : BN - 1) / N - (tile * TILE) / N;   // 0 .. F_QJ-1
+          uint32_t w[8];
 #pragma unroll
-        for (int mb = 0; mb < 2; ++mb)
+          for (int i = 0; i < 8; ++i) w[i] = 0u;
+          w[0] = 0x3F803F80u;
+          if (r < BN) {
 #pragma unroll
-          for (int ks = 0; ks < TILE / 16; ++ks)
-            umma_bf16(tmem + (mb == 0 ? RW2A_COL : RW2B_COL), umma_desc_mn(sG2 + mb * 2 * A_BLK + ks * 2048, A_BLK),
-                      umma_desc_mn(sA1 + ks * 2048, A_BLK), umma_idesc_t(N1, 1, 1), (acc_flag || ks > 0) ? 1u : 0u);
-      });
-      first_mma = false;
-    } else {
-      sync_issue([&]() {   // dH1 = G2 * W2   (B = W2 image read MN-major: N = 160 inputs, K = 192 outputs)
-#pragma unroll
-        for (int ks = 0; ks < N2 / 16; ++ks) {
-          const uint32_t blk = ks >> 2, j = ks & 3;
-          umma_bf16(tmem + RS_COL, umma_desc(sG2 + blk * A_BLK + j * 32), umma_desc_mn(sW2 + ks * 2048, W2_BLK),
-                    umma_idesc_t(N1, 0, 1), ks > 0);
+            for (int i = 1; i < 8; ++i)
+              if (i == ((2 + js) >> 1)) w[i] = 0x3F80u << (16 * (js & 1));
+          }
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sH0 + swz_chunk(row, 96, A_BLK)), "r"(w[0]),
+                       "r"(w[1]), "r"(w[2]), "r"(w[3]));
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sH0 + swz_chunk(row, 104, A_BLK)), "r"(w[4]),
+                       "r"(w[5]), "r"(w[6]), "r"(w[7]));
+          st_zero_chunk(sH0 + swz_chunk(row, 112, A_BLK));
+          st_zero_chunk(sH0 + swz_chunk(row, 120, A_BLK));
         }
-      });
-      // ---- e3: G1 = dH1 * f'(D1) * keep1 (divided by s) -> bf16 tile over the G2 tile --------------------
-      {
+      };
+      auto build_h0 = [&](int it) {
+        if (h_tile != h_loaded) {
+          h_loaded = h_tile;
+          const int r = h_tile * TILE + row;
+          const int rc = r < BN ? r : BN - 1;
+          h_r = rc;
+          h_qoff = (uint32_t)(rc / N - (h_tile * TILE) / N) * F_QROW + (uint32_t)q * 32u;
+          const float* p = a.P + (size_t)rc * K0 + q * 8;
+#pragma unroll
+          for (int c = 0; c < Q0 / 8; ++c) {
+            const float4 v0 = __ldg(reinterpret_cast<const float4*>(p + 32 * c));
+            const float4 v1 = __ldg(reinterpret_cast<const float4*>(p + 32 * c + 4));
+            Preg[8 * c] = v0.x; Preg[8 * c + 1] = v0.y; Preg[8 * c + 2] = v0.z; Preg[8 * c + 3] = v0.w;
+            Preg[8 * c + 4] = v1.x; Preg[8 * c + 5] = v1.y; Preg[8 * c + 6] = v1.z; Preg[8 * c + 7] = v1.w;
+          }
+        }
+        if (DROP) k0w_next = edge_drop_bits(drop.seed, (uint64_t)h_r * N + h_s, q, 0).x;
+        mbar_wait(bar0 + BwdBars::q + 8 * (it % QS), (it / QS) & 1);
+        const uint32_t qa = sQ + (uint32_t)(it % QS) * F_QSTAGE + h_qoff;
+        s0_next = 0;
+#pragma unroll
+        for (int c = 0; c < Q0 / 8; ++c) {
+          float v[8];
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                       : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(qa + c * 128));
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                       : "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(qa + c * 128 + 16));
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) {
+            w[e >> 1] = pack_bf16(lrelu_g(v[e] + Preg[8 * c + e], cg), lrelu_g(v[e + 1] + Preg[8 * c + e + 1], cg));
+            if (CH) sign_put(s0_next, w[e >> 1], 4 * c + (e >> 1));
+            if (DROP) w[e >> 1] &= keep_pair(k0w_next, 8 * c + e);
+          }
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(((c & 1) ? xs1 : xs0) + OFF_H0T + (c >> 1) * A_BLK),
+                       "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]));
+        }
+        mbar_arrive(bar0 + BwdBars::qe + 8 * (it % QS));
+        fence_async_smem();
+        mbar_arrive(bar0 + BwdBars::rdyA);
+        if (++h_s == N) { h_s = 0; ++h_tile; }
+      };
+
+      // ---- state of the current step ------------------------------------------------------------------------
+      int c_tile = h_tile, c_s = h_s, c_r = 0, c_jet = 0;
+      bool c_valid = false;
+      auto enter_tile = [&]() {   // rows of the tile the current step belongs to; their dAgg
+        const int r = c_tile * TILE + row;
+        c_valid = r < BN;
+        c_r = c_valid ? r : BN - 1;
+        c_jet = c_r / N;
+        const float* dg = a.dagg + (size_t)c_r * N2 + q * 8;
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int c = 0; c < QH / 8; ++c) {
+            const float4 v0 = __ldg(reinterpret_cast<const float4*>(dg + h * NH2 + 32 * c));
+            const float4 v1 = __ldg(reinterpret_cast<const float4*>(dg + h * NH2 + 32 * c + 4));
+            dAggp[h * (QH / 2) + 4 * c] = pack_bf16(v0.x, v0.y);
+            dAggp[h * (QH / 2) + 4 * c + 1] = pack_bf16(v0.z, v0.w);
+            dAggp[h * (QH / 2) + 4 * c + 2] = pack_bf16(v1.x, v1.y);
+            dAggp[h * (QH / 2) + 4 * c + 3] = pack_bf16(v1.z, v1.w);
+          }
+      };
+      enter_tile();
+      if (CH) {
+#pragma unroll
+        for (int c = 0; c < Q0; ++c) dPacc[c] = 0.f;
+        write_onehot(c_tile);
+      } else {
+        if (q == 0) {
+          st_ones_chunk(sH0 + swz_chunk(row, 96, A_BLK));
+          st_zero_chunk(sH0 + swz_chunk(row, 104, A_BLK));
+        }
+        if (q == 1) {   // constant-1 columns 160,161 of both H1' buffers (db2 column of the dW2 accumulators)
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            st_ones_chunk(base + D_OFF_H1 + b * H1_BYTES + swz_chunk(row, 160, A_BLK));
+            st_zero_chunk(base + D_OFF_H1 + b * H1_BYTES + swz_chunk(row, 168, A_BLK));
+          }
+        }
+      }
+      build_h0(0);
+      s0 = s0_next;
+      k0w = k0w_next;
+      if (!CH && nsteps > 1) {   // DW2: layer 1 runs one step ahead
+        mbar_wait(bar0 + BwdBars::doneA, 0);
+        build_h0(1);
+      }
+
+      int p_j0 = 0, p_nj = 0, p_s = 0;   // CHAIN: the step whose per-jet dQ sums sit in RB[0,96)
+      auto dq_readout = [&]() {          // rows 98+j of RB[0,96) -> dQ[(j0+j)*N + s]: a handful of lanes
+        if ((warp & 3) == 3) {
+          float v[QH];
+          tmem_ld8x3(tl + C_RB, v);
+          if (lane >= 2 && lane < 2 + p_nj) {
+            float* dq = a.dQ + ((size_t)(p_j0 + lane - 2) * N + p_s) * K0 + q * 8;
+#pragma unroll
+            for (int e = 0; e < QH; ++e) atomicAdd(dq + 32 * (e >> 3) + (e & 7), v[e] * ssl);
+          }
+        }
+      };
+
+      for (int it = 0; it < nsteps; ++it) {
+        const uint32_t par = it & 1;
+        const float mfac = c_valid ? (a.mask ? __ldg(a.mask + (size_t)c_jet * N + c_s) : 1.f) * a.out_scale : 0.f;
+        u4 kb{0, 0, 0, 0};
+        if (DROP) kb = edge_drop_bits(drop.seed, (uint64_t)c_r * N + c_s, q, 1);
+
+        // ---- E1: D1 -> H1' (+ sign words): chunks 0..2, then 3..4 (24 / 16 live values) -----------------------------
+        uint32_t s1[2] = {0, 0};
+        mbar_wait(bar0 + BwdBars::doneA, par);
+        tc_fence_after();
+        auto e1_round = [&](auto RND) {
+          constexpr int rnd = decltype(RND)::value, nc = rnd == 0 ? 3 : 2, c0 = rnd * 3;
+          float v[8 * nc];
+          if constexpr (rnd == 0) tmem_ld8x3(tl + (CH ? C_RA : D_R), v);
+          else tmem_ld8x2(tl + (CH ? C_RA : D_R) + 96, v);
+          uint32_t w[4 * nc];
+#pragma unroll
+          for (int i = 0; i < 8 * nc; i += 2) {
+            const int el = 8 * c0 + i, p = el >> 1;   // element / pair index inside the thread's 40-wide slice
+            w[i >> 1] = pack_bf16(lrelu_g(v[i], cg), lrelu_g(v[i + 1], cg));
+            if (CH) sign_put(s1[p >> 4], w[i >> 1], p & 15);
+            if (DROP) w[i >> 1] &= keep_pair(el < 32 ? kb.x : kb.y, el & 31);
+          }
+          if constexpr (CH) {
+            // in place: packed columns 16c+4q.. overlap fp32 columns other warps of this lane quarter read
+            // in round 0 (chunks 0..2); by round 1 everything below column 96 has been consumed
+            if constexpr (rnd == 0) named_bar_sync(bar_id, 128);
+#pragma unroll
+            for (int c = 0; c < nc; ++c)
+              tmem_st4(tp + C_RA + 16 * (c0 + c), w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+          } else {
+#pragma unroll
+            for (int c = 0; c < nc; ++c) {
+              const int cc = c0 + c;
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(((cc & 1) ? xs1 : xs0) + D_OFF_H1 + par * H1_BYTES + (cc >> 1) * A_BLK),
+                           "r"(w[4 * c]), "r"(w[4 * c + 1]), "r"(w[4 * c + 2]), "r"(w[4 * c + 3]));
+            }
+          }
+        };
+        e1_round(std::integral_constant<int, 0>{});
+        e1_round(std::integral_constant<int, 1>{});
+        if constexpr (CH) {
+          if (q == 0) tmem_st8(tl + C_RA + N1 / 2, 0x3F803F80u, 0u);   // bias K-step: columns 160,161 = 1.0
+          tmem_st_wait();
+          // dQ of the previous step must leave RB before M2 of this step overwrites it
+          if (it >= 1) {
+            mbar_wait(bar0 + BwdBars::doneE, (it - 1) & 1);
+            tc_fence_after();
+            dq_readout();
+            if (c_s == 0) write_onehot(c_tile);   // first step of a new tile: the old one-hot columns are free now
+          }
+        } else {
+          fence_async_smem();
+        }
+        tc_fence_before();
+        mbar_arrive(bar0 + BwdBars::rdyB);
+
+        // ---- G2' = dAgg * m * keep2 * (1 + cg sgn D2) ----------------------------------------------------------------
+        const uint32_t U_POS = bf16x2_dup(mfac * (1.f + cg)), U_NEG = bf16x2_dup(mfac * (1.f - cg));
+        if constexpr (CH) {
+          uint2 sb{0, 0};
+          mbar_wait(bar0 + BwdBars::doneB, par);
+          tc_fence_after();
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float v[QH];
+            tmem_ld8x3(tl + C_RB + h * NH2, v);
+            uint32_t sw = 0, gw[QH / 2];
+#pragma unroll
+            for (int i = 0; i < QH; i += 2) {
+              const int p = i >> 1;
+              const uint32_t zw = pack_bf16(v[i], v[i + 1]);
+              sign_put(sw, zw, p);
+              gw[p] = mul_bf16x2(dAggp[h * (QH / 2) + p], sel_pair(prmt(zw, 0u, 0xbb99u), U_NEG, U_POS));
+              if (DROP) gw[p] &= keep_pair(h ? kb.w : kb.z, i);
+            }
+            if (h == 0) sb.x = sw; else sb.y = sw;
+            // in place over D2: both packed halves land in fp32 columns [0,96), which round h = 0 reads
+            if (h == 0) named_bar_sync(bar_id, 128);
+#pragma unroll
+            for (int c = 0; c < QH / 8; ++c)
+              tmem_st4(tp + C_RB + h * (NH2 / 2) + 16 * c, gw[4 * c], gw[4 * c + 1], gw[4 * c + 2], gw[4 * c + 3]);
+          }
+          t.sbits[(size_t)(g0 + it) * F_NEPI + threadIdx.x] = sb;
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(bar0 + BwdBars::rdyC);
+        } else {
+          const uint2 sb = t.sbits[(size_t)(g0 + it) * F_NEPI + threadIdx.x];
+          uint32_t g2w[Q2 / 2];
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int p = 0; p < QH / 2; ++p) {
+              uint32_t gw = mul_bf16x2(dAggp[h * (QH / 2) + p], sel_pair(neg_pair_mask(h ? sb.y : sb.x, p), U_NEG, U_POS));
+              if (DROP) gw &= keep_pair(h ? kb.w : kb.z, 2 * p);
+              g2w[h * (QH / 2) + p] = gw;
+            }
+          if (it >= 1) mbar_wait(bar0 + BwdBars::doneC, (it - 1) & 1);   // M6(it-1) done: G2' tile free
+          // chunk 12h + 4c + q of the G2' tile = chunk 4(c + 3h) + q
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int c = 0; c < QH / 8; ++c) {
+              const int cc = c + 3 * h;
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(((cc & 1) ? xs1 : xs0) + D_OFF_G2 + (cc >> 1) * A_BLK),
+                           "r"(g2w[h * 12 + 4 * c]), "r"(g2w[h * 12 + 4 * c + 1]), "r"(g2w[h * 12 + 4 * c + 2]),
+                           "r"(g2w[h * 12 + 4 * c + 3]));
+            }
+          fence_async_smem();
+          mbar_arrive(bar0 + BwdBars::rdyC);
+        }
+
+        if constexpr (CH) {
+          // ---- E3: G1' = dH1 * keep1 * (1 + cg sgn D1) -> TMEM in place (A of M4) and shared memory (B of M5) ---------
+          mbar_wait(bar0 + BwdBars::doneC, par);
+          tc_fence_after();
+          auto e3_round = [&](auto RND) {
+            constexpr int rnd = decltype(RND)::value, nc = rnd == 0 ? 3 : 2, c0 = rnd * 3;
+            float v[8 * nc];
+            if constexpr (rnd == 0) tmem_ld8x3(tl + C_RA, v);
+            else tmem_ld8x2(tl + C_RA + 96, v);
+            uint32_t w[4 * nc];
+#pragma unroll
+            for (int i = 0; i < 8 * nc; i += 2) {
+              const int el = 8 * c0 + i, p = el >> 1;
+              w[i >> 1] = mul_bf16x2(pack_bf16(v[i], v[i + 1]), sel_pair(neg_pair_mask(s1[p >> 4], p & 15), F_NEG, F_POS));
+              if (DROP) w[i >> 1] &= keep_pair(el < 32 ? kb.x : kb.y, el & 31);
+            }
+            if constexpr (rnd == 0) named_bar_sync(bar_id, 128);
+#pragma unroll
+            for (int c = 0; c < nc; ++c) {
+              const int cc = c0 + c;
+              tmem_st4(tp + C_RA + 16 * cc, w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(((cc & 1) ? xs1 : xs0) + C_OFF_X + (cc >> 1) * A_BLK),
+                           "r"(w[4 * c]), "r"(w[4 * c + 1]), "r"(w[4 * c + 2]), "r"(w[4 * c + 3]));
+            }
+          };
+          e3_round(std::integral_constant<int, 0>{});
+          e3_round(std::integral_constant<int, 1>{});
+          tmem_st_wait();
+          fence_async_smem();
+          tc_fence_before();
+          mbar_arrive(bar0 + BwdBars::rdyD);
+
+          // ---- H0' of the next step under M4 (M5 has released the H0' tile and X) ---------------------------------------
+          mbar_wait(bar0 + BwdBars::doneD5, par);
+          if (it + 1 < nsteps) build_h0(it + 1);
+
+          // ---- E4: G0' = dH0 * keep0 * (1 + cg sgn pre0): dP in registers, bf16 tile for the dQ MMA ----------------------
+          mbar_wait(bar0 + BwdBars::doneD4, par);
+          tc_fence_after();
+          {
+            float v[Q0];
+            tmem_ld8x3(tl + C_RB + NH2, v);
+#pragma unroll
+            for (int c = 0; c < Q0 / 8; ++c) {
+              uint32_t w[4];
+#pragma unroll
+              for (int e = 0; e < 8; e += 2) {
+                const int p = 4 * c + (e >> 1);
+                uint32_t gw = mul_bf16x2(pack_bf16(v[8 * c + e], v[8 * c + e + 1]), sel_pair(neg_pair_mask(s0, p), F_NEG, F_POS));
+                if (DROP) gw &= keep_pair(k0w, 8 * c + e);
+                w[e >> 1] = gw;
+                dPacc[8 * c + e] += __uint_as_float(gw << 16);
+                dPacc[8 * c + e + 1] += __uint_as_float(gw & 0xFFFF0000u);
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(((c & 1) ? xs1 : xs0) + C_OFF_X + (c >> 1) * A_BLK),
+                           "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]));
+            }
+          }
+          fence_async_smem();
+          tc_fence_before();
+          mbar_arrive(bar0 + BwdBars::rdyE);
+          s0 = s0_next;
+          k0w = k0w_next;
+          // remember where this step's dQ sums belong, then advance
+          p_j0 = (c_tile * TILE) / N;
+          p_nj = min(c_tile * TILE + TILE - 1, BN - 1) / N - p_j0 + 1;
+          p_s = c_s;
+          if (++c_s == N) {
+            if (c_valid) {
+              float* dst = a.dP + (size_t)c_r * K0 + q * 8;
+#pragma unroll
+              for (int c = 0; c < Q0; ++c) atomicAdd(dst + 32 * (c >> 3) + (c & 7), dPacc[c] * ssl);
+            }
+#pragma unroll
+            for (int c = 0; c < Q0; ++c) dPacc[c] = 0.f;
+            c_s = 0;
+            ++c_tile;
+            if (it + 1 < nsteps) enter_tile();
+          }
+        } else {
+          // ---- DW2: H0' two steps ahead (layer 1 runs one step ahead of the dW2 MMA) ---------------------------------------
+          if (it + 2 < nsteps) {
+            mbar_wait(bar0 + BwdBars::doneA, (it + 1) & 1);   // M1(it+1) done: H0' tile free
+            build_h0(it + 2);
+          }
+          if (++c_s == N) {
+            c_s = 0;
+            ++c_tile;
+            if (it + 1 < nsteps) enter_tile();
+          }
+        }
+      }
+
+      // ---- drain -----------------------------------------------------------------------------------------------------------
+      if constexpr (CH) {
+        mbar_wait(bar0 + BwdBars::doneE, (nsteps - 1) & 1);
+        tc_fence_after();
+        dq_readout();
+        if (c_s != 0 && c_valid) {   // partial tile: flush dP
+          float* dst = a.dP + (size_t)c_r * K0 + q * 8;
+#pragma unroll
+          for (int c = 0; c < Q0; ++c) atomicAdd(dst + 32 * (c >> 3) + (c & 7), dPacc[c] * ssl);
+        }
+        // dW1^T accumulator: lane = H0' column k0 (< 96: dW1[:, k0]; 96: db1), column n1 = 32c + 8q + e
         float v[Q1];
-        tmem_ld8x5(tmem + tlane + RS_COL + q * 8, v);
+        tmem_ld8x5(tl + C_PW1, v);
 #pragma unroll
-        for (int le = 0; le < Q1; ++le) {
-          float gval = v[le] * (((pos1[le >> 5] >> (le & 31)) & 1u) ? 1.f : a.alpha);
-          if (DROP) gval = apply_keep(gval, keep_one(le < 32 ? bits.x : bits.y, le & 31));
-          v[le] = gval;
+        for (int i = 0; i < Q1; ++i) {
+          const int n1 = 32 * (i >> 3) + 8 * q + (i & 7);
+          if (row < K0) atomicAdd(a.dW1 + (size_t)n1 * K0 + row, v[i] * ssl * ssl);
+          else if (row == K0) atomicAdd(a.db1 + n1, v[i] * ssl);
         }
+      } else {
+        mbar_wait(bar0 + BwdBars::doneC, (nsteps - 1) & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int mb = 0; mb < 2; ++mb) {
+          const int n2 = mb * 128 + row;
+#pragma unroll 1
+          for (int c = 0; c < 6; ++c) {
+            const int col = 32 * c + 8 * q;   // accumulator column n1 (160 = db2)
+            if (col >= NDW) continue;         // warp-uniform
+            float v[8];
+            tmem_ld8(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (mb ? D_PW2B : D_PW2A) + col, v);
+            if (n2 < N2) {
 #pragma unroll
-        for (int c = 0; c < Q1 / 8; ++c) st_chunk(sA1 + swz_chunk(row, 32 * c + 8 * q, A_BLK), v + 8 * c);
-      }
-      const bool acc_flag = !first_mma;
-      sync_issue([&]() {
-        // dH0 = G1 * W1   (B = W1 image read MN-major: N = 96 inputs, K = 160 outputs)
-#pragma unroll
-        for (int ks = 0; ks < N1 / 16; ++ks) {
-          const uint32_t blk = ks >> 2, j = ks & 3;
-          umma_bf16(tmem + RS_COL, umma_desc(sA1 + blk * A_BLK + j * 32), umma_desc_mn(sW1 + ks * 2048, W1_BLK),
-                    umma_idesc_t(K0, 0, 1), ks > 0);
-        }
-        // dW1^T[k0][n1] += H0^T G1   (M = 128 columns of the H0 tile incl. the constant-1 columns, K = 128 rows)
-#pragma unroll
-        for (int ks = 0; ks < TILE / 16; ++ks)
-          umma_bf16(tmem + RW1_COL, umma_desc_mn(sA0 + ks * 2048, A_BLK), umma_desc_mn(sA1 + ks * 2048, A_BLK),
-                    umma_idesc_t(N1, 1, 1), (acc_flag || ks > 0) ? 1u : 0u);
-      });
-      first_mma = false;
-      // ---- e4: G0 = dH0 * s * f'(pre0) * keep0 -> dP (registers), dQ (red.global) ---------------------------
-      {
-        float* dq = a.dQ + ((size_t)jet * a.N + s) * K0 + q * 8;
-        float v[Q0];
-        tmem_ld8x3(tmem + tlane + RS_COL + q * 8, v);
-#pragma unroll
-        for (int e = 0; e < Q0; ++e) {
-          float gval = v[e] * sdrop * (((pos0 >> e) & 1u) ? 1.f : a.alpha);
-          if (DROP) gval = apply_keep(gval, keep_one(k0w, e));
-          if (valid) {
-            dPacc[e] += gval;
-            if (gval != 0.f) atomicAdd(dq + 32 * (e >> 3) + (e & 7), gval);
+              for (int e = 0; e < 8; ++e) {
+                if (col + e < N1) atomicAdd(a.dW2 + (size_t)n2 * N1 + col + e, v[e] * ssl * ssl);
+                else if (col + e == N1) atomicAdd(a.db2 + n2, v[e] * ssl);
+              }
+            }
           }
         }
       }
     }
   }
-  flush_dP();
 
-  // ---- flush the TMEM weight-gradient accumulators ----------------------------------------------------
-  if (nsteps > 0) {
-    tc_fence_after();
-    if constexpr (MODE == BWD_CHAIN) {
-      // accumulator row m' = H0-tile column (k0 < 96: dW1[:, k0]; 96: db1), column n1
-      float v[Q1];
-      tmem_ld_cols<Q1>(tmem + tlane + RW1_COL + q * Q1, v);
-#pragma unroll
-      for (int e = 0; e < Q1; ++e) {
-        const int n1 = q * Q1 + e;
-        if (row < K0) atomicAdd(a.dW1 + (size_t)n1 * K0 + row, v[e] * sdrop * sdrop);
-        else if (row == K0) atomicAdd(a.db1 + n1, v[e] * sdrop);
-      }
-    } else {
-#pragma unroll 1
-      for (int mb = 0; mb < 2; ++mb) {
-        const int n2 = mb * 128 + row;
-        float v[Q1];
-        tmem_ld_cols<Q1>(tmem + tlane + (mb == 0 ? RW2A_COL : RW2B_COL) + q * Q1, v);
-        if (n2 < N2) {
-#pragma unroll
-          for (int e = 0; e < Q1; ++e) atomicAdd(a.dW2 + (size_t)n2 * N1 + q * Q1 + e, v[e] * sdrop * sdrop);
-        }
-      }
-      if (threadIdx.x < 384) {
-        const int cp = threadIdx.x % 96;
-        atomicAdd(a.db2 + 2 * cp, db2acc0 * sdrop);
-        atomicAdd(a.db2 + 2 * cp + 1, db2acc1 * sdrop);
-      }
-    }
-  }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
+  if (warp == 16) tmem_dealloc(tmem, TMEM_COLS);
 }
