@@ -47,9 +47,16 @@ static size_t tc_sbits_bytes(int B, int N) {   // backward: one uint2 per (step,
   return (size_t)tiles * N * F_NEPI * sizeof(uint2);
 }
 
+static int tc_num_sms() {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+}
+static size_t tc_slab_bytes() { return (size_t)tc_num_sms() * SLAB_FLOATS * sizeof(float); }
+
 size_t edge_tc_workspace_bytes(int B, int N, int H0, int H1, int H2) {
   if (H0 != K0 || H1 != N1 || H2 != N2) return 0;
-  return W1_BYTES + W2_BYTES + 1024 + tc_sbits_bytes(B, N);
+  return W1_BYTES + W2_BYTES + 1024 + tc_sbits_bytes(B, N) + 256 + tc_slab_bytes();
 }
 
 // the activation / gradient tiles hold X / (sd * sl) (dropout and leaky-relu scales), the weight images sd * sl * W
@@ -60,6 +67,7 @@ static int tc_prepare(const EdgeArgs& a, void* ws, TcArgs& t, int* grid, cudaStr
   t.w1img = img;
   t.w2img = img + W1_BYTES;
   t.sbits = reinterpret_cast<uint2*>(img + W1_BYTES + W2_BYTES);
+  t.wslab = reinterpret_cast<float*>(img + W1_BYTES + W2_BYTES + ((tc_sbits_bytes(a.B, a.N) + 255) & ~(size_t)255));
   const float s = (a.drop.p > 0.f ? 2.f : 1.f) * 0.5f * (1.f + a.alpha);
   weight_image_kernel<<<cdiv(N1 * 128, 256), 256, 0, stream>>>(a.W1, a.b1, N1, K0, 128, s, img);
   MPG_LAUNCH_CHECK();
@@ -68,9 +76,7 @@ static int tc_prepare(const EdgeArgs& a, void* ws, TcArgs& t, int* grid, cudaStr
   const long long BN = (long long)a.B * a.N;
   t.num_tiles = (int)((BN + TILE - 1) / TILE);
   t.total_steps = (long long)t.num_tiles * a.N;
-  int dev = 0, sms = 148;
-  MPG_CUDA(cudaGetDevice(&dev));
-  MPG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int sms = tc_num_sms();
   *grid = (int)(t.total_steps < sms ? t.total_steps : sms);
   return 0;
 }
@@ -116,6 +122,8 @@ int launch_edge_tc_bwd(const EdgeArgs& a, void* ws, cudaStream_t stream) {
     if (launch_bwd_one<BWD_CHAIN, false>(t, grid, C_SMEM, stream)) return 1;
     if (launch_bwd_one<BWD_DW2, false>(t, grid, D_SMEM, stream)) return 1;
   }
+  wgrad_reduce_kernel<<<cdiv(SLAB_FLOATS, 256), 256, 0, stream>>>(t.wslab, grid, a.dW1, a.db1, a.dW2, a.db2);
+  MPG_LAUNCH_CHECK();
   return 0;
 }
 

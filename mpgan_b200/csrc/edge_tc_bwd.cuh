@@ -14,14 +14,18 @@
 //          dW2 += G2'^T H1' in two M=128 TMEM accumulators; the constant-1 column of the H1' tile
 //          (N = 176) makes column 160 of them db2.  No W2 image, no second-layer MMA.
 //
-// Primed tiles are scaled: X' = X / (sd*sl) with sd = dropout scale (2 or 1) and sl = (1+alpha)/2, and
-// the weight images carry sd*sl (forward convention, edge_tc_fwd.cuh), so every MMA sees true products:
-//   g(v) = v + cg|v| = lrelu(v)/sl,  lrelu'(v) = sl*(1 + cg*sgn v).
-//   G2' = dAgg*m*keep2*(1 + cg sgn D2),  G1' = dH1*keep1*(1 + cg sgn D1),  G0' = dH0*keep0*(1 + cg sgn pre0)
-//   dW = (sd*sl)^2 * acc,  db = sd*sl * acc,  dP/dQ = sd*sl * G0'.
-// Gradient tiles are produced in packed bf16x2 arithmetic: pack two fp32 values, multiply by a factor
-// pair selected per lane from the sign bits (PRMT sign-replication mask + one LOP3).  Sign bits are kept
-// one word per 32 elements (sign_put / neg_pair_mask).
+// Scale conventions (sd = dropout scale 2 or 1, sl = (1+alpha)/2, os = out_scale, m = sender mask):
+// activation tiles hold X' = X / (sd*sl) and the weight images sd*sl*W exactly as in the forward kernel,
+// g(v) = v + cg|v| = lrelu(v)/sl.  Gradient tiles are multiplied only by the EXACT slope pair {1, alpha}
+// (1 is exact in bf16, so only the small negative-slope terms carry bf16(alpha)'s 0.1% error):
+//   G2+ = dAgg*m*keep2*{1,a}(D2) = G2/(sd*os)        dH1c = G2+ W2img = (sl/os) dH1
+//   G1+ = dH1c*keep1*{1,a}(D1)  = (sl/(os*sd)) G1    dH0c = G1+ W1img = (sl^2/os) dH0
+//   G0+ = dH0c*keep0*{1,a}(pre0) = (sl^2/(os*sd)) G0
+//   dP,dQ = sd*os/sl^2 * G0+;  dW1 = sd^2*os * H0'^T G1+;  db1 = sd*os/sl * sum G1+;
+//   dW2 = sd^2*sl*os * G2+^T H1';  db2 = sd*os * sum G2+.
+// G2+/G1+ are produced in packed bf16x2 arithmetic (pack two fp32 values, multiply by a factor pair
+// selected per lane from the sign bits: PRMT sign-replication mask + one LOP3); G0+ is formed in fp32 so
+// that dP accumulates unrounded terms.  Sign bits are kept one word per 32 elements (sign_put / neg_*_mask).
 //
 // Structure as in the forward kernel: 16 epilogue warps (thread <-> tile row x column chunks 4c+q), a
 // control warpgroup (warp 16 issues every MMA through an elected lane, warp 17 runs the TMA Q ring),
@@ -63,6 +67,11 @@ constexpr uint32_t D_SMEM = D_OFF_BAR + 256 + 1024;
 constexpr uint32_t C_RA = 0, C_RB = 160, C_PW1 = 352;       // CHAIN: D1/H1'/dH1/G1' | D2/G2'/dQ + dH0 | dW1^T
 constexpr uint32_t D_R = 0, D_PW2A = 160, D_PW2B = 336;     // DW2: D1 | dW2 rows 0..127 | rows 128..191
 constexpr int NDW = N1 + 16;                                 // 176: dW2 accumulator width incl. the db2 column
+// weight-gradient partials: every CTA stores its TMEM accumulators to a private slab laid out like the
+// final tensors (dW1 [160,96] | db1 [160] | dW2 [192,160] | db2 [192]); wgrad_reduce_kernel sums the slabs.
+// (148 CTAs x 46k atomics onto the same addresses cost more than the whole N=30 main loop.)
+constexpr int SLAB_DW1 = 0, SLAB_DB1 = N1 * K0, SLAB_DW2 = SLAB_DB1 + N1, SLAB_DB2 = SLAB_DW2 + N2 * N1,
+              SLAB_FLOATS = SLAB_DB2 + N2;
 
 __device__ __forceinline__ uint32_t mul_bf16x2(uint32_t a, uint32_t b) {
   uint32_t d;
@@ -78,6 +87,10 @@ __device__ __forceinline__ void sign_put(uint32_t& acc, uint32_t w, int p) {
 // 0xFFFF per negative lane of pair p
 __device__ __forceinline__ uint32_t neg_pair_mask(uint32_t sw, int p) {
   return p < 8 ? prmt(sw << p, 0u, 0xbb99u) : prmt(sw << (p - 8), 0u, 0xaa88u);
+}
+// all ones if lane `hi` (0 / 1) of pair p is negative
+__device__ __forceinline__ uint32_t neg_lane_mask(uint32_t sw, int p, int hi) {
+  return p < 8 ? prmt(sw << p, 0u, hi ? 0xbbbbu : 0x9999u) : prmt(sw << (p - 8), 0u, hi ? 0xaaaau : 0x8888u);
 }
 // per-lane select: negative lanes take `neg`, the others `pos`
 __device__ __forceinline__ uint32_t sel_pair(uint32_t mask, uint32_t neg, uint32_t pos) {
@@ -280,10 +293,12 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
       const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)q * 8;   // chunk q of this lane
       const uint32_t tp = tl - (uint32_t)q * 4;                                            // packed column 4q
       const float cg = (1.f - a.alpha) / (1.f + a.alpha);
-      const float ssl = (DROP ? 2.f : 1.f) * 0.5f * (1.f + a.alpha);                      // sd * sl
+      const float sd = DROP ? 2.f : 1.f, sl = 0.5f * (1.f + a.alpha), os = a.out_scale;
+      const float sc_g0 = sd * os / (sl * sl), sc_dw1 = sd * sd * os, sc_db1 = sd * os / sl, sc_dw2 = sd * sd * sl * os,
+                  sc_db2 = sd * os;
       DropCfg drop = a.drop;
       if (DROP) resolve_seed(drop);
-      const uint32_t F_NEG = bf16x2_dup(1.f - cg), F_POS = bf16x2_dup(1.f + cg);
+      const uint32_t F_NEG = bf16x2_dup(a.alpha), F_POS = 0x3F803F80u;   // slope pair {alpha, 1}
       // this thread's two 16-byte positions inside a swizzled 128-byte tile row (chunk 4c+q -> xs{c&1} + (c>>1)*A_BLK)
       uint32_t xs0 = base + (uint32_t)row * 128u + ((uint32_t)(q ^ (row & 7)) << 4);
       uint32_t xs1 = base + (uint32_t)row * 128u + ((uint32_t)((4 + q) ^ (row & 7)) << 4);
@@ -420,14 +435,14 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
           if (lane >= 2 && lane < 2 + p_nj) {
             float* dq = a.dQ + ((size_t)(p_j0 + lane - 2) * N + p_s) * K0 + q * 8;
 #pragma unroll
-            for (int e = 0; e < QH; ++e) atomicAdd(dq + 32 * (e >> 3) + (e & 7), v[e] * ssl);
+            for (int e = 0; e < QH; ++e) atomicAdd(dq + 32 * (e >> 3) + (e & 7), v[e] * sc_g0);
           }
         }
       };
 
       for (int it = 0; it < nsteps; ++it) {
         const uint32_t par = it & 1;
-        const float mfac = c_valid ? (a.mask ? __ldg(a.mask + (size_t)c_jet * N + c_s) : 1.f) * a.out_scale : 0.f;
+        const float mfac = c_valid ? (a.mask ? __ldg(a.mask + (size_t)c_jet * N + c_s) : 1.f) : 0.f;
         u4 kb{0, 0, 0, 0};
         if (DROP) kb = edge_drop_bits(drop.seed, (uint64_t)c_r * N + c_s, q, 1);
 
@@ -483,7 +498,7 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
         mbar_arrive(bar0 + BwdBars::rdyB);
 
         // ---- G2' = dAgg * m * keep2 * (1 + cg sgn D2) ----------------------------------------------------------------
-        const uint32_t U_POS = bf16x2_dup(mfac * (1.f + cg)), U_NEG = bf16x2_dup(mfac * (1.f - cg));
+        const uint32_t U_POS = bf16x2_dup(mfac), U_NEG = bf16x2_dup(mfac * a.alpha);
         if constexpr (CH) {
           uint2 sb{0, 0};
           mbar_wait(bar0 + BwdBars::doneB, par);
@@ -498,7 +513,15 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
               const int p = i >> 1;
               const uint32_t zw = pack_bf16(v[i], v[i + 1]);
               sign_put(sw, zw, p);
+#ifdef MPG_FP32_SLOPE
+              {
+                const uint32_t dw = dAggp[h * (QH / 2) + p];
+                const float f0 = v[i] < 0.f ? mfac * a.alpha : mfac, f1 = v[i + 1] < 0.f ? mfac * a.alpha : mfac;
+                gw[p] = pack_bf16(__uint_as_float(dw << 16) * f0, __uint_as_float(dw & 0xFFFF0000u) * f1);
+              }
+#else
               gw[p] = mul_bf16x2(dAggp[h * (QH / 2) + p], sel_pair(prmt(zw, 0u, 0xbb99u), U_NEG, U_POS));
+#endif
               if (DROP) gw[p] &= keep_pair(h ? kb.w : kb.z, i);
             }
             if (h == 0) sb.x = sw; else sb.y = sw;
@@ -551,7 +574,16 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
 #pragma unroll
             for (int i = 0; i < 8 * nc; i += 2) {
               const int el = 8 * c0 + i, p = el >> 1;
+#ifdef MPG_FP32_SLOPE
+              {
+                const uint32_t a_bits = __float_as_uint(a.alpha), one_bits = 0x3F800000u;
+                const float f0 = __uint_as_float(sel_pair(neg_lane_mask(s1[p >> 4], p & 15, 0), a_bits, one_bits));
+                const float f1 = __uint_as_float(sel_pair(neg_lane_mask(s1[p >> 4], p & 15, 1), a_bits, one_bits));
+                w[i >> 1] = pack_bf16(v[i] * f0, v[i + 1] * f1);
+              }
+#else
               w[i >> 1] = mul_bf16x2(pack_bf16(v[i], v[i + 1]), sel_pair(neg_pair_mask(s1[p >> 4], p & 15), F_NEG, F_POS));
+#endif
               if (DROP) w[i >> 1] &= keep_pair(el < 32 ? kb.x : kb.y, el & 31);
             }
             if constexpr (rnd == 0) named_bar_sync(bar_id, 128);
@@ -580,17 +612,22 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
           {
             float v[Q0];
             tmem_ld8x3(tl + C_RB + NH2, v);
+            const uint32_t a_bits = __float_as_uint(a.alpha), one_bits = 0x3F800000u;
 #pragma unroll
             for (int c = 0; c < Q0 / 8; ++c) {
               uint32_t w[4];
 #pragma unroll
               for (int e = 0; e < 8; e += 2) {
                 const int p = 4 * c + (e >> 1);
-                uint32_t gw = mul_bf16x2(pack_bf16(v[8 * c + e], v[8 * c + e + 1]), sel_pair(neg_pair_mask(s0, p), F_NEG, F_POS));
-                if (DROP) gw &= keep_pair(k0w, 8 * c + e);
-                w[e >> 1] = gw;
-                dPacc[8 * c + e] += __uint_as_float(gw << 16);
-                dPacc[8 * c + e + 1] += __uint_as_float(gw & 0xFFFF0000u);
+                float g[2];
+#pragma unroll
+                for (int hi = 0; hi < 2; ++hi) {
+                  uint32_t f = sel_pair(neg_lane_mask(s0, p, hi), a_bits, one_bits);
+                  if (DROP) f &= keep_one(k0w, 8 * c + e + hi);
+                  g[hi] = v[8 * c + e + hi] * __uint_as_float(f);
+                  dPacc[8 * c + e + hi] += g[hi];
+                }
+                w[e >> 1] = pack_bf16(g[0], g[1]);
               }
               asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(((c & 1) ? xs1 : xs0) + C_OFF_X + (c >> 1) * A_BLK),
                            "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]));
@@ -609,7 +646,7 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
             if (c_valid) {
               float* dst = a.dP + (size_t)c_r * K0 + q * 8;
 #pragma unroll
-              for (int c = 0; c < Q0; ++c) atomicAdd(dst + 32 * (c >> 3) + (c & 7), dPacc[c] * ssl);
+              for (int c = 0; c < Q0; ++c) atomicAdd(dst + 32 * (c >> 3) + (c & 7), dPacc[c] * sc_g0);
             }
 #pragma unroll
             for (int c = 0; c < Q0; ++c) dPacc[c] = 0.f;
@@ -639,20 +676,22 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
         if (c_s != 0 && c_valid) {   // partial tile: flush dP
           float* dst = a.dP + (size_t)c_r * K0 + q * 8;
 #pragma unroll
-          for (int c = 0; c < Q0; ++c) atomicAdd(dst + 32 * (c >> 3) + (c & 7), dPacc[c] * ssl);
+          for (int c = 0; c < Q0; ++c) atomicAdd(dst + 32 * (c >> 3) + (c & 7), dPacc[c] * sc_g0);
         }
         // dW1^T accumulator: lane = H0' column k0 (< 96: dW1[:, k0]; 96: db1), column n1 = 32c + 8q + e
+        float* slab = t.wslab + (size_t)blockIdx.x * SLAB_FLOATS;
         float v[Q1];
         tmem_ld8x5(tl + C_PW1, v);
 #pragma unroll
         for (int i = 0; i < Q1; ++i) {
           const int n1 = 32 * (i >> 3) + 8 * q + (i & 7);
-          if (row < K0) atomicAdd(a.dW1 + (size_t)n1 * K0 + row, v[i] * ssl * ssl);
-          else if (row == K0) atomicAdd(a.db1 + n1, v[i] * ssl);
+          if (row < K0) slab[SLAB_DW1 + n1 * K0 + row] = v[i] * sc_dw1;
+          else if (row == K0) slab[SLAB_DB1 + n1] = v[i] * sc_db1;
         }
       } else {
         mbar_wait(bar0 + BwdBars::doneC, (nsteps - 1) & 1);
         tc_fence_after();
+        float* slab = t.wslab + (size_t)blockIdx.x * SLAB_FLOATS;
 #pragma unroll 1
         for (int mb = 0; mb < 2; ++mb) {
           const int n2 = mb * 128 + row;
@@ -665,8 +704,8 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
             if (n2 < N2) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
-                if (col + e < N1) atomicAdd(a.dW2 + (size_t)n2 * N1 + col + e, v[e] * ssl * ssl);
-                else if (col + e == N1) atomicAdd(a.db2 + n2, v[e] * ssl);
+                if (col + e < N1) slab[SLAB_DW2 + n2 * N1 + col + e] = v[e] * sc_dw2;
+                else if (col + e == N1) slab[SLAB_DB2 + n2] = v[e] * sc_db2;
               }
             }
           }
@@ -678,4 +717,15 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
   tc_fence_before();
   __syncthreads();
   if (warp == 16) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+// dW1 / db1 / dW2 / db2 += sum over the CTAs' slabs (coalesced: consecutive threads, consecutive elements)
+__global__ void wgrad_reduce_kernel(const float* __restrict__ slabs, int nslabs, float* __restrict__ dW1,
+                                    float* __restrict__ db1, float* __restrict__ dW2, float* __restrict__ db2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= SLAB_FLOATS) return;
+  float s = 0.f;
+  for (int c = 0; c < nslabs; ++c) s += slabs[(size_t)c * SLAB_FLOATS + i];
+  float* dst = i < SLAB_DB1 ? dW1 + i : (i < SLAB_DW2 ? db1 + (i - SLAB_DB1) : (i < SLAB_DB2 ? dW2 + (i - SLAB_DW2) : db2 + (i - SLAB_DB2)));
+  *dst += s;
 }

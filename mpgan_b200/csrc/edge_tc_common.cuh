@@ -289,6 +289,7 @@ struct TcArgs {
   const uint8_t* w1img;   // pre-swizzled bf16 images (weight_image_kernel)
   const uint8_t* w2img;
   uint2* sbits;           // backward: sign bits of D2, one uint2 per (step, epilogue thread)
+  float* wslab;           // backward: per-CTA weight-gradient partials (edge_tc_bwd.cuh: SLAB_*)
   int num_tiles;
   long long total_steps;
 };

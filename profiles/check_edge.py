@@ -11,15 +11,20 @@ import torch
 import mpgan_b200.ops as O
 
 B, N, p = int(sys.argv[1]), int(sys.argv[2]), float(sys.argv[3])
-F = 32
+F = int(sys.argv[4]) if len(sys.argv) > 4 else 32
+dlike = len(sys.argv) > 5          # discriminator-like data: features zeroed on padded rows, dAgg zero there too
 torch.manual_seed(1)
 x0 = torch.randn(B, N, F, device="cuda") * 0.5
 n = torch.randint(1, N + 1, (B,), device="cuda")
 mask = (torch.arange(N, device="cuda")[None, :] < n[:, None]).float().unsqueeze(2)
+if dlike:
+    x0 = (torch.rand(B, N, F, device="cuda") - 0.5) * mask
 ws0 = []
 for i, o in ((2 * F, 96), (96, 160), (160, 192)):
     ws0 += [torch.randn(o, i, device="cuda") / i ** 0.5, torch.randn(o, device="cuda") * 0.1]
 dagg = torch.randn(B, N, 192, device="cuda")
+if dlike:
+    dagg = dagg * mask * 1e-3
 res = []
 for prec in (0, 1):
     O.set_precision(prec)
