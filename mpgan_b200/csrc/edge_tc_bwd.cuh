@@ -435,7 +435,8 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
           if (lane >= 2 && lane < 2 + p_nj) {
             float* dq = a.dQ + ((size_t)(p_j0 + lane - 2) * N + p_s) * K0 + q * 8;
 #pragma unroll
-            for (int e = 0; e < QH; ++e) atomicAdd(dq + 32 * (e >> 3) + (e & 7), v[e] * sc_g0);
+            for (int e = 0; e < QH; e += 4)
+              red_add_v4(dq + 32 * (e >> 3) + (e & 7), v[e] * sc_g0, v[e + 1] * sc_g0, v[e + 2] * sc_g0, v[e + 3] * sc_g0);
           }
         }
       };
@@ -646,7 +647,9 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
             if (c_valid) {
               float* dst = a.dP + (size_t)c_r * K0 + q * 8;
 #pragma unroll
-              for (int c = 0; c < Q0; ++c) atomicAdd(dst + 32 * (c >> 3) + (c & 7), dPacc[c] * sc_g0);
+              for (int c = 0; c < Q0; c += 4)
+                red_add_v4(dst + 32 * (c >> 3) + (c & 7), dPacc[c] * sc_g0, dPacc[c + 1] * sc_g0, dPacc[c + 2] * sc_g0,
+                           dPacc[c + 3] * sc_g0);
             }
 #pragma unroll
             for (int c = 0; c < Q0; ++c) dPacc[c] = 0.f;
@@ -676,7 +679,9 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
         if (c_s != 0 && c_valid) {   // partial tile: flush dP
           float* dst = a.dP + (size_t)c_r * K0 + q * 8;
 #pragma unroll
-          for (int c = 0; c < Q0; ++c) atomicAdd(dst + 32 * (c >> 3) + (c & 7), dPacc[c] * sc_g0);
+          for (int c = 0; c < Q0; c += 4)
+            red_add_v4(dst + 32 * (c >> 3) + (c & 7), dPacc[c] * sc_g0, dPacc[c + 1] * sc_g0, dPacc[c + 2] * sc_g0,
+                       dPacc[c + 3] * sc_g0);
         }
         // dW1^T accumulator: lane = H0' column k0 (< 96: dW1[:, k0]; 96: db1), column n1 = 32c + 8q + e
         float* slab = t.wslab + (size_t)blockIdx.x * SLAB_FLOATS;

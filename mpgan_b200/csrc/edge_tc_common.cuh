@@ -171,6 +171,10 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
+// one 16-byte reduction instead of four scalar atomics (addr 16-byte aligned)
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 // hides a value from loop-invariant code motion
 __device__ __forceinline__ void opaque(uint32_t& v) { asm volatile("" : "+r"(v)); }
 __device__ __forceinline__ void opaque(uint64_t& v) { asm volatile("" : "+l"(v)); }

@@ -70,8 +70,13 @@ __device__ long long* g_trace = nullptr;
   do {                                                                                           \
     if (g_trace && blockIdx.x == 0 && lane == 0 && (it) < 256) g_trace[(it) * 16 + (slot)] = clock64(); \
   } while (0)
+#define MPG_TP(slot)                                                                              \
+  do {                                                                                            \
+    if (g_trace && blockIdx.x == 0 && threadIdx.x == 0) g_trace[4080 + (slot)] = clock64();       \
+  } while (0)
 #else
 #define MPG_TR(it, slot) do { } while (0)
+#define MPG_TP(slot) do { } while (0)
 #endif
 
 template <bool DROP>
@@ -93,6 +98,7 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
   const long long g1 = t.total_steps * (blockIdx.x + 1) / gridDim.x;
   const int nsteps = (int)(g1 - g0);
   const int N = a.N, BN = a.B * a.N;
+  MPG_TP(0);
 
   if (threadIdx.x == 0) {
     mbar_init(bar_w, 1);
@@ -188,6 +194,24 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
         mbar_wait(bar_h1, it & 1);
         MPG_TR(it, 10);
         if (it >= 1) mbar_wait(bar_f2lo, (it - 1) & 1);
+#ifdef MPG_M2_UNSPLIT   // experiment: one N=192 MMA per K step
+        if (it >= 1) mbar_wait(bar_f2hi, (it - 1) & 1);
+        tc_fence_after();
+        {
+          const uint32_t at = tmem + F_D1_COL + (uint32_t)(it & 1) * N1;
+          if (elect_one()) {
+            opaque(dW2);
+#pragma unroll
+            for (uint32_t ks = 0; ks < KSTEPS2; ++ks) {
+              const uint32_t blk = ks >> 2, j = ks & 3;
+              umma_bf16_ts(tmem + F_D2LO_COL, at + ks * 8, dW2 + ((blk * W2_BLK + j * 32) >> 4), umma_idesc(N2), ks);
+            }
+            umma_commit(bar_d2lo);
+            umma_commit(bar_d2hi);
+          }
+          __syncwarp();
+        }
+#else
         tc_fence_after();
         MPG_TR(it, 11);
         issue_m2(it, F_D2LO_COL, 0, bar_d2lo);
@@ -199,11 +223,13 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
         MPG_TR(it, 13);
         issue_m2(it, F_D2HI_COL, NH2 * 128, bar_d2hi);
         MPG_TR(it, 14);
+#endif
       }
     }
   } else {
     // =============================== epilogue warps ==============================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(F_REGS_EPI));
+    MPG_TP(1);
     if (nsteps > 0) {
     const int q = warp >> 2;                        // column quarter: chunks 4c + q (edge_tc_common.cuh)
     const int row = (warp & 3) * 32 + lane;         // tile row == TMEM lane
@@ -297,7 +323,10 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
 #pragma unroll
           for (int c = 0; c < QH / 8; ++c)
 #pragma unroll
-            for (int e = 0; e < 8; ++e) atomicAdd(dst + h * NH2 + 32 * c + e, acc[h * QH + 8 * c + e] * fl_scale);
+            for (int e = 0; e < 8; e += 4) {
+              const float* v = acc + h * QH + 8 * c + e;
+              red_add_v4(dst + h * NH2 + 32 * c + e, v[0] * fl_scale, v[1] * fl_scale, v[2] * fl_scale, v[3] * fl_scale);
+            }
       }
 #pragma unroll
       for (int c = 0; c < 2 * QH; ++c) acc[c] = 0.f;
@@ -317,7 +346,9 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
 
     e_enter_tile();
     e_load_mask();
+    MPG_TP(2);
     build_h0(0);
+    MPG_TP(3);
     if (nsteps > 1) {
       mbar_wait(bar_d1, 0);   // M1(0) done: the H0' tile may be overwritten
       build_h0(1);
@@ -397,17 +428,21 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
         MPG_TR(it, 7);
       }
     }
+    MPG_TP(4);
     // ---- drain: E2 of the last step ------------------------------------------------------------------
     mbar_wait(bar_d2lo, (nsteps - 1) & 1);
     mbar_wait(bar_d2hi, (nsteps - 1) & 1);
     tc_fence_after();
     e2_half(F_D2LO_COL, acc, kz);
     e2_half(F_D2HI_COL, acc + QH, kwd);
+    MPG_TP(5);
     flush();
+    MPG_TP(6);
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  MPG_TP(7);
   if (warp == 16) tmem_dealloc(tmem, TMEM_COLS);
 }
