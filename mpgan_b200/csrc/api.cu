@@ -88,11 +88,15 @@ int edge_common(EdgeArgs& a, EdgeWs& w, const float* x, int ldx, const float* ma
   const bool precise = precision == 0;
   *use_tc = !precise && edge_tc_supported(a);
   // factorised first layer: W0 [x_i ; x_j ; ef] = Wa x_i + Wb x_j + Wef ef   (node-level GEMMs)
-  GemmEpi e;
-  e.bias = b0;
-  if (launch_gemm(true, true, true, x, ldx, w0, a.ldwef, w.P, H0, B * N, H0, F, e, 1, s)) return 1;
-  GemmEpi e2;
-  if (launch_gemm(true, true, true, x, ldx, w0 + F, a.ldwef, w.Q, H0, B * N, H0, F, e2, 1, s)) return 1;
+  if (pq_supported(F, H0)) {
+    if (launch_pq_fwd(x, ldx, w0, a.ldwef, b0, w.P, w.Q, B * N, F, H0, s)) return 1;
+  } else {
+    GemmEpi e;
+    e.bias = b0;
+    if (launch_gemm(true, true, true, x, ldx, w0, a.ldwef, w.P, H0, B * N, H0, F, e, 1, s)) return 1;
+    GemmEpi e2;
+    if (launch_gemm(true, true, true, x, ldx, w0 + F, a.ldwef, w.Q, H0, B * N, H0, F, e2, 1, s)) return 1;
+  }
   if (!*use_tc) {
     if (launch_transpose(w1, H1, H0, w.W1t, s)) return 1;
     if (launch_transpose(w2, H2, H1, w.W2t, s)) return 1;
@@ -214,16 +218,20 @@ int mpg_edge_bwd(const float* x, int ldx, const float* mask, const float* w0, co
   }
   const bool precise = precision == 0;
   // node-level tail of the factorised first layer
-  if (launch_colsum(w.dP, H0, (int)BN, H0, db0, s)) return 1;
-  int split = cdiv((long long)BN, 256);
-  if (split > 64) split = 64;
-  GemmEpi acc;
-  acc.accumulate = 1;
-  if (launch_gemm(false, false, precise, w.dP, H0, x, ldx, dw0, a.ldwef, H0, F, (int)BN, acc, split, s)) return 1;
-  if (launch_gemm(false, false, precise, w.dQ, H0, x, ldx, dw0 + F, a.ldwef, H0, F, (int)BN, acc, split, s)) return 1;
-  GemmEpi e0;
-  if (launch_gemm(true, false, precise, w.dP, H0, w0, a.ldwef, dx, lddx, (int)BN, F, H0, e0, 1, s)) return 1;
-  if (launch_gemm(true, false, precise, w.dQ, H0, w0 + F, a.ldwef, dx, lddx, (int)BN, F, H0, acc, 1, s)) return 1;
+  if (pq_supported(F, H0)) {
+    if (launch_pq_bwd(w.dP, w.dQ, x, ldx, w0, a.ldwef, dx, lddx, dw0, db0, (int)BN, F, H0, s)) return 1;
+  } else {
+    if (launch_colsum(w.dP, H0, (int)BN, H0, db0, s)) return 1;
+    int split = cdiv((long long)BN, 256);
+    if (split > 64) split = 64;
+    GemmEpi acc;
+    acc.accumulate = 1;
+    if (launch_gemm(false, false, precise, w.dP, H0, x, ldx, dw0, a.ldwef, H0, F, (int)BN, acc, split, s)) return 1;
+    if (launch_gemm(false, false, precise, w.dQ, H0, x, ldx, dw0 + F, a.ldwef, H0, F, (int)BN, acc, split, s)) return 1;
+    GemmEpi e0;
+    if (launch_gemm(true, false, precise, w.dP, H0, w0, a.ldwef, dx, lddx, (int)BN, F, H0, e0, 1, s)) return 1;
+    if (launch_gemm(true, false, precise, w.dQ, H0, w0 + F, a.ldwef, dx, lddx, (int)BN, F, H0, acc, 1, s)) return 1;
+  }
   if (a.n_ef) {
     add_strided_kernel<<<cdiv((long long)BN * F, 256), 256, 0, s>>>(dx, lddx, w.dxef, F, (int)BN, F);
     MPG_LAUNCH_CHECK();

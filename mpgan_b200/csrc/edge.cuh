@@ -38,6 +38,13 @@ size_t edge_generic_smem(const EdgeArgs& a, bool bwd);
 int launch_edge_generic(const EdgeArgs& a, bool bwd, cudaStream_t stream);
 int launch_transpose(const float* in, int rows, int cols, float* out, cudaStream_t stream);
 
+// node-level ends of the factorised first layer (edge_node.cu)
+bool pq_supported(int F, int H0);
+int launch_pq_fwd(const float* x, int ldx, const float* W0, int ldw, const float* b0, float* P, float* Q, int BN,
+                  int F, int H0, cudaStream_t stream);
+int launch_pq_bwd(const float* dP, const float* dQ, const float* x, int ldx, const float* W0, int ldw, float* dx,
+                  int lddx, float* dW0, float* db0, int BN, int F, int H0, cudaStream_t stream);
+
 // tcgen05 path (edge_tc.cu): default architecture only
 int edge_tc_features();
 void edge_tc_arm_probe(int id, cudaEvent_t e0, cudaEvent_t e1);

@@ -1,0 +1,175 @@
+// Node-level ends of the factorised first edge layer (W0 [x_i ; x_j ; ef] = Wa x_i + Wb x_j + Wef ef).
+//
+//   forward   P = x Wa^T + b0,  Q = x Wb^T                                    [B*N, H0] each
+//   backward  dx = dP Wa + dQ Wb,  dWa += dP^T x,  dWb += dQ^T x,  db0 += sum_r dP
+//
+// These are O(B*N) x (F <= 64) x (H0 <= 128) problems: a few MFLOP that used to cost six TF32 GEMM
+// launches + a column sum (~20 us each, latency-bound).  One fp32 SIMT kernel per direction does the
+// same work from shared memory in a few microseconds, exactly (no TF32 rounding).
+// Reference: first Linear of fe applied to cat(x_i, x_j), mpgan/model.py:77-83, 294-311.
+#include "edge.cuh"
+
+namespace mpg {
+namespace {
+
+constexpr int FWD_ROWS = 32;     // rows per block, forward
+constexpr int BWD_ROWS = 64;     // rows per block, backward (two blocks per SM)
+constexpr int NT = 256;
+
+// Ws[c][k] = W0[k][c] for c < 2F (column c of the weight, all H0 outputs), stride H0P
+__device__ __forceinline__ void load_w_t(float* Ws, const float* __restrict__ W0, int ldw, int F, int H0, int H0P) {
+  for (int idx = threadIdx.x; idx < 2 * F * H0; idx += NT) {
+    const int k = idx / (2 * F), c = idx % (2 * F);     // consecutive threads: consecutive columns of one row (coalesced)
+    Ws[c * H0P + k] = W0[(size_t)k * ldw + c];
+  }
+}
+
+__global__ void __launch_bounds__(NT) pq_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ W0,
+                                                    int ldw, const float* __restrict__ b0, float* __restrict__ P,
+                                                    float* __restrict__ Q, int BN, int F, int H0) {
+  extern __shared__ float sm[];
+  const int H0P = H0 + 1, FP = F + 1;
+  float* Ws = sm;                       // [2F][H0P]
+  float* xs = Ws + 2 * F * H0P;         // [FWD_ROWS][FP]
+  const int r0 = blockIdx.x * FWD_ROWS;
+  load_w_t(Ws, W0, ldw, F, H0, H0P);
+  for (int idx = threadIdx.x; idx < FWD_ROWS * F; idx += NT) {
+    const int r = idx / F, f = idx % F;
+    xs[r * FP + f] = r0 + r < BN ? x[(size_t)(r0 + r) * ldx + f] : 0.f;
+  }
+  __syncthreads();
+  // thread -> output column c of [P | Q] (c < 2*H0), 4 rows at a time
+  for (int idx = threadIdx.x; idx < 2 * H0 * (FWD_ROWS / 4); idx += NT) {
+    const int c = idx % (2 * H0), rg = idx / (2 * H0);
+    const int k = c < H0 ? c : c - H0;
+    const float* w = Ws + (c < H0 ? 0 : F) * H0P + k;
+    float acc[4];
+    const float bias = c < H0 ? b0[k] : 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i] = bias;
+    for (int f = 0; f < F; ++f) {
+      const float wv = w[f * H0P];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i] = fmaf(xs[(rg * 4 + i) * FP + f], wv, acc[i]);
+    }
+    float* dst = c < H0 ? P : Q;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = r0 + rg * 4 + i;
+      if (r < BN) dst[(size_t)r * H0 + k] = acc[i];
+    }
+  }
+}
+
+// dx, dW0[:, :2F] += [dP^T x | dQ^T x], db0 += column sums of dP.  Shared-memory bandwidth (one warp load per
+// clock) is the limit, so both products are register-blocked around 16-byte loads: 4 rows x 4 k per W/d quad
+// for dx, 24 gradient columns per x value for dW0.
+__global__ void __launch_bounds__(NT) pq_bwd_kernel(const float* __restrict__ dP, const float* __restrict__ dQ,
+                                                    const float* __restrict__ x, int ldx, const float* __restrict__ W0,
+                                                    int ldw, float* __restrict__ dx, int lddx, float* __restrict__ dW0,
+                                                    float* __restrict__ db0, int BN, int F, int H0) {
+  extern __shared__ __align__(16) float sm[];
+  const int H0P = H0 + 4, FP = F + 1, DP = 2 * H0 + 4;   // H0 % 4 == 0 (launcher): rows stay 16-byte aligned
+  float* Ws = sm;                          // [2F][H0P]   Ws[c][k] = W0[k][c]
+  float* ds = Ws + 2 * F * H0P;            // [BWD_ROWS][DP]  row = [dP | dQ]
+  float* xs = ds + BWD_ROWS * DP;          // [BWD_ROWS][FP]
+  const int r0 = blockIdx.x * BWD_ROWS;
+  load_w_t(Ws, W0, ldw, F, H0, H0P);
+  for (int idx = threadIdx.x; idx < BWD_ROWS * F; idx += NT) {
+    const int r = idx / F, f = idx % F;
+    xs[r * FP + f] = r0 + r < BN ? x[(size_t)(r0 + r) * ldx + f] : 0.f;
+  }
+  for (int idx = threadIdx.x; idx < BWD_ROWS * 2 * H0; idx += NT) {
+    const int r = idx / (2 * H0), c = idx % (2 * H0);
+    float v = 0.f;
+    if (r0 + r < BN) v = c < H0 ? dP[(size_t)(r0 + r) * H0 + c] : dQ[(size_t)(r0 + r) * H0 + c - H0];
+    ds[r * DP + c] = v;
+  }
+  __syncthreads();
+  // ---- dx[r][f] = sum_k dP[r][k] Wa[k][f] + dQ[r][k] Wb[k][f]: 8 rows (independent accumulators) per thread ----
+  for (int idx = threadIdx.x; idx < (BWD_ROWS / 8) * F; idx += NT) {
+    const int f = idx % F, rg = idx / F;
+    const float4* wa = reinterpret_cast<const float4*>(Ws + f * H0P);
+    const float4* wb = reinterpret_cast<const float4*>(Ws + (F + f) * H0P);
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll 2
+    for (int k4 = 0; k4 < H0 / 4; ++k4) {
+      const float4 a4 = wa[k4], b4 = wb[k4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float* d = ds + (rg * 8 + i) * DP;
+        const float4 p4 = *reinterpret_cast<const float4*>(d + 4 * k4);
+        const float4 q4 = *reinterpret_cast<const float4*>(d + H0 + 4 * k4);
+        acc[i] = fmaf(p4.x, a4.x, acc[i]); acc[i] = fmaf(q4.x, b4.x, acc[i]);
+        acc[i] = fmaf(p4.y, a4.y, acc[i]); acc[i] = fmaf(q4.y, b4.y, acc[i]);
+        acc[i] = fmaf(p4.z, a4.z, acc[i]); acc[i] = fmaf(q4.z, b4.z, acc[i]);
+        acc[i] = fmaf(p4.w, a4.w, acc[i]); acc[i] = fmaf(q4.w, b4.w, acc[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = r0 + rg * 8 + i;
+      if (r < BN) dx[(size_t)r * lddx + f] = acc[i];
+    }
+  }
+  // ---- dW0[k][c] += sum_r d[r][k (+H0 for c >= F)] x[r][c mod F]: 8 consecutive gradient columns per thread --
+  const int ngrp = 2 * H0 / 8;
+  for (int idx = threadIdx.x; idx < ngrp * F; idx += NT) {
+    const int f = idx % F, g = idx / F;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll 8
+    for (int r = 0; r < BWD_ROWS; ++r) {
+      const float xv = xs[r * FP + f];
+      const float4 d0 = *reinterpret_cast<const float4*>(ds + r * DP + 8 * g);
+      const float4 d1 = *reinterpret_cast<const float4*>(ds + r * DP + 8 * g + 4);
+      acc[0] = fmaf(d0.x, xv, acc[0]); acc[1] = fmaf(d0.y, xv, acc[1]);
+      acc[2] = fmaf(d0.z, xv, acc[2]); acc[3] = fmaf(d0.w, xv, acc[3]);
+      acc[4] = fmaf(d1.x, xv, acc[4]); acc[5] = fmaf(d1.y, xv, acc[5]);
+      acc[6] = fmaf(d1.z, xv, acc[6]); acc[7] = fmaf(d1.w, xv, acc[7]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int dc = 8 * g + i;                       // column of [dP | dQ]
+      const int k = dc < H0 ? dc : dc - H0;
+      atomicAdd(dW0 + (size_t)k * ldw + (dc < H0 ? f : F + f), acc[i]);
+    }
+  }
+  for (int k = threadIdx.x; k < H0; k += NT) {
+    float acc = 0.f;
+    for (int r = 0; r < BWD_ROWS; ++r) acc += ds[r * DP + k];
+    atomicAdd(db0 + k, acc);
+  }
+}
+
+size_t fwd_smem(int F, int H0) { return (size_t)(2 * F * (H0 + 1) + FWD_ROWS * (F + 1)) * sizeof(float); }
+size_t bwd_smem(int F, int H0) {
+  return (size_t)(2 * F * (H0 + 4) + BWD_ROWS * (F + 1) + BWD_ROWS * (2 * H0 + 4)) * sizeof(float);
+}
+
+}  // namespace
+
+bool pq_supported(int F, int H0) { return F >= 1 && F <= 64 && H0 >= 8 && H0 <= 128 && H0 % 8 == 0; }
+
+int launch_pq_fwd(const float* x, int ldx, const float* W0, int ldw, const float* b0, float* P, float* Q, int BN,
+                  int F, int H0, cudaStream_t stream) {
+  const size_t smem = fwd_smem(F, H0);
+  MPG_CUDA(cudaFuncSetAttribute(pq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  pq_fwd_kernel<<<cdiv(BN, FWD_ROWS), NT, smem, stream>>>(x, ldx, W0, ldw, b0, P, Q, BN, F, H0);
+  MPG_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_pq_bwd(const float* dP, const float* dQ, const float* x, int ldx, const float* W0, int ldw, float* dx,
+                  int lddx, float* dW0, float* db0, int BN, int F, int H0, cudaStream_t stream) {
+  const size_t smem = bwd_smem(F, H0);
+  MPG_CUDA(cudaFuncSetAttribute(pq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  pq_bwd_kernel<<<cdiv(BN, BWD_ROWS), NT, smem, stream>>>(dP, dQ, x, ldx, W0, ldw, dx, lddx, dW0, db0, BN, F, H0);
+  MPG_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace mpg

@@ -54,9 +54,14 @@ static int tc_num_sms() {
 }
 static size_t tc_slab_bytes() { return (size_t)tc_num_sms() * SLAB_FLOATS * sizeof(float); }
 
+static size_t tc_steps_bytes(int B, int N) {   // work list: int2 per (tile, sender) + the total
+  const long long tiles = ((long long)B * N + TILE - 1) / TILE;
+  return ((size_t)tiles * N * sizeof(int2) + 256 + 255) & ~(size_t)255;
+}
+
 size_t edge_tc_workspace_bytes(int B, int N, int H0, int H1, int H2) {
   if (H0 != K0 || H1 != N1 || H2 != N2) return 0;
-  return W1_BYTES + W2_BYTES + 1024 + tc_sbits_bytes(B, N) + 256 + tc_slab_bytes();
+  return W1_BYTES + W2_BYTES + 1024 + tc_steps_bytes(B, N) + tc_sbits_bytes(B, N) + 256 + tc_slab_bytes();
 }
 
 // the activation / gradient tiles hold X / (sd * sl) (dropout and leaky-relu scales), the weight images sd * sl * W
@@ -66,18 +71,26 @@ static int tc_prepare(const EdgeArgs& a, void* ws, TcArgs& t, int* grid, cudaStr
   t.a = a;
   t.w1img = img;
   t.w2img = img + W1_BYTES;
-  t.sbits = reinterpret_cast<uint2*>(img + W1_BYTES + W2_BYTES);
-  t.wslab = reinterpret_cast<float*>(img + W1_BYTES + W2_BYTES + ((tc_sbits_bytes(a.B, a.N) + 255) & ~(size_t)255));
+  uint8_t* p = img + W1_BYTES + W2_BYTES;
+  int* total = reinterpret_cast<int*>(p);
+  t.total_steps = total;
+  t.steps = reinterpret_cast<int2*>(p + 256);
+  p += tc_steps_bytes(a.B, a.N);
+  t.sbits = reinterpret_cast<uint2*>(p);
+  t.wslab = reinterpret_cast<float*>(p + ((tc_sbits_bytes(a.B, a.N) + 255) & ~(size_t)255));
   const float s = (a.drop.p > 0.f ? 2.f : 1.f) * 0.5f * (1.f + a.alpha);
-  weight_image_kernel<<<cdiv(N1 * 128, 256), 256, 0, stream>>>(a.W1, a.b1, N1, K0, 128, s, img);
+  weight_image_kernel<<<cdiv(N1 * 128, 256), 256, 0, stream>>>(a.W1, a.b1, N1, K0, 128, s, img, nullptr);
   MPG_LAUNCH_CHECK();
-  weight_image_kernel<<<cdiv(N2 * 192, 256), 256, 0, stream>>>(a.W2, a.b2, N2, N1, 192, s, img + W1_BYTES);
+  weight_image_kernel<<<cdiv(N2 * 192, 256), 256, 0, stream>>>(a.W2, a.b2, N2, N1, 192, s, img + W1_BYTES, reinterpret_cast<int*>(img + W1_BYTES + W2_BYTES));
   MPG_LAUNCH_CHECK();
   const long long BN = (long long)a.B * a.N;
   t.num_tiles = (int)((BN + TILE - 1) / TILE);
-  t.total_steps = (long long)t.num_tiles * a.N;
+  step_list_kernel<<<cdiv(t.num_tiles, 8), 256, 0, stream>>>(a.mask, a.B, a.N, t.num_tiles, const_cast<int2*>(t.steps), total);
+  MPG_LAUNCH_CHECK();
+  // the number of live steps is only known on the device: one CTA per SM, CTAs without steps exit at once
+  const long long max_steps = (long long)t.num_tiles * a.N;
   const int sms = tc_num_sms();
-  *grid = (int)(t.total_steps < sms ? t.total_steps : sms);
+  *grid = (int)(max_steps < sms ? max_steps : sms);
   return 0;
 }
 

@@ -121,9 +121,11 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + OFF_BARS + 192);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long g0 = t.total_steps * blockIdx.x / gridDim.x;
-  const long long g1 = t.total_steps * (blockIdx.x + 1) / gridDim.x;
+  const long long total_steps = *t.total_steps;
+  const long long g0 = total_steps * blockIdx.x / gridDim.x;
+  const long long g1 = total_steps * (blockIdx.x + 1) / gridDim.x;
   const int nsteps = (int)(g1 - g0);
+  const int2* steps = t.steps + g0;   // this CTA's (tile, sender) list
   const int N = a.N, BN = a.B * a.N;
 
   if (threadIdx.x == 0) {
@@ -156,10 +158,11 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
         mbar_expect_tx_elect(ubar + BwdBars::w, W1_BYTES);
         bulk_g2s_elect(ub + OFF_W1, t.w1img, W1_BYTES, ubar + BwdBars::w);
       }
-      int q_tile = (int)(g0 / N), q_s = (int)(g0 % N);
       for (int it = 0; it < nsteps; ++it) {
         const int st = it % QS;
         if (it >= QS) mbar_wait(ubar + BwdBars::qe + 8 * st, (it / QS - 1) & 1);
+        const int2 ts = steps[it];
+        const int q_tile = ts.x, q_s = ts.y;
         const int j0 = (q_tile * TILE) / N;
         const int rl = min(q_tile * TILE + TILE - 1, BN - 1);
         const int nj = rl / N - j0 + 1;
@@ -168,7 +171,6 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
         mbar_expect_tx_elect(bar, (uint32_t)nj * F_QROW);
         for (int j = 0; j < nj; ++j)
           bulk_g2s_elect(dst + (uint32_t)j * F_QROW, a.Q + ((size_t)(j0 + j) * N + q_s) * K0, F_QROW, bar);
-        if (++q_s == N) { q_s = 0; ++q_tile; }
       }
     } else if (warp == 16 && nsteps > 0) {
       // =============================== MMA issuer ======================================================
@@ -287,6 +289,10 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
   } else {
     // =============================== epilogue warps ====================================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(F_REGS_EPI));
+    if (nsteps == 0) {   // no work (fewer live steps than CTAs): this CTA's part of its slab must still be defined
+      float* slab = t.wslab + (size_t)blockIdx.x * SLAB_FLOATS;
+      for (int i = (CH ? SLAB_DW1 : SLAB_DW2) + threadIdx.x; i < (CH ? SLAB_DW2 : SLAB_FLOATS); i += F_NEPI) slab[i] = 0.f;
+    }
     if (nsteps > 0) {
       const int q = warp >> 2;
       const int row = (warp & 3) * 32 + lane;
@@ -314,7 +320,7 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
       uint32_t s0_next = 0, k0w_next = 0;     // ... of the step whose H0' was built last
 
       // ---- H0' builder state -------------------------------------------------------------------------------
-      int h_tile = (int)(g0 / N), h_s = (int)(g0 % N), h_loaded = -1, h_r = 0;
+      int h_loaded = -1, h_r = 0;
       uint32_t h_qoff = 0;
       auto write_onehot = [&](int tile) {   // CHAIN: constant-1 columns 96,97 and one-hot jet columns 98+j of the H0' tile
         if (q == 0) {
@@ -338,6 +344,8 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
         }
       };
       auto build_h0 = [&](int it) {
+        const int2 hts = steps[it];
+        const int h_tile = hts.x, h_s = hts.y;
         if (h_tile != h_loaded) {
           h_loaded = h_tile;
           const int r = h_tile * TILE + row;
@@ -377,12 +385,11 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
         mbar_arrive(bar0 + BwdBars::qe + 8 * (it % QS));
         fence_async_smem();
         mbar_arrive(bar0 + BwdBars::rdyA);
-        if (++h_s == N) { h_s = 0; ++h_tile; }
       };
 
       // ---- state of the current step ------------------------------------------------------------------------
-      int c_tile = h_tile, c_s = h_s, c_r = 0, c_jet = 0;
-      bool c_valid = false;
+      int c_tile = steps[0].x, c_s = steps[0].y, c_r = 0, c_jet = 0;
+      bool c_valid = false, c_first = true;   // c_first: first step of its tile inside this CTA's range
       auto enter_tile = [&]() {   // rows of the tile the current step belongs to; their dAgg
         const int r = c_tile * TILE + row;
         c_valid = r < BN;
@@ -490,7 +497,7 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
             mbar_wait(bar0 + BwdBars::doneE, (it - 1) & 1);
             tc_fence_after();
             dq_readout();
-            if (c_s == 0) write_onehot(c_tile);   // first step of a new tile: the old one-hot columns are free now
+            if (c_first) write_onehot(c_tile);   // first step of a new tile: the old one-hot columns are free now
           }
         } else {
           fence_async_smem();
@@ -643,19 +650,23 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
           p_j0 = (c_tile * TILE) / N;
           p_nj = min(c_tile * TILE + TILE - 1, BN - 1) / N - p_j0 + 1;
           p_s = c_s;
-          if (++c_s == N) {
-            if (c_valid) {
-              float* dst = a.dP + (size_t)c_r * K0 + q * 8;
+          {   // advance; flush dP when the next step belongs to another tile (or there is none)
+            const int2 nx = it + 1 < nsteps ? steps[it + 1] : make_int2(-1, 0);
+            c_first = nx.x != c_tile;
+            c_s = nx.y;
+            if (c_first) {
+              if (c_valid) {
+                float* dst = a.dP + (size_t)c_r * K0 + q * 8;
 #pragma unroll
-              for (int c = 0; c < Q0; c += 4)
-                red_add_v4(dst + 32 * (c >> 3) + (c & 7), dPacc[c] * sc_g0, dPacc[c + 1] * sc_g0, dPacc[c + 2] * sc_g0,
-                           dPacc[c + 3] * sc_g0);
+                for (int c = 0; c < Q0; c += 4)
+                  red_add_v4(dst + 32 * (c >> 3) + (c & 7), dPacc[c] * sc_g0, dPacc[c + 1] * sc_g0, dPacc[c + 2] * sc_g0,
+                             dPacc[c + 3] * sc_g0);
+              }
+#pragma unroll
+              for (int c = 0; c < Q0; ++c) dPacc[c] = 0.f;
+              c_tile = nx.x;
+              if (it + 1 < nsteps) enter_tile();
             }
-#pragma unroll
-            for (int c = 0; c < Q0; ++c) dPacc[c] = 0.f;
-            c_s = 0;
-            ++c_tile;
-            if (it + 1 < nsteps) enter_tile();
           }
         } else {
           // ---- DW2: H0' two steps ahead (layer 1 runs one step ahead of the dW2 MMA) ---------------------------------------
@@ -663,10 +674,13 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
             mbar_wait(bar0 + BwdBars::doneA, (it + 1) & 1);   // M1(it+1) done: H0' tile free
             build_h0(it + 2);
           }
-          if (++c_s == N) {
-            c_s = 0;
-            ++c_tile;
-            if (it + 1 < nsteps) enter_tile();
+          if (it + 1 < nsteps) {
+            const int2 nx = steps[it + 1];
+            c_s = nx.y;
+            if (nx.x != c_tile) {
+              c_tile = nx.x;
+              enter_tile();
+            }
           }
         }
       }
@@ -676,13 +690,6 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
         mbar_wait(bar0 + BwdBars::doneE, (nsteps - 1) & 1);
         tc_fence_after();
         dq_readout();
-        if (c_s != 0 && c_valid) {   // partial tile: flush dP
-          float* dst = a.dP + (size_t)c_r * K0 + q * 8;
-#pragma unroll
-          for (int c = 0; c < Q0; c += 4)
-            red_add_v4(dst + 32 * (c >> 3) + (c & 7), dPacc[c] * sc_g0, dPacc[c + 1] * sc_g0, dPacc[c + 2] * sc_g0,
-                       dPacc[c + 3] * sc_g0);
-        }
         // dW1^T accumulator: lane = H0' column k0 (< 96: dW1[:, k0]; 96: db1), column n1 = 32c + 8q + e
         float* slab = t.wslab + (size_t)blockIdx.x * SLAB_FLOATS;
         float v[Q1];

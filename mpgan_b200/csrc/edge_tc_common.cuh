@@ -294,8 +294,11 @@ struct TcArgs {
   const uint8_t* w2img;
   uint2* sbits;           // backward: sign bits of D2, one uint2 per (step, epilogue thread)
   float* wslab;           // backward: per-CTA weight-gradient partials (edge_tc_bwd.cuh: SLAB_*)
+  // work list: the (tile, sender) steps with at least one unmasked sender row, tile-major, sender ascending
+  // (step_list_kernel); CTA b owns steps [total*b/grid, total*(b+1)/grid)
+  const int2* steps;
+  const int* total_steps;
   int num_tiles;
-  long long total_steps;
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -303,8 +306,9 @@ struct TcArgs {
 // k = K, K+1, zero elsewhere.
 // ---------------------------------------------------------------------------------------------------
 __global__ void weight_image_kernel(const float* __restrict__ W, const float* __restrict__ bias, int Nout, int K,
-                                    int Kpad, float scale, uint8_t* __restrict__ img) {
+                                    int Kpad, float scale, uint8_t* __restrict__ img, int* __restrict__ zero_me) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx == 0 && zero_me != nullptr) *zero_me = 0;   // the work-list counter of the step_list_kernel that follows
   if (idx >= Nout * Kpad) return;
   const int n = idx / Kpad, k = idx % Kpad;
   float v = 0.f;
@@ -316,3 +320,38 @@ __global__ void weight_image_kernel(const float* __restrict__ W, const float* __
   *reinterpret_cast<__nv_bfloat16*>(img + off) = __float2bfloat16_rn(v);
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Work list.  A step (128-receiver tile, sender index s) whose sender rows are masked in every jet the
+// tile touches contributes exactly zero to the aggregate and to every gradient: it is dropped here, so
+// padded particles cost nothing.  One warp per tile: ballots compact its live senders (ascending), one
+// atomicAdd reserves the tile's contiguous slice of the list (tiles land in arbitrary order; only the
+// grouping by tile matters to the kernels).  *total must be zero on entry (weight_image_kernel does it).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) step_list_kernel(const float* __restrict__ mask, int B, int N, int num_tiles,
+                                                        int2* __restrict__ steps, int* __restrict__ total) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x * 8 + warp;
+  if (tile >= num_tiles) return;
+  const int BN = B * N;
+  const int j0 = (tile * TILE) / N;
+  const int j1 = min(tile * TILE + TILE - 1, BN - 1) / N;
+  auto active = [&](int s) {
+    if (s >= N) return false;
+    if (mask == nullptr) return true;
+    bool any = false;
+    for (int j = j0; j <= j1; ++j) any |= mask[(size_t)j * N + s] != 0.f;
+    return any;
+  };
+  int count = 0;
+  for (int s0 = 0; s0 < N; s0 += 32) count += __popc(__ballot_sync(0xffffffffu, active(s0 + lane)));
+  int off = 0;
+  if (lane == 0 && count > 0) off = atomicAdd(total, count);
+  off = __shfl_sync(0xffffffffu, off, 0);
+  for (int s0 = 0; s0 < N; s0 += 32) {
+    const bool f = active(s0 + lane);
+    const uint32_t b = __ballot_sync(0xffffffffu, f);
+    if (f) steps[off + __popc(b & ((1u << lane) - 1u))] = make_int2(tile, s0 + lane);
+    off += __popc(b);
+  }
+}

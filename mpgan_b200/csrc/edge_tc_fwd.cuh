@@ -94,9 +94,11 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + F_OFF_BAR + 192);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long g0 = t.total_steps * blockIdx.x / gridDim.x;
-  const long long g1 = t.total_steps * (blockIdx.x + 1) / gridDim.x;
+  const long long total_steps = *t.total_steps;
+  const long long g0 = total_steps * blockIdx.x / gridDim.x;
+  const long long g1 = total_steps * (blockIdx.x + 1) / gridDim.x;
   const int nsteps = (int)(g1 - g0);
+  const int2* steps = t.steps + g0;   // this CTA's (tile, sender) list
   const int N = a.N, BN = a.B * a.N;
   MPG_TP(0);
 
@@ -130,10 +132,11 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
       mbar_expect_tx_elect(bar_w, W1_BYTES + W2_BYTES);
       bulk_g2s_elect(sW1, t.w1img, W1_BYTES, bar_w);
       bulk_g2s_elect(sW2, t.w2img, W2_BYTES, bar_w);
-      int q_tile = (int)(g0 / N), q_s = (int)(g0 % N);   // step whose Q rows are loaded next
       for (int it = 0; it < nsteps; ++it) {
         // stage it % F_QS is free once every builder thread has read the rows of step it - F_QS
         if (it >= F_QS) mbar_wait(bar_qe + 8 * (it & (F_QS - 1)), (it / F_QS - 1) & 1);
+        const int2 ts = steps[it];
+        const int q_tile = ts.x, q_s = ts.y;
         const int j0 = (q_tile * TILE) / N;
         const int rl = min(q_tile * TILE + TILE - 1, BN - 1);
         const int nj = rl / N - j0 + 1;
@@ -142,7 +145,6 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
         mbar_expect_tx_elect(bar, (uint32_t)nj * F_QROW);
         for (int j = 0; j < nj; ++j)
           bulk_g2s_elect(dst + (uint32_t)j * F_QROW, a.Q + ((size_t)(j0 + j) * N + q_s) * K0, F_QROW, bar);
-        if (++q_s == N) { q_s = 0; ++q_tile; }
       }
     } else if (warp == 16 && nsteps > 0) {
       // =============================== MMA issuer ================================================
@@ -257,10 +259,11 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
     float Preg[Q0];
 
     // ---- state of the H0' builder (step it+2) -----------------------------------------------------
-    int h_tile = (int)(g0 / N), h_s = (int)(g0 % N);
     int h_loaded = -1, h_r = 0;
     uint32_t h_qoff = 0;
     auto build_h0 = [&](int it) {
+      const int2 hts = steps[it];
+      const int h_tile = hts.x, h_s = hts.y;
       if (h_tile != h_loaded) {
         h_loaded = h_tile;
         const int r = h_tile * TILE + row;
@@ -300,24 +303,26 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
       mbar_arrive(bar_qe + 8 * (it & (F_QS - 1)));   // Q rows consumed (generic-proxy reads are complete)
       fence_async_smem();
       mbar_arrive(bar_h0);
-      if (++h_s == N) { h_s = 0; ++h_tile; }
     };
 
-    // ---- state of the accumulating epilogue (step it-1) -------------------------------------------
-    int e_tile = h_tile, e_s = h_s, e_row = 0, e_jet = 0;
-    bool e_valid = false;
-    float e_m = 0.f;
-    auto e_enter_tile = [&]() {
-      const int r = e_tile * TILE + row;
-      e_valid = r < BN;
-      e_row = e_valid ? r : BN - 1;
-      e_jet = e_row / N;
+    // ---- tile state: `cur` = tile of step `it` (mask / dropout rows), `acc` = tile the accumulators belong to
+    int cur_tile = -1, cur_row = 0, cur_jet = 0;
+    bool cur_valid = false;
+    int acc_tile = steps[0].x, acc_row = 0;
+    bool acc_valid = false;
+    float e_m = 0.f;      // mask multiplier of the step whose E2 is pending
+    auto enter_cur = [&](int tile) {
+      cur_tile = tile;
+      const int r = tile * TILE + row;
+      cur_valid = r < BN;
+      cur_row = cur_valid ? r : BN - 1;
+      cur_jet = cur_row / N;
     };
-    auto e_load_mask = [&]() { e_m = e_valid ? (a.mask ? __ldg(a.mask + (size_t)e_jet * N + e_s) : 1.f) : 0.f; };
+    auto mask_of = [&](int s) { return cur_valid ? (a.mask ? __ldg(a.mask + (size_t)cur_jet * N + s) : 1.f) : 0.f; };
     const float fl_scale = a.out_scale * (DROP ? 2.f : 1.f) * 0.5f * (1.f + a.alpha);
     auto flush = [&]() {
-      if (e_valid) {
-        float* dst = a.agg + (size_t)e_row * N2 + q * 8;
+      if (acc_valid) {
+        float* dst = a.agg + (size_t)acc_row * N2 + q * 8;
 #pragma unroll
         for (int h = 0; h < 2; ++h)
 #pragma unroll
@@ -344,8 +349,9 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
     };
     uint32_t kz = 0, kwd = 0;   // layer-2 keep words of the step whose E1 ran last (consumed one iteration later)
 
-    e_enter_tile();
-    e_load_mask();
+    enter_cur(acc_tile);
+    acc_row = cur_row;
+    acc_valid = cur_valid;
     MPG_TP(2);
     build_h0(0);
     MPG_TP(3);
@@ -354,10 +360,12 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
       build_h0(1);
     }
 
-    // pair row of the step whose E1 runs in iteration `it` (for the dropout draw)
-    int d_tile = e_tile, d_s = e_s;
+    float m_cur = 0.f;   // mask multiplier of step `it`
 
     for (int it = 0; it < nsteps; ++it) {
+      const int2 ts = steps[it];
+      if (ts.x != cur_tile) enter_cur(ts.x);
+      m_cur = mask_of(ts.y);
       // ---- E2lo(it-1) ----------------------------------------------------------------------------
       if (it >= 1) {
         mbar_wait(bar_d2lo, (it - 1) & 1);
@@ -371,10 +379,8 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
       // ---- E1(it): D1 -> H1' ---------------------------------------------------------------------
       uint32_t kx = 0, ky = 0, kz_n = 0, kw_n = 0;
       if (DROP) {
-        const int r = d_tile * TILE + row;
-        const u4 b = edge_drop_bits(drop.seed, (uint64_t)(r < BN ? r : BN - 1) * N + d_s, q, 1);
+        const u4 b = edge_drop_bits(drop.seed, (uint64_t)cur_row * N + ts.y, q, 1);
         kx = b.x; ky = b.y; kz_n = b.z; kw_n = b.w;
-        if (++d_s == N) { d_s = 0; ++d_tile; }
       }
       mbar_wait(bar_d1 + 8 * (it & 1), (it >> 1) & 1);
       MPG_TR(it, 3);
@@ -410,14 +416,14 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
         tc_fence_before();
         mbar_arrive(bar_f2hi);
         MPG_TR(it, 5);
-        if (++e_s == N) {   // step it-1 was the tile's last sender
+        if (cur_tile != acc_tile) {   // step it-1 was the last one of its tile
           flush();
-          e_s = 0;
-          ++e_tile;
-          e_enter_tile();
+          acc_tile = cur_tile;
+          acc_row = cur_row;
+          acc_valid = cur_valid;
         }
-        e_load_mask();      // multiplier of step `it` (used in the next iteration)
       }
+      e_m = m_cur;          // multiplier of step `it` (its E2 runs in the next iteration)
       kz = kz_n;
       kwd = kw_n;
       // ---- H0'(it+2) -----------------------------------------------------------------------------

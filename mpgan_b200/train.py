@@ -71,8 +71,9 @@ def get_gen_noise(batch_size, num_particles, latent_node_size, sd=0.2, device="c
 
 class GANTrainer:
     def __init__(self, G, D, lr_gen=1e-5, lr_disc=3e-5, num_particles=30, latent_node_size=32, sd=0.2,
-                 process_group=None):
+                 process_group=None, batch_real_fake=True):
         self.G, self.D = G, D
+        self.batch_real_fake = batch_real_fake
         self.fpG, self.fpD = FlatParams(G), FlatParams(D)
         self.optG, self.optD = FusedRMSprop(self.fpG, lr_gen), FusedRMSprop(self.fpD, lr_disc)
         self.num_particles, self.latent, self.sd = num_particles, latent_node_size, sd
@@ -103,10 +104,18 @@ class GANTrainer:
         self.D.train()
         self.fpD.zero_grad()
         self.G.eval()
-        d_real = self.D(data, labels)
         with torch.no_grad():
             fake = self.gen(data.shape[0], labels, noise)
-        d_fake = self.D(fake, labels)
+        if self.batch_real_fake:
+            # D(real) and D(fake) as ONE forward/backward over 2B jets: jets never interact inside D (no
+            # BatchNorm; per-row dropout), so outputs and gradients equal the reference's two calls
+            # (train.py:425,446) while every kernel sees twice the rows per launch
+            B = data.shape[0]
+            d_both = self.D(torch.cat((data, fake), 0), torch.cat((labels, labels), 0))
+            d_real, d_fake = d_both[:B], d_both[B:]
+        else:
+            d_real = self.D(data, labels)
+            d_fake = self.D(fake, labels)
         # least squares: real -> 1, fake -> 0 (train.py:357-358, 369-370, 378)
         loss = ((d_real - 1.0) ** 2).mean() + (d_fake ** 2).mean()
         loss.backward()
