@@ -35,6 +35,9 @@ WORKLOADS = {
 }
 H = (96, 160, 192)
 FN = (256, 256)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the ncu --set full
+# captures summarised under profiles/ (filled in per round; null where no capture exists for the workload)
+DRAM_TRAFFIC = {}
 
 
 def layer_flops(N, F, Fout):
@@ -64,7 +67,8 @@ def peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """Samples nvidia-smi clocks / throttle reasons (100 ms period) from before the warm-up on; stop(t0, t1)
+    reports the samples that fall inside the timed window [t0, t1] (wall clock)."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -84,26 +88,37 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def wait_first(self, timeout=5.0):
+        t_end = time.time() + timeout
+        while self.proc is not None and not self.rows and time.time() < t_end:
+            time.sleep(0.05)
+
+    def stop(self, t0, t1):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)   # let the sample covering the end of the window arrive
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             pass
-        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        ok = [(t, r) for t, r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        win = [r for t, r in ok if t0 <= t <= t1 + 0.12]
+        note = "samples inside the timed window"
+        if len(win) < 2:   # window shorter than two sampling periods: use every sample taken under load
+            win = [r for t, r in ok if t >= t0 - 2.0]
+            note = "timed window < 2 sampling periods: samples from 2 s before it to the end of the bench"
+        sm = sorted(float(r[1]) for r in win)
+        mx = [float(r[2]) for r in win if r[2].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
-            if len(r) >= 9:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+        for r in win:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "note": note}
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -200,7 +215,7 @@ def run_ours(args, wl):
     G.load_state_dict(torch.load(os.path.join(gold, "mp_g_weights.pt"), map_location=dev))
     D.load_state_dict(torch.load(os.path.join(gold, "mp_d_seed4_weights.pt"), map_location=dev))
     gen = torch.Generator(device=dev).manual_seed(4 + rank)
-    data, labels, _ = train.synthetic_jets(B, N, dev, gen)
+    data, labels, _ = train.synthetic_jets(B, N, dev, gen, all_real=args.all_real)
     flush_buf = torch.empty(256 * 1024 * 1024 // 4, device=dev)  # > 126 MB L2
 
     eager_step = None
@@ -231,27 +246,40 @@ def run_ours(args, wl):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
+        one_step(data, labels)
+    # keep the GPUs under load for ~1.5 s so nvidia-smi (100 ms period, slow to start) has samples before the
+    # timed window opens; every rank runs the SAME number of extra steps (the steps contain collectives)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    one_step(data, labels)
+    torch.cuda.synchronize()
+    n_extra = torch.tensor([min(3000, int(1.5 / max(time.time() - t0, 1e-4)) + 1)], device=dev)
+    if world > 1:
+        dist.all_reduce(n_extra, op=dist.ReduceOp.MAX)
+    for _ in range(int(n_extra)):
         one_step(data, labels)
     barrier()
 
     # ---- device-resident timed region ---------------------------------------------------------------
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches0 = L.mpg_launch_count()
     barrier()
+    t_wall0 = time.time()
     for i in range(args.steps):
         flush_buf.zero_()  # evict L2 between timed steps (untimed)
         ev[i][0].record()
         one_step(data, labels)
         ev[i][1].record()
     barrier()
+    t_wall1 = time.time()
     launches = L.mpg_launch_count() - launches0
     if kind == "train" and args.graph:
         launches = tr.launches_per_step * args.steps   # replayed kernels: counted once at capture
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = torch.tensor([sum(step_ms)], device=dev, dtype=torch.float64)
     if world > 1:
@@ -300,24 +328,29 @@ def run_ours(args, wl):
         pk = peaks()
         # dominant kernel class by device time
         by = {}
-        for name, a, b, fl in prof:
-            t = by.setdefault(name, [0.0, 0, 0.0])
+        for name, a, b, fl, fl_exec in prof:
+            t = by.setdefault(name, [0.0, 0, 0.0, 0.0])
             t[0] += a.elapsed_time(b)
             t[1] += 1
             t[2] += fl
+            t[3] += fl_exec
         kernels = {k: v for k, v in by.items() if k.endswith("_kernel")} or by
         dom = max(kernels, key=lambda k: kernels[k][0]) if kernels else None
         prof_steps = 3
         roof = None
         if dom:
-            ms, cnt, fl = by[dom]
-            ach = fl / (ms * 1e-3) / 1e12
+            ms, cnt, fl, fl_exec = by[dom]
+            # `achieved` counts only the (tile, sender) steps the kernel executes (fully masked senders are
+            # skipped); `achieved_dense` is SURVEY 8(d)'s dense N^2 figure over the same time
+            ach = fl_exec / (ms * 1e-3) / 1e12
             roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s",
-                    "frac": ach / pk["tflops"], "traffic": None, "peak_source": pk["src"] + " bf16 sustained",
+                    "frac": ach / pk["tflops"], "traffic": DRAM_TRAFFIC.get((args.workload, dom)),
+                    "achieved_dense": fl / (ms * 1e-3) / 1e12, "executed_step_fraction": fl_exec / fl if fl else None,
+                    "peak_source": pk["src"] + " bf16 sustained",
                     "launches": cnt, "avg_launch_ms": ms / cnt,
                     "share_of_step": (ms / prof_steps) / (sum(step_ms) / len(step_ms)),
-                    "all": {k: {"ms_total": v[0], "launches": v[1], "tflops": v[2] / (v[0] * 1e-3) / 1e12}
-                            for k, v in by.items()}}
+                    "all": {k: {"ms_total": v[0], "launches": v[1], "tflops_executed": v[3] / (v[0] * 1e-3) / 1e12,
+                                "tflops_dense": v[2] / (v[0] * 1e-3) / 1e12} for k, v in by.items()}}
         alg = step_flops(N) if kind == "train" else net_flops(N)[0]
         # CPU baseline: bounded sample of the same workload on the host cores
         try:
@@ -332,6 +365,7 @@ def run_ours(args, wl):
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": args.workload, "particles": N, "batch_per_gpu": B, "global_batch": B * world,
+                       "particles_per_jet": "all N real" if args.all_real else "n ~ U{1..N} (padded rows masked)",
                        "l2": "flushed between timed steps (256 MiB write)", "precision": "bf16 tcgen05 edge network, "
                        "TF32 node GEMMs, fp32 accumulate", "parallelism": f"dp{world}",
                        "cuda_graph": bool(kind == "train" and args.graph)},
@@ -352,12 +386,14 @@ def run_ours(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="run the training step eagerly instead of replaying the captured CUDA graph")
     ap.add_argument("--workload", default="train_n30_b256", choices=sorted(WORKLOADS))
+    ap.add_argument("--all-real", action="store_true",
+                    help="every jet has N real particles (no padding: the unmasked worst case of SURVEY 8d); default n ~ U{1..N}")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -72,8 +72,9 @@ class _Timed:
     """Brackets one C-ABI edge call with events; additionally arms the library's one-shot probes so
     the tcgen05 kernels inside the call are timed on their own (kernel ids: include/mpgan_b200.h)."""
 
-    def __init__(self, name, flops, probes=()):
-        self.name, self.flops, self.probes = name, flops, probes
+    def __init__(self, name, flops, probes=(), frac=1.0):
+        # frac: share of the (tile, sender) steps the kernels execute (fully masked steps are skipped)
+        self.name, self.flops, self.probes, self.frac = name, flops, probes, frac
 
     def __enter__(self):
         if _profile is not None:
@@ -86,14 +87,14 @@ class _Timed:
                 a.record()  # materialise the cudaEvent_t handles
                 b.record()
                 L.mpg_probe(kid, a.cuda_event, b.cuda_event)
-                self.pe.append((kname, a, b, kflops))
+                self.pe.append((kname, a, b, kflops, kflops * self.frac))
             self.e0.record()
         return self
 
     def __exit__(self, *exc):
         if _profile is not None:
             self.e1.record()
-            _profile.append((self.name, self.e0, self.e1, self.flops))
+            _profile.append((self.name, self.e0, self.e1, self.flops, self.flops * self.frac))
             _profile.extend(self.pe)
         return False
 
@@ -105,6 +106,23 @@ def edge_flops(B, N, F, H0, H1, H2):
 
 def _pair_flops(B, N, Ha, Hb):
     return 2.0 * B * N * N * Ha * Hb
+
+
+def edge_active_fraction(mask, B, N):
+    """Share of the (128-receiver tile, sender) steps the tcgen05 kernels execute: a step is dropped when
+    the sender is masked in every jet the tile touches (csrc/edge_tc_common.cuh: step_list_kernel).
+    Reporting helper (synchronises); not on the compute path."""
+    if mask is None:
+        return 1.0
+    m = (mask.reshape(B, N) != 0).to(torch.int32)
+    BN = B * N
+    tiles = (BN + 127) // 128
+    r0 = torch.arange(tiles, device=m.device) * 128
+    j0 = r0 // N
+    j1 = torch.clamp(r0 + 127, max=BN - 1) // N
+    cs = torch.cat((torch.zeros(1, N, dtype=torch.int32, device=m.device), m.cumsum(0).to(torch.int32)), 0)
+    act = (cs[j1 + 1] - cs[j0]) > 0
+    return float(act.sum().item()) / float(tiles * N)
 
 
 def _rows(t):
@@ -181,8 +199,9 @@ class EdgeAggFn(torch.autograd.Function):
         m = None if mask is None else mask.reshape(B, N).contiguous()
         ws_ = [t.contiguous() for t in (w0, b0, w1, b1, w2, b2)]
         seed = next_seed() if p_drop > 0 else 0
+        frac = edge_active_fraction(m, B, N) if _profile is not None else 1.0
         with _Timed("edge_fwd", edge_flops(B, N, F, H0, H1, H2),
-                    [(1, "edge_tc_fwd_kernel", _pair_flops(B, N, H0, H1) + _pair_flops(B, N, H1, H2))]):
+                    [(1, "edge_tc_fwd_kernel", _pair_flops(B, N, H0, H1) + _pair_flops(B, N, H1, H2))], frac):
             _lib.check(L.mpg_edge_fwd(_lib.ptr(x3), ldx, _lib.ptr(m), *[_lib.ptr(t) for t in ws_], B, N, F, H0, H1,
                                       H2, int(ef_mode), int(nd), int(mean), float(alpha), float(p_drop), seed,
                                       _seed_ptr(), _PRECISION, ws.data_ptr(), ws_bytes, _lib.ptr(agg),
@@ -203,9 +222,10 @@ class EdgeAggFn(torch.autograd.Function):
         ws = torch.empty(ws_bytes, device=dagg.device, dtype=torch.uint8)
         dx = torch.empty(B, N, F, device=dagg.device, dtype=torch.float32)
         grads = [torch.zeros_like(t) for t in (w0, b0, w1, b1, w2, b2)]
+        frac = edge_active_fraction(m, B, N) if _profile is not None else 1.0
         with _Timed("edge_bwd", 2.0 * edge_flops(B, N, F, H0, H1, H2),
                     [(2, "edge_tc_bwd_chain_kernel", 2 * _pair_flops(B, N, H0, H1) + _pair_flops(B, N, H1, H2)),
-                     (3, "edge_tc_bwd_dw2_kernel", _pair_flops(B, N, H1, H2))]):
+                     (3, "edge_tc_bwd_dw2_kernel", _pair_flops(B, N, H1, H2))], frac):
             _lib.check(L.mpg_edge_bwd(_lib.ptr(x3), ldx, _lib.ptr(m),
                                       *[_lib.ptr(t) for t in (w0, b0, w1, b1, w2, b2)], B, N, F, H0, H1, H2, ef_mode,
                                       nd, mean, alpha, p, seed, sptr, prec, ws.data_ptr(), ws_bytes, _lib.ptr(dagg),
