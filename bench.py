@@ -380,7 +380,11 @@ def run_ours(args, wl):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # NCCL communicators referenced by a captured CUDA graph do not tear down reliably
+        # (destroy_process_group hung here): everything is measured and printed, so leave at once
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
