@@ -68,7 +68,7 @@ constexpr uint32_t C_RA = 0, C_RB = 160, C_PW1 = 352;       // CHAIN: D1/H1'/dH1
 constexpr uint32_t D_R = 0, D_PW2A = 160, D_PW2B = 336;     // DW2: D1 | dW2 rows 0..127 | rows 128..191
 constexpr int NDW = N1 + 16;                                 // 176: dW2 accumulator width incl. the db2 column
 // weight-gradient partials: every CTA stores its TMEM accumulators to a private slab laid out like the
-// final tensors (dW1 [160,96] | db1 [160] | dW2 [192,160] | db2 [192]); wgrad_reduce_kernel sums the slabs.
+// final tensors (dW1 [160,96] | db1 [160] | dW2^T [160,192] | db2 [192]); wgrad_reduce_kernel sums the slabs.
 // (148 CTAs x 46k atomics onto the same addresses cost more than the whole N=30 main loop.)
 constexpr int SLAB_DW1 = 0, SLAB_DB1 = N1 * K0, SLAB_DW2 = SLAB_DB1 + N1, SLAB_DB2 = SLAB_DW2 + N2 * N1,
               SLAB_FLOATS = SLAB_DB2 + N2;
@@ -716,7 +716,7 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
             if (n2 < N2) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
-                if (col + e < N1) slab[SLAB_DW2 + n2 * N1 + col + e] = v[e] * sc_dw2;
+                if (col + e < N1) slab[SLAB_DW2 + (col + e) * N2 + n2] = v[e] * sc_dw2;   // [n1][n2]: lanes = n2, coalesced
                 else if (col + e == N1) slab[SLAB_DB2 + n2] = v[e] * sc_db2;
               }
             }
@@ -738,6 +738,10 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ slabs, int nslabs,
   if (i >= SLAB_FLOATS) return;
   float s = 0.f;
   for (int c = 0; c < nslabs; ++c) s += slabs[(size_t)c * SLAB_FLOATS + i];
-  float* dst = i < SLAB_DB1 ? dW1 + i : (i < SLAB_DW2 ? db1 + (i - SLAB_DB1) : (i < SLAB_DB2 ? dW2 + (i - SLAB_DW2) : db2 + (i - SLAB_DB2)));
+  float* dst;
+  if (i < SLAB_DB1) dst = dW1 + i;
+  else if (i < SLAB_DW2) dst = db1 + (i - SLAB_DB1);
+  else if (i < SLAB_DB2) dst = dW2 + ((i - SLAB_DW2) % N2) * N1 + (i - SLAB_DW2) / N2;   // slab holds dW2 transposed
+  else dst = db2 + (i - SLAB_DB2);
   *dst += s;
 }
