@@ -94,6 +94,12 @@ __device__ __forceinline__ float tile_at(const float* __restrict__ s, int r, int
 
 constexpr int TILE_FLOATS = (BM * KS > BK * MS) ? BM * KS : BK * MS;
 
+// The epilogue is unrolled over 32 outputs per thread; inlining the Philox-based keep decision twice per
+// output made the kernel 15k instructions (245 KB) and the short node-level GEMMs instruction-cache bound.
+__device__ __noinline__ bool drop_keep_call(const DropCfg& d, uint32_t stream, uint64_t row, uint32_t col) {
+  return drop_keep(d, stream, row, col);
+}
+
 template <bool A_K, bool B_K, bool PRECISE>
 __global__ void __launch_bounds__(NT) gemm_kernel(const float* __restrict__ A, int lda,
                                                   const float* __restrict__ B, int ldb,
@@ -178,31 +184,42 @@ __global__ void __launch_bounds__(NT) gemm_kernel(const float* __restrict__ A, i
   }
 
   // ---- epilogue ---------------------------------------------------------------------------------
+  // Accumulator fragments go through shared memory (the operand tiles are dead) so that the per-element
+  // epilogue is a short ROLLED loop with coalesced rows: unrolled over the 32 fragment values it was
+  // thousands of instructions, and these short GEMMs ran instruction-cache bound.
+  float* Cs = &As[0][0];                 // [BM][BN + 1] floats = 16.6 KB <= sizeof(As)
+  constexpr int CS = BN + 1;
+  static_assert(BM * CS <= 2 * TILE_FLOATS, "C staging tile must fit the A operand buffers");
 #pragma unroll
   for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
     for (int ni = 0; ni < 4; ++ni)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int m = m0 + wm + mi * 16 + g + ((q & 2) ? 8 : 0);
-        const int n = n0 + wn + ni * 8 + 2 * t + (q & 1);
-        if (m >= M || n >= N) continue;
-        float v = acc[mi][ni][q] * epi.scale;
-        if (epi.bias != nullptr && blockIdx.z == 0) v += epi.bias[n];
-        if (epi.act) v = lrelu(v, epi.alpha);
-        if (epi.drop) v = drop_keep(epi.dc, epi.stream, (uint64_t)m, (uint32_t)n) ? v * epi.dc.scale : 0.f;
-        if (epi.gy != nullptr) {
-          const float y = epi.gy[(size_t)m * epi.ldgy + n];
-          float gfac = epi.g_act ? lrelu_grad_from_out(y, epi.alpha) : 1.f;
-          if (epi.g_drop)
-            gfac = drop_keep(epi.gdc, epi.gstream, (uint64_t)m, (uint32_t)n) ? gfac * epi.gdc.scale : 0.f;
-          v *= gfac;
-        }
-        float* dst = C + (size_t)m * ldc + n;
-        if (epi.atomic) atomicAdd(dst, v);
-        else if (epi.accumulate) *dst += v;
-        else *dst = v;
-      }
+      for (int q = 0; q < 4; ++q)
+        Cs[(wm + mi * 16 + g + ((q & 2) ? 8 : 0)) * CS + wn + ni * 8 + 2 * t + (q & 1)] = acc[mi][ni][q];
+  __syncthreads();
+  const bool add_bias = epi.bias != nullptr && blockIdx.z == 0;
+#pragma unroll 2
+  for (int idx = tid; idx < BM * BN; idx += NT) {
+    const int r = idx / BN, c = idx % BN;
+    const int m = m0 + r, n = n0 + c;
+    if (m >= M || n >= N) continue;
+    float v = Cs[r * CS + c] * epi.scale;
+    if (add_bias) v += epi.bias[n];
+    if (epi.act) v = lrelu(v, epi.alpha);
+    if (epi.drop) v = drop_keep_call(epi.dc, epi.stream, (uint64_t)m, (uint32_t)n) ? v * epi.dc.scale : 0.f;
+    if (epi.gy != nullptr) {
+      const float y = epi.gy[(size_t)m * epi.ldgy + n];
+      float gfac = epi.g_act ? lrelu_grad_from_out(y, epi.alpha) : 1.f;
+      if (epi.g_drop)
+        gfac = drop_keep_call(epi.gdc, epi.gstream, (uint64_t)m, (uint32_t)n) ? gfac * epi.gdc.scale : 0.f;
+      v *= gfac;
+    }
+    float* dst = C + (size_t)m * ldc + n;
+    if (epi.atomic) atomicAdd(dst, v);
+    else if (epi.accumulate) *dst += v;
+    else *dst = v;
+  }
 }
 
 __global__ void colsum_kernel(const float* __restrict__ X, int ldx, int M, int N, float* __restrict__ out,
