@@ -32,7 +32,18 @@ WORKLOADS = {
     "train_n150_b256": dict(kind="train", N=150, B=256),
     "gen_n30_b1024": dict(kind="gen", N=30, B=1024),
     "gen_n150_b1024": dict(kind="gen", N=150, B=1024),
+    # BASELINE configs[3]: GAPT (masked set attention) training step, reference batch 512 (setup_training.py:836-838)
+    "train_gapt_n30_b512": dict(kind="train", N=30, B=512, model="gapt"),
+    "train_gapt_isab_n30_b512": dict(kind="train", N=30, B=512, model="gapt", isab=True),
 }
+# GAPT is HBM/latency-bound: algorithmic bytes per jet: each MAB reads x, y and writes its output,
+# (Nq + Nk + Nq) * 64 * 4 B; a G+D step costs 8 D-forward-equivalents + 4 G-forward-equivalents as for MPGAN
+def gapt_step_bytes(N, isab, M=10):
+    mab = lambda nq, nk: (2 * nq + nk) * 64 * 4.0
+    block = (mab(M, N) + mab(N, M)) if isab else mab(N, N)
+    g = 4 * block + N * (64 + 4) * 4.0
+    d = 2 * block + mab(1, N) + N * (4 + 64) * 4.0
+    return 8.0 * d + 4.0 * g
 H = (96, 160, 192)
 FN = (256, 256)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the ncu --set full
@@ -158,15 +169,64 @@ def cpu_step_time(N, B_sample, reps, warm=1, kind="train"):
     return sum(times[warm:]) / reps, torch.get_num_threads()
 
 
+def cpu_gapt_step_time(N, B_sample, reps, warm=1, isab=False):
+    """Times the CPU oracle port of one GAPT train_D + train_G step (oracle/gapt_oracle.py) on B_sample jets."""
+    import torch
+    from mpgan_b200 import presets
+    from oracle import gapt_oracle as go
+    from oracle import mpgan_oracle as mo
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(4)
+    sdG = {k: v.clone().requires_grad_(True) for k, v in presets.gapt_generator(num_hits=N, use_isab=isab).state_dict().items()}
+    sdD = {k: v.clone().requires_grad_(True) for k, v in presets.gapt_discriminator(num_hits=N, use_isab=isab).state_dict().items()}
+    cfgG = go.GaptCfg(num_particles=N, sab_layers=4, use_isab=isab)
+    cfgD = go.GaptCfg(num_particles=N, sab_layers=2, use_isab=isab, dropout_p=0.5, linear_dropout_p=0.5)
+    g = torch.Generator().manual_seed(4)
+    data, labels, _ = mo.synthetic_jets(B_sample, N, g)
+    stD, stG, times = {}, {}, []
+    for i in range(warm + reps):
+        nd = torch.randn(B_sample, N, 64, generator=g) * 0.2
+        ng = torch.randn(B_sample, N, 64, generator=g) * 0.2
+        t0 = time.perf_counter()
+        real_out = go.gapt_d(sdD, data.clone(), labels, cfgD, training=True)
+        fake_out = go.gapt_d(sdD, go.gapt_g(sdG, nd, labels, cfgG, training=False), labels, cfgD, training=True)
+        gD = torch.autograd.grad(mo.d_loss_ls(real_out, fake_out), list(sdD.values()), allow_unused=True)
+        with torch.no_grad():
+            for (k, p), gr in zip(sdD.items(), gD):
+                if gr is not None:
+                    mo.rmsprop_step(p, gr, stD.setdefault(k, torch.zeros_like(gr)), 0.5e-4)
+        fake_out = go.gapt_d(sdD, go.gapt_g(sdG, ng, labels, cfgG, training=True), labels, cfgD, training=True)
+        gG = torch.autograd.grad(mo.g_loss_ls(fake_out), list(sdG.values()), allow_unused=True)
+        with torch.no_grad():
+            for (k, p), gr in zip(sdG.items(), gG):
+                if gr is not None:
+                    mo.rmsprop_step(p, gr, stG.setdefault(k, torch.zeros_like(gr)), 1.5e-4)
+        times.append(time.perf_counter() - t0)
+    return sum(times[warm:]) / reps, torch.get_num_threads()
+
+
+def cpu_time(wl, N, B_sample, reps, warm, kind):
+    if wl.get("model") == "gapt":
+        return cpu_gapt_step_time(N, B_sample, reps, warm, isab=wl.get("isab", False))
+    return cpu_step_time(N, B_sample, reps, warm=warm, kind=kind)
+
+
+def cpu_sample_size(wl):
+    N, kind = wl["N"], wl["kind"]
+    if wl.get("model") == "gapt":
+        return 512
+    return ({30: 32, 150: 2}.get(N, 4)) if kind == "train" else ({30: 256, 150: 16}.get(N, 16))
+
+
 def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     N, kind = wl["N"], wl["kind"]
     # bounded sample: sized so one step is ~1-2 s on a few cores
-    B_sample = {30: 32, 150: 2}.get(N, 4) if kind == "train" else {30: 256, 150: 16}.get(N, 16)
+    B_sample = cpu_sample_size(wl)
     reps = max(1, min(args.steps, 8))
-    sec, cores = cpu_step_time(N, B_sample, reps, warm=min(args.warmup, 1), kind=kind)
+    sec, cores = cpu_time(wl, N, B_sample, reps, min(args.warmup, 1), kind)
     val = B_sample / sec
     line = {
         "impl": "reference", "metric": metric_name(wl), "value": val, "unit": "jets/s", "n_gpus": args.gpus,
@@ -208,19 +268,26 @@ def run_ours(args, wl):
     ops.set_precision(1)
     torch.manual_seed(4 + rank)
 
-    G = presets.mp_generator(num_hits=N).to(dev)
-    D = presets.mp_discriminator(num_hits=N).to(dev)
+    gapt = wl.get("model") == "gapt"
+    latent = 64 if gapt else 32
     torch.manual_seed(4)  # identical initial weights on every rank
-    gold = os.path.join(ROOT, "tests", "golden")
-    G.load_state_dict(torch.load(os.path.join(gold, "mp_g_weights.pt"), map_location=dev))
-    D.load_state_dict(torch.load(os.path.join(gold, "mp_d_seed4_weights.pt"), map_location=dev))
+    if gapt:
+        G = presets.gapt_generator(num_hits=N, use_isab=wl.get("isab", False)).to(dev)
+        D = presets.gapt_discriminator(num_hits=N, use_isab=wl.get("isab", False)).to(dev)
+    else:
+        G = presets.mp_generator(num_hits=N).to(dev)
+        D = presets.mp_discriminator(num_hits=N).to(dev)
+        gold = os.path.join(ROOT, "tests", "golden")
+        G.load_state_dict(torch.load(os.path.join(gold, "mp_g_weights.pt"), map_location=dev))
+        D.load_state_dict(torch.load(os.path.join(gold, "mp_d_seed4_weights.pt"), map_location=dev))
     gen = torch.Generator(device=dev).manual_seed(4 + rank)
     data, labels, _ = train.synthetic_jets(B, N, dev, gen, all_real=args.all_real)
     flush_buf = torch.empty(256 * 1024 * 1024 // 4, device=dev)  # > 126 MB L2
 
     eager_step = None
     if kind == "train":
-        tr = train.GANTrainer(G, D, lr_gen=1e-5, lr_disc=3e-5, num_particles=N)
+        tr = train.GANTrainer(G, D, lr_gen=1.5e-4 if gapt else 1e-5, lr_disc=0.5e-4 if gapt else 3e-5, num_particles=N,
+                              latent_node_size=latent)
 
         def eager_step(d, l):
             return tr.step(d, l)
@@ -239,7 +306,7 @@ def run_ours(args, wl):
 
         def one_step(d, l):
             with torch.no_grad():
-                return G(train.get_gen_noise(B, N, 32, 0.2, dev), l)
+                return G(train.get_gen_noise(B, N, latent, 0.2, dev), l)
 
     def barrier():
         if world > 1:
@@ -352,10 +419,16 @@ def run_ours(args, wl):
                     "all": {k: {"ms_total": v[0], "launches": v[1], "tflops_executed": v[3] / (v[0] * 1e-3) / 1e12,
                                 "tflops_dense": v[2] / (v[0] * 1e-3) / 1e12} for k, v in by.items()}}
         alg = step_flops(N) if kind == "train" else net_flops(N)[0]
+        if gapt:   # HBM-bound path: the roofline is stated on the whole step against the measured copy bandwidth
+            gb = gapt_step_bytes(N, wl.get("isab", False))
+            ach = value / world * gb / 1e9
+            roof = {"bound": "hbm", "kernel": "whole G+D step (attention, projection and dropout kernels)",
+                    "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": None,
+                    "algorithmic_bytes_per_jet": gb, "peak_source": pk["src"] + " HBM copy"}
         # CPU baseline: bounded sample of the same workload on the host cores
         try:
-            bs = {30: 32, 150: 2}.get(N, 4) if kind == "train" else {30: 256, 150: 16}.get(N, 16)
-            sec, cores = cpu_step_time(N, bs, reps=2, warm=1, kind=kind)
+            bs = cpu_sample_size(wl)
+            sec, cores = cpu_time(wl, N, bs, 2, 1, kind)
             cpu = {"value": bs / sec, "unit": "jets/s", "cores": cores, "kind": "port",
                    "sample": f"{bs} jets/step x 2 steps (oracle port of the reference fp32 PyTorch path)"}
         except Exception as e:  # pragma: no cover
@@ -363,18 +436,19 @@ def run_ours(args, wl):
         line = {
             "metric": metric_name(wl), "value": value, "unit": "jets/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if gapt else "bf16", "data": "synthetic",
             "config": {"workload": args.workload, "particles": N, "batch_per_gpu": B, "global_batch": B * world,
                        "particles_per_jet": "all N real" if args.all_real else "n ~ U{1..N} (padded rows masked)",
-                       "l2": "flushed between timed steps (256 MiB write)", "precision": "bf16 tcgen05 edge network, "
-                       "TF32 node GEMMs, fp32 accumulate", "parallelism": f"dp{world}",
+                       "l2": "flushed between timed steps (256 MiB write)",
+                       "precision": ("TF32 projections, fp32 attention core" if gapt else
+                                     "bf16 tcgen05 edge network, TF32 node GEMMs, fp32 accumulate"), "parallelism": f"dp{world}",
                        "cuda_graph": bool(kind == "train" and args.graph)},
             "e2e": {"value": e2e_val, "unit": "jets/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "roofline": roof,
-            "step_roofline": {"algorithmic_gflop_per_jet": alg / 1e9,
-                              "achieved_tflops": value / world * alg / 1e12,
-                              "frac_of_peak": value / world * alg / 1e12 / pk["tflops"]},
+            "step_roofline": None if gapt else {"algorithmic_gflop_per_jet": alg / 1e9,
+                                                "achieved_tflops": value / world * alg / 1e12,
+                                                "frac_of_peak": value / world * alg / 1e12 / pk["tflops"]},
             "cpu_baseline": cpu,
             "clocks": clocks,
         }
