@@ -6,7 +6,7 @@ namespace mpg {
 namespace {
 
 constexpr int BM = 64, BN = 64, BK = 32, NT = 128;
-constexpr int KS = BK + 4;   // stride of a [rows][k] tile  (conflict-free fragment reads)
+constexpr int KS = BK + 8;   // stride of a [rows][k] tile  (conflict-free 64-bit fragment reads)
 constexpr int MS = BM + 8;   // stride of a [k][rows] tile
 
 __device__ __forceinline__ uint32_t to_tf32(float x) {
@@ -28,24 +28,28 @@ template <bool KMAJ>
 __device__ __forceinline__ void load_tile(float (&reg)[16], const float* __restrict__ src, int ld, int r0,
                                           int k0, int R, int K, int tid, bool vec_ok) {
   if (KMAJ) {
-    // thread -> (row = tid/8 + 16*i, k = (tid%8)*4 .. +3)
-    const int kk = k0 + (tid & 7) * 4;
+    // thread -> (row = tid/4 + 32*i, k = (tid%4)*8 .. +7): 8 consecutive k per row, so that the store can
+    // interleave k and k+4 (the two halves of an mma fragment pair)
+    const int kk = k0 + (tid & 3) * 8;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = r0 + (tid >> 3) + 16 * i;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < 2; ++i) {
+      const int r = r0 + (tid >> 2) + 32 * i;
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = 0.f;
       if (r < R) {
         const float* p = src + (size_t)r * ld + kk;
-        if (vec_ok && kk + 3 < K) {
-          v = *reinterpret_cast<const float4*>(p);
+        if (vec_ok && kk + 7 < K) {
+          const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
         } else {
-          if (kk + 0 < K) v.x = p[0];
-          if (kk + 1 < K) v.y = p[1];
-          if (kk + 2 < K) v.z = p[2];
-          if (kk + 3 < K) v.w = p[3];
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (kk + e < K) v[e] = p[e];
         }
       }
-      reg[4 * i + 0] = v.x; reg[4 * i + 1] = v.y; reg[4 * i + 2] = v.z; reg[4 * i + 3] = v.w;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) reg[8 * i + e] = v[e];
     }
   } else {
     // thread -> (k = tid/16 + 8*i, row = (tid%16)*4 .. +3)
@@ -70,26 +74,33 @@ __device__ __forceinline__ void load_tile(float (&reg)[16], const float* __restr
   }
 }
 
-template <bool KMAJ>
+// CVT: round to TF32 here, once per element (fast path); the 3xTF32 path keeps fp32 and splits at use.
+// K-major tiles store k and k+4 of every 8-group next to each other: position 2*(k%4) + (k/4)%2.
+template <bool KMAJ, bool CVT>
 __device__ __forceinline__ void store_tile(float* __restrict__ s, const float (&reg)[16], int tid) {
-  if (KMAJ) {  // s[row][k], stride KS
+  auto cv = [](float x) { return CVT ? __uint_as_float(to_tf32(x)) : x; };
+  if (KMAJ) {  // s[row][k'], stride KS
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float* p = s + ((tid >> 3) + 16 * i) * KS + (tid & 7) * 4;
-      *reinterpret_cast<float4*>(p) = make_float4(reg[4 * i], reg[4 * i + 1], reg[4 * i + 2], reg[4 * i + 3]);
+    for (int i = 0; i < 2; ++i) {
+      float* p = s + ((tid >> 2) + 32 * i) * KS + (tid & 3) * 8;
+      const float* v = reg + 8 * i;
+      *reinterpret_cast<float4*>(p) = make_float4(cv(v[0]), cv(v[4]), cv(v[1]), cv(v[5]));
+      *reinterpret_cast<float4*>(p + 4) = make_float4(cv(v[2]), cv(v[6]), cv(v[3]), cv(v[7]));
     }
   } else {     // s[k][row], stride MS
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       float* p = s + ((tid >> 4) + 8 * i) * MS + (tid & 15) * 4;
-      *reinterpret_cast<float4*>(p) = make_float4(reg[4 * i], reg[4 * i + 1], reg[4 * i + 2], reg[4 * i + 3]);
+      *reinterpret_cast<float4*>(p) = make_float4(cv(reg[4 * i]), cv(reg[4 * i + 1]), cv(reg[4 * i + 2]), cv(reg[4 * i + 3]));
     }
   }
 }
 
+// (element (r, k), element (r, k + 4)) of a tile, k = kk + t with kk a multiple of 8
 template <bool KMAJ>
-__device__ __forceinline__ float tile_at(const float* __restrict__ s, int r, int k) {
-  return KMAJ ? s[r * KS + k] : s[k * MS + r];
+__device__ __forceinline__ float2 tile_pair(const float* __restrict__ s, int r, int kk, int t) {
+  if (KMAJ) return *reinterpret_cast<const float2*>(s + r * KS + kk + 2 * t);
+  return make_float2(s[(kk + t) * MS + r], s[(kk + t + 4) * MS + r]);
 }
 
 constexpr int TILE_FLOATS = (BM * KS > BK * MS) ? BM * KS : BK * MS;
@@ -104,7 +115,7 @@ template <bool A_K, bool B_K, bool PRECISE>
 __global__ void __launch_bounds__(NT) gemm_kernel(const float* __restrict__ A, int lda,
                                                   const float* __restrict__ B, int ldb,
                                                   float* __restrict__ C, int ldc, int M, int N, int K,
-                                                  int k_per_split, GemmEpi epi, bool vecA, bool vecB) {
+                                                  int k_per_split, GemmEpi epi, bool vecA, bool vecB, bool vecC) {
   if (epi.drop) resolve_seed(epi.dc);
   if (epi.g_drop) resolve_seed(epi.gdc);
   __shared__ __align__(16) float As[2][TILE_FLOATS];
@@ -129,8 +140,8 @@ __global__ void __launch_bounds__(NT) gemm_kernel(const float* __restrict__ A, i
   if (nchunks > 0) {
     load_tile<A_K>(ra, A, lda, m0, kbeg, M, kend, tid, vecA);
     load_tile<B_K>(rb, B, ldb, n0, kbeg, N, kend, tid, vecB);
-    store_tile<A_K>(As[0], ra, tid);
-    store_tile<B_K>(Bs[0], rb, tid);
+    store_tile<A_K, !PRECISE>(As[0], ra, tid);
+    store_tile<B_K, !PRECISE>(Bs[0], rb, tid);
   }
   __syncthreads();
   for (int c = 0; c < nchunks; ++c) {
@@ -147,22 +158,30 @@ __global__ void __launch_bounds__(NT) gemm_kernel(const float* __restrict__ A, i
 #pragma unroll
       for (int mi = 0; mi < 2; ++mi) {
         const int r = wm + mi * 16 + g;
-        const float v[4] = {tile_at<A_K>(as, r, kk + t), tile_at<A_K>(as, r + 8, kk + t),
-                            tile_at<A_K>(as, r, kk + t + 4), tile_at<A_K>(as, r + 8, kk + t + 4)};
+        const float2 p0 = tile_pair<A_K>(as, r, kk, t), p1 = tile_pair<A_K>(as, r + 8, kk, t);
+        const float v[4] = {p0.x, p1.x, p0.y, p1.y};   // (r,t) (r+8,t) (r,t+4) (r+8,t+4)
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          ah[mi][q] = to_tf32(v[q]);
-          if (PRECISE) al[mi][q] = to_tf32(v[q] - __uint_as_float(ah[mi][q]));
+          if (PRECISE) {
+            ah[mi][q] = to_tf32(v[q]);
+            al[mi][q] = to_tf32(v[q] - __uint_as_float(ah[mi][q]));
+          } else {
+            ah[mi][q] = __float_as_uint(v[q]);   // rounded to TF32 when the tile was stored
+          }
         }
       }
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) {
-        const int r = wn + ni * 8 + g;
-        const float v[2] = {tile_at<B_K>(bs, r, kk + t), tile_at<B_K>(bs, r, kk + t + 4)};
+        const float2 p = tile_pair<B_K>(bs, wn + ni * 8 + g, kk, t);
+        const float v[2] = {p.x, p.y};
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-          bh[ni][q] = to_tf32(v[q]);
-          if (PRECISE) bl[ni][q] = to_tf32(v[q] - __uint_as_float(bh[ni][q]));
+          if (PRECISE) {
+            bh[ni][q] = to_tf32(v[q]);
+            bl[ni][q] = to_tf32(v[q] - __uint_as_float(bh[ni][q]));
+          } else {
+            bh[ni][q] = __float_as_uint(v[q]);
+          }
         }
       }
 #pragma unroll
@@ -177,8 +196,8 @@ __global__ void __launch_bounds__(NT) gemm_kernel(const float* __restrict__ A, i
         }
     }
     if (c + 1 < nchunks) {
-      store_tile<A_K>(As[cur ^ 1], ra, tid);
-      store_tile<B_K>(Bs[cur ^ 1], rb, tid);
+      store_tile<A_K, !PRECISE>(As[cur ^ 1], ra, tid);
+      store_tile<B_K, !PRECISE>(Bs[cur ^ 1], rb, tid);
     }
     __syncthreads();
   }
@@ -199,12 +218,8 @@ __global__ void __launch_bounds__(NT) gemm_kernel(const float* __restrict__ A, i
         Cs[(wm + mi * 16 + g + ((q & 2) ? 8 : 0)) * CS + wn + ni * 8 + 2 * t + (q & 1)] = acc[mi][ni][q];
   __syncthreads();
   const bool add_bias = epi.bias != nullptr && blockIdx.z == 0;
-#pragma unroll 2
-  for (int idx = tid; idx < BM * BN; idx += NT) {
-    const int r = idx / BN, c = idx % BN;
-    const int m = m0 + r, n = n0 + c;
-    if (m >= M || n >= N) continue;
-    float v = Cs[r * CS + c] * epi.scale;
+  auto finish = [&](float v, int m, int n) {   // everything after the GEMM for output element (m, n)
+    v *= epi.scale;
     if (add_bias) v += epi.bias[n];
     if (epi.act) v = lrelu(v, epi.alpha);
     if (epi.drop) v = drop_keep_call(epi.dc, epi.stream, (uint64_t)m, (uint32_t)n) ? v * epi.dc.scale : 0.f;
@@ -215,10 +230,35 @@ __global__ void __launch_bounds__(NT) gemm_kernel(const float* __restrict__ A, i
         gfac = drop_keep_call(epi.gdc, epi.gstream, (uint64_t)m, (uint32_t)n) ? gfac * epi.gdc.scale : 0.f;
       v *= gfac;
     }
-    float* dst = C + (size_t)m * ldc + n;
-    if (epi.atomic) atomicAdd(dst, v);
-    else if (epi.accumulate) *dst += v;
-    else *dst = v;
+    return v;
+  };
+  if (vecC && !epi.atomic) {   // 16-byte rows: one float4 per thread and iteration
+#pragma unroll 2
+    for (int idx = tid; idx < BM * BN / 4; idx += NT) {
+      const int r = idx / (BN / 4), c = (idx % (BN / 4)) * 4;
+      const int m = m0 + r, n = n0 + c;
+      if (m >= M || n >= N) continue;   // N % 4 == 0 on this path
+      float4* dst = reinterpret_cast<float4*>(C + (size_t)m * ldc + n);
+      float4 o = make_float4(finish(Cs[r * CS + c], m, n), finish(Cs[r * CS + c + 1], m, n + 1),
+                             finish(Cs[r * CS + c + 2], m, n + 2), finish(Cs[r * CS + c + 3], m, n + 3));
+      if (epi.accumulate) {
+        const float4 old = *dst;
+        o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+      }
+      *dst = o;
+    }
+  } else {
+#pragma unroll 2
+    for (int idx = tid; idx < BM * BN; idx += NT) {
+      const int r = idx / BN, c = idx % BN;
+      const int m = m0 + r, n = n0 + c;
+      if (m >= M || n >= N) continue;
+      const float v = finish(Cs[r * CS + c], m, n);
+      float* dst = C + (size_t)m * ldc + n;
+      if (epi.atomic) atomicAdd(dst, v);
+      else if (epi.accumulate) *dst += v;
+      else *dst = v;
+    }
   }
 }
 
@@ -260,11 +300,12 @@ int launch_gemm(bool a_k, bool b_k, bool precise, const float* A, int lda, const
   }
   const bool vecA = (lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
   const bool vecB = (ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
+  const bool vecC = (N % 4 == 0) && (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
   dim3 grid(cdiv(N, BN), cdiv(M, BM), split_k), block(NT);
 #define MPG_GEMM_CASE(AK, BK_, PR)                                                                    \
   if (a_k == AK && b_k == BK_ && precise == PR)                                                       \
     gemm_kernel<AK, BK_, PR><<<grid, block, 0, stream>>>(A, lda, B, ldb, C, ldc, M, N, K, k_per_split, \
-                                                         epi, vecA, vecB);
+                                                         epi, vecA, vecB, vecC);
   MPG_GEMM_CASE(true, true, false)
   MPG_GEMM_CASE(true, true, true)
   MPG_GEMM_CASE(true, false, false)
