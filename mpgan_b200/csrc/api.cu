@@ -29,6 +29,27 @@ __global__ void add_strided_kernel(float* __restrict__ dst, int ldd, const float
   }
 }
 
+// one helper stream + fork/join events per device, created on first use (never destroyed: process lifetime)
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+SideStream* side_stream() {
+  static SideStream per_dev[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  SideStream& ss = per_dev[dev];
+  if (ss.stream == nullptr) {
+    if (cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) != cudaSuccess) {
+      ss.stream = nullptr;
+      return nullptr;
+    }
+  }
+  return &ss;
+}
+
 struct EdgeWs {
   float *P, *Q, *W1t, *W2t, *dP, *dQ, *dxef;
   void* tc;
@@ -147,10 +168,15 @@ int mpg_linear_bwd(const float* dy, const float* y, const float* x, int ldx, con
     if (launch_act_bwd(dy, y, dz, M, N, act, alpha, make_drop(p_drop, seed, seed_dev), rng_stream, s)) return 1;
     g = dz;
   }
-  if (dx != nullptr) {
-    GemmEpi e;
-    e.accumulate = dx_accumulate;
-    if (launch_gemm(true, false, precise, g, N, w, K, dx, lddx, M, K, N, e, 1, s)) return 1;
+  // The input-gradient GEMM and the weight/bias-gradient kernels are independent and each too small to fill
+  // the GPU (2-4 CTAs per SM, latency-bound): fork the weight side onto a second stream and join before
+  // returning.  Stream-ordered events only, so the fork/join is captured into CUDA graphs as parallel branches.
+  SideStream* side = (dx != nullptr && (dw != nullptr || db != nullptr)) ? side_stream() : nullptr;
+  cudaStream_t sw = s;
+  if (side != nullptr) {
+    MPG_CUDA(cudaEventRecord(side->fork, s));
+    MPG_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+    sw = side->stream;
   }
   if (dw != nullptr) {
     GemmEpi e;
@@ -158,10 +184,19 @@ int mpg_linear_bwd(const float* dy, const float* y, const float* x, int ldx, con
     const int tiles = cdiv(N, 64) * cdiv(K, 64);
     int split = tiles >= 148 ? 1 : (2 * 148) / tiles;
     if (split > cdiv(M, 128)) split = cdiv(M, 128);
-    if (launch_gemm(false, false, precise, g, N, x, ldx, dw, K, N, K, M, e, split < 1 ? 1 : split, s)) return 1;
+    if (launch_gemm(false, false, precise, g, N, x, ldx, dw, K, N, K, M, e, split < 1 ? 1 : split, sw)) return 1;
   }
   if (db != nullptr)
-    if (launch_colsum(g, N, M, N, db, s)) return 1;
+    if (launch_colsum(g, N, M, N, db, sw)) return 1;
+  if (dx != nullptr) {
+    GemmEpi e;
+    e.accumulate = dx_accumulate;
+    if (launch_gemm(true, false, precise, g, N, w, K, dx, lddx, M, K, N, e, 1, s)) return 1;
+  }
+  if (side != nullptr) {
+    MPG_CUDA(cudaEventRecord(side->join, side->stream));
+    MPG_CUDA(cudaStreamWaitEvent(s, side->join, 0));
+  }
   return 0;
 }
 
