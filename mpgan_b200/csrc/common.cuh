@@ -96,6 +96,14 @@ __host__ __device__ __forceinline__ bool drop_keep(const DropCfg& d, uint32_t st
   return h >= d.thr16;
 }
 
+// keep bits (bit j = column 32*col32 + j) of one row for the p == 0.5 path: ONE Philox draw serves 32 columns
+// (same bits as drop_keep(), which evaluates them one element at a time)
+__host__ __device__ __forceinline__ uint32_t drop_word32(const DropCfg& d, uint32_t stream, uint64_t row, uint32_t col32) {
+  const u4 r = drop_bits128(d.seed, stream, row, col32 >> 2);
+  const uint32_t w = col32 & 3;
+  return w == 0 ? r.x : (w == 1 ? r.y : (w == 2 ? r.z : r.w));
+}
+
 // ---- edge-network dropout, p == 0.5 ---------------------------------------------------------------
 // The tcgen05 kernels give one thread one pair row x one column "quarter" q of every fe layer, where
 // quarter q is the set of 8-column chunks 4c + q (columns 32c + 8q + [0, 8), c = 0, 1, ...); layer 2 is

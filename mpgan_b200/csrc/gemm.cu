@@ -218,46 +218,56 @@ __global__ void __launch_bounds__(NT) gemm_kernel(const float* __restrict__ A, i
         Cs[(wm + mi * 16 + g + ((q & 2) ? 8 : 0)) * CS + wn + ni * 8 + 2 * t + (q & 1)] = acc[mi][ni][q];
   __syncthreads();
   const bool add_bias = epi.bias != nullptr && blockIdx.z == 0;
-  auto finish = [&](float v, int m, int n) {   // everything after the GEMM for output element (m, n)
-    v *= epi.scale;
-    if (add_bias) v += epi.bias[n];
-    if (epi.act) v = lrelu(v, epi.alpha);
-    if (epi.drop) v = drop_keep_call(epi.dc, epi.stream, (uint64_t)m, (uint32_t)n) ? v * epi.dc.scale : 0.f;
-    if (epi.gy != nullptr) {
-      const float y = epi.gy[(size_t)m * epi.ldgy + n];
-      float gfac = epi.g_act ? lrelu_grad_from_out(y, epi.alpha) : 1.f;
-      if (epi.g_drop)
-        gfac = drop_keep_call(epi.gdc, epi.gstream, (uint64_t)m, (uint32_t)n) ? gfac * epi.gdc.scale : 0.f;
-      v *= gfac;
-    }
-    return v;
-  };
-  if (vecC && !epi.atomic) {   // 16-byte rows: one float4 per thread and iteration
+  // thread -> (row r = tid / 2, 32-column half h = tid % 2): the p == 0.5 keep bits of its 32 outputs (and of the
+  // fused backward factor) come from ONE Philox draw each instead of one per element
+  {
+    const int r = tid >> 1, h = tid & 1;
+    const int m = m0 + r, nb = n0 + 32 * h;
+    if (m < M && nb < N) {
+      uint32_t kw = 0xFFFFFFFFu, gkw = 0xFFFFFFFFu;
+      if (epi.drop && epi.dc.half) kw = drop_word32(epi.dc, epi.stream, (uint64_t)m, (uint32_t)(nb >> 5));
+      if (epi.gy != nullptr && epi.g_drop && epi.gdc.half) gkw = drop_word32(epi.gdc, epi.gstream, (uint64_t)m, (uint32_t)(nb >> 5));
+      auto finish = [&](float v, int j) {   // everything after the GEMM for output element (m, nb + j)
+        const int n = nb + j;
+        v *= epi.scale;
+        if (add_bias) v += epi.bias[n];
+        if (epi.act) v = lrelu(v, epi.alpha);
+        if (epi.drop) {
+          const bool keep = epi.dc.half ? ((kw >> j) & 1u) : drop_keep_call(epi.dc, epi.stream, (uint64_t)m, (uint32_t)n);
+          v = keep ? v * epi.dc.scale : 0.f;
+        }
+        if (epi.gy != nullptr) {
+          const float y = epi.gy[(size_t)m * epi.ldgy + n];
+          float gfac = epi.g_act ? lrelu_grad_from_out(y, epi.alpha) : 1.f;
+          if (epi.g_drop) {
+            const bool keep = epi.gdc.half ? ((gkw >> j) & 1u) : drop_keep_call(epi.gdc, epi.gstream, (uint64_t)m, (uint32_t)n);
+            gfac = keep ? gfac * epi.gdc.scale : 0.f;
+          }
+          v *= gfac;
+        }
+        return v;
+      };
+      const float* cs = Cs + r * CS + 32 * h;
+      float* crow = C + (size_t)m * ldc + nb;
+      if (vecC && !epi.atomic) {   // N % 4 == 0, 16-byte aligned rows
 #pragma unroll 2
-    for (int idx = tid; idx < BM * BN / 4; idx += NT) {
-      const int r = idx / (BN / 4), c = (idx % (BN / 4)) * 4;
-      const int m = m0 + r, n = n0 + c;
-      if (m >= M || n >= N) continue;   // N % 4 == 0 on this path
-      float4* dst = reinterpret_cast<float4*>(C + (size_t)m * ldc + n);
-      float4 o = make_float4(finish(Cs[r * CS + c], m, n), finish(Cs[r * CS + c + 1], m, n + 1),
-                             finish(Cs[r * CS + c + 2], m, n + 2), finish(Cs[r * CS + c + 3], m, n + 3));
-      if (epi.accumulate) {
-        const float4 old = *dst;
-        o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+        for (int j = 0; j < 32 && nb + j < N; j += 4) {
+          float4 o = make_float4(finish(cs[j], j), finish(cs[j + 1], j + 1), finish(cs[j + 2], j + 2), finish(cs[j + 3], j + 3));
+          float4* dst = reinterpret_cast<float4*>(crow + j);
+          if (epi.accumulate) {
+            const float4 old = *dst;
+            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+          }
+          *dst = o;
+        }
+      } else {
+        for (int j = 0; j < 32 && nb + j < N; ++j) {
+          const float v = finish(cs[j], j);
+          if (epi.atomic) atomicAdd(crow + j, v);
+          else if (epi.accumulate) crow[j] += v;
+          else crow[j] = v;
+        }
       }
-      *dst = o;
-    }
-  } else {
-#pragma unroll 2
-    for (int idx = tid; idx < BM * BN; idx += NT) {
-      const int r = idx / BN, c = idx % BN;
-      const int m = m0 + r, n = n0 + c;
-      if (m >= M || n >= N) continue;
-      const float v = finish(Cs[r * CS + c], m, n);
-      float* dst = C + (size_t)m * ldc + n;
-      if (epi.atomic) atomicAdd(dst, v);
-      else if (epi.accumulate) *dst += v;
-      else *dst = v;
     }
   }
 }

@@ -28,15 +28,38 @@ __global__ void rank_mask_kernel(const float* __restrict__ x, int ldx, const flo
 }
 
 // ---- dz = dy * d(act, dropout)/dz evaluated from the layer OUTPUT y --------------------------------
+// One thread per (row, 32-column group): the p == 0.5 keep bits of the group come from ONE Philox draw
+// (an element-wise kernel spent ~80 instructions of RNG per element).
 __global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dz,
                                int M, int N, int act, float alpha, DropCfg dc, uint32_t stream) {
   resolve_seed(dc);
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)M * N) return;
-  const int m = (int)(idx / N), n = (int)(idx % N);
-  float g = act ? lrelu_grad_from_out(y[idx], alpha) : 1.f;
-  if (dc.p > 0.f) g = drop_keep(dc, stream, (uint64_t)m, (uint32_t)n) ? g * dc.scale : 0.f;
-  dz[idx] = dy[idx] * g;
+  const int ng = (N + 31) >> 5;
+  const size_t gidx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gidx >= (size_t)M * ng) return;
+  const int m = (int)(gidx / ng), c32 = (int)(gidx % ng);
+  const int n0 = c32 * 32, nn = min(32, N - n0);
+  const bool drop = dc.p > 0.f;
+  uint32_t kw = 0xFFFFFFFFu;
+  if (drop && dc.half) kw = drop_word32(dc, stream, (uint64_t)m, (uint32_t)c32);
+  const size_t base = (size_t)m * N + n0;
+  const float keep_scale = drop ? dc.scale : 1.f;
+  auto one = [&](float yv, float dyv, int j) {
+    float g = act ? lrelu_grad_from_out(yv, alpha) : 1.f;
+    bool keep = true;
+    if (drop) keep = dc.half ? ((kw >> j) & 1u) : drop_keep(dc, stream, (uint64_t)m, (uint32_t)(n0 + j));
+    return keep ? dyv * g * keep_scale : 0.f;
+  };
+  if (nn == 32 && (N & 3) == 0) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 yv = *reinterpret_cast<const float4*>(y + base + j);
+      const float4 dv = *reinterpret_cast<const float4*>(dy + base + j);
+      *reinterpret_cast<float4*>(dz + base + j) =
+          make_float4(one(yv.x, dv.x, j), one(yv.y, dv.y, j + 1), one(yv.z, dv.z, j + 2), one(yv.w, dv.w, j + 3));
+    }
+  } else {
+    for (int j = 0; j < nn; ++j) dz[base + j] = one(y[base + j], dy[base + j], j);
+  }
 }
 
 // ---- generator tail: out[..., :Fo] = act(h), out[..., Fo] = mask - 0.5 (model.py:535-536,752) ------
@@ -220,7 +243,7 @@ int launch_act_bwd(const float* dy, const float* y, float* dz, int M, int N, int
                    uint32_t stream, cudaStream_t s) {
   const size_t n = (size_t)M * N;
   if (n == 0) return 0;
-  act_bwd_kernel<<<cdiv(n, 256), 256, 0, s>>>(dy, y, dz, M, N, act, alpha, dc, stream);
+  act_bwd_kernel<<<cdiv((size_t)M * ((N + 31) / 32), 128), 128, 0, s>>>(dy, y, dz, M, N, act, alpha, dc, stream);
   MPG_LAUNCH_CHECK();
   return 0;
 }
