@@ -51,7 +51,7 @@ SideStream* side_stream() {
 }
 
 struct EdgeWs {
-  float *P, *Q, *W1t, *W2t, *dP, *dQ, *dxef;
+  float *P, *Q, *W1t, *W2t, *dP, *dQ, *dxef, *wg_scratch;
   void* tc;
   size_t total;
 };
@@ -75,6 +75,8 @@ EdgeWs carve_edge_ws(void* base, int B, int N, int F, int H0, int H1, int H2) {
   w.dP = take(BN * H0);
   w.dQ = take(BN * H0);
   w.dxef = take(BN * F);
+  // sink for the weight gradients of a dx-only backward on the generic path (never read)
+  w.wg_scratch = take((size_t)H0 * (2 * F + 64) + H0 + (size_t)H1 * H0 + H1 + (size_t)H2 * H1 + H2);
   w.tc = p + off;
   off += align_up(edge_tc_workspace_bytes(B, N, H0, H1, H2));
   w.total = off;
@@ -232,15 +234,28 @@ int mpg_edge_bwd(const float* x, int ldx, const float* mask, const float* w0, co
   if (edge_common(a, w, x, ldx, mask, w0, b0, w1, b1, w2, b2, B, N, F, H0, H1, H2, ef_mode, nd, mean, alpha,
                   p_drop, seed, seed_dev, precision, workspace, workspace_bytes, &use_tc, s))
     return 1;
-  MPG_CHECK(dagg && dx && dw0 && db0 && dw1 && db1 && dw2 && db2, "edge_bwd: null gradient pointer");
+  MPG_CHECK(dagg && dx, "edge_bwd: null gradient pointer");
+  // all six weight-gradient pointers null = input gradient only (train_G back-propagates through a frozen D)
+  const bool dx_only = !dw0 && !db0 && !dw1 && !db1 && !dw2 && !db2;
+  MPG_CHECK(dx_only || (dw0 && db0 && dw1 && db1 && dw2 && db2), "edge_bwd: pass all six weight gradients or none");
+  const bool tc_path = use_tc && (edge_tc_features() & 2);
+  if (dx_only && !tc_path) {   // the generic kernel always accumulates them: give it a sink
+    float* sink = w.wg_scratch;
+    dw0 = sink; sink += (size_t)H0 * a.ldwef;
+    db0 = sink; sink += H0;
+    dw1 = sink; sink += (size_t)H1 * H0;
+    db1 = sink; sink += H1;
+    dw2 = sink; sink += (size_t)H2 * H1;
+    db2 = sink;
+  }
   const size_t BN = (size_t)B * N;
   a.dagg = dagg;
   a.dW1 = dw1; a.db1 = db1; a.dW2 = dw2; a.db2 = db2;
   a.dP = w.dP; a.dQ = w.dQ; a.dx_ef = w.dxef;
-  a.dWef = dw0 + 2 * F;
+  a.dWef = dw0 ? dw0 + 2 * F : nullptr;
   MPG_CUDA(cudaMemsetAsync(w.dQ, 0, BN * H0 * sizeof(float), s));
   if (a.n_ef) MPG_CUDA(cudaMemsetAsync(w.dxef, 0, BN * F * sizeof(float), s));
-  const bool tc_bwd = use_tc && (edge_tc_features() & 2);
+  const bool tc_bwd = tc_path;
   if (tc_bwd) {
     MPG_CUDA(cudaMemsetAsync(w.dP, 0, BN * H0 * sizeof(float), s));
     if (launch_edge_tc_bwd(a, w.tc, s)) return 1;

@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(NT) pq_bwd_kernel(const float* __restrict__ dP
       if (r < BN) dx[(size_t)r * lddx + f] = acc[i];
     }
   }
+  if (dW0 == nullptr) return;   // input gradient only
   // ---- dW0[k][c] += sum_r d[r][k (+H0 for c >= F)] x[r][c mod F]: 8 consecutive gradient columns per thread --
   const int ngrp = 2 * H0 / 8;
   for (int idx = threadIdx.x; idx < ngrp * F; idx += NT) {

@@ -128,15 +128,18 @@ int launch_edge_tc_bwd(const EdgeArgs& a, void* ws, cudaStream_t stream) {
   TcArgs t;
   int grid = 1;
   if (tc_prepare(a, ws, t, &grid, stream)) return 1;
+  const bool wgrad = a.dW1 != nullptr;   // null: input gradient only -> CHAIN alone (its dW1 slab is simply not reduced)
   if (a.drop.p > 0.f) {
     if (launch_bwd_one<BWD_CHAIN, true>(t, grid, C_SMEM, stream)) return 1;
-    if (launch_bwd_one<BWD_DW2, true>(t, grid, D_SMEM, stream)) return 1;
+    if (wgrad && launch_bwd_one<BWD_DW2, true>(t, grid, D_SMEM, stream)) return 1;
   } else {
     if (launch_bwd_one<BWD_CHAIN, false>(t, grid, C_SMEM, stream)) return 1;
-    if (launch_bwd_one<BWD_DW2, false>(t, grid, D_SMEM, stream)) return 1;
+    if (wgrad && launch_bwd_one<BWD_DW2, false>(t, grid, D_SMEM, stream)) return 1;
   }
-  wgrad_reduce_kernel<<<cdiv(SLAB_FLOATS, 256), 256, 0, stream>>>(t.wslab, grid, a.dW1, a.db1, a.dW2, a.db2);
-  MPG_LAUNCH_CHECK();
+  if (wgrad) {
+    wgrad_reduce_kernel<<<cdiv(SLAB_FLOATS, 256), 256, 0, stream>>>(t.wslab, grid, a.dW1, a.db1, a.dW2, a.db2);
+    MPG_LAUNCH_CHECK();
+  }
   return 0;
 }
 

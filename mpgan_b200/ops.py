@@ -221,7 +221,16 @@ class EdgeAggFn(torch.autograd.Function):
         ws_bytes = L.mpg_edge_workspace_bytes(B, N, F, H0, H1, H2)
         ws = torch.empty(ws_bytes, device=dagg.device, dtype=torch.uint8)
         dx = torch.empty(B, N, F, device=dagg.device, dtype=torch.float32)
-        grads = [torch.zeros_like(t) for t in (w0, b0, w1, b1, w2, b2)]
+        if any(ctx.needs_input_grad[2:8]):
+            # one zero-filled buffer, six views (one fill kernel instead of six)
+            ws_ = (w0, b0, w1, b1, w2, b2)
+            flat = torch.zeros(sum(t.numel() for t in ws_), device=dagg.device, dtype=torch.float32)
+            grads, off = [], 0
+            for t in ws_:
+                grads.append(flat[off:off + t.numel()].view_as(t))
+                off += t.numel()
+        else:   # frozen weights (train_G back-propagating through D): input gradient only
+            grads = [None] * 6
         frac = edge_active_fraction(m, B, N) if _profile is not None else 1.0
         with _Timed("edge_bwd", 2.0 * edge_flops(B, N, F, H0, H1, H2),
                     [(2, "edge_tc_bwd_chain_kernel", 2 * _pair_flops(B, N, H0, H1) + _pair_flops(B, N, H1, H2)),
