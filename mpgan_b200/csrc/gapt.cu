@@ -59,11 +59,20 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(AttnArgs a, float* __rest
       for (int c = 0; c < MAXD; ++c) acc[c] = 0.f;
       for (int j = 0; j < Nk; ++j) {
         const float p = myrow[j] * inv;
-        if (valid) P[(((size_t)b * a.heads + h) * Nq + i) * Nk + j] = p;
+        myrow[j] = p;
 #pragma unroll
         for (int c = 0; c < MAXD; ++c)
           if (c < d) acc[c] = fmaf(p, vs[j * E + h * d + c], acc[c]);
       }
+      // probabilities of this (head, query chunk): the warp's score rows -> P, contiguous in memory
+      __syncwarp();
+      {
+        const int ni = min(32, Nq - i0);
+        float* Pd = P + (((size_t)b * a.heads + h) * Nq + i0) * Nk;
+        const float* rows = sc + (size_t)warp * 32 * (Nk + 1);
+        for (int idx = lane; idx < ni * Nk; idx += 32) Pd[idx] = rows[(idx / Nk) * (Nk + 1) + idx % Nk];
+      }
+      __syncwarp();
       if (valid)
 #pragma unroll
         for (int c = 0; c < MAXD; ++c)
@@ -80,9 +89,10 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(AttnArgs a, const float* 
   const int E = a.E, Nk = a.Nk, Nq = a.Nq, d = E / a.heads;
   float* ks = sm;
   float* vs = ks + (size_t)Nk * E;
+  const int EP = E + 1;                                   // padded row: lane = query reads are conflict-free
   float* qs = vs + (size_t)Nk * E;
-  float* dos = qs + (size_t)Nq * E;
-  float* dSs = dos + (size_t)Nq * E;                      // [warps][32][Nk+1]
+  float* dos = qs + (size_t)Nq * EP;
+  float* dSs = dos + (size_t)Nq * EP;                     // [warps][32][Nk+1]
   float* Ps = dSs + (size_t)(blockDim.x >> 5) * 32 * (Nk + 1);
   const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   for (int idx = threadIdx.x; idx < Nk * E; idx += blockDim.x) {
@@ -92,8 +102,8 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(AttnArgs a, const float* 
   }
   for (int idx = threadIdx.x; idx < Nq * E; idx += blockDim.x) {
     const int i = idx / E, c = idx % E;
-    qs[idx] = a.q[((size_t)b * Nq + i) * a.ldq + c];
-    dos[idx] = dO[((size_t)b * Nq + i) * E + c];
+    qs[i * EP + c] = a.q[((size_t)b * Nq + i) * a.ldq + c];
+    dos[i * EP + c] = dO[((size_t)b * Nq + i) * E + c];
   }
   __syncthreads();
   const float scale = rsqrtf((float)d);
@@ -110,16 +120,26 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(AttnArgs a, const float* 
         const int i = i0 + lane;
         const bool valid = i < Nq;
         __syncwarp();
+        {   // probabilities of this (head, query chunk): contiguous in memory -> the warp's P rows
+          const int ni = min(32, Nq - i0);
+          const float* Ps_g = P + (((size_t)b * a.heads + h) * Nq + i0) * Nk;
+          for (int idx = lane; idx < ni * Nk; idx += 32) myP[(idx / Nk) * (Nk + 1) + idx % Nk] = Ps_g[idx];
+        }
+        float dor[MAXD];   // this query's dO row for head h (was re-read from shared memory for every key)
+#pragma unroll
+        for (int c = 0; c < MAXD; ++c) dor[c] = (valid && c < d) ? dos[i * EP + h * d + c] : 0.f;
+        __syncwarp();
         float D = 0.f;
         for (int j = 0; j < Nk; ++j) {
           float p = 0.f, dp = 0.f;
           if (valid) {
-            p = P[(((size_t)b * a.heads + h) * Nq + i) * Nk + j];
+            p = myP[lane * (Nk + 1) + j];
 #pragma unroll
             for (int c = 0; c < MAXD; ++c)
-              if (c < d) dp = fmaf(dos[i * E + h * d + c], vs[j * E + h * d + c], dp);
+              if (c < d) dp = fmaf(dor[c], vs[j * E + h * d + c], dp);
+          } else {
+            myP[lane * (Nk + 1) + j] = 0.f;
           }
-          myP[lane * (Nk + 1) + j] = p;
           mydS[lane * (Nk + 1) + j] = dp;
           D = fmaf(p, dp, D);
         }
@@ -150,8 +170,8 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(AttnArgs a, const float* 
 #pragma unroll
             for (int c = 0; c < MAXD; ++c)
               if (c < d) {
-                dkacc[c] = fmaf(ds, qs[(i0 + ii) * E + h * d + c], dkacc[c]);
-                dvacc[c] = fmaf(p, dos[(i0 + ii) * E + h * d + c], dvacc[c]);
+                dkacc[c] = fmaf(ds, qs[(i0 + ii) * EP + h * d + c], dkacc[c]);
+                dvacc[c] = fmaf(p, dos[(i0 + ii) * EP + h * d + c], dvacc[c]);
               }
           }
         }
@@ -227,7 +247,7 @@ int launch_attn_bwd(const AttnArgs& a, const float* P, const float* dO, float* d
   if (attn_check(a)) return 1;
   if (a.B == 0) return 0;
   const size_t smem =
-      ((size_t)2 * a.Nk * a.E + (size_t)2 * a.Nq * a.E + (size_t)2 * 4 * 32 * (a.Nk + 1)) * sizeof(float);
+      ((size_t)2 * a.Nk * a.E + (size_t)2 * a.Nq * (a.E + 1) + (size_t)2 * 4 * 32 * (a.Nk + 1)) * sizeof(float);
   MPG_CHECK(smem <= 227 * 1024, "attention backward: set too large for shared memory (%zu B)", smem);
   MPG_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   attn_bwd_kernel<<<a.B, 128, smem, s>>>(a, P, dO, dq, dk, dv);
