@@ -32,6 +32,25 @@ def get_precision() -> int:
     return _PRECISION
 
 
+# When on, weight/bias gradients of leaf parameters that already own a ``.grad`` buffer (train.FlatParams) are
+# accumulated by the kernels straight into that buffer and the autograd functions return ``None`` for them:
+# no zero-filled temporaries, no AccumulateGrad add kernel per parameter and backward pass.
+_DIRECT_GRAD = False
+
+
+def set_direct_grad(on: bool):
+    global _DIRECT_GRAD
+    _DIRECT_GRAD = bool(on)
+
+
+def _grad_sink(p):
+    """``p.grad`` if the kernels may accumulate into it directly, else ``None``."""
+    if _DIRECT_GRAD and p.is_leaf and p.requires_grad and p.grad is not None and p.grad.is_contiguous() \
+            and p.grad.dtype == torch.float32:
+        return p.grad
+    return None
+
+
 def set_device_seed(t):
     """Register a 1-element int64 CUDA tensor whose value is added to every dropout seed."""
     global _device_seed
@@ -156,6 +175,7 @@ class LinearFn(torch.autograd.Function):
                                     float(alpha), float(p_drop), seed, _seed_ptr(), int(rng_stream), _PRECISION,
                                     _lib.stream()), "mpg_linear_fwd")
         ctx.save_for_backward(x2, w, y)
+        ctx.params = (w, b)
         ctx.cfg = (ldx, M, K, N, int(act), float(alpha), float(p_drop), seed, int(rng_stream), _PRECISION,
                    _seed_ptr())
         return y
@@ -169,12 +189,16 @@ class LinearFn(torch.autograd.Function):
         dy = dy.contiguous()
         dz = torch.empty_like(dy) if (act or p > 0) else None
         dx = torch.empty(*x2.shape, device=dy.device, dtype=torch.float32) if ctx.needs_input_grad[0] else None
-        dw = torch.zeros_like(w) if ctx.needs_input_grad[1] else None
-        db = torch.zeros(N, device=dy.device, dtype=torch.float32) if ctx.needs_input_grad[2] else None
+        wp, bp = ctx.params
+        dw_sink = _grad_sink(wp) if ctx.needs_input_grad[1] else None
+        db_sink = _grad_sink(bp) if ctx.needs_input_grad[2] else None
+        dw = dw_sink if dw_sink is not None else (torch.zeros_like(w) if ctx.needs_input_grad[1] else None)
+        db = db_sink if db_sink is not None else (
+            torch.zeros(N, device=dy.device, dtype=torch.float32) if ctx.needs_input_grad[2] else None)
         _lib.check(L.mpg_linear_bwd(_lib.ptr(dy), _lib.ptr(y), _lib.ptr(x2), ldx, _lib.ptr(w), _lib.ptr(dz),
                                     _lib.ptr(dx), K, 0, _lib.ptr(dw), _lib.ptr(db), M, K, N, act, alpha, p, seed,
                                     sptr, rstream, prec, _lib.stream()), "mpg_linear_bwd")
-        return dx, dw, db, None, None, None, None
+        return (dx, None if dw_sink is not None else dw, None if db_sink is not None else db, None, None, None, None)
 
 
 def linear(x, w, b, act: bool, alpha: float, p_drop: float, rng_stream: int = 16):
@@ -207,6 +231,7 @@ class EdgeAggFn(torch.autograd.Function):
                                       _seed_ptr(), _PRECISION, ws.data_ptr(), ws_bytes, _lib.ptr(agg),
                                       _lib.stream()), "mpg_edge_fwd")
         ctx.save_for_backward(x3, m, *ws_)
+        ctx.params = (w0, b0, w1, b1, w2, b2)
         ctx.cfg = (ldx, B, N, F, H0, H1, H2, int(ef_mode), int(nd), int(mean), float(alpha), float(p_drop), seed,
                    _PRECISION, _seed_ptr())
         return agg
@@ -221,7 +246,11 @@ class EdgeAggFn(torch.autograd.Function):
         ws_bytes = L.mpg_edge_workspace_bytes(B, N, F, H0, H1, H2)
         ws = torch.empty(ws_bytes, device=dagg.device, dtype=torch.uint8)
         dx = torch.empty(B, N, F, device=dagg.device, dtype=torch.float32)
-        if any(ctx.needs_input_grad[2:8]):
+        sinks = [_grad_sink(p) for p in ctx.params] if all(ctx.needs_input_grad[2:8]) else [None] * 6
+        direct = all(g is not None for g in sinks)
+        if direct:
+            grads = sinks
+        elif any(ctx.needs_input_grad[2:8]):
             # one zero-filled buffer, six views (one fill kernel instead of six)
             ws_ = (w0, b0, w1, b1, w2, b2)
             flat = torch.zeros(sum(t.numel() for t in ws_), device=dagg.device, dtype=torch.float32)
@@ -240,6 +269,8 @@ class EdgeAggFn(torch.autograd.Function):
                                       nd, mean, alpha, p, seed, sptr, prec, ws.data_ptr(), ws_bytes, _lib.ptr(dagg),
                                       _lib.ptr(dx), F, *[_lib.ptr(g) for g in grads], _lib.stream()),
                        "mpg_edge_bwd")
+        if direct:
+            grads = [None] * 6
         return (dx, None, *grads, None, None, None, None, None)
 
 

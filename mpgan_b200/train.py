@@ -75,6 +75,7 @@ class GANTrainer:
         self.G, self.D = G, D
         self.batch_real_fake = batch_real_fake
         self.fpG, self.fpD = FlatParams(G), FlatParams(D)
+        ops.set_direct_grad(True)   # kernels accumulate weight gradients straight into the flat .grad buffers
         self.optG, self.optD = FusedRMSprop(self.fpG, lr_gen), FusedRMSprop(self.fpD, lr_disc)
         self.num_particles, self.latent, self.sd = num_particles, latent_node_size, sd
         self.pg = process_group
