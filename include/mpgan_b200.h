@@ -77,6 +77,26 @@ int mpg_edge_bwd(const float* x, int ldx, const float* mask, const float* w0, co
                  int precision, void* workspace, size_t workspace_bytes, const float* dagg, float* dx, int lddx, float* dw0,
                  float* db0, float* dw1, float* db1, float* dw2, float* db2, void* stream);
 
+/* ---- fused node network fn (mpgan/model.py:268-279 with LinearNet :70-85) -------------------------
+ * out = LinearNet([H1, H2] -> NO, final_linear)(cat(a, b)) for rows [M]: a [M, Ka] (the aggregated messages),
+ * b [M, Kb] (the node features), w0 [H1, Ka+Kb], w1 [H2, H1], w2 [NO, H2] in the reference layout.  One
+ * tcgen05 (TF32) kernel per direction; y0 [M, H1] and y1 [M, H2] (layer outputs) are saved for backward.
+ * Dropout uses RNG streams 16, 17, 18 of `seed` (the streams LinearNet gives its layers), p in {0, 0.5}.
+ * mpg_fn_supported() != 0 iff the shape is covered; other shapes go through mpg_linear_* per layer. */
+int mpg_fn_supported(int Ka, int Kb, int H1, int H2, int NO, float p_drop);
+size_t mpg_fn_workspace_bytes(int Ka, int Kb, int H1, int H2, int NO);
+int mpg_fn_fwd(const float* a, int lda, int Ka, const float* b, int ldb, int Kb, int M, const float* w0,
+               const float* b0, const float* w1, const float* b1, const float* w2, const float* b2, int H1, int H2,
+               int NO, float alpha, float p_drop, uint64_t seed, const uint64_t* seed_dev, void* workspace,
+               size_t workspace_bytes, float* y0, float* y1, float* out, void* stream);
+/* da [M, Ka] and db [M, Kb] (dense) are overwritten; dz0 [M, H1], dz1 [M, H2], dz2 [M, NO] are scratch (dz2 only
+ * read/written when p_drop > 0).  Weight/bias gradients are ACCUMULATED (dw0 NULL: input gradients only). */
+int mpg_fn_bwd(const float* dout, const float* y0, const float* y1, const float* a, int lda, int Ka, const float* b,
+               int ldb, int Kb, int M, const float* w0, const float* w1, const float* w2, int H1, int H2, int NO,
+               float alpha, float p_drop, uint64_t seed, const uint64_t* seed_dev, void* workspace,
+               size_t workspace_bytes, float* dz0, float* dz1, float* dz2, float* da, float* db, float* dw0,
+               float* db0, float* dw1, float* db1, float* dw2, float* db2, void* stream);
+
 /* ---- masks and tails ------------------------------------------------------------------------------ */
 /* mask[b,i] = rank(x[b,i,0]) <= int(labels[b]*N) - 1   (bit-exact; mpgan/model.py:692-699) */
 int mpg_rank_mask(const float* x, int ldx, const float* labels, int ldl, int B, int N, float* mask, void* stream);

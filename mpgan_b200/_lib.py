@@ -24,6 +24,12 @@ _SIGS = {
     "mpg_linear_fwd": (C.c_int, [_f, _i, _f, _f, _f, _i, _i, _i, _i, _fl, _fl, _u64, _f, _u32, _i, _f]),
     "mpg_linear_bwd": (C.c_int, [_f, _f, _f, _i, _f, _f, _f, _i, _i, _f, _f, _i, _i, _i, _i, _fl, _fl, _u64, _f,
                                  _u32, _i, _f]),
+    "mpg_fn_supported": (C.c_int, [_i, _i, _i, _i, _i, _fl]),
+    "mpg_fn_workspace_bytes": (C.c_size_t, [_i] * 5),
+    "mpg_fn_fwd": (C.c_int, [_f, _i, _i, _f, _i, _i, _i, _f, _f, _f, _f, _f, _f, _i, _i, _i, _fl, _fl, _u64, _f, _f,
+                             _sz, _f, _f, _f, _f]),
+    "mpg_fn_bwd": (C.c_int, [_f, _f, _f, _f, _i, _i, _f, _i, _i, _i, _f, _f, _f, _i, _i, _i, _fl, _fl, _u64, _f, _f,
+                             _sz, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f]),
     "mpg_edge_workspace_bytes": (C.c_size_t, [_i] * 6),
     "mpg_edge_fwd": (C.c_int, [_f, _i, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _i, _fl, _fl,
                                _u64, _f, _i, _f, _sz, _f, _f]),

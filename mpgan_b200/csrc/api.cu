@@ -4,6 +4,7 @@
 
 #include "../../include/mpgan_b200.h"
 #include "edge.cuh"
+#include "fn_tc.cuh"
 #include "gapt.cuh"
 #include "gemm.cuh"
 #include "misc.cuh"
@@ -195,6 +196,91 @@ int mpg_linear_bwd(const float* dy, const float* y, const float* x, int ldx, con
     e.accumulate = dx_accumulate;
     if (launch_gemm(true, false, precise, g, N, w, K, dx, lddx, M, K, N, e, 1, s)) return 1;
   }
+  if (side != nullptr) {
+    MPG_CUDA(cudaEventRecord(side->join, side->stream));
+    MPG_CUDA(cudaStreamWaitEvent(s, side->join, 0));
+  }
+  return 0;
+}
+
+int mpg_fn_supported(int Ka, int Kb, int H1, int H2, int NO, float p_drop) {
+  return fn_tc_supported(Ka, Kb, H1, H2, NO, p_drop) ? 1 : 0;
+}
+size_t mpg_fn_workspace_bytes(int Ka, int Kb, int H1, int H2, int NO) {
+  return fn_tc_workspace_bytes(Ka, Kb, H1, H2, NO);
+}
+
+int mpg_fn_fwd(const float* a, int lda, int Ka, const float* b, int ldb, int Kb, int M, const float* w0,
+               const float* b0, const float* w1, const float* b1, const float* w2, const float* b2, int H1, int H2,
+               int NO, float alpha, float p_drop, uint64_t seed, const uint64_t* seed_dev, void* workspace,
+               size_t workspace_bytes, float* y0, float* y1, float* out, void* stream) {
+  MPG_CHECK(fn_tc_supported(Ka, Kb, H1, H2, NO, p_drop), "fn: unsupported shape Ka=%d Kb=%d H1=%d H2=%d NO=%d p=%g",
+            Ka, Kb, H1, H2, NO, (double)p_drop);
+  MPG_CHECK(workspace != nullptr && workspace_bytes >= fn_tc_workspace_bytes(Ka, Kb, H1, H2, NO),
+            "fn workspace too small");
+  if (M <= 0) return 0;
+  FnTcArgs t;
+  memset(&t, 0, sizeof(t));
+  t.M = M;
+  t.a = a; t.lda = lda; t.Ka = Ka; t.b = b; t.ldb = ldb; t.Kb = Kb;
+  t.bias[0] = b0; t.bias[1] = b1; t.bias[2] = b2;
+  t.out01[0] = y0; t.out01[1] = y1;
+  t.outa = out; t.ldoa = NO; t.Na = NO; t.outb = nullptr; t.ldob = 0; t.Nb = 0;
+  t.alpha = alpha;
+  t.drop = make_drop(p_drop, seed, seed_dev);
+  t.stream[0] = 16; t.stream[1] = 17; t.stream[2] = 18;
+  return launch_fn_tc(t, false, w0, w1, w2, H1, H2, NO, workspace, (cudaStream_t)stream);
+}
+
+int mpg_fn_bwd(const float* dout, const float* y0, const float* y1, const float* a, int lda, int Ka, const float* b,
+               int ldb, int Kb, int M, const float* w0, const float* w1, const float* w2, int H1, int H2, int NO,
+               float alpha, float p_drop, uint64_t seed, const uint64_t* seed_dev, void* workspace,
+               size_t workspace_bytes, float* dz0, float* dz1, float* dz2, float* da, float* db, float* dw0,
+               float* db0, float* dw1, float* db1, float* dw2, float* db2, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  MPG_CHECK(fn_tc_supported(Ka, Kb, H1, H2, NO, p_drop), "fn: unsupported shape Ka=%d Kb=%d H1=%d H2=%d NO=%d p=%g",
+            Ka, Kb, H1, H2, NO, (double)p_drop);
+  MPG_CHECK(workspace != nullptr && workspace_bytes >= fn_tc_workspace_bytes(Ka, Kb, H1, H2, NO),
+            "fn workspace too small");
+  MPG_CHECK(dz0 != nullptr && dz1 != nullptr && (p_drop == 0.f || dz2 != nullptr), "fn_bwd needs its dz scratch buffers");
+  if (M <= 0) return 0;
+  FnTcArgs t;
+  memset(&t, 0, sizeof(t));
+  t.M = M;
+  t.a = dout; t.lda = NO; t.Ka = NO; t.b = nullptr; t.ldb = 0; t.Kb = 0;
+  t.ysave[0] = y1; t.ysave[1] = y0;
+  t.out01[0] = dz1; t.out01[1] = dz0;
+  t.dz2 = dz2;
+  t.outa = da; t.ldoa = Ka; t.Na = Ka; t.outb = db; t.ldob = Kb; t.Nb = Kb;
+  t.alpha = alpha;
+  t.drop = make_drop(p_drop, seed, seed_dev);
+  t.stream[0] = 16; t.stream[1] = 17; t.stream[2] = 18;
+  if (launch_fn_tc(t, true, w0, w1, w2, H1, H2, NO, workspace, s)) return 1;
+  if (dw0 == nullptr) return 0;
+  // weight / bias gradients: dW_l += dz_l^T (input of layer l), db_l += colsum(dz_l) on the side stream (the
+  // caller's next kernels need only da / db)
+  SideStream* side = side_stream();
+  cudaStream_t sw = s;
+  if (side != nullptr) {
+    MPG_CUDA(cudaEventRecord(side->fork, s));
+    MPG_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+    sw = side->stream;
+  }
+  const float* g2 = p_drop > 0.f ? dz2 : dout;
+  {
+    FnDwArgs d;
+    memset(&d, 0, sizeof(d));
+    d.M = M;
+    // slot order = processing order: the two big layers first, the narrow last layer at the end
+    d.dz[0] = dz1; d.na[0] = H2; d.ina[0] = y0; d.lda[0] = H1; d.ka[0] = H1; d.dw[0] = dw1; d.lddw[0] = H1;
+    d.dz[1] = dz0; d.na[1] = H1; d.ina[1] = a; d.lda[1] = lda; d.ka[1] = Ka; d.inb[1] = b; d.ldb[1] = ldb; d.kb[1] = Kb;
+    d.dw[1] = dw0; d.lddw[1] = Ka + Kb;
+    d.dz[2] = g2; d.na[2] = NO; d.ina[2] = y1; d.lda[2] = H2; d.ka[2] = H2; d.dw[2] = dw2; d.lddw[2] = H2;
+    if (launch_fn_dw(d, sw)) return 1;
+  }
+  if (launch_colsum(g2, NO, M, NO, db2, sw)) return 1;
+  if (launch_colsum(dz1, H2, M, H2, db1, sw)) return 1;
+  if (launch_colsum(dz0, H1, M, H1, db0, sw)) return 1;
   if (side != nullptr) {
     MPG_CUDA(cudaEventRecord(side->join, side->stream));
     MPG_CUDA(cudaStreamWaitEvent(s, side->join, 0));

@@ -72,9 +72,10 @@ class LinearNet(nn.Module):
 
     def forward(self, x: Tensor):
         p = self.dropout_p if self.training else 0.0
+        seed = ops.next_seed() if p > 0 else 0   # one seed per call; layer i draws from RNG stream 16 + i
         for i in range(len(self.net)):
             w, b = self.layer_params(i)
-            x = ops.linear(x, w, b, self.has_act(i), self.leaky_relu_alpha, p, rng_stream=16 + i)
+            x = ops.linear(x, w, b, self.has_act(i), self.leaky_relu_alpha, p, rng_stream=16 + i, seed=seed)
         return x
 
     def __repr__(self):
@@ -179,9 +180,21 @@ class MPLayer(nn.Module):
         p = fe.dropout_p if self.training else 0.0
         agg = ops.edge_aggregate(x, mask if use_mask else None, w0, b0, w1, b1, w2, b2, ef_mode=self._ef_mode,
                                  nd=self._nd, mean=not self.sum, alpha=fe.leaky_relu_alpha, p_drop=p)
+        fn = self.fn
+        pn = fn.dropout_p if self.training else 0.0
+        if len(fn.net) == 3 and fn.final_linear and ops.node_net_supported(
+                agg.shape[2], x.shape[2], self._fn_out(0), self._fn_out(1),
+                self._fn_out(2), pn):
+            # cat(agg, x) -> fn as ONE kernel per direction (the cat is never materialised)
+            (f0, c0), (f1, c1), (f2, c2) = fn.layer_params(0), fn.layer_params(1), fn.layer_params(2)
+            return ops.node_net(agg, x, f0, c0, f1, c1, f2, c2, fn.leaky_relu_alpha, pn)
         h = torch.cat((agg, x), 2).view(batch_size * num_nodes, -1)
         h = self.fn(h)
         return h.view(batch_size, num_nodes, self.output_node_size)
+
+    def _fn_out(self, i: int) -> int:
+        layer = self.fn.net[i]
+        return (layer.module if isinstance(layer, SpectralNorm) else layer).out_features
 
     def __repr__(self):
         return f"MPLayer(fe = {self.fe}, fn = {self.fn})"

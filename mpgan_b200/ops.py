@@ -161,7 +161,7 @@ class LinearFn(torch.autograd.Function):
     """y = dropout(act(x W^T + b)) on rows; mpgan/model.py:77-83."""
 
     @staticmethod
-    def forward(ctx, x, w, b, act, alpha, p_drop, rng_stream):
+    def forward(ctx, x, w, b, act, alpha, p_drop, rng_stream, seed=None):
         L = _lib.lib()
         x2, ldx = _rows(x)
         lead = x2.shape[:-1]
@@ -170,7 +170,8 @@ class LinearFn(torch.autograd.Function):
         w = w.contiguous()
         b = b.contiguous()
         y = torch.empty(*lead, N, device=x.device, dtype=torch.float32)
-        seed = next_seed() if p_drop > 0 else 0
+        if seed is None:
+            seed = next_seed() if p_drop > 0 else 0
         _lib.check(L.mpg_linear_fwd(_lib.ptr(x2), ldx, _lib.ptr(w), _lib.ptr(b), _lib.ptr(y), M, K, N, int(act),
                                     float(alpha), float(p_drop), seed, _seed_ptr(), int(rng_stream), _PRECISION,
                                     _lib.stream()), "mpg_linear_fwd")
@@ -198,11 +199,14 @@ class LinearFn(torch.autograd.Function):
         _lib.check(L.mpg_linear_bwd(_lib.ptr(dy), _lib.ptr(y), _lib.ptr(x2), ldx, _lib.ptr(w), _lib.ptr(dz),
                                     _lib.ptr(dx), K, 0, _lib.ptr(dw), _lib.ptr(db), M, K, N, act, alpha, p, seed,
                                     sptr, rstream, prec, _lib.stream()), "mpg_linear_bwd")
-        return (dx, None if dw_sink is not None else dw, None if db_sink is not None else db, None, None, None, None)
+        return (dx, None if dw_sink is not None else dw, None if db_sink is not None else db, None, None, None, None,
+                None)
 
 
-def linear(x, w, b, act: bool, alpha: float, p_drop: float, rng_stream: int = 16):
-    return LinearFn.apply(x, w, b, act, alpha, p_drop, rng_stream)
+def linear(x, w, b, act: bool, alpha: float, p_drop: float, rng_stream: int = 16, seed=None):
+    """``seed``: dropout seed (None draws a fresh one); layers of one LinearNet call share a seed and differ
+    in ``rng_stream``, which is what lets the fused node-network kernel reproduce their masks."""
+    return LinearFn.apply(x, w, b, act, alpha, p_drop, rng_stream, seed)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -276,6 +280,84 @@ class EdgeAggFn(torch.autograd.Function):
 
 def edge_aggregate(x, mask, w0, b0, w1, b1, w2, b2, ef_mode=0, nd=0, mean=False, alpha=0.2, p_drop=0.0):
     return EdgeAggFn.apply(x, mask, w0, b0, w1, b1, w2, b2, ef_mode, nd, mean, alpha, p_drop)
+
+
+# --------------------------------------------------------------------------------------------------
+# fused node network fn: cat(agg, x) -> H1 -> H2 -> out in one tcgen05 kernel per direction
+# --------------------------------------------------------------------------------------------------
+class NodeNetFn(torch.autograd.Function):
+    """out = LinearNet([H1, H2] -> NO, final_linear)(cat(agg, x)); mpgan/model.py:268-279 with :70-85."""
+
+    @staticmethod
+    def forward(ctx, agg, x, w0, b0, w1, b1, w2, b2, alpha, p_drop, seed):
+        L = _lib.lib()
+        a2, lda = _rows(agg)
+        x2, ldx = _rows(x)
+        Ka, Kb = a2.shape[-1], x2.shape[-1]
+        M = int(a2.numel() // Ka)
+        H1, H2, NO = w0.shape[0], w1.shape[0], w2.shape[0]
+        ws_ = [t.contiguous() for t in (w0, b0, w1, b1, w2, b2)]
+        ws_bytes = L.mpg_fn_workspace_bytes(Ka, Kb, H1, H2, NO)
+        ws = torch.empty(ws_bytes, device=agg.device, dtype=torch.uint8)
+        y0 = torch.empty(M, H1, device=agg.device, dtype=torch.float32)
+        y1 = torch.empty(M, H2, device=agg.device, dtype=torch.float32)
+        out = torch.empty(*a2.shape[:-1], NO, device=agg.device, dtype=torch.float32)
+        if seed is None:
+            seed = next_seed() if p_drop > 0 else 0
+        _lib.check(L.mpg_fn_fwd(_lib.ptr(a2), lda, Ka, _lib.ptr(x2), ldx, Kb, M, *[_lib.ptr(t) for t in ws_], H1, H2,
+                                NO, float(alpha), float(p_drop), seed, _seed_ptr(), ws.data_ptr(), ws_bytes,
+                                _lib.ptr(y0), _lib.ptr(y1), _lib.ptr(out), _lib.stream()), "mpg_fn_fwd")
+        ctx.save_for_backward(a2, x2, y0, y1, ws_[0], ws_[2], ws_[4])
+        ctx.params = (w0, b0, w1, b1, w2, b2)
+        ctx.cfg = (lda, ldx, Ka, Kb, M, H1, H2, NO, float(alpha), float(p_drop), seed, _seed_ptr())
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        L = _lib.lib()
+        a2, x2, y0, y1, w0, w1, w2 = ctx.saved_tensors
+        lda, ldx, Ka, Kb, M, H1, H2, NO, alpha, p, seed, sptr = ctx.cfg
+        dev = dout.device
+        dout = dout.contiguous()
+        ws_bytes = L.mpg_fn_workspace_bytes(Ka, Kb, H1, H2, NO)
+        ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+        dz0 = torch.empty(M, H1, device=dev, dtype=torch.float32)
+        dz1 = torch.empty(M, H2, device=dev, dtype=torch.float32)
+        dz2 = torch.empty(M, NO, device=dev, dtype=torch.float32) if p > 0 else None
+        da = torch.empty(*a2.shape, device=dev, dtype=torch.float32)
+        db = torch.empty(*x2.shape, device=dev, dtype=torch.float32)
+        need_w = any(ctx.needs_input_grad[2:8])
+        sinks = [_grad_sink(q) for q in ctx.params] if all(ctx.needs_input_grad[2:8]) else [None] * 6
+        direct = all(g is not None for g in sinks)
+        if direct:
+            grads = sinks
+        elif need_w:
+            flat = torch.zeros(sum(q.numel() for q in ctx.params), device=dev, dtype=torch.float32)
+            grads, off = [], 0
+            for q in ctx.params:
+                grads.append(flat[off:off + q.numel()].view(q.shape))
+                off += q.numel()
+        else:
+            grads = [None] * 6
+        _lib.check(L.mpg_fn_bwd(_lib.ptr(dout), _lib.ptr(y0), _lib.ptr(y1), _lib.ptr(a2), lda, Ka, _lib.ptr(x2), ldx,
+                                Kb, M, _lib.ptr(w0), _lib.ptr(w1), _lib.ptr(w2), H1, H2, NO, alpha, p, seed, sptr,
+                                ws.data_ptr(), ws_bytes, _lib.ptr(dz0), _lib.ptr(dz1), _lib.ptr(dz2), _lib.ptr(da),
+                                _lib.ptr(db), *[_lib.ptr(g) for g in grads], _lib.stream()), "mpg_fn_bwd")
+        if direct:
+            grads = [None] * 6
+        return (da if ctx.needs_input_grad[0] else None, db if ctx.needs_input_grad[1] else None, *grads,
+                None, None, None)
+
+
+def node_net_supported(Ka, Kb, H1, H2, NO, p_drop) -> bool:
+    """True iff the fused tcgen05 node network covers this shape in the current precision mode."""
+    return _PRECISION == 1 and bool(_lib.lib().mpg_fn_supported(int(Ka), int(Kb), int(H1), int(H2), int(NO),
+                                                                float(p_drop)))
+
+
+def node_net(agg, x, w0, b0, w1, b1, w2, b2, alpha: float, p_drop: float, seed=None):
+    return NodeNetFn.apply(agg, x, w0, b0, w1, b1, w2, b2, alpha, p_drop, seed)
 
 
 # --------------------------------------------------------------------------------------------------

@@ -333,3 +333,105 @@ def test_edge_tc_vs_fp32_kernel(B, N, p):
     names = ["agg", "dx", "dW0", "db0", "dW1", "db1", "dW2", "db2"]
     for name, r0, r1 in zip(names, res[0], res[1]):
         close(r1, r0, 2e-2 if name == "agg" else 6e-2, f"edge {name} B={B} N={N} p={p}")
+
+
+def _fn_reference(agg, x, ws, alpha):
+    """fp32 torch restatement of LinearNet(final_linear)(cat(agg, x)) (mpgan/model.py:70-85, 268-279), p = 0."""
+    w0, b0, w1, b1, w2, b2 = ws
+    h = torch.cat((agg, x), -1)
+    y0 = torch.nn.functional.leaky_relu(h @ w0.t() + b0, alpha)
+    y1 = torch.nn.functional.leaky_relu(y0 @ w1.t() + b1, alpha)
+    return y1 @ w2.t() + b2
+
+
+@pytest.mark.parametrize("M,Ka,Kb,H,NO,strided", [(300, 192, 32, 256, 32, False), (129, 192, 3, 256, 32, True),
+                                                  (1000, 192, 32, 256, 3, False), (64, 192, 32, 128, 32, False),
+                                                  (4500, 192, 32, 256, 32, False)])
+def test_node_net_tc_vs_fp32(M, Ka, Kb, H, NO, strided):
+    """Fused tcgen05 node network (TF32 operands, fp32 accumulate) against fp64 torch math: forward, input
+    gradients and all six parameter gradients.  Tolerance: TF32 (10-bit mantissa) through three chained GEMMs
+    -> 5e-3 max-abs relative forward.  Gradients: 5e-2 relative L2 -- a fraction ~1e-3 of the hidden units has a
+    pre-activation within TF32 rounding of zero and lands on the other leaky-relu slope (relative error 0.8 on
+    that unit => sqrt(1e-3) * 0.8 = 2.5e-2 in L2); the tight statement of the backward math is
+    test_node_net_tc_matches_layerwise (same activations, 5e-3)."""
+    from mpgan_b200 import ops
+    ops.set_precision(1)
+    g = torch.Generator().manual_seed(11)
+    K0 = Ka + Kb
+    agg = torch.randn(M, Ka, generator=g).cuda().requires_grad_(True)
+    if strided:   # D's first layer: x = input[:, :, :-1], a strided view
+        xfull = torch.randn(M, Kb + 1, generator=g).cuda().requires_grad_(True)
+        x = xfull[:, :Kb]
+    else:
+        xfull = torch.randn(M, Kb, generator=g).cuda().requires_grad_(True)
+        x = xfull
+    shapes = [(H, K0), (H,), (H, H), (H,), (NO, H), (NO,)]
+    ws = [(torch.randn(*s, generator=g) / (s[-1] ** 0.5 if len(s) == 2 else 4.0)).cuda().requires_grad_(True)
+          for s in shapes]
+    assert ops.node_net_supported(Ka, Kb, H, H, NO, 0.0)
+    out = ops.node_net(agg, x, *ws, 0.2, 0.0)
+    gout = torch.randn(M, NO, generator=g).cuda()
+    out.backward(gout)
+    got = [out.detach(), agg.grad, xfull.grad] + [w.grad for w in ws]
+    agg_r = agg.detach().double().requires_grad_(True)
+    xf_r = xfull.detach().double().requires_grad_(True)
+    ws_r = [w.detach().double().requires_grad_(True) for w in ws]
+    out_r = _fn_reference(agg_r, xf_r[:, :Kb], ws_r, 0.2)
+    out_r.backward(gout.double())
+    ref = [out_r.detach(), agg_r.grad, xf_r.grad] + [w.grad for w in ws_r]
+    names = ["out", "dagg", "dx", "dw0", "db0", "dw1", "db1", "dw2", "db2"]
+    close(got[0], ref[0], 5e-3, "out")
+    for n, a, b in zip(names[1:], got[1:], ref[1:]):
+        assert rel_l2(a, b) <= 5e-2, f"{n}: rel L2 {rel_l2(a, b):.3e}"
+
+
+@pytest.mark.parametrize("p,M,Kb,NO", [(0.5, 700, 32, 32), (0.0, 700, 32, 32), (0.5, 257, 32, 3), (0.0, 90, 8, 32)])
+def test_node_net_tc_matches_layerwise(p, M, Kb, NO):
+    """The fused kernel against the per-layer TF32 GEMM kernels (same operand rounding, so the same activation
+    signs): forward, input and parameter gradients within 5e-3; with p = 0.5 it draws the same masks (seed,
+    streams 16/17/18), in forward and in backward."""
+    from mpgan_b200 import _lib, ops
+    ops.set_precision(1)
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(12)
+    Ka, H, seed = 192, 256, 0x1234567
+    agg = torch.randn(M, Ka, generator=g).cuda().requires_grad_(True)
+    x = torch.randn(M, Kb, generator=g).cuda().requires_grad_(True)
+    shapes = [(H, Ka + Kb), (H,), (H, H), (H,), (NO, H), (NO,)]
+    ws = [(torch.randn(*s, generator=g) / (s[-1] ** 0.5 if len(s) == 2 else 4.0)).cuda().requires_grad_(True)
+          for s in shapes]
+    out = ops.node_net(agg, x, *ws, 0.2, p, seed)
+    gout = torch.randn(M, NO, generator=g).cuda()
+    out.backward(gout)
+    # layer-wise reference through the C ABI with the same seed / streams
+    h = torch.cat((agg, x), 1).detach().contiguous()
+    ys, cur = [], h
+    for i in range(3):
+        w, b = ws[2 * i].detach(), ws[2 * i + 1].detach()
+        y = torch.empty(M, w.shape[0], device="cuda")
+        _lib.check(L.mpg_linear_fwd(cur.data_ptr(), cur.shape[1], w.data_ptr(), b.data_ptr(), y.data_ptr(), M,
+                                    cur.shape[1], w.shape[0], int(i < 2), 0.2, p, seed, None, 16 + i, 1,
+                                    _lib.stream()), "linear_fwd")
+        ys.append(y)
+        cur = y
+    torch.cuda.synchronize()
+    assert torch.equal(out.detach() == 0, ys[2] == 0), "output dropout mask differs"
+    close(out, ys[2], 2e-3, "out")
+    dy, ins, grads = gout, [h, ys[0], ys[1]], {}
+    for i in (2, 1, 0):
+        w = ws[2 * i].detach()
+        dy = dy.contiguous()
+        dz = torch.empty_like(dy)
+        dx = torch.empty(M, w.shape[1], device="cuda")
+        dw, db = torch.zeros_like(w), torch.zeros(w.shape[0], device="cuda")
+        _lib.check(L.mpg_linear_bwd(dy.data_ptr(), ys[i].data_ptr(), ins[i].data_ptr(), ins[i].shape[1], w.data_ptr(),
+                                    dz.data_ptr(), dx.data_ptr(), w.shape[1], 0, dw.data_ptr(), db.data_ptr(), M,
+                                    w.shape[1], w.shape[0], int(i < 2), 0.2, p, seed, None, 16 + i, 1,
+                                    _lib.stream()), "linear_bwd")
+        grads[i] = (dw, db)
+        dy = dx
+    torch.cuda.synchronize()
+    assert rel_l2(agg.grad, dy[:, :Ka]) <= 5e-3 and rel_l2(x.grad, dy[:, Ka:]) <= 5e-3
+    for i in range(3):
+        assert rel_l2(ws[2 * i].grad, grads[i][0]) <= 5e-3, i
+        assert rel_l2(ws[2 * i + 1].grad, grads[i][1]) <= 5e-3, i
