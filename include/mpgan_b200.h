@@ -97,6 +97,19 @@ int mpg_fn_bwd(const float* dout, const float* y0, const float* y1, const float*
                size_t workspace_bytes, float* dz0, float* dz1, float* dz2, float* da, float* db, float* dw0,
                float* db0, float* dw1, float* db1, float* dw2, float* db2, void* stream);
 
+/* The forward writes everything that depends only on (x, weights, mask) -- the factorised first layer P/Q, the
+ * swizzled weight images, the work list -- into the first mpg_edge_fwd_workspace_bytes() bytes of its workspace
+ * (a forward-only caller may pass just that much).  mpg_edge_bwd_saved() is mpg_edge_bwd() reading those from the
+ * forward's still-intact workspace instead of recomputing them (4 fewer kernels per call); `workspace` is the
+ * backward's own scratch of mpg_edge_workspace_bytes(). */
+size_t mpg_edge_fwd_workspace_bytes(int B, int N, int F, int H0, int H1, int H2);
+int mpg_edge_bwd_saved(const void* fwd_workspace, size_t fwd_workspace_bytes, const float* x, int ldx,
+                       const float* mask, const float* w0, const float* b0, const float* w1, const float* b1,
+                       const float* w2, const float* b2, int B, int N, int F, int H0, int H1, int H2, int ef_mode,
+                       int nd, int mean, float alpha, float p_drop, uint64_t seed, const uint64_t* seed_dev,
+                       int precision, void* workspace, size_t workspace_bytes, const float* dagg, float* dx, int lddx,
+                       float* dw0, float* db0, float* dw1, float* db1, float* dw2, float* db2, void* stream);
+
 /* ---- masks and tails ------------------------------------------------------------------------------ */
 /* mask[b,i] = rank(x[b,i,0]) <= int(labels[b]*N) - 1   (bit-exact; mpgan/model.py:692-699) */
 int mpg_rank_mask(const float* x, int ldx, const float* labels, int ldl, int B, int N, float* mask, void* stream);

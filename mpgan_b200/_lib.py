@@ -35,6 +35,9 @@ _SIGS = {
                                _u64, _f, _i, _f, _sz, _f, _f]),
     "mpg_edge_bwd": (C.c_int, [_f, _i, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _i, _fl, _fl,
                                _u64, _f, _i, _f, _sz, _f, _f, _i, _f, _f, _f, _f, _f, _f, _f]),
+    "mpg_edge_fwd_workspace_bytes": (C.c_size_t, [_i] * 6),
+    "mpg_edge_bwd_saved": (C.c_int, [_f, _sz, _f, _i, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _i,
+                                     _fl, _fl, _u64, _f, _i, _f, _sz, _f, _f, _i, _f, _f, _f, _f, _f, _f, _f]),
     "mpg_rank_mask": (C.c_int, [_f, _i, _f, _i, _i, _i, _f, _f]),
     "mpg_split_mask": (C.c_int, [_f, _i, _i, _f, _f]),
     "mpg_gen_tail_fwd": (C.c_int, [_f, _f, _f, _i, _i, _i, _f]),

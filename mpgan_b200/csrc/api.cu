@@ -51,10 +51,13 @@ SideStream* side_stream() {
   return &ss;
 }
 
+// Workspace of one fused edge call.  The first `persist` bytes (P, Q, the transposed / swizzled weight copies,
+// the work list) are produced by the forward and depend only on (x, weights, mask): the backward of the same
+// call can read them from the forward's buffer instead of recomputing them (mpg_edge_bwd_saved).
 struct EdgeWs {
   float *P, *Q, *W1t, *W2t, *dP, *dQ, *dxef, *wg_scratch;
-  void* tc;
-  size_t total;
+  void *tc, *tc_scratch;
+  size_t persist, total;
 };
 
 size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -73,13 +76,16 @@ EdgeWs carve_edge_ws(void* base, int B, int N, int F, int H0, int H1, int H2) {
   w.Q = take(BN * H0);
   w.W1t = take((size_t)H0 * H1);
   w.W2t = take((size_t)H1 * H2);
-  w.dP = take(BN * H0);
+  w.tc = p + off;
+  off += align_up(edge_tc_persist_bytes(B, N, H0, H1, H2));
+  w.persist = off;
+  w.dP = take(BN * H0);     // dP and dQ are adjacent: one memset clears both
   w.dQ = take(BN * H0);
   w.dxef = take(BN * F);
   // sink for the weight gradients of a dx-only backward on the generic path (never read)
   w.wg_scratch = take((size_t)H0 * (2 * F + 64) + H0 + (size_t)H1 * H0 + H1 + (size_t)H2 * H1 + H2);
-  w.tc = p + off;
-  off += align_up(edge_tc_workspace_bytes(B, N, H0, H1, H2));
+  w.tc_scratch = p + off;
+  off += align_up(edge_tc_scratch_bytes(B, N, H0, H1, H2));
   w.total = off;
   return w;
 }
@@ -88,13 +94,20 @@ int edge_common(EdgeArgs& a, EdgeWs& w, const float* x, int ldx, const float* ma
                 const float* b0, const float* w1, const float* b1, const float* w2, const float* b2, int B, int N,
                 int F, int H0, int H1, int H2, int ef_mode, int nd, int mean, float alpha, float p_drop,
                 uint64_t seed, const uint64_t* seed_dev, int precision, void* workspace, size_t workspace_bytes, bool* use_tc,
-                cudaStream_t s) {
+                cudaStream_t s, bool fwd_only = false, const void* saved = nullptr, size_t saved_bytes = 0) {
   MPG_CHECK(B > 0 && N > 0 && F > 0, "bad edge problem size B=%d N=%d F=%d", B, N, F);
   MPG_CHECK(ef_mode >= 0 && ef_mode <= 3 && (ef_mode == 0 || (nd > 0 && nd <= F)), "bad ef_mode/nd");
   MPG_CHECK(p_drop >= 0.f && p_drop < 1.f, "dropout p must be in [0,1)");
   w = carve_edge_ws(workspace, B, N, F, H0, H1, H2);
-  MPG_CHECK(workspace != nullptr && workspace_bytes >= w.total, "edge workspace too small: need %zu bytes, got %zu",
-            w.total, workspace_bytes);
+  const size_t need = fwd_only ? w.persist : w.total;
+  MPG_CHECK(workspace != nullptr && workspace_bytes >= need, "edge workspace too small: need %zu bytes, got %zu",
+            need, workspace_bytes);
+  if (saved != nullptr) {   // P, Q, weight copies and work list come from the forward's workspace
+    MPG_CHECK(saved_bytes >= w.persist, "saved forward workspace too small: need %zu bytes, got %zu", w.persist,
+              saved_bytes);
+    const EdgeWs f = carve_edge_ws(const_cast<void*>(saved), B, N, F, H0, H1, H2);
+    w.P = f.P; w.Q = f.Q; w.W1t = f.W1t; w.W2t = f.W2t; w.tc = f.tc;
+  }
   memset(&a, 0, sizeof(a));
   a.B = B; a.N = N; a.F = F; a.H0 = H0; a.H1 = H1; a.H2 = H2;
   a.n_ef = ((ef_mode & 2) ? nd : 0) + (ef_mode & 1);
@@ -111,6 +124,7 @@ int edge_common(EdgeArgs& a, EdgeWs& w, const float* x, int ldx, const float* ma
   a.drop = make_drop(p_drop, seed, seed_dev);
   const bool precise = precision == 0;
   *use_tc = !precise && edge_tc_supported(a);
+  if (saved != nullptr) return 0;
   // factorised first layer: W0 [x_i ; x_j ; ef] = Wa x_i + Wb x_j + Wef ef   (node-level GEMMs)
   if (pq_supported(F, H0)) {
     if (launch_pq_fwd(x, ldx, w0, a.ldwef, b0, w.P, w.Q, B * N, F, H0, s)) return 1;
@@ -255,6 +269,7 @@ int mpg_fn_bwd(const float* dout, const float* y0, const float* y1, const float*
   t.alpha = alpha;
   t.drop = make_drop(p_drop, seed, seed_dev);
   t.stream[0] = 16; t.stream[1] = 17; t.stream[2] = 18;
+  if (dw0 != nullptr) { t.dbias[0] = db0; t.dbias[1] = db1; t.dbias[2] = db2; }   // column sums in the epilogues
   if (launch_fn_tc(t, true, w0, w1, w2, H1, H2, NO, workspace, s)) return 1;
   if (dw0 == nullptr) return 0;
   // weight / bias gradients: dW_l += dz_l^T (input of layer l), db_l += colsum(dz_l) on the side stream (the
@@ -278,9 +293,6 @@ int mpg_fn_bwd(const float* dout, const float* y0, const float* y1, const float*
     d.dz[2] = g2; d.na[2] = NO; d.ina[2] = y1; d.lda[2] = H2; d.ka[2] = H2; d.dw[2] = dw2; d.lddw[2] = H2;
     if (launch_fn_dw(d, sw)) return 1;
   }
-  if (launch_colsum(g2, NO, M, NO, db2, sw)) return 1;
-  if (launch_colsum(dz1, H2, M, H2, db1, sw)) return 1;
-  if (launch_colsum(dz0, H1, M, H1, db0, sw)) return 1;
   if (side != nullptr) {
     MPG_CUDA(cudaEventRecord(side->join, side->stream));
     MPG_CUDA(cudaStreamWaitEvent(s, side->join, 0));
@@ -290,6 +302,9 @@ int mpg_fn_bwd(const float* dout, const float* y0, const float* y1, const float*
 
 size_t mpg_edge_workspace_bytes(int B, int N, int F, int H0, int H1, int H2) {
   return carve_edge_ws(nullptr, B, N, F, H0, H1, H2).total;
+}
+size_t mpg_edge_fwd_workspace_bytes(int B, int N, int F, int H0, int H1, int H2) {
+  return carve_edge_ws(nullptr, B, N, F, H0, H1, H2).persist;
 }
 
 int mpg_edge_fwd(const float* x, int ldx, const float* mask, const float* w0, const float* b0, const float* w1,
@@ -301,24 +316,25 @@ int mpg_edge_fwd(const float* x, int ldx, const float* mask, const float* w0, co
   EdgeWs w;
   bool use_tc = false;
   if (edge_common(a, w, x, ldx, mask, w0, b0, w1, b1, w2, b2, B, N, F, H0, H1, H2, ef_mode, nd, mean, alpha,
-                  p_drop, seed, seed_dev, precision, workspace, workspace_bytes, &use_tc, s))
+                  p_drop, seed, seed_dev, precision, workspace, workspace_bytes, &use_tc, s, true))
     return 1;
   a.agg = agg;
   if (use_tc) return launch_edge_tc_fwd(a, w.tc, s);
   return launch_edge_generic(a, false, s);
 }
 
-int mpg_edge_bwd(const float* x, int ldx, const float* mask, const float* w0, const float* b0, const float* w1,
-                 const float* b1, const float* w2, const float* b2, int B, int N, int F, int H0, int H1, int H2,
-                 int ef_mode, int nd, int mean, float alpha, float p_drop, uint64_t seed, const uint64_t* seed_dev,
-                 int precision, void* workspace, size_t workspace_bytes, const float* dagg, float* dx, int lddx, float* dw0,
-                 float* db0, float* dw1, float* db1, float* dw2, float* db2, void* stream) {
+static int edge_bwd_impl(const void* saved, size_t saved_bytes, const float* x, int ldx, const float* mask,
+                         const float* w0, const float* b0, const float* w1, const float* b1, const float* w2,
+                         const float* b2, int B, int N, int F, int H0, int H1, int H2, int ef_mode, int nd, int mean,
+                         float alpha, float p_drop, uint64_t seed, const uint64_t* seed_dev, int precision,
+                         void* workspace, size_t workspace_bytes, const float* dagg, float* dx, int lddx, float* dw0,
+                         float* db0, float* dw1, float* db1, float* dw2, float* db2, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   EdgeArgs a;
   EdgeWs w;
   bool use_tc = false;
   if (edge_common(a, w, x, ldx, mask, w0, b0, w1, b1, w2, b2, B, N, F, H0, H1, H2, ef_mode, nd, mean, alpha,
-                  p_drop, seed, seed_dev, precision, workspace, workspace_bytes, &use_tc, s))
+                  p_drop, seed, seed_dev, precision, workspace, workspace_bytes, &use_tc, s, false, saved, saved_bytes))
     return 1;
   MPG_CHECK(dagg && dx, "edge_bwd: null gradient pointer");
   // all six weight-gradient pointers null = input gradient only (train_G back-propagates through a frozen D)
@@ -339,12 +355,15 @@ int mpg_edge_bwd(const float* x, int ldx, const float* mask, const float* w0, co
   a.dW1 = dw1; a.db1 = db1; a.dW2 = dw2; a.db2 = db2;
   a.dP = w.dP; a.dQ = w.dQ; a.dx_ef = w.dxef;
   a.dWef = dw0 ? dw0 + 2 * F : nullptr;
-  MPG_CUDA(cudaMemsetAsync(w.dQ, 0, BN * H0 * sizeof(float), s));
-  if (a.n_ef) MPG_CUDA(cudaMemsetAsync(w.dxef, 0, BN * F * sizeof(float), s));
   const bool tc_bwd = tc_path;
+  if (tc_bwd) {   // dP | dQ adjacent: one clear
+    MPG_CUDA(cudaMemsetAsync(w.dP, 0, (size_t)((char*)w.dQ - (char*)w.dP) + BN * H0 * sizeof(float), s));
+  } else {
+    MPG_CUDA(cudaMemsetAsync(w.dQ, 0, BN * H0 * sizeof(float), s));
+  }
+  if (a.n_ef) MPG_CUDA(cudaMemsetAsync(w.dxef, 0, BN * F * sizeof(float), s));
   if (tc_bwd) {
-    MPG_CUDA(cudaMemsetAsync(w.dP, 0, BN * H0 * sizeof(float), s));
-    if (launch_edge_tc_bwd(a, w.tc, s)) return 1;
+    if (launch_edge_tc_bwd(a, w.tc, w.tc_scratch, saved != nullptr, s)) return 1;
   } else {
     if (use_tc) {  // forward ran on tensor cores, backward kernel not built: generic needs W^T copies
       if (launch_transpose(w1, H1, H0, w.W1t, s)) return 1;
@@ -373,6 +392,28 @@ int mpg_edge_bwd(const float* x, int ldx, const float* mask, const float* w0, co
     MPG_LAUNCH_CHECK();
   }
   return 0;
+}
+
+int mpg_edge_bwd(const float* x, int ldx, const float* mask, const float* w0, const float* b0, const float* w1,
+                 const float* b1, const float* w2, const float* b2, int B, int N, int F, int H0, int H1, int H2,
+                 int ef_mode, int nd, int mean, float alpha, float p_drop, uint64_t seed, const uint64_t* seed_dev,
+                 int precision, void* workspace, size_t workspace_bytes, const float* dagg, float* dx, int lddx, float* dw0,
+                 float* db0, float* dw1, float* db1, float* dw2, float* db2, void* stream) {
+  return edge_bwd_impl(nullptr, 0, x, ldx, mask, w0, b0, w1, b1, w2, b2, B, N, F, H0, H1, H2, ef_mode, nd, mean, alpha,
+                       p_drop, seed, seed_dev, precision, workspace, workspace_bytes, dagg, dx, lddx, dw0, db0, dw1, db1,
+                       dw2, db2, stream);
+}
+
+int mpg_edge_bwd_saved(const void* fwd_workspace, size_t fwd_workspace_bytes, const float* x, int ldx,
+                       const float* mask, const float* w0, const float* b0, const float* w1, const float* b1,
+                       const float* w2, const float* b2, int B, int N, int F, int H0, int H1, int H2, int ef_mode,
+                       int nd, int mean, float alpha, float p_drop, uint64_t seed, const uint64_t* seed_dev,
+                       int precision, void* workspace, size_t workspace_bytes, const float* dagg, float* dx, int lddx,
+                       float* dw0, float* db0, float* dw1, float* db1, float* dw2, float* db2, void* stream) {
+  MPG_CHECK(fwd_workspace != nullptr, "edge_bwd_saved: null forward workspace");
+  return edge_bwd_impl(fwd_workspace, fwd_workspace_bytes, x, ldx, mask, w0, b0, w1, b1, w2, b2, B, N, F, H0, H1, H2,
+                       ef_mode, nd, mean, alpha, p_drop, seed, seed_dev, precision, workspace, workspace_bytes, dagg, dx,
+                       lddx, dw0, db0, dw1, db1, dw2, db2, stream);
 }
 
 int mpg_rank_mask(const float* x, int ldx, const float* labels, int ldl, int B, int N, float* mask, void* stream) {

@@ -49,8 +49,12 @@ int launch_pq_bwd(const float* dP, const float* dQ, const float* x, int ldx, con
 int edge_tc_features();
 void edge_tc_arm_probe(int id, cudaEvent_t e0, cudaEvent_t e1);
 bool edge_tc_supported(const EdgeArgs& a);
-size_t edge_tc_workspace_bytes(int B, int N, int H0, int H1, int H2);
-int launch_edge_tc_fwd(const EdgeArgs& a, void* ws, cudaStream_t stream);
-int launch_edge_tc_bwd(const EdgeArgs& a, void* ws, cudaStream_t stream);
+// workspace in two parts: `persist` (weight images + work list: written by the forward, reusable by the backward
+// of the same call -- reuse = true skips the kernels that build them) and `scratch` (backward only: sign bits,
+// weight-gradient slabs)
+size_t edge_tc_persist_bytes(int B, int N, int H0, int H1, int H2);
+size_t edge_tc_scratch_bytes(int B, int N, int H0, int H1, int H2);
+int launch_edge_tc_fwd(const EdgeArgs& a, void* persist, cudaStream_t stream);
+int launch_edge_tc_bwd(const EdgeArgs& a, void* persist, void* scratch, bool reuse, cudaStream_t stream);
 
 }  // namespace mpg

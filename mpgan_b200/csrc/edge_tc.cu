@@ -59,15 +59,20 @@ static size_t tc_steps_bytes(int B, int N) {   // work list: int2 per (tile, sen
   return ((size_t)tiles * N * sizeof(int2) + 256 + 255) & ~(size_t)255;
 }
 
-size_t edge_tc_workspace_bytes(int B, int N, int H0, int H1, int H2) {
+size_t edge_tc_persist_bytes(int B, int N, int H0, int H1, int H2) {
   if (H0 != K0 || H1 != N1 || H2 != N2) return 0;
-  return W1_BYTES + W2_BYTES + 1024 + tc_steps_bytes(B, N) + tc_sbits_bytes(B, N) + 256 + tc_slab_bytes();
+  return W1_BYTES + W2_BYTES + 1024 + tc_steps_bytes(B, N);
+}
+size_t edge_tc_scratch_bytes(int B, int N, int H0, int H1, int H2) {
+  if (H0 != K0 || H1 != N1 || H2 != N2) return 0;
+  return tc_sbits_bytes(B, N) + 512 + tc_slab_bytes();
 }
 
 // the activation / gradient tiles hold X / (sd * sl) (dropout and leaky-relu scales), the weight images sd * sl * W
-static int tc_prepare(const EdgeArgs& a, void* ws, TcArgs& t, int* grid, cudaStream_t stream) {
+static int tc_prepare(const EdgeArgs& a, void* persist, void* scratch, bool reuse, TcArgs& t, int* grid,
+                      cudaStream_t stream) {
   MPG_CHECK(edge_tc_supported(a), "edge_tc: unsupported configuration");
-  uint8_t* img = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  uint8_t* img = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(persist) + 255) & ~(uintptr_t)255);
   t.a = a;
   t.w1img = img;
   t.w2img = img + W1_BYTES;
@@ -75,18 +80,24 @@ static int tc_prepare(const EdgeArgs& a, void* ws, TcArgs& t, int* grid, cudaStr
   int* total = reinterpret_cast<int*>(p);
   t.total_steps = total;
   t.steps = reinterpret_cast<int2*>(p + 256);
-  p += tc_steps_bytes(a.B, a.N);
-  t.sbits = reinterpret_cast<uint2*>(p);
-  t.wslab = reinterpret_cast<float*>(p + ((tc_sbits_bytes(a.B, a.N) + 255) & ~(size_t)255));
-  const float s = (a.drop.p > 0.f ? 2.f : 1.f) * 0.5f * (1.f + a.alpha);
-  weight_image_kernel<<<cdiv(N1 * 128, 256), 256, 0, stream>>>(a.W1, a.b1, N1, K0, 128, s, img, nullptr);
-  MPG_LAUNCH_CHECK();
-  weight_image_kernel<<<cdiv(N2 * 192, 256), 256, 0, stream>>>(a.W2, a.b2, N2, N1, 192, s, img + W1_BYTES, reinterpret_cast<int*>(img + W1_BYTES + W2_BYTES));
-  MPG_LAUNCH_CHECK();
+  t.sbits = nullptr;
+  t.wslab = nullptr;
+  if (scratch != nullptr) {
+    uint8_t* q = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(scratch) + 255) & ~(uintptr_t)255);
+    t.sbits = reinterpret_cast<uint2*>(q);
+    t.wslab = reinterpret_cast<float*>(q + ((tc_sbits_bytes(a.B, a.N) + 255) & ~(size_t)255));
+  }
   const long long BN = (long long)a.B * a.N;
   t.num_tiles = (int)((BN + TILE - 1) / TILE);
-  step_list_kernel<<<cdiv(t.num_tiles, 8), 256, 0, stream>>>(a.mask, a.B, a.N, t.num_tiles, const_cast<int2*>(t.steps), total);
-  MPG_LAUNCH_CHECK();
+  if (!reuse) {   // images and work list of this (weights, mask): the backward of the same call finds them here
+    const float s = (a.drop.p > 0.f ? 2.f : 1.f) * 0.5f * (1.f + a.alpha);
+    weight_image_kernel<<<cdiv(N1 * 128, 256), 256, 0, stream>>>(a.W1, a.b1, N1, K0, 128, s, img, nullptr);
+    MPG_LAUNCH_CHECK();
+    weight_image_kernel<<<cdiv(N2 * 192, 256), 256, 0, stream>>>(a.W2, a.b2, N2, N1, 192, s, img + W1_BYTES, reinterpret_cast<int*>(img + W1_BYTES + W2_BYTES));
+    MPG_LAUNCH_CHECK();
+    step_list_kernel<<<cdiv(t.num_tiles, 8), 256, 0, stream>>>(a.mask, a.B, a.N, t.num_tiles, const_cast<int2*>(t.steps), total);
+    MPG_LAUNCH_CHECK();
+  }
   // the number of live steps is only known on the device: one CTA per SM, CTAs without steps exit at once
   const long long max_steps = (long long)t.num_tiles * a.N;
   const int sms = tc_num_sms();
@@ -94,10 +105,10 @@ static int tc_prepare(const EdgeArgs& a, void* ws, TcArgs& t, int* grid, cudaStr
   return 0;
 }
 
-int launch_edge_tc_fwd(const EdgeArgs& a, void* ws, cudaStream_t stream) {
+int launch_edge_tc_fwd(const EdgeArgs& a, void* persist, cudaStream_t stream) {
   TcArgs t;
   int grid = 1;
-  if (tc_prepare(a, ws, t, &grid, stream)) return 1;
+  if (tc_prepare(a, persist, nullptr, false, t, &grid, stream)) return 1;
   MPG_CUDA(cudaMemsetAsync(a.agg, 0, (size_t)a.B * a.N * N2 * sizeof(float), stream));
   if (a.drop.p > 0.f) {
     MPG_CUDA(cudaFuncSetAttribute(edge_tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
@@ -124,10 +135,10 @@ static int launch_bwd_one(const TcArgs& t, int grid, uint32_t smem, cudaStream_t
 }
 
 // dP and dQ must be zeroed by the caller (both are accumulated with atomics here)
-int launch_edge_tc_bwd(const EdgeArgs& a, void* ws, cudaStream_t stream) {
+int launch_edge_tc_bwd(const EdgeArgs& a, void* persist, void* scratch, bool reuse, cudaStream_t stream) {
   TcArgs t;
   int grid = 1;
-  if (tc_prepare(a, ws, t, &grid, stream)) return 1;
+  if (tc_prepare(a, persist, scratch, reuse, t, &grid, stream)) return 1;
   const bool wgrad = a.dW1 != nullptr;   // null: input gradient only -> CHAIN alone (its dW1 slab is simply not reduced)
   if (a.drop.p > 0.f) {
     if (launch_bwd_one<BWD_CHAIN, true>(t, grid, C_SMEM, stream)) return 1;

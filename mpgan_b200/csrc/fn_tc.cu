@@ -33,7 +33,13 @@ constexpr int FN_STAGES = 3;
 constexpr uint32_t FN_OFF_A = 0;
 constexpr uint32_t FN_OFF_W = 8 * FN_ABLK;                          // 131072
 constexpr uint32_t FN_OFF_BAR = FN_OFF_W + FN_STAGES * FN_STAGE;    // 229376
-constexpr uint32_t FN_SMEM = FN_OFF_BAR + 256 + 1024;               // 230656 <= 232448
+constexpr uint32_t FN_OFF_CSUM = FN_OFF_BAR + 256;                  // 256 floats: column sums of dz2 (backward)
+constexpr uint32_t FN_SMEM = FN_OFF_CSUM + 1024 + 1024;             // 231680 <= 232448
+// Weight ring: stages 0..2 live in their own 96 KB and carry the blocks of GEMM 0 and then GEMM 2; stages 3..6
+// are the A tile's 128 KB, free once GEMM 0 has completed, and carry GEMM 1 -- so GEMM 1's first four blocks
+// and GEMM 2's first three are in flight while the epilogues run.
+constexpr int FN_RING1 = 4;
+constexpr int FN_NSTG = FN_STAGES + FN_RING1;
 
 __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t r;
@@ -127,6 +133,17 @@ __global__ void fn_image_kernel(FnImageJobs jobs) {
 // ---------------------------------------------------------------------------------------------------
 // The chain kernel
 // ---------------------------------------------------------------------------------------------------
+// optional event trace (profiles/trace_fn.py): globaltimer stamps of CTA 0 -- slots 0..15 epilogue thread 0,
+// 16..31 MMA issuer, 32..47 loader
+__device__ long long* g_fn_trace = nullptr;
+__device__ __forceinline__ void fn_stamp(int slot) {
+  if (g_fn_trace != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0) {
+    long long tnow;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tnow));
+    g_fn_trace[slot] = tnow;
+  }
+}
+
 template <bool BWD>
 __global__ void __launch_bounds__(FN_THREADS, 1) fn_tc_kernel(FnTcArgs t) {
   extern __shared__ uint8_t smem_raw[];
@@ -136,60 +153,74 @@ __global__ void __launch_bounds__(FN_THREADS, 1) fn_tc_kernel(FnTcArgs t) {
   const uint32_t bar_a = bar0;                   // A tile built (FN_EPI arrivals)
   const uint32_t bar_e = bar0 + 8;               // [2] epilogue l done: TMEM A operand of layer l+1 ready
   const uint32_t bar_d = bar0 + 24;              // [3] accumulator of layer l complete
-  const uint32_t bar_full = bar0 + 48;           // [FN_STAGES]
-  const uint32_t bar_empty = bar0 + 48 + 8 * FN_STAGES;
+  const uint32_t bar_full = bar0 + 48;           // [FN_NSTG]
+  const uint32_t bar_empty = bar0 + 48 + 8 * FN_NSTG;
+  float* csum = reinterpret_cast<float*>(sm + FN_OFF_CSUM);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + FN_OFF_BAR + 192);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row0 = blockIdx.x * 128;
+  if (warp == 1) fn_stamp(15);
 
   if (threadIdx.x == 0) {
     mbar_init(bar_a, FN_EPI);
     mbar_init(bar_e, FN_EPI);
     mbar_init(bar_e + 8, FN_EPI);
     for (int l = 0; l < 3; ++l) mbar_init(bar_d + 8 * l, 1);
-    for (int s = 0; s < FN_STAGES; ++s) {
+    for (int s = 0; s < FN_NSTG; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (BWD && threadIdx.x < 256) csum[threadIdx.x] = 0.f;
   if (warp == 16) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  // ring position -> (stage, use count): ring 0 = stages [0, FN_STAGES), ring 1 = stages [FN_STAGES, FN_NSTG)
+  auto stage_of = [](int ring, uint32_t g) { return ring ? FN_STAGES + g % FN_RING1 : g % FN_STAGES; };
+  auto use_of = [](int ring, uint32_t g) { return ring ? g / FN_RING1 : g / FN_STAGES; };
+  auto stage_addr = [&](uint32_t st) { return st < FN_STAGES ? sW + st * FN_STAGE : sA + (st - FN_STAGES) * FN_STAGE; };
 
   if (warp == 17) {
-    // =============================== loader: weight-image K blocks through the ring ===================
-    uint32_t g = 0;
-    for (int l = 0; l < 3; ++l) {
+    // =============================== loader: weight-image K blocks through the rings ==================
+    uint32_t gr[2] = {0, 0};
+    auto load = [&](int l, int blk) {
+      const int ring = l == 1;
       const uint32_t bytes = (uint32_t)t.n[l] * 128u;
-      const int kb = (t.kmma[l] + 3) >> 2;
-      for (int blk = 0; blk < kb; ++blk, ++g) {
-        const uint32_t st = g % FN_STAGES;
-        if (g >= FN_STAGES) mbar_wait(bar_empty + 8 * st, (g / FN_STAGES - 1) & 1);
-        mbar_expect_tx_elect(bar_full + 8 * st, bytes);
-        bulk_g2s_elect(sW + st * FN_STAGE, t.img[l] + (size_t)blk * bytes, bytes, bar_full + 8 * st);
-      }
-    }
+      const uint32_t g = gr[ring]++, st = stage_of(ring, g), use = use_of(ring, g);
+      if (use >= 1) mbar_wait(bar_empty + 8 * st, (use - 1) & 1);
+      mbar_expect_tx_elect(bar_full + 8 * st, bytes);
+      bulk_g2s_elect(stage_addr(st), t.img[l] + (size_t)blk * bytes, bytes, bar_full + 8 * st);
+    };
+    const int kb0 = (t.kmma[0] + 3) >> 2, kb1 = (t.kmma[1] + 3) >> 2, kb2 = (t.kmma[2] + 3) >> 2;
+    const int pre2 = min(kb2, FN_STAGES);
+    for (int blk = 0; blk < kb0; ++blk) load(0, blk);
+    for (int blk = 0; blk < pre2; ++blk) load(2, blk);   // behind GEMM 0's last blocks
+    mbar_wait(bar_d, 0);                                  // GEMM 0 complete: the A tile's memory is ring 1
+    for (int blk = 0; blk < kb1; ++blk) load(1, blk);
+    for (int blk = pre2; blk < kb2; ++blk) load(2, blk);
   } else if (warp == 16) {
     // =============================== MMA issuer ========================================================
-    uint32_t g = 0;
+    uint32_t gr[2] = {0, 0};
     for (int l = 0; l < 3; ++l) {
+      const int ring = l == 1;
       mbar_wait(l == 0 ? bar_a : bar_e + 8 * (l - 1), 0);
       tc_fence_after();
+      fn_stamp(16 + 2 * l);
       const uint32_t idesc = idesc_tf32(t.n[l]);
       const uint32_t dcol = tmem + (l == 1 ? 256u : 0u);
       const uint32_t acol = tmem + (l == 1 ? 0u : 256u);   // TMEM A operand (layers 1, 2)
       const int kb = (t.kmma[l] + 3) >> 2;
-      for (int blk = 0; blk < kb; ++blk, ++g) {
-        const uint32_t st = g % FN_STAGES;
-        mbar_wait(bar_full + 8 * st, (g / FN_STAGES) & 1);
+      for (int blk = 0; blk < kb; ++blk) {
+        const uint32_t g = gr[ring]++, st = stage_of(ring, g);
+        mbar_wait(bar_full + 8 * st, use_of(ring, g) & 1);
         tc_fence_after();
         const int nm = min(4, t.kmma[l] - 4 * blk);
         if (elect_one()) {
-          const uint64_t bd = umma_desc(sW + st * FN_STAGE);
+          const uint64_t bd = umma_desc(stage_addr(st));
           if (l == 0) {
             const uint64_t ad = umma_desc(sA + (uint32_t)blk * FN_ABLK);
             for (int j = 0; j < nm; ++j) umma_tf32_ss(dcol, ad + (uint64_t)(j * 2), bd + (uint64_t)(j * 2), idesc, (uint32_t)(blk | j));
@@ -203,6 +234,7 @@ __global__ void __launch_bounds__(FN_THREADS, 1) fn_tc_kernel(FnTcArgs t) {
       }
       if (elect_one()) umma_commit(bar_d + 8 * l);
       __syncwarp();
+      fn_stamp(17 + 2 * l);
     }
   } else {
     // =============================== epilogue warps ====================================================
@@ -214,16 +246,17 @@ __global__ void __launch_bounds__(FN_THREADS, 1) fn_tc_kernel(FnTcArgs t) {
     DropCfg dc = t.drop;
     resolve_seed(dc);
     const bool drop = dc.p > 0.f;                  // p == 0.5 only (host-checked)
+    if (warp == 0) fn_stamp(0);
 
     // ---- A tile of layer 0: [a | b] (forward) or dout * drop' (backward), TF32-rounded, swizzled ------
     {
       const int kb = (t.kmma[0] + 3) >> 2;
       const int nch = kb * 8;                      // 16-byte chunks per row
       const int K = t.Ka + t.Kb;
-      for (int idx = threadIdx.x; idx < 128 * nch; idx += FN_EPI) {
+      const int total = 128 * nch;
+      auto load_item = [&](int idx, float* v) {
         const int r = idx / nch, c = idx % nch;
         const int gr = row0 + r, k0 = c * 4;
-        float v[4] = {0.f, 0.f, 0.f, 0.f};
         if (gr < t.M && k0 < K) {
           if (k0 + 3 < t.Ka && t.vec_a) {
             const float4 x = *reinterpret_cast<const float4*>(t.a + (size_t)gr * t.lda + k0);
@@ -239,7 +272,13 @@ __global__ void __launch_bounds__(FN_THREADS, 1) fn_tc_kernel(FnTcArgs t) {
               else if (k < K) v[e] = t.b[(size_t)gr * t.ldb + (k - t.Ka)];
             }
           }
-          if (BWD && drop) {   // dz2 = dout * keep * 2 (dropout after the final linear layer, stream 2)
+        }
+      };
+      auto store_item = [&](int idx, float* v) {
+        const int r = idx / nch, c = idx % nch;
+        const int gr = row0 + r, k0 = c * 4;
+        if (BWD && gr < t.M && k0 < K) {
+          if (drop) {   // dz2 = dout * keep * 2 (dropout after the final linear layer, stream 2)
             const uint32_t kw = drop_word32(dc, t.stream[2], (uint64_t)gr, (uint32_t)(k0 >> 5));
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -247,13 +286,39 @@ __global__ void __launch_bounds__(FN_THREADS, 1) fn_tc_kernel(FnTcArgs t) {
               if (k0 + e < K) t.dz2[(size_t)gr * K + k0 + e] = v[e];
             }
           }
+          if (t.dbias[2] != nullptr) {   // db2 = column sums of dz2
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (k0 + e < K) atomicAdd(&csum[k0 + e], v[e]);
+          }
         }
         const uint32_t off = (uint32_t)(c >> 3) * FN_ABLK + (uint32_t)r * 128u + ((((uint32_t)c & 7u) ^ ((uint32_t)r & 7u)) << 4);
         asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(sA + off), "f"(tf32_rna(v[0])), "f"(tf32_rna(v[1])),
                      "f"(tf32_rna(v[2])), "f"(tf32_rna(v[3])));
+      };
+      // batches of 8 chunks per thread: all loads of a batch are issued before the first dependent store
+      constexpr int NB = 8;
+      for (int i0 = threadIdx.x; i0 < total; i0 += FN_EPI * NB) {
+        float v[NB][4];
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+          v[u][0] = v[u][1] = v[u][2] = v[u][3] = 0.f;
+          if (i0 + u * FN_EPI < total) load_item(i0 + u * FN_EPI, v[u]);
+        }
+        if (warp == 0 && i0 == (int)threadIdx.x) fn_stamp(9);
+#pragma unroll
+        for (int u = 0; u < NB; ++u)
+          if (i0 + u * FN_EPI < total) store_item(i0 + u * FN_EPI, v[u]);
+        if (warp == 0 && i0 == (int)threadIdx.x) fn_stamp(10);
       }
+      if (warp == 0) fn_stamp(11);
       fence_async_smem();
       mbar_arrive(bar_a);
+      if (warp == 0) fn_stamp(1);
+      if (BWD && t.dbias[2] != nullptr) {
+        named_bar_sync(1, FN_EPI);   // every epilogue thread's shared-memory atomics have landed
+        if ((int)threadIdx.x < K) atomicAdd(t.dbias[2] + threadIdx.x, csum[threadIdx.x]);
+      }
     }
 
     // ---- hidden layers: accumulator -> activation (or its derivative) -> HBM + TMEM in place ----------
@@ -266,6 +331,7 @@ __global__ void __launch_bounds__(FN_THREADS, 1) fn_tc_kernel(FnTcArgs t) {
       float* dst = t.out01[l];
       mbar_wait(bar_d + 8 * l, 0);
       tc_fence_after();
+      if (warp == 0) fn_stamp(2 + 2 * l);
 #pragma unroll 1
       for (int c0 = q * cw; c0 < (q + 1) * cw; c0 += 32) {
         float v[32];
@@ -302,15 +368,32 @@ __global__ void __launch_bounds__(FN_THREADS, 1) fn_tc_kernel(FnTcArgs t) {
           for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         }
         tmem_st32(dcol + (uint32_t)c0, v);
+        if (BWD && t.dbias[1 - l] != nullptr) {
+          // db = column sums of dz: butterfly transpose-reduce over the warp's 32 rows (31 shuffles for 32
+          // columns; rows past M hold zeros), lane j ends with column c0 + j, one coalesced reduction per warp
+#pragma unroll
+          for (int ofs = 16; ofs >= 1; ofs >>= 1) {
+            const bool up = (lane & ofs) != 0;
+#pragma unroll
+            for (int j = 0; j < ofs; ++j) {
+              const float send = up ? v[j] : v[j + ofs];
+              const float keep = up ? v[j + ofs] : v[j];
+              v[j] = keep + __shfl_xor_sync(0xffffffffu, send, ofs);
+            }
+          }
+          atomicAdd(t.dbias[1 - l] + c0 + lane, v[0]);
+        }
       }
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(bar_e + 8 * l);
+      if (warp == 0) fn_stamp(3 + 2 * l);
     }
 
     // ---- last layer: 8-column chunks q, q+4, ... of the accumulator at column 0 -----------------------
     mbar_wait(bar_d + 16, 0);
     tc_fence_after();
+    if (warp == 0) fn_stamp(6);
     const int NC = t.Na + t.Nb;
     for (int c0 = q * 8; c0 < t.n[2]; c0 += 32) {
       float v[8];
@@ -348,8 +431,10 @@ __global__ void __launch_bounds__(FN_THREADS, 1) fn_tc_kernel(FnTcArgs t) {
     }
   }
 
+  if (warp == 0) fn_stamp(7);
   tc_fence_before();
   __syncthreads();
+  if (warp == 0) fn_stamp(8);
   if (warp == 16) tmem_dealloc(tmem, 512);
 }
 
@@ -533,6 +618,8 @@ __global__ void __launch_bounds__(DW_THREADS, 1) fn_dw_kernel(FnDwArgs t) {
 }
 
 }  // namespace
+
+extern "C" int mpg_debug_set_fn_trace(void* p) { return (int)cudaMemcpyToSymbol(g_fn_trace, &p, sizeof(p)); }
 
 bool fn_tc_supported(int Ka, int Kb, int H1, int H2, int NO, float p) {
   return Ka > 0 && Kb >= 0 && Ka + Kb <= 256 && (H1 == 128 || H1 == 256) && (H2 == 128 || H2 == 256) && NO >= 1 &&

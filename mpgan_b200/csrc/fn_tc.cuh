@@ -25,6 +25,7 @@ struct FnTcArgs {
   const float* ysave[2];        // backward: {y1, y0} (outputs of the layer whose derivative epilogue l applies)
   float* out01[2];              // forward {y0, y1}; backward {dz1, dz0}; contiguous [M, n[l]]
   float* dz2;                   // backward with dropout: dout * drop' [M, NO]
+  float* dbias[3];              // backward: bias gradients of layer 0, 1, 2 (accumulated; NULL = skip)
   // last GEMM's output columns [0, Na) -> outa, [Na, Na+Nb) -> outb   (forward: out, Nb = 0; backward: da, db)
   float* outa; int ldoa, Na;
   float* outb; int ldob, Nb;

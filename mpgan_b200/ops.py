@@ -36,6 +36,9 @@ def get_precision() -> int:
 # accumulated by the kernels straight into that buffer and the autograd functions return ``None`` for them:
 # no zero-filled temporaries, no AccumulateGrad add kernel per parameter and backward pass.
 _DIRECT_GRAD = False
+# Keep the forward's edge workspace (P/Q, weight images, work list: ~0.8 KB per particle) alive for the backward
+# instead of rebuilding it there.
+_SAVE_EDGE_WS = True
 
 
 def set_direct_grad(on: bool):
@@ -221,7 +224,8 @@ class EdgeAggFn(torch.autograd.Function):
         x3, ldx = _rows(x)
         B, N, F = x3.shape
         H0, H1, H2 = w0.shape[0], w1.shape[0], w2.shape[0]
-        ws_bytes = L.mpg_edge_workspace_bytes(B, N, F, H0, H1, H2)
+        # forward-only part of the workspace (P/Q, weight images, work list); kept for the backward when one follows
+        ws_bytes = L.mpg_edge_fwd_workspace_bytes(B, N, F, H0, H1, H2)
         ws = torch.empty(ws_bytes, device=x.device, dtype=torch.uint8)
         agg = torch.empty(B, N, H2, device=x.device, dtype=torch.float32)
         m = None if mask is None else mask.reshape(B, N).contiguous()
@@ -236,6 +240,7 @@ class EdgeAggFn(torch.autograd.Function):
                                       _lib.stream()), "mpg_edge_fwd")
         ctx.save_for_backward(x3, m, *ws_)
         ctx.params = (w0, b0, w1, b1, w2, b2)
+        ctx.fwd_ws = ws if _SAVE_EDGE_WS else None
         ctx.cfg = (ldx, B, N, F, H0, H1, H2, int(ef_mode), int(nd), int(mean), float(alpha), float(p_drop), seed,
                    _PRECISION, _seed_ptr())
         return agg
@@ -268,11 +273,14 @@ class EdgeAggFn(torch.autograd.Function):
         with _Timed("edge_bwd", 2.0 * edge_flops(B, N, F, H0, H1, H2),
                     [(2, "edge_tc_bwd_chain_kernel", 2 * _pair_flops(B, N, H0, H1) + _pair_flops(B, N, H1, H2)),
                      (3, "edge_tc_bwd_dw2_kernel", _pair_flops(B, N, H1, H2))], frac):
-            _lib.check(L.mpg_edge_bwd(_lib.ptr(x3), ldx, _lib.ptr(m),
-                                      *[_lib.ptr(t) for t in (w0, b0, w1, b1, w2, b2)], B, N, F, H0, H1, H2, ef_mode,
-                                      nd, mean, alpha, p, seed, sptr, prec, ws.data_ptr(), ws_bytes, _lib.ptr(dagg),
-                                      _lib.ptr(dx), F, *[_lib.ptr(g) for g in grads], _lib.stream()),
-                       "mpg_edge_bwd")
+            args = (_lib.ptr(x3), ldx, _lib.ptr(m), *[_lib.ptr(t) for t in (w0, b0, w1, b1, w2, b2)], B, N, F, H0, H1,
+                    H2, ef_mode, nd, mean, alpha, p, seed, sptr, prec, ws.data_ptr(), ws_bytes, _lib.ptr(dagg),
+                    _lib.ptr(dx), F, *[_lib.ptr(g) for g in grads], _lib.stream())
+            fws = ctx.fwd_ws
+            if fws is not None:   # P/Q, weight images and work list as the forward left them
+                _lib.check(L.mpg_edge_bwd_saved(fws.data_ptr(), fws.numel(), *args), "mpg_edge_bwd_saved")
+            else:
+                _lib.check(L.mpg_edge_bwd(*args), "mpg_edge_bwd")
         if direct:
             grads = [None] * 6
         return (dx, None, *grads, None, None, None, None, None)
