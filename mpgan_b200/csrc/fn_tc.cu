@@ -29,17 +29,17 @@ constexpr int FN_EPI = 512;                       // epilogue threads (16 warps)
 constexpr int FN_THREADS = FN_EPI + 64;           // + warp 16 (MMA issuer) + warp 17 (loader)
 constexpr uint32_t FN_ABLK = 128 * 128;           // one 32-wide K block of the A tile: 128 rows x 128 B
 constexpr uint32_t FN_STAGE = 256 * 128;          // one 32-wide K block of a weight image: <= 256 rows x 128 B
-constexpr int FN_STAGES = 3;
-constexpr uint32_t FN_OFF_A = 0;
-constexpr uint32_t FN_OFF_W = 8 * FN_ABLK;                          // 131072
-constexpr uint32_t FN_OFF_BAR = FN_OFF_W + FN_STAGES * FN_STAGE;    // 229376
+// Shared memory.  [0, 128 KB) is the staging tile through which every [128 x H] activation / gradient tile
+// moves between the thread-per-row world of TMEM and coalesced global accesses (rows of H floats, 16-byte chunks
+// XOR-swizzled with row & 7).  Forward: the same 128 KB first hold the A tile of GEMM 0 (up to 8 K blocks) and
+// the ring has 3 stages; backward: the A tile is one K block (NO <= 32) behind the staging tile and the ring has
+// 2 stages.
+constexpr uint32_t FN_OFF_STG = 0;
+constexpr uint32_t FN_STG_BYTES = 128 * 256 * 4;                    // 131072
+constexpr uint32_t FN_OFF_BAR = FN_STG_BYTES + 3 * FN_STAGE;        // 229376
 constexpr uint32_t FN_OFF_CSUM = FN_OFF_BAR + 256;                  // 256 floats: column sums of dz2 (backward)
 constexpr uint32_t FN_SMEM = FN_OFF_CSUM + 1024 + 1024;             // 231680 <= 232448
-// Weight ring: stages 0..2 live in their own 96 KB and carry the blocks of GEMM 0 and then GEMM 2; stages 3..6
-// are the A tile's 128 KB, free once GEMM 0 has completed, and carry GEMM 1 -- so GEMM 1's first four blocks
-// and GEMM 2's first three are in flight while the epilogues run.
-constexpr int FN_RING1 = 4;
-constexpr int FN_NSTG = FN_STAGES + FN_RING1;
+constexpr int FN_MAX_STAGES = 3;
 
 __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t r;
@@ -147,14 +147,17 @@ __device__ __forceinline__ void fn_stamp(int slot) {
 template <bool BWD>
 __global__ void __launch_bounds__(FN_THREADS, 1) fn_tc_kernel(FnTcArgs t) {
   extern __shared__ uint8_t smem_raw[];
+  constexpr int NSTG = BWD ? 2 : 3;
+  constexpr uint32_t OFF_A = BWD ? FN_STG_BYTES : 0u;                       // A tile of GEMM 0
+  constexpr uint32_t OFF_W = BWD ? FN_STG_BYTES + FN_ABLK : FN_STG_BYTES;   // weight ring
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SW128 tiles need 1024-byte alignment
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t sA = base + FN_OFF_A, sW = base + FN_OFF_W, bar0 = base + FN_OFF_BAR;
+  const uint32_t sA = base + OFF_A, sW = base + OFF_W, sS = base + FN_OFF_STG, bar0 = base + FN_OFF_BAR;
   const uint32_t bar_a = bar0;                   // A tile built (FN_EPI arrivals)
   const uint32_t bar_e = bar0 + 8;               // [2] epilogue l done: TMEM A operand of layer l+1 ready
   const uint32_t bar_d = bar0 + 24;              // [3] accumulator of layer l complete
-  const uint32_t bar_full = bar0 + 48;           // [FN_NSTG]
-  const uint32_t bar_empty = bar0 + 48 + 8 * FN_NSTG;
+  const uint32_t bar_full = bar0 + 48;           // [FN_MAX_STAGES]
+  const uint32_t bar_empty = bar0 + 48 + 8 * FN_MAX_STAGES;
   float* csum = reinterpret_cast<float*>(sm + FN_OFF_CSUM);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + FN_OFF_BAR + 192);
 
@@ -167,7 +170,7 @@ __global__ void __launch_bounds__(FN_THREADS, 1) fn_tc_kernel(FnTcArgs t) {
     mbar_init(bar_e, FN_EPI);
     mbar_init(bar_e + 8, FN_EPI);
     for (int l = 0; l < 3; ++l) mbar_init(bar_d + 8 * l, 1);
-    for (int s = 0; s < FN_NSTG; ++s) {
+    for (int s = 0; s < NSTG; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
@@ -179,34 +182,24 @@ __global__ void __launch_bounds__(FN_THREADS, 1) fn_tc_kernel(FnTcArgs t) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  // ring position -> (stage, use count): ring 0 = stages [0, FN_STAGES), ring 1 = stages [FN_STAGES, FN_NSTG)
-  auto stage_of = [](int ring, uint32_t g) { return ring ? FN_STAGES + g % FN_RING1 : g % FN_STAGES; };
-  auto use_of = [](int ring, uint32_t g) { return ring ? g / FN_RING1 : g / FN_STAGES; };
-  auto stage_addr = [&](uint32_t st) { return st < FN_STAGES ? sW + st * FN_STAGE : sA + (st - FN_STAGES) * FN_STAGE; };
 
   if (warp == 17) {
-    // =============================== loader: weight-image K blocks through the rings ==================
-    uint32_t gr[2] = {0, 0};
-    auto load = [&](int l, int blk) {
-      const int ring = l == 1;
+    // =============================== loader: weight-image K blocks through the ring ===================
+    uint32_t g = 0;
+    for (int l = 0; l < 3; ++l) {
       const uint32_t bytes = (uint32_t)t.n[l] * 128u;
-      const uint32_t g = gr[ring]++, st = stage_of(ring, g), use = use_of(ring, g);
-      if (use >= 1) mbar_wait(bar_empty + 8 * st, (use - 1) & 1);
-      mbar_expect_tx_elect(bar_full + 8 * st, bytes);
-      bulk_g2s_elect(stage_addr(st), t.img[l] + (size_t)blk * bytes, bytes, bar_full + 8 * st);
-    };
-    const int kb0 = (t.kmma[0] + 3) >> 2, kb1 = (t.kmma[1] + 3) >> 2, kb2 = (t.kmma[2] + 3) >> 2;
-    const int pre2 = min(kb2, FN_STAGES);
-    for (int blk = 0; blk < kb0; ++blk) load(0, blk);
-    for (int blk = 0; blk < pre2; ++blk) load(2, blk);   // behind GEMM 0's last blocks
-    mbar_wait(bar_d, 0);                                  // GEMM 0 complete: the A tile's memory is ring 1
-    for (int blk = 0; blk < kb1; ++blk) load(1, blk);
-    for (int blk = pre2; blk < kb2; ++blk) load(2, blk);
+      const int kb = (t.kmma[l] + 3) >> 2;
+      for (int blk = 0; blk < kb; ++blk, ++g) {
+        const uint32_t st = g % NSTG;
+        if (g >= NSTG) mbar_wait(bar_empty + 8 * st, (g / NSTG - 1) & 1);
+        mbar_expect_tx_elect(bar_full + 8 * st, bytes);
+        bulk_g2s_elect(sW + st * FN_STAGE, t.img[l] + (size_t)blk * bytes, bytes, bar_full + 8 * st);
+      }
+    }
   } else if (warp == 16) {
     // =============================== MMA issuer ========================================================
-    uint32_t gr[2] = {0, 0};
+    uint32_t g = 0;
     for (int l = 0; l < 3; ++l) {
-      const int ring = l == 1;
       mbar_wait(l == 0 ? bar_a : bar_e + 8 * (l - 1), 0);
       tc_fence_after();
       fn_stamp(16 + 2 * l);
@@ -214,13 +207,13 @@ __global__ void __launch_bounds__(FN_THREADS, 1) fn_tc_kernel(FnTcArgs t) {
       const uint32_t dcol = tmem + (l == 1 ? 256u : 0u);
       const uint32_t acol = tmem + (l == 1 ? 0u : 256u);   // TMEM A operand (layers 1, 2)
       const int kb = (t.kmma[l] + 3) >> 2;
-      for (int blk = 0; blk < kb; ++blk) {
-        const uint32_t g = gr[ring]++, st = stage_of(ring, g);
-        mbar_wait(bar_full + 8 * st, use_of(ring, g) & 1);
+      for (int blk = 0; blk < kb; ++blk, ++g) {
+        const uint32_t st = g % NSTG;
+        mbar_wait(bar_full + 8 * st, (g / NSTG) & 1);
         tc_fence_after();
         const int nm = min(4, t.kmma[l] - 4 * blk);
         if (elect_one()) {
-          const uint64_t bd = umma_desc(stage_addr(st));
+          const uint64_t bd = umma_desc(sW + st * FN_STAGE);
           if (l == 0) {
             const uint64_t ad = umma_desc(sA + (uint32_t)blk * FN_ABLK);
             for (int j = 0; j < nm; ++j) umma_tf32_ss(dcol, ad + (uint64_t)(j * 2), bd + (uint64_t)(j * 2), idesc, (uint32_t)(blk | j));
@@ -247,6 +240,49 @@ __global__ void __launch_bounds__(FN_THREADS, 1) fn_tc_kernel(FnTcArgs t) {
     resolve_seed(dc);
     const bool drop = dc.p > 0.f;                  // p == 0.5 only (host-checked)
     if (warp == 0) fn_stamp(0);
+
+    // Staging tile <-> global, coalesced: warp w moves rows w, w+16, ...; a lane moves the 16-byte chunks lane,
+    // lane+32 of a row (512 contiguous bytes per warp instruction).  Chunk c of row r sits at chunk c ^ (r & 7).
+    auto stage_to_global = [&](float* dst, int H) {
+      const int cpr = H >> 2;                      // chunks per row
+      for (int r = warp; r < 128; r += 16) {
+        if (row0 + r >= t.M) break;
+        float* o = dst + (size_t)(row0 + r) * H;
+        for (int c = lane; c < cpr; c += 32) {
+          float4 v;
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                       : "r"(sS + (uint32_t)r * (uint32_t)(H * 4) + (((uint32_t)c ^ ((uint32_t)r & 7u)) << 4)));
+          *reinterpret_cast<float4*>(o + 4 * c) = v;
+        }
+      }
+    };
+    auto global_to_stage = [&](const float* src, int H) {
+      const int cpr = H >> 2;
+      for (int rb = warp; rb < 128; rb += 64) {    // 4 rows per batch: all loads in flight before the first store
+        float4 v[4][2];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = rb + 16 * u;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int c = lane + 32 * i;
+            v[u][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row0 + r < t.M && c < cpr) v[u][i] = *reinterpret_cast<const float4*>(src + (size_t)(row0 + r) * H + 4 * c);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = rb + 16 * u;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int c = lane + 32 * i;
+            if (c < cpr)
+              asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(sS + (uint32_t)r * (uint32_t)(H * 4) + (((uint32_t)c ^ ((uint32_t)r & 7u)) << 4)),
+                           "f"(v[u][i].x), "f"(v[u][i].y), "f"(v[u][i].z), "f"(v[u][i].w) : "memory");
+          }
+        }
+      }
+    };
 
     // ---- A tile of layer 0: [a | b] (forward) or dout * drop' (backward), TF32-rounded, swizzled ------
     {
@@ -294,24 +330,43 @@ __global__ void __launch_bounds__(FN_THREADS, 1) fn_tc_kernel(FnTcArgs t) {
         }
         const uint32_t off = (uint32_t)(c >> 3) * FN_ABLK + (uint32_t)r * 128u + ((((uint32_t)c & 7u) ^ ((uint32_t)r & 7u)) << 4);
         asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(sA + off), "f"(tf32_rna(v[0])), "f"(tf32_rna(v[1])),
-                     "f"(tf32_rna(v[2])), "f"(tf32_rna(v[3])));
+                     "f"(tf32_rna(v[2])), "f"(tf32_rna(v[3])) : "memory");
       };
-      // batches of 8 chunks per thread: all loads of a batch are issued before the first dependent store
-      constexpr int NB = 8;
-      for (int i0 = threadIdx.x; i0 < total; i0 += FN_EPI * NB) {
-        float v[NB][4];
+      if (!BWD && t.vec_a && (t.vec_b || t.Kb == 0) && (K & 3) == 0) {
+        // fast path (16-byte aligned sources, whole chunks): short code, 8 loads in flight per thread
+        constexpr int NB = 8;
+        for (int i0 = threadIdx.x; i0 < total; i0 += FN_EPI * NB) {
+          float4 v[NB];
 #pragma unroll
-        for (int u = 0; u < NB; ++u) {
-          v[u][0] = v[u][1] = v[u][2] = v[u][3] = 0.f;
-          if (i0 + u * FN_EPI < total) load_item(i0 + u * FN_EPI, v[u]);
+          for (int u = 0; u < NB; ++u) {
+            const int idx = i0 + u * FN_EPI;
+            const int r = idx / nch, c = idx - r * nch;
+            const int gr = row0 + r, k0 = c * 4;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (idx < total && gr < t.M && k0 < K) {
+              const float* src = k0 < t.Ka ? t.a + (size_t)gr * t.lda + k0 : t.b + (size_t)gr * t.ldb + (k0 - t.Ka);
+              v[u] = *reinterpret_cast<const float4*>(src);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < NB; ++u) {
+            const int idx = i0 + u * FN_EPI;
+            const int r = idx / nch, c = idx - r * nch;
+            if (idx < total) {
+              const uint32_t off = (uint32_t)(c >> 3) * FN_ABLK + (uint32_t)r * 128u + ((((uint32_t)c & 7u) ^ ((uint32_t)r & 7u)) << 4);
+              asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(sA + off), "f"(tf32_rna(v[u].x)), "f"(tf32_rna(v[u].y)),
+                           "f"(tf32_rna(v[u].z)), "f"(tf32_rna(v[u].w)) : "memory");
+            }
+          }
         }
-        if (warp == 0 && i0 == (int)threadIdx.x) fn_stamp(9);
-#pragma unroll
-        for (int u = 0; u < NB; ++u)
-          if (i0 + u * FN_EPI < total) store_item(i0 + u * FN_EPI, v[u]);
-        if (warp == 0 && i0 == (int)threadIdx.x) fn_stamp(10);
+      } else {
+#pragma unroll 1
+        for (int idx = threadIdx.x; idx < total; idx += FN_EPI) {
+          float v[4] = {0.f, 0.f, 0.f, 0.f};
+          load_item(idx, v);
+          store_item(idx, v);
+        }
       }
-      if (warp == 0) fn_stamp(11);
       fence_async_smem();
       mbar_arrive(bar_a);
       if (warp == 0) fn_stamp(1);
@@ -321,14 +376,20 @@ __global__ void __launch_bounds__(FN_THREADS, 1) fn_tc_kernel(FnTcArgs t) {
       }
     }
 
-    // ---- hidden layers: accumulator -> activation (or its derivative) -> HBM + TMEM in place ----------
+    // ---- hidden layers: accumulator -> activation (or its derivative) -> staging tile + TMEM in place ------
 #pragma unroll 1
     for (int l = 0; l < 2; ++l) {
       const int H = t.n[l], cw = H >> 2;           // this thread's columns: [q*cw, (q+1)*cw)
       const uint32_t dcol = tl + (l == 1 ? 256u : 0u);
       const uint32_t stream = t.stream[BWD ? 1 - l : l];
-      const float* side = BWD ? t.ysave[l] : t.bias[l];
       float* dst = t.out01[l];
+      const uint32_t srow = sS + (uint32_t)row * (uint32_t)(H * 4);
+      if (BWD) {
+        // the saved layer output whose derivative this epilogue applies: coalesced into the staging tile while the
+        // GEMM runs (the tile is free: the previous layer's copy-out ended at the barrier below)
+        global_to_stage(t.ysave[l], H);
+        named_bar_sync(2, FN_EPI);
+      }
       mbar_wait(bar_d + 8 * l, 0);
       tc_fence_after();
       if (warp == 0) fn_stamp(2 + 2 * l);
@@ -339,18 +400,19 @@ __global__ void __launch_bounds__(FN_THREADS, 1) fn_tc_kernel(FnTcArgs t) {
         uint32_t kw = 0xFFFFFFFFu;
         if (drop) kw = drop_word32(dc, stream, (uint64_t)grow, (uint32_t)(c0 >> 5));
         if (!BWD) {
+          const float* bias = t.bias[l];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {   // bias: warp-uniform address (parameters need not be 16-byte aligned)
-            float x = lrelu(v[j] + __ldg(side + c0 + j), t.alpha);
+            float x = lrelu(v[j] + __ldg(bias + c0 + j), t.alpha);
             if (drop) x = ((kw >> j) & 1u) ? x * dc.scale : 0.f;
             v[j] = x;
           }
         } else {
-          const float* yr = side + (size_t)(valid ? grow : 0) * H + c0;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            const float4 yy = *reinterpret_cast<const float4*>(yr + j);
-            const float y4[4] = {yy.x, yy.y, yy.z, yy.w};
+            float y4[4];
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(y4[0]), "=f"(y4[1]), "=f"(y4[2]), "=f"(y4[3])
+                         : "r"(srow + ((((uint32_t)(c0 + j) >> 2) ^ ((uint32_t)row & 7u)) << 4)));
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               float gfac = lrelu_grad_from_out(y4[e], t.alpha);
@@ -362,11 +424,10 @@ __global__ void __launch_bounds__(FN_THREADS, 1) fn_tc_kernel(FnTcArgs t) {
         // rounded to TF32 once: the saved copy only ever feeds TF32 GEMMs (weight gradients) and the sign test
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = tf32_rna(v[j]);
-        if (valid && dst != nullptr) {
-          float* o = dst + (size_t)grow * H + c0;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        }
+        for (int j = 0; j < 32; j += 4)
+          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(srow + ((((uint32_t)(c0 + j) >> 2) ^ ((uint32_t)row & 7u)) << 4)),
+                       "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
         tmem_st32(dcol + (uint32_t)c0, v);
         if (BWD && t.dbias[1 - l] != nullptr) {
           // db = column sums of dz: butterfly transpose-reduce over the warp's 32 rows (31 shuffles for 32
@@ -386,8 +447,11 @@ __global__ void __launch_bounds__(FN_THREADS, 1) fn_tc_kernel(FnTcArgs t) {
       }
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(bar_e + 8 * l);
+      mbar_arrive(bar_e + 8 * l);                  // the next GEMM starts; the copy-out below runs under it
       if (warp == 0) fn_stamp(3 + 2 * l);
+      named_bar_sync(1, FN_EPI);                   // staging tile complete
+      if (dst != nullptr) stage_to_global(dst, H);
+      named_bar_sync(2, FN_EPI);                   // staging tile free again
     }
 
     // ---- last layer: 8-column chunks q, q+4, ... of the accumulator at column 0 -----------------------
@@ -437,7 +501,6 @@ __global__ void __launch_bounds__(FN_THREADS, 1) fn_tc_kernel(FnTcArgs t) {
   if (warp == 0) fn_stamp(8);
   if (warp == 16) tmem_dealloc(tmem, 512);
 }
-
 
 // ---------------------------------------------------------------------------------------------------
 // Weight gradients of the node network: dW_l += dz_l^T in_l  (l = 0, 1, 2; reduction over the M rows).
@@ -622,8 +685,9 @@ __global__ void __launch_bounds__(DW_THREADS, 1) fn_dw_kernel(FnDwArgs t) {
 extern "C" int mpg_debug_set_fn_trace(void* p) { return (int)cudaMemcpyToSymbol(g_fn_trace, &p, sizeof(p)); }
 
 bool fn_tc_supported(int Ka, int Kb, int H1, int H2, int NO, float p) {
+  // NO <= 32: the backward kernel's first A tile (dz2) is one 32-wide K block
   return Ka > 0 && Kb >= 0 && Ka + Kb <= 256 && (H1 == 128 || H1 == 256) && (H2 == 128 || H2 == 256) && NO >= 1 &&
-         NO <= 256 && (p == 0.f || p == 0.5f);
+         NO <= 32 && (p == 0.f || p == 0.5f);
 }
 
 static int r_up(int v, int m) { return (v + m - 1) / m * m; }
