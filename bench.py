@@ -305,8 +305,7 @@ def run_ours(args, wl):
         G.eval()
 
         def one_step(d, l):
-            with torch.no_grad():
-                return G(train.get_gen_noise(B, N, latent, 0.2, dev), l)
+            return train.generate(G, l, N, latent, 0.2)   # public generation call (sorts by count, un-sorts output)
 
     def barrier():
         if world > 1:
@@ -439,6 +438,8 @@ def run_ours(args, wl):
             "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if gapt else "bf16", "data": "synthetic",
             "config": {"workload": args.workload, "particles": N, "batch_per_gpu": B, "global_batch": B * world,
                        "particles_per_jet": "all N real" if args.all_real else "n ~ U{1..N} (padded rows masked)",
+                       "batch_order": "jets ordered by particle count inside each batch (GANTrainer.sort_by_count / "
+                                      "train.generate); fully padded (tile, sender) steps are dropped by the kernels",
                        "l2": "flushed between timed steps (256 MiB write)",
                        "precision": ("TF32 projections, fp32 attention core" if gapt else
                                      "bf16 tcgen05 edge network, TF32 node GEMMs, fp32 accumulate"), "parallelism": f"dp{world}",

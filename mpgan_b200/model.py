@@ -253,10 +253,30 @@ class MPNet(nn.Module):
             raise RuntimeError("mpgan_b200 modules run on CUDA only (no CPU fallback)")
         x = self._pre_mp(x, labels)
         x, use_mask, mask, num_jet_particles = self._get_mask(x, labels, **self.mask_args)
+        idx = None
+        if use_mask and self.sort_particles and x.shape[1] > 1:
+            # Real particles first inside every jet.  The layers are permutation-equivariant over particles
+            # (fully connected, sum / mean aggregation), so this only changes the layout: a generated jet's real
+            # particles are wherever its noise ranks put them, and a sender index that is padded in every jet of a
+            # 128-particle tile is a (tile, sender) step the edge kernels drop.
+            idx = torch.argsort(mask[:, :, 0], dim=1, descending=True, stable=True).unsqueeze(2)
+            x = torch.gather(x, 1, idx.expand(-1, -1, x.shape[2]))
+            mask = torch.gather(mask, 1, idx)
         for i in range(self.mp_iters):
             x = self.mp_layers[i](x, use_mask, mask, labels, num_jet_particles)
+        if idx is not None and not self._pool_is_order_free():
+            # back to the caller's particle order: out[b, idx[b, k]] = x[b, k]
+            ix = idx.expand(-1, -1, x.shape[2])
+            x = torch.empty_like(x).scatter(1, ix, x)
+            mask = torch.empty_like(mask).scatter(1, idx, mask)
         x = self._post_mp(x, labels, use_mask, mask, num_jet_particles)
         return self._tail(x, mask)
+
+    sort_particles = True     # class-level switch (tests compare both layouts)
+
+    def _pool_is_order_free(self) -> bool:
+        """True if ``_post_mp`` reduces over particles (then the permutation need not be undone)."""
+        return False
 
     def _tail(self, x, mask):
         x = self._final_activation(x)
@@ -347,6 +367,9 @@ class MPDiscriminator(MPNet):
         if dea:
             self.fnd_layer = LinearNet(fnd, input_size=self.hidden_node_size + int(mask_fnd_np), output_size=1,
                                        final_linear=True, **self.linear_args)
+
+    def _pool_is_order_free(self) -> bool:
+        return True   # masked sum / mean over particles (with or without the fnd head)
 
     def _post_mp(self, x, labels, use_mask, mask, num_jet_particles):
         do_mean = not (self.dea and self.dea_sum)

@@ -71,9 +71,15 @@ def get_gen_noise(batch_size, num_particles, latent_node_size, sd=0.2, device="c
 
 class GANTrainer:
     def __init__(self, G, D, lr_gen=1e-5, lr_disc=3e-5, num_particles=30, latent_node_size=32, sd=0.2,
-                 process_group=None, batch_real_fake=True):
+                 process_group=None, batch_real_fake=True, sort_by_count=True):
         self.G, self.D = G, D
         self.batch_real_fake = batch_real_fake
+        # step(): order the jets of a batch by particle count.  Jets never interact (no BatchNorm) and both losses
+        # are batch means, so the update is the same; what changes is that every 128-particle tile of the edge
+        # kernels then holds jets with (nearly) the same padding, and the (tile, sender) steps whose sender is
+        # padded in ALL of the tile's jets -- which the kernels drop -- go from ~5-30 % to ~50 % of the steps
+        # for n ~ U{1..N}.
+        self.sort_by_count = sort_by_count
         self.fpG, self.fpD = FlatParams(G), FlatParams(D)
         ops.set_direct_grad(True)   # kernels accumulate weight gradients straight into the flat .grad buffers
         self.optG, self.optD = FusedRMSprop(self.fpG, lr_gen), FusedRMSprop(self.fpD, lr_disc)
@@ -142,6 +148,8 @@ class GANTrainer:
 
     def step(self, data, labels):
         """One critic + one generator update (train.py:841-878 with num_critic = num_gen = 1)."""
+        if self.sort_by_count:
+            data, labels = sort_by_count(data, labels)
         return self.train_D(data, labels), self.train_G(labels)
 
     # -- whole-step CUDA graph (SURVEY 8f rank 1) ---------------------------------------------------
@@ -188,6 +196,26 @@ class GANTrainer:
         return self._static_losses
 
 
+def sort_by_count(data, labels):
+    """Reorders a batch by descending particle count (labels[:, -1] = n / N); see GANTrainer.sort_by_count."""
+    order = torch.argsort(labels[:, -1], descending=True)
+    return data.index_select(0, order), labels.index_select(0, order)
+
+
+@torch.no_grad()
+def generate(G, labels, num_particles, latent_node_size=32, sd=0.2, noise=None):
+    """G(noise, labels) with the jets processed in order of particle count (fewer live edge-kernel steps, see
+    GANTrainer.sort_by_count) and returned in the caller's order."""
+    B = labels.shape[0]
+    order = torch.argsort(labels[:, -1], descending=True)
+    if noise is None:
+        noise = get_gen_noise(B, num_particles, latent_node_size, sd, labels.device)
+    else:
+        noise = noise.index_select(0, order)
+    out_sorted = G(noise, labels.index_select(0, order))
+    return torch.empty_like(out_sorted).index_copy_(0, order, out_sorted)
+
+
 def synthetic_jets(B, N, device="cuda", generator=None, all_real=False):
     """SURVEY 8(d) synthetic batch: features U(-.5,.5) zeroed on padded rows, 4th channel mask-0.5;
     labels n * fp32(1/N)."""
@@ -216,8 +244,11 @@ def gen_multi_batch(G, num_samples, batch_size, num_particles, labels=None, late
     for start in range(0, num_samples, batch_size):
         n = min(batch_size, num_samples - start)
         lab = None if labels is None else labels[start:start + n].to(dev, non_blocking=True)
-        noise = get_gen_noise(n, num_particles, latent_node_size, sd, dev)
-        out[start:start + n].copy_(G(noise, lab), non_blocking=True)
+        if lab is None:
+            jets = G(get_gen_noise(n, num_particles, latent_node_size, sd, dev), lab)
+        else:
+            jets = generate(G, lab, num_particles, latent_node_size, sd)
+        out[start:start + n].copy_(jets, non_blocking=True)
     if dev.type == "cuda":
         torch.cuda.current_stream().synchronize()
     return out

@@ -435,3 +435,73 @@ def test_node_net_tc_matches_layerwise(p, M, Kb, NO):
     for i in range(3):
         assert rel_l2(ws[2 * i].grad, grads[i][0]) <= 5e-3, i
         assert rel_l2(ws[2 * i + 1].grad, grads[i][1]) <= 5e-3, i
+
+
+def test_sorted_batch_same_update(golden):
+    """GANTrainer.step orders the jets of a batch by particle count (a layout choice for the edge kernels' work
+    list).  Jets never interact and the losses are batch means, so losses and gradients must equal those of the
+    caller's order (precision 0, no dropout, explicit noise permuted alongside)."""
+    from mpgan_b200 import presets, train
+    res = []
+    x, labels, _ = train.synthetic_jets(48, 30, "cuda", torch.Generator(device="cuda").manual_seed(21))
+    noise = train.get_gen_noise(48, 30, 32, 0.2, "cuda", torch.Generator(device="cuda").manual_seed(22))
+    for sort in (False, True):
+        G = presets.mp_generator().cuda()
+        D = presets.mp_discriminator(disc_dropout=0.0).cuda()
+        G.load_state_dict(golden("mp_g_weights.pt"), strict=True)
+        D.load_state_dict(golden("mp_d_seed4_weights.pt"), strict=True)
+        tr = train.GANTrainer(G, D, num_particles=30)
+        d, l, nz = x, labels, noise
+        if sort:
+            order = torch.argsort(labels[:, -1], descending=True)
+            d, l, nz = x[order], labels[order], noise[order]
+            d2, l2 = train.sort_by_count(x, labels)
+            assert torch.equal(l2, l) and torch.equal(d2.sum((1, 2)), d.sum((1, 2)))
+        ld = tr.train_D(d, l, noise=nz)
+        gD = tr.named_grads("D")
+        res.append((float(ld), gD))
+    assert abs(res[0][0] - res[1][0]) < 1e-5
+    for k in res[0][1]:
+        close(res[1][1][k], res[0][1][k], 1e-3, "sorted vs unsorted D grad " + k)
+
+
+def test_generate_keeps_caller_order(golden):
+    """train.generate sorts by count internally and returns the jets in the caller's order: the mask channel of
+    jet i must have exactly n_i particles."""
+    from mpgan_b200 import presets, train
+    G = presets.mp_generator().cuda().eval()
+    G.load_state_dict(golden("mp_g_weights.pt"), strict=True)
+    _, labels, n = train.synthetic_jets(64, 30, "cuda", torch.Generator(device="cuda").manual_seed(23))
+    out = train.generate(G, labels, 30)
+    assert torch.equal((out[..., 3] > 0).sum(1), n)
+
+
+def test_particle_sort_is_layout_only(golden):
+    """MPNet.forward puts the real particles of every jet first (fewer live edge-kernel steps) and undoes the
+    permutation: outputs and gradients must equal those of the caller's particle order (precision 0)."""
+    from mpgan_b200 import model, presets, train
+    G = presets.mp_generator().cuda().train()
+    D = presets.mp_discriminator(disc_dropout=0.0).cuda().train()
+    G.load_state_dict(golden("mp_g_weights.pt"), strict=True)
+    D.load_state_dict(golden("mp_d_seed4_weights.pt"), strict=True)
+    _, labels, n = train.synthetic_jets(24, 30, "cuda", torch.Generator(device="cuda").manual_seed(31))
+    noise = train.get_gen_noise(24, 30, 32, 0.2, "cuda", torch.Generator(device="cuda").manual_seed(32))
+    res = []
+    try:
+        for sort in (False, True):
+            model.MPNet.sort_particles = sort
+            G.zero_grad(); D.zero_grad()
+            fake = G(noise, labels)
+            loss = ((D(fake, labels) - 1) ** 2).mean()
+            loss.backward()
+            res.append((fake.detach().clone(), float(loss), {k: p.grad.clone() for k, p in G.named_parameters()},
+                        {k: p.grad.clone() for k, p in D.named_parameters()}))
+    finally:
+        model.MPNet.sort_particles = True
+    assert torch.equal(res[0][0][..., 3], res[1][0][..., 3])          # mask channel: same particles are real
+    assert torch.equal((res[1][0][..., 3] > 0).sum(1), n)
+    close(res[1][0], res[0][0], 1e-4, "generator output, sorted vs caller order")
+    assert abs(res[0][1] - res[1][1]) < 1e-5
+    for which in (2, 3):
+        for k in res[0][which]:
+            close(res[1][which][k], res[0][which][k], 1e-3, f"grad {k}")
