@@ -113,6 +113,14 @@ int mpg_edge_bwd_saved(const void* fwd_workspace, size_t fwd_workspace_bytes, co
 /* ---- masks and tails ------------------------------------------------------------------------------ */
 /* mask[b,i] = rank(x[b,i,0]) <= int(labels[b]*N) - 1   (bit-exact; mpgan/model.py:692-699) */
 int mpg_rank_mask(const float* x, int ldx, const float* labels, int ldl, int B, int N, float* mask, void* stream);
+/* Layout helpers: the layers are permutation-equivariant over particles (mpgan/model.py:206-282: fully connected,
+ * sum / mean aggregation), so a jet's real particles may be moved first -- then a sender index that is padded in
+ * every jet of a 128-particle tile is a step the edge kernels drop.  pos[b,i] (int32) = new index of particle i
+ * (stable, mask != 0 first); mask_sorted = the mask in that order.  mpg_permute_rows: mode 0 scatters
+ * dst[b, pos[b,i], :] = src[b, i, :], mode 1 gathers dst[b, i, :] = src[b, pos[b,i], :] (each the other's adjoint). */
+int mpg_particle_order(const float* mask, int B, int N, int* pos, float* mask_sorted, void* stream);
+int mpg_permute_rows(const float* src, int lds, float* dst, int ldd, const int* pos, int B, int N, int F, int mode,
+                     void* stream);
 /* mask[r] = x[r, ldx-1] + 0.5   (mpgan/model.py:881) */
 int mpg_split_mask(const float* x, int ldx, int rows, float* mask, void* stream);
 /* out[r, :Fo] = act(h[r, :]); out[r, Fo] = mask[r] - 0.5 if mask   (mpgan/model.py:535-536, 752) */

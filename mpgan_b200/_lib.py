@@ -39,6 +39,8 @@ _SIGS = {
     "mpg_edge_bwd_saved": (C.c_int, [_f, _sz, _f, _i, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _i,
                                      _fl, _fl, _u64, _f, _i, _f, _sz, _f, _f, _i, _f, _f, _f, _f, _f, _f, _f]),
     "mpg_rank_mask": (C.c_int, [_f, _i, _f, _i, _i, _i, _f, _f]),
+    "mpg_particle_order": (C.c_int, [_f, _i, _i, _f, _f, _f]),
+    "mpg_permute_rows": (C.c_int, [_f, _i, _f, _i, _f, _i, _i, _i, _i, _f]),
     "mpg_split_mask": (C.c_int, [_f, _i, _i, _f, _f]),
     "mpg_gen_tail_fwd": (C.c_int, [_f, _f, _f, _i, _i, _i, _f]),
     "mpg_gen_tail_bwd": (C.c_int, [_f, _f, _f, _i, _i, _i, _i, _f]),
@@ -89,7 +91,7 @@ def ptr(t):
         return None
     if not t.is_cuda:
         raise RuntimeError("mpgan_b200 ops need CUDA tensors (no CPU fallback)")
-    if t.dtype not in (torch.float32, torch.int64, torch.uint8):
+    if t.dtype not in (torch.float32, torch.int64, torch.int32, torch.uint8):
         raise RuntimeError(f"mpgan_b200 ops are fp32 at the boundary, got {t.dtype}")
     return t.data_ptr()
 

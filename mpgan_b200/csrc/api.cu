@@ -420,6 +420,14 @@ int mpg_rank_mask(const float* x, int ldx, const float* labels, int ldl, int B, 
   MPG_CHECK(N > 0 && N <= 8192, "rank_mask: N out of range");
   return launch_rank_mask(x, ldx, labels, ldl, B, N, mask, (cudaStream_t)stream);
 }
+int mpg_particle_order(const float* mask, int B, int N, int* pos, float* mask_sorted, void* stream) {
+  return launch_particle_order(mask, B, N, pos, mask_sorted, (cudaStream_t)stream);
+}
+int mpg_permute_rows(const float* src, int lds, float* dst, int ldd, const int* pos, int B, int N, int F, int mode,
+                     void* stream) {
+  MPG_CHECK(mode == 0 || mode == 1, "permute_rows: mode must be 0 (scatter) or 1 (gather)");
+  return launch_permute_rows(src, lds, dst, ldd, pos, B, N, F, mode, (cudaStream_t)stream);
+}
 int mpg_split_mask(const float* x, int ldx, int rows, float* mask, void* stream) {
   return launch_split_mask(x, ldx, rows, mask, (cudaStream_t)stream);
 }

@@ -17,6 +17,8 @@
 // (TMEM lane quarter x column quarter), one MMA-issuer warp, one loader warp.  TMEM: D0 [0,256) D1 [256,512),
 // D2 over D0.  Weight gradients (dz^T y) stay on the TF32 mma.sync GEMM (gemm.cu), launched by the caller on a
 // side stream.
+#include <stdlib.h>
+
 #include "fn_tc.cuh"
 #include "edge.cuh"      // EdgeArgs (referenced by the shared tcgen05 header)
 
@@ -570,11 +572,47 @@ __global__ void __launch_bounds__(DW_THREADS, 1) fn_dw_kernel(FnDwArgs t) {
       // ============================ producers ===========================================================
       const int chA = nblkA * 8, chB = nblkB * 8;         // 16-byte chunks per row
       const int per_sub = 32 * (chA + chB);
+      // The chunk -> (source, destination) map of a thread is the same for every sub-tile of the run: computed once
+      // (the per-chunk divisions made eight producer warps instruction-latency bound: ~17 us per 128-row item).
+      constexpr int MAXC = 16;                            // 32 * (64 + 64) chunks / 256 threads
+      const bool fast = t.vec_dz[l] && t.vec_a[l] && (t.kb[l] == 0 || t.vec_b[l]) && (na & 31) == 0 && (K & 31) == 0;
+      uint32_t dsto[MAXC], srco[MAXC], sel = 0;           // sel: 2 bits per chunk (0 dz, 1 ina, 2 inb, 3 none)
+#pragma unroll
+      for (int i = 0; i < MAXC; ++i) {
+        const int idx = threadIdx.x + i * DW_PROD;
+        dsto[i] = srco[i] = 0;
+        uint32_t sl = 3;
+        if (idx < per_sub) {
+          const bool isB = idx >= 32 * chA;
+          const int j = isB ? idx - 32 * chA : idx;
+          const int ch = isB ? chB : chA;
+          const int r = j / ch, cc = j % ch, col = cc * 4;
+          const uint32_t c16 = (uint32_t)cc & 7u;
+          dsto[i] = (isB ? DW_OPER : 0u) + (uint32_t)(cc >> 3) * DW_BLK + (uint32_t)r * 128u +
+                    ((((c16 >> 1) ^ ((uint32_t)r & 3u)) << 5) | ((c16 & 1u) << 4));
+          if (!isB) { sl = 0; srco[i] = (uint32_t)(r * na + col); }
+          else if (col < t.ka[l]) { sl = 1; srco[i] = (uint32_t)(r * t.lda[l] + col); }
+          else { sl = 2; srco[i] = (uint32_t)(r * t.ldb[l] + (col - t.ka[l])); }
+        }
+        sel |= sl << (2 * i);
+      }
       auto issue = [&](int sidx) {
         const uint32_t gi = g + (uint32_t)sidx, st = gi % DW_STAGES;
         if (gi >= DW_STAGES) mbar_wait(bar_empty + 8 * st, (gi / DW_STAGES - 1) & 1);
         const int rbase = ((ib - l * t.T) + (sidx >> 2)) * 128 + (sidx & 3) * 32;
         const uint32_t sbase = base + st * DW_STAGE;
+        if (fast && rbase + 32 <= t.M) {
+          const float* s0 = t.dz[l] + (size_t)rbase * na;
+          const float* s1 = t.ina[l] + (size_t)rbase * t.lda[l];
+          const float* s2 = t.kb[l] ? t.inb[l] + (size_t)rbase * t.ldb[l] : s1;
+#pragma unroll
+          for (int i = 0; i < MAXC; ++i) {
+            const uint32_t sl = (sel >> (2 * i)) & 3u;
+            if (sl != 3u) cp_async16(sbase + dsto[i], (sl == 0 ? s0 : (sl == 1 ? s1 : s2)) + srco[i]);
+          }
+          asm volatile("cp.async.commit_group;" ::: "memory");
+          return;
+        }
         for (int idx = threadIdx.x; idx < per_sub; idx += DW_PROD) {
           const bool isB = idx >= 32 * chA;
           const int j = isB ? idx - 32 * chA : idx;
@@ -660,7 +698,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) fn_dw_kernel(FnDwArgs t) {
           const uint32_t sa = base + st * DW_STAGE, sb = sa + DW_OPER;
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
-            for (int mh = 0; mh < nmh; ++mh)
+            for (int mh = 0; mh < nmh && !t.debug_nomma; ++mh)
               umma_tf32_ss(tmem + (uint32_t)mh * 256u, desc_mn_tf32(sa + (uint32_t)mh * 4u * DW_BLK + (uint32_t)ks * 1024u),
                            desc_mn_tf32(sb + (uint32_t)ks * 1024u), idesc, (uint32_t)(s | ks));
           umma_commit(bar_empty + 8 * st);
@@ -766,7 +804,15 @@ int launch_fn_dw(FnDwArgs t, cudaStream_t stream) {
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int items = 3 * t.T;
-  const int grid = items < sms ? items : sms;
+  // Every CTA ends with a ~64k-element atomic flush of its accumulators; the row streaming it does first shrinks
+  // with the number of CTAs.  ~6 items (128-row tiles) per CTA balances the two at B*N ~ 10^4 rows; large
+  // problems use every SM.
+  static const int per_cta = getenv("MPG_DW_ITEMS") ? atoi(getenv("MPG_DW_ITEMS")) : 1;
+  t.debug_nomma = getenv("MPG_DW_NOMMA") != nullptr;
+  int grid = items / (per_cta > 0 ? per_cta : 1);
+  if (grid < 16) grid = 16;
+  if (grid > sms) grid = sms;
+  if (grid > items) grid = items;
   MPG_CUDA(cudaFuncSetAttribute(fn_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DW_SMEM));
   fn_dw_kernel<<<grid, DW_THREADS, DW_SMEM, stream>>>(t);
   MPG_LAUNCH_CHECK();

@@ -62,6 +62,51 @@ __global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __rest
   }
 }
 
+// ---- particle order: real particles first inside every jet (stable) ----------------------------------
+// pos[b, i] = new index of particle i: its rank among the real ones (mask != 0) if real, else n_real + its rank
+// among the padded ones.  One warp per jet; also writes the permuted mask.  The message-passing layers are
+// permutation-equivariant over particles, so this is a layout choice (model.py: MPNet.forward).
+__global__ void particle_order_kernel(const float* __restrict__ mask, int B, int N, int* __restrict__ pos,
+                                      float* __restrict__ mask_sorted) {
+  const int jet = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (jet >= B) return;
+  const float* m = mask + (size_t)jet * N;
+  int n_real = 0;
+  for (int i0 = 0; i0 < N; i0 += 32) {
+    const bool real = i0 + lane < N && m[i0 + lane] != 0.f;
+    n_real += __popc(__ballot_sync(0xffffffffu, real));
+  }
+  int seen_real = 0, seen_pad = 0;
+  for (int i0 = 0; i0 < N; i0 += 32) {
+    const int i = i0 + lane;
+    const bool in = i < N;
+    const float mv = in ? m[i] : 0.f;
+    const bool real = in && mv != 0.f;
+    const uint32_t br = __ballot_sync(0xffffffffu, real), bp = __ballot_sync(0xffffffffu, in && !real);
+    const uint32_t below = (1u << lane) - 1u;
+    if (in) {
+      const int p = real ? seen_real + __popc(br & below) : n_real + seen_pad + __popc(bp & below);
+      pos[(size_t)jet * N + i] = p;
+      mask_sorted[(size_t)jet * N + p] = mv;
+    }
+    seen_real += __popc(br);
+    seen_pad += __popc(bp);
+  }
+}
+
+// scatter (mode 0): dst[b, pos[b,i], :] = src[b, i, :];  gather (mode 1): dst[b, i, :] = src[b, pos[b,i], :]
+__global__ void permute_rows_kernel(const float* __restrict__ src, int lds, float* __restrict__ dst, int ldd,
+                                    const int* __restrict__ pos, int N, int F, size_t total, int mode) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const size_t r = idx / F;
+  const int f = (int)(idx % F);
+  const size_t jet0 = (r / N) * N;
+  const size_t pr = jet0 + pos[r];
+  if (mode == 0) dst[pr * ldd + f] = src[r * lds + f];
+  else dst[r * ldd + f] = src[pr * lds + f];
+}
+
 // ---- generator tail: out[..., :Fo] = act(h), out[..., Fo] = mask - 0.5 (model.py:535-536,752) ------
 __global__ void gen_tail_fwd_kernel(const float* __restrict__ h, const float* __restrict__ mask,
                                     float* __restrict__ out, int rows, int Fo, int act) {
@@ -259,6 +304,20 @@ int launch_gen_tail_bwd(const float* dout, const float* out, float* dh, int rows
   const size_t n = (size_t)rows * Fo;
   if (n == 0) return 0;
   gen_tail_bwd_kernel<<<cdiv(n, 256), 256, 0, s>>>(dout, out, dh, rows, Fo, ldo, act);
+  MPG_LAUNCH_CHECK();
+  return 0;
+}
+int launch_particle_order(const float* mask, int B, int N, int* pos, float* mask_sorted, cudaStream_t s) {
+  if (B <= 0 || N <= 0) return 0;
+  particle_order_kernel<<<cdiv(B, 8), 256, 0, s>>>(mask, B, N, pos, mask_sorted);
+  MPG_LAUNCH_CHECK();
+  return 0;
+}
+int launch_permute_rows(const float* src, int lds, float* dst, int ldd, const int* pos, int B, int N, int F, int mode,
+                        cudaStream_t s) {
+  const size_t total = (size_t)B * N * F;
+  if (total == 0) return 0;
+  permute_rows_kernel<<<cdiv(total, 256), 256, 0, s>>>(src, lds, dst, ldd, pos, N, F, total, mode);
   MPG_LAUNCH_CHECK();
   return 0;
 }

@@ -7,6 +7,9 @@ int launch_act_bwd(const float* dy, const float* y, float* dz, int M, int N, int
 int launch_gen_tail_fwd(const float* h, const float* mask, float* out, int rows, int Fo, int act, cudaStream_t s);
 int launch_gen_tail_bwd(const float* dout, const float* out, float* dh, int rows, int Fo, int ldo, int act,
                         cudaStream_t s);
+int launch_particle_order(const float* mask, int B, int N, int* pos, float* mask_sorted, cudaStream_t s);
+int launch_permute_rows(const float* src, int lds, float* dst, int ldd, const int* pos, int B, int N, int F, int mode,
+                        cudaStream_t s);
 int launch_split_mask(const float* x, int ldx, int rows, float* mask, cudaStream_t s);
 int launch_pool_fwd(const float* h, const float* mask, float* out, int B, int N, int C, int mean, cudaStream_t s);
 int launch_pool_bwd(const float* dout, const float* mask, float* dh, int B, int N, int C, int mean, cudaStream_t s);

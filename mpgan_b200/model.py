@@ -259,16 +259,14 @@ class MPNet(nn.Module):
             # (fully connected, sum / mean aggregation), so this only changes the layout: a generated jet's real
             # particles are wherever its noise ranks put them, and a sender index that is padded in every jet of a
             # 128-particle tile is a (tile, sender) step the edge kernels drop.
-            idx = torch.argsort(mask[:, :, 0], dim=1, descending=True, stable=True).unsqueeze(2)
-            x = torch.gather(x, 1, idx.expand(-1, -1, x.shape[2]))
-            mask = torch.gather(mask, 1, idx)
+            idx, mask_sorted = ops.particle_order(mask)       # idx[b, i] = new position of particle i
+            x = ops.permute_rows(x, idx, 0)
+            mask_orig, mask = mask, mask_sorted
         for i in range(self.mp_iters):
             x = self.mp_layers[i](x, use_mask, mask, labels, num_jet_particles)
         if idx is not None and not self._pool_is_order_free():
-            # back to the caller's particle order: out[b, idx[b, k]] = x[b, k]
-            ix = idx.expand(-1, -1, x.shape[2])
-            x = torch.empty_like(x).scatter(1, ix, x)
-            mask = torch.empty_like(mask).scatter(1, idx, mask)
+            x = ops.permute_rows(x, idx, 1)                    # back to the caller's particle order
+            mask = mask_orig
         x = self._post_mp(x, labels, use_mask, mask, num_jet_particles)
         return self._tail(x, mask)
 

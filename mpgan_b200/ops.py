@@ -385,6 +385,50 @@ def rank_mask(x, labels, num_particles: int):
     return mask
 
 
+def particle_order(mask):
+    """(pos int32 [B, N], mask in the new order [B, N, 1]): real particles (mask != 0) first, stable."""
+    L = _lib.lib()
+    B, N = mask.shape[0], mask.shape[1]
+    m = mask.detach().reshape(B, N).contiguous()
+    pos = torch.empty(B, N, device=mask.device, dtype=torch.int32)
+    ms = torch.empty(B, N, 1, device=mask.device, dtype=torch.float32)
+    _lib.check(L.mpg_particle_order(_lib.ptr(m), B, N, _lib.ptr(pos), _lib.ptr(ms), _lib.stream()),
+               "mpg_particle_order")
+    return pos, ms
+
+
+class PermuteRowsFn(torch.autograd.Function):
+    """mode 0: out[b, pos[b,i]] = x[b, i];  mode 1: out[b, i] = x[b, pos[b,i]]  (adjoint of each other)."""
+
+    @staticmethod
+    def forward(ctx, x, pos, mode):
+        L = _lib.lib()
+        x3, ldx = _rows(x)
+        B, N, F = x3.shape
+        out = torch.empty(B, N, F, device=x.device, dtype=torch.float32)
+        _lib.check(L.mpg_permute_rows(_lib.ptr(x3), ldx, _lib.ptr(out), F, _lib.ptr(pos), B, N, F, int(mode),
+                                      _lib.stream()), "mpg_permute_rows")
+        ctx.save_for_backward(pos)
+        ctx.mode = int(mode)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        L = _lib.lib()
+        (pos,) = ctx.saved_tensors
+        dout = dout.contiguous()
+        B, N, F = dout.shape
+        dx = torch.empty_like(dout)
+        _lib.check(L.mpg_permute_rows(_lib.ptr(dout), F, _lib.ptr(dx), F, _lib.ptr(pos), B, N, F, 1 - ctx.mode,
+                                      _lib.stream()), "mpg_permute_rows")
+        return dx, None, None
+
+
+def permute_rows(x, pos, mode: int):
+    return PermuteRowsFn.apply(x, pos, mode)
+
+
 def split_mask(x):
     """mask = x[..., -1:] + 0.5 (fp32 multiplier) for the discriminator input."""
     L = _lib.lib()
