@@ -138,6 +138,12 @@ int mpg_sn_fwd(const float* w_bar, float* u, float* v, float* w_out, float* sigm
 int mpg_sn_bwd(const float* dw, const float* w_bar, const float* u, const float* v, const float* sigma,
                float* dw_bar, int H, int W, void* stream);
 
+/* ---- least-squares GAN loss (train.py:357-358,369-370,378 for D; :467,472 for G): MSELoss against constant
+ * targets.  loss = mean_{i<n0}(d_i - t0)^2 + mean_{i>=n0}(d_i - t1)^2 (second term absent when n0 == n), d = the
+ * discriminator outputs [n]; bwd: dd_i = *gout * dloss/dd_i (gout: device scalar). */
+int mpg_ls_loss_fwd(const float* d, int n, int n0, float t0, float t1, float* loss, void* stream);
+int mpg_ls_loss_bwd(const float* d, const float* gout, int n, int n0, float t0, float t1, float* dd, void* stream);
+
 /* ---- optimizer: torch.optim.RMSprop(alpha, eps) on a flat buffer; g is scaled by gscale first ------ */
 int mpg_rmsprop(float* p, const float* g, float* sq, size_t n, float lr, float alpha, float eps, float gscale,
                 void* stream);

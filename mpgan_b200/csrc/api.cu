@@ -428,6 +428,14 @@ int mpg_permute_rows(const float* src, int lds, float* dst, int ldd, const int* 
   MPG_CHECK(mode == 0 || mode == 1, "permute_rows: mode must be 0 (scatter) or 1 (gather)");
   return launch_permute_rows(src, lds, dst, ldd, pos, B, N, F, mode, (cudaStream_t)stream);
 }
+int mpg_ls_loss_fwd(const float* d, int n, int n0, float t0, float t1, float* loss, void* stream) {
+  MPG_CHECK(n0 >= 1 && n0 <= n, "ls_loss: need 1 <= n0 <= n (n0 = %d, n = %d)", n0, n);
+  return launch_ls_loss(d, nullptr, n, n0, t0, t1, loss, false, (cudaStream_t)stream);
+}
+int mpg_ls_loss_bwd(const float* d, const float* gout, int n, int n0, float t0, float t1, float* dd, void* stream) {
+  MPG_CHECK(n0 >= 1 && n0 <= n, "ls_loss: need 1 <= n0 <= n (n0 = %d, n = %d)", n0, n);
+  return launch_ls_loss(d, gout, n, n0, t0, t1, dd, true, (cudaStream_t)stream);
+}
 int mpg_split_mask(const float* x, int ldx, int rows, float* mask, void* stream) {
   return launch_split_mask(x, ldx, rows, mask, (cudaStream_t)stream);
 }

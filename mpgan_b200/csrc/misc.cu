@@ -174,6 +174,34 @@ __global__ void pool_bwd_kernel(const float* __restrict__ dout, const float* __r
   }
 }
 
+// ---- least-squares GAN loss (train.py:357-358,369-370,378,467,472: MSELoss against 1 / 0 targets) --------
+// loss = mean_{i < n0} (d_i - t0)^2 + [n0 < n] mean_{i >= n0} (d_i - t1)^2: one CTA, one launch instead of the
+// sub / pow / mean / add chain (and its autograd mirror) on [B, 1] tensors.
+__global__ void ls_loss_fwd_kernel(const float* __restrict__ d, int n, int n0, float t0, float t1, float* __restrict__ loss) {
+  __shared__ float red[2][8];
+  float s0 = 0.f, s1 = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float e = d[i] - (i < n0 ? t0 : t1);
+    if (i < n0) s0 += e * e; else s1 += e * e;
+  }
+  s0 = warp_sum(s0);
+  s1 = warp_sum(s1);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s0; red[1][threadIdx.x >> 5] = s1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += red[0][w]; b += red[1][w]; }
+    *loss = a / (float)n0 + (n > n0 ? b / (float)(n - n0) : 0.f);
+  }
+}
+__global__ void ls_loss_bwd_kernel(const float* __restrict__ d, const float* __restrict__ gout, int n, int n0, float t0,
+                                   float t1, float* __restrict__ dd) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float g = *gout;
+  dd[i] = i < n0 ? g * 2.f * (d[i] - t0) / (float)n0 : g * 2.f * (d[i] - t1) / (float)(n - n0);
+}
+
 // ---- elementwise unary with backward from output ---------------------------------------------------
 __global__ void unary_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n, int act) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -318,6 +346,14 @@ int launch_permute_rows(const float* src, int lds, float* dst, int ldd, const in
   const size_t total = (size_t)B * N * F;
   if (total == 0) return 0;
   permute_rows_kernel<<<cdiv(total, 256), 256, 0, s>>>(src, lds, dst, ldd, pos, N, F, total, mode);
+  MPG_LAUNCH_CHECK();
+  return 0;
+}
+int launch_ls_loss(const float* d, const float* gout, int n, int n0, float t0, float t1, float* out, bool bwd,
+                   cudaStream_t s) {
+  if (n <= 0) return 0;
+  if (bwd) ls_loss_bwd_kernel<<<cdiv(n, 256), 256, 0, s>>>(d, gout, n, n0, t0, t1, out);
+  else ls_loss_fwd_kernel<<<1, 256, 0, s>>>(d, n, n0, t0, t1, out);
   MPG_LAUNCH_CHECK();
   return 0;
 }

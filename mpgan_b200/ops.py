@@ -429,6 +429,37 @@ def permute_rows(x, pos, mode: int):
     return PermuteRowsFn.apply(x, pos, mode)
 
 
+class LSLossFn(torch.autograd.Function):
+    """mean((d[:n0] - t0)^2) + mean((d[n0:] - t1)^2): the least-squares GAN losses of train.py:357-378,467-472."""
+
+    @staticmethod
+    def forward(ctx, d, n0, t0, t1):
+        L = _lib.lib()
+        d1 = d.reshape(-1).contiguous()
+        loss = torch.empty((), device=d.device, dtype=torch.float32)
+        _lib.check(L.mpg_ls_loss_fwd(_lib.ptr(d1), d1.numel(), int(n0), float(t0), float(t1), _lib.ptr(loss),
+                                     _lib.stream()), "mpg_ls_loss_fwd")
+        ctx.save_for_backward(d1)
+        ctx.cfg = (int(n0), float(t0), float(t1), d.shape)
+        return loss
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        L = _lib.lib()
+        (d1,) = ctx.saved_tensors
+        n0, t0, t1, shape = ctx.cfg
+        dd = torch.empty_like(d1)
+        g = gout.contiguous().float()
+        _lib.check(L.mpg_ls_loss_bwd(_lib.ptr(d1), _lib.ptr(g), d1.numel(), n0, t0, t1, _lib.ptr(dd), _lib.stream()),
+                   "mpg_ls_loss_bwd")
+        return dd.view(shape), None, None, None
+
+
+def ls_loss(d, n_first: int, target_first: float, target_rest: float = 0.0):
+    return LSLossFn.apply(d, n_first, target_first, target_rest)
+
+
 def split_mask(x):
     """mask = x[..., -1:] + 0.5 (fp32 multiplier) for the discriminator input."""
     L = _lib.lib()

@@ -119,12 +119,11 @@ class GANTrainer:
             # (train.py:425,446) while every kernel sees twice the rows per launch
             B = data.shape[0]
             d_both = self.D(torch.cat((data, fake), 0), torch.cat((labels, labels), 0))
-            d_real, d_fake = d_both[:B], d_both[B:]
         else:
-            d_real = self.D(data, labels)
-            d_fake = self.D(fake, labels)
-        # least squares: real -> 1, fake -> 0 (train.py:357-358, 369-370, 378)
-        loss = ((d_real - 1.0) ** 2).mean() + (d_fake ** 2).mean()
+            B = data.shape[0]
+            d_both = torch.cat((self.D(data, labels), self.D(fake, labels)), 0)
+        # least squares: real -> 1, fake -> 0 (train.py:357-358, 369-370, 378), one kernel
+        loss = ops.ls_loss(d_both, B, 1.0, 0.0)
         loss.backward()
         self.optD.step(self._allreduce(self.fpD))
         return loss.detach()
@@ -138,7 +137,7 @@ class GANTrainer:
             p.requires_grad_(False)
         try:
             d_fake = self.D(fake, labels)  # D stays in train mode: its dropout is active (train.py:419,494)
-            loss = ((d_fake - 1.0) ** 2).mean()  # train.py:467,472
+            loss = ops.ls_loss(d_fake, d_fake.shape[0], 1.0)  # train.py:467,472
             loss.backward()
         finally:
             for p in self.fpD.params:

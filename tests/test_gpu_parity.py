@@ -505,3 +505,18 @@ def test_particle_sort_is_layout_only(golden):
     for which in (2, 3):
         for k in res[0][which]:
             close(res[1][which][k], res[0][which][k], 1e-3, f"grad {k}")
+
+
+def test_ls_loss_matches_torch():
+    """Fused least-squares GAN loss (train.py:357-378, 467-472) against the torch expression, value and gradient."""
+    from mpgan_b200 import ops
+    g = torch.Generator().manual_seed(41)
+    for n, n0, t0, t1 in ((512, 256, 1.0, 0.0), (37, 37, 1.0, 1.0), (300, 100, 1.0, 0.0)):
+        d = torch.rand(n, 1, generator=g).cuda().requires_grad_(True)
+        loss = ops.ls_loss(d, n0, t0, t1)
+        (loss * 3.0).backward()
+        dr = d.detach().clone().requires_grad_(True)
+        ref = ((dr[:n0] - t0) ** 2).mean() + (((dr[n0:] - t1) ** 2).mean() if n0 < n else 0.0)
+        (ref * 3.0).backward()
+        assert abs(float(loss) - float(ref)) <= 1e-6 * max(1.0, abs(float(ref)))
+        close(d.grad, dr.grad, 1e-6, "ls_loss grad")
