@@ -262,6 +262,7 @@ def run_ours(args, wl):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the ONE JSON line only
         dist.init_process_group("nccl", device_id=dev)
     N, B, kind = wl["N"], wl["B"], wl["kind"]
     L = _lib.lib()
@@ -426,12 +427,14 @@ def run_ours(args, wl):
                     "algorithmic_bytes_per_jet": gb, "peak_source": pk["src"] + " HBM copy"}
         # CPU baseline: bounded sample of the same workload on the host cores
         try:
+            if world > 1:   # the CPU baseline is reported at N = 1 only (the other ranks would idle behind it)
+                raise RuntimeError("reported by the 1-GPU run only")
             bs = cpu_sample_size(wl)
             sec, cores = cpu_time(wl, N, bs, 2, 1, kind)
             cpu = {"value": bs / sec, "unit": "jets/s", "cores": cores, "kind": "port",
                    "sample": f"{bs} jets/step x 2 steps (oracle port of the reference fp32 PyTorch path)"}
         except Exception as e:  # pragma: no cover
-            cpu = {"value": None, "unit": "jets/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+            cpu = {"value": None, "unit": "jets/s", "cores": 0, "kind": "port", "sample": f"not measured: {e}"}
         line = {
             "metric": metric_name(wl), "value": value, "unit": "jets/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -455,8 +458,15 @@ def run_ours(args, wl):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        # every rank stays until rank 0 has printed (a rank that leaves early takes the job down with it), then:
         # NCCL communicators referenced by a captured CUDA graph do not tear down reliably
         # (destroy_process_group hung here): everything is measured and printed, so leave at once
+        sys.stdout.flush()
+        try:
+            dist.barrier()
+            torch.cuda.synchronize()
+        except Exception:
+            pass
         sys.stdout.flush()
         sys.stderr.flush()
         os._exit(0)
