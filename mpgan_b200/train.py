@@ -89,6 +89,10 @@ class GANTrainer:
         if self.world > 1:  # identical weights on every rank (reference: DataParallel replicate)
             dist.broadcast(self.fpG.flat, 0, group=self.pg)
             dist.broadcast(self.fpD.flat, 0, group=self.pg)
+        # step(): D's gradient all-reduce + RMSprop run on a side stream under train_G's generator forward (which
+        # does not read D); train_G joins before its D forward.  Captured as a parallel branch of the step's graph.
+        self._comm_stream = None
+        self._comm_pending = False
 
     # -- helpers ---------------------------------------------------------------------------------
     def _allreduce(self, fp: FlatParams) -> float:
@@ -107,7 +111,13 @@ class GANTrainer:
         return self.G(noise, labels)
 
     # -- train.py:398-462 ------------------------------------------------------------------------
-    def train_D(self, data, labels, noise=None):
+    def _join_comm(self):
+        if self._comm_pending:
+            torch.cuda.current_stream().wait_stream(self._comm_stream)
+            self._comm_pending = False
+
+    def train_D(self, data, labels, noise=None, overlap_update=False):
+        self._join_comm()
         self.D.train()
         self.fpD.zero_grad()
         self.G.eval()
@@ -125,7 +135,15 @@ class GANTrainer:
         # least squares: real -> 1, fake -> 0 (train.py:357-358, 369-370, 378), one kernel
         loss = ops.ls_loss(d_both, B, 1.0, 0.0)
         loss.backward()
-        self.optD.step(self._allreduce(self.fpD))
+        if overlap_update and self.world > 1 and data.is_cuda:
+            if self._comm_stream is None:
+                self._comm_stream = torch.cuda.Stream(device=data.device)
+            self._comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._comm_stream):
+                self.optD.step(self._allreduce(self.fpD))
+            self._comm_pending = True
+        else:
+            self.optD.step(self._allreduce(self.fpD))
         return loss.detach()
 
     # -- train.py:479-523 ------------------------------------------------------------------------
@@ -133,6 +151,7 @@ class GANTrainer:
         self.G.train()
         self.fpG.zero_grad()
         fake = self.gen(batch_size or labels.shape[0], labels, noise)
+        self._join_comm()   # D's update (side stream) must have landed before D runs
         for p in self.fpD.params:
             p.requires_grad_(False)
         try:
@@ -149,7 +168,7 @@ class GANTrainer:
         """One critic + one generator update (train.py:841-878 with num_critic = num_gen = 1)."""
         if self.sort_by_count:
             data, labels = sort_by_count(data, labels)
-        return self.train_D(data, labels), self.train_G(labels)
+        return self.train_D(data, labels, overlap_update=True), self.train_G(labels)
 
     # -- whole-step CUDA graph (SURVEY 8f rank 1) ---------------------------------------------------
     def capture(self, data, labels, warmup=3):
