@@ -286,6 +286,8 @@ int mpg_fn_bwd(const float* dout, const float* y0, const float* y1, const float*
     FnDwArgs d;
     memset(&d, 0, sizeof(d));
     d.M = M;
+    d.nslots = 3;
+    d.items_per_cta = 1;
     // slot order = processing order: the two big layers first, the narrow last layer at the end
     d.dz[0] = dz1; d.na[0] = H2; d.ina[0] = y0; d.lda[0] = H1; d.ka[0] = H1; d.dw[0] = dw1; d.lddw[0] = H1;
     d.dz[1] = dz0; d.na[1] = H1; d.ina[1] = a; d.lda[1] = lda; d.ka[1] = Ka; d.inb[1] = b; d.ldb[1] = ldb; d.kb[1] = Kb;

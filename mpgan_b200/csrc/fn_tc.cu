@@ -555,7 +555,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) fn_dw_kernel(FnDwArgs t) {
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  const int items = 3 * t.T;
+  const int items = t.nslots * t.T;
   const int i0 = (int)((long long)items * blockIdx.x / gridDim.x);
   const int i1 = (int)((long long)items * (blockIdx.x + 1) / gridDim.x);
   uint32_t g = 0;       // sub-tiles streamed so far (ring position), same sequence in every role
@@ -792,9 +792,10 @@ int launch_fn_dw(FnDwArgs t, cudaStream_t stream) {
   if (t.M <= 0) return 0;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   t.T = cdiv(t.M, 128);
-  for (int l = 0; l < 3; ++l) {
+  MPG_CHECK(t.nslots >= 1 && t.nslots <= 3, "fn_dw: 1..3 products per launch");
+  for (int l = 0; l < t.nslots; ++l) {
     const int K = t.ka[l] + t.kb[l];
-    MPG_CHECK(t.na[l] >= 1 && t.na[l] <= 256 && K >= 1 && K <= 256, "fn_dw: layer %d shape [%d x %d] unsupported", l,
+    MPG_CHECK(t.na[l] >= 1 && t.na[l] <= 256 && K >= 1 && K <= 256, "fn_dw: product %d shape [%d x %d] unsupported", l,
               t.na[l], K);
     t.vec_dz[l] = (t.na[l] % 4 == 0) && al16(t.dz[l]);
     t.vec_a[l] = (t.lda[l] % 4 == 0) && (t.ka[l] % 4 == 0) && al16(t.ina[l]);
@@ -803,16 +804,15 @@ int launch_fn_dw(FnDwArgs t, cudaStream_t stream) {
   }
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int items = 3 * t.T;
-  // Every CTA ends with a ~64k-element atomic flush of its accumulators; the row streaming it does first shrinks
-  // with the number of CTAs.  ~6 items (128-row tiles) per CTA balances the two at B*N ~ 10^4 rows; large
-  // problems use every SM.
-  static const int per_cta = getenv("MPG_DW_ITEMS") ? atoi(getenv("MPG_DW_ITEMS")) : 1;
-  t.debug_nomma = getenv("MPG_DW_NOMMA") != nullptr;
-  int grid = items / (per_cta > 0 ? per_cta : 1);
-  if (grid < 16) grid = 16;
+  // The kernel is bound by the per-SM rate at which rows stream in (measured: time ~ 1 / CTAs), so the wide node
+  // network products take every SM; items_per_cta > 1 trades that against the per-CTA atomic flush for narrow
+  // products.
+  const int items = t.nslots * t.T;
+  int grid = items / (t.items_per_cta > 0 ? t.items_per_cta : 1);
+  if (grid < 1) grid = 1;
   if (grid > sms) grid = sms;
   if (grid > items) grid = items;
+  t.debug_nomma = 0;
   MPG_CUDA(cudaFuncSetAttribute(fn_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DW_SMEM));
   fn_dw_kernel<<<grid, DW_THREADS, DW_SMEM, stream>>>(t);
   MPG_LAUNCH_CHECK();

@@ -41,9 +41,11 @@ size_t fn_tc_workspace_bytes(int Ka, int Kb, int H1, int H2, int NO);
 int launch_fn_tc(FnTcArgs t, bool bwd, const float* w0, const float* w1, const float* w2, int H1, int H2, int NO,
                  void* ws, cudaStream_t stream);
 
-// weight gradients dW_l += dz_l^T [ina_l | inb_l] for the three layers in one launch (fn_dw_kernel)
+// weight gradients dW_l += dz_l^T [ina_l | inb_l] for up to three products over the same M rows in one launch
+// (fn_dw_kernel): the node network's three layers, or the two halves of the factorised first edge layer
 struct FnDwArgs {
   int M, T;                        // rows; 128-row tiles (filled by launch_fn_dw)
+  int nslots, items_per_cta;       // products in this launch (1..3); 128-row items a CTA should own (>= 1)
   const float* dz[3]; int na[3];   // dz_l [M, na] contiguous
   const float* ina[3]; int lda[3], ka[3];
   const float* inb[3]; int ldb[3], kb[3];
