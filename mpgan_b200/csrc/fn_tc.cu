@@ -17,8 +17,6 @@
 // (TMEM lane quarter x column quarter), one MMA-issuer warp, one loader warp.  TMEM: D0 [0,256) D1 [256,512),
 // D2 over D0.  Weight gradients (dz^T y) stay on the TF32 mma.sync GEMM (gemm.cu), launched by the caller on a
 // side stream.
-#include <stdlib.h>
-
 #include "fn_tc.cuh"
 #include "edge.cuh"      // EdgeArgs (referenced by the shared tcgen05 header)
 
@@ -698,7 +696,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) fn_dw_kernel(FnDwArgs t) {
           const uint32_t sa = base + st * DW_STAGE, sb = sa + DW_OPER;
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
-            for (int mh = 0; mh < nmh && !t.debug_nomma; ++mh)
+            for (int mh = 0; mh < nmh; ++mh)
               umma_tf32_ss(tmem + (uint32_t)mh * 256u, desc_mn_tf32(sa + (uint32_t)mh * 4u * DW_BLK + (uint32_t)ks * 1024u),
                            desc_mn_tf32(sb + (uint32_t)ks * 1024u), idesc, (uint32_t)(s | ks));
           umma_commit(bar_empty + 8 * st);
@@ -812,7 +810,6 @@ int launch_fn_dw(FnDwArgs t, cudaStream_t stream) {
   if (grid < 1) grid = 1;
   if (grid > sms) grid = sms;
   if (grid > items) grid = items;
-  t.debug_nomma = 0;
   MPG_CUDA(cudaFuncSetAttribute(fn_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DW_SMEM));
   fn_dw_kernel<<<grid, DW_THREADS, DW_SMEM, stream>>>(t);
   MPG_LAUNCH_CHECK();

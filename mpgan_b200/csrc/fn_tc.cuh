@@ -51,7 +51,6 @@ struct FnDwArgs {
   const float* inb[3]; int ldb[3], kb[3];
   float* dw[3]; int lddw[3];       // dW_l [na, ka + kb], row stride lddw (accumulated)
   int vec_dz[3], vec_a[3], vec_b[3], vec_dw[3];   // filled by launch_fn_dw
-  int debug_nomma;                 // experiment switch: stream the operands but issue no MMA
 };
 int launch_fn_dw(FnDwArgs t, cudaStream_t stream);
 

@@ -48,15 +48,60 @@ def test_library_has_no_torch_dependency(libpath):
     assert "torch" not in out and "c10" not in out, out
 
 
-def test_sass_is_blackwell_native(libpath):
-    """The edge kernels must be tcgen05 / TMEM / bulk-async code, not recompiled mma.sync."""
+_SASS = {}
+
+
+def _sass(libpath):
+    """SASS of the library (one cuobjdump run per session)."""
     cuobjdump = "/usr/local/cuda/bin/cuobjdump"
     if not os.path.exists(cuobjdump):
         pytest.skip("cuobjdump not available")
-    sass = subprocess.run([cuobjdump, "-sass", libpath], capture_output=True, text=True).stdout
+    if libpath not in _SASS:
+        _SASS[libpath] = subprocess.run([cuobjdump, "-sass", libpath], capture_output=True, text=True).stdout
+    return _SASS[libpath]
+
+
+def test_sass_is_blackwell_native(libpath):
+    """The edge kernels must be tcgen05 / TMEM / bulk-async code, not recompiled mma.sync."""
+    sass = _sass(libpath)
     assert "UTCHMMA" in sass, "no tcgen05.mma in SASS"
     assert "LDTM" in sass, "no tcgen05.ld in SASS"
     assert "UBLKCP" in sass, "no bulk-async (TMA) copy in SASS"
+
+
+def test_node_network_kernels_are_tcgen05(libpath):
+    """The fused node-network kernels (fn_tc.cu) issue tcgen05.mma / tcgen05.ld / tcgen05.st themselves."""
+    sass = _sass(libpath)
+    cur, seen = None, {}
+    for line in sass.splitlines():
+        if "Function :" in line:
+            cur = line.split("Function :")[1].strip()
+        elif cur is not None:
+            for op in ("UTCHMMA", "LDTM", "STTM", "UBLKCP", "LDGSTS"):
+                if op in line:
+                    seen.setdefault(cur, set()).add(op)
+    chain = [k for k in seen if "fn_tc_kernel" in k]
+    dw = [k for k in seen if "fn_dw_kernel" in k]
+    assert len(chain) == 2 and len(dw) == 1, (chain, dw)
+    for k in chain:   # MMA, accumulator loads, in-place TMEM write-back of the next A operand, bulk weight copies
+        assert {"UTCHMMA", "LDTM", "STTM", "UBLKCP"} <= seen[k], (k, seen[k])
+    assert {"UTCHMMA", "LDTM", "LDGSTS"} <= seen[dw[0]], seen[dw[0]]   # cp.async staged MN-major operands
+
+
+def test_workspace_queries_and_support_matrix():
+    """Host-only entry points: no GPU needed."""
+    from mpgan_b200 import _lib
+    L = _lib.lib()
+    fwd = L.mpg_edge_fwd_workspace_bytes(256, 30, 32, 96, 160, 192)
+    full = L.mpg_edge_workspace_bytes(256, 30, 32, 96, 160, 192)
+    assert 0 < fwd < full
+    assert L.mpg_fn_supported(192, 32, 256, 256, 32, 0.5) == 1      # G layers, D layer 1
+    assert L.mpg_fn_supported(192, 3, 256, 256, 32, 0.5) == 1       # D layer 0
+    assert L.mpg_fn_supported(192, 32, 256, 256, 3, 0.0) == 1       # G's last layer
+    assert L.mpg_fn_supported(192, 32, 256, 256, 32, 0.3) == 0      # other dropout rates: per-layer kernels
+    assert L.mpg_fn_supported(192, 32, 200, 256, 32, 0.0) == 0      # other widths: per-layer kernels
+    assert L.mpg_fn_supported(192, 100, 256, 256, 32, 0.0) == 0     # cat input wider than 256
+    assert L.mpg_fn_workspace_bytes(192, 32, 256, 256, 32) >= (256 * 224 + 256 * 256 + 32 * 256) * 4
 
 
 def test_state_dict_layout_matches_reference(golden):
