@@ -135,14 +135,18 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------
 # CPU oracle arm
 # ----------------------------------------------------------------------------------------------------
-def cpu_step_time(N, B_sample, reps, warm=1, kind="train"):
-    """Times the CPU oracle port (oracle/mpgan_oracle.py) on B_sample jets; returns seconds/step."""
+def cpu_step_time(N, B_sample, reps, warm=1, kind="train", device="cpu"):
+    """Times the oracle port of the reference's eager PyTorch path (oracle/mpgan_oracle.py) on B_sample jets;
+    returns seconds/step.  device="cpu": the CPU baseline; device="cuda": the same eager fp32 PyTorch code on the
+    GPU (SURVEY 8d's like-for-like GPU baseline) -- a baseline leg either way, never the product path."""
     import torch
     from oracle import mpgan_oracle as mo
     torch.set_num_threads(os.cpu_count() or 1)
     gold = os.path.join(ROOT, "tests", "golden")
     sdG = torch.load(os.path.join(gold, "mp_g_weights.pt"), map_location="cpu")
     sdD = torch.load(os.path.join(gold, "mp_d_seed4_weights.pt"), map_location="cpu")
+    if device != "cpu":
+        return _gpu_eager_step_time(mo, sdG, sdD, N, B_sample, reps, warm, kind, device)
     cfgG = mo.NetCfg(num_particles=N, final_activation="tanh")
     cfgD = mo.NetCfg(num_particles=N, final_activation="sigmoid", dropout_p=0.5,
                      layers=[mo.EdgeCfg(all_ef=False), mo.EdgeCfg()])
@@ -167,6 +171,57 @@ def cpu_step_time(N, B_sample, reps, warm=1, kind="train"):
         mo.gd_step(pG, pD, cfgG, cfgD, data, labels, nd, ng, stateD=stD, stateG=stG)
         times.append(time.perf_counter() - t0)
     return sum(times[warm:]) / reps, torch.get_num_threads()
+
+
+def _gpu_eager_step_time(mo, sdG, sdD, N, B_sample, reps, warm, kind, device):
+    import torch
+    sdG = {k: v.to(device) for k, v in sdG.items()}
+    sdD = {k: v.to(device) for k, v in sdD.items()}
+    cfgG = mo.NetCfg(num_particles=N, final_activation="tanh")
+    cfgD = mo.NetCfg(num_particles=N, final_activation="sigmoid", dropout_p=0.5,
+                     layers=[mo.EdgeCfg(all_ef=False), mo.EdgeCfg()])
+    g = torch.Generator().manual_seed(4)
+    data, labels, _ = mo.synthetic_jets(B_sample, N, g)
+    data, labels = data.to(device), labels.to(device)
+    pG = {k: v.clone().requires_grad_(True) for k, v in sdG.items()}
+    pD = {k: v.clone().requires_grad_(True) for k, v in sdD.items()}
+    stD, stG = {}, {}
+    times = []
+    for i in range(warm + reps):
+        nd = torch.randn(B_sample, N, 32, device=device) * 0.2
+        ng = torch.randn(B_sample, N, 32, device=device) * 0.2
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        if kind == "gen":
+            with torch.no_grad():
+                mo.generator(sdG, nd, labels, cfgG)
+        else:
+            mo.gd_step(pG, pD, cfgG, cfgD, data, labels, nd, ng, stateD=stD, stateG=stG)
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+    return min(times[warm:]), 0
+
+
+def gpu_eager_baseline(wl, N, kind):
+    """Eager fp32 PyTorch (oracle port of the reference modules) on this GPU, fp32 and TF32-allowed matmuls."""
+    import torch
+    if wl.get("model") == "gapt":
+        return None
+    bs = {30: 256, 150: 8}.get(N, 8) if kind == "train" else {30: 256, 150: 16}.get(N, 16)
+    out = {"unit": "jets/s", "sample": f"{bs} jets/step, best of 3 (oracle port of the reference's eager PyTorch path on this GPU)"}
+    for name, tf32 in (("fp32", False), ("tf32_allowed", True)):
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        try:
+            sec, _ = cpu_step_time(N, bs, 3, 1, kind, device="cuda")
+            out[name] = bs / sec
+        except Exception as e:  # pragma: no cover
+            out[name] = None
+            out["error"] = str(e)[:200]
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = old
+            torch.cuda.empty_cache()
+    return out
 
 
 def cpu_gapt_step_time(N, B_sample, reps, warm=1, isab=False):
@@ -433,6 +488,9 @@ def run_ours(args, wl):
             sec, cores = cpu_time(wl, N, bs, 2, 1, kind)
             cpu = {"value": bs / sec, "unit": "jets/s", "cores": cores, "kind": "port",
                    "sample": f"{bs} jets/step x 2 steps (oracle port of the reference fp32 PyTorch path)"}
+            ge = gpu_eager_baseline(wl, N, kind)
+            if ge is not None:
+                cpu["gpu_eager"] = ge   # the same eager PyTorch code on this B200 (like-for-like GPU baseline)
         except Exception as e:  # pragma: no cover
             cpu = {"value": None, "unit": "jets/s", "cores": 0, "kind": "port", "sample": f"not measured: {e}"}
         line = {
