@@ -70,7 +70,7 @@ size_t edge_tc_scratch_bytes(int B, int N, int H0, int H1, int H2) {
 
 // the activation / gradient tiles hold X / (sd * sl) (dropout and leaky-relu scales), the weight images sd * sl * W
 static int tc_prepare(const EdgeArgs& a, void* persist, void* scratch, bool reuse, TcArgs& t, int* grid,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, float* zero_agg = nullptr) {
   MPG_CHECK(edge_tc_supported(a), "edge_tc: unsupported configuration");
   uint8_t* img = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(persist) + 255) & ~(uintptr_t)255);
   t.a = a;
@@ -91,9 +91,10 @@ static int tc_prepare(const EdgeArgs& a, void* persist, void* scratch, bool reus
   t.num_tiles = (int)((BN + TILE - 1) / TILE);
   if (!reuse) {   // images and work list of this (weights, mask): the backward of the same call finds them here
     const float s = (a.drop.p > 0.f ? 2.f : 1.f) * 0.5f * (1.f + a.alpha);
-    weight_image_kernel<<<cdiv(N1 * 128, 256), 256, 0, stream>>>(a.W1, a.b1, N1, K0, 128, s, img, nullptr);
-    MPG_LAUNCH_CHECK();
-    weight_image_kernel<<<cdiv(N2 * 192, 256), 256, 0, stream>>>(a.W2, a.b2, N2, N1, 192, s, img + W1_BYTES, reinterpret_cast<int*>(img + W1_BYTES + W2_BYTES));
+    const size_t agg_floats = zero_agg != nullptr ? (size_t)a.B * a.N * N2 : 0;   // N2 % 4 == 0; torch buffers are 16-byte aligned
+    MPG_CHECK((reinterpret_cast<uintptr_t>(zero_agg) & 15) == 0, "edge_tc: agg must be 16-byte aligned");
+    edge_prepare_kernel<<<cdiv(N1 * 128 + N2 * 192, 256), 256, 0, stream>>>(
+        a.W1, a.b1, a.W2, a.b2, s, img, img + W1_BYTES, total, reinterpret_cast<float4*>(zero_agg), agg_floats / 4);
     MPG_LAUNCH_CHECK();
     step_list_kernel<<<cdiv(t.num_tiles, 8), 256, 0, stream>>>(a.mask, a.B, a.N, t.num_tiles, const_cast<int2*>(t.steps), total);
     MPG_LAUNCH_CHECK();
@@ -108,8 +109,7 @@ static int tc_prepare(const EdgeArgs& a, void* persist, void* scratch, bool reus
 int launch_edge_tc_fwd(const EdgeArgs& a, void* persist, cudaStream_t stream) {
   TcArgs t;
   int grid = 1;
-  if (tc_prepare(a, persist, nullptr, false, t, &grid, stream)) return 1;
-  MPG_CUDA(cudaMemsetAsync(a.agg, 0, (size_t)a.B * a.N * N2 * sizeof(float), stream));
+  if (tc_prepare(a, persist, nullptr, false, t, &grid, stream, a.agg)) return 1;   // also zero-fills agg
   if (a.drop.p > 0.f) {
     MPG_CUDA(cudaFuncSetAttribute(edge_tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
     ProbeScope probe(1, stream);

@@ -321,6 +321,35 @@ __global__ void weight_image_kernel(const float* __restrict__ W, const float* __
 }
 
 
+// Both weight images of a call, the work-list counter and (forward) the zero fill of the aggregate the kernel
+// accumulates into with reductions: one launch instead of two image kernels and a memset node.
+__global__ void edge_prepare_kernel(const float* __restrict__ W1, const float* __restrict__ b1,
+                                    const float* __restrict__ W2, const float* __restrict__ b2, float scale,
+                                    uint8_t* __restrict__ img1, uint8_t* __restrict__ img2, int* __restrict__ total,
+                                    float4* __restrict__ agg4, size_t agg_n4) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx == 0) *total = 0;   // the work-list counter of the step_list_kernel that follows
+  constexpr int E1 = N1 * 128, E2 = N2 * 192;
+  if (idx < E1 + E2) {
+    const bool first = idx < E1;
+    const int j = first ? idx : idx - E1;
+    const int Kpad = first ? 128 : 192, K = first ? K0 : N1, Nout = first ? N1 : N2;
+    const float* W = first ? W1 : W2;
+    const float* bias = first ? b1 : b2;
+    uint8_t* img = first ? img1 : img2;
+    const int n = j / Kpad, k = j % Kpad;
+    float v = 0.f;
+    if (k < K) v = W[(size_t)n * K + k] * scale;
+    else if (k == K) v = bias[n];
+    else if (k == K + 1) v = bias[n] - __bfloat162float(__float2bfloat16_rn(bias[n]));
+    const uint32_t off = (uint32_t)(k >> 6) * (uint32_t)Nout * 128u + (uint32_t)n * 128u +
+                         ((((uint32_t)(k & 63) >> 3) ^ ((uint32_t)n & 7u)) << 4) + (uint32_t)(k & 7) * 2u;
+    *reinterpret_cast<__nv_bfloat16*>(img + off) = __float2bfloat16_rn(v);
+  }
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = idx; i < agg_n4; i += stride) agg4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Work list.  A step (128-receiver tile, sender index s) whose sender rows are masked in every jet the
 // tile touches contributes exactly zero to the aggregate and to every gradient: it is dropped here, so
