@@ -121,6 +121,10 @@ int mpg_rank_mask(const float* x, int ldx, const float* labels, int ldl, int B, 
 int mpg_particle_order(const float* mask, int B, int N, int* pos, float* mask_sorted, void* stream);
 int mpg_permute_rows(const float* src, int lds, float* dst, int ldd, const int* pos, int B, int N, int F, int mode,
                      void* stream);
+/* pos[b] (int32) = index of jet b when the batch is ordered by descending key (key[b * ldk], e.g. the particle-count
+ * label), ties in index order; B <= 8192.  Jets never interact, so the batch order is a layout choice too: with
+ * mpg_permute_rows(B = 1, N = batch, F = row length) it puts jets with similar padding into the same tiles. */
+int mpg_batch_order(const float* key, int ldk, int B, int* pos, void* stream);
 /* mask[r] = x[r, ldx-1] + 0.5   (mpgan/model.py:881) */
 int mpg_split_mask(const float* x, int ldx, int rows, float* mask, void* stream);
 /* out[r, :Fo] = act(h[r, :]); out[r, Fo] = mask[r] - 0.5 if mask   (mpgan/model.py:535-536, 752) */

@@ -40,6 +40,7 @@ _SIGS = {
                                      _fl, _fl, _u64, _f, _i, _f, _sz, _f, _f, _i, _f, _f, _f, _f, _f, _f, _f]),
     "mpg_rank_mask": (C.c_int, [_f, _i, _f, _i, _i, _i, _f, _f]),
     "mpg_particle_order": (C.c_int, [_f, _i, _i, _f, _f, _f]),
+    "mpg_batch_order": (C.c_int, [_f, _i, _i, _f, _f]),
     "mpg_permute_rows": (C.c_int, [_f, _i, _f, _i, _f, _i, _i, _i, _i, _f]),
     "mpg_ls_loss_fwd": (C.c_int, [_f, _i, _i, _fl, _fl, _f, _f]),
     "mpg_ls_loss_bwd": (C.c_int, [_f, _f, _i, _i, _fl, _fl, _f, _f]),

@@ -425,6 +425,9 @@ int mpg_rank_mask(const float* x, int ldx, const float* labels, int ldl, int B, 
 int mpg_particle_order(const float* mask, int B, int N, int* pos, float* mask_sorted, void* stream) {
   return launch_particle_order(mask, B, N, pos, mask_sorted, (cudaStream_t)stream);
 }
+int mpg_batch_order(const float* key, int ldk, int B, int* pos, void* stream) {
+  return launch_batch_order(key, ldk, B, pos, (cudaStream_t)stream);
+}
 int mpg_permute_rows(const float* src, int lds, float* dst, int ldd, const int* pos, int B, int N, int F, int mode,
                      void* stream) {
   MPG_CHECK(mode == 0 || mode == 1, "permute_rows: mode must be 0 (scatter) or 1 (gather)");

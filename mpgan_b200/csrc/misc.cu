@@ -94,6 +94,23 @@ __global__ void particle_order_kernel(const float* __restrict__ mask, int B, int
   }
 }
 
+// ---- batch order: jets by descending particle-count key, stable (train.py has no counterpart: layout only) ----
+// pos[b] = #{b' : key[b'] > key[b]} + #{b' < b : key[b'] == key[b]}: one CTA, keys in shared memory (B <= 8192).
+__global__ void batch_order_kernel(const float* __restrict__ key, int ldk, int B, int* __restrict__ pos) {
+  extern __shared__ float keys[];
+  for (int i = threadIdx.x; i < B; i += blockDim.x) keys[i] = key[(size_t)i * ldk];
+  __syncthreads();
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const float k = keys[b];
+    int p = 0;
+    for (int j = 0; j < B; ++j) {
+      const float kj = keys[j];
+      p += (kj > k) || (kj == k && j < b);
+    }
+    pos[b] = p;
+  }
+}
+
 // scatter (mode 0): dst[b, pos[b,i], :] = src[b, i, :];  gather (mode 1): dst[b, i, :] = src[b, pos[b,i], :]
 __global__ void permute_rows_kernel(const float* __restrict__ src, int lds, float* __restrict__ dst, int ldd,
                                     const int* __restrict__ pos, int N, int F, size_t total, int mode) {
@@ -338,6 +355,14 @@ int launch_gen_tail_bwd(const float* dout, const float* out, float* dh, int rows
 int launch_particle_order(const float* mask, int B, int N, int* pos, float* mask_sorted, cudaStream_t s) {
   if (B <= 0 || N <= 0) return 0;
   particle_order_kernel<<<cdiv(B, 8), 256, 0, s>>>(mask, B, N, pos, mask_sorted);
+  MPG_LAUNCH_CHECK();
+  return 0;
+}
+int launch_batch_order(const float* key, int ldk, int B, int* pos, cudaStream_t s) {
+  if (B <= 0) return 0;
+  MPG_CHECK(B <= 8192, "batch_order: at most 8192 jets per call (got %d)", B);
+  const int nt = B < 1024 ? ((B + 31) / 32) * 32 : 1024;
+  batch_order_kernel<<<1, nt, (size_t)B * sizeof(float), s>>>(key, ldk, B, pos);
   MPG_LAUNCH_CHECK();
   return 0;
 }

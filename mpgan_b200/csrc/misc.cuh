@@ -8,6 +8,7 @@ int launch_gen_tail_fwd(const float* h, const float* mask, float* out, int rows,
 int launch_gen_tail_bwd(const float* dout, const float* out, float* dh, int rows, int Fo, int ldo, int act,
                         cudaStream_t s);
 int launch_particle_order(const float* mask, int B, int N, int* pos, float* mask_sorted, cudaStream_t s);
+int launch_batch_order(const float* key, int ldk, int B, int* pos, cudaStream_t s);
 int launch_permute_rows(const float* src, int lds, float* dst, int ldd, const int* pos, int B, int N, int F, int mode,
                         cudaStream_t s);
 int launch_ls_loss(const float* d, const float* gout, int n, int n0, float t0, float t1, float* out, bool bwd,

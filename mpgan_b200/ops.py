@@ -460,6 +460,28 @@ def ls_loss(d, n_first: int, target_first: float, target_rest: float = 0.0):
     return LSLossFn.apply(d, n_first, target_first, target_rest)
 
 
+def batch_order(labels):
+    """pos int32 [B]: index of jet b when the batch is ordered by descending labels[:, -1] (particle count)."""
+    L = _lib.lib()
+    lab = labels.detach()
+    if lab.dim() == 1:
+        lab = lab.unsqueeze(1)
+    lab = lab.float()
+    if lab.stride(1) != 1:
+        lab = lab.contiguous()
+    B = lab.shape[0]
+    key = lab[:, -1]
+    pos = torch.empty(B, device=lab.device, dtype=torch.int32)
+    _lib.check(L.mpg_batch_order(key.data_ptr(), lab.stride(0), B, _lib.ptr(pos), _lib.stream()), "mpg_batch_order")
+    return pos
+
+
+def permute_batch(x, pos, mode: int):
+    """Rows of a batch-first tensor moved by ``pos`` (mode 0: out[pos[b]] = x[b]; mode 1: out[b] = x[pos[b]])."""
+    B = x.shape[0]
+    return permute_rows(x.reshape(1, B, -1), pos.view(1, B), mode).view(x.shape)
+
+
 def split_mask(x):
     """mask = x[..., -1:] + 0.5 (fp32 multiplier) for the discriminator input."""
     L = _lib.lib()

@@ -66,7 +66,8 @@ class FusedRMSprop:
 
 def get_gen_noise(batch_size, num_particles, latent_node_size, sd=0.2, device="cuda", generator=None):
     """Normal(0, sd) noise [B, N, latent] (train.py:113-127, ``--sd 0.2``)."""
-    return torch.randn(batch_size, num_particles, latent_node_size, device=device, generator=generator) * sd
+    # one kernel (normal_ scales in place) instead of randn followed by a multiply
+    return torch.empty(batch_size, num_particles, latent_node_size, device=device).normal_(0.0, sd, generator=generator)
 
 
 class GANTrainer:
@@ -216,7 +217,10 @@ class GANTrainer:
 
 def sort_by_count(data, labels):
     """Reorders a batch by descending particle count (labels[:, -1] = n / N); see GANTrainer.sort_by_count."""
-    order = torch.argsort(labels[:, -1], descending=True)
+    if data.is_cuda and labels.shape[0] <= 8192:
+        pos = ops.batch_order(labels)                      # one kernel; pos[b] = new index of jet b
+        return ops.permute_batch(data, pos, 0), ops.permute_batch(labels, pos, 0)
+    order = torch.argsort(labels[:, -1], descending=True, stable=True)
     return data.index_select(0, order), labels.index_select(0, order)
 
 
@@ -225,7 +229,15 @@ def generate(G, labels, num_particles, latent_node_size=32, sd=0.2, noise=None):
     """G(noise, labels) with the jets processed in order of particle count (fewer live edge-kernel steps, see
     GANTrainer.sort_by_count) and returned in the caller's order."""
     B = labels.shape[0]
-    order = torch.argsort(labels[:, -1], descending=True)
+    if labels.is_cuda and B <= 8192:
+        pos = ops.batch_order(labels)
+        if noise is None:
+            noise = get_gen_noise(B, num_particles, latent_node_size, sd, labels.device)
+        else:
+            noise = ops.permute_batch(noise, pos, 0)
+        out_sorted = G(noise, ops.permute_batch(labels, pos, 0))
+        return ops.permute_batch(out_sorted, pos, 1)       # out[b] = out_sorted[pos[b]]
+    order = torch.argsort(labels[:, -1], descending=True, stable=True)
     if noise is None:
         noise = get_gen_noise(B, num_particles, latent_node_size, sd, labels.device)
     else:

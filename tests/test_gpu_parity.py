@@ -453,7 +453,7 @@ def test_sorted_batch_same_update(golden):
         tr = train.GANTrainer(G, D, num_particles=30)
         d, l, nz = x, labels, noise
         if sort:
-            order = torch.argsort(labels[:, -1], descending=True)
+            order = torch.argsort(labels[:, -1], descending=True, stable=True)
             d, l, nz = x[order], labels[order], noise[order]
             d2, l2 = train.sort_by_count(x, labels)
             assert torch.equal(l2, l) and torch.equal(d2.sum((1, 2)), d.sum((1, 2)))
