@@ -360,8 +360,17 @@ def run_ours(args, wl):
     else:
         G.eval()
 
-        def one_step(d, l):
-            return train.generate(G, l, N, latent, 0.2)   # public generation call (sorts by count, un-sorts output)
+        def eager_step(d, l):   # the per-kernel probe leg needs eager launches
+            return train.generate(G, l, N, latent, 0.2)
+
+        if args.graph:
+            gg = train.GraphedGenerator(G, B, N, latent, 0.2, label_width=labels.shape[1])   # public API, CUDA graph
+
+            def one_step(d, l):
+                return gg(l)
+        else:
+            def one_step(d, l):
+                return train.generate(G, l, N, latent, 0.2)   # sorts by count, un-sorts the output
 
     def barrier():
         if world > 1:
@@ -401,6 +410,8 @@ def run_ours(args, wl):
     launches = L.mpg_launch_count() - launches0
     if kind == "train" and args.graph:
         launches = tr.launches_per_step * args.steps   # replayed kernels: counted once at capture
+    elif kind != "train" and args.graph:
+        launches = gg.launches_per_call * args.steps
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = torch.tensor([sum(step_ms)], device=dev, dtype=torch.float64)
@@ -504,7 +515,7 @@ def run_ours(args, wl):
                        "l2": "flushed between timed steps (256 MiB write)",
                        "precision": ("TF32 projections, fp32 attention core" if gapt else
                                      "bf16 tcgen05 edge network, TF32 node GEMMs, fp32 accumulate"), "parallelism": f"dp{world}",
-                       "cuda_graph": bool(kind == "train" and args.graph)},
+                       "cuda_graph": bool(args.graph)},
             "e2e": {"value": e2e_val, "unit": "jets/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "roofline": roof,

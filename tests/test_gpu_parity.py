@@ -520,3 +520,21 @@ def test_ls_loss_matches_torch():
         (ref * 3.0).backward()
         assert abs(float(loss) - float(ref)) <= 1e-6 * max(1.0, abs(float(ref)))
         close(d.grad, dr.grad, 1e-6, "ls_loss grad")
+
+
+def test_graphed_generator(golden):
+    """CUDA-graphed generation: fresh noise on every replay, particle counts follow the labels passed per call."""
+    from mpgan_b200 import presets, train
+    G = presets.mp_generator().cuda().eval()
+    G.load_state_dict(golden("mp_g_weights.pt"), strict=True)
+    gg = train.GraphedGenerator(G, 64, 30)
+    assert gg.launches_per_call > 0
+    outs = []
+    for seed in (51, 52):
+        _, labels, n = train.synthetic_jets(64, 30, "cuda", torch.Generator(device="cuda").manual_seed(seed))
+        out = gg(labels).clone()
+        assert torch.equal((out[..., 3] > 0).sum(1), n)
+        outs.append(out)
+    assert not torch.equal(outs[0][..., :3], outs[1][..., :3])
+    full = train.gen_multi_batch(G, 8 * 32 + 5, 32, 30, labels=torch.cat([labels] * 5)[:8 * 32 + 5].cpu())
+    assert full.shape == (8 * 32 + 5, 30, 4) and bool(torch.isfinite(full).all())
