@@ -288,9 +288,12 @@ __device__ __forceinline__ uint32_t keep_mask(const u4& bits, int b) {
 }
 __device__ __forceinline__ float apply_keep(float x, uint32_t mask) { return __uint_as_float(__float_as_uint(x) & mask); }
 
+// Everything below is specific to the edge-network kernels; fn_tc.cu includes this header for the PTX wrappers
+// above only (MPG_TC_WRAPPERS_ONLY).
+#ifndef MPG_TC_WRAPPERS_ONLY
 struct TcArgs {
   EdgeArgs a;
-  const uint8_t* w1img;   // pre-swizzled bf16 images (weight_image_kernel)
+  const uint8_t* w1img;   // pre-swizzled bf16 images (edge_prepare_kernel)
   const uint8_t* w2img;
   uint2* sbits;           // backward: sign bits of D2, one uint2 per (step, epilogue thread)
   float* wslab;           // backward: per-CTA weight-gradient partials (edge_tc_bwd.cuh: SLAB_*)
@@ -302,25 +305,9 @@ struct TcArgs {
 };
 
 // ---------------------------------------------------------------------------------------------------
-// weight image: img[n][k] (K-major, SW128) = bf16(scale * W[n][k]) for k < K, bias_hi / bias_lo at
+// weight images: img[n][k] (K-major, SW128) = bf16(scale * W[n][k]) for k < K, bias_hi / bias_lo at
 // k = K, K+1, zero elsewhere.
 // ---------------------------------------------------------------------------------------------------
-__global__ void weight_image_kernel(const float* __restrict__ W, const float* __restrict__ bias, int Nout, int K,
-                                    int Kpad, float scale, uint8_t* __restrict__ img, int* __restrict__ zero_me) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx == 0 && zero_me != nullptr) *zero_me = 0;   // the work-list counter of the step_list_kernel that follows
-  if (idx >= Nout * Kpad) return;
-  const int n = idx / Kpad, k = idx % Kpad;
-  float v = 0.f;
-  if (k < K) v = W[(size_t)n * K + k] * scale;
-  else if (k == K) v = bias[n];
-  else if (k == K + 1) v = bias[n] - __bfloat162float(__float2bfloat16_rn(bias[n]));
-  const uint32_t off = (uint32_t)(k >> 6) * (uint32_t)Nout * 128u + (uint32_t)n * 128u +
-                       ((((uint32_t)(k & 63) >> 3) ^ ((uint32_t)n & 7u)) << 4) + (uint32_t)(k & 7) * 2u;
-  *reinterpret_cast<__nv_bfloat16*>(img + off) = __float2bfloat16_rn(v);
-}
-
-
 // Both weight images of a call, the work-list counter and (forward) the zero fill of the aggregate the kernel
 // accumulates into with reductions: one launch instead of two image kernels and a memset node.
 __global__ void edge_prepare_kernel(const float* __restrict__ W1, const float* __restrict__ b1,
@@ -355,7 +342,7 @@ __global__ void edge_prepare_kernel(const float* __restrict__ W1, const float* _
 // tile touches contributes exactly zero to the aggregate and to every gradient: it is dropped here, so
 // padded particles cost nothing.  One warp per tile: ballots compact its live senders (ascending), one
 // atomicAdd reserves the tile's contiguous slice of the list (tiles land in arbitrary order; only the
-// grouping by tile matters to the kernels).  *total must be zero on entry (weight_image_kernel does it).
+// grouping by tile matters to the kernels).  *total must be zero on entry (edge_prepare_kernel does it).
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) step_list_kernel(const float* __restrict__ mask, int B, int N, int num_tiles,
                                                         int2* __restrict__ steps, int* __restrict__ total) {
@@ -384,3 +371,4 @@ __global__ void __launch_bounds__(256) step_list_kernel(const float* __restrict_
     off += __popc(b);
   }
 }
+#endif  // MPG_TC_WRAPPERS_ONLY

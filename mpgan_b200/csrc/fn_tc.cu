@@ -18,11 +18,11 @@
 // D2 over D0.  Weight gradients (dz^T y) stay on the TF32 mma.sync GEMM (gemm.cu), launched by the caller on a
 // side stream.
 #include "fn_tc.cuh"
-#include "edge.cuh"      // EdgeArgs (referenced by the shared tcgen05 header)
 
 namespace mpg {
 namespace {
 
+#define MPG_TC_WRAPPERS_ONLY
 #include "edge_tc_common.cuh"   // PTX wrappers (mbarrier, bulk copies, tcgen05 alloc/commit/ld/st), umma_desc
 
 constexpr int FN_EPI = 512;                       // epilogue threads (16 warps)
