@@ -6,7 +6,11 @@ Workloads (config.workload):
   train_n30_b256   MPGAN G+D training step, 30-particle jets, batch 256 per GPU  (BASELINE configs[1];
                    the default: the configuration the metric is quoted on)
   train_n150_b32   same at 150 particles, batch 32 per GPU (configs[2], reference default batch)
+  train_n150_b256  same at batch 256 per GPU (what the fused kernels make possible)
+  train_n100_b256  100-point clouds, batch 256 (configs[4]: sparsified-MNIST shapes with masking)
   gen_n30_b1024    generator inference from the mp_g weights, batch 1024 (configs[0])
+  gen_n150_b1024   the same at 150 particles
+  train_gapt_*     GAPT (SAB / ISAB) training step, 30 particles, batch 512 (configs[3])
 
 A "step" is one train_D + train_G on one synthetic batch (train.py:841-878, num_critic=num_gen=1,
 LS loss, RMSprop, D dropout 0.5).  `value` times K steps on the device with the batch resident in
@@ -30,6 +34,9 @@ WORKLOADS = {
     "train_n30_b256": dict(kind="train", N=30, B=256),
     "train_n150_b32": dict(kind="train", N=150, B=32),
     "train_n150_b256": dict(kind="train", N=150, B=256),
+    # BASELINE configs[4]: sparsified-MNIST point clouds (train_mnist.py shapes: 100 points x (x, y, intensity) + mask
+    # channel); same networks at num_hits = 100
+    "train_n100_b256": dict(kind="train", N=100, B=256),
     "gen_n30_b1024": dict(kind="gen", N=30, B=1024),
     "gen_n150_b1024": dict(kind="gen", N=150, B=1024),
     # BASELINE configs[3]: GAPT (masked set attention) training step, reference batch 512 (setup_training.py:836-838)
