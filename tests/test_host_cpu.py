@@ -184,3 +184,13 @@ def test_flops_model_matches_survey():
     assert abs(fg / 1e6 - 181.9) < 0.1 and abs(fd / 1e6 - 181.6) < 0.1
     assert abs(bench.step_flops(30) / 1e9 - 2.180) < 0.001
     assert abs(bench.step_flops(150) / 1e9 - 50.71) < 0.01
+
+
+def test_sort_by_count_host_path():
+    """train.sort_by_count on CPU tensors (torch path): descending particle count, ties in the caller's order."""
+    from mpgan_b200 import train
+    labels = torch.tensor([[0.5], [1.0], [0.5], [0.1], [1.0]])
+    data = torch.arange(5, dtype=torch.float32).view(5, 1, 1).expand(5, 3, 4).contiguous()
+    d, l = train.sort_by_count(data, labels)
+    assert l[:, 0].tolist() == [1.0, 1.0, 0.5, 0.5, pytest.approx(0.1)]
+    assert d[:, 0, 0].tolist() == [1.0, 4.0, 0.0, 2.0, 3.0]
