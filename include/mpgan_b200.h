@@ -82,7 +82,9 @@ int mpg_edge_bwd(const float* x, int ldx, const float* mask, const float* w0, co
  * b [M, Kb] (the node features), w0 [H1, Ka+Kb], w1 [H2, H1], w2 [NO, H2] in the reference layout.  One
  * tcgen05 (TF32) kernel per direction; y0 [M, H1] and y1 [M, H2] (layer outputs) are saved for backward.
  * Dropout uses RNG streams 16, 17, 18 of `seed` (the streams LinearNet gives its layers), p in {0, 0.5}.
- * mpg_fn_supported() != 0 iff the shape is covered; other shapes go through mpg_linear_* per layer. */
+ * y0 / y1 hold the layer outputs rounded to TF32 (they only feed TF32 GEMMs and the leaky-relu sign test).
+ * mpg_fn_supported() != 0 iff the shape is covered (Ka + Kb <= 256, H1, H2 in {128, 256}, NO <= 32, p in
+ * {0, 0.5}); other shapes go through mpg_linear_* per layer. */
 int mpg_fn_supported(int Ka, int Kb, int H1, int H2, int NO, float p_drop);
 size_t mpg_fn_workspace_bytes(int Ka, int Kb, int H1, int H2, int NO);
 int mpg_fn_fwd(const float* a, int lda, int Ka, const float* b, int ldb, int Kb, int M, const float* w0,
