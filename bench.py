@@ -1,25 +1,28 @@
-"""Benchmark of the MPGAN hot path (BASELINE.json metric: jets/s per G+D train step).
+"""Benchmark of the MPGAN hot path (BASELINE.json metric: jets/s per G+D train step at 30 & 150 particles; gen jets/s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--no-suite]
+    torchrun ... bench.py --gpus N --check        # 1-rank vs N-rank gradient equality on real NCCL (prints one JSON line)
 
-Workloads (config.workload):
-  train_n30_b256   MPGAN G+D training step, 30-particle jets, batch 256 per GPU  (BASELINE configs[1];
-                   the default: the configuration the metric is quoted on)
-  train_n150_b32   same at 150 particles, batch 32 per GPU (configs[2], reference default batch)
-  train_n150_b256  same at batch 256 per GPU (what the fused kernels make possible)
-  train_n100_b256  100-point clouds, batch 256 (configs[4]: sparsified-MNIST shapes with masking)
-  gen_n30_b1024    generator inference from the mp_g weights, batch 1024 (configs[0])
-  gen_n150_b1024   the same at 150 particles
-  train_gapt_*     GAPT (SAB / ISAB) training step, 30 particles, batch 512 (configs[3])
+The ONE JSON line's top level is the headline workload (default `train_n30_b256`: BASELINE configs[1], the
+configuration the metric is quoted on).  Unless `--no-suite` / `--workload` is given, the same run also times the
+other configurations the metric names and embeds them under `"workloads"` (each with value / e2e / roofline / clocks /
+gpu_launches), so one driver invocation per `--gpus N` covers N=150, generation, GAPT and the all-real variants:
 
-A "step" is one train_D + train_G on one synthetic batch (train.py:841-878, num_critic=num_gen=1,
-LS loss, RMSprop, D dropout 0.5).  `value` times K steps on the device with the batch resident in
-HBM (per-step CUDA events, L2 flushed between steps, max over ranks); `e2e` times the same K steps
-through the public API starting from pinned HOST buffers, host->device copies and the device->host
-read of the two losses inside the timed region.  `--impl reference` times the CPU oracle port of the
-same step (oracle/mpgan_oracle.gd_step) on the host cores, on a bounded sample of the batch.
+  train_n30_b256[_allreal]    MPGAN G+D training step, 30-particle jets, batch 256 per GPU   (configs[1])
+  train_n150_b32              150 particles, batch 32 per GPU (configs[2], the reference's default batch)
+  train_n150_b256[_allreal]   150 particles, batch 256 per GPU (what the fused kernels make possible)
+  train_n100_b256             100-point clouds, batch 256 (configs[4]: sparsified-MNIST shapes with masking)
+  gen_n30_b1024, gen_n150_b1024   generator inference from the mp_g weights, batch 1024 per GPU (configs[0], [2])
+  train_gapt_n30_b512, train_gapt_isab_n30_b512   GAPT (SAB / ISAB) training step, batch 512 (configs[3])
+
+A "step" is one train_D + train_G on one synthetic batch (train.py:841-878, num_critic = num_gen = 1, LS loss,
+RMSprop, D dropout 0.5) or one generator batch.  `value` times K steps on the device with the batch resident in HBM
+(per-step CUDA events, L2 flushed between steps, max over ranks); `e2e` times the same K steps through the public API
+starting from pinned HOST buffers, host->device copies and the device->host read of the result inside the timed
+region.  `--impl reference` times the UNMODIFIED reference (oracle/_ref, see oracle/build_ref.py) on the host cores.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -32,8 +35,10 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     "train_n30_b256": dict(kind="train", N=30, B=256),
+    "train_n30_b256_allreal": dict(kind="train", N=30, B=256, all_real=True),
     "train_n150_b32": dict(kind="train", N=150, B=32),
     "train_n150_b256": dict(kind="train", N=150, B=256),
+    "train_n150_b256_allreal": dict(kind="train", N=150, B=256, all_real=True),
     # BASELINE configs[4]: sparsified-MNIST point clouds (train_mnist.py shapes: 100 points x (x, y, intensity) + mask
     # channel); same networks at num_hits = 100
     "train_n100_b256": dict(kind="train", N=100, B=256),
@@ -43,6 +48,11 @@ WORKLOADS = {
     "train_gapt_n30_b512": dict(kind="train", N=30, B=512, model="gapt"),
     "train_gapt_isab_n30_b512": dict(kind="train", N=30, B=512, model="gapt", isab=True),
 }
+HEADLINE = "train_n30_b256"
+SUITE = ["train_n30_b256_allreal", "train_n150_b32", "train_n150_b256", "train_n150_b256_allreal", "train_n100_b256",
+         "gen_n30_b1024", "gen_n150_b1024", "train_gapt_n30_b512", "train_gapt_isab_n30_b512"]
+
+
 # GAPT is HBM/latency-bound: algorithmic bytes per jet: each MAB reads x, y and writes its output,
 # (Nq + Nk + Nq) * 64 * 4 B; a G+D step costs 8 D-forward-equivalents + 4 G-forward-equivalents as for MPGAN
 def gapt_step_bytes(N, isab, M=10):
@@ -51,11 +61,21 @@ def gapt_step_bytes(N, isab, M=10):
     g = 4 * block + N * (64 + 4) * 4.0
     d = 2 * block + mab(1, N) + N * (4 + 64) * 4.0
     return 8.0 * d + 4.0 * g
+
+
 H = (96, 160, 192)
 FN = (256, 256)
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the ncu --set full
-# captures summarised under profiles/ (filled in per round; null where no capture exists for the workload)
-DRAM_TRAFFIC = {}
+
+
+def _dram_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of each tcgen05 edge kernel, from the `ncu --set full`
+    captures summarised under profiles/ (profiles/dram_traffic.json: {workload: {kernel: bytes}}); null where no
+    capture of that workload exists."""
+    p = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
 
 
 def layer_flops(N, F, Fout):
@@ -85,8 +105,8 @@ def peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons (100 ms period) from before the warm-up on; stop(t0, t1)
-    reports the samples that fall inside the timed window [t0, t1] (wall clock)."""
+    """Samples nvidia-smi clocks / throttle reasons (100 ms period) for the whole bench; window(t0, t1) reports the
+    samples that fall inside one timed window [t0, t1] (wall clock)."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -108,26 +128,16 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def wait_first(self, timeout=5.0):
-        t_end = time.time() + timeout
-        while self.proc is not None and not self.rows and time.time() < t_end:
-            time.sleep(0.05)
-
-    def stop(self, t0, t1):
+    def window(self, t0, t1):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)   # let the sample covering the end of the window arrive
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            pass
-        ok = [(t, r) for t, r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        ok = [(t, r) for t, r in list(self.rows) if len(r) >= 9 and r[1].replace(".", "").isdigit()]
         win = [r for t, r in ok if t0 <= t <= t1 + 0.12]
         note = "samples inside the timed window"
-        if len(win) < 2:   # window shorter than two sampling periods: use every sample taken under load
-            win = [r for t, r in ok if t >= t0 - 2.0]
-            note = "timed window < 2 sampling periods: samples from 2 s before it to the end of the bench"
+        if len(win) < 2:   # window shorter than two sampling periods: use the samples taken under load just before it
+            win = [r for t, r in ok if t0 - 1.5 <= t <= t1 + 0.25]
+            note = "timed window < 2 sampling periods: samples from the 1.5 s of load before it to its end"
         sm = sorted(float(r[1]) for r in win)
         mx = [float(r[2]) for r in win if r[2].replace(".", "").isdigit()]
         reasons = set()
@@ -138,90 +148,103 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "samples": len(sm), "reasons": sorted(reasons), "note": note}
 
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                pass
+
 
 # ----------------------------------------------------------------------------------------------------
-# CPU oracle arm
+# reference arms: the UNMODIFIED reference modules (oracle/_ref) on the host cores or, eager, on the GPU;
+# the oracle port is the stand-in only when oracle/_ref is absent
 # ----------------------------------------------------------------------------------------------------
-def cpu_step_time(N, B_sample, reps, warm=1, kind="train", device="cpu"):
-    """Times the oracle port of the reference's eager PyTorch path (oracle/mpgan_oracle.py) on B_sample jets;
-    returns seconds/step.  device="cpu": the CPU baseline; device="cuda": the same eager fp32 PyTorch code on the
-    GPU (SURVEY 8d's like-for-like GPU baseline) -- a baseline leg either way, never the product path."""
+def _golden_weights(device):
+    import torch
+    gold = os.path.join(ROOT, "tests", "golden")
+    return (torch.load(os.path.join(gold, "mp_g_weights.pt"), map_location=device),
+            torch.load(os.path.join(gold, "mp_d_seed4_weights.pt"), map_location=device))
+
+
+def reference_step_time(wl, B_sample, reps, warm, device="cpu"):
+    """Seconds per step of the reference's own train_D + train_G (or generator forward) on B_sample jets.
+    Returns (seconds, threads, kind)."""
     import torch
     from oracle import mpgan_oracle as mo
+    from oracle import ref_loader
     torch.set_num_threads(os.cpu_count() or 1)
-    gold = os.path.join(ROOT, "tests", "golden")
-    sdG = torch.load(os.path.join(gold, "mp_g_weights.pt"), map_location="cpu")
-    sdD = torch.load(os.path.join(gold, "mp_d_seed4_weights.pt"), map_location="cpu")
-    if device != "cpu":
-        return _gpu_eager_step_time(mo, sdG, sdD, N, B_sample, reps, warm, kind, device)
-    cfgG = mo.NetCfg(num_particles=N, final_activation="tanh")
-    cfgD = mo.NetCfg(num_particles=N, final_activation="sigmoid", dropout_p=0.5,
-                     layers=[mo.EdgeCfg(all_ef=False), mo.EdgeCfg()])
+    N, kind, gapt = wl["N"], wl["kind"], wl.get("model") == "gapt"
     g = torch.Generator().manual_seed(4)
-    data, labels, _ = mo.synthetic_jets(B_sample, N, g)
-    times = []
-    if kind == "gen":
-        for i in range(warm + reps):
-            noise = torch.randn(B_sample, N, 32, generator=g) * 0.2
-            t0 = time.perf_counter()
-            with torch.no_grad():
-                mo.generator(sdG, noise, labels, cfgG)
-            times.append(time.perf_counter() - t0)
-        return min(times[warm:]), torch.get_num_threads()
-    pG = {k: v.clone().requires_grad_(True) for k, v in sdG.items()}
-    pD = {k: v.clone().requires_grad_(True) for k, v in sdD.items()}
-    stD, stG = {}, {}
-    for i in range(warm + reps):
-        nd = torch.randn(B_sample, N, 32, generator=g) * 0.2
-        ng = torch.randn(B_sample, N, 32, generator=g) * 0.2
-        t0 = time.perf_counter()
-        mo.gd_step(pG, pD, cfgG, cfgD, data, labels, nd, ng, stateD=stD, stateG=stG)
-        times.append(time.perf_counter() - t0)
-    return sum(times[warm:]) / reps, torch.get_num_threads()
-
-
-def _gpu_eager_step_time(mo, sdG, sdD, N, B_sample, reps, warm, kind, device):
-    import torch
-    sdG = {k: v.to(device) for k, v in sdG.items()}
-    sdD = {k: v.to(device) for k, v in sdD.items()}
-    cfgG = mo.NetCfg(num_particles=N, final_activation="tanh")
-    cfgD = mo.NetCfg(num_particles=N, final_activation="sigmoid", dropout_p=0.5,
-                     layers=[mo.EdgeCfg(all_ef=False), mo.EdgeCfg()])
-    g = torch.Generator().manual_seed(4)
-    data, labels, _ = mo.synthetic_jets(B_sample, N, g)
+    data, labels, _ = mo.synthetic_jets(B_sample, N, g, all_real=wl.get("all_real", False))
     data, labels = data.to(device), labels.to(device)
+    sync = torch.cuda.synchronize if device != "cpu" else (lambda: None)
+    if ref_loader.available():
+        torch.manual_seed(4)
+        weights = None if (gapt or N is None) else _golden_weights(device)
+        rs = ref_loader.RefStep(N, device, "gapt" if gapt else "mpgan", wl.get("isab", False), weights)
+        fn = (lambda: rs.generate(labels)) if kind == "gen" else (lambda: rs.step(data, labels))
+        how = "reference"
+    else:   # stand-in: the oracle port of the same step
+        fn = _port_step(wl, data, labels, device, g)
+        how = "port"
+    times = []
+    for _ in range(warm + reps):
+        sync()
+        t0 = time.perf_counter()
+        fn()
+        sync()
+        times.append(time.perf_counter() - t0)
+    best = min(times[warm:]) if (kind == "gen" or device != "cpu") else sum(times[warm:]) / reps
+    return best, torch.get_num_threads(), how
+
+
+def _port_step(wl, data, labels, device, g):
+    import torch
+    from oracle import mpgan_oracle as mo
+    N, kind = wl["N"], wl["kind"]
+    if wl.get("model") == "gapt":
+        raise RuntimeError("oracle/_ref absent and no GAPT port step")
+    sdG, sdD = _golden_weights(device)
+    cfgG = mo.NetCfg(num_particles=N, final_activation="tanh")
+    cfgD = mo.NetCfg(num_particles=N, final_activation="sigmoid", dropout_p=0.5,
+                     layers=[mo.EdgeCfg(all_ef=False), mo.EdgeCfg()])
     pG = {k: v.clone().requires_grad_(True) for k, v in sdG.items()}
     pD = {k: v.clone().requires_grad_(True) for k, v in sdD.items()}
     stD, stG = {}, {}
-    times = []
-    for i in range(warm + reps):
-        nd = torch.randn(B_sample, N, 32, device=device) * 0.2
-        ng = torch.randn(B_sample, N, 32, device=device) * 0.2
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
+    B = data.shape[0]
+
+    def fn():
+        nd = torch.randn(B, N, 32, device=device) * 0.2
+        ng = torch.randn(B, N, 32, device=device) * 0.2
         if kind == "gen":
             with torch.no_grad():
                 mo.generator(sdG, nd, labels, cfgG)
         else:
             mo.gd_step(pG, pD, cfgG, cfgD, data, labels, nd, ng, stateD=stD, stateG=stG)
-        torch.cuda.synchronize()
-        times.append(time.perf_counter() - t0)
-    return min(times[warm:]), 0
+    return fn
 
 
-def gpu_eager_baseline(wl, N, kind):
-    """Eager fp32 PyTorch (oracle port of the reference modules) on this GPU, fp32 and TF32-allowed matmuls."""
+def gpu_eager_baseline(wl):
+    """The reference's eager PyTorch modules on this GPU, fp32 and with TF32 matmuls allowed (like-for-like GPU
+    baseline)."""
     import torch
-    if wl.get("model") == "gapt":
-        return None
-    bs = {30: 256, 150: 8}.get(N, 8) if kind == "train" else {30: 256, 150: 16}.get(N, 16)
-    out = {"unit": "jets/s", "sample": f"{bs} jets/step, best of 3 (oracle port of the reference's eager PyTorch path on this GPU)"}
+    N, kind, gapt = wl["N"], wl["kind"], wl.get("model") == "gapt"
+    if gapt:
+        bs = wl["B"]
+    elif kind == "train":
+        bs = {30: 256, 100: 16, 150: 8}.get(N, 8)    # the N^2 x hidden tensors of larger batches do not fit comfortably
+    else:
+        bs = {30: 1024, 100: 64, 150: 32}.get(N, 32)
+    out = {"unit": "jets/s"}
     for name, tf32 in (("fp32", False), ("tf32_allowed", True)):
         old = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = tf32
         try:
-            sec, _ = cpu_step_time(N, bs, 3, 1, kind, device="cuda")
+            sec, _, how = reference_step_time(wl, bs, 3, 1, device="cuda")
             out[name] = bs / sec
+            out["sample"] = f"{bs} jets/step, best of 3 ({'unmodified reference modules' if how == 'reference' else 'oracle port'}, eager PyTorch on this GPU)"
         except Exception as e:  # pragma: no cover
             out[name] = None
             out["error"] = str(e)[:200]
@@ -231,73 +254,45 @@ def gpu_eager_baseline(wl, N, kind):
     return out
 
 
-def cpu_gapt_step_time(N, B_sample, reps, warm=1, isab=False):
-    """Times the CPU oracle port of one GAPT train_D + train_G step (oracle/gapt_oracle.py) on B_sample jets."""
-    import torch
-    from mpgan_b200 import presets
-    from oracle import gapt_oracle as go
-    from oracle import mpgan_oracle as mo
-    torch.set_num_threads(os.cpu_count() or 1)
-    torch.manual_seed(4)
-    sdG = {k: v.clone().requires_grad_(True) for k, v in presets.gapt_generator(num_hits=N, use_isab=isab).state_dict().items()}
-    sdD = {k: v.clone().requires_grad_(True) for k, v in presets.gapt_discriminator(num_hits=N, use_isab=isab).state_dict().items()}
-    cfgG = go.GaptCfg(num_particles=N, sab_layers=4, use_isab=isab)
-    cfgD = go.GaptCfg(num_particles=N, sab_layers=2, use_isab=isab, dropout_p=0.5, linear_dropout_p=0.5)
-    g = torch.Generator().manual_seed(4)
-    data, labels, _ = mo.synthetic_jets(B_sample, N, g)
-    stD, stG, times = {}, {}, []
-    for i in range(warm + reps):
-        nd = torch.randn(B_sample, N, 64, generator=g) * 0.2
-        ng = torch.randn(B_sample, N, 64, generator=g) * 0.2
-        t0 = time.perf_counter()
-        real_out = go.gapt_d(sdD, data.clone(), labels, cfgD, training=True)
-        fake_out = go.gapt_d(sdD, go.gapt_g(sdG, nd, labels, cfgG, training=False), labels, cfgD, training=True)
-        gD = torch.autograd.grad(mo.d_loss_ls(real_out, fake_out), list(sdD.values()), allow_unused=True)
-        with torch.no_grad():
-            for (k, p), gr in zip(sdD.items(), gD):
-                if gr is not None:
-                    mo.rmsprop_step(p, gr, stD.setdefault(k, torch.zeros_like(gr)), 0.5e-4)
-        fake_out = go.gapt_d(sdD, go.gapt_g(sdG, ng, labels, cfgG, training=True), labels, cfgD, training=True)
-        gG = torch.autograd.grad(mo.g_loss_ls(fake_out), list(sdG.values()), allow_unused=True)
-        with torch.no_grad():
-            for (k, p), gr in zip(sdG.items(), gG):
-                if gr is not None:
-                    mo.rmsprop_step(p, gr, stG.setdefault(k, torch.zeros_like(gr)), 1.5e-4)
-        times.append(time.perf_counter() - t0)
-    return sum(times[warm:]) / reps, torch.get_num_threads()
-
-
-def cpu_time(wl, N, B_sample, reps, warm, kind):
-    if wl.get("model") == "gapt":
-        return cpu_gapt_step_time(N, B_sample, reps, warm, isab=wl.get("isab", False))
-    return cpu_step_time(N, B_sample, reps, warm=warm, kind=kind)
-
-
-def cpu_sample_size(wl):
+def cpu_sample_size(wl, budget_steps=None):
+    """Jets per CPU step: the workload's own batch where a step stays near ~10 s on the host, else a bounded sample."""
     N, kind = wl["N"], wl["kind"]
     if wl.get("model") == "gapt":
-        return 512
-    return ({30: 32, 150: 2}.get(N, 4)) if kind == "train" else ({30: 256, 150: 16}.get(N, 16))
+        return wl["B"]
+    if kind == "train":
+        return {30: wl["B"], 100: 8, 150: 4}.get(N, 4)
+    return {30: wl["B"], 100: 64, 150: 32}.get(N, 32)
 
 
-def run_reference(args, wl):
+def run_reference(args, name, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import torch
     N, kind = wl["N"], wl["kind"]
-    # bounded sample: sized so one step is ~1-2 s on a few cores
     B_sample = cpu_sample_size(wl)
-    reps = max(1, min(args.steps, 8))
-    sec, cores = cpu_time(wl, N, B_sample, reps, min(args.warmup, 1), kind)
+    # bounded: time one probe step, then shrink the per-step sample until warmup + steps fit ~3.5 minutes
+    warm, reps = max(0, args.warmup), max(1, args.steps)
+    probe_B = max(1, min(B_sample, 32))
+    sec_probe, cores, how = reference_step_time(wl, probe_B, 1, 0)
+    budget = 210.0
+    while B_sample > 8 and sec_probe / probe_B * B_sample * (warm + reps) > budget:
+        B_sample //= 2
+    if sec_probe / probe_B * B_sample * (warm + reps) > budget:   # still too long: fewer steps of the same sample
+        reps = max(2, int(budget / (sec_probe / probe_B * B_sample)) - 1)
+        warm = 1
+    sec, cores, how = reference_step_time(wl, B_sample, reps, warm)
     val = B_sample / sec
+    what = "unmodified reference (oracle/_ref: train.train_D + train.train_G, torch.optim.RMSprop)" if how == "reference" \
+        else "oracle port of the reference fp32 PyTorch path (oracle/_ref absent)"
     line = {
         "impl": "reference", "metric": metric_name(wl), "value": val, "unit": "jets/s", "n_gpus": args.gpus,
-        "steps": reps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "steps": reps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "sample_jets_per_step": B_sample, "particles": N},
-        "cpu_baseline": {"value": val, "unit": "jets/s", "cores": cores, "kind": "port",
-                         "sample": f"{B_sample} jets/step x {reps} steps of the same workload (oracle port of the "
-                                   "reference fp32 PyTorch path)"},
+        "config": {"workload": name, "particles": N, "batch_per_gpu": B_sample, "global_batch": B_sample,
+                   "same_batch_as_gpu_arm": B_sample == wl["B"], "device": "host CPU", "threads": cores},
+        "cpu_baseline": {"value": val, "unit": "jets/s", "cores": cores, "kind": how,
+                         "sample": f"{B_sample} jets/step x {reps} steps of the same workload ({what})"},
         "e2e": {"value": val, "unit": "jets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -310,27 +305,21 @@ def metric_name(wl):
 # ----------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------
-def run_ours(args, wl):
+class Env:
+    pass
+
+
+def measure(name, wl, args, env, with_baselines):
+    """Times one workload; returns its result dict (every rank runs it; rank 0's dict is the one reported)."""
     import torch
     import torch.distributed as dist
     from mpgan_b200 import _lib, ops, presets, train
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py --impl ours needs a CUDA device (no CPU fallback)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the ONE JSON line only
-        dist.init_process_group("nccl", device_id=dev)
+    dev, rank, world = env.dev, env.rank, env.world
     N, B, kind = wl["N"], wl["B"], wl["kind"]
+    all_real = wl.get("all_real", False) or args.all_real
     L = _lib.lib()
     ops.set_precision(1)
-    torch.manual_seed(4 + rank)
-
     gapt = wl.get("model") == "gapt"
     latent = 64 if gapt else 32
     torch.manual_seed(4)  # identical initial weights on every rank
@@ -340,14 +329,16 @@ def run_ours(args, wl):
     else:
         G = presets.mp_generator(num_hits=N).to(dev)
         D = presets.mp_discriminator(num_hits=N).to(dev)
-        gold = os.path.join(ROOT, "tests", "golden")
-        G.load_state_dict(torch.load(os.path.join(gold, "mp_g_weights.pt"), map_location=dev))
-        D.load_state_dict(torch.load(os.path.join(gold, "mp_d_seed4_weights.pt"), map_location=dev))
-    gen = torch.Generator(device=dev).manual_seed(4 + rank)
-    data, labels, _ = train.synthetic_jets(B, N, dev, gen, all_real=args.all_real)
-    flush_buf = torch.empty(256 * 1024 * 1024 // 4, device=dev)  # > 126 MB L2
+        sdG, sdD = _golden_weights(dev)
+        G.load_state_dict(sdG)
+        D.load_state_dict(sdD)
+    # from here on every rank draws its own data, noise and dropout masks (an independent shard of the global batch)
+    torch.manual_seed(4 + 1000 * rank)
+    gen = torch.Generator(device=dev).manual_seed(4 + 1000 * rank)
+    data, labels, _ = train.synthetic_jets(B, N, dev, gen, all_real=all_real)
 
     eager_step = None
+    tr = gg = None
     if kind == "train":
         tr = train.GANTrainer(G, D, lr_gen=1.5e-4 if gapt else 1e-5, lr_disc=0.5e-4 if gapt else 3e-5, num_particles=N,
                               latent_node_size=latent)
@@ -376,26 +367,22 @@ def run_ours(args, wl):
             def one_step(d, l):
                 return gg(l)
         else:
-            def one_step(d, l):
-                return train.generate(G, l, N, latent, 0.2)   # sorts by count, un-sorts the output
+            one_step = eager_step
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     for _ in range(max(args.warmup, 3)):
         one_step(data, labels)
-    # keep the GPUs under load for ~1.5 s so nvidia-smi (100 ms period, slow to start) has samples before the
-    # timed window opens; every rank runs the SAME number of extra steps (the steps contain collectives)
+    # keep the GPUs under load for ~1 s so the clock samples describe the loaded state when the timed window opens;
+    # every rank runs the SAME number of extra steps (the steps contain collectives)
     torch.cuda.synchronize()
     t0 = time.time()
     one_step(data, labels)
     torch.cuda.synchronize()
-    n_extra = torch.tensor([min(3000, int(1.5 / max(time.time() - t0, 1e-4)) + 1)], device=dev)
+    n_extra = torch.tensor([min(2000, int(args.preload_s / max(time.time() - t0, 1e-4)) + 1)], device=dev)
     if world > 1:
         dist.all_reduce(n_extra, op=dist.ReduceOp.MAX)
     for _ in range(int(n_extra)):
@@ -408,7 +395,7 @@ def run_ours(args, wl):
     barrier()
     t_wall0 = time.time()
     for i in range(args.steps):
-        flush_buf.zero_()  # evict L2 between timed steps (untimed)
+        env.flush_buf.zero_()  # evict L2 between timed steps (untimed)
         ev[i][0].record()
         one_step(data, labels)
         ev[i][1].record()
@@ -419,7 +406,7 @@ def run_ours(args, wl):
         launches = tr.launches_per_step * args.steps   # replayed kernels: counted once at capture
     elif kind != "train" and args.graph:
         launches = gg.launches_per_call * args.steps
-    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    clocks = env.sampler.window(t_wall0, t_wall1) if rank == 0 else None
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = torch.tensor([sum(step_ms)], device=dev, dtype=torch.float64)
     if world > 1:
@@ -429,94 +416,104 @@ def run_ours(args, wl):
 
     # ---- end-to-end through the public API from pinned host buffers -------------------------------
     h_data, h_labels = data.cpu().pin_memory(), labels.cpu().pin_memory()
+    h_out = torch.empty(B, N, 4, pin_memory=True) if kind == "gen" else None
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     sink = 0.0
     for i in range(args.steps):
-        d = h_data.to(dev, non_blocking=True)
         l = h_labels.to(dev, non_blocking=True)
-        out = one_step(d, l)
         if kind == "train":
+            d = h_data.to(dev, non_blocking=True)
+            out = one_step(d, l)
             sink += float(out[0]) + float(out[1])   # D2H read of both losses (train.py:390-393,523)
         else:
-            sink += float(out[0, 0, 0].cpu())
+            out = one_step(None, l)
+            h_out.copy_(out, non_blocking=True)       # the generated jets land in pinned host memory (gen.py:143)
+            torch.cuda.current_stream().synchronize()
+            sink += float(h_out[0, 0, 0])
     e1.record()
     barrier()
     e2e_ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_val = B * world * args.steps / (float(e2e_ms) * 1e-3)
-    h2d = h_data.numel() * 4 + h_labels.numel() * 4
-    d2h = 8 if kind == "train" else 4
+    h2d = h_labels.numel() * 4 + (h_data.numel() * 4 if kind == "train" else 0)
+    d2h = 8 if kind == "train" else h_out.numel() * 4
 
     # ---- per-kernel device time (roofline leg): eager steps with the library's event probes armed.
     # A queue of large GEMMs is enqueued first so the host runs ahead and the probed kernels execute
     # back to back on the device (no host-launch gaps inside the event pairs).
-    prof_fn = eager_step if eager_step is not None else one_step
-    big = torch.randn(8192, 8192, device=dev, dtype=torch.bfloat16)
-    ops.profile_start()
-    for _ in range(3):
-        for _ in range(16):
-            big @ big
-        prof_fn(data, labels)
-    prof = ops.profile_stop()
-    barrier()
-    del big
+    prof, prof_steps = [], 3
+    if not gapt:
+        big = torch.randn(8192, 8192, device=dev, dtype=torch.bfloat16)
+        ops.profile_start()
+        for _ in range(prof_steps):
+            for _ in range(16):
+                big @ big
+            eager_step(data, labels)
+        prof = ops.profile_stop()
+        barrier()
+        del big
 
+    res = None
     if rank == 0:
         pk = peaks()
-        # dominant kernel class by device time
         by = {}
-        for name, a, b, fl, fl_exec in prof:
-            t = by.setdefault(name, [0.0, 0, 0.0, 0.0])
+        for kname, a, b, fl, fl_exec in prof:
+            t = by.setdefault(kname, [0.0, 0, 0.0, 0.0])
             t[0] += a.elapsed_time(b)
             t[1] += 1
             t[2] += fl
             t[3] += fl_exec
-        kernels = {k: v for k, v in by.items() if k.endswith("_kernel")} or by
+        kernels = {k: v for k, v in by.items() if k.endswith("_kernel")}
         dom = max(kernels, key=lambda k: kernels[k][0]) if kernels else None
-        prof_steps = 3
         roof = None
         if dom:
             ms, cnt, fl, fl_exec = by[dom]
-            # `achieved` counts only the (tile, sender) steps the kernel executes (fully masked senders are
-            # skipped); `achieved_dense` is SURVEY 8(d)'s dense N^2 figure over the same time
+            # `achieved` counts only the (tile, sender) steps the kernel executes (fully masked senders are skipped and
+            # not credited).  Peak = the measured BURST bf16 figure: each kernel is timed alone by its own event pair,
+            # for well under a second.
             ach = fl_exec / (ms * 1e-3) / 1e12
-            roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s",
-                    "frac": ach / pk["tflops"], "traffic": DRAM_TRAFFIC.get((args.workload, dom)),
-                    "achieved_dense": fl / (ms * 1e-3) / 1e12, "executed_step_fraction": fl_exec / fl if fl else None,
-                    "peak_source": pk["src"] + " bf16 sustained",
+            traffic = _dram_traffic().get(name, {})
+            roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": pk["tflops_burst"], "unit": "TFLOP/s",
+                    "frac": ach / pk["tflops_burst"], "traffic": traffic.get(dom),
+                    "frac_of_sustained_peak": ach / pk["tflops"], "executed_step_fraction": fl_exec / fl if fl else None,
+                    "peak_source": pk["src"] + " bf16 burst (kernel timed alone by CUDA events; sustained figure: %.1f)" % pk["tflops"],
                     "launches": cnt, "avg_launch_ms": ms / cnt,
                     "share_of_step": (ms / prof_steps) / (sum(step_ms) / len(step_ms)),
-                    "all": {k: {"ms_total": v[0], "launches": v[1], "tflops_executed": v[3] / (v[0] * 1e-3) / 1e12,
-                                "tflops_dense": v[2] / (v[0] * 1e-3) / 1e12} for k, v in by.items()}}
-        alg = step_flops(N) if kind == "train" else net_flops(N)[0]
+                    "kernels": {k: {"ms_per_step": v[0] / prof_steps, "launches_per_step": v[1] / prof_steps,
+                                    "tflops": v[3] / (v[0] * 1e-3) / 1e12, "frac": v[3] / (v[0] * 1e-3) / 1e12 / pk["tflops_burst"],
+                                    "traffic": traffic.get(k)}
+                                for k, v in kernels.items()}}
         if gapt:   # HBM-bound path: the roofline is stated on the whole step against the measured copy bandwidth
             gb = gapt_step_bytes(N, wl.get("isab", False))
             ach = value / world * gb / 1e9
             roof = {"bound": "hbm", "kernel": "whole G+D step (attention, projection and dropout kernels)",
                     "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": None,
                     "algorithmic_bytes_per_jet": gb, "peak_source": pk["src"] + " HBM copy"}
-        # CPU baseline: bounded sample of the same workload on the host cores
-        try:
-            if world > 1:   # the CPU baseline is reported at N = 1 only (the other ranks would idle behind it)
-                raise RuntimeError("reported by the 1-GPU run only")
-            bs = cpu_sample_size(wl)
-            sec, cores = cpu_time(wl, N, bs, 2, 1, kind)
-            cpu = {"value": bs / sec, "unit": "jets/s", "cores": cores, "kind": "port",
-                   "sample": f"{bs} jets/step x 2 steps (oracle port of the reference fp32 PyTorch path)"}
-            ge = gpu_eager_baseline(wl, N, kind)
-            if ge is not None:
-                cpu["gpu_eager"] = ge   # the same eager PyTorch code on this B200 (like-for-like GPU baseline)
-        except Exception as e:  # pragma: no cover
-            cpu = {"value": None, "unit": "jets/s", "cores": 0, "kind": "port", "sample": f"not measured: {e}"}
-        line = {
+        cpu = None
+        if with_baselines and world == 1:
+            cpu = {}
+            if with_baselines == "full":   # CPU baseline: bounded sample of the same workload on the host cores
+                try:
+                    bs = min(cpu_sample_size(wl), 64 if not gapt else wl["B"])
+                    sec, cores, how = reference_step_time(wl, bs, 2, 1)
+                    cpu = {"value": bs / sec, "unit": "jets/s", "cores": cores, "kind": how,
+                           "sample": f"{bs} jets/step x 2 steps ({'unmodified reference, oracle/_ref' if how == 'reference' else 'oracle port'}; "
+                                     "the --impl reference arm runs the full batch)"}
+                except Exception as e:  # pragma: no cover
+                    cpu = {"value": None, "unit": "jets/s", "cores": 0, "kind": "port", "sample": f"not measured: {e}"}
+            try:
+                cpu["gpu_eager"] = gpu_eager_baseline(wl)   # the reference's eager PyTorch code on this B200
+            except Exception as e:  # pragma: no cover
+                cpu["gpu_eager"] = {"error": str(e)[:200]}
+        res = {
             "metric": metric_name(wl), "value": value, "unit": "jets/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if gapt else "bf16", "data": "synthetic",
-            "config": {"workload": args.workload, "particles": N, "batch_per_gpu": B, "global_batch": B * world,
-                       "particles_per_jet": "all N real" if args.all_real else "n ~ U{1..N} (padded rows masked)",
+            "config": {"workload": name, "particles": N, "batch_per_gpu": B, "global_batch": B * world,
+                       "particles_per_jet": "all N real" if all_real else "n ~ U{1..N} (padded rows masked)",
                        "batch_order": "jets ordered by particle count inside each batch (GANTrainer.sort_by_count / "
                                       "train.generate); fully padded (tile, sender) steps are dropped by the kernels",
                        "l2": "flushed between timed steps (256 MiB write)",
@@ -526,45 +523,165 @@ def run_ours(args, wl):
             "e2e": {"value": e2e_val, "unit": "jets/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "roofline": roof,
-            "step_roofline": None if gapt else {"algorithmic_gflop_per_jet": alg / 1e9,
-                                                "achieved_tflops": value / world * alg / 1e12,
-                                                "frac_of_peak": value / world * alg / 1e12 / pk["tflops"]},
-            "cpu_baseline": cpu,
             "clocks": clocks,
         }
+        if cpu is not None:
+            res["cpu_baseline"] = cpu
+    # release the graphs (they reference the NCCL communicator) before the next workload / teardown
+    ops.set_device_seed(None)
+    del one_step, eager_step
+    if tr is not None:
+        tr.release()
+    tr = gg = None
+    gc.collect()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    env = Env()
+    env.rank = int(os.environ.get("RANK", "0"))
+    env.world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    env.dev = torch.device("cuda", local)
+    if env.world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the ONE JSON line only
+        dist.init_process_group("nccl", device_id=env.dev)
+    env.flush_buf = torch.empty(256 * 1024 * 1024 // 4, device=env.dev)  # > 126 MB L2
+    env.sampler = ClockSampler(local)
+    if env.rank == 0:
+        env.sampler.start()
+
+    if args.check:
+        line = dp_check(args, env)
+    else:
+        head = args.workload or HEADLINE
+        line = measure(head, WORKLOADS[head], args, env, with_baselines="full")
+        if args.suite and args.workload is None:
+            extra = {}
+            for name in SUITE:
+                try:
+                    r = measure(name, WORKLOADS[name], args, env,
+                                with_baselines="gpu" if name in ("train_n150_b256", "gen_n30_b1024", "gen_n150_b1024",
+                                                                 "train_gapt_n30_b512", "train_gapt_isab_n30_b512") else None)
+                except Exception as e:  # a failing secondary workload must not take the headline down with it
+                    r = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+                    if env.world > 1:
+                        raise
+                if env.rank == 0:
+                    extra[name] = r
+            if env.rank == 0:
+                line["workloads"] = extra
+    if env.rank == 0:
+        env.sampler.stop()
         print(json.dumps(line), flush=True)
-    if world > 1:
-        # every rank stays until rank 0 has printed (a rank that leaves early takes the job down with it), then:
-        # NCCL communicators referenced by a captured CUDA graph do not tear down reliably
-        # (destroy_process_group hung here): everything is measured and printed, so leave at once
-        sys.stdout.flush()
-        try:
-            dist.barrier()
-            torch.cuda.synchronize()
-        except Exception:
-            pass
+    if env.world > 1:
+        teardown(dist, torch)
+
+
+def teardown(dist, torch):
+    """Leave together: every rank stays until rank 0 has printed.  The graphs that referenced the NCCL communicator
+    were released in measure(); destroy_process_group() then returns promptly.  A watchdog bounds the teardown in
+    case a communicator still hangs (it did while captured graphs were alive): everything is measured and printed."""
+    sys.stdout.flush()
+    try:
+        dist.barrier()
+        torch.cuda.synchronize()
+    except Exception:
+        pass
+
+    def _bail():
         sys.stdout.flush()
         sys.stderr.flush()
         os._exit(0)
+
+    wd = threading.Timer(20.0, _bail)
+    wd.daemon = True
+    wd.start()
+    try:
+        dist.destroy_process_group()
+    except Exception:
+        pass
+    wd.cancel()
+
+
+def dp_check(args, env):
+    """1 rank on the global batch vs `world` ranks on its shards, on real NCCL: the averaged flat gradients of D and
+    G and the weights after the RMSprop step must agree (setup_training.py:1418-1421 DataParallel semantics).  Runs
+    eagerly and through the captured graph's own all-reduce path (GANTrainer.train_D / train_G)."""
+    import torch
+    import torch.distributed as dist
+    from mpgan_b200 import ops, presets, train
+
+    dev, rank, world = env.dev, env.rank, env.world
+    N, Bs = 30, 64
+    res = {"check": "dp_gradient_equality", "n_gpus": world, "shard_batch": Bs, "global_batch": Bs * world}
+    for prec in (0, 1):
+        ops.set_precision(prec)
+        g = torch.Generator(device=dev).manual_seed(77)
+        data, labels, _ = train.synthetic_jets(Bs * world, N, dev, g)
+        nd = train.get_gen_noise(Bs * world, N, 32, 0.2, dev, g)
+        ng = train.get_gen_noise(Bs * world, N, 32, 0.2, dev, g)
+        sl = slice(rank * Bs, (rank + 1) * Bs)
+        out = {}
+        for mode in ("sharded", "single"):
+            torch.manual_seed(4)
+            G = presets.mp_generator(num_hits=N).to(dev)
+            D = presets.mp_discriminator(num_hits=N, disc_dropout=0.0).to(dev)
+            sdG, sdD = _golden_weights(dev)
+            G.load_state_dict(sdG)
+            D.load_state_dict(sdD)
+            tr = train.GANTrainer(G, D, num_particles=N, world_override=1 if mode == "single" else None)
+            if mode == "sharded":
+                ld = tr.train_D(data[sl], labels[sl], noise=nd[sl])
+                gD = tr.fpD.grad.clone() / world
+                lg = tr.train_G(labels[sl], noise=ng[sl])
+                gG = tr.fpG.grad.clone() / world
+            else:
+                ld = tr.train_D(data, labels, noise=nd)
+                gD = tr.fpD.grad.clone()
+                lg = tr.train_G(labels, noise=ng)
+                gG = tr.fpG.grad.clone()
+            out[mode] = (gD, gG, tr.fpD.flat.clone(), tr.fpG.flat.clone())
+        rel = lambda a, b: float((a - b).norm() / b.norm().clamp_min(1e-20))
+        errs = {k: rel(out["sharded"][i], out["single"][i]) for i, k in enumerate(("gradD", "gradG", "weightsD", "weightsG"))}
+        t = torch.tensor([max(errs["gradD"], errs["gradG"])], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX) if world > 1 else None
+        res[f"precision{prec}"] = {**errs, "max_over_ranks": float(t)}
+    ops.set_precision(1)
+    res["ok"] = res["precision0"]["max_over_ranks"] < 1e-4 and res["precision1"]["max_over_ranks"] < 3e-2
+    return res
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="run the training step eagerly instead of replaying the captured CUDA graph")
-    ap.add_argument("--workload", default="train_n30_b256", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
+                    help="time this workload only (default: the headline train_n30_b256 plus the suite under 'workloads')")
+    ap.add_argument("--no-suite", dest="suite", action="store_false", help="headline workload only")
     ap.add_argument("--all-real", action="store_true",
                     help="every jet has N real particles (no padding: the unmasked worst case of SURVEY 8d); default n ~ U{1..N}")
+    ap.add_argument("--preload-s", type=float, default=1.0, help="seconds of untimed load before each timed window")
+    ap.add_argument("--check", action="store_true", help="data-parallel gradient-equality check (use under torchrun)")
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
     if args.impl == "reference":
-        run_reference(args, wl)
+        name = args.workload or HEADLINE
+        run_reference(args, name, WORKLOADS[name])
     else:
-        run_ours(args, wl)
+        run_ours(args)
 
 
 if __name__ == "__main__":

@@ -83,7 +83,8 @@ EdgeWs carve_edge_ws(void* base, int B, int N, int F, int H0, int H1, int H2) {
   w.dQ = take(BN * H0);
   w.dxef = take(BN * F);
   // sink for the weight gradients of a dx-only backward on the generic path (never read)
-  w.wg_scratch = take((size_t)H0 * (2 * F + 64) + H0 + (size_t)H1 * H0 + H1 + (size_t)H2 * H1 + H2);
+  // (first-layer rows are 2F + n_ef wide, n_ef <= F + 1)
+  w.wg_scratch = take((size_t)H0 * (3 * F + 1) + H0 + (size_t)H1 * H0 + H1 + (size_t)H2 * H1 + H2);
   w.tc_scratch = p + off;
   off += align_up(edge_tc_scratch_bytes(B, N, H0, H1, H2));
   w.total = off;
@@ -378,13 +379,15 @@ static int edge_bwd_impl(const void* saved, size_t saved_bytes, const float* x, 
   if (pq_supported(F, H0)) {
     if (launch_pq_bwd(w.dP, w.dQ, x, ldx, w0, a.ldwef, dx, lddx, dw0, db0, (int)BN, F, H0, s)) return 1;
   } else {
-    if (launch_colsum(w.dP, H0, (int)BN, H0, db0, s)) return 1;
-    int split = cdiv((long long)BN, 256);
-    if (split > 64) split = 64;
     GemmEpi acc;
     acc.accumulate = 1;
-    if (launch_gemm(false, false, precise, w.dP, H0, x, ldx, dw0, a.ldwef, H0, F, (int)BN, acc, split, s)) return 1;
-    if (launch_gemm(false, false, precise, w.dQ, H0, x, ldx, dw0 + F, a.ldwef, H0, F, (int)BN, acc, split, s)) return 1;
+    if (dw0 != nullptr) {   // null on the tcgen05 path of an input-gradient-only backward (frozen weights)
+      if (launch_colsum(w.dP, H0, (int)BN, H0, db0, s)) return 1;
+      int split = cdiv((long long)BN, 256);
+      if (split > 64) split = 64;
+      if (launch_gemm(false, false, precise, w.dP, H0, x, ldx, dw0, a.ldwef, H0, F, (int)BN, acc, split, s)) return 1;
+      if (launch_gemm(false, false, precise, w.dQ, H0, x, ldx, dw0 + F, a.ldwef, H0, F, (int)BN, acc, split, s)) return 1;
+    }
     GemmEpi e0;
     if (launch_gemm(true, false, precise, w.dP, H0, w0, a.ldwef, dx, lddx, (int)BN, F, H0, e0, 1, s)) return 1;
     if (launch_gemm(true, false, precise, w.dQ, H0, w0 + F, a.ldwef, dx, lddx, (int)BN, F, H0, acc, 1, s)) return 1;

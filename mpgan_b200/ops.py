@@ -46,6 +46,24 @@ def set_direct_grad(on: bool):
     _DIRECT_GRAD = bool(on)
 
 
+class direct_grad:
+    """Context manager scoping the direct-gradient mode (train.GANTrainer wraps its own backward passes in it, so
+    modules outside the trainer keep ordinary autograd semantics: returned gradients, hooks, autograd.grad)."""
+
+    def __init__(self, on: bool = True):
+        self.on = bool(on)
+
+    def __enter__(self):
+        global _DIRECT_GRAD
+        self.prev, _DIRECT_GRAD = _DIRECT_GRAD, self.on
+        return self
+
+    def __exit__(self, *exc):
+        global _DIRECT_GRAD
+        _DIRECT_GRAD = self.prev
+        return False
+
+
 def _grad_sink(p):
     """``p.grad`` if the kernels may accumulate into it directly, else ``None``."""
     if _DIRECT_GRAD and p.is_leaf and p.requires_grad and p.grad is not None and p.grad.is_contiguous() \

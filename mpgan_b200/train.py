@@ -72,9 +72,14 @@ def get_gen_noise(batch_size, num_particles, latent_node_size, sd=0.2, device="c
 
 class GANTrainer:
     def __init__(self, G, D, lr_gen=1e-5, lr_disc=3e-5, num_particles=30, latent_node_size=32, sd=0.2,
-                 process_group=None, batch_real_fake=True, sort_by_count=True):
+                 process_group=None, batch_real_fake=True, sort_by_count=True, world_override=None):
         self.G, self.D = G, D
-        self.batch_real_fake = batch_real_fake
+        # With spectral norm every D forward runs one power iteration (u, v advance; spectral_normalization.py:21-33):
+        # the reference's two calls D(real), D(fake) advance them twice per train_D and use different sigmas, so one
+        # batched pass would not be the same update -> keep the two calls.
+        from .spectral_normalization import SpectralNorm
+        has_sn = any(isinstance(m, SpectralNorm) for m in D.modules())
+        self.batch_real_fake = batch_real_fake and not has_sn
         # step(): order the jets of a batch by particle count.  Jets never interact (no BatchNorm) and both losses
         # are batch means, so the update is the same; what changes is that every 128-particle tile of the edge
         # kernels then holds jets with (nearly) the same padding, and the (tile, sender) steps whose sender is
@@ -82,14 +87,22 @@ class GANTrainer:
         # for n ~ U{1..N}.
         self.sort_by_count = sort_by_count
         self.fpG, self.fpD = FlatParams(G), FlatParams(D)
-        ops.set_direct_grad(True)   # kernels accumulate weight gradients straight into the flat .grad buffers
+        # inside train_D / train_G the kernels accumulate weight gradients straight into the flat .grad buffers
+        # (ops.direct_grad, scoped to the trainer's own backward passes)
         self.optG, self.optD = FusedRMSprop(self.fpG, lr_gen), FusedRMSprop(self.fpD, lr_disc)
         self.num_particles, self.latent, self.sd = num_particles, latent_node_size, sd
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        if world_override is not None:   # e.g. 1: a single-process trainer inside a multi-rank job (bench.py --check)
+            self.world = int(world_override)
         if self.world > 1:  # identical weights on every rank (reference: DataParallel replicate)
             dist.broadcast(self.fpG.flat, 0, group=self.pg)
             dist.broadcast(self.fpD.flat, 0, group=self.pg)
+            # state that is not in the flat buffers: spectral-norm u / v (requires_grad=False) and module buffers
+            for mod in (G, D):
+                extra = [p for p in mod.parameters() if not p.requires_grad] + list(mod.buffers())
+                for t in extra:
+                    dist.broadcast(t.data, 0, group=self.pg)
         # step(): D's gradient all-reduce + RMSprop run on a side stream under train_G's generator forward (which
         # does not read D); train_G joins before its D forward.  Captured as a parallel branch of the step's graph.
         self._comm_stream = None
@@ -135,7 +148,8 @@ class GANTrainer:
             d_both = torch.cat((self.D(data, labels), self.D(fake, labels)), 0)
         # least squares: real -> 1, fake -> 0 (train.py:357-358, 369-370, 378), one kernel
         loss = ops.ls_loss(d_both, B, 1.0, 0.0)
-        loss.backward()
+        with ops.direct_grad():
+            loss.backward()
         if overlap_update and self.world > 1 and data.is_cuda:
             if self._comm_stream is None:
                 self._comm_stream = torch.cuda.Stream(device=data.device)
@@ -158,7 +172,8 @@ class GANTrainer:
         try:
             d_fake = self.D(fake, labels)  # D stays in train mode: its dropout is active (train.py:419,494)
             loss = ops.ls_loss(d_fake, d_fake.shape[0], 1.0)  # train.py:467,472
-            loss.backward()
+            with ops.direct_grad():
+                loss.backward()
         finally:
             for p in self.fpD.params:
                 p.requires_grad_(True)
@@ -203,6 +218,13 @@ class GANTrainer:
             self._static_losses = body()
         self.launches_per_step = int(_lib.lib().mpg_launch_count() - n0)  # our kernels inside one replay
         return self
+
+    def release(self):
+        """Drops the captured graph and its static buffers (the graph references the NCCL communicator: release it
+        before ``destroy_process_group``)."""
+        self._graph = None
+        self._static_losses = self._static_data = self._static_labels = None
+        ops.set_device_seed(None)
 
     def step_graphed(self, data=None, labels=None):
         """Replays the captured step; ``data``/``labels`` (host or device) are copied into the graph's

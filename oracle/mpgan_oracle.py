@@ -31,6 +31,9 @@ class EdgeCfg:
     clabels: int = 0
     mask_fne_np: bool = False
     sum: bool = True
+    fully_connected: bool = True
+    num_knn: int = 20
+    self_loops: bool = True
 
 
 @dataclass
@@ -140,6 +143,34 @@ def pair_tensor(x: Tensor, ec: EdgeCfg) -> Tensor:
     return torch.cat(parts, dim=3).reshape(B * N * N, -1)
 
 
+def knn_pair_tensor(x: Tensor, ec: EdgeCfg, mask: Optional[Tensor]):
+    """k-nearest-neighbour edge inputs (:319-381): A[b, i*k+m] = (x_i | x_nbr(i,m) | [dist]), plus the neighbours'
+    masks.  Distances are taken to the senders scaled by 1e4 where masked (so padded particles are never picked
+    before real ones), over all features unless pos_diffs without all_ef (then the coordinates only); the distance
+    fed to the edge network is the (differentiable) sorted value itself."""
+    B, N, Fdim = x.shape
+    k = ec.num_knn
+    x1 = x.unsqueeze(2).expand(B, N, N, Fdim)
+    x2s = x if mask is None else ((1 - 1e4) * mask + 1e4) * x       # :336-340
+    x2 = x2s.unsqueeze(1).expand(B, N, N, Fdim)
+    nc = 3 if ec.coords == "cartesian" else 2
+    diffs = (x2 - x1) if (ec.all_ef or not ec.pos_diffs) else (x2[..., :nc] - x1[..., :nc])   # :343-346
+    dists = torch.norm(diffs + 1e-12, dim=3)                         # [B, N, N]  (:348)
+    srt = torch.sort(dists, dim=2)                                   # :351
+    s0 = int(ec.self_loops is False)                                 # :354
+    d_k = srt[0][:, :, s0:k + s0].reshape(B, N * k, 1)               # :358-360
+    idx = srt[1][:, :, s0:k + s0].reshape(B, N * k, 1)               # :361-363
+    x1_knn = x.unsqueeze(2).expand(B, N, k, Fdim).reshape(B, N * k, Fdim)   # :366
+    A_mask = None
+    if mask is not None:                                             # :369-374
+        g = torch.gather(torch.cat((x, mask), dim=2), 1, idx.expand(-1, -1, Fdim + 1))
+        A_mask, x2_knn = g[:, :, -1:], g[:, :, :-1]
+    else:
+        x2_knn = torch.gather(x, 1, idx.expand(-1, -1, Fdim))        # :376
+    A = torch.cat((x1_knn, x2_knn, d_k), dim=2) if ec.pos_diffs else torch.cat((x1_knn, x2_knn), dim=2)   # :380-383
+    return A.reshape(B * N * k, -1), A_mask
+
+
 def mp_layer(
     x: Tensor,
     sd: Dict[str, Tensor],
@@ -154,15 +185,22 @@ def mp_layer(
     sn_out: Optional[dict] = None,
 ) -> Tensor:
     B, N, _ = x.shape
-    A = pair_tensor(x, ec)
+    if ec.fully_connected:  # :241-246
+        A, A_mask, K = pair_tensor(x, ec), None, N
+    else:
+        A, A_mask = knn_pair_tensor(x, ec, mask)
+        K = ec.num_knn
     if ec.clabels:  # :247-249  (row r of jet b gets labels[r % B] -- reference quirk of .repeat)
-        A = torch.cat((A, labels[:, : ec.clabels].repeat(N * N, 1)), dim=1)
+        A = torch.cat((A, labels[:, : ec.clabels].repeat(N * K, 1)), dim=1)
     if ec.mask_fne_np:  # :251-253
-        A = torch.cat((A, num_jet_particles.repeat(N * N, 1)), dim=1)
+        A = torch.cat((A, num_jet_particles.repeat(N * K, 1)), dim=1)
     A = linear_net(A, sd, prefix + ".fe", False, alpha, dropout_p, training, sn_out)  # :256
-    A = A.view(B, N, N, -1)
+    A = A.view(B, N, K, -1)
     if mask is not None:
-        A = A * mask.unsqueeze(1)  # sender axis (:262)
+        if ec.fully_connected:
+            A = A * mask.unsqueeze(1)  # sender axis (:262)
+        else:
+            A = A * A_mask.view(B, N, K, 1)  # the gathered neighbours' masks (:264)
     A = A.sum(2) if ec.sum else A.mean(2)  # mean divides by N (:267)
     h = torch.cat((A, x), 2).reshape(B * N, -1)  # :268
     if ec.clabels:
@@ -182,10 +220,10 @@ def rank_mask(x0: Tensor, labels_last: Tensor, num_particles: int) -> Tensor:
     return (x0.argsort(1).argsort(1) <= n.unsqueeze(1)).unsqueeze(2).float()
 
 
-def _run_layers(x, sd, cfg, mask, labels, training, sn_out):
+def _run_layers(x, sd, cfg, mask, labels, training, sn_out, num_jet_particles=None):
     for i in range(cfg.mp_iters):
         x = mp_layer(
-            x, sd, f"mp_layers.{i}", cfg.layer(i), mask, labels, None,
+            x, sd, f"mp_layers.{i}", cfg.layer(i), mask, labels, num_jet_particles,
             cfg.alpha, cfg.dropout_p, training, sn_out,
         )
     return x
@@ -211,7 +249,8 @@ def discriminator(sd, x: Tensor, labels: Optional[Tensor], cfg: NetCfg, training
     if cfg.mask_c:
         mask = x[:, :, -1:] + 0.5  # real-valued multiplier (:881)
         x = x[:, :, :-1]  # :884
-    x = _run_layers(x, sd, cfg, mask, labels, training, sn_out)
+    njp = mask.mean(1) if (mask is not None and any(l.mask_fne_np for l in cfg.layers)) else None  # :886-887
+    x = _run_layers(x, sd, cfg, mask, labels, training, sn_out, njp)
     do_mean = not (cfg.dea and cfg.dea_sum)  # :811-813
     if mask is not None:
         x = (x * mask).sum(1)  # :816-817
@@ -239,6 +278,22 @@ def d_loss_ls(real_out: Tensor, fake_out: Tensor) -> Tensor:
 
 def g_loss_ls(fake_out: Tensor) -> Tensor:
     return F.mse_loss(fake_out, torch.ones_like(fake_out))  # train.py:467,472
+
+
+def gradient_penalty(sdD, cfgD: NetCfg, real: Tensor, fake: Tensor, alpha: Tensor, gp_lambda: float,
+                     training: bool = True) -> Tensor:
+    """WGAN-GP term (train.py:286-324): D at x = alpha*real + (1-alpha)*fake, the gradient of sum(D(x)) w.r.t. x with
+    the graph kept, gp = lambda * mean((sqrt(sum_jet grad^2 + 1e-12) - 1)^2).  ``alpha`` [B,1,1] is the uniform draw
+    the reference makes first (:289-293); D is called WITHOUT labels (:303)."""
+    x = (alpha * real + (1 - alpha) * fake).detach().requires_grad_(True)
+    out = discriminator(sdD, x, None, cfgD, training=training)
+    (g,) = torch.autograd.grad(out, x, grad_outputs=torch.ones_like(out), create_graph=True, retain_graph=True)
+    gn = torch.sqrt(torch.sum(g.reshape(x.shape[0], -1) ** 2, dim=1) + 1e-12)
+    return gp_lambda * ((gn - 1) ** 2).mean()
+
+
+def d_loss_w(real_out: Tensor, fake_out: Tensor) -> Tensor:
+    return -real_out.mean() + fake_out.mean()  # train.py:371-373
 
 
 def rmsprop_step(p: Tensor, g: Tensor, sq: Tensor, lr: float, alpha=0.99, eps=1e-8):

@@ -154,3 +154,123 @@ def test_train_step(golden):
         g = c["gradsD"][k]
         ok = g.abs() > 1e-3 * g.abs().max()
         assert float((sdD[k].detach() - v)[ok].abs().max()) < 2e-6
+
+
+# ---- round-2 fixtures --------------------------------------------------------------------------------
+def test_large_n_gradients(golden):
+    cases = golden("disc_fwd_bwd_large.pt")
+    c = cases["d_n100"]
+    sd = leafify(golden("mp_d_seed4_weights.pt"))
+    cfg = mo.NetCfg(num_particles=100, final_activation="sigmoid", layers=D_CFG.layers)
+    x = c["x"].clone().requires_grad_(True)
+    out = mo.discriminator(sd, x, c["labels"], cfg, training=True)
+    close(out, c["out"])
+    mo.g_loss_ls(out).backward()
+    close(x.grad, c["dx"], 1e-4)
+    for k, g in c["grads"].items():
+        close(sd[k].grad, g, 1e-4)
+    for N in (100, 150):
+        c = cases[f"g_through_d_n{N}"]
+        sdG, sdD = leafify(golden("mp_g_weights.pt")), golden("mp_d_seed4_weights.pt")
+        cg = mo.NetCfg(num_particles=N, final_activation="tanh")
+        cd = mo.NetCfg(num_particles=N, final_activation="sigmoid", layers=D_CFG.layers)
+        fake = mo.generator(sdG, c["noise"], c["labels"], cg, training=True)
+        close(fake, c["fake"], 1e-5)
+        loss = mo.g_loss_ls(mo.discriminator(sdD, fake, c["labels"], cd, training=True))
+        close(loss, c["loss"])
+        loss.backward()
+        for k, g in c["grads"].items():
+            close(sdG[k].grad, g, 2e-4)
+
+
+def test_net_variants(golden):
+    cases = golden("net_variants.pt")
+    c = cases["lfc"]
+    sd = leafify(c["sd"])
+    out = mo.generator(sd, c["noise"], c["labels"], mo.NetCfg(final_activation="tanh", lfc=True), training=True)
+    assert torch.equal(out[..., 3], c["out"][..., 3])
+    close(out, c["out"], 1e-5)
+    (out * c["w"]).sum().backward()
+    for k, g in c["grads"].items():
+        close(sd[k].grad, g, 1e-4)
+    for name in ("dea_false", "sum_false"):
+        c = cases[name]
+        sd = leafify(c["sd"])
+        s = c["over"].get("sum", True)
+        cfg = mo.NetCfg(final_activation="sigmoid", dea=c["over"].get("dea", True), dea_sum=s,
+                        layers=[mo.EdgeCfg(all_ef=False, sum=s), mo.EdgeCfg(sum=s)])
+        x = c["x"].clone().requires_grad_(True)
+        out = mo.discriminator(sd, x, c["labels"], cfg, training=True)
+        close(out, c["out"])
+        mo.g_loss_ls(out).backward()
+        close(x.grad, c["dx"], 1e-4)
+        for k, g in c["grads"].items():
+            close(sd[k].grad, g, 1e-4)
+
+
+def test_train_step_n100(golden):
+    c = golden("train_step_n100.pt")
+    sdG, sdD = leafify(golden("mp_g_weights.pt")), leafify(golden("mp_d_seed4_weights.pt"))
+    cg = mo.NetCfg(num_particles=100, final_activation="tanh")
+    cd = mo.NetCfg(num_particles=100, final_activation="sigmoid", layers=D_CFG.layers)
+    r = mo.gd_step(sdG, sdD, cg, cd, c["data"], c["labels"], c["noise_d"], c["noise_g"], lr_d=c["lr_d"], lr_g=c["lr_g"])
+    assert abs(r["loss_d"] - c["loss_d"]) < 1e-5 and abs(r["loss_g"] - c["loss_g"]) < 1e-5
+    for k, g in c["gradsD"].items():
+        close(r["grads_d"][k], g, 1e-4)
+    for k, g in c["gradsG"].items():
+        close(r["grads_g"][k], g, 3e-4)
+
+
+def test_wgan_gp(golden):
+    for name, c in golden("wgan_gp.pt").items():
+        sd = leafify(c["sd"])
+        cfg = mo.NetCfg(final_activation="", mask_c=c["over"].get("mask_c", True), layers=D_CFG.layers)
+        gp = mo.gradient_penalty(sd, cfg, c["real"], c["fake"], c["alpha"], 10.0)
+        close(gp, c["gp"], 1e-4)
+        gp.backward()
+        for k, g in c["gp_grads"].items():
+            close(sd[k].grad, g, 2e-4)
+        # first-order input gradient, mask channel included
+        xi = (c["alpha"] * c["real"] + (1 - c["alpha"]) * c["fake"]).requires_grad_(True)
+        (gi,) = torch.autograd.grad(mo.discriminator(sd, xi, None, cfg, training=True).sum(), xi)
+        close(gi, c["dx_interp"], 1e-4)
+        for v in sd.values():
+            v.grad = None
+        dl = mo.d_loss_w(mo.discriminator(sd, c["real"].clone(), c["labels"], cfg, training=True),
+                         mo.discriminator(sd, c["fake"], c["labels"], cfg, training=True)) + \
+            mo.gradient_penalty(sd, cfg, c["real"], c["fake"], c["alpha"], 10.0)
+        close(dl, c["d_loss"], 1e-4)
+        dl.backward()
+        for k, g in c["d_loss_grads"].items():
+            close(sd[k].grad, g, 2e-4)
+
+
+def test_mplayer_variants2(golden):
+    """kNN message passing and the conditioning columns (clabels / mask_fne_np)."""
+    for name, c in golden("mplayer_variants2.pt").items():
+        sd = leafify({"l." + k: v for k, v in c["sd"].items()})
+        ec = mo.EdgeCfg(**c["kw"])
+        x = c["x"].clone().requires_grad_(True)
+        out = mo.mp_layer(x, sd, "l", ec, c["mask"], c["labels"], c["njp"])
+        close(out, c["out"], 5e-5)
+        (out * c["w"]).sum().backward()
+        close(x.grad, c["dx"], 2e-4)
+        for k, g in c["grads"].items():
+            close(sd["l." + k].grad, g, 2e-4)
+
+
+def test_gapt_layernorm(golden):
+    for name, c in golden("gapt_layernorm.pt").items():
+        cfg = go.GaptCfg(sab_layers=2, use_isab=(name == "isab"), layer_norm=True)
+        sdG, sdD = leafify(c["sdG"]), leafify(c["sdD"])
+        noise = c["noise"].clone().requires_grad_(True)
+        fake = go.gapt_g(sdG, noise, c["labels"], cfg)
+        close(fake, c["fake"])
+        dout = go.gapt_d(sdD, fake, c["labels"], cfg)
+        close(dout, c["dout"])
+        mo.g_loss_ls(dout).backward()
+        close(noise.grad, c["dnoise"], 1e-4)
+        for k, g in c["gradsG"].items():
+            close(sdG[k].grad, g, 1e-4)
+        for k, g in c["gradsD"].items():
+            close(sdD[k].grad, g, 1e-4)
