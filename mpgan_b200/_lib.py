@@ -10,7 +10,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmpgan_b200.so")
+_VARIANT = os.environ.get("MPG_LIB_VARIANT", "")   # experiment / trace builds (mpgan_b200/build.py)
+LIB_PATH = os.path.join(_HERE, "lib", f"libmpgan_b200{'_' + _VARIANT if _VARIANT else ''}.so")
 
 _f = C.c_void_p  # device pointers travel as integers
 _i, _fl, _u64, _u32, _sz = C.c_int, C.c_float, C.c_uint64, C.c_uint32, C.c_size_t

@@ -15,7 +15,11 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
-LIB = os.path.join(LIBDIR, "libmpgan_b200.so")
+# MPG_LIB_VARIANT=<tag> builds an experiment / trace variant (its own flags, objects and file name:
+# lib/libmpgan_b200_<tag>.so, loaded when MPG_LIB_VARIANT is set at import time) next to the product library
+VARIANT = os.environ.get("MPG_LIB_VARIANT", "")
+LIB = os.path.join(LIBDIR, f"libmpgan_b200{'_' + VARIANT if VARIANT else ''}.so")
+OBJDIR = os.path.join(LIBDIR, "obj" + ("_" + VARIANT if VARIANT else ""))
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + os.environ.get("MPG_NVCC_FLAGS", "").split()
@@ -32,13 +36,13 @@ def _newest_header():
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    os.makedirs(os.path.join(LIBDIR, "obj"), exist_ok=True)
+    os.makedirs(OBJDIR, exist_ok=True)
     hdr = _newest_header()
     jobs = []
     objs = []
     for src in _sources():
         s = os.path.join(CSRC, src)
-        o = os.path.join(LIBDIR, "obj", src[:-3] + ".o")
+        o = os.path.join(OBJDIR, src[:-3] + ".o")
         objs.append(o)
         if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(s), hdr):
             jobs.append((s, o))

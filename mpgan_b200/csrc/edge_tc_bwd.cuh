@@ -198,6 +198,7 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
           const uint32_t par = it & 1;
           // ---- M2: D2 = H1'(TMEM RA) W2'^T -> RB ---------------------------------------------------------
           mbar_wait(ubar + BwdBars::rdyB, par);
+          MPG_TR(it, 11);
           tc_fence_after();
           if (elect_one()) {
             opaque(dW2);
@@ -209,8 +210,10 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
             umma_commit(ubar + BwdBars::doneB);
           }
           __syncwarp();
+          MPG_TR(it, 12);
           // ---- M3: dH1 = G2'(TMEM RB) W2' (B = W2 image read MN-major: N = 160 inputs, K = 192 outputs) -> RA
           mbar_wait(ubar + BwdBars::rdyC, par);
+          MPG_TR(it, 13);
           tc_fence_after();
           if (elect_one()) {
             uint64_t dB = umma_desc_mn(ub + OFF_W2, W2_BLK);
@@ -223,6 +226,7 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
           __syncwarp();
           // ---- M5: dW1^T += H0'^T G1' (both MN-major from shared memory); M4: dH0 = G1'(TMEM RA) W1' -> RB+96
           mbar_wait(ubar + BwdBars::rdyD, par);
+          MPG_TR(it, 14);
           tc_fence_after();
           if (elect_one()) {
             uint64_t dA = umma_desc_mn(ub + C_OFF_H0, A_BLK), dB = umma_desc_mn(ub + C_OFF_X, A_BLK);
@@ -248,6 +252,7 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
           }
           // ---- M7: per-jet column sums of G0' = rows 98+j of H0'^T G0' -> RB[0,96) --------------------------------
           mbar_wait(ubar + BwdBars::rdyE, par);
+          MPG_TR(it, 15);
           tc_fence_after();
           if (elect_one()) {
             uint64_t dA = umma_desc_mn(ub + C_OFF_H0, A_BLK), dB = umma_desc_mn(ub + C_OFF_X, A_BLK);
@@ -456,7 +461,9 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
 
         // ---- E1: D1 -> H1' (+ sign words): chunks 0..2, then 3..4 (24 / 16 live values) -----------------------------
         uint32_t s1[2] = {0, 0};
+        MPG_TRW(it, 0);
         mbar_wait(bar0 + BwdBars::doneA, par);
+        MPG_TRW(it, 1);
         tc_fence_after();
         auto e1_round = [&](auto RND) {
           constexpr int rnd = decltype(RND)::value, nc = rnd == 0 ? 3 : 2, c0 = rnd * 3;
@@ -504,12 +511,14 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
         }
         tc_fence_before();
         mbar_arrive(bar0 + BwdBars::rdyB);
+        MPG_TRW(it, 2);
 
         // ---- G2' = dAgg * m * keep2 * (1 + cg sgn D2) ----------------------------------------------------------------
         const uint32_t U_POS = bf16x2_dup(mfac), U_NEG = bf16x2_dup(mfac * a.alpha);
         if constexpr (CH) {
           uint2 sb{0, 0};
           mbar_wait(bar0 + BwdBars::doneB, par);
+          MPG_TRW(it, 3);
           tc_fence_after();
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -543,6 +552,7 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(bar0 + BwdBars::rdyC);
+          MPG_TRW(it, 4);
         } else {
           const uint2 sb = t.sbits[(size_t)(g0 + it) * F_NEPI + threadIdx.x];
           uint32_t g2w[Q2 / 2];
@@ -572,6 +582,7 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
         if constexpr (CH) {
           // ---- E3: G1' = dH1 * keep1 * (1 + cg sgn D1) -> TMEM in place (A of M4) and shared memory (B of M5) ---------
           mbar_wait(bar0 + BwdBars::doneC, par);
+          MPG_TRW(it, 5);
           tc_fence_after();
           auto e3_round = [&](auto RND) {
             constexpr int rnd = decltype(RND)::value, nc = rnd == 0 ? 3 : 2, c0 = rnd * 3;
@@ -609,13 +620,17 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
           fence_async_smem();
           tc_fence_before();
           mbar_arrive(bar0 + BwdBars::rdyD);
+          MPG_TRW(it, 6);
 
           // ---- H0' of the next step under M4 (M5 has released the H0' tile and X) ---------------------------------------
           mbar_wait(bar0 + BwdBars::doneD5, par);
+          MPG_TRW(it, 7);
           if (it + 1 < nsteps) build_h0(it + 1);
+          MPG_TRW(it, 8);
 
           // ---- E4: G0' = dH0 * keep0 * (1 + cg sgn pre0): dP in registers, bf16 tile for the dQ MMA ----------------------
           mbar_wait(bar0 + BwdBars::doneD4, par);
+          MPG_TRW(it, 9);
           tc_fence_after();
           {
             float v[Q0];
@@ -644,6 +659,7 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
           fence_async_smem();
           tc_fence_before();
           mbar_arrive(bar0 + BwdBars::rdyE);
+          MPG_TRW(it, 10);
           s0 = s0_next;
           k0w = k0w_next;
           // remember where this step's dQ sums belong, then advance

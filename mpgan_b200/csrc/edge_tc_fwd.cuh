@@ -70,12 +70,17 @@ __device__ long long* g_trace = nullptr;
   do {                                                                                           \
     if (g_trace && blockIdx.x == 0 && lane == 0 && (it) < 256) g_trace[(it) * 16 + (slot)] = clock64(); \
   } while (0)
+#define MPG_TRW(it, slot)                                                                       \
+  do {                                                                                           \
+    if (g_trace && blockIdx.x == 0 && threadIdx.x == 0 && (it) < 256) g_trace[(it) * 16 + (slot)] = clock64(); \
+  } while (0)
 #define MPG_TP(slot)                                                                              \
   do {                                                                                            \
     if (g_trace && blockIdx.x == 0 && threadIdx.x == 0) g_trace[4080 + (slot)] = clock64();       \
   } while (0)
 #else
 #define MPG_TR(it, slot) do { } while (0)
+#define MPG_TRW(it, slot) do { } while (0)
 #define MPG_TP(slot) do { } while (0)
 #endif
 

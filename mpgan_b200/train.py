@@ -180,28 +180,52 @@ class GANTrainer:
         self.optG.step(self._allreduce(self.fpG))
         return loss.detach()
 
-    def step(self, data, labels):
-        """One critic + one generator update (train.py:841-878 with num_critic = num_gen = 1)."""
+    def step(self, data, labels, noise_d=None, noise_g=None):
+        """One critic + one generator update (train.py:841-878 with num_critic = num_gen = 1).  ``noise_d`` /
+        ``noise_g``: explicit generator noise per jet (reproducible runs, parity tests); drawn when None."""
         if self.sort_by_count:
-            data, labels = sort_by_count(data, labels)
-        return self.train_D(data, labels, overlap_update=True), self.train_G(labels)
+            if noise_d is not None or noise_g is not None:
+                pos = ops.batch_order(labels)
+                noise_d = None if noise_d is None else ops.permute_batch(noise_d, pos, 0)
+                noise_g = None if noise_g is None else ops.permute_batch(noise_g, pos, 0)
+                data, labels = ops.permute_batch(data, pos, 0), ops.permute_batch(labels, pos, 0)
+            else:
+                data, labels = sort_by_count(data, labels)
+        return self.train_D(data, labels, noise_d, overlap_update=True), self.train_G(labels, noise_g)
+
+    def state(self):
+        """Clones of everything a step changes (weights and RMSprop accumulators)."""
+        return [t.clone() for t in (self.fpG.flat, self.fpD.flat, self.optG.square_avg, self.optD.square_avg)]
+
+    def load_state(self, st):
+        for t, v in zip((self.fpG.flat, self.fpD.flat, self.optG.square_avg, self.optD.square_avg), st):
+            t.copy_(v)
 
     # -- whole-step CUDA graph (SURVEY 8f rank 1) ---------------------------------------------------
-    def capture(self, data, labels, warmup=3):
+    def capture(self, data, labels, warmup=3, explicit_noise=False, keep_state=False):
         """Captures train_D + train_G (kernels, NCCL all-reduces, RMSprop) into one CUDA graph.
 
-        Noise is drawn inside the graph (torch's graph-safe Philox state); dropout masks change on
-        every replay because the kernels add a device-resident counter, bumped in-graph, to their
-        seeds.  Returns self; afterwards ``step_graphed`` replays the graph on new batches.
+        Noise is drawn inside the graph (torch's graph-safe Philox state) unless ``explicit_noise``: then
+        ``step_graphed`` takes the two noise tensors as inputs.  Dropout masks change on every replay because the
+        kernels add a device-resident counter, bumped in-graph, to their seeds.  The warm-up and capture passes are
+        real steps on the static batch; ``keep_state`` restores weights and optimizer state afterwards.  Returns
+        self; afterwards ``step_graphed`` replays the graph on new batches.
         """
         dev = data.device
         self._static_data = data.clone()
         self._static_labels = labels.clone()
+        self._static_noise = None
+        if explicit_noise:
+            self._static_noise = tuple(get_gen_noise(data.shape[0], self.num_particles, self.latent, self.sd, dev)
+                                       for _ in range(2))
         self._seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         ops.set_device_seed(self._seed_dev)
+        saved = self.state() if keep_state else None
 
         def body():
             self._seed_dev.add_(0x9E3779B97F4A7C15 >> 1)
+            if self._static_noise is not None:
+                return self.step(self._static_data, self._static_labels, *self._static_noise)
             return self.step(self._static_data, self._static_labels)
 
         side = torch.cuda.Stream(device=dev)
@@ -217,22 +241,31 @@ class GANTrainer:
         with torch.cuda.graph(self._graph):
             self._static_losses = body()
         self.launches_per_step = int(_lib.lib().mpg_launch_count() - n0)  # our kernels inside one replay
+        if saved is not None:
+            torch.cuda.synchronize()
+            self.load_state(saved)
+            self._seed_dev.zero_()
         return self
 
     def release(self):
         """Drops the captured graph and its static buffers (the graph references the NCCL communicator: release it
         before ``destroy_process_group``)."""
         self._graph = None
-        self._static_losses = self._static_data = self._static_labels = None
+        self._static_losses = self._static_data = self._static_labels = self._static_noise = None
         ops.set_device_seed(None)
 
-    def step_graphed(self, data=None, labels=None):
+    def step_graphed(self, data=None, labels=None, noise_d=None, noise_g=None):
         """Replays the captured step; ``data``/``labels`` (host or device) are copied into the graph's
         static input buffers first (``non_blocking`` so pinned host batches stream in)."""
         if data is not None:
             self._static_data.copy_(data, non_blocking=True)
         if labels is not None:
             self._static_labels.copy_(labels, non_blocking=True)
+        if noise_d is not None or noise_g is not None:
+            if self._static_noise is None:
+                raise RuntimeError("the step was captured with in-graph noise; capture(explicit_noise=True) to pass it")
+            self._static_noise[0].copy_(noise_d, non_blocking=True)
+            self._static_noise[1].copy_(noise_g, non_blocking=True)
         self._graph.replay()
         return self._static_losses
 

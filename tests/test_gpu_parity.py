@@ -7,7 +7,10 @@ Tolerances (max abs error / max abs of the reference tensor):
   precision 1: 3e-2 forward (bf16 operands, fp32 accumulate); 5e-2 for the generator at
                N >= 100 (the N=30 weights summed over 100-150 senders: the bf16 operand noise of the edge
                network grows with the number of messages).
-               Gradients: 8e-2 in RELATIVE L2 NORM (||a-b|| / ||b||) plus a 2e-1 max-abs guard.  Through
+               Gradients: 8e-2 in RELATIVE L2 NORM (||a-b|| / ||b||) plus a 1.6e-1 max-abs guard -- the per-tensor
+               table profiles/r2_error_table.txt (every golden case, both precisions) shows worst cases of 7.7e-2 /
+               1.34e-1 for generator gradients taken through four message-passing layers and 3.6e-2 / 8.2e-2 for the
+               discriminator's own.  Through
                2-4 message-passing layers the max-abs error is set by a handful of elements whose
                near-zero pre-activation lands on the other leaky-relu slope (1 vs 0.2) once operands are
                rounded to bf16; the L2 norm is the stable statement of the same accuracy.
@@ -22,7 +25,7 @@ from oracle import mpgan_oracle as mo
 pytestmark = pytest.mark.gpu
 
 TOL = {0: (1e-4, 1e-3), 1: (3e-2, 8e-2)}
-GRAD_MAX_GUARD = 2e-1
+GRAD_MAX_GUARD = 1.6e-1    # measured worst case 1.34e-1 (profiles/r2_error_table.txt)
 
 
 def rel(a, b):
