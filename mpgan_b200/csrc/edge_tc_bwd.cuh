@@ -102,8 +102,14 @@ __device__ __forceinline__ uint32_t bf16x2_dup(float v) {
 }
 
 struct BwdBars {   // byte offsets from the barrier block
-  static constexpr uint32_t w = 0, rdyA = 8, rdyB = 16, rdyC = 24, rdyD = 32, rdyE = 40, doneA = 48, doneB = 56,
-                            doneC = 64, doneD5 = 72, doneD4 = 80, doneE = 88, q = 96 /* [4] */, qe = 128 /* [4] */;
+  // rdy*: signalled by the 16 epilogue warps (one arrival each); done*: tcgen05.commit of the issuer.
+  // CHAIN splits its hand-offs so that an MMA starts on the part of its operand that exists already:
+  //   rdyB / rdyB1   H1' K columns [0,96) / [96,176) written (E1 rounds 0 / 1)   -> M2 K steps 0..5 / 6..10
+  //   doneB / doneB1 D2 low / high N half complete                                  -> E2 half 0 / 1
+  //   rdyC / rdyC1   G2' low / high half written                                    -> M3 K steps 0..5 / 6..11
+  static constexpr uint32_t w = 0, rdyA = 8, rdyB = 16, rdyB1 = 24, rdyC = 32, rdyC1 = 40, rdyD = 48, rdyE = 56,
+                            doneA = 64, doneB = 72, doneB1 = 80, doneC = 88, doneD5 = 96, doneD4 = 104, doneE = 112,
+                            q = 128 /* [4] */, qe = 160 /* [4] */;
 };
 
 template <int MODE, bool DROP>
@@ -130,11 +136,12 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
 
   if (threadIdx.x == 0) {
     mbar_init(bar0 + BwdBars::w, 1);
-    for (uint32_t b = BwdBars::rdyA; b <= BwdBars::rdyE; b += 8) mbar_init(bar0 + b, F_NEPI);
+    for (uint32_t b = BwdBars::rdyA; b <= BwdBars::rdyE; b += 8) mbar_init(bar0 + b, F_NEPIW);
     for (uint32_t b = BwdBars::doneA; b <= BwdBars::doneE; b += 8) mbar_init(bar0 + b, 1);
+    static_assert(BwdBars::rdyE + 8 == BwdBars::doneA && BwdBars::qe + 32 <= 192, "barrier block layout");
     for (int i = 0; i < 4; ++i) {
       mbar_init(bar0 + BwdBars::q + 8 * i, 1);
-      mbar_init(bar0 + BwdBars::qe + 8 * i, F_NEPI);
+      mbar_init(bar0 + BwdBars::qe + 8 * i, F_NEPIW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -158,19 +165,28 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
         mbar_expect_tx_elect(ubar + BwdBars::w, W1_BYTES);
         bulk_g2s_elect(ub + OFF_W1, t.w1img, W1_BYTES, ubar + BwdBars::w);
       }
+      int2 ts = steps[0];
       for (int it = 0; it < nsteps; ++it) {
+        const int2 ts_next = steps[it + 1 < nsteps ? it + 1 : it];   // in flight while this step's copies are issued
         const int st = it % QS;
         if (it >= QS) mbar_wait(ubar + BwdBars::qe + 8 * st, (it / QS - 1) & 1);
-        const int2 ts = steps[it];
         const int q_tile = ts.x, q_s = ts.y;
         const int j0 = (q_tile * TILE) / N;
         const int rl = min(q_tile * TILE + TILE - 1, BN - 1);
         const int nj = rl / N - j0 + 1;
         const uint32_t bar = ubar + BwdBars::q + 8 * st;
         const uint32_t dst = ub + OFF_QR + (uint32_t)st * F_QSTAGE;
+        // stage header (tile, sender, the sender's mask in each jet of the tile): see edge_tc_fwd.cuh
+        if (lane < nj) {
+          const float mv = a.mask ? __ldg(a.mask + (size_t)(j0 + lane) * N + q_s) : 1.f;
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst + F_QHDR + 8 + 4 * (uint32_t)lane), "f"(mv) : "memory");
+        }
+        if (lane == 0) asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(dst + F_QHDR), "r"(q_tile), "r"(q_s) : "memory");
+        __syncwarp();
         mbar_expect_tx_elect(bar, (uint32_t)nj * F_QROW);
         for (int j = 0; j < nj; ++j)
           bulk_g2s_elect(dst + (uint32_t)j * F_QROW, a.Q + ((size_t)(j0 + j) * N + q_s) * K0, F_QROW, bar);
+        ts = ts_next;
       }
     } else if (warp == 16 && nsteps > 0) {
       // =============================== MMA issuer ======================================================
@@ -196,22 +212,46 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
         uint64_t dW2 = umma_desc(ub + OFF_W2);
         for (int it = 0; it < nsteps; ++it) {
           const uint32_t par = it & 1;
-          // ---- M2: D2 = H1'(TMEM RA) W2'^T -> RB ---------------------------------------------------------
+          // ---- M2: D2 = H1'(TMEM RA) W2'^T -> RB as two N = 96 halves.  K steps 0..5 read H1' columns [0,96), which
+          // E1's first round has written (rdyB); the rest follows after the second round (rdyB1).  The low half is
+          // committed first so that E2 starts on it while the high half is still in the tensor pipe.
           mbar_wait(ubar + BwdBars::rdyB, par);
           MPG_TR(it, 11);
           tc_fence_after();
           if (elect_one()) {
             opaque(dW2);
 #pragma unroll
-            for (uint32_t ks = 0; ks < KSTEPS2; ++ks) {
+            for (uint32_t ks = 0; ks < 6; ++ks) {
               const uint32_t blk = ks >> 2, j = ks & 3;
-              umma_bf16_ts(tmem + C_RB, tmem + C_RA + ks * 8, dW2 + ((blk * W2_BLK + j * 32) >> 4), umma_idesc(N2), ks);
+              umma_bf16_ts(tmem + C_RB, tmem + C_RA + ks * 8, dW2 + ((blk * W2_BLK + j * 32) >> 4), umma_idesc(NH2), ks);
+              umma_bf16_ts(tmem + C_RB + NH2, tmem + C_RA + ks * 8, dW2 + ((blk * W2_BLK + NH2 * 128 + j * 32) >> 4),
+                           umma_idesc(NH2), ks);
+            }
+          }
+          __syncwarp();
+          mbar_wait(ubar + BwdBars::rdyB1, par);
+          tc_fence_after();
+          if (elect_one()) {
+            opaque(dW2);
+#pragma unroll
+            for (uint32_t ks = 6; ks < KSTEPS2; ++ks) {
+              const uint32_t blk = ks >> 2, j = ks & 3;
+              umma_bf16_ts(tmem + C_RB, tmem + C_RA + ks * 8, dW2 + ((blk * W2_BLK + j * 32) >> 4), umma_idesc(NH2), 1u);
             }
             umma_commit(ubar + BwdBars::doneB);
+#pragma unroll
+            for (uint32_t ks = 6; ks < KSTEPS2; ++ks) {
+              const uint32_t blk = ks >> 2, j = ks & 3;
+              umma_bf16_ts(tmem + C_RB + NH2, tmem + C_RA + ks * 8, dW2 + ((blk * W2_BLK + NH2 * 128 + j * 32) >> 4),
+                           umma_idesc(NH2), 1u);
+            }
+            umma_commit(ubar + BwdBars::doneB1);
           }
           __syncwarp();
           MPG_TR(it, 12);
-          // ---- M3: dH1 = G2'(TMEM RB) W2' (B = W2 image read MN-major: N = 160 inputs, K = 192 outputs) -> RA
+          // ---- M3: dH1 = G2'(TMEM RB) W2' (B = W2 image read MN-major: N = 160 inputs, K = 192 outputs) -> RA.
+          // K steps 0..5 take the low half of G2' (rdyC), 6..11 the high half (rdyC1).  RA still holds H1' until M2's
+          // last K step has executed: the tensor pipe runs the MMAs of one CTA in issue order.
           mbar_wait(ubar + BwdBars::rdyC, par);
           MPG_TR(it, 13);
           tc_fence_after();
@@ -219,8 +259,18 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
             uint64_t dB = umma_desc_mn(ub + OFF_W2, W2_BLK);
             opaque(dB);
 #pragma unroll
-            for (uint32_t ks = 0; ks < N2 / 16; ++ks)
+            for (uint32_t ks = 0; ks < 6; ++ks)
               umma_bf16_ts(tmem + C_RA, tmem + C_RB + ks * 8, dB + ((ks * 2048) >> 4), umma_idesc_t(N1, 0, 1), ks);
+          }
+          __syncwarp();
+          mbar_wait(ubar + BwdBars::rdyC1, par);
+          tc_fence_after();
+          if (elect_one()) {
+            uint64_t dB = umma_desc_mn(ub + OFF_W2, W2_BLK);
+            opaque(dB);
+#pragma unroll
+            for (uint32_t ks = 6; ks < N2 / 16; ++ks)
+              umma_bf16_ts(tmem + C_RA, tmem + C_RB + ks * 8, dB + ((ks * 2048) >> 4), umma_idesc_t(N1, 0, 1), 1u);
             umma_commit(ubar + BwdBars::doneC);
           }
           __syncwarp();
@@ -326,7 +376,11 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
 
       // ---- H0' builder state -------------------------------------------------------------------------------
       int h_loaded = -1, h_r = 0;
-      uint32_t h_qoff = 0;
+      uint32_t h_qoff = 0, h_moff = 0;
+      bool h_valid = false;
+      // record of the step whose H0' was built last (tile, sender, this row's mask multiplier)
+      int n_tile = -1, n_s = 0;
+      float n_m = 0.f;
       auto write_onehot = [&](int tile) {   // CHAIN: constant-1 columns 96,97 and one-hot jet columns 98+j of the H0' tile
         if (q == 0) {
           const int r = tile * TILE + row;
@@ -349,14 +403,19 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
         }
       };
       auto build_h0 = [&](int it) {
-        const int2 hts = steps[it];
-        const int h_tile = hts.x, h_s = hts.y;
+        mbar_wait(bar0 + BwdBars::q + 8 * (it % QS), (it / QS) & 1);
+        const uint32_t stage = sQ + (uint32_t)(it % QS) * F_QSTAGE;
+        int h_tile, h_s;
+        asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(h_tile), "=r"(h_s) : "r"(stage + F_QHDR));
         if (h_tile != h_loaded) {
           h_loaded = h_tile;
           const int r = h_tile * TILE + row;
           const int rc = r < BN ? r : BN - 1;
           h_r = rc;
-          h_qoff = (uint32_t)(rc / N - (h_tile * TILE) / N) * F_QROW + (uint32_t)q * 32u;
+          h_valid = r < BN;
+          const uint32_t jl = (uint32_t)(rc / N - (h_tile * TILE) / N);
+          h_moff = F_QHDR + 8 + 4 * jl;
+          h_qoff = jl * F_QROW + (uint32_t)q * 32u;
           const float* p = a.P + (size_t)rc * K0 + q * 8;
 #pragma unroll
           for (int c = 0; c < Q0 / 8; ++c) {
@@ -366,9 +425,13 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
             Preg[8 * c + 4] = v1.x; Preg[8 * c + 5] = v1.y; Preg[8 * c + 6] = v1.z; Preg[8 * c + 7] = v1.w;
           }
         }
+        {
+          float mv;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(mv) : "r"(stage + h_moff));
+          n_tile = h_tile; n_s = h_s; n_m = h_valid ? mv : 0.f;
+        }
         if (DROP) k0w_next = edge_drop_bits(drop.seed, (uint64_t)h_r * N + h_s, q, 0).x;
-        mbar_wait(bar0 + BwdBars::q + 8 * (it % QS), (it / QS) & 1);
-        const uint32_t qa = sQ + (uint32_t)(it % QS) * F_QSTAGE + h_qoff;
+        const uint32_t qa = stage + h_qoff;
         s0_next = 0;
 #pragma unroll
         for (int c = 0; c < Q0 / 8; ++c) {
@@ -387,19 +450,25 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
           asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(((c & 1) ? xs1 : xs0) + OFF_H0T + (c >> 1) * A_BLK),
                        "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]));
         }
-        mbar_arrive(bar0 + BwdBars::qe + 8 * (it % QS));
         fence_async_smem();
-        mbar_arrive(bar0 + BwdBars::rdyA);
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(bar0 + BwdBars::qe + 8 * (it % QS));
+          mbar_arrive(bar0 + BwdBars::rdyA);
+        }
       };
 
       // ---- state of the current step ------------------------------------------------------------------------
-      int c_tile = steps[0].x, c_s = steps[0].y, c_r = 0, c_jet = 0;
+      int c_tile = 0, c_s = 0, c_r = 0;
+      float c_m = 0.f;                        // mask multiplier of the current step (0 for rows past the end)
       bool c_valid = false, c_first = true;   // c_first: first step of its tile inside this CTA's range
+      // DW2 builds two steps ahead: records of steps it+1 (p1_*) and it+2 (n_*)
+      int p1_tile = -1, p1_s = 0;
+      float p1_m = 0.f;
       auto enter_tile = [&]() {   // rows of the tile the current step belongs to; their dAgg
         const int r = c_tile * TILE + row;
         c_valid = r < BN;
         c_r = c_valid ? r : BN - 1;
-        c_jet = c_r / N;
         const float* dg = a.dagg + (size_t)c_r * N2 + q * 8;
 #pragma unroll
         for (int h = 0; h < 2; ++h)
@@ -413,11 +482,9 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
             dAggp[h * (QH / 2) + 4 * c + 3] = pack_bf16(v1.z, v1.w);
           }
       };
-      enter_tile();
       if (CH) {
 #pragma unroll
         for (int c = 0; c < Q0; ++c) dPacc[c] = 0.f;
-        write_onehot(c_tile);
       } else {
         if (q == 0) {
           st_ones_chunk(sH0 + swz_chunk(row, 96, A_BLK));
@@ -431,12 +498,21 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
           }
         }
       }
+      if (CH) {   // the first tile's constant-1 / one-hot columns must be in place before build_h0(0) releases M1(0)
+        mbar_wait(bar0 + BwdBars::q, 0);
+        int t0;
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(t0) : "r"(sQ + F_QHDR));
+        write_onehot(t0);
+      }
       build_h0(0);
+      c_tile = n_tile; c_s = n_s; c_m = n_m;
+      enter_tile();
       s0 = s0_next;
       k0w = k0w_next;
       if (!CH && nsteps > 1) {   // DW2: layer 1 runs one step ahead
         mbar_wait(bar0 + BwdBars::doneA, 0);
         build_h0(1);
+        p1_tile = n_tile; p1_s = n_s; p1_m = n_m;
       }
 
       int p_j0 = 0, p_nj = 0, p_s = 0;   // CHAIN: the step whose per-jet dQ sums sit in RB[0,96)
@@ -455,7 +531,7 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
 
       for (int it = 0; it < nsteps; ++it) {
         const uint32_t par = it & 1;
-        const float mfac = c_valid ? (a.mask ? __ldg(a.mask + (size_t)c_jet * N + c_s) : 1.f) : 0.f;
+        const float mfac = c_m;
         u4 kb{0, 0, 0, 0};
         if (DROP) kb = edge_drop_bits(drop.seed, (uint64_t)c_r * N + c_s, q, 1);
 
@@ -495,9 +571,7 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
           }
         };
         e1_round(std::integral_constant<int, 0>{});
-        e1_round(std::integral_constant<int, 1>{});
         if constexpr (CH) {
-          if (q == 0) tmem_st8(tl + C_RA + N1 / 2, 0x3F803F80u, 0u);   // bias K-step: columns 160,161 = 1.0
           tmem_st_wait();
           // dQ of the previous step must leave RB before M2 of this step overwrites it
           if (it >= 1) {
@@ -506,22 +580,31 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
             dq_readout();
             if (c_first) write_onehot(c_tile);   // first step of a new tile: the old one-hot columns are free now
           }
+          tc_fence_before();
+          warp_arrive(bar0 + BwdBars::rdyB);     // H1' columns [0,96) in place: M2's K steps 0..5 may start
+        }
+        e1_round(std::integral_constant<int, 1>{});
+        if constexpr (CH) {
+          if (q == 0) tmem_st8(tl + C_RA + N1 / 2, 0x3F803F80u, 0u);   // bias K-step: columns 160,161 = 1.0
+          tmem_st_wait();
+          tc_fence_before();
+          warp_arrive(bar0 + BwdBars::rdyB1);
         } else {
           fence_async_smem();
+          tc_fence_before();
+          warp_arrive(bar0 + BwdBars::rdyB);
         }
-        tc_fence_before();
-        mbar_arrive(bar0 + BwdBars::rdyB);
         MPG_TRW(it, 2);
 
         // ---- G2' = dAgg * m * keep2 * (1 + cg sgn D2) ----------------------------------------------------------------
         const uint32_t U_POS = bf16x2_dup(mfac), U_NEG = bf16x2_dup(mfac * a.alpha);
         if constexpr (CH) {
           uint2 sb{0, 0};
-          mbar_wait(bar0 + BwdBars::doneB, par);
-          MPG_TRW(it, 3);
-          tc_fence_after();
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
+            mbar_wait(bar0 + (h ? BwdBars::doneB1 : BwdBars::doneB), par);   // this N half of D2 is complete
+            if (h == 0) MPG_TRW(it, 3);
+            tc_fence_after();
             float v[QH];
             tmem_ld8x3(tl + C_RB + h * NH2, v);
             uint32_t sw = 0, gw[QH / 2];
@@ -547,11 +630,11 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
 #pragma unroll
             for (int c = 0; c < QH / 8; ++c)
               tmem_st4(tp + C_RB + h * (NH2 / 2) + 16 * c, gw[4 * c], gw[4 * c + 1], gw[4 * c + 2], gw[4 * c + 3]);
+            tmem_st_wait();
+            tc_fence_before();
+            warp_arrive(bar0 + (h ? BwdBars::rdyC1 : BwdBars::rdyC));   // this half of G2' feeds M3's K steps 6h..6h+5
           }
           t.sbits[(size_t)(g0 + it) * F_NEPI + threadIdx.x] = sb;
-          tmem_st_wait();
-          tc_fence_before();
-          mbar_arrive(bar0 + BwdBars::rdyC);
           MPG_TRW(it, 4);
         } else {
           const uint2 sb = t.sbits[(size_t)(g0 + it) * F_NEPI + threadIdx.x];
@@ -576,7 +659,7 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
                            "r"(g2w[h * 12 + 4 * c + 3]));
             }
           fence_async_smem();
-          mbar_arrive(bar0 + BwdBars::rdyC);
+          warp_arrive(bar0 + BwdBars::rdyC);
         }
 
         if constexpr (CH) {
@@ -619,7 +702,7 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
           tmem_st_wait();
           fence_async_smem();
           tc_fence_before();
-          mbar_arrive(bar0 + BwdBars::rdyD);
+          warp_arrive(bar0 + BwdBars::rdyD);
           MPG_TRW(it, 6);
 
           // ---- H0' of the next step under M4 (M5 has released the H0' tile and X) ---------------------------------------
@@ -658,7 +741,7 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
           }
           fence_async_smem();
           tc_fence_before();
-          mbar_arrive(bar0 + BwdBars::rdyE);
+          warp_arrive(bar0 + BwdBars::rdyE);
           MPG_TRW(it, 10);
           s0 = s0_next;
           k0w = k0w_next;
@@ -667,9 +750,10 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
           p_nj = min(c_tile * TILE + TILE - 1, BN - 1) / N - p_j0 + 1;
           p_s = c_s;
           {   // advance; flush dP when the next step belongs to another tile (or there is none)
-            const int2 nx = it + 1 < nsteps ? steps[it + 1] : make_int2(-1, 0);
+            const int2 nx = it + 1 < nsteps ? make_int2(n_tile, n_s) : make_int2(-1, 0);   // build_h0(it + 1) ran above
             c_first = nx.x != c_tile;
             c_s = nx.y;
+            c_m = n_m;
             if (c_first) {
               if (c_valid) {
                 float* dst = a.dP + (size_t)c_r * K0 + q * 8;
@@ -691,12 +775,13 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
             build_h0(it + 2);
           }
           if (it + 1 < nsteps) {
-            const int2 nx = steps[it + 1];
-            c_s = nx.y;
-            if (nx.x != c_tile) {
-              c_tile = nx.x;
+            c_s = p1_s;
+            c_m = p1_m;
+            if (p1_tile != c_tile) {
+              c_tile = p1_tile;
               enter_tile();
             }
+            p1_tile = n_tile; p1_s = n_s; p1_m = n_m;
           }
         }
       }

@@ -38,7 +38,9 @@ constexpr int F_REGS_EPI = 112, F_REGS_CTL = 32;   // setmaxnreg split of the 64
 constexpr int F_QS = 4;                      // Q ring stages
 constexpr int F_QJ = 10;                     // jets a 128-row tile can span (N >= 15)
 constexpr uint32_t F_QROW = K0 * 4;          // bytes of one Q row
-constexpr uint32_t F_QSTAGE = F_QJ * F_QROW;
+constexpr uint32_t F_QHDR = F_QJ * F_QROW;   // stage header: int tile, int sender, float mask[F_QJ] (written by the loader warp)
+constexpr uint32_t F_QSTAGE = F_QHDR + 64;
+constexpr int F_NEPIW = 16;                  // epilogue warps = arrivals per barrier phase
 constexpr uint32_t F_OFF_Q = OFF_H1;                       // 147456 (no H1 tile in shared memory)
 constexpr uint32_t F_OFF_BAR = F_OFF_Q + F_QS * F_QSTAGE;  // 211968
 constexpr uint32_t F_SMEM = F_OFF_BAR + 256 + 1024;
@@ -109,17 +111,17 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
 
   if (threadIdx.x == 0) {
     mbar_init(bar_w, 1);
-    mbar_init(bar_h0, F_NEPI);
+    mbar_init(bar_h0, F_NEPIW);
     mbar_init(bar_d1, 1);
     mbar_init(bar_d1 + 8, 1);
-    mbar_init(bar_h1, F_NEPI);
+    mbar_init(bar_h1, F_NEPIW);
     mbar_init(bar_d2lo, 1);
     mbar_init(bar_d2hi, 1);
-    mbar_init(bar_f2lo, F_NEPI);
-    mbar_init(bar_f2hi, F_NEPI);
+    mbar_init(bar_f2lo, F_NEPIW);
+    mbar_init(bar_f2hi, F_NEPIW);
     for (int i = 0; i < F_QS; ++i) {
       mbar_init(bar_q + 8 * i, 1);
-      mbar_init(bar_qe + 8 * i, F_NEPI);
+      mbar_init(bar_qe + 8 * i, F_NEPIW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -137,19 +139,29 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
       mbar_expect_tx_elect(bar_w, W1_BYTES + W2_BYTES);
       bulk_g2s_elect(sW1, t.w1img, W1_BYTES, bar_w);
       bulk_g2s_elect(sW2, t.w2img, W2_BYTES, bar_w);
+      int2 ts = steps[0];
       for (int it = 0; it < nsteps; ++it) {
+        const int2 ts_next = steps[it + 1 < nsteps ? it + 1 : it];   // in flight while this step's copies are issued
         // stage it % F_QS is free once every builder thread has read the rows of step it - F_QS
         if (it >= F_QS) mbar_wait(bar_qe + 8 * (it & (F_QS - 1)), (it / F_QS - 1) & 1);
-        const int2 ts = steps[it];
         const int q_tile = ts.x, q_s = ts.y;
         const int j0 = (q_tile * TILE) / N;
         const int rl = min(q_tile * TILE + TILE - 1, BN - 1);
         const int nj = rl / N - j0 + 1;
         const uint32_t bar = bar_q + 8 * (it & (F_QS - 1));
         const uint32_t dst = sQ + (uint32_t)(it & (F_QS - 1)) * F_QSTAGE;
+        // header: the step and the sender's mask in each jet of the tile, so that no epilogue thread touches global
+        // memory per step (the loader runs F_QS steps ahead: its own loads are off everybody's critical path)
+        if (lane < nj) {
+          const float mv = a.mask ? __ldg(a.mask + (size_t)(j0 + lane) * N + q_s) : 1.f;
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst + F_QHDR + 8 + 4 * (uint32_t)lane), "f"(mv) : "memory");
+        }
+        if (lane == 0) asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(dst + F_QHDR), "r"(q_tile), "r"(q_s) : "memory");
+        __syncwarp();
         mbar_expect_tx_elect(bar, (uint32_t)nj * F_QROW);
         for (int j = 0; j < nj; ++j)
           bulk_g2s_elect(dst + (uint32_t)j * F_QROW, a.Q + ((size_t)(j0 + j) * N + q_s) * K0, F_QROW, bar);
+        ts = ts_next;
       }
     } else if (warp == 16 && nsteps > 0) {
       // =============================== MMA issuer ================================================
@@ -265,16 +277,26 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
 
     // ---- state of the H0' builder (step it+2) -----------------------------------------------------
     int h_loaded = -1, h_r = 0;
-    uint32_t h_qoff = 0;
+    uint32_t h_qoff = 0, h_moff = 0;
+    bool h_valid = false;
+    // step records (tile, sender, this row's mask multiplier) of the steps whose H0' has been built: step it+2 is
+    // built during iteration it, so three are live
+    int s_tile[3] = {0, 0, 0}, s_snd[3] = {0, 0, 0}, s_row[3] = {0, 0, 0};
+    float s_m[3] = {0.f, 0.f, 0.f};
     auto build_h0 = [&](int it) {
-      const int2 hts = steps[it];
-      const int h_tile = hts.x, h_s = hts.y;
+      mbar_wait(bar_q + 8 * (it & (F_QS - 1)), (it / F_QS) & 1);
+      const uint32_t stage = sQ + (uint32_t)(it & (F_QS - 1)) * F_QSTAGE;
+      int h_tile, h_s;
+      asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(h_tile), "=r"(h_s) : "r"(stage + F_QHDR));
       if (h_tile != h_loaded) {
         h_loaded = h_tile;
         const int r = h_tile * TILE + row;
         const int rc = r < BN ? r : BN - 1;
         h_r = rc;
-        h_qoff = (uint32_t)(rc / N - (h_tile * TILE) / N) * F_QROW + (uint32_t)q * 32u;
+        h_valid = r < BN;
+        const uint32_t jl = (uint32_t)(rc / N - (h_tile * TILE) / N);
+        h_moff = F_QHDR + 8 + 4 * jl;
+        h_qoff = jl * F_QROW + (uint32_t)q * 32u;
         const float* p = a.P + (size_t)rc * K0 + q * 8;
 #pragma unroll
         for (int c = 0; c < Q0 / 8; ++c) {
@@ -284,10 +306,14 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
           Preg[8 * c + 4] = v1.x; Preg[8 * c + 5] = v1.y; Preg[8 * c + 6] = v1.z; Preg[8 * c + 7] = v1.w;
         }
       }
+      {
+        float mv;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(mv) : "r"(stage + h_moff));
+        s_tile[2] = h_tile; s_snd[2] = h_s; s_row[2] = h_r; s_m[2] = h_valid ? mv : 0.f;
+      }
       uint32_t kw = 0;
       if (DROP) kw = edge_drop_bits(drop.seed, (uint64_t)h_r * N + h_s, q, 0).x;
-      mbar_wait(bar_q + 8 * (it & (F_QS - 1)), (it / F_QS) & 1);
-      const uint32_t qa = sQ + (uint32_t)(it & (F_QS - 1)) * F_QSTAGE + h_qoff;
+      const uint32_t qa = stage + h_qoff;
 #pragma unroll
       for (int c = 0; c < Q0 / 8; ++c) {
         float v[8];
@@ -305,25 +331,22 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
         asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(xs[c & 1] + OFF_H0 + (c >> 1) * A_BLK),
                      "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]));
       }
-      mbar_arrive(bar_qe + 8 * (it & (F_QS - 1)));   // Q rows consumed (generic-proxy reads are complete)
       fence_async_smem();
-      mbar_arrive(bar_h0);
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar_qe + 8 * (it & (F_QS - 1)));   // Q rows consumed (generic-proxy reads are complete)
+        mbar_arrive(bar_h0);
+      }
+    };
+    auto rotate = [&]() {   // records of steps it+1, it+2 become those of it, it+1
+#pragma unroll
+      for (int i = 0; i < 2; ++i) { s_tile[i] = s_tile[i + 1]; s_snd[i] = s_snd[i + 1]; s_row[i] = s_row[i + 1]; s_m[i] = s_m[i + 1]; }
     };
 
     // ---- tile state: `cur` = tile of step `it` (mask / dropout rows), `acc` = tile the accumulators belong to
-    int cur_tile = -1, cur_row = 0, cur_jet = 0;
-    bool cur_valid = false;
-    int acc_tile = steps[0].x, acc_row = 0;
+    int acc_tile = 0, acc_row = 0;
     bool acc_valid = false;
     float e_m = 0.f;      // mask multiplier of the step whose E2 is pending
-    auto enter_cur = [&](int tile) {
-      cur_tile = tile;
-      const int r = tile * TILE + row;
-      cur_valid = r < BN;
-      cur_row = cur_valid ? r : BN - 1;
-      cur_jet = cur_row / N;
-    };
-    auto mask_of = [&](int s) { return cur_valid ? (a.mask ? __ldg(a.mask + (size_t)cur_jet * N + s) : 1.f) : 0.f; };
     const float fl_scale = a.out_scale * (DROP ? 2.f : 1.f) * 0.5f * (1.f + a.alpha);
     auto flush = [&]() {
       if (acc_valid) {
@@ -354,23 +377,23 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
     };
     uint32_t kz = 0, kwd = 0;   // layer-2 keep words of the step whose E1 ran last (consumed one iteration later)
 
-    enter_cur(acc_tile);
-    acc_row = cur_row;
-    acc_valid = cur_valid;
     MPG_TP(2);
     build_h0(0);
+    rotate();
+    rotate();              // record of step 0 -> slot 0
+    acc_tile = s_tile[0];
+    acc_row = s_row[0];
+    acc_valid = acc_tile * TILE + row < BN;
     MPG_TP(3);
     if (nsteps > 1) {
       mbar_wait(bar_d1, 0);   // M1(0) done: the H0' tile may be overwritten
       build_h0(1);
+      s_tile[1] = s_tile[2]; s_snd[1] = s_snd[2]; s_row[1] = s_row[2]; s_m[1] = s_m[2];
     }
 
-    float m_cur = 0.f;   // mask multiplier of step `it`
-
     for (int it = 0; it < nsteps; ++it) {
-      const int2 ts = steps[it];
-      if (ts.x != cur_tile) enter_cur(ts.x);
-      m_cur = mask_of(ts.y);
+      const int cur_tile = s_tile[0], cur_s = s_snd[0], cur_row = s_row[0];
+      const float m_cur = s_m[0];   // mask multiplier of step `it`
       // ---- E2lo(it-1) ----------------------------------------------------------------------------
       if (it >= 1) {
         mbar_wait(bar_d2lo, (it - 1) & 1);
@@ -378,13 +401,13 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
         tc_fence_after();
         e2_half(F_D2LO_COL, acc, kz);
         tc_fence_before();
-        mbar_arrive(bar_f2lo);
+        warp_arrive(bar_f2lo);
         MPG_TR(it, 1);
       }
       // ---- E1(it): D1 -> H1' ---------------------------------------------------------------------
       uint32_t kx = 0, ky = 0, kz_n = 0, kw_n = 0;
       if (DROP) {
-        const u4 b = edge_drop_bits(drop.seed, (uint64_t)cur_row * N + ts.y, q, 1);
+        const u4 b = edge_drop_bits(drop.seed, (uint64_t)cur_row * N + cur_s, q, 1);
         kx = b.x; ky = b.y; kz_n = b.z; kw_n = b.w;
       }
       mbar_wait(bar_d1 + 8 * (it & 1), (it >> 1) & 1);
@@ -410,7 +433,7 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
         tmem_st_wait();
       }
       tc_fence_before();
-      mbar_arrive(bar_h1);
+      warp_arrive(bar_h1);
       MPG_TR(it, 4);
       // ---- E2hi(it-1) ----------------------------------------------------------------------------
       if (it >= 1) {
@@ -419,13 +442,13 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
         tc_fence_after();
         e2_half(F_D2HI_COL, acc + QH, kwd);
         tc_fence_before();
-        mbar_arrive(bar_f2hi);
+        warp_arrive(bar_f2hi);
         MPG_TR(it, 5);
         if (cur_tile != acc_tile) {   // step it-1 was the last one of its tile
           flush();
           acc_tile = cur_tile;
           acc_row = cur_row;
-          acc_valid = cur_valid;
+          acc_valid = cur_tile * TILE + row < BN;
         }
       }
       e_m = m_cur;          // multiplier of step `it` (its E2 runs in the next iteration)
@@ -438,6 +461,7 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
         build_h0(it + 2);
         MPG_TR(it, 7);
       }
+      rotate();
     }
     MPG_TP(4);
     // ---- drain: E2 of the last step ------------------------------------------------------------------

@@ -67,8 +67,11 @@ def test_graph_replay_matches_eager_steps(golden, prec):
         torch.cuda.synchronize()
         res[mode] = (losses, tr.fpG.flat.clone(), tr.fpD.flat.clone(), tr.optD.square_avg.clone())
         tr.release()
+    # precision 1: an fp32 sum that differs in its last bit can round a bf16 operand the other way (0.4 % of that
+    # element), so the two modes drift apart by ~1e-4 over three steps at this learning rate; precision 0: 1e-4
+    ltol = 1e-4 if prec == 0 else 1e-3
     for (a, b), (c, d) in zip(res["eager"][0], res["graph"][0]):
-        assert abs(a - c) <= 1e-4 * max(1, abs(a)) and abs(b - d) <= 1e-4 * max(1, abs(b)), (res["eager"][0], res["graph"][0])
+        assert abs(a - c) <= ltol * max(1, abs(a)) and abs(b - d) <= ltol * max(1, abs(b)), (res["eager"][0], res["graph"][0])
     # Weights after K RMSprop steps.  An element's first update is lr * g / (sqrt(0.01 g^2) + eps) ~ 10 lr sign(g): it
     # depends on g only through its sign, so elements whose gradient is zero up to the order of the fp32 atomic sums
     # may step the other way; everything else must agree.  Stated in L2 over the whole flat buffer: the difference
@@ -80,7 +83,8 @@ def test_graph_replay_matches_eager_steps(golden, prec):
         assert moved > 1e-3, "the steps must change the weights"
         diff = float((res["eager"][i] - res["graph"][i]).norm())
         assert diff <= 0.05 * moved, (name, diff, moved)
-    assert rel_l2(res["graph"][3], res["eager"][3]) <= 1e-3, rel_l2(res["graph"][3], res["eager"][3])
+    # RMSprop's running mean of squared D gradients (measured 1.0e-3 at precision 1: the same bf16 re-rounding drift)
+    assert rel_l2(res["graph"][3], res["eager"][3]) <= (1e-3 if prec == 0 else 5e-3), rel_l2(res["graph"][3], res["eager"][3])
 
 
 def test_graph_replay_fresh_noise_and_dropout(golden):
