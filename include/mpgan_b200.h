@@ -124,7 +124,7 @@ int mpg_particle_order(const float* mask, int B, int N, int* pos, float* mask_so
 int mpg_permute_rows(const float* src, int lds, float* dst, int ldd, const int* pos, int B, int N, int F, int mode,
                      void* stream);
 /* pos[b] (int32) = index of jet b when the batch is ordered by descending key (key[b * ldk], e.g. the particle-count
- * label), ties in index order; B <= 8192.  Jets never interact, so the batch order is a layout choice too: with
+ * label), ties in index order.  Jets never interact, so the batch order is a layout choice too: with
  * mpg_permute_rows(B = 1, N = batch, F = row length) it puts jets with similar padding into the same tiles. */
 int mpg_batch_order(const float* key, int ldk, int B, int* pos, void* stream);
 /* mask[r] = x[r, ldx-1] + 0.5   (mpgan/model.py:881) */
@@ -170,6 +170,61 @@ int mpg_residual_dropout_fwd(const float* x, const float* r, float* out, size_t 
                              uint64_t seed, const uint64_t* seed_dev, uint32_t rng_stream, void* stream);
 int mpg_residual_dropout_bwd(const float* dout, float* dx, size_t rows, int cols, float p_drop, uint64_t seed,
                              const uint64_t* seed_dev, uint32_t rng_stream, void* stream);
+
+/* ---- k-nearest-neighbour message passing (mpgan/model.py:319-381, `fully_connected=False`) ----------------------
+ * mpg_knn_select: idx[b,i,m] (int32, [B,N,k]) = index inside jet b of the m-th nearest sender of receiver i, by the
+ * Euclidean distance over the first nd features to the sender scaled by (1 - 1e4) * mask + 1e4 (masked particles
+ * rank last, :336-340), 1e-12 added per component (:348); ascending, ties by index; self_loops = 0 skips the nearest
+ * entry (:354-363).  mpg_edge_nbr_fwd / _bwd: the fused edge network of mpg_edge_fwd / _bwd with receiver i
+ * aggregating over its k listed senders only (mask = the listed sender's mask, mean = 1/k); ef_mode 1 feeds the
+ * distance (to the scaled sender when knn_scale != 0) as the pair feature.  fp32 SIMT kernels.  With nbr == NULL
+ * mpg_edge_nbr_bwd is the fully connected backward on the fp32 kernels; dmask (optional, [B*N], overwritten) receives
+ * the gradient w.r.t. the mask multiplier: dmask[b,j] = scale * sum_i <fe(x_i | x_j), dagg[b,i]>. */
+int mpg_knn_select(const float* x, int ldx, const float* mask, int B, int N, int nd, int k, int self_loops, int* idx,
+                   void* stream);
+int mpg_edge_nbr_fwd(const int* nbr, int K, int knn_scale, const float* x, int ldx, const float* mask, const float* w0,
+                     const float* b0, const float* w1, const float* b1, const float* w2, const float* b2, int B, int N,
+                     int F, int H0, int H1, int H2, int ef_mode, int nd, int mean, float alpha, float p_drop,
+                     uint64_t seed, const uint64_t* seed_dev, void* workspace, size_t workspace_bytes, float* agg,
+                     void* stream);
+int mpg_edge_nbr_bwd(const int* nbr, int K, int knn_scale, const float* x, int ldx, const float* mask, const float* w0,
+                     const float* b0, const float* w1, const float* b1, const float* w2, const float* b2, int B, int N,
+                     int F, int H0, int H1, int H2, int ef_mode, int nd, int mean, float alpha, float p_drop,
+                     uint64_t seed, const uint64_t* seed_dev, void* workspace, size_t workspace_bytes, const float* dagg,
+                     float* dx, int lddx, float* dmask, float* dw0, float* db0, float* dw1, float* db1, float* dw2,
+                     float* db2, void* stream);
+
+/* ---- second-order products of the fused edge op: double backward for WGAN-GP (train.py:286-324) -----------------
+ * fe is piecewise linear, so with u [B*N, F] the cotangent the double backward receives for mpg_edge_bwd's dx output,
+ * s = <u, dx> depends on (dagg, mask, weights) through the tangent t = J_fe u taken along the slopes / dropout masks
+ * of the primal pass:  tagg [B*N, H2] = ds/d(dagg) = scale * sum_j mask_j t_ij;  gmask [B*N] (optional) = ds/d(mask);
+ * dw0 [H0, 2F], dw1, dw2 += ds/dW (optional, all or none; the biases and x have no second-order term).  Pair
+ * features (ef_mode != 0) are not supported.  fp32 SIMT kernel. */
+size_t mpg_edge_bwd2_workspace_bytes(int B, int N, int F, int H0, int H1, int H2);
+int mpg_edge_bwd2(const float* x, int ldx, const float* u, int ldu, const float* mask, const float* w0, const float* b0,
+                  const float* w1, const float* b1, const float* w2, const float* b2, int B, int N, int F, int H0, int H1,
+                  int H2, int mean, float alpha, float p_drop, uint64_t seed, const uint64_t* seed_dev, void* workspace,
+                  size_t workspace_bytes, const float* dagg, float* tagg, float* gmask, float* dw0, float* dw1, float* dw2,
+                  void* stream);
+
+/* ---- mask-channel gradients (the discriminator's mask = x[..., -1] + 0.5 is differentiable, mpgan/model.py:881) --
+ * mpg_split_mask_bwd: dx [rows, ldx] = 0 except dx[r, ldx-1] = dmask[r];  mpg_pool_dmask: dmask[b,i] = scale *
+ * <h[b,i,:], dout[b,:]> (gradient of the masked sum pool w.r.t. the mask). */
+int mpg_split_mask_bwd(const float* dmask, float* dx, int ldx, size_t rows, void* stream);
+int mpg_pool_dmask(const float* h, const float* dout, float* dmask, int B, int N, int C, float scale, void* stream);
+
+/* ---- generation post-processing (gen.py:126-141): out[r, i] = ((jets[r, i] - shift[i]) / norm[i]) * maxv[i] for
+ * i < nfeat (shift / norm / maxv are HOST arrays; a NaN entry = gen.py's None: step skipped), rows whose mask channel
+ * jets[r, ldj-1] < 0.5 zeroed (use_mask), feature 2 clamped at 0.  `out` [rows, ldo] may be pinned host memory. */
+int mpg_gen_postprocess(const float* jets, int ldj, float* out, int ldo, size_t rows, int nfeat, const float* shift,
+                        const float* norm, const float* maxv, int use_mask, void* stream);
+
+/* ---- LayerNorm over the last dimension (gapt/model.py:116-118, 130-136: nn.LayerNorm(embed_dim), eps 1e-5) --------
+ * mean / rstd [rows] are saved for backward; dw / db (optional, both or none) are ACCUMULATED. */
+int mpg_layernorm_fwd(const float* x, const float* w, const float* b, float* y, float* mean, float* rstd, size_t rows,
+                      int C, float eps, void* stream);
+int mpg_layernorm_bwd(const float* dy, const float* x, const float* w, const float* mean, const float* rstd, float* dx,
+                      float* dw, float* db, size_t rows, int C, void* stream);
 
 #ifdef __cplusplus
 }

@@ -4,6 +4,7 @@
 
 #include "../../include/mpgan_b200.h"
 #include "edge.cuh"
+#include "extra.cuh"
 #include "fn_tc.cuh"
 #include "gapt.cuh"
 #include "gemm.cuh"
@@ -90,6 +91,15 @@ EdgeWs carve_edge_ws(void* base, int B, int N, int F, int H0, int H1, int H2) {
   w.total = off;
   return w;
 }
+
+// optional operands of the fp32 kernels: neighbour list (kNN) and the mask gradient
+struct EdgeExtra {
+  const int* nbr = nullptr;
+  int K = 0;
+  int knn_scale = 0;
+  float* dmask = nullptr;
+  bool any() const { return nbr != nullptr || dmask != nullptr; }
+};
 
 int edge_common(EdgeArgs& a, EdgeWs& w, const float* x, int ldx, const float* mask, const float* w0,
                 const float* b0, const float* w1, const float* b1, const float* w2, const float* b2, int B, int N,
@@ -310,23 +320,49 @@ size_t mpg_edge_fwd_workspace_bytes(int B, int N, int F, int H0, int H1, int H2)
   return carve_edge_ws(nullptr, B, N, F, H0, H1, H2).persist;
 }
 
-int mpg_edge_fwd(const float* x, int ldx, const float* mask, const float* w0, const float* b0, const float* w1,
-                 const float* b1, const float* w2, const float* b2, int B, int N, int F, int H0, int H1, int H2,
-                 int ef_mode, int nd, int mean, float alpha, float p_drop, uint64_t seed, const uint64_t* seed_dev,
-                 int precision, void* workspace, size_t workspace_bytes, float* agg, void* stream) {
+static int edge_fwd_impl(const EdgeExtra& ex, const float* x, int ldx, const float* mask, const float* w0,
+                         const float* b0, const float* w1, const float* b1, const float* w2, const float* b2, int B, int N,
+                         int F, int H0, int H1, int H2, int ef_mode, int nd, int mean, float alpha, float p_drop,
+                         uint64_t seed, const uint64_t* seed_dev, int precision, void* workspace, size_t workspace_bytes,
+                         float* agg, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   EdgeArgs a;
   EdgeWs w;
   bool use_tc = false;
   if (edge_common(a, w, x, ldx, mask, w0, b0, w1, b1, w2, b2, B, N, F, H0, H1, H2, ef_mode, nd, mean, alpha,
-                  p_drop, seed, seed_dev, precision, workspace, workspace_bytes, &use_tc, s, true))
+                  p_drop, seed, seed_dev, ex.nbr ? 0 : precision, workspace, workspace_bytes, &use_tc, s, true))
     return 1;
   a.agg = agg;
+  if (ex.nbr != nullptr) {
+    MPG_CHECK(ex.K > 0 && ex.K <= N, "edge_nbr: need 0 < K <= N (K = %d, N = %d)", ex.K, N);
+    a.nbr = ex.nbr; a.K = ex.K; a.knn_scale = ex.knn_scale;
+    if (mean) a.out_scale = 1.f / (float)ex.K;   // torch.mean over the num_knn axis (model.py:267)
+  }
   if (use_tc) return launch_edge_tc_fwd(a, w.tc, s);
   return launch_edge_generic(a, false, s);
 }
 
-static int edge_bwd_impl(const void* saved, size_t saved_bytes, const float* x, int ldx, const float* mask,
+int mpg_edge_fwd(const float* x, int ldx, const float* mask, const float* w0, const float* b0, const float* w1,
+                 const float* b1, const float* w2, const float* b2, int B, int N, int F, int H0, int H1, int H2,
+                 int ef_mode, int nd, int mean, float alpha, float p_drop, uint64_t seed, const uint64_t* seed_dev,
+                 int precision, void* workspace, size_t workspace_bytes, float* agg, void* stream) {
+  return edge_fwd_impl(EdgeExtra(), x, ldx, mask, w0, b0, w1, b1, w2, b2, B, N, F, H0, H1, H2, ef_mode, nd, mean, alpha,
+                       p_drop, seed, seed_dev, precision, workspace, workspace_bytes, agg, stream);
+}
+
+int mpg_edge_nbr_fwd(const int* nbr, int K, int knn_scale, const float* x, int ldx, const float* mask, const float* w0,
+                     const float* b0, const float* w1, const float* b1, const float* w2, const float* b2, int B, int N,
+                     int F, int H0, int H1, int H2, int ef_mode, int nd, int mean, float alpha, float p_drop,
+                     uint64_t seed, const uint64_t* seed_dev, void* workspace, size_t workspace_bytes, float* agg,
+                     void* stream) {
+  MPG_CHECK(nbr != nullptr, "edge_nbr_fwd: null neighbour list");
+  EdgeExtra ex;
+  ex.nbr = nbr; ex.K = K; ex.knn_scale = knn_scale;
+  return edge_fwd_impl(ex, x, ldx, mask, w0, b0, w1, b1, w2, b2, B, N, F, H0, H1, H2, ef_mode, nd, mean, alpha, p_drop,
+                       seed, seed_dev, 0, workspace, workspace_bytes, agg, stream);
+}
+
+static int edge_bwd_impl(const EdgeExtra& ex, const void* saved, size_t saved_bytes, const float* x, int ldx, const float* mask,
                          const float* w0, const float* b0, const float* w1, const float* b1, const float* w2,
                          const float* b2, int B, int N, int F, int H0, int H1, int H2, int ef_mode, int nd, int mean,
                          float alpha, float p_drop, uint64_t seed, const uint64_t* seed_dev, int precision,
@@ -337,9 +373,20 @@ static int edge_bwd_impl(const void* saved, size_t saved_bytes, const float* x, 
   EdgeWs w;
   bool use_tc = false;
   if (edge_common(a, w, x, ldx, mask, w0, b0, w1, b1, w2, b2, B, N, F, H0, H1, H2, ef_mode, nd, mean, alpha,
-                  p_drop, seed, seed_dev, precision, workspace, workspace_bytes, &use_tc, s, false, saved, saved_bytes))
+                  p_drop, seed, seed_dev, ex.any() ? 0 : precision, workspace, workspace_bytes, &use_tc, s, false, saved,
+                  saved_bytes))
     return 1;
   MPG_CHECK(dagg && dx, "edge_bwd: null gradient pointer");
+  if (ex.nbr != nullptr) {
+    MPG_CHECK(ex.K > 0 && ex.K <= N, "edge_nbr: need 0 < K <= N (K = %d, N = %d)", ex.K, N);
+    a.nbr = ex.nbr; a.K = ex.K; a.knn_scale = ex.knn_scale;
+    if (mean) a.out_scale = 1.f / (float)ex.K;
+  }
+  if (ex.dmask != nullptr) {
+    MPG_CHECK(mask != nullptr, "edge_bwd: a mask gradient needs a mask");
+    a.dmask = ex.dmask;
+    MPG_CUDA(cudaMemsetAsync(ex.dmask, 0, (size_t)B * N * sizeof(float), s));
+  }
   // all six weight-gradient pointers null = input gradient only (train_G back-propagates through a frozen D)
   const bool dx_only = !dw0 && !db0 && !dw1 && !db1 && !dw2 && !db2;
   MPG_CHECK(dx_only || (dw0 && db0 && dw1 && db1 && dw2 && db2), "edge_bwd: pass all six weight gradients or none");
@@ -404,9 +451,22 @@ int mpg_edge_bwd(const float* x, int ldx, const float* mask, const float* w0, co
                  int ef_mode, int nd, int mean, float alpha, float p_drop, uint64_t seed, const uint64_t* seed_dev,
                  int precision, void* workspace, size_t workspace_bytes, const float* dagg, float* dx, int lddx, float* dw0,
                  float* db0, float* dw1, float* db1, float* dw2, float* db2, void* stream) {
-  return edge_bwd_impl(nullptr, 0, x, ldx, mask, w0, b0, w1, b1, w2, b2, B, N, F, H0, H1, H2, ef_mode, nd, mean, alpha,
-                       p_drop, seed, seed_dev, precision, workspace, workspace_bytes, dagg, dx, lddx, dw0, db0, dw1, db1,
-                       dw2, db2, stream);
+  return edge_bwd_impl(EdgeExtra(), nullptr, 0, x, ldx, mask, w0, b0, w1, b1, w2, b2, B, N, F, H0, H1, H2, ef_mode, nd,
+                       mean, alpha, p_drop, seed, seed_dev, precision, workspace, workspace_bytes, dagg, dx, lddx, dw0, db0,
+                       dw1, db1, dw2, db2, stream);
+}
+
+int mpg_edge_nbr_bwd(const int* nbr, int K, int knn_scale, const float* x, int ldx, const float* mask, const float* w0,
+                     const float* b0, const float* w1, const float* b1, const float* w2, const float* b2, int B, int N,
+                     int F, int H0, int H1, int H2, int ef_mode, int nd, int mean, float alpha, float p_drop,
+                     uint64_t seed, const uint64_t* seed_dev, void* workspace, size_t workspace_bytes, const float* dagg,
+                     float* dx, int lddx, float* dmask, float* dw0, float* db0, float* dw1, float* db1, float* dw2,
+                     float* db2, void* stream) {
+  EdgeExtra ex;
+  ex.nbr = nbr; ex.K = K; ex.knn_scale = knn_scale; ex.dmask = dmask;
+  return edge_bwd_impl(ex, nullptr, 0, x, ldx, mask, w0, b0, w1, b1, w2, b2, B, N, F, H0, H1, H2, ef_mode, nd, mean, alpha,
+                       p_drop, seed, seed_dev, 0, workspace, workspace_bytes, dagg, dx, lddx, dw0, db0, dw1, db1, dw2, db2,
+                       stream);
 }
 
 int mpg_edge_bwd_saved(const void* fwd_workspace, size_t fwd_workspace_bytes, const float* x, int ldx,
@@ -416,7 +476,7 @@ int mpg_edge_bwd_saved(const void* fwd_workspace, size_t fwd_workspace_bytes, co
                        int precision, void* workspace, size_t workspace_bytes, const float* dagg, float* dx, int lddx,
                        float* dw0, float* db0, float* dw1, float* db1, float* dw2, float* db2, void* stream) {
   MPG_CHECK(fwd_workspace != nullptr, "edge_bwd_saved: null forward workspace");
-  return edge_bwd_impl(fwd_workspace, fwd_workspace_bytes, x, ldx, mask, w0, b0, w1, b1, w2, b2, B, N, F, H0, H1, H2,
+  return edge_bwd_impl(EdgeExtra(), fwd_workspace, fwd_workspace_bytes, x, ldx, mask, w0, b0, w1, b1, w2, b2, B, N, F, H0, H1, H2,
                        ef_mode, nd, mean, alpha, p_drop, seed, seed_dev, precision, workspace, workspace_bytes, dagg, dx,
                        lddx, dw0, db0, dw1, db1, dw2, db2, stream);
 }
@@ -500,6 +560,116 @@ int mpg_residual_dropout_bwd(const float* dout, float* dx, size_t rows, int cols
                              const uint64_t* seed_dev, uint32_t rng_stream, void* stream) {
   return launch_resdrop(dout, nullptr, dx, rows, cols, make_drop(p_drop, seed, seed_dev), rng_stream, true,
                         (cudaStream_t)stream);
+}
+
+// ---- second-order products of the fused edge op (double backward, WGAN-GP) ------------------------------------
+size_t mpg_edge_bwd2_workspace_bytes(int B, int N, int F, int H0, int H1, int H2) {
+  return carve_edge_ws(nullptr, B, N, F, H0, H1, H2).total + 2 * align_up((size_t)B * N * H0 * sizeof(float)) + align_up(H0 * sizeof(float));
+}
+
+int mpg_edge_bwd2(const float* x, int ldx, const float* u, int ldu, const float* mask, const float* w0, const float* b0,
+                  const float* w1, const float* b1, const float* w2, const float* b2, int B, int N, int F, int H0, int H1,
+                  int H2, int mean, float alpha, float p_drop, uint64_t seed, const uint64_t* seed_dev, void* workspace,
+                  size_t workspace_bytes, const float* dagg, float* tagg, float* gmask, float* dw0, float* dw1, float* dw2,
+                  void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  MPG_CHECK(workspace != nullptr && workspace_bytes >= mpg_edge_bwd2_workspace_bytes(B, N, F, H0, H1, H2),
+            "edge_bwd2 workspace too small");
+  MPG_CHECK(u && dagg && tagg, "edge_bwd2: null operand");
+  EdgeArgs a;
+  EdgeWs w;
+  bool use_tc = false;
+  // fp32 kernels: P/Q of the primal point, transposed weight copies
+  if (edge_common(a, w, x, ldx, mask, w0, b0, w1, b1, w2, b2, B, N, F, H0, H1, H2, 0, 0, mean, alpha, p_drop, seed,
+                  seed_dev, 0, workspace, workspace_bytes, &use_tc, s, false))
+    return 1;
+  const size_t BN = (size_t)B * N;
+  char* extra = reinterpret_cast<char*>(workspace) + w.total;
+  float* Pt = reinterpret_cast<float*>(extra);
+  float* Qt = reinterpret_cast<float*>(extra + align_up(BN * H0 * sizeof(float)));
+  float* zero_b = reinterpret_cast<float*>(extra + 2 * align_up(BN * H0 * sizeof(float)));
+  // the first layer applied to the direction u (no bias: a constant has no tangent)
+  MPG_CUDA(cudaMemsetAsync(zero_b, 0, H0 * sizeof(float), s));
+  if (pq_supported(F, H0)) {
+    if (launch_pq_fwd(u, ldu, w0, a.ldwef, zero_b, Pt, Qt, (int)BN, F, H0, s)) return 1;
+  } else {
+    GemmEpi e;
+    if (launch_gemm(true, true, true, u, ldu, w0, a.ldwef, Pt, H0, (int)BN, H0, F, e, 1, s)) return 1;
+    if (launch_gemm(true, true, true, u, ldu, w0 + F, a.ldwef, Qt, H0, (int)BN, H0, F, e, 1, s)) return 1;
+  }
+  a.dagg = dagg;
+  a.Pt = Pt; a.Qt = Qt; a.tagg = tagg; a.gmask = gmask;
+  // weight-gradient sinks when the caller wants only tagg / gmask
+  float* sink = w.wg_scratch;
+  float* sdw0 = sink; sink += (size_t)H0 * a.ldwef;
+  float* sdb0 = sink; sink += H0;
+  float* sdw1 = sink; sink += (size_t)H1 * H0 + H1;
+  float* sdw2 = sink;
+  a.dW1 = dw1 ? dw1 : sdw1;
+  a.dW2 = dw2 ? dw2 : sdw2;
+  a.db1 = nullptr; a.db2 = nullptr;   // biases have no second-order term
+  a.dP = w.dP; a.dQ = w.dQ;
+  MPG_CUDA(cudaMemsetAsync(w.dQ, 0, BN * H0 * sizeof(float), s));
+  if (gmask != nullptr) MPG_CUDA(cudaMemsetAsync(gmask, 0, BN * sizeof(float), s));
+  if (launch_edge_generic_tangent(a, s)) return 1;
+  // dW0(2nd) = [dP^T u | dQ^T u] with the first-order dP / dQ; the dx and db0 the node-level kernel also produces go
+  // to scratch
+  if (dw0 != nullptr) {
+    if (pq_supported(F, H0)) {
+      if (launch_pq_bwd(w.dP, w.dQ, u, ldu, w0, a.ldwef, w.dxef, F, dw0, sdb0, (int)BN, F, H0, s)) return 1;
+    } else {
+      int split = cdiv((long long)BN, 256);
+      if (split > 64) split = 64;
+      GemmEpi acc;
+      acc.accumulate = 1;
+      if (launch_gemm(false, false, true, w.dP, H0, u, ldu, dw0, a.ldwef, H0, F, (int)BN, acc, split, s)) return 1;
+      if (launch_gemm(false, false, true, w.dQ, H0, u, ldu, dw0 + F, a.ldwef, H0, F, (int)BN, acc, split, s)) return 1;
+    }
+  }
+  (void)sdw0;
+  return 0;
+}
+
+int mpg_knn_select(const float* x, int ldx, const float* mask, int B, int N, int nd, int k, int self_loops, int* idx,
+                   void* stream) {
+  MPG_CHECK(N > 0 && N <= 1024 && nd > 0, "knn_select: need 0 < N <= 1024 and nd > 0");
+  const int skip = self_loops ? 0 : 1;
+  MPG_CHECK(k > 0 && k + skip <= N, "knn_select: k + skipped self loop must not exceed N (k = %d, N = %d)", k, N);
+  return launch_knn_select(x, ldx, mask, B, N, nd, k, skip, idx, (cudaStream_t)stream);
+}
+
+int mpg_gen_postprocess(const float* jets, int ldj, float* out, int ldo, size_t rows, int nfeat, const float* shift,
+                        const float* norm, const float* maxv, int use_mask, void* stream) {
+  MPG_CHECK(nfeat > 0 && nfeat <= 8 && nfeat < ldj + (use_mask ? 0 : 1) && nfeat <= ldo, "gen_postprocess: bad feature count");
+  PostCfg c;
+  memset(&c, 0, sizeof(c));
+  c.nfeat = nfeat;
+  for (int i = 0; i < nfeat; ++i) {   // host arrays; NaN = "None" in gen.py's lists (skip the step)
+    if (shift != nullptr && shift[i] == shift[i] && shift[i] != 0.f) { c.shift[i] = shift[i]; c.has_shift |= 1u << i; }
+    if (norm != nullptr && norm[i] == norm[i]) {
+      MPG_CHECK(maxv != nullptr, "gen_postprocess: norm without maxes");
+      c.norm[i] = norm[i]; c.maxv[i] = maxv[i]; c.has_norm |= 1u << i;
+    }
+  }
+  return launch_gen_postprocess(jets, ldj, out, ldo, rows, c, use_mask, (cudaStream_t)stream);
+}
+
+int mpg_split_mask_bwd(const float* dmask, float* dx, int ldx, size_t rows, void* stream) {
+  return launch_split_mask_bwd(dmask, dx, ldx, rows, (cudaStream_t)stream);
+}
+int mpg_pool_dmask(const float* h, const float* dout, float* dmask, int B, int N, int C, float scale, void* stream) {
+  return launch_pool_dmask(h, dout, dmask, B, N, C, scale, (cudaStream_t)stream);
+}
+int mpg_layernorm_fwd(const float* x, const float* w, const float* b, float* y, float* mean, float* rstd, size_t rows,
+                      int C, float eps, void* stream) {
+  MPG_CHECK(C > 0 && C <= 4096, "layernorm: C out of range");
+  return launch_layernorm_fwd(x, w, b, y, mean, rstd, rows, C, eps, (cudaStream_t)stream);
+}
+int mpg_layernorm_bwd(const float* dy, const float* x, const float* w, const float* mean, const float* rstd, float* dx,
+                      float* dw, float* db, size_t rows, int C, void* stream) {
+  MPG_CHECK(C > 0 && C <= 4096, "layernorm: C out of range");
+  MPG_CHECK((dw == nullptr) == (db == nullptr), "layernorm_bwd: pass both parameter gradients or none");
+  return launch_layernorm_bwd(dy, x, w, mean, rstd, dx, dw, db, rows, C, (cudaStream_t)stream);
 }
 
 }  // extern "C"

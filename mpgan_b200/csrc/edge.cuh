@@ -32,10 +32,25 @@ struct EdgeArgs {
   float *dP, *dQ;        // [B*N, H0]; dQ must be zeroed by the caller
   float* dWef;           // &dW0[0][2F], row stride ldwef (accumulated)
   float* dx_ef;          // [B*N, F] zeroed by the caller
+  // ---- generic (fp32 SIMT) kernel only --------------------------------------------------------------------------
+  // kNN message passing (mpgan/model.py:319-381): receiver i sends over its K listed neighbours instead of all N
+  // particles; the distance feature is taken to the sender scaled by (1 - 1e4) * mask + 1e4 (:336-340)
+  const int* nbr;        // [B*N, K] sender indices inside the jet, or null (fully connected)
+  int K;                 // senders per receiver (N when nbr is null)
+  int knn_scale;         // scale masked senders in the distance feature (kNN with a mask)
+  float* dmask;          // optional [B*N]: d/d(mask), accumulated with atomics (zeroed by the caller)
+  // second-order ("tangent") mode of the backward kernel, see mpg_edge_bwd2: Pt/Qt = first layer applied to the
+  // direction u (no bias); tagg [B*N, H2] and gmask [B*N] (zeroed by the caller) are outputs; dW1/dW2 receive the
+  // second-order weight gradients, dP/dQ the ordinary first-order ones
+  const float* Pt;
+  const float* Qt;
+  float* tagg;
+  float* gmask;
 };
 
-size_t edge_generic_smem(const EdgeArgs& a, bool bwd);
+size_t edge_generic_smem(const EdgeArgs& a, bool bwd, bool tangent = false);
 int launch_edge_generic(const EdgeArgs& a, bool bwd, cudaStream_t stream);
+int launch_edge_generic_tangent(const EdgeArgs& a, cudaStream_t stream);
 int launch_transpose(const float* in, int rows, int cols, float* out, cudaStream_t stream);
 
 // node-level ends of the factorised first layer (edge_node.cu)

@@ -6,6 +6,15 @@
 // path (fp32 accumulate, fp32 operands) and the fallback for non-default architectures; the
 // tcgen05 kernel in edge_tc.cu covers the default 96/160/192 edge network.
 //
+// The senders of a receiver are either all N particles of its jet (fully connected) or the K listed neighbours
+// (kNN message passing, mpgan/model.py:319-381): `nbr` carries the list, everything else is unchanged.
+//
+// The backward kernel has a second-order ("tangent") mode for double backward (WGAN-GP, train.py:286-324): fe is
+// piecewise linear (leaky-relu + dropout), so the derivative of <u, dx> -- u the cotangent of the first backward's
+// dx output -- w.r.t. dagg / mask / weights is a forward pass of the tangent t = J u through the SAME slopes the
+// primal pass took, combined with the ordinary backward signals g: dW_l(2nd) = g_l (x) t_{l-1}, d/d(dagg) = sum_j
+// mask_j t_2, d/d(mask_j) = sum_i <t_2, dagg_i>.
+//
 // Reference semantics: mpgan/model.py:256-267 (fe, mask on the sender axis, sum/mean over senders),
 // :284-317 (pair features), LinearNet :77-83 (Linear -> leaky_relu -> Dropout).
 #include "edge.cuh"
@@ -51,19 +60,37 @@ __device__ __forceinline__ bool edge_keep(const EdgeArgs& a, uint32_t layer, uin
 }
 
 struct ChunkCtx {
-  int b, i, j0, nvalid;   // senders j0 .. j0+nvalid-1
-  uint64_t pair0;         // (b*N + i)*N
+  int b, i, j0, nvalid;   // senders j0 .. j0+nvalid-1 of the receiver's sender list
+  uint64_t pair0;         // (b*N + i) * K
+  const int* sj;          // shared memory: particle index (inside the jet) of each sender of the chunk
 };
+
+// particle index of the chunk's senders: the list entry (kNN) or the position itself (fully connected)
+__device__ __forceinline__ void load_senders(const EdgeArgs& a, const ChunkCtx& c, int* sj) {
+  for (int r = threadIdx.x; r < R; r += NTHR) {
+    int j = c.j0 + min(r, c.nvalid - 1);
+    if (a.nbr != nullptr) j = a.nbr[((size_t)c.b * a.N + c.i) * a.K + j];
+    sj[r] = j;
+  }
+}
+
+// multiplier of a masked sender's coordinates in the kNN distance feature (model.py:336-340)
+__device__ __forceinline__ float knn_sender_scale(const EdgeArgs& a, const ChunkCtx& c, int j) {
+  if (!a.knn_scale || a.mask == nullptr) return 1.f;
+  return fmaf(1.f - 1e4f, a.mask[(size_t)c.b * a.N + j], 1e4f);
+}
 
 // pair features for the chunk: efs[e*RS + r]
 __device__ __forceinline__ void build_ef(const EdgeArgs& a, const ChunkCtx& c, float* efs, float* diffs) {
   if (a.n_ef == 0) return;
   for (int r = threadIdx.x; r < R; r += NTHR) {
     float d2 = 0.f;
+    const int j = c.sj[r];
+    const float sc = knn_sender_scale(a, c, j);
     const float* xi = a.x + ((size_t)c.b * a.N + c.i) * a.ldx;
-    const float* xj = a.x + ((size_t)c.b * a.N + min(c.j0 + r, a.N - 1)) * a.ldx;
+    const float* xj = a.x + ((size_t)c.b * a.N + j) * a.ldx;
     for (int e = 0; e < a.nd; ++e) {
-      const float d = xj[e] - xi[e];
+      const float d = sc * xj[e] - xi[e];
       diffs[e * RS + r] = d;
       const float de = d + 1e-12f;           // eps per component before the norm (model.py:304)
       d2 += de * de;
@@ -82,7 +109,7 @@ __device__ __forceinline__ void build_h0(const EdgeArgs& a, const ChunkCtx& c, c
     const int r = idx % R, k = idx / R;
     float v = 0.f;
     if (r < c.nvalid) {
-      v = Pi[k] + a.Q[((size_t)c.b * a.N + c.j0 + r) * a.H0 + k];
+      v = Pi[k] + a.Q[((size_t)c.b * a.N + c.sj[r]) * a.H0 + k];
       for (int e = 0; e < a.n_ef; ++e) v = fmaf(efs[e * RS + r], a.Wef[(size_t)k * a.ldwef + e], v);
       v = lrelu(v, a.alpha);
       if (a.drop.p > 0.f) v = edge_keep(a, 0, c.pair0 + c.j0 + r, k) ? v * a.drop.scale : 0.f;
@@ -113,8 +140,10 @@ __device__ __forceinline__ void layer_fwd(const EdgeArgs& a, const ChunkCtx& c, 
   }
 }
 
-__device__ __forceinline__ void chunk_forward(const EdgeArgs& a, const ChunkCtx& c, float* efs, float* diffs,
+__device__ __forceinline__ void chunk_forward(const EdgeArgs& a, const ChunkCtx& c, int* sj, float* efs, float* diffs,
                                               float* H0s, float* H1s, float* H2s) {
+  load_senders(a, c, sj);
+  __syncthreads();
   build_ef(a, c, efs, diffs);
   __syncthreads();
   build_h0(a, c, efs, H0s);
@@ -131,7 +160,7 @@ __device__ __forceinline__ void chunk_forward(const EdgeArgs& a, const ChunkCtx&
 
 __device__ __forceinline__ float sender_mask(const EdgeArgs& a, const ChunkCtx& c, int r) {
   if (r >= c.nvalid) return 0.f;
-  return a.mask ? a.mask[(size_t)c.b * a.N + c.j0 + r] : 1.f;
+  return a.mask ? a.mask[(size_t)c.b * a.N + c.sj[r]] : 1.f;
 }
 
 __global__ void __launch_bounds__(NTHR) edge_fwd_generic(EdgeArgs a) {
@@ -143,14 +172,16 @@ __global__ void __launch_bounds__(NTHR) edge_fwd_generic(EdgeArgs a) {
   float* efs = H2s + a.H2 * RS;
   float* diffs = efs + (a.n_ef + 1) * RS;
   float* aggs = diffs + (a.nd + 1) * RS;
+  int* sj = reinterpret_cast<int*>(aggs + a.H2);
   const int bi = blockIdx.x;
   ChunkCtx c;
   c.b = bi / a.N; c.i = bi % a.N;
-  c.pair0 = (uint64_t)bi * a.N;
+  c.pair0 = (uint64_t)bi * a.K;
+  c.sj = sj;
   for (int k = threadIdx.x; k < a.H2; k += NTHR) aggs[k] = 0.f;
-  for (c.j0 = 0; c.j0 < a.N; c.j0 += R) {
-    c.nvalid = min(R, a.N - c.j0);
-    chunk_forward(a, c, efs, diffs, H0s, H1s, H2s);
+  for (c.j0 = 0; c.j0 < a.K; c.j0 += R) {
+    c.nvalid = min(R, a.K - c.j0);
+    chunk_forward(a, c, sj, efs, diffs, H0s, H1s, H2s);
     for (int k = threadIdx.x; k < a.H2; k += NTHR) {
       float s = 0.f;
       for (int r = 0; r < c.nvalid; ++r) s = fmaf(H2s[k * RS + r], sender_mask(a, c, r), s);
@@ -222,6 +253,28 @@ __device__ __forceinline__ void dgrad(const EdgeArgs& a, const ChunkCtx& c, cons
   }
 }
 
+// tangent of one layer: T_out[c][r] = (sum_k T_in[k][r] * Wt[k][c]) * act_grad(Y[c][r])  (no bias: it has no tangent)
+template <int U>
+__device__ __forceinline__ void layer_tan(const EdgeArgs& a, const ChunkCtx& c, const float* Tin, int K, const float* Wt,
+                                          int C, const float* Y, uint32_t stream, float* Tout) {
+  const int tr = threadIdx.x >> 6, tc = threadIdx.x & 63;
+  float acc[8][U];
+  tile_matmul<U>(acc, Tin, K, Wt, C, C, tr, tc);
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int col = tc + 64 * u;
+    if (col >= C) continue;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int row = tr * 8 + r;
+      float v = 0.f;
+      if (row < c.nvalid) v = acc[r][u] * act_grad(a, Y[col * RS + row], stream, c.pair0 + c.j0 + row, col);
+      Tout[col * RS + row] = v;
+    }
+  }
+}
+
+template <bool TAN>
 __global__ void __launch_bounds__(NTHR) edge_bwd_generic(EdgeArgs a) {
   resolve_seed(a.drop);
   extern __shared__ __align__(16) float sm[];
@@ -233,16 +286,65 @@ __global__ void __launch_bounds__(NTHR) edge_bwd_generic(EdgeArgs a) {
   float* efs = dH0s + a.H0 * RS;
   float* diffs = efs + (a.n_ef + 1) * RS;
   float* dPs = diffs + (a.nd + 1) * RS;   // [H0]
-  float* defs = dPs + a.H0;               // [(n_ef+1)][RS]
+  float* defs = dPs + ((a.H0 + 3) & ~3);  // [(n_ef+1)][RS]  (tiles stay 16-byte aligned for any layer width)
+  int* sj = reinterpret_cast<int*>(defs + (a.n_ef + 1) * RS);   // [R]
+  float* T0s = reinterpret_cast<float*>(sj + R);                // tangent mode only
+  float* T1s = T0s + (TAN ? a.H0 * RS : 0);
+  float* T2s = T1s + (TAN ? a.H1 * RS : 0);
+  float* taggs = T2s + (TAN ? a.H2 * RS : 0);                   // [H2]
   const int bi = blockIdx.x;
   ChunkCtx c;
   c.b = bi / a.N; c.i = bi % a.N;
-  c.pair0 = (uint64_t)bi * a.N;
+  c.pair0 = (uint64_t)bi * a.K;
+  c.sj = sj;
   for (int k = threadIdx.x; k < a.H0; k += NTHR) dPs[k] = 0.f;
+  if (TAN)
+    for (int k = threadIdx.x; k < a.H2; k += NTHR) taggs[k] = 0.f;
   const float* dAgg = a.dagg + (size_t)bi * a.H2;
-  for (c.j0 = 0; c.j0 < a.N; c.j0 += R) {
-    c.nvalid = min(R, a.N - c.j0);
-    chunk_forward(a, c, efs, diffs, H0s, H1s, H2s);
+  for (c.j0 = 0; c.j0 < a.K; c.j0 += R) {
+    c.nvalid = min(R, a.K - c.j0);
+    chunk_forward(a, c, sj, efs, diffs, H0s, H1s, H2s);
+    if (TAN) {
+      // tangent forward through the slopes of the primal pass
+      const float* Pti = a.Pt + ((size_t)c.b * a.N + c.i) * a.H0;
+      for (int idx = threadIdx.x; idx < a.H0 * R; idx += NTHR) {
+        const int r = idx % R, k = idx / R;
+        float v = 0.f;
+        if (r < c.nvalid)
+          v = (Pti[k] + a.Qt[((size_t)c.b * a.N + c.sj[r]) * a.H0 + k]) *
+              act_grad(a, H0s[k * RS + r], 0, c.pair0 + c.j0 + r, k);
+        T0s[k * RS + r] = v;
+      }
+      __syncthreads();
+      if (a.H1 <= 64) layer_tan<1>(a, c, T0s, a.H0, a.W1t, a.H1, H1s, 1, T1s);
+      else if (a.H1 <= 128) layer_tan<2>(a, c, T0s, a.H0, a.W1t, a.H1, H1s, 1, T1s);
+      else layer_tan<4>(a, c, T0s, a.H0, a.W1t, a.H1, H1s, 1, T1s);
+      __syncthreads();
+      if (a.H2 <= 64) layer_tan<1>(a, c, T1s, a.H1, a.W2t, a.H2, H2s, 2, T2s);
+      else if (a.H2 <= 128) layer_tan<2>(a, c, T1s, a.H1, a.W2t, a.H2, H2s, 2, T2s);
+      else layer_tan<4>(a, c, T1s, a.H1, a.W2t, a.H2, H2s, 2, T2s);
+      __syncthreads();
+      // d<u,dx>/d(dagg_i) = scale * sum_j mask_j t2_ij;  d<u,dx>/d(mask_j) += scale * <t2_ij, dagg_i>
+      for (int k = threadIdx.x; k < a.H2; k += NTHR) {
+        float s = 0.f;
+        for (int r = 0; r < c.nvalid; ++r) s = fmaf(T2s[k * RS + r], sender_mask(a, c, r), s);
+        taggs[k] += s;
+      }
+      if (a.gmask != nullptr && threadIdx.x < c.nvalid) {
+        const int r = threadIdx.x;
+        float s = 0.f;
+        for (int k = 0; k < a.H2; ++k) s = fmaf(T2s[k * RS + r], dAgg[k], s);
+        atomicAdd(a.gmask + (size_t)c.b * a.N + c.sj[r], s * a.out_scale);
+      }
+    }
+    // d agg / d mask_j = scale * <message_ij, dagg_i>  (only when the mask itself needs a gradient)
+    if (a.dmask != nullptr && threadIdx.x < c.nvalid) {
+      const int r = threadIdx.x;
+      float s = 0.f;
+      for (int k = 0; k < a.H2; ++k) s = fmaf(H2s[k * RS + r], dAgg[k], s);
+      atomicAdd(a.dmask + (size_t)c.b * a.N + c.sj[r], s * a.out_scale);
+    }
+    __syncthreads();
     // dH2 (pre-activation grads of layer 2), in place
     for (int idx = threadIdx.x; idx < a.H2 * R; idx += NTHR) {
       const int r = idx % R, k = idx / R;
@@ -253,22 +355,24 @@ __global__ void __launch_bounds__(NTHR) edge_bwd_generic(EdgeArgs a) {
       H2s[k * RS + r] = v;
     }
     __syncthreads();
-    wgrad(H2s, a.H2, H1s, a.H1, a.dW2, a.H1);
-    for (int k = threadIdx.x; k < a.H2; k += NTHR) {
-      float s = 0.f;
-      for (int r = 0; r < c.nvalid; ++r) s += H2s[k * RS + r];
-      if (s != 0.f) atomicAdd(a.db2 + k, s);
-    }
+    wgrad(H2s, a.H2, TAN ? T1s : H1s, a.H1, a.dW2, a.H1);
+    if (!TAN)
+      for (int k = threadIdx.x; k < a.H2; k += NTHR) {
+        float s = 0.f;
+        for (int r = 0; r < c.nvalid; ++r) s += H2s[k * RS + r];
+        if (s != 0.f) atomicAdd(a.db2 + k, s);
+      }
     if (a.H1 <= 64) dgrad<1>(a, c, H2s, a.H2, a.W2, a.H1, H1s, 1, dH1s);
     else if (a.H1 <= 128) dgrad<2>(a, c, H2s, a.H2, a.W2, a.H1, H1s, 1, dH1s);
     else dgrad<4>(a, c, H2s, a.H2, a.W2, a.H1, H1s, 1, dH1s);
     __syncthreads();
-    wgrad(dH1s, a.H1, H0s, a.H0, a.dW1, a.H0);
-    for (int k = threadIdx.x; k < a.H1; k += NTHR) {
-      float s = 0.f;
-      for (int r = 0; r < c.nvalid; ++r) s += dH1s[k * RS + r];
-      if (s != 0.f) atomicAdd(a.db1 + k, s);
-    }
+    wgrad(dH1s, a.H1, TAN ? T0s : H0s, a.H0, a.dW1, a.H0);
+    if (!TAN)
+      for (int k = threadIdx.x; k < a.H1; k += NTHR) {
+        float s = 0.f;
+        for (int r = 0; r < c.nvalid; ++r) s += dH1s[k * RS + r];
+        if (s != 0.f) atomicAdd(a.db1 + k, s);
+      }
     if (a.H0 <= 64) dgrad<1>(a, c, dH1s, a.H1, a.W1, a.H0, H0s, 0, dH0s);
     else if (a.H0 <= 128) dgrad<2>(a, c, dH1s, a.H1, a.W1, a.H0, H0s, 0, dH0s);
     else dgrad<4>(a, c, dH1s, a.H1, a.W1, a.H0, H0s, 0, dH0s);
@@ -283,10 +387,10 @@ __global__ void __launch_bounds__(NTHR) edge_bwd_generic(EdgeArgs a) {
       const int k = idx % a.H0, r = idx / a.H0;
       if (r < c.nvalid) {
         const float v = dH0s[k * RS + r];
-        if (v != 0.f) atomicAdd(a.dQ + ((size_t)c.b * a.N + c.j0 + r) * a.H0 + k, v);
+        if (v != 0.f) atomicAdd(a.dQ + ((size_t)c.b * a.N + c.sj[r]) * a.H0 + k, v);
       }
     }
-    if (a.n_ef > 0) {
+    if (!TAN && a.n_ef > 0) {
       // d ef_e(r) = sum_k dH0[k][r] * Wef[k][e];  dWef[k][e] += sum_r dH0[k][r] * ef_e(r)
       for (int idx = threadIdx.x; idx < a.n_ef * R; idx += NTHR) {
         const int r = idx % R, e = idx / R;
@@ -301,7 +405,7 @@ __global__ void __launch_bounds__(NTHR) edge_bwd_generic(EdgeArgs a) {
         if (s != 0.f) atomicAdd(a.dWef + (size_t)k * a.ldwef + e, s);
       }
       __syncthreads();
-      // chain to x through diffs / dist
+      // chain to x through diffs / dist (the sender side carries the kNN scale of a masked sender)
       for (int idx = threadIdx.x; idx < a.nd * R; idx += NTHR) {
         const int r = idx % R, e = idx / R;
         if (r >= c.nvalid) continue;
@@ -313,7 +417,8 @@ __global__ void __launch_bounds__(NTHR) edge_bwd_generic(EdgeArgs a) {
           gd += defs[col * RS + r] * (diffs[e * RS + r] + 1e-12f) / dist;
         }
         if (gd != 0.f) {
-          atomicAdd(a.dx_ef + ((size_t)c.b * a.N + c.j0 + r) * a.F + e, gd);
+          const int j = c.sj[r];
+          atomicAdd(a.dx_ef + ((size_t)c.b * a.N + j) * a.F + e, gd * knn_sender_scale(a, c, j));
           atomicAdd(a.dx_ef + ((size_t)c.b * a.N + c.i) * a.F + e, -gd);
         }
       }
@@ -321,6 +426,8 @@ __global__ void __launch_bounds__(NTHR) edge_bwd_generic(EdgeArgs a) {
     __syncthreads();
   }
   for (int k = threadIdx.x; k < a.H0; k += NTHR) a.dP[(size_t)bi * a.H0 + k] = dPs[k];
+  if (TAN)
+    for (int k = threadIdx.x; k < a.H2; k += NTHR) a.tagg[(size_t)bi * a.H2 + k] = taggs[k] * a.out_scale;
 }
 
 __global__ void transpose_kernel(const float* __restrict__ in, int rows, int cols, float* __restrict__ out) {
@@ -334,10 +441,11 @@ __global__ void transpose_kernel(const float* __restrict__ in, int rows, int col
 
 }  // namespace
 
-size_t edge_generic_smem(const EdgeArgs& a, bool bwd) {
-  size_t f = (size_t)(a.H0 + a.H1 + a.H2) * RS + (size_t)(a.n_ef + 1) * RS + (size_t)(a.nd + 1) * RS;
-  if (bwd) f += (size_t)(a.H1 + a.H0) * RS + a.H0 + (size_t)(a.n_ef + 1) * RS;
+size_t edge_generic_smem(const EdgeArgs& a, bool bwd, bool tangent) {
+  size_t f = (size_t)(a.H0 + a.H1 + a.H2) * RS + (size_t)(a.n_ef + 1) * RS + (size_t)(a.nd + 1) * RS + R;
+  if (bwd) f += (size_t)(a.H1 + a.H0) * RS + ((a.H0 + 3) & ~3) + (size_t)(a.n_ef + 1) * RS;
   else f += a.H2;
+  if (tangent) f += (size_t)(a.H0 + a.H1 + a.H2) * RS + a.H2;
   return f * sizeof(float);
 }
 
@@ -348,17 +456,34 @@ int launch_transpose(const float* in, int rows, int cols, float* out, cudaStream
   return 0;
 }
 
-int launch_edge_generic(const EdgeArgs& a, bool bwd, cudaStream_t stream) {
+int launch_edge_generic(const EdgeArgs& a0, bool bwd, cudaStream_t stream) {
+  EdgeArgs a = a0;
+  if (a.nbr == nullptr) a.K = a.N;
   MPG_CHECK(a.H0 <= 256 && a.H1 <= 256 && a.H2 <= 256, "edge layer widths must be <= 256");
+  MPG_CHECK(a.K > 0, "edge network: no senders");
   const size_t smem = edge_generic_smem(a, bwd);
   MPG_CHECK(smem <= 227 * 1024, "edge network too wide for shared memory (%zu B)", smem);
   if (bwd) {
-    MPG_CUDA(cudaFuncSetAttribute(edge_bwd_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    edge_bwd_generic<<<a.B * a.N, NTHR, smem, stream>>>(a);
+    MPG_CUDA(cudaFuncSetAttribute(edge_bwd_generic<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    edge_bwd_generic<false><<<a.B * a.N, NTHR, smem, stream>>>(a);
   } else {
     MPG_CUDA(cudaFuncSetAttribute(edge_fwd_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     edge_fwd_generic<<<a.B * a.N, NTHR, smem, stream>>>(a);
   }
+  MPG_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_edge_generic_tangent(const EdgeArgs& a0, cudaStream_t stream) {
+  EdgeArgs a = a0;
+  if (a.nbr == nullptr) a.K = a.N;
+  MPG_CHECK(a.H0 <= 256 && a.H1 <= 256 && a.H2 <= 256, "edge layer widths must be <= 256");
+  MPG_CHECK(a.n_ef == 0, "second-order edge products are implemented for networks without pair features (pos_diffs)");
+  MPG_CHECK(a.Pt && a.Qt && a.tagg, "edge tangent: null operand");
+  const size_t smem = edge_generic_smem(a, true, true);
+  MPG_CHECK(smem <= 227 * 1024, "edge network too wide for the second-order kernel's shared memory (%zu B)", smem);
+  MPG_CUDA(cudaFuncSetAttribute(edge_bwd_generic<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  edge_bwd_generic<true><<<a.B * a.N, NTHR, smem, stream>>>(a);
   MPG_LAUNCH_CHECK();
   return 0;
 }

@@ -95,20 +95,26 @@ __global__ void particle_order_kernel(const float* __restrict__ mask, int B, int
 }
 
 // ---- batch order: jets by descending particle-count key, stable (train.py has no counterpart: layout only) ----
-// pos[b] = #{b' : key[b'] > key[b]} + #{b' < b : key[b'] == key[b]}: one CTA, keys in shared memory (B <= 8192).
+// pos[b] = #{b' : key[b'] > key[b]} + #{b' < b : key[b'] == key[b]}: one thread per jet, the keys streamed through
+// shared memory in tiles of 2048 (any B; B = 256: one CTA, one tile).
 __global__ void batch_order_kernel(const float* __restrict__ key, int ldk, int B, int* __restrict__ pos) {
-  extern __shared__ float keys[];
-  for (int i = threadIdx.x; i < B; i += blockDim.x) keys[i] = key[(size_t)i * ldk];
-  __syncthreads();
-  for (int b = threadIdx.x; b < B; b += blockDim.x) {
-    const float k = keys[b];
-    int p = 0;
-    for (int j = 0; j < B; ++j) {
-      const float kj = keys[j];
-      p += (kj > k) || (kj == k && j < b);
-    }
-    pos[b] = p;
+  constexpr int TILE_K = 2048;
+  __shared__ float keys[TILE_K];
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const float k = b < B ? key[(size_t)b * ldk] : 0.f;
+  int p = 0;
+  for (int j0 = 0; j0 < B; j0 += TILE_K) {
+    const int nj = min(TILE_K, B - j0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nj; i += blockDim.x) keys[i] = key[(size_t)(j0 + i) * ldk];
+    __syncthreads();
+    if (b < B)
+      for (int j = 0; j < nj; ++j) {
+        const float kj = keys[j];
+        p += (kj > k) || (kj == k && j0 + j < b);
+      }
   }
+  if (b < B) pos[b] = p;
 }
 
 // scatter (mode 0): dst[b, pos[b,i], :] = src[b, i, :];  gather (mode 1): dst[b, i, :] = src[b, pos[b,i], :]
@@ -360,9 +366,8 @@ int launch_particle_order(const float* mask, int B, int N, int* pos, float* mask
 }
 int launch_batch_order(const float* key, int ldk, int B, int* pos, cudaStream_t s) {
   if (B <= 0) return 0;
-  MPG_CHECK(B <= 8192, "batch_order: at most 8192 jets per call (got %d)", B);
-  const int nt = B < 1024 ? ((B + 31) / 32) * 32 : 1024;
-  batch_order_kernel<<<1, nt, (size_t)B * sizeof(float), s>>>(key, ldk, B, pos);
+  const int nt = B < 256 ? ((B + 31) / 32) * 32 : 256;
+  batch_order_kernel<<<cdiv(B, nt), nt, 0, s>>>(key, ldk, B, pos);
   MPG_LAUNCH_CHECK();
   return 0;
 }

@@ -22,8 +22,6 @@ class MAB(nn.Module):
     def __init__(self, embed_dim: int, num_heads: int, ff_layers: list = [], layer_norm: bool = False,
                  dropout_p: float = 0.0, final_linear: bool = True, linear_args={}):
         super().__init__()
-        if layer_norm:
-            raise NotImplementedError("layer_norm=True is not supported by the fused GAPT path (reference default: off)")
         self.num_heads = num_heads
         self.embed_dim = embed_dim
         # parameter container only (in_proj_weight [3E,E], in_proj_bias, out_proj.{weight,bias});
@@ -32,6 +30,9 @@ class MAB(nn.Module):
         self.ff = LinearNet(ff_layers, input_size=embed_dim, output_size=embed_dim, final_linear=final_linear,
                             **linear_args)
         self.layer_norm = layer_norm
+        if layer_norm:   # reference :116-118 (same module / parameter names: norm1.weight, norm1.bias, ...)
+            self.norm1 = nn.LayerNorm(embed_dim)
+            self.norm2 = nn.LayerNorm(embed_dim)
         self.dropout_p = float(dropout_p)
         self.dropout = nn.Dropout(p=dropout_p)
 
@@ -51,6 +52,12 @@ class MAB(nn.Module):
         o = ops.attention(q, k, v, y_mask, self.num_heads)
         a = ops.linear(o, att.out_proj.weight, att.out_proj.bias, False, 0.0, 0.0)
         p = self.dropout_p if self.training else 0.0
+        if self.layer_norm:   # x + attn -> LayerNorm -> Dropout -> + ff -> LayerNorm -> Dropout (:129-137)
+            h = ops.layer_norm(ops.residual_dropout(x, a, 0.0), self.norm1.weight, self.norm1.bias, self.norm1.eps)
+            h = ops.residual_dropout(h, None, p, rng_stream=48) if p > 0 else h
+            f = self.ff(h)
+            o = ops.layer_norm(ops.residual_dropout(h, f, 0.0), self.norm2.weight, self.norm2.bias, self.norm2.eps)
+            return ops.residual_dropout(o, None, p, rng_stream=49) if p > 0 else o
         h = ops.residual_dropout(x, a, p, rng_stream=48)
         f = self.ff(h)
         return ops.residual_dropout(h, f, p, rng_stream=49)

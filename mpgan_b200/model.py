@@ -111,8 +111,6 @@ class MPLayer(nn.Module):
         **linear_args,
     ):
         super().__init__()
-        if not fully_connected:
-            raise NotImplementedError("kNN message passing (fully_connected=False) is outside the fused path")
         if int_diffs:
             raise NotImplementedError("int_diffs is not implemented in the reference either")
         if clabels or mask_fne_np:
@@ -157,10 +155,19 @@ class MPLayer(nn.Module):
             elif delta_coords:
                 self._ef_mode = 2
             cols = (self._nd if self._ef_mode & 2 else 0) + (self._ef_mode & 1)
-            if cols != num_ef:
+            if fully_connected and cols != num_ef:
                 raise ValueError(
                     f"pair-feature options give {cols} columns but the edge network expects {num_ef} "
                     "(the reference fails with a shape error for this combination)")
+        if not fully_connected:
+            # kNN (reference _getA_knn :319-381): neighbours by distance over all features unless pos_diffs without
+            # all_ef (then the coordinates); with pos_diffs the ONLY pair feature is that distance (:380-383)
+            ncoord = 3 if coords == "cartesian" else 2
+            self._nd = input_node_size if (all_ef or not pos_diffs) else ncoord
+            self._ef_mode = 1 if pos_diffs else 0
+            if pos_diffs and num_ef != 1:
+                raise ValueError("kNN message passing feeds one distance column; these pair-feature options make the "
+                                 f"edge network expect {num_ef} (the reference fails with a shape error)")
 
         fe_in_size = 2 * input_node_size + num_ef + clabels + mask_fne_np
         self.fe = LinearNet(self.fe_layers, input_size=fe_in_size, final_linear=False, **linear_args)
@@ -178,8 +185,14 @@ class MPLayer(nn.Module):
         w1, b1 = fe.layer_params(1)
         w2, b2 = fe.layer_params(2)
         p = fe.dropout_p if self.training else 0.0
-        agg = ops.edge_aggregate(x, mask if use_mask else None, w0, b0, w1, b1, w2, b2, ef_mode=self._ef_mode,
-                                 nd=self._nd, mean=not self.sum, alpha=fe.leaky_relu_alpha, p_drop=p)
+        if self.fully_connected:
+            agg = ops.edge_aggregate(x, mask if use_mask else None, w0, b0, w1, b1, w2, b2, ef_mode=self._ef_mode,
+                                     nd=self._nd, mean=not self.sum, alpha=fe.leaky_relu_alpha, p_drop=p)
+        else:
+            m = mask if use_mask else None
+            nbr = ops.knn_select(x, m, self.num_knn, self._nd, self.self_loops)
+            agg = ops.edge_aggregate_knn(x, m, nbr, w0, b0, w1, b1, w2, b2, ef_mode=self._ef_mode, nd=self._nd,
+                                         mean=not self.sum, alpha=fe.leaky_relu_alpha, p_drop=p)
         fn = self.fn
         pn = fn.dropout_p if self.training else 0.0
         if len(fn.net) == 3 and fn.final_linear and ops.node_net_supported(
@@ -254,7 +267,8 @@ class MPNet(nn.Module):
         x = self._pre_mp(x, labels)
         x, use_mask, mask, num_jet_particles = self._get_mask(x, labels, **self.mask_args)
         idx = None
-        if use_mask and self.sort_particles and x.shape[1] > 1:
+        if use_mask and self.sort_particles and x.shape[1] > 1 and not mask.requires_grad:
+            # (a mask that carries a gradient -- D differentiated w.r.t. its input's mask channel -- keeps its layout)
             # Real particles first inside every jet.  The layers are permutation-equivariant over particles
             # (fully connected, sum / mean aggregation), so this only changes the layout: a generated jet's real
             # particles are wherever its noise ranks put them, and a sender index that is padded in every jet of a
@@ -384,7 +398,7 @@ class MPDiscriminator(MPNet):
         if mask_fne_np:
             raise NotImplementedError("mask_fne_np is not supported")
         if use_mask or mask_fnd_np:
-            mask = ops.split_mask(x)          # x[:, :, -1:] + 0.5, a real-valued multiplier
+            mask = ops.split_mask(x)          # x[:, :, -1:] + 0.5, a real-valued multiplier (differentiable)
         if use_mask:
             x = x[:, :, :-1]                  # strided view: the kernels take a row stride, no copy
         return x, use_mask, mask, None

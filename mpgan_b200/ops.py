@@ -2,8 +2,14 @@
 
 Each op is a ``torch.autograd.Function`` whose forward/backward call straight into
 ``libmpgan_b200.so`` on the current CUDA stream.  PyTorch is used for device memory and autograd
-bookkeeping only.  Backward passes are ``once_differentiable``: double backward (WGAN-GP,
-``create_graph=True``) raises instead of silently producing wrong gradients.
+bookkeeping only.
+
+Double backward (``create_graph=True``: the WGAN-GP term, train.py:286-324) is supported for the ops a
+discriminator is made of -- ``linear``, ``edge_aggregate``, ``node_net``, ``split_mask``, ``masked_pool`` -- through
+second functions (``*BwdFn``) whose forward is the first-order backward and whose backward holds the second-order
+products (the networks are piecewise linear, so these are tangent passes along the slopes of the primal pass, see
+``mpg_edge_bwd2``).  Everything else is ``once_differentiable`` and raises under ``create_graph`` instead of silently
+producing wrong gradients.
 """
 from __future__ import annotations
 
@@ -62,6 +68,28 @@ class direct_grad:
         global _DIRECT_GRAD
         _DIRECT_GRAD = self.prev
         return False
+
+
+# Inside ``input_grad_only()`` the backward passes skip weight / bias gradients altogether (they return None for
+# them): ``torch.autograd.grad(D(x), x, create_graph=True)`` of the gradient penalty asks for dD/dx only, but
+# ``needs_input_grad`` is True for every parameter that requires grad.
+_INPUT_GRAD_ONLY = False
+
+
+class input_grad_only:
+    def __enter__(self):
+        global _INPUT_GRAD_ONLY
+        self.prev, _INPUT_GRAD_ONLY = _INPUT_GRAD_ONLY, True
+        return self
+
+    def __exit__(self, *exc):
+        global _INPUT_GRAD_ONLY
+        _INPUT_GRAD_ONLY = self.prev
+        return False
+
+
+def _want_wgrad(ctx, lo, hi):
+    return (not _INPUT_GRAD_ONLY) and any(ctx.needs_input_grad[lo:hi])
 
 
 def _grad_sink(p):
@@ -203,25 +231,91 @@ class LinearFn(torch.autograd.Function):
         return y
 
     @staticmethod
-    @once_differentiable
     def backward(ctx, dy):
         L = _lib.lib()
         x2, w, y = ctx.saved_tensors
         ldx, M, K, N, act, alpha, p, seed, rstream, prec, sptr = ctx.cfg
+        if torch.is_grad_enabled():   # create_graph: differentiable backward
+            wp, bp = ctx.params
+            need_w = _want_wgrad(ctx, 1, 3)
+            dx, dw, db = LinearBwdFn.apply(dy, y, x2, wp, ctx.cfg, ctx.needs_input_grad[0], need_w)
+            return (dx if ctx.needs_input_grad[0] else None, dw if need_w else None, db if need_w else None, None, None,
+                    None, None, None)
         dy = dy.contiguous()
         dz = torch.empty_like(dy) if (act or p > 0) else None
         dx = torch.empty(*x2.shape, device=dy.device, dtype=torch.float32) if ctx.needs_input_grad[0] else None
         wp, bp = ctx.params
-        dw_sink = _grad_sink(wp) if ctx.needs_input_grad[1] else None
-        db_sink = _grad_sink(bp) if ctx.needs_input_grad[2] else None
-        dw = dw_sink if dw_sink is not None else (torch.zeros_like(w) if ctx.needs_input_grad[1] else None)
+        need_w = ctx.needs_input_grad[1] and not _INPUT_GRAD_ONLY
+        need_b = ctx.needs_input_grad[2] and not _INPUT_GRAD_ONLY
+        dw_sink = _grad_sink(wp) if need_w else None
+        db_sink = _grad_sink(bp) if need_b else None
+        dw = dw_sink if dw_sink is not None else (torch.zeros_like(w) if need_w else None)
         db = db_sink if db_sink is not None else (
-            torch.zeros(N, device=dy.device, dtype=torch.float32) if ctx.needs_input_grad[2] else None)
+            torch.zeros(N, device=dy.device, dtype=torch.float32) if need_b else None)
         _lib.check(L.mpg_linear_bwd(_lib.ptr(dy), _lib.ptr(y), _lib.ptr(x2), ldx, _lib.ptr(w), _lib.ptr(dz),
                                     _lib.ptr(dx), K, 0, _lib.ptr(dw), _lib.ptr(db), M, K, N, act, alpha, p, seed,
                                     sptr, rstream, prec, _lib.stream()), "mpg_linear_bwd")
         return (dx, None if dw_sink is not None else dw, None if db_sink is not None else db, None, None, None, None,
                 None)
+
+
+class LinearBwdFn(torch.autograd.Function):
+    """First-order backward of ``LinearFn`` as a differentiable function of (dy, w): dz = dy * S with S = d(act,
+    dropout)/dz read off the layer output y (piecewise constant), dx = dz W, dw = dz^T x, db = colsum(dz).  Its
+    backward (the double backward) for the cotangent v of dx:  d<v,dx>/d(dy) = S * (v W^T),  d<v,dx>/dW = dz^T v;
+    x and y get none (piecewise linear).  Cotangents of dw / db are not supported (nothing on this path forms them)."""
+
+    @staticmethod
+    def forward(ctx, dy, y, x2, w, cfg, need_dx, need_w):
+        L = _lib.lib()
+        ldx, M, K, N, act, alpha, p, seed, rstream, prec, sptr = cfg
+        dy = dy.contiguous()
+        wc = w.contiguous()
+        dz = torch.empty_like(dy) if (act or p > 0) else None
+        dx = torch.empty(*x2.shape, device=dy.device, dtype=torch.float32) if need_dx else None
+        dw = torch.zeros_like(wc) if need_w else None
+        db = torch.zeros(N, device=dy.device, dtype=torch.float32) if need_w else None
+        _lib.check(L.mpg_linear_bwd(_lib.ptr(dy), _lib.ptr(y), _lib.ptr(x2), ldx, _lib.ptr(wc), _lib.ptr(dz),
+                                    _lib.ptr(dx), K, 0, _lib.ptr(dw), _lib.ptr(db), M, K, N, act, alpha, p, seed,
+                                    sptr, rstream, prec, _lib.stream()), "mpg_linear_bwd")
+        ctx.save_for_backward(dy, y, wc)
+        ctx.cfg = cfg
+        ctx.xshape = x2.shape
+        if dx is None:
+            dx = torch.zeros(0, device=dy.device)
+        if dw is None:
+            dw, db = torch.zeros(0, device=dy.device), torch.zeros(0, device=dy.device)
+        ctx.mark_non_differentiable(dw, db)
+        return dx, dw, db
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, v, v_w, v_b):
+        L = _lib.lib()
+        dy, y, w = ctx.saved_tensors
+        ldx, M, K, N, act, alpha, p, seed, rstream, prec, sptr = ctx.cfg
+        g_dy = g_w = None
+        if v is not None and v.numel():
+            v = v.contiguous().view(M, K)
+            if ctx.needs_input_grad[0]:
+                t = torch.empty(M, N, device=v.device, dtype=torch.float32)      # v W^T
+                _lib.check(L.mpg_linear_fwd(_lib.ptr(v), K, _lib.ptr(w), None, _lib.ptr(t), M, K, N, 0, 0.0, 0.0, 0, None,
+                                            0, prec, _lib.stream()), "mpg_linear_fwd")
+                if act or p > 0:                                                 # * S (dz-only call)
+                    g_dy = torch.empty_like(t)
+                    _lib.check(L.mpg_linear_bwd(_lib.ptr(t), _lib.ptr(y), None, 0, _lib.ptr(w), _lib.ptr(g_dy), None, K, 0,
+                                                None, None, M, K, N, act, alpha, p, seed, sptr, rstream, prec,
+                                                _lib.stream()), "mpg_linear_bwd")
+                else:
+                    g_dy = t
+                g_dy = g_dy.view(dy.shape)
+            if ctx.needs_input_grad[3]:
+                g_w = torch.zeros_like(w)                                        # dz^T v
+                dz = torch.empty(M, N, device=v.device, dtype=torch.float32) if (act or p > 0) else None
+                _lib.check(L.mpg_linear_bwd(_lib.ptr(dy), _lib.ptr(y), _lib.ptr(v), K, _lib.ptr(w), _lib.ptr(dz), None, K, 0,
+                                            _lib.ptr(g_w), None, M, K, N, act, alpha, p, seed, sptr, rstream, prec,
+                                            _lib.stream()), "mpg_linear_bwd")
+        return g_dy, None, None, g_w, None, None, None
 
 
 def linear(x, w, b, act: bool, alpha: float, p_drop: float, rng_stream: int = 16, seed=None):
@@ -256,28 +350,38 @@ class EdgeAggFn(torch.autograd.Function):
                                       H2, int(ef_mode), int(nd), int(mean), float(alpha), float(p_drop), seed,
                                       _seed_ptr(), _PRECISION, ws.data_ptr(), ws_bytes, _lib.ptr(agg),
                                       _lib.stream()), "mpg_edge_fwd")
-        ctx.save_for_backward(x3, m, *ws_)
+        # (x, mask themselves are saved too: the double backward returns gradients w.r.t. the ORIGINAL inputs)
+        ctx.save_for_backward(x3, m, *ws_, x, mask if mask is not None else x3.new_zeros(0))
         ctx.params = (w0, b0, w1, b1, w2, b2)
+        ctx.mask_shape = None if mask is None else tuple(mask.shape)
         ctx.fwd_ws = ws if _SAVE_EDGE_WS else None
         ctx.cfg = (ldx, B, N, F, H0, H1, H2, int(ef_mode), int(nd), int(mean), float(alpha), float(p_drop), seed,
                    _PRECISION, _seed_ptr())
         return agg
 
     @staticmethod
-    @once_differentiable
     def backward(ctx, dagg):
         L = _lib.lib()
-        x3, m, w0, b0, w1, b1, w2, b2 = ctx.saved_tensors
+        x3, m, w0, b0, w1, b1, w2, b2, x_in, mask_in = ctx.saved_tensors
         ldx, B, N, F, H0, H1, H2, ef_mode, nd, mean, alpha, p, seed, prec, sptr = ctx.cfg
+        need_mask = m is not None and ctx.needs_input_grad[1]
+        if torch.is_grad_enabled():   # create_graph: differentiable backward (second-order products in EdgeAggBwdFn)
+            need_w = _want_wgrad(ctx, 2, 8)
+            outs = EdgeAggBwdFn.apply(dagg, x_in, mask_in if m is not None else None, *ctx.params, ctx.cfg, need_mask,
+                                      need_w)
+            dx, dmask, grads = outs[0], outs[1], outs[2:]
+            return (dx, dmask.view(ctx.mask_shape) if need_mask else None, *(grads if need_w else [None] * 6), None, None,
+                    None, None, None)
         dagg = dagg.contiguous()
         ws_bytes = L.mpg_edge_workspace_bytes(B, N, F, H0, H1, H2)
         ws = torch.empty(ws_bytes, device=dagg.device, dtype=torch.uint8)
         dx = torch.empty(B, N, F, device=dagg.device, dtype=torch.float32)
-        sinks = [_grad_sink(p) for p in ctx.params] if all(ctx.needs_input_grad[2:8]) else [None] * 6
+        want_w = _want_wgrad(ctx, 2, 8)
+        sinks = [_grad_sink(p) for p in ctx.params] if (want_w and all(ctx.needs_input_grad[2:8])) else [None] * 6
         direct = all(g is not None for g in sinks)
         if direct:
             grads = sinks
-        elif any(ctx.needs_input_grad[2:8]):
+        elif want_w:
             # one zero-filled buffer, six views (one fill kernel instead of six)
             ws_ = (w0, b0, w1, b1, w2, b2)
             flat = torch.zeros(sum(t.numel() for t in ws_), device=dagg.device, dtype=torch.float32)
@@ -287,21 +391,122 @@ class EdgeAggFn(torch.autograd.Function):
                 off += t.numel()
         else:   # frozen weights (train_G back-propagating through D): input gradient only
             grads = [None] * 6
-        frac = edge_active_fraction(m, B, N) if _profile is not None else 1.0
-        with _Timed("edge_bwd", 2.0 * edge_flops(B, N, F, H0, H1, H2),
-                    [(2, "edge_tc_bwd_chain_kernel", 2 * _pair_flops(B, N, H0, H1) + _pair_flops(B, N, H1, H2)),
-                     (3, "edge_tc_bwd_dw2_kernel", _pair_flops(B, N, H1, H2))], frac):
-            args = (_lib.ptr(x3), ldx, _lib.ptr(m), *[_lib.ptr(t) for t in (w0, b0, w1, b1, w2, b2)], B, N, F, H0, H1,
-                    H2, ef_mode, nd, mean, alpha, p, seed, sptr, prec, ws.data_ptr(), ws_bytes, _lib.ptr(dagg),
-                    _lib.ptr(dx), F, *[_lib.ptr(g) for g in grads], _lib.stream())
-            fws = ctx.fwd_ws
-            if fws is not None:   # P/Q, weight images and work list as the forward left them
-                _lib.check(L.mpg_edge_bwd_saved(fws.data_ptr(), fws.numel(), *args), "mpg_edge_bwd_saved")
-            else:
-                _lib.check(L.mpg_edge_bwd(*args), "mpg_edge_bwd")
+        dmask = None
+        if need_mask:
+            # the mask multiplier itself needs a gradient (D differentiated w.r.t. its input's mask channel): the fp32
+            # kernels compute it next to dx
+            dmask = torch.empty(B, N, device=dagg.device, dtype=torch.float32)
+            _lib.check(L.mpg_edge_nbr_bwd(None, 0, 0, _lib.ptr(x3), ldx, _lib.ptr(m), *[_lib.ptr(t) for t in (w0, b0, w1, b1, w2, b2)],
+                                          B, N, F, H0, H1, H2, ef_mode, nd, mean, alpha, p, seed, sptr, ws.data_ptr(), ws_bytes,
+                                          _lib.ptr(dagg), _lib.ptr(dx), F, _lib.ptr(dmask), *[_lib.ptr(g) for g in grads],
+                                          _lib.stream()), "mpg_edge_nbr_bwd")
+            dmask = dmask.view(ctx.mask_shape)
+        else:
+            frac = edge_active_fraction(m, B, N) if _profile is not None else 1.0
+            with _Timed("edge_bwd", 2.0 * edge_flops(B, N, F, H0, H1, H2),
+                        [(2, "edge_tc_bwd_chain_kernel", 2 * _pair_flops(B, N, H0, H1) + _pair_flops(B, N, H1, H2)),
+                         (3, "edge_tc_bwd_dw2_kernel", _pair_flops(B, N, H1, H2))], frac):
+                args = (_lib.ptr(x3), ldx, _lib.ptr(m), *[_lib.ptr(t) for t in (w0, b0, w1, b1, w2, b2)], B, N, F, H0, H1,
+                        H2, ef_mode, nd, mean, alpha, p, seed, sptr, prec, ws.data_ptr(), ws_bytes, _lib.ptr(dagg),
+                        _lib.ptr(dx), F, *[_lib.ptr(g) for g in grads], _lib.stream())
+                fws = ctx.fwd_ws
+                if fws is not None:   # P/Q, weight images and work list as the forward left them
+                    _lib.check(L.mpg_edge_bwd_saved(fws.data_ptr(), fws.numel(), *args), "mpg_edge_bwd_saved")
+                else:
+                    _lib.check(L.mpg_edge_bwd(*args), "mpg_edge_bwd")
         if direct:
             grads = [None] * 6
-        return (dx, None, *grads, None, None, None, None, None)
+        return (dx, dmask, *grads, None, None, None, None, None)
+
+
+class EdgeAggBwdFn(torch.autograd.Function):
+    """First-order backward of ``EdgeAggFn`` as a differentiable function of (dagg, x, mask, weights); outputs
+    (dx, dmask, dw0, db0, dw1, db1, dw2, db2).  Its backward -- the double backward the WGAN-GP term needs -- takes the
+    cotangents u of dx and vm of dmask (none of the weight gradients: nothing on this path forms them) and returns
+
+      d/d(dagg) = tagg(u) + agg(x; mask := vm)          tangent pass + an ordinary forward with vm as the mask
+      d/d(mask) = gmask(u)
+      d/d(x)    = dx(x, dagg; mask := vm)               ordinary backward with vm as the mask
+      d/dW      = dW2nd(u) + dW(x, dagg; mask := vm)
+
+    because fe is piecewise linear: <u, dx> = sum_ij mask_j <J_ij u, dagg_i> and <vm, dmask> = sum_ij vm_j <fe_ij,
+    dagg_i> (mpg_edge_bwd2; fp32 kernels; same dropout seed as the forward)."""
+
+    @staticmethod
+    def forward(ctx, dagg, x, mask, w0, b0, w1, b1, w2, b2, cfg, need_mask, need_w):
+        L = _lib.lib()
+        _, B, N, F, H0, H1, H2, ef_mode, nd, mean, alpha, p, seed, prec, sptr = cfg
+        x3, ldx = _rows(x)
+        m = None if mask is None else mask.reshape(B, N).contiguous()
+        cfg = (ldx,) + tuple(cfg[1:])
+        dev = dagg.device
+        dagg = dagg.contiguous()
+        ws_ = [t.contiguous() for t in (w0, b0, w1, b1, w2, b2)]
+        ws_bytes = L.mpg_edge_workspace_bytes(B, N, F, H0, H1, H2)
+        ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+        dx = torch.empty(B, N, F, device=dev, dtype=torch.float32)
+        grads = [torch.zeros_like(t) for t in ws_] if need_w else [None] * 6
+        dmask = torch.empty(B, N, device=dev, dtype=torch.float32) if need_mask else None
+        if need_mask:
+            _lib.check(L.mpg_edge_nbr_bwd(None, 0, 0, _lib.ptr(x3), ldx, _lib.ptr(m), *[_lib.ptr(t) for t in ws_], B, N, F,
+                                          H0, H1, H2, ef_mode, nd, mean, alpha, p, seed, sptr, ws.data_ptr(), ws_bytes,
+                                          _lib.ptr(dagg), _lib.ptr(dx), F, _lib.ptr(dmask), *[_lib.ptr(g) for g in grads],
+                                          _lib.stream()), "mpg_edge_nbr_bwd")
+        else:
+            _lib.check(L.mpg_edge_bwd(_lib.ptr(x3), ldx, _lib.ptr(m), *[_lib.ptr(t) for t in ws_], B, N, F, H0, H1, H2,
+                                      ef_mode, nd, mean, alpha, p, seed, sptr, prec, ws.data_ptr(), ws_bytes,
+                                      _lib.ptr(dagg), _lib.ptr(dx), F, *[_lib.ptr(g) for g in grads], _lib.stream()),
+                       "mpg_edge_bwd")
+        ctx.save_for_backward(dagg, x3, m, *ws_)
+        ctx.cfg = cfg
+        ctx.mask_in_shape = None if mask is None else tuple(mask.shape)
+        empty = torch.zeros(0, device=dev)
+        outs = [dx, dmask if need_mask else empty] + [g if need_w else empty for g in grads]
+        ctx.mark_non_differentiable(*outs[2:])
+        return tuple(outs)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, u, vm, *v_w):
+        L = _lib.lib()
+        dagg, x3, m, w0, b0, w1, b1, w2, b2 = ctx.saved_tensors
+        ldx, B, N, F, H0, H1, H2, ef_mode, nd, mean, alpha, p, seed, prec, sptr = ctx.cfg
+        if ef_mode != 0:
+            raise NotImplementedError("double backward through pair features (pos_diffs) is not implemented")
+        dev = dagg.device
+        ws_ = (w0, b0, w1, b1, w2, b2)
+        need_w = any(ctx.needs_input_grad[3:9])
+        g_dagg = torch.zeros(B, N, H2, device=dev, dtype=torch.float32)
+        g_x = g_mask = None
+        g_ws = [torch.zeros_like(t) for t in ws_] if need_w else [None] * 6
+        have_u = u is not None and u.numel() > 0
+        have_vm = vm is not None and vm.numel() > 0 and m is not None
+        if have_u:
+            u = u.contiguous()
+            ws_bytes = L.mpg_edge_bwd2_workspace_bytes(B, N, F, H0, H1, H2)
+            ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+            g_mask = torch.empty(B, N, device=dev, dtype=torch.float32) if (m is not None and ctx.needs_input_grad[2]) else None
+            _lib.check(L.mpg_edge_bwd2(_lib.ptr(x3), ldx, _lib.ptr(u), F, _lib.ptr(m), *[_lib.ptr(t) for t in ws_], B, N, F,
+                                       H0, H1, H2, mean, alpha, p, seed, sptr, ws.data_ptr(), ws_bytes, _lib.ptr(dagg),
+                                       _lib.ptr(g_dagg), _lib.ptr(g_mask), _lib.ptr(g_ws[0]), _lib.ptr(g_ws[2]),
+                                       _lib.ptr(g_ws[4]), _lib.stream()), "mpg_edge_bwd2")
+        if have_vm:
+            vmc = vm.contiguous().view(B, N)
+            ws_bytes = L.mpg_edge_workspace_bytes(B, N, F, H0, H1, H2)
+            ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+            agg_vm = torch.empty(B, N, H2, device=dev, dtype=torch.float32)
+            _lib.check(L.mpg_edge_fwd(_lib.ptr(x3), ldx, _lib.ptr(vmc), *[_lib.ptr(t) for t in ws_], B, N, F, H0, H1, H2,
+                                      ef_mode, nd, mean, alpha, p, seed, sptr, 0, ws.data_ptr(), ws_bytes,
+                                      _lib.ptr(agg_vm), _lib.stream()), "mpg_edge_fwd")
+            g_dagg += agg_vm
+            g_x = torch.empty(B, N, F, device=dev, dtype=torch.float32)
+            _lib.check(L.mpg_edge_bwd(_lib.ptr(x3), ldx, _lib.ptr(vmc), *[_lib.ptr(t) for t in ws_], B, N, F, H0, H1, H2,
+                                      ef_mode, nd, mean, alpha, p, seed, sptr, 0, ws.data_ptr(), ws_bytes, _lib.ptr(dagg),
+                                      _lib.ptr(g_x), F, *[_lib.ptr(g) for g in g_ws], _lib.stream()), "mpg_edge_bwd")
+        # gradients are w.r.t. this function's inputs: x [B, N, F] (dense), mask in its original shape
+        if g_mask is not None:
+            g_mask = g_mask.view(ctx.mask_in_shape)
+        return (g_dagg, g_x, g_mask, *g_ws, None, None, None)
 
 
 def edge_aggregate(x, mask, w0, b0, w1, b1, w2, b2, ef_mode=0, nd=0, mean=False, alpha=0.2, p_drop=0.0):
@@ -339,11 +544,25 @@ class NodeNetFn(torch.autograd.Function):
         return out
 
     @staticmethod
-    @once_differentiable
     def backward(ctx, dout):
         L = _lib.lib()
         a2, x2, y0, y1, w0, w1, w2 = ctx.saved_tensors
         lda, ldx, Ka, Kb, M, H1, H2, NO, alpha, p, seed, sptr = ctx.cfg
+        if torch.is_grad_enabled():
+            # create_graph: the chain layer by layer through the differentiable per-layer backward (same saved layer
+            # outputs, same dropout seed / streams 16, 17, 18 as the fused kernel)
+            need_w = _want_wgrad(ctx, 2, 8)
+            pw0, pb0, pw1, pb1, pw2, pb2 = ctx.params
+            lead = dout.shape[:-1]
+            cat = torch.cat((a2.reshape(M, Ka), x2.reshape(M, Kb)), 1)
+            cfg = lambda K, N, act, st: (K, M, K, N, act, alpha, p, seed, st, 1, sptr)
+            d1, gw2, gb2 = LinearBwdFn.apply(dout.reshape(M, NO), dout.reshape(M, NO), y1, pw2, cfg(H2, NO, 0, 18), True, need_w)
+            d0, gw1, gb1 = LinearBwdFn.apply(d1, y1, y0, pw1, cfg(H1, H2, 1, 17), True, need_w)
+            dc, gw0, gb0 = LinearBwdFn.apply(d0, y0, cat, pw0, cfg(Ka + Kb, H1, 1, 16), True, need_w)
+            da = dc[:, :Ka].reshape(*lead, Ka) if ctx.needs_input_grad[0] else None
+            db = dc[:, Ka:].reshape(*lead, Kb) if ctx.needs_input_grad[1] else None
+            gs = (gw0, gb0, gw1, gb1, gw2, gb2) if need_w else (None,) * 6
+            return (da, db, *gs, None, None, None)
         dev = dout.device
         dout = dout.contiguous()
         ws_bytes = L.mpg_fn_workspace_bytes(Ka, Kb, H1, H2, NO)
@@ -353,8 +572,8 @@ class NodeNetFn(torch.autograd.Function):
         dz2 = torch.empty(M, NO, device=dev, dtype=torch.float32) if p > 0 else None
         da = torch.empty(*a2.shape, device=dev, dtype=torch.float32)
         db = torch.empty(*x2.shape, device=dev, dtype=torch.float32)
-        need_w = any(ctx.needs_input_grad[2:8])
-        sinks = [_grad_sink(q) for q in ctx.params] if all(ctx.needs_input_grad[2:8]) else [None] * 6
+        need_w = _want_wgrad(ctx, 2, 8)
+        sinks = [_grad_sink(q) for q in ctx.params] if (need_w and all(ctx.needs_input_grad[2:8])) else [None] * 6
         direct = all(g is not None for g in sinks)
         if direct:
             grads = sinks
@@ -500,10 +719,9 @@ def permute_batch(x, pos, mode: int):
     return permute_rows(x.reshape(1, B, -1), pos.view(1, B), mode).view(x.shape)
 
 
-def split_mask(x):
-    """mask = x[..., -1:] + 0.5 (fp32 multiplier) for the discriminator input."""
+def _split_mask_raw(x):
     L = _lib.lib()
-    x3, ldx = _rows(x.detach())
+    x3, ldx = _rows(x)
     if ldx != x3.shape[-1]:
         x3 = x3.contiguous()
         ldx = x3.shape[-1]
@@ -511,6 +729,52 @@ def split_mask(x):
     mask = torch.empty(B, N, 1, device=x.device, dtype=torch.float32)
     _lib.check(L.mpg_split_mask(_lib.ptr(x3), ldx, B * N, _lib.ptr(mask), _lib.stream()), "mpg_split_mask")
     return mask
+
+
+class SplitMaskFn(torch.autograd.Function):
+    """mask = x[..., -1:] + 0.5, differentiable (mpgan/model.py:881, gapt/model.py:334): the gradient lands in the last
+    column of dx.  Linear, so the double backward is the slice of the cotangent."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.xshape = tuple(x.shape)
+        return _split_mask_raw(x)
+
+    @staticmethod
+    def backward(ctx, dmask):
+        if torch.is_grad_enabled():
+            return SplitMaskBwdFn.apply(dmask, ctx.xshape)
+        return _split_mask_bwd_raw(dmask, ctx.xshape)
+
+
+def _split_mask_bwd_raw(dmask, xshape):
+    L = _lib.lib()
+    dm = dmask.contiguous()
+    dx = torch.empty(xshape, device=dm.device, dtype=torch.float32)
+    _lib.check(L.mpg_split_mask_bwd(_lib.ptr(dm), _lib.ptr(dx), xshape[-1], dm.numel(), _lib.stream()),
+               "mpg_split_mask_bwd")
+    return dx
+
+
+class SplitMaskBwdFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, dmask, xshape):
+        ctx.mshape = tuple(dmask.shape)
+        return _split_mask_bwd_raw(dmask, xshape)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, v):
+        return (_split_mask_raw(v) - 0.5).view(ctx.mshape), None
+
+
+def split_mask(x):
+    """mask = x[..., -1:] + 0.5 (fp32 multiplier) for the discriminator input.  Differentiable when ``x`` requires
+    grad, unless ``x`` is marked as having a constant mask channel (``GenTailFn`` output: a generated jet's mask is a
+    function of the noise ranks only, so its gradient would be discarded upstream anyway)."""
+    if x.requires_grad and torch.is_grad_enabled() and not getattr(x, "_mpg_const_mask", False):
+        return SplitMaskFn.apply(x)
+    return _split_mask_raw(x.detach())
 
 
 _ACT = {"": 0, "tanh": 1, "sigmoid": 2}
@@ -547,7 +811,10 @@ class GenTailFn(torch.autograd.Function):
 
 
 def gen_tail(h, mask, activation: str):
-    return GenTailFn.apply(h, mask, _ACT[activation])
+    out = GenTailFn.apply(h, mask, _ACT[activation])
+    if mask is not None:
+        out._mpg_const_mask = True   # see split_mask: nothing upstream consumes d/d(mask channel)
+    return out
 
 
 class PoolFn(torch.autograd.Function):
@@ -568,19 +835,111 @@ class PoolFn(torch.autograd.Function):
         return out
 
     @staticmethod
-    @once_differentiable
     def backward(ctx, dout):
-        L = _lib.lib()
         m = ctx.saved_tensors[0] if ctx.has_mask else None
+        if torch.is_grad_enabled():   # linear in dout: its own adjoint is the forward pool
+            return PoolBwdFn.apply(dout, m, ctx.cfg), None, None
+        return _pool_bwd(dout, m, ctx.cfg), None, None
+
+
+def _pool_bwd(dout, m, cfg):
+    L = _lib.lib()
+    B, N, Cc, mean = cfg
+    dout = dout.contiguous()
+    dh = torch.empty(B, N, Cc, device=dout.device, dtype=torch.float32)
+    _lib.check(L.mpg_pool_bwd(_lib.ptr(dout), _lib.ptr(m), _lib.ptr(dh), B, N, Cc, mean, _lib.stream()), "mpg_pool_bwd")
+    return dh
+
+
+class PoolBwdFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, dout, m, cfg):
+        ctx.m, ctx.cfg = m, cfg
+        return _pool_bwd(dout, m, cfg)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, v):
+        L = _lib.lib()
         B, N, Cc, mean = ctx.cfg
-        dout = dout.contiguous()
-        dh = torch.empty(B, N, Cc, device=dout.device, dtype=torch.float32)
-        _lib.check(L.mpg_pool_bwd(_lib.ptr(dout), _lib.ptr(m), _lib.ptr(dh), B, N, Cc, mean, _lib.stream()),
-                   "mpg_pool_bwd")
-        return dh, None, None
+        v = v.contiguous()
+        g = torch.empty(B, Cc, device=v.device, dtype=torch.float32)
+        _lib.check(L.mpg_pool_fwd(_lib.ptr(v), _lib.ptr(ctx.m), _lib.ptr(g), B, N, Cc, mean, _lib.stream()), "mpg_pool_fwd")
+        return g, None, None
+
+
+class PoolSumFn(torch.autograd.Function):
+    """sum_i h[b,i] * mask[b,i] with gradients w.r.t. BOTH h and the mask (bilinear); double-differentiable."""
+
+    @staticmethod
+    def forward(ctx, h, mask):
+        L = _lib.lib()
+        hc = h.contiguous()
+        B, N, Cc = hc.shape
+        m = mask.reshape(B, N).contiguous()
+        out = torch.empty(B, Cc, device=h.device, dtype=torch.float32)
+        _lib.check(L.mpg_pool_fwd(_lib.ptr(hc), _lib.ptr(m), _lib.ptr(out), B, N, Cc, 0, _lib.stream()), "mpg_pool_fwd")
+        ctx.save_for_backward(h, mask)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        h, mask = ctx.saved_tensors
+        if torch.is_grad_enabled():
+            return PoolSumBwdFn.apply(dout, h, mask)
+        return _pool_sum_bwd(dout, h, mask)
+
+
+def _pool_sum_bwd(dout, h, mask):
+    L = _lib.lib()
+    hc, dout = h.contiguous(), dout.contiguous()
+    B, N, Cc = hc.shape
+    m = mask.reshape(B, N).contiguous()
+    dh = torch.empty(B, N, Cc, device=h.device, dtype=torch.float32)
+    dm = torch.empty(B, N, device=h.device, dtype=torch.float32)
+    _lib.check(L.mpg_pool_bwd(_lib.ptr(dout), _lib.ptr(m), _lib.ptr(dh), B, N, Cc, 0, _lib.stream()), "mpg_pool_bwd")
+    _lib.check(L.mpg_pool_dmask(_lib.ptr(hc), _lib.ptr(dout), _lib.ptr(dm), B, N, Cc, 1.0, _lib.stream()), "mpg_pool_dmask")
+    return dh, dm.view(mask.shape)
+
+
+class PoolSumBwdFn(torch.autograd.Function):
+    """(dh, dmask) = (dout * mask, <h, dout>); backward for cotangents (vh, vm):
+    d/d(dout) = pool(vh, mask) + pool(h, vm),  d/dh = dout * vm,  d/d(mask) = <vh, dout>."""
+
+    @staticmethod
+    def forward(ctx, dout, h, mask):
+        ctx.save_for_backward(dout, h, mask)
+        return _pool_sum_bwd(dout, h, mask)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, vh, vm):
+        L = _lib.lib()
+        dout, h, mask = ctx.saved_tensors
+        hc, dout = h.contiguous(), dout.contiguous()
+        B, N, Cc = hc.shape
+        m = mask.reshape(B, N).contiguous()
+        vh = vh.contiguous()
+        vmc = vm.reshape(B, N).contiguous()
+        g_dout = torch.empty(B, Cc, device=h.device, dtype=torch.float32)
+        t = torch.empty_like(g_dout)
+        _lib.check(L.mpg_pool_fwd(_lib.ptr(vh), _lib.ptr(m), _lib.ptr(g_dout), B, N, Cc, 0, _lib.stream()), "mpg_pool_fwd")
+        _lib.check(L.mpg_pool_fwd(_lib.ptr(hc), _lib.ptr(vmc), _lib.ptr(t), B, N, Cc, 0, _lib.stream()), "mpg_pool_fwd")
+        g_dout += t
+        g_h = torch.empty(B, N, Cc, device=h.device, dtype=torch.float32)
+        _lib.check(L.mpg_pool_bwd(_lib.ptr(dout), _lib.ptr(vmc), _lib.ptr(g_h), B, N, Cc, 0, _lib.stream()), "mpg_pool_bwd")
+        g_m = torch.empty(B, N, device=h.device, dtype=torch.float32)
+        _lib.check(L.mpg_pool_dmask(_lib.ptr(vh), _lib.ptr(dout), _lib.ptr(g_m), B, N, Cc, 1.0, _lib.stream()), "mpg_pool_dmask")
+        return g_dout, g_h, g_m.view(mask.shape)
 
 
 def masked_pool(h, mask, mean: bool):
+    """sum_i h[b,i] * mask[b,i], divided by (sum_i mask + 1e-12) if ``mean`` (mpgan/model.py:810-822).  When the mask
+    itself carries a gradient (D differentiated w.r.t. its input's mask channel, e.g. the gradient penalty) the
+    bilinear sum is its own doubly differentiable op and the division is left to autograd on the [B, C] result."""
+    if mask is not None and mask.requires_grad and torch.is_grad_enabled():
+        s = PoolSumFn.apply(h, mask)
+        return s / (mask.sum(1) + 1e-12) if mean else s
     return PoolFn.apply(h, mask, mean)
 
 
@@ -707,7 +1066,7 @@ class ResidualDropoutFn(torch.autograd.Function):
     def forward(ctx, x, r, p_drop, rng_stream):
         L = _lib.lib()
         x = x.contiguous()
-        r = r.contiguous()
+        r = None if r is None else r.contiguous()
         cols = x.shape[-1]
         rows = x.numel() // cols
         out = torch.empty_like(x)
@@ -716,6 +1075,7 @@ class ResidualDropoutFn(torch.autograd.Function):
                                               seed, _seed_ptr(), int(rng_stream), _lib.stream()),
                    "mpg_residual_dropout_fwd")
         ctx.cfg = (rows, cols, float(p_drop), seed, _seed_ptr(), int(rng_stream))
+        ctx.has_r = r is not None
         return out
 
     @staticmethod
@@ -725,12 +1085,160 @@ class ResidualDropoutFn(torch.autograd.Function):
         rows, cols, p, seed, sptr, rstream = ctx.cfg
         dout = dout.contiguous()
         if p == 0:
-            return dout, dout, None, None
+            return dout, (dout if ctx.has_r else None), None, None
         dx = torch.empty_like(dout)
         _lib.check(L.mpg_residual_dropout_bwd(_lib.ptr(dout), _lib.ptr(dx), rows, cols, p, seed, sptr, rstream,
                                               _lib.stream()), "mpg_residual_dropout_bwd")
-        return dx, dx, None, None
+        return dx, (dx if ctx.has_r else None), None, None
 
 
 def residual_dropout(x, r, p_drop: float, rng_stream: int = 48):
     return ResidualDropoutFn.apply(x, r, p_drop, rng_stream)
+
+
+# --------------------------------------------------------------------------------------------------
+# GAPT LayerNorm
+# --------------------------------------------------------------------------------------------------
+class LayerNormFn(torch.autograd.Function):
+    """nn.LayerNorm(C) over the last dimension (gapt/model.py:116-118, 130-136)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, eps):
+        L = _lib.lib()
+        xc = x.contiguous()
+        Cc = xc.shape[-1]
+        rows = xc.numel() // Cc
+        y = torch.empty_like(xc)
+        mean = torch.empty(rows, device=x.device, dtype=torch.float32)
+        rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
+        wc, bc = w.contiguous(), b.contiguous()
+        _lib.check(L.mpg_layernorm_fwd(_lib.ptr(xc), _lib.ptr(wc), _lib.ptr(bc), _lib.ptr(y), _lib.ptr(mean),
+                                       _lib.ptr(rstd), rows, Cc, float(eps), _lib.stream()), "mpg_layernorm_fwd")
+        ctx.save_for_backward(xc, wc, mean, rstd)
+        ctx.params = (w, b)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        L = _lib.lib()
+        xc, wc, mean, rstd = ctx.saved_tensors
+        Cc = xc.shape[-1]
+        rows = xc.numel() // Cc
+        dy = dy.contiguous()
+        dx = torch.empty_like(xc)
+        need_w = _want_wgrad(ctx, 1, 3)
+        sinks = [_grad_sink(q) for q in ctx.params] if need_w else [None, None]
+        direct = all(g is not None for g in sinks)
+        if direct:
+            dw, db = sinks
+        elif need_w:
+            dw, db = torch.zeros_like(wc), torch.zeros_like(wc)
+        else:
+            dw = db = None
+        _lib.check(L.mpg_layernorm_bwd(_lib.ptr(dy), _lib.ptr(xc), _lib.ptr(wc), _lib.ptr(mean), _lib.ptr(rstd),
+                                       _lib.ptr(dx), _lib.ptr(dw), _lib.ptr(db), rows, Cc, _lib.stream()),
+                   "mpg_layernorm_bwd")
+        if direct:
+            dw = db = None
+        return dx, dw, db, None
+
+
+def layer_norm(x, w, b, eps: float = 1e-5):
+    return LayerNormFn.apply(x, w, b, eps)
+
+
+# --------------------------------------------------------------------------------------------------
+# kNN message passing (mpgan/model.py:319-381)
+# --------------------------------------------------------------------------------------------------
+def knn_select(x, mask, k: int, nd: int, self_loops: bool = True):
+    """int32 [B, N, k]: the k nearest senders of every receiver (see mpg_knn_select)."""
+    L = _lib.lib()
+    x3, ldx = _rows(x.detach())
+    B, N = x3.shape[0], x3.shape[1]
+    m = None if mask is None else mask.detach().reshape(B, N).contiguous()
+    idx = torch.empty(B, N, k, device=x.device, dtype=torch.int32)
+    _lib.check(L.mpg_knn_select(_lib.ptr(x3), ldx, _lib.ptr(m), B, N, int(nd), int(k), int(bool(self_loops)),
+                                _lib.ptr(idx), _lib.stream()), "mpg_knn_select")
+    return idx
+
+
+class EdgeNbrFn(torch.autograd.Function):
+    """agg[b,i] = scale * sum_m mask[b, nbr[b,i,m]] fe(x_i | x_nbr | [dist]) over the listed neighbours."""
+
+    @staticmethod
+    def forward(ctx, x, mask, nbr, w0, b0, w1, b1, w2, b2, ef_mode, nd, mean, alpha, p_drop):
+        L = _lib.lib()
+        x3, ldx = _rows(x)
+        B, N, F = x3.shape
+        K = nbr.shape[2]
+        H0, H1, H2 = w0.shape[0], w1.shape[0], w2.shape[0]
+        ws_bytes = L.mpg_edge_workspace_bytes(B, N, F, H0, H1, H2)
+        ws = torch.empty(ws_bytes, device=x.device, dtype=torch.uint8)
+        agg = torch.empty(B, N, H2, device=x.device, dtype=torch.float32)
+        m = None if mask is None else mask.reshape(B, N).contiguous()
+        ws_ = [t.contiguous() for t in (w0, b0, w1, b1, w2, b2)]
+        seed = next_seed() if p_drop > 0 else 0
+        scale = int(m is not None)
+        _lib.check(L.mpg_edge_nbr_fwd(_lib.ptr(nbr), K, scale, _lib.ptr(x3), ldx, _lib.ptr(m), *[_lib.ptr(t) for t in ws_],
+                                      B, N, F, H0, H1, H2, int(ef_mode), int(nd), int(mean), float(alpha), float(p_drop),
+                                      seed, _seed_ptr(), ws.data_ptr(), ws_bytes, _lib.ptr(agg), _lib.stream()),
+                   "mpg_edge_nbr_fwd")
+        ctx.save_for_backward(x3, m, nbr, *ws_)
+        ctx.params = (w0, b0, w1, b1, w2, b2)
+        ctx.cfg = (ldx, B, N, F, K, H0, H1, H2, int(ef_mode), int(nd), int(mean), float(alpha), float(p_drop), seed,
+                   scale, _seed_ptr())
+        return agg
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dagg):
+        L = _lib.lib()
+        x3, m, nbr, w0, b0, w1, b1, w2, b2 = ctx.saved_tensors
+        ldx, B, N, F, K, H0, H1, H2, ef_mode, nd, mean, alpha, p, seed, scale, sptr = ctx.cfg
+        dagg = dagg.contiguous()
+        ws_bytes = L.mpg_edge_workspace_bytes(B, N, F, H0, H1, H2)
+        ws = torch.empty(ws_bytes, device=dagg.device, dtype=torch.uint8)
+        dx = torch.empty(B, N, F, device=dagg.device, dtype=torch.float32)
+        want_w = _want_wgrad(ctx, 3, 9)
+        sinks = [_grad_sink(q) for q in ctx.params] if (want_w and all(ctx.needs_input_grad[3:9])) else [None] * 6
+        direct = all(g is not None for g in sinks)
+        if direct:
+            grads = sinks
+        elif want_w:
+            grads = [torch.zeros_like(t) for t in (w0, b0, w1, b1, w2, b2)]
+        else:
+            grads = [None] * 6
+        _lib.check(L.mpg_edge_nbr_bwd(_lib.ptr(nbr), K, scale, _lib.ptr(x3), ldx, _lib.ptr(m),
+                                      *[_lib.ptr(t) for t in (w0, b0, w1, b1, w2, b2)], B, N, F, H0, H1, H2, ef_mode, nd,
+                                      mean, alpha, p, seed, sptr, ws.data_ptr(), ws_bytes, _lib.ptr(dagg), _lib.ptr(dx), F,
+                                      None, *[_lib.ptr(g) for g in grads], _lib.stream()), "mpg_edge_nbr_bwd")
+        if direct:
+            grads = [None] * 6
+        return (dx, None, None, *grads, None, None, None, None, None)
+
+
+def edge_aggregate_knn(x, mask, nbr, w0, b0, w1, b1, w2, b2, ef_mode=0, nd=0, mean=False, alpha=0.2, p_drop=0.0):
+    return EdgeNbrFn.apply(x, mask, nbr, w0, b0, w1, b1, w2, b2, ef_mode, nd, mean, alpha, p_drop)
+
+
+# --------------------------------------------------------------------------------------------------
+# generation post-processing (gen.py:126-141)
+# --------------------------------------------------------------------------------------------------
+def gen_postprocess(jets, out, shift, norm, maxv, use_mask: bool = True):
+    """out[r, i] = ((jets[r, i] - shift[i]) / norm[i]) * maxv[i], masked particles zeroed, feature 2 clamped at 0.
+    ``out`` ([rows..., nfeat], fp32) may be a pinned host tensor: the kernel writes straight into it."""
+    import ctypes as C
+    L = _lib.lib()
+    j3, ldj = _rows(jets.detach())
+    nfeat = out.shape[-1]
+    rows = j3.numel() // j3.shape[-1]
+    if out.numel() != rows * nfeat or not out.is_contiguous() or out.dtype != torch.float32:
+        raise ValueError("gen_postprocess: out must be a contiguous fp32 tensor of shape [..., nfeat] matching jets")
+    if not (out.is_cuda or out.is_pinned()):
+        raise RuntimeError("gen_postprocess: out must live on the GPU or in pinned host memory")
+    nan = float("nan")
+    arr = lambda v: (C.c_float * nfeat)(*[nan if (v is None or v[i] is None) else float(v[i]) for i in range(nfeat)])
+    _lib.check(L.mpg_gen_postprocess(_lib.ptr(j3), ldj, out.data_ptr(), nfeat, rows, nfeat, arr(shift), arr(norm),
+                                     arr(maxv), int(bool(use_mask)), _lib.stream()), "mpg_gen_postprocess")
+    return out

@@ -70,10 +70,54 @@ def get_gen_noise(batch_size, num_particles, latent_node_size, sd=0.2, device="c
     return torch.empty(batch_size, num_particles, latent_node_size, device=device).normal_(0.0, sd, generator=generator)
 
 
+def gradient_penalty(gp_lambda, D, real_data, generated_data, alpha=None, labels=None):
+    """WGAN-GP term (reference ``gradient_penalty``, train.py:286-324): D at the interpolate
+    x = alpha * real + (1 - alpha) * fake (alpha ~ U[0,1) per jet), the gradient of sum(D(x)) w.r.t. x taken with the
+    graph kept (``create_graph``: the second-order kernels of ops.EdgeAggBwdFn / LinearBwdFn), and
+    gp = lambda * mean((sqrt(sum_jet grad^2 + 1e-12) - 1)^2).  The reference calls D without labels (:303)."""
+    B = real_data.shape[0]
+    if alpha is None:
+        alpha = torch.rand(B, 1, 1, device=real_data.device)
+    x = (alpha * real_data + (1 - alpha) * generated_data).detach().requires_grad_(True)
+    out = D(x, labels)
+    with ops.input_grad_only():   # dD/dx only: the parameters' first-order gradients are not part of the penalty
+        (g,) = torch.autograd.grad(out, x, grad_outputs=torch.ones_like(out), create_graph=True, retain_graph=True)
+    gn = torch.sqrt(torch.sum(g.reshape(B, -1) ** 2, dim=1) + 1e-12)
+    return gp_lambda * ((gn - 1) ** 2).mean()
+
+
+def d_loss(loss, real_out, fake_out):
+    """Critic losses of calc_D_loss (train.py:364-378) without label smoothing / noise."""
+    if loss == "ls":
+        return ops.ls_loss(torch.cat((real_out, fake_out), 0), real_out.shape[0], 1.0, 0.0)
+    if loss == "w":
+        return fake_out.mean() - real_out.mean()
+    if loss == "hinge":
+        return torch.relu(1.0 - real_out).mean() + torch.relu(1.0 + fake_out).mean()
+    if loss == "og":
+        return torch.nn.functional.binary_cross_entropy(real_out, torch.ones_like(real_out)) + \
+            torch.nn.functional.binary_cross_entropy(fake_out, torch.zeros_like(fake_out))
+    raise ValueError(f"unknown loss {loss!r}")
+
+
+def g_loss(loss, fake_out):
+    """calc_G_loss (train.py:465-476)."""
+    if loss == "ls":
+        return ops.ls_loss(fake_out, fake_out.shape[0], 1.0)
+    if loss in ("w", "hinge"):
+        return -fake_out.mean()
+    if loss == "og":
+        return torch.nn.functional.binary_cross_entropy(fake_out, torch.ones_like(fake_out))
+    raise ValueError(f"unknown loss {loss!r}")
+
+
 class GANTrainer:
     def __init__(self, G, D, lr_gen=1e-5, lr_disc=3e-5, num_particles=30, latent_node_size=32, sd=0.2,
-                 process_group=None, batch_real_fake=True, sort_by_count=True, world_override=None):
+                 process_group=None, batch_real_fake=True, sort_by_count=True, world_override=None, loss="ls", gp=0.0):
         self.G, self.D = G, D
+        # loss in {"ls", "w", "hinge", "og"} and gp = the gradient-penalty weight (train.py --loss / --gp); the losses
+        # other than "ls" are a few torch reductions over the [B, 1] discriminator outputs
+        self.loss, self.gp = loss, float(gp)
         # With spectral norm every D forward runs one power iteration (u, v advance; spectral_normalization.py:21-33):
         # the reference's two calls D(real), D(fake) advance them twice per train_D and use different sigmas, so one
         # batched pass would not be the same update -> keep the two calls.
@@ -130,7 +174,7 @@ class GANTrainer:
             torch.cuda.current_stream().wait_stream(self._comm_stream)
             self._comm_pending = False
 
-    def train_D(self, data, labels, noise=None, overlap_update=False):
+    def train_D(self, data, labels, noise=None, overlap_update=False, gp_alpha=None):
         self._join_comm()
         self.D.train()
         self.fpD.zero_grad()
@@ -147,9 +191,13 @@ class GANTrainer:
             B = data.shape[0]
             d_both = torch.cat((self.D(data, labels), self.D(fake, labels)), 0)
         # least squares: real -> 1, fake -> 0 (train.py:357-358, 369-370, 378), one kernel
-        loss = ops.ls_loss(d_both, B, 1.0, 0.0)
+        loss = ops.ls_loss(d_both, B, 1.0, 0.0) if self.loss == "ls" else d_loss(self.loss, d_both[:B], d_both[B:])
         with ops.direct_grad():
             loss.backward()
+        if self.gp:   # train.py:380-383: the penalty's gradients add to the critic loss's
+            gp = gradient_penalty(self.gp, self.D, data, fake, alpha=gp_alpha)
+            gp.backward()
+            loss = loss.detach() + gp.detach()
         if overlap_update and self.world > 1 and data.is_cuda:
             if self._comm_stream is None:
                 self._comm_stream = torch.cuda.Stream(device=data.device)
@@ -171,7 +219,7 @@ class GANTrainer:
             p.requires_grad_(False)
         try:
             d_fake = self.D(fake, labels)  # D stays in train mode: its dropout is active (train.py:419,494)
-            loss = ops.ls_loss(d_fake, d_fake.shape[0], 1.0)  # train.py:467,472
+            loss = g_loss(self.loss, d_fake)  # train.py:467,472
             with ops.direct_grad():
                 loss.backward()
         finally:
@@ -272,11 +320,8 @@ class GANTrainer:
 
 def sort_by_count(data, labels):
     """Reorders a batch by descending particle count (labels[:, -1] = n / N); see GANTrainer.sort_by_count."""
-    if data.is_cuda and labels.shape[0] <= 8192:
-        pos = ops.batch_order(labels)                      # one kernel; pos[b] = new index of jet b
-        return ops.permute_batch(data, pos, 0), ops.permute_batch(labels, pos, 0)
-    order = torch.argsort(labels[:, -1], descending=True, stable=True)
-    return data.index_select(0, order), labels.index_select(0, order)
+    pos = ops.batch_order(labels)                      # one kernel; pos[b] = new index of jet b
+    return ops.permute_batch(data, pos, 0), ops.permute_batch(labels, pos, 0)
 
 
 @torch.no_grad()
@@ -284,21 +329,13 @@ def generate(G, labels, num_particles, latent_node_size=32, sd=0.2, noise=None):
     """G(noise, labels) with the jets processed in order of particle count (fewer live edge-kernel steps, see
     GANTrainer.sort_by_count) and returned in the caller's order."""
     B = labels.shape[0]
-    if labels.is_cuda and B <= 8192:
-        pos = ops.batch_order(labels)
-        if noise is None:
-            noise = get_gen_noise(B, num_particles, latent_node_size, sd, labels.device)
-        else:
-            noise = ops.permute_batch(noise, pos, 0)
-        out_sorted = G(noise, ops.permute_batch(labels, pos, 0))
-        return ops.permute_batch(out_sorted, pos, 1)       # out[b] = out_sorted[pos[b]]
-    order = torch.argsort(labels[:, -1], descending=True, stable=True)
+    pos = ops.batch_order(labels)
     if noise is None:
         noise = get_gen_noise(B, num_particles, latent_node_size, sd, labels.device)
     else:
-        noise = noise.index_select(0, order)
-    out_sorted = G(noise, labels.index_select(0, order))
-    return torch.empty_like(out_sorted).index_copy_(0, order, out_sorted)
+        noise = ops.permute_batch(noise, pos, 0)
+    out_sorted = G(noise, ops.permute_batch(labels, pos, 0))
+    return ops.permute_batch(out_sorted, pos, 1)       # out[b] = out_sorted[pos[b]]
 
 
 class GraphedGenerator:
@@ -350,25 +387,69 @@ def synthetic_jets(B, N, device="cuda", generator=None, all_real=False):
     return x, labels, n
 
 
+# un-normalisation constants of gen.py:10-17 (JetNet gluon / light-quark / top jets)
+FEATURE_MAXES = {
+    "g": [1.4532885551452637, 0.520724892616272, 0.8537549376487732, 1.0],
+    "q": [1.6211985349655151, 0.4568111002445221, 0.8896132111549377, 1.0],
+    "t": [1.4242753982543945, 0.4949831962585449, 0.8774275183677673, 1.0],
+}
+FEATURE_NORMS = [1.0, 1.0, 1.0, 1.0]
+FEATURE_SHIFTS = [0.0, 0.0, -0.5, -0.5]
+
+
+def rank_shard(num_samples, rank=None, world=None):
+    """[start, end) of the samples rank ``rank`` of ``world`` generates: generation shards over jets with no
+    communication (every rank holds the full generator)."""
+    if world is None:
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        rank = dist.get_rank() if world > 1 else 0
+    per = (num_samples + world - 1) // world
+    return min(rank * per, num_samples), min((rank + 1) * per, num_samples)
+
+
 @torch.no_grad()
 def gen_multi_batch(G, num_samples, batch_size, num_particles, labels=None, latent_node_size=32, sd=0.2,
-                    out_device="cpu", pin=True):
+                    out_device="cpu", pin=True, noise=None, jets=None, mask=True, rank=None, world=None):
     """Generates ``num_samples`` jets in batches into ONE pre-allocated output (train.py:226-282
     without its O(n^2) ``torch.cat`` and without the duplicated last batch when
-    ``num_samples % batch_size == 0``)."""
+    ``num_samples % batch_size == 0``).
+
+    ``jets`` in {"g", "q", "t"}: also apply gen.py's post-processing (:126-141: un-normalise, zero the masked
+    particles, clamp the third feature, drop the mask channel) -- one kernel per batch writing straight into the
+    (pinned) output, which is then [n, N, 3] and ready for ``np.save``.  ``noise``: explicit [num_samples, N, latent]
+    noise (reproducible runs).  ``rank`` / ``world``: generate only this rank's shard (``rank_shard``); the returned
+    tensor holds the shard's jets in order."""
     G.eval()
     dev = next(G.parameters()).device
-    out_feats = G.output_node_size + 1
-    out = torch.empty(num_samples, num_particles, out_feats, device=out_device,
+    start0, end0 = (0, num_samples) if (world is None and rank is None and not (dist.is_available() and dist.is_initialized())) \
+        else rank_shard(num_samples, rank, world)
+    n_out = end0 - start0
+    out_feats = 3 if jets is not None else G.output_node_size + 1
+    out = torch.empty(n_out, num_particles, out_feats, device=out_device,
                       pin_memory=(pin and out_device == "cpu"))
-    for start in range(0, num_samples, batch_size):
-        n = min(batch_size, num_samples - start)
+    direct = jets is not None and (out.is_cuda or out.is_pinned())
+    for start in range(start0, end0, batch_size):
+        n = min(batch_size, end0 - start)
         lab = None if labels is None else labels[start:start + n].to(dev, non_blocking=True)
+        nz = None if noise is None else noise[start:start + n].to(dev, non_blocking=True)
         if lab is None:
-            jets = G(get_gen_noise(n, num_particles, latent_node_size, sd, dev), lab)
+            batch = G(get_gen_noise(n, num_particles, latent_node_size, sd, dev) if nz is None else nz, lab)
         else:   # eager: at 4096-jet batches the launches are not the bound (a graph's capture cost loses on a 1M sweep)
-            jets = generate(G, lab, num_particles, latent_node_size, sd)
-        out[start:start + n].copy_(jets, non_blocking=True)
+            batch = generate(G, lab, num_particles, latent_node_size, sd, noise=nz)
+        dst = out[start - start0:start - start0 + n]
+        if jets is not None:
+            tgt = dst if direct else torch.empty(n, num_particles, 3, device=dev)
+            ops.gen_postprocess(batch, tgt, FEATURE_SHIFTS[:3], FEATURE_NORMS[:3], FEATURE_MAXES[jets][:3], use_mask=mask)
+            if not direct:
+                dst.copy_(tgt, non_blocking=True)
+        else:
+            dst.copy_(batch, non_blocking=True)
     if dev.type == "cuda":
         torch.cuda.current_stream().synchronize()
     return out
+
+
+def save_jets(path, gen_jets):
+    """gen.py:143: ``np.save(output_file, gen_jets[:, :, :3])``."""
+    import numpy as np
+    np.save(path, gen_jets[:, :, :3].cpu().numpy())

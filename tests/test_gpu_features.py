@@ -1,0 +1,240 @@
+"""GPU parity of the round-2 features against goldens minted from the unmodified reference: WGAN-GP (double backward
+incl. the mask-channel gradient), kNN message passing, GAPT LayerNorm, the generation driver's post-processing, and
+small op-level checks (LayerNorm, second-order linear layer, batch ordering beyond one CTA)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mpgan_oracle as mo
+from test_gpu_parity import close, close_grad, rel, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _precision():
+    from mpgan_b200 import ops
+    ops.set_precision(0)
+    yield
+    ops.set_precision(1)
+
+
+@pytest.mark.parametrize("prec", [0, 1])
+def test_wgan_gp_golden(golden, prec):
+    """train.gradient_penalty (train.py:286-324) through the reference's own function: the penalty, its gradients
+    w.r.t. every D parameter (second-order kernels), the first-order input gradient incl. the mask channel, and the
+    whole critic loss 'w' + 10 * gp.  precision 1 runs the first-order passes on the tcgen05 / TF32 kernels (the
+    second-order products are fp32 kernels in both modes)."""
+    from mpgan_b200 import ops, presets, train
+    ops.set_precision(prec)
+    ft, gt = (2e-4, 3e-3) if prec == 0 else (3e-2, 1e-1)
+
+    def close_grad(a, b, prec, what, tol):   # precision 1: relative L2 (1e-1) + a 3e-1 max-abs guard -- these are
+        if prec == 0:                        # gradients OF gradients of a randomly initialised D on 6 jets
+            return close(a, b, tol, what)
+        assert rel_l2(a, b) <= tol and rel(a, b) <= 3e-1, f"{what}: rel L2 {rel_l2(a, b):.3e}, max-abs {rel(a, b):.3e}"
+
+    for name, c in golden("wgan_gp.pt").items():
+        D = presets.mp_discriminator(disc_dropout=0.0, loss="w", **c["over"]).cuda().train()
+        D.load_state_dict(c["sd"], strict=True)
+        real, fake, alpha = c["real"].cuda(), c["fake"].cuda(), c["alpha"].cuda()
+        # first-order dD/dx at the interpolate (mask channel included)
+        xi = (alpha * real + (1 - alpha) * fake).requires_grad_(True)
+        (gi,) = torch.autograd.grad(D(xi).sum(), xi)
+        close_grad(gi, c["dx_interp"], prec, f"{name} dD/dx", tol=gt)
+        if name == "masked":
+            assert float(gi[..., 3].abs().max()) > 0, "the mask channel must carry a gradient"
+            close_grad(gi[..., 3], c["dx_interp"][..., 3], prec, f"{name} dD/d(mask channel)", tol=gt)
+        D.zero_grad()
+        gp = train.gradient_penalty(10.0, D, real, fake, alpha=alpha)
+        close(gp, c["gp"], ft, f"{name} gp")
+        gp.backward()
+        params = dict(D.named_parameters())
+        for k, g in c["gp_grads"].items():
+            close_grad(params[k].grad, g, prec, f"{name} gp grad {k}", tol=gt)
+        # whole critic loss
+        D.zero_grad()
+        labels = c["labels"].cuda()
+        loss = train.d_loss("w", D(real, labels), D(fake, labels)) + train.gradient_penalty(10.0, D, real, fake, alpha=alpha)
+        close(loss, c["d_loss"], ft, f"{name} critic loss")
+        loss.backward()
+        for k, g in c["d_loss_grads"].items():
+            close_grad(params[k].grad, g, prec, f"{name} critic grad {k}", tol=gt)
+
+
+def test_trainer_with_gradient_penalty(golden):
+    """GANTrainer(loss='w', gp=10): one critic + generator step runs on the flat buffers and moves both networks."""
+    from mpgan_b200 import presets, train
+    G = presets.mp_generator().cuda()
+    D = presets.mp_discriminator(loss="w").cuda()
+    G.load_state_dict(golden("mp_g_weights.pt"), strict=True)
+    tr = train.GANTrainer(G, D, loss="w", gp=10.0, lr_gen=1e-4, lr_disc=1e-4)
+    x, labels, _ = train.synthetic_jets(16, 30, "cuda", torch.Generator(device="cuda").manual_seed(3))
+    w0 = (tr.fpG.flat.clone(), tr.fpD.flat.clone())
+    ld, lg = tr.step(x, labels)
+    assert torch.isfinite(ld) and torch.isfinite(lg)
+    assert float((tr.fpD.flat - w0[1]).abs().max()) > 0 and float((tr.fpG.flat - w0[0]).abs().max()) > 0
+
+
+def test_knn_message_passing_golden(golden):
+    """MPLayer(fully_connected=False) (mpgan/model.py:319-381): neighbour selection + index-list edge kernel."""
+    from mpgan_b200 import MPLayer
+    done = 0
+    for name, c in golden("mplayer_variants2.pt").items():
+        if not name.startswith("knn"):
+            continue
+        sd = c["sd"]
+        fe = [sd[f"fe.net.{i}.weight"].shape[0] for i in range(3)]
+        fn = [sd["fn.net.0.weight"].shape[0], sd["fn.net.1.weight"].shape[0]]
+        layer = MPLayer(c["x"].shape[2], fe, fn, sd["fn.net.2.weight"].shape[0], **c["kw"]).cuda()
+        layer.load_state_dict(sd, strict=True)
+        x = c["x"].cuda().requires_grad_(True)
+        mask = None if c["mask"] is None else c["mask"].cuda()
+        out = layer(x, mask is not None, mask)
+        close(out, c["out"], 2e-4, name)
+        (out * c["w"].cuda()).sum().backward()
+        close(x.grad, c["dx"], 2e-3, name + " dx")
+        for k, g in c["grads"].items():
+            close(dict(layer.named_parameters())[k].grad, g, 2e-3, f"{name} {k}")
+        done += 1
+    assert done >= 8
+
+
+def test_knn_select_matches_torch_sort():
+    from mpgan_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(4, 37, 6, generator=g)
+    mask = (torch.rand(4, 37, 1, generator=g) > 0.3).float()
+    for nd, k, sl, m in ((6, 5, True, mask), (2, 7, False, mask), (6, 4, True, None)):
+        x2 = x if m is None else ((1 - 1e4) * m + 1e4) * x
+        d = torch.norm(x2[:, None, :, :nd] - x[:, :, None, :nd] + 1e-12, dim=3)
+        s0 = 0 if sl else 1
+        ref = torch.sort(d, dim=2, stable=True)[1][:, :, s0:k + s0]
+        idx = ops.knn_select(x.cuda(), None if m is None else m.cuda(), k, nd, sl).cpu().long()
+        # compare through the distances (equal-distance neighbours may swap)
+        close(torch.gather(d, 2, idx), torch.gather(d, 2, ref), 1e-5, "knn distances")
+
+
+@pytest.mark.parametrize("prec", [0, 1])
+def test_gapt_layernorm_golden(golden, prec):
+    from mpgan_b200 import ops, presets
+    ops.set_precision(prec)
+    ft, gt = (1e-4, 1e-3) if prec == 0 else (5e-3, 1e-1)
+    bad = []
+
+    def close(a, b, tol, what):   # precision 1 (TF32 projections): LayerNorm divides by a small per-row std, which
+        r2, rm = rel_l2(a, b), rel(a, b)   # amplifies the operand rounding -- stated in relative L2 + max-abs guard
+        ok = rm <= tol if prec == 0 else (r2 <= tol and rm <= 4e-1)
+        if not ok:
+            bad.append(f"{what}: rel L2 {r2:.3e}, max-abs {rm:.3e}")
+
+    for name, c in golden("gapt_layernorm.pt").items():
+        isab = name == "isab"
+        GG = presets.gapt_generator(use_isab=isab, layer_norm_gen=True, sab_layers_gen=2).cuda().train()
+        GD = presets.gapt_discriminator(use_isab=isab, layer_norm_disc=True, disc_dropout=0.0).cuda().train()
+        GG.load_state_dict(c["sdG"], strict=True)
+        GD.load_state_dict(c["sdD"], strict=True)
+        noise = c["noise"].cuda().requires_grad_(True)
+        labels = c["labels"].cuda()
+        fake = GG(noise, labels)
+        close(fake, c["fake"], ft, name + " fake")
+        dout = GD(fake, labels)
+        close(dout, c["dout"], ft, name + " dout")
+        ((dout - 1) ** 2).mean().backward()
+        close(noise.grad, c["dnoise"], gt, name + " dnoise")
+        for k, g in c["gradsG"].items():
+            close(dict(GG.named_parameters())[k].grad, g, gt, f"{name} G {k}")
+        for k, g in c["gradsD"].items():
+            close(dict(GD.named_parameters())[k].grad, g, gt, f"{name} D {k}")
+    assert not bad, "\n".join(bad)
+
+
+def test_layernorm_op_matches_torch():
+    from mpgan_b200 import ops
+    g = torch.Generator().manual_seed(8)
+    for rows, C in ((50, 64), (1000, 64), (7, 33)):
+        x = torch.randn(rows, C, generator=g).requires_grad_(True)
+        w = (1 + 0.3 * torch.randn(C, generator=g)).requires_grad_(True)
+        b = (0.2 * torch.randn(C, generator=g)).requires_grad_(True)
+        dy = torch.randn(rows, C, generator=g)
+        torch.nn.functional.layer_norm(x, (C,), w, b, 1e-5).backward(dy)
+        xc, wc, bc = (t.detach().cuda().requires_grad_(True) for t in (x, w, b))
+        y = ops.layer_norm(xc, wc, bc, 1e-5)
+        y.backward(dy.cuda())
+        close(y, torch.nn.functional.layer_norm(x, (C,), w, b, 1e-5), 1e-5, "ln y")
+        close(xc.grad, x.grad, 1e-4, "ln dx")
+        close(wc.grad, w.grad, 1e-4, "ln dw")
+        close(bc.grad, b.grad, 1e-4, "ln db")
+
+
+def test_linear_double_backward_matches_torch():
+    """grad-of-grad of one LinearNet layer (leaky-relu) against torch autograd on the same expression."""
+    from mpgan_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(40, 12, generator=g)
+    w = torch.randn(20, 12, generator=g) / 3
+    b = torch.randn(20, generator=g) * 0.1
+    v = torch.randn(40, 20, generator=g)
+    res = []
+    for dev in ("cpu", "cuda"):
+        xd, wd, bd = (t.to(dev).clone().requires_grad_(True) for t in (x, w, b))
+        if dev == "cpu":
+            y = torch.nn.functional.leaky_relu(torch.nn.functional.linear(xd, wd, bd), 0.2)
+        else:
+            y = ops.linear(xd, wd, bd, True, 0.2, 0.0)
+        (gx,) = torch.autograd.grad(y, xd, grad_outputs=v.to(dev), create_graph=True)
+        pen = (gx ** 2).sum()
+        pen.backward()
+        res.append((gx.detach().cpu(), wd.grad.cpu(), None if bd.grad is None else bd.grad.cpu()))
+    close(res[1][0], res[0][0], 1e-4, "dy/dx")
+    close(res[1][1], res[0][1], 1e-3, "d(pen)/dW")
+    assert res[0][2] is None or float(res[0][2].abs().max()) == 0   # the bias has no second-order term
+    assert res[1][2] is None or float(res[1][2].abs().max()) == 0
+
+
+def test_generation_driver_values(golden):
+    """train.gen_multi_batch with gen.py's post-processing against the oracle generator + the numpy restatement of
+    gen.py:126-141 on fixed noise: masked particles exactly zero, features within the generator's forward tolerance."""
+    from mpgan_b200 import ops, presets, train
+    ops.set_precision(0)
+    sd = golden("mp_g_weights.pt")
+    G = presets.mp_generator().cuda().eval()
+    G.load_state_dict(sd, strict=True)
+    n, B = 70, 32
+    g = torch.Generator().manual_seed(13)
+    cnt = torch.randint(1, 31, (n,), generator=g)
+    labels = (cnt.float() * torch.tensor(1.0 / 30)).unsqueeze(1)
+    noise = torch.randn(n, 30, 32, generator=g) * 0.2
+    out = train.gen_multi_batch(G, n, B, 30, labels=labels, noise=noise, jets="g")
+    assert out.shape == (n, 30, 3) and out.is_pinned()
+    ref = mo.generator(sd, noise, labels, mo.NetCfg(num_particles=30, final_activation="tanh")).numpy().copy()
+    for i in range(3):   # gen.py:126-132
+        if train.FEATURE_SHIFTS[i]:
+            ref[:, :, i] -= train.FEATURE_SHIFTS[i]
+        ref[:, :, i] /= train.FEATURE_NORMS[i]
+        ref[:, :, i] *= train.FEATURE_MAXES["g"][i]
+    keep = ref[:, :, -1] >= 0.5
+    ref[~keep] = 0                                  # :136-137
+    ref[:, :, 2][ref[:, :, 2] < 0] = 0              # :139
+    ref = ref[:, :, :3]
+    o = out.numpy()
+    assert np.array_equal(o[~keep], np.zeros_like(o[~keep])), "masked particles must be exactly zero"
+    assert (o[:, :, 2] >= 0).all()
+    assert float(np.abs(o - ref).max()) <= 1e-4 * float(np.abs(ref).max())
+    # raw (un-processed) output and rank sharding: the two shards of a 2-rank job tile the single-process result
+    full = train.gen_multi_batch(G, n, B, 30, labels=labels, noise=noise)
+    parts = [train.gen_multi_batch(G, n, B, 30, labels=labels, noise=noise, rank=r, world=2) for r in range(2)]
+    assert parts[0].shape[0] + parts[1].shape[0] == n
+    close(torch.cat(parts, 0), full, 1e-5, "sharded generation")
+
+
+def test_batch_order_large_batch():
+    from mpgan_b200 import ops
+    g = torch.Generator().manual_seed(17)
+    for B in (5, 300, 10000, 70000):
+        key = torch.randint(1, 151, (B,), generator=g).float() / 150
+        pos = ops.batch_order(key.unsqueeze(1).cuda()).cpu().long()
+        order = torch.argsort(key, descending=True, stable=True)
+        ref = torch.empty(B, dtype=torch.long)
+        ref[order] = torch.arange(B)
+        assert torch.equal(pos, ref), B

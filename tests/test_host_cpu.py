@@ -45,7 +45,7 @@ def test_binding_table_matches_header(libpath):
 
 def test_library_has_no_torch_dependency(libpath):
     out = subprocess.run(["ldd", libpath], capture_output=True, text=True).stdout
-    assert "torch" not in out and "c10" not in out, out
+    assert "libtorch" not in out and "libc10" not in out, out   # (bare "c10" also matches load addresses)
 
 
 _SASS = {}
@@ -159,13 +159,18 @@ def test_unsupported_options_fail_loudly():
     with pytest.raises(NotImplementedError):
         LinearNet([8], input_size=4, batch_norm=True)
     with pytest.raises(NotImplementedError):
-        MPLayer(3, [96, 160, 192], [256, 256], 32, fully_connected=False)
-    with pytest.raises(NotImplementedError):
         MPLayer(3, [96, 160, 192], [256, 256], 32, clabels=1)
     with pytest.raises(NotImplementedError):
         presets.mp_generator(mask_learn=True)
-    with pytest.raises(NotImplementedError):
-        presets.gapt_generator(layer_norm_gen=True)
+    with pytest.raises(ValueError):   # kNN feeds ONE distance column; the reference dies with a shape error here
+        MPLayer(3, [96, 160, 192], [256, 256], 32, fully_connected=False, pos_diffs=True, delta_coords=True, delta_r=True)
+    # supported since round 2: kNN message passing, GAPT LayerNorm (reference parameter names)
+    l = MPLayer(3, [96, 160, 192], [256, 256], 32, fully_connected=False, num_knn=5, pos_diffs=True, all_ef=False)
+    assert (l._ef_mode, l._nd, l.num_ef) == (1, 2, 1) and l.fe.net[0].weight.shape == (96, 7)
+    g = presets.gapt_generator(layer_norm_gen=True)
+    assert "sabs.0.mab.norm1.weight" in g.state_dict() and "sabs.3.mab.norm2.bias" in g.state_dict()
+    with pytest.raises(RuntimeError):   # and still no CPU path
+        l(torch.zeros(1, 4, 3))
 
 
 def test_pair_feature_modes():
@@ -186,11 +191,19 @@ def test_flops_model_matches_survey():
     assert abs(bench.step_flops(150) / 1e9 - 50.71) < 0.01
 
 
-def test_sort_by_count_host_path():
-    """train.sort_by_count on CPU tensors (torch path): descending particle count, ties in the caller's order."""
+def test_sort_by_count_has_no_host_path():
+    """train.sort_by_count orders the batch with the library's kernels for any batch size; CPU tensors raise (there is
+    no torch detour inside the product path)."""
     from mpgan_b200 import train
     labels = torch.tensor([[0.5], [1.0], [0.5], [0.1], [1.0]])
     data = torch.arange(5, dtype=torch.float32).view(5, 1, 1).expand(5, 3, 4).contiguous()
-    d, l = train.sort_by_count(data, labels)
-    assert l[:, 0].tolist() == [1.0, 1.0, 0.5, 0.5, pytest.approx(0.1)]
-    assert d[:, 0, 0].tolist() == [1.0, 4.0, 0.0, 2.0, 3.0]
+    with pytest.raises(RuntimeError):
+        train.sort_by_count(data, labels)
+
+
+def test_rank_shard_covers_all_samples():
+    from mpgan_b200 import train
+    for n, w in ((1000, 8), (1001, 8), (5, 8), (1_000_000, 8), (7, 1)):
+        spans = [train.rank_shard(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
