@@ -335,13 +335,19 @@ def measure(name, wl, args, env, with_baselines):
     # from here on every rank draws its own data, noise and dropout masks (an independent shard of the global batch)
     torch.manual_seed(4 + 1000 * rank)
     gen = torch.Generator(device=dev).manual_seed(4 + 1000 * rank)
-    data, labels, _ = train.synthetic_jets(B, N, dev, gen, all_real=all_real)
+    # weak scaling = fixed per-GPU work: every rank's shard has the same particle-count multiset (drawn from one seed),
+    # its own feature values, noise and dropout masks
+    data, labels, _ = train.synthetic_jets(B, N, dev, gen, all_real=all_real,
+                                           count_generator=torch.Generator(device=dev).manual_seed(4))
 
     eager_step = None
     tr = gg = None
+    tr_collective = None
     if kind == "train":
         tr = train.GANTrainer(G, D, lr_gen=1.5e-4 if gapt else 1e-5, lr_disc=0.5e-4 if gapt else 3e-5, num_particles=N,
-                              latent_node_size=latent)
+                              latent_node_size=latent, fused_allreduce=args.fused)
+
+        tr_collective = tr.collective if world > 1 else None
 
         def eager_step(d, l):
             return tr.step(d, l)
@@ -513,13 +519,15 @@ def measure(name, wl, args, env, with_baselines):
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if gapt else "bf16", "data": "synthetic",
             "config": {"workload": name, "particles": N, "batch_per_gpu": B, "global_batch": B * world,
-                       "particles_per_jet": "all N real" if all_real else "n ~ U{1..N} (padded rows masked)",
+                       "particles_per_jet": "all N real" if all_real else "n ~ U{1..N} (padded rows masked); every rank's "
+                                            "shard has the same particle-count multiset (fixed per-GPU work)",
                        "batch_order": "jets ordered by particle count inside each batch (GANTrainer.sort_by_count / "
                                       "train.generate); fully padded (tile, sender) steps are dropped by the kernels",
                        "l2": "flushed between timed steps (256 MiB write)",
                        "precision": ("TF32 projections, fp32 attention core" if gapt else
                                      "bf16 tcgen05 edge network, TF32 node GEMMs, fp32 accumulate"), "parallelism": f"dp{world}",
-                       "cuda_graph": bool(args.graph)},
+                       "cuda_graph": bool(args.graph),
+                       **({"collective": tr_collective} if tr_collective else {})},
             "e2e": {"value": e2e_val, "unit": "jets/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "roofline": roof,
@@ -614,9 +622,10 @@ def teardown(dist, torch):
 
 
 def dp_check(args, env):
-    """1 rank on the global batch vs `world` ranks on its shards, on real NCCL: the averaged flat gradients of D and
-    G and the weights after the RMSprop step must agree (setup_training.py:1418-1421 DataParallel semantics).  Runs
-    eagerly and through the captured graph's own all-reduce path (GANTrainer.train_D / train_G)."""
+    """1 rank on the global batch vs `world` ranks on its shards, on real NVLink / NCCL: after one train_D + train_G
+    the RMSprop accumulators (0.01 * g_avg^2 after the first step, i.e. the averaged gradients the optimizers consumed)
+    and the weights must agree (setup_training.py:1418-1421 DataParallel semantics).  Both collectives are checked: the
+    fused peer-memory all-reduce + RMSprop kernel and ncclAllReduce + the RMSprop kernel."""
     import torch
     import torch.distributed as dist
     from mpgan_b200 import ops, presets, train
@@ -624,6 +633,7 @@ def dp_check(args, env):
     dev, rank, world = env.dev, env.rank, env.world
     N, Bs = 30, 64
     res = {"check": "dp_gradient_equality", "n_gpus": world, "shard_batch": Bs, "global_batch": Bs * world}
+    worst = {0: 0.0, 1: 0.0}
     for prec in (0, 1):
         ops.set_precision(prec)
         g = torch.Generator(device=dev).manual_seed(77)
@@ -632,32 +642,52 @@ def dp_check(args, env):
         ng = train.get_gen_noise(Bs * world, N, 32, 0.2, dev, g)
         sl = slice(rank * Bs, (rank + 1) * Bs)
         out = {}
-        for mode in ("sharded", "single"):
+        for mode in ("single", "fused", "nccl"):
             torch.manual_seed(4)
             G = presets.mp_generator(num_hits=N).to(dev)
             D = presets.mp_discriminator(num_hits=N, disc_dropout=0.0).to(dev)
             sdG, sdD = _golden_weights(dev)
             G.load_state_dict(sdG)
             D.load_state_dict(sdD)
-            tr = train.GANTrainer(G, D, num_particles=N, world_override=1 if mode == "single" else None)
-            if mode == "sharded":
-                ld = tr.train_D(data[sl], labels[sl], noise=nd[sl])
-                gD = tr.fpD.grad.clone() / world
-                lg = tr.train_G(labels[sl], noise=ng[sl])
-                gG = tr.fpG.grad.clone() / world
+            tr = train.GANTrainer(G, D, num_particles=N, lr_gen=1e-4, lr_disc=3e-4, world_override=1 if mode == "single" else None,
+                                  fused_allreduce=(mode == "fused"))
+            w0 = (tr.fpD.flat.clone(), tr.fpG.flat.clone())
+            if mode == "single":
+                tr.train_D(data, labels, noise=nd)
+                tr.train_G(labels, noise=ng)
             else:
-                ld = tr.train_D(data, labels, noise=nd)
-                gD = tr.fpD.grad.clone()
-                lg = tr.train_G(labels, noise=ng)
-                gG = tr.fpG.grad.clone()
-            out[mode] = (gD, gG, tr.fpD.flat.clone(), tr.fpG.flat.clone())
-        rel = lambda a, b: float((a - b).norm() / b.norm().clamp_min(1e-20))
-        errs = {k: rel(out["sharded"][i], out["single"][i]) for i, k in enumerate(("gradD", "gradG", "weightsD", "weightsG"))}
-        t = torch.tensor([max(errs["gradD"], errs["gradG"])], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX) if world > 1 else None
-        res[f"precision{prec}"] = {**errs, "max_over_ranks": float(t)}
+                tr.train_D(data[sl], labels[sl], noise=nd[sl])
+                tr.train_G(labels[sl], noise=ng[sl])
+            torch.cuda.synchronize()
+            out[mode] = (tr.optD.square_avg.clone(), tr.optG.square_avg.clone(), tr.fpD.flat.clone(), tr.fpG.flat.clone(), w0,
+                         tr.collective)
+        rel = lambda a, b: float((a - b).norm() / b.norm().clamp_min(1e-30))
+        pr = {}
+        for mode in ("fused", "nccl"):
+            o, r = out[mode], out["single"]
+            e = {"sqD": rel(o[0], r[0]), "sqG": rel(o[1], r[1]),
+                 # weights: difference between the modes relative to the distance the step moved them (RMSprop's first
+                 # update is ~10 lr sign(g): elements with g ~ 0 may step either way)
+                 "weightsD": float((o[2] - r[2]).norm() / (r[2] - r[4][0]).norm()),
+                 "weightsG": float((o[3] - r[3]).norm() / (r[3] - r[4][1]).norm()), "collective": o[5]}
+            t = torch.tensor([max(e["sqD"], e["sqG"])], device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e["sq_max_over_ranks"] = float(t)
+            worst[prec] = max(worst[prec], float(t))
+            # every rank must hold the same weights afterwards
+            ref = o[2].clone()
+            if world > 1:
+                dist.broadcast(ref, 0)
+            same = torch.tensor([float(torch.equal(ref, o[2]))], device=dev)
+            if world > 1:
+                dist.all_reduce(same, op=dist.ReduceOp.MIN)
+            e["weights_identical_on_all_ranks"] = bool(same.item())
+            pr[mode] = e
+        res[f"precision{prec}"] = pr
     ops.set_precision(1)
-    res["ok"] = res["precision0"]["max_over_ranks"] < 1e-4 and res["precision1"]["max_over_ranks"] < 3e-2
+    res["ok"] = bool(worst[0] < 2e-4 and worst[1] < 6e-2 and all(
+        res[f"precision{p}"][m]["weights_identical_on_all_ranks"] for p in (0, 1) for m in ("fused", "nccl")))
     return res
 
 
@@ -675,6 +705,8 @@ def main():
     ap.add_argument("--all-real", action="store_true",
                     help="every jet has N real particles (no padding: the unmasked worst case of SURVEY 8d); default n ~ U{1..N}")
     ap.add_argument("--preload-s", type=float, default=1.0, help="seconds of untimed load before each timed window")
+    ap.add_argument("--no-fused-allreduce", dest="fused", action="store_false",
+                    help="multi-GPU: ncclAllReduce + RMSprop kernel instead of the fused peer-memory kernel")
     ap.add_argument("--check", action="store_true", help="data-parallel gradient-equality check (use under torchrun)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -226,6 +226,19 @@ int mpg_layernorm_fwd(const float* x, const float* w, const float* b, float* y, 
 int mpg_layernorm_bwd(const float* dy, const float* x, const float* w, const float* mean, const float* rstd, float* dx,
                       float* dw, float* db, size_t rows, int C, void* stream);
 
+/* ---- data-parallel update: one-shot gradient all-reduce fused with RMSprop over NVLink peer memory ------------------
+ * (replaces DataParallel's gradient reduction, setup_training.py:1418-1421, + torch.optim.RMSprop, :1511-1513.)
+ * peer_grads[r] / peer_flags[r] (HOST arrays of `world` device pointers) are rank r's flat gradient buffer and flag
+ * block as mapped on THIS GPU (symmetric / peer memory, e.g. torch.distributed._symmetric_memory); the flag blocks hold
+ * mpg_peer_flag_words(ctas, world) zero-initialised 32-bit words.  Every rank calls it once per step on its own
+ * stream with the same n / ctas: the kernel waits (system-scope flags, bounded spin) until every peer's gradients
+ * are complete, sums them in rank order, applies p -= lr * g / (sqrt(sq) + eps) with g = sum / world and
+ * sq = alpha * sq + (1 - alpha) * g^2, and returns only after every peer has finished reading this rank's
+ * gradients.  ctas <= the SM count (all CTAs must be co-resident).  Graph-capturable (the epoch lives on the device). */
+size_t mpg_peer_flag_words(int ctas, int world);
+int mpg_allreduce_rmsprop(float* p, float* sq, const void* const* peer_grads, void* const* peer_flags, size_t n, int rank,
+                          int world, int ctas, float lr, float alpha, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,6 +9,7 @@
 #include "gapt.cuh"
 #include "gemm.cuh"
 #include "misc.cuh"
+#include "peer.cuh"
 
 namespace mpg {
 static thread_local char g_err[512] = "";
@@ -670,6 +671,22 @@ int mpg_layernorm_bwd(const float* dy, const float* x, const float* w, const flo
   MPG_CHECK(C > 0 && C <= 4096, "layernorm: C out of range");
   MPG_CHECK((dw == nullptr) == (db == nullptr), "layernorm_bwd: pass both parameter gradients or none");
   return launch_layernorm_bwd(dy, x, w, mean, rstd, dx, dw, db, rows, C, (cudaStream_t)stream);
+}
+
+size_t mpg_peer_flag_words(int ctas, int world) { return peer_flag_words(ctas, world); }
+
+int mpg_allreduce_rmsprop(float* p, float* sq, const void* const* peer_grads, void* const* peer_flags, size_t n, int rank,
+                          int world, int ctas, float lr, float alpha, float eps, void* stream) {
+  MPG_CHECK(peer_grads != nullptr && peer_flags != nullptr, "allreduce_rmsprop: null pointer table");
+  MPG_CHECK(world >= 2 && world <= MPG_PEER_MAX, "allreduce_rmsprop: world size must be in [2, %d]", MPG_PEER_MAX);
+  PeerArgs a;
+  memset(&a, 0, sizeof(a));
+  a.p = p; a.sq = sq; a.n = n; a.rank = rank; a.world = world; a.lr = lr; a.alpha = alpha; a.eps = eps;
+  for (int r = 0; r < world; ++r) {
+    a.grads[r] = reinterpret_cast<const float*>(peer_grads[r]);
+    a.flags[r] = reinterpret_cast<unsigned*>(peer_flags[r]);
+  }
+  return launch_allreduce_rmsprop(a, ctas, (cudaStream_t)stream);
 }
 
 }  // extern "C"

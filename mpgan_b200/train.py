@@ -23,15 +23,16 @@ from . import ops
 
 
 class FlatParams:
-    """Re-homes a module's trainable parameters and their grads into two flat fp32 buffers."""
+    """Re-homes a module's trainable parameters and their grads into two flat fp32 buffers.  ``grad_alloc`` lets the
+    gradient buffer live in symmetric (peer-mapped) memory for the fused all-reduce + RMSprop kernel."""
 
-    def __init__(self, module: torch.nn.Module):
+    def __init__(self, module: torch.nn.Module, grad_alloc=None):
         self.params = [p for p in module.parameters() if p.requires_grad]
         self.names = [n for n, p in module.named_parameters() if p.requires_grad]
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device
         self.flat = torch.zeros(n, device=dev, dtype=torch.float32)
-        self.grad = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.grad = torch.zeros(n, device=dev, dtype=torch.float32) if grad_alloc is None else grad_alloc(n, dev).zero_()
         off = 0
         for p in self.params:
             k = p.numel()
@@ -62,6 +63,44 @@ class FusedRMSprop:
 
     def step(self, grad_scale: float = 1.0):
         ops.rmsprop_(self.fp.flat, self.fp.grad, self.square_avg, self.lr, self.alpha, self.eps, grad_scale)
+
+
+class PeerReducer:
+    """Peer-memory plumbing of ``mpg_allreduce_rmsprop``: the flat gradient buffer and a flag block of one network
+    allocated in symmetric memory (torch.distributed._symmetric_memory), rendezvoused over the process group, and the
+    pointer tables the kernel takes.  Construction is collective; it raises if the GPUs cannot map each other's
+    memory (the trainer then keeps ncclAllReduce + the RMSprop kernel)."""
+
+    CTAS = 64    # measured on 2 B200s (profiles/r2_bench_peer_2gpu.txt): 21 us per 1.4 MB update vs 32 us for NCCL + RMSprop
+
+    def __init__(self, module, group):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        grp = group if group is not None else dist.group.WORLD
+        handles = []
+
+        def alloc(n, dev):
+            g = symm_mem.empty(n, dtype=torch.float32, device=dev)
+            handles.append(symm_mem.rendezvous(g, grp))
+            return g
+
+        self.fp = FlatParams(module, grad_alloc=alloc)
+        dev = self.fp.flat.device
+        words = int(_lib.lib().mpg_peer_flag_words(self.CTAS, self.world))
+        self.flags = symm_mem.empty(words, dtype=torch.int32, device=dev).zero_()
+        hf = symm_mem.rendezvous(self.flags, grp)
+        torch.cuda.synchronize()
+        dist.barrier(group)   # every rank's flags are zero before anyone signals
+        self._handles = (handles[0], hf)
+        self.grad_ptrs = (C.c_void_p * self.world)(*[int(p) for p in handles[0].buffer_ptrs])
+        self.flag_ptrs = (C.c_void_p * self.world)(*[int(p) for p in hf.buffer_ptrs])
+
+    def step(self, opt):
+        ops.allreduce_rmsprop_(self.fp.flat, opt.square_avg, self.grad_ptrs, self.flag_ptrs, self.rank, self.world,
+                               self.CTAS, opt.lr, opt.alpha, opt.eps)
 
 
 def get_gen_noise(batch_size, num_particles, latent_node_size, sd=0.2, device="cuda", generator=None):
@@ -113,7 +152,8 @@ def g_loss(loss, fake_out):
 
 class GANTrainer:
     def __init__(self, G, D, lr_gen=1e-5, lr_disc=3e-5, num_particles=30, latent_node_size=32, sd=0.2,
-                 process_group=None, batch_real_fake=True, sort_by_count=True, world_override=None, loss="ls", gp=0.0):
+                 process_group=None, batch_real_fake=True, sort_by_count=True, world_override=None, loss="ls", gp=0.0,
+                 fused_allreduce=True):
         self.G, self.D = G, D
         # loss in {"ls", "w", "hinge", "og"} and gp = the gradient-penalty weight (train.py --loss / --gp); the losses
         # other than "ls" are a few torch reductions over the [B, 1] discriminator outputs
@@ -130,7 +170,25 @@ class GANTrainer:
         # padded in ALL of the tile's jets -- which the kernels drop -- go from ~5-30 % to ~50 % of the steps
         # for n ~ U{1..N}.
         self.sort_by_count = sort_by_count
-        self.fpG, self.fpD = FlatParams(G), FlatParams(D)
+        world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        if world_override is not None:
+            world = int(world_override)
+        # Data parallel: the gradient all-reduce and the RMSprop update of each network are ONE kernel over NVLink
+        # peer memory (PeerReducer / mpg_allreduce_rmsprop) when the GPUs can map each other's memory, else
+        # ncclAllReduce followed by the RMSprop kernel.  self.collective says which.
+        self.peerG = self.peerD = None
+        self.collective = "none"
+        if world > 1 and fused_allreduce and next(G.parameters()).is_cuda:
+            try:
+                self.peerG, self.peerD = PeerReducer(G, process_group), PeerReducer(D, process_group)
+                self.collective = "fused peer-memory all-reduce + RMSprop (mpg_allreduce_rmsprop)"
+            except Exception as e:   # no peer access / symmetric memory unavailable
+                self.peerG = self.peerD = None
+                self.collective = f"ncclAllReduce + RMSprop kernel (peer memory unavailable: {type(e).__name__})"
+        elif world > 1:
+            self.collective = "ncclAllReduce + RMSprop kernel"
+        self.fpG = self.peerG.fp if self.peerG else FlatParams(G)
+        self.fpD = self.peerD.fp if self.peerD else FlatParams(D)
         # inside train_D / train_G the kernels accumulate weight gradients straight into the flat .grad buffers
         # (ops.direct_grad, scoped to the trainer's own backward passes)
         self.optG, self.optD = FusedRMSprop(self.fpG, lr_gen), FusedRMSprop(self.fpD, lr_disc)
@@ -159,6 +217,12 @@ class GANTrainer:
             return 1.0
         dist.all_reduce(fp.grad, op=dist.ReduceOp.SUM, group=self.pg)
         return 1.0 / self.world
+
+    def _update(self, fp, opt, peer):
+        if peer is not None and self.world > 1:
+            peer.step(opt)            # all-reduce + RMSprop in one kernel over peer memory
+        else:
+            opt.step(self._allreduce(fp))
 
     def named_grads(self, which):
         return (self.fpG if which == "G" else self.fpD).named_grads()
@@ -203,10 +267,10 @@ class GANTrainer:
                 self._comm_stream = torch.cuda.Stream(device=data.device)
             self._comm_stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self._comm_stream):
-                self.optD.step(self._allreduce(self.fpD))
+                self._update(self.fpD, self.optD, self.peerD)
             self._comm_pending = True
         else:
-            self.optD.step(self._allreduce(self.fpD))
+            self._update(self.fpD, self.optD, self.peerD)
         return loss.detach()
 
     # -- train.py:479-523 ------------------------------------------------------------------------
@@ -225,7 +289,7 @@ class GANTrainer:
         finally:
             for p in self.fpD.params:
                 p.requires_grad_(True)
-        self.optG.step(self._allreduce(self.fpG))
+        self._update(self.fpG, self.optG, self.peerG)
         return loss.detach()
 
     def step(self, data, labels, noise_d=None, noise_g=None):
@@ -373,13 +437,14 @@ class GraphedGenerator:
         return self._out
 
 
-def synthetic_jets(B, N, device="cuda", generator=None, all_real=False):
+def synthetic_jets(B, N, device="cuda", generator=None, all_real=False, count_generator=None):
     """SURVEY 8(d) synthetic batch: features U(-.5,.5) zeroed on padded rows, 4th channel mask-0.5;
-    labels n * fp32(1/N)."""
+    labels n * fp32(1/N).  ``count_generator``: separate RNG for the particle counts (a multi-GPU weak-scaling bench
+    seeds it identically on every rank so that each GPU's shard carries the same amount of work)."""
     if all_real:
         n = torch.full((B,), N, device=device)
     else:
-        n = torch.randint(1, N + 1, (B,), device=device, generator=generator)
+        n = torch.randint(1, N + 1, (B,), device=device, generator=count_generator or generator)
     real = (torch.arange(N, device=device)[None, :] < n[:, None]).float().unsqueeze(2)
     feats = (torch.rand(B, N, 3, device=device, generator=generator) - 0.5) * real
     x = torch.cat((feats, real - 0.5), dim=2)
