@@ -572,13 +572,13 @@ def run_ours(args):
         line = dp_check(args, env)
     else:
         head = args.workload or HEADLINE
-        line = measure(head, WORKLOADS[head], args, env, with_baselines="full")
+        line = measure(head, WORKLOADS[head], args, env, with_baselines="full" if args.baselines else None)
         if args.suite and args.workload is None:
             extra = {}
             for name in SUITE:
                 try:
                     r = measure(name, WORKLOADS[name], args, env,
-                                with_baselines="gpu" if name in ("train_n150_b256", "gen_n30_b1024", "gen_n150_b1024",
+                                with_baselines="gpu" if args.baselines and name in ("train_n150_b256", "gen_n30_b1024", "gen_n150_b1024",
                                                                  "train_gapt_n30_b512", "train_gapt_isab_n30_b512") else None)
                 except Exception as e:  # a failing secondary workload must not take the headline down with it
                     r = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
@@ -707,6 +707,8 @@ def main():
     ap.add_argument("--preload-s", type=float, default=1.0, help="seconds of untimed load before each timed window")
     ap.add_argument("--no-fused-allreduce", dest="fused", action="store_false",
                     help="multi-GPU: ncclAllReduce + RMSprop kernel instead of the fused peer-memory kernel")
+    ap.add_argument("--no-baselines", dest="baselines", action="store_false",
+                    help="skip the CPU / GPU-eager reference legs (profiling runs)")
     ap.add_argument("--check", action="store_true", help="data-parallel gradient-equality check (use under torchrun)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -8,6 +8,7 @@
 #include "fn_tc.cuh"
 #include "gapt.cuh"
 #include "gemm.cuh"
+#include "mab.cuh"
 #include "misc.cuh"
 #include "peer.cuh"
 
@@ -671,6 +672,62 @@ int mpg_layernorm_bwd(const float* dy, const float* x, const float* w, const flo
   MPG_CHECK(C > 0 && C <= 4096, "layernorm: C out of range");
   MPG_CHECK((dw == nullptr) == (db == nullptr), "layernorm_bwd: pass both parameter gradients or none");
   return launch_layernorm_bwd(dy, x, w, mean, rstd, dx, dw, db, rows, C, (cudaStream_t)stream);
+}
+
+int mpg_mab_supported(int E, int heads, int Nq, int Nk) { return mab_supported(E, heads, Nq, Nk) ? 1 : 0; }
+size_t mpg_mab_workspace_bytes(int B) { return mab_workspace_bytes(B); }
+
+static int mab_args(MabArgs& a, const float* x, int ldx, const float* y, int ldy, const float* key_mask, const float* w_in,
+                    const float* b_in, const float* w_out, const float* b_out, const float* w_ff, const float* b_ff, int B,
+                    int Nq, int Nk, int E, int heads, float alpha, float p_res, float p_ff, uint64_t seed,
+                    const uint64_t* seed_dev, float* q, float* kv, float* o, float* h, float* f, float* out) {
+  MPG_CHECK(mab_supported(E, heads, Nq, Nk), "mab: unsupported shape E=%d heads=%d Nq=%d Nk=%d", E, heads, Nq, Nk);
+  MPG_CHECK(p_res >= 0.f && p_res < 1.f && p_ff >= 0.f && p_ff < 1.f, "mab: dropout p must be in [0,1)");
+  MPG_CHECK(x && y && w_in && b_in && w_out && b_out && w_ff && b_ff && q && kv && o && h && f, "mab: null operand");
+  memset(&a, 0, sizeof(a));
+  a.x = x; a.ldx = ldx; a.y = y; a.ldy = ldy; a.key_mask = key_mask;
+  a.w_in = w_in; a.b_in = b_in; a.w_out = w_out; a.b_out = b_out; a.w_ff = w_ff; a.b_ff = b_ff;
+  a.B = B; a.Nq = Nq; a.Nk = Nk; a.alpha = alpha;
+  a.drop_res = make_drop(p_res, seed, seed_dev);
+  a.drop_ff = make_drop(p_ff, seed, seed_dev);
+  a.q = q; a.kv = kv; a.o = o; a.h = h; a.f = f; a.out = out;
+  return 0;
+}
+
+int mpg_mab_fwd(const float* x, int ldx, const float* y, int ldy, const float* key_mask, const float* w_in,
+                const float* b_in, const float* w_out, const float* b_out, const float* w_ff, const float* b_ff, int B,
+                int Nq, int Nk, int E, int heads, float alpha, float p_res, float p_ff, uint64_t seed,
+                const uint64_t* seed_dev, void* workspace, size_t workspace_bytes, float* q, float* kv, float* o, float* h,
+                float* f, float* out, void* stream) {
+  MabArgs a;
+  if (mab_args(a, x, ldx, y, ldy, key_mask, w_in, b_in, w_out, b_out, w_ff, b_ff, B, Nq, Nk, E, heads, alpha, p_res, p_ff,
+               seed, seed_dev, q, kv, o, h, f, out))
+    return 1;
+  MPG_CHECK(out != nullptr && workspace != nullptr && workspace_bytes >= mab_workspace_bytes(B), "mab_fwd: workspace too small");
+  return launch_mab_fwd(a, workspace, (cudaStream_t)stream);
+}
+
+int mpg_mab_bwd(const float* x, int ldx, const float* y, int ldy, const float* key_mask, const float* w_in,
+                const float* b_in, const float* w_out, const float* b_out, const float* w_ff, const float* b_ff, int B,
+                int Nq, int Nk, int E, int heads, float alpha, float p_res, float p_ff, uint64_t seed,
+                const uint64_t* seed_dev, void* workspace, size_t workspace_bytes, const float* q, const float* kv,
+                const float* o, const float* h, const float* f, const float* dout, float* dx, float* dy, float* dw_in,
+                float* db_in, float* dw_out, float* db_out, float* dw_ff, float* db_ff, void* stream) {
+  MabArgs a;
+  if (mab_args(a, x, ldx, y, ldy, key_mask, w_in, b_in, w_out, b_out, w_ff, b_ff, B, Nq, Nk, E, heads, alpha, p_res, p_ff,
+               seed, seed_dev, const_cast<float*>(q), const_cast<float*>(kv), const_cast<float*>(o), const_cast<float*>(h),
+               const_cast<float*>(f), nullptr))
+    return 1;
+  MPG_CHECK(workspace != nullptr && workspace_bytes >= mab_workspace_bytes(B), "mab_bwd: workspace too small");
+  const bool self = x == y && ldx == ldy && Nq == Nk;
+  MPG_CHECK(dout && dx && (self || dy), "mab_bwd: null gradient pointer");
+  const bool none = !dw_in && !db_in && !dw_out && !db_out && !dw_ff && !db_ff;
+  MPG_CHECK(none || (dw_in && db_in && dw_out && db_out && dw_ff && db_ff), "mab_bwd: pass all six parameter gradients or none");
+  MabGrads g;
+  memset(&g, 0, sizeof(g));
+  g.dout = dout; g.dx = dx; g.dy = dy;
+  g.dw_in = dw_in; g.db_in = db_in; g.dw_out = dw_out; g.db_out = db_out; g.dw_ff = dw_ff; g.db_ff = db_ff;
+  return launch_mab_bwd(a, g, workspace, (cudaStream_t)stream);
 }
 
 size_t mpg_peer_flag_words(int ctas, int world) { return peer_flag_words(ctas, world); }

@@ -19,6 +19,8 @@ from .model import LinearNet
 
 
 class MAB(nn.Module):
+    fused = True    # class-level switch (tests compare the fused kernel with the per-op path)
+
     def __init__(self, embed_dim: int, num_heads: int, ff_layers: list = [], layer_norm: bool = False,
                  dropout_p: float = 0.0, final_linear: bool = True, linear_args={}):
         super().__init__()
@@ -42,6 +44,14 @@ class MAB(nn.Module):
         E = self.embed_dim
         att = self.attention
         w, b = att.in_proj_weight, att.in_proj_bias
+        if self.fused and not self.layer_norm and len(self.ff.net) == 1 and not self.ff.final_linear and x.dim() == 3 \
+                and ops.mab_supported(E, self.num_heads, x.shape[1], y.shape[1]):
+            # the whole block as ONE kernel per direction (ops.MabFn)
+            wf, bf = self.ff.layer_params(0)
+            tr = self.training
+            return ops.mab(x, None if x is y else y, y_mask, w, b, att.out_proj.weight, att.out_proj.bias, wf, bf,
+                           self.num_heads, self.ff.leaky_relu_alpha, self.dropout_p if tr else 0.0,
+                           self.ff.dropout_p if tr else 0.0)
         if x is y:
             qkv = ops.linear(x, w, b, False, 0.0, 0.0)
             q, k, v = qkv[..., :E], qkv[..., E:2 * E], qkv[..., 2 * E:]

@@ -1251,3 +1251,80 @@ def gen_postprocess(jets, out, shift, norm, maxv, use_mask: bool = True):
     _lib.check(L.mpg_gen_postprocess(_lib.ptr(j3), ldj, out.data_ptr(), nfeat, rows, nfeat, arr(shift), arr(norm),
                                      arr(maxv), int(bool(use_mask)), _lib.stream()), "mpg_gen_postprocess")
     return out
+
+
+# --------------------------------------------------------------------------------------------------
+# fused GAPT attention block
+# --------------------------------------------------------------------------------------------------
+def mab_supported(E, heads, Nq, Nk) -> bool:
+    return bool(_lib.lib().mpg_mab_supported(int(E), int(heads), int(Nq), int(Nk)))
+
+
+class MabFn(torch.autograd.Function):
+    """One MAB (gapt/model.py:124-139 without LayerNorm) as one kernel per direction; see mpg_mab_fwd."""
+
+    @staticmethod
+    def forward(ctx, x, y, key_mask, w_in, b_in, w_out, b_out, w_ff, b_ff, heads, alpha, p_res, p_ff):
+        L = _lib.lib()
+        self_attn = y is None
+        x3, ldx = _rows(x)
+        y3, ldy = (x3, ldx) if self_attn else _rows(y)
+        B, Nq, E = x3.shape
+        Nk = y3.shape[1]
+        dev = x.device
+        km = None if key_mask is None else key_mask.reshape(B, Nk).contiguous().float()
+        ws_ = [t.contiguous() for t in (w_in, b_in, w_out, b_out, w_ff, b_ff)]
+        ws_bytes = L.mpg_mab_workspace_bytes(B)
+        ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+        q = torch.empty(B, Nq, E, device=dev, dtype=torch.float32)
+        kv = torch.empty(B, Nk, 2 * E, device=dev, dtype=torch.float32)
+        o, h, f, out = (torch.empty(B, Nq, E, device=dev, dtype=torch.float32) for _ in range(4))
+        seed = next_seed() if (p_res > 0 or p_ff > 0) else 0
+        _lib.check(L.mpg_mab_fwd(_lib.ptr(x3), ldx, _lib.ptr(y3), ldy, _lib.ptr(km), *[_lib.ptr(t) for t in ws_], B, Nq, Nk,
+                                 E, int(heads), float(alpha), float(p_res), float(p_ff), seed, _seed_ptr(), ws.data_ptr(),
+                                 ws_bytes, _lib.ptr(q), _lib.ptr(kv), _lib.ptr(o), _lib.ptr(h), _lib.ptr(f), _lib.ptr(out),
+                                 _lib.stream()), "mpg_mab_fwd")
+        ctx.save_for_backward(x3, y3 if not self_attn else None, km, q, kv, o, h, f, *ws_)
+        ctx.params = (w_in, b_in, w_out, b_out, w_ff, b_ff)
+        ctx.cfg = (ldx, ldy, B, Nq, Nk, E, int(heads), float(alpha), float(p_res), float(p_ff), seed, _seed_ptr(), self_attn)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        L = _lib.lib()
+        x3, y3, km, q, kv, o, h, f, *ws_ = ctx.saved_tensors
+        ldx, ldy, B, Nq, Nk, E, heads, alpha, p_res, p_ff, seed, sptr, self_attn = ctx.cfg
+        if self_attn:
+            y3 = x3
+        dev = dout.device
+        dout = dout.contiguous()
+        ws_bytes = L.mpg_mab_workspace_bytes(B)
+        ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+        dx = torch.empty(B, Nq, E, device=dev, dtype=torch.float32)
+        dy = None if self_attn else torch.empty(B, Nk, E, device=dev, dtype=torch.float32)
+        want_w = _want_wgrad(ctx, 3, 9)
+        sinks = [_grad_sink(p) for p in ctx.params] if (want_w and all(ctx.needs_input_grad[3:9])) else [None] * 6
+        direct = all(g is not None for g in sinks)
+        if direct:
+            grads = sinks
+        elif want_w:
+            flat = torch.zeros(sum(t.numel() for t in ws_), device=dev, dtype=torch.float32)
+            grads, off = [], 0
+            for t in ws_:
+                grads.append(flat[off:off + t.numel()].view_as(t))
+                off += t.numel()
+        else:
+            grads = [None] * 6
+        _lib.check(L.mpg_mab_bwd(_lib.ptr(x3), ldx, _lib.ptr(y3), ldy, _lib.ptr(km), *[_lib.ptr(t) for t in ws_], B, Nq, Nk,
+                                 E, heads, alpha, p_res, p_ff, seed, sptr, ws.data_ptr(), ws_bytes, _lib.ptr(q), _lib.ptr(kv),
+                                 _lib.ptr(o), _lib.ptr(h), _lib.ptr(f), _lib.ptr(dout), _lib.ptr(dx), _lib.ptr(dy),
+                                 *[_lib.ptr(g) for g in grads], _lib.stream()), "mpg_mab_bwd")
+        if direct:
+            grads = [None] * 6
+        return (dx, dy, None, *grads, None, None, None, None)
+
+
+def mab(x, y, key_mask, w_in, b_in, w_out, b_out, w_ff, b_ff, heads, alpha, p_res, p_ff):
+    """``y`` None = self attention (keys / values from ``x``)."""
+    return MabFn.apply(x, y, key_mask, w_in, b_in, w_out, b_out, w_ff, b_ff, heads, alpha, p_res, p_ff)

@@ -242,3 +242,71 @@ def test_batch_order_large_batch():
         ref = torch.empty(B, dtype=torch.long)
         ref[order] = torch.arange(B)
         assert torch.equal(pos, ref), B
+
+
+@pytest.mark.parametrize("Nq,Nk,masked", [(30, 30, True), (10, 30, True), (30, 10, False), (1, 30, True), (17, 17, False)])
+def test_fused_mab_matches_per_op_path(Nq, Nk, masked):
+    """ops.MabFn (one kernel per direction) against the per-op path (projection GEMMs + attention core + residual
+    kernels, itself pinned to the reference by the GAPT goldens): forward, input and all parameter gradients."""
+    from mpgan_b200 import gapt, ops
+    ops.set_precision(0)
+    torch.manual_seed(100 + Nq + Nk)
+    lin = dict(leaky_relu_alpha=0.2, dropout_p=0.0, batch_norm=False, spectral_norm=False)
+    m = gapt.MAB(64, 4, ff_layers=[], final_linear=False, dropout_p=0.0, linear_args=lin).cuda().train()
+    B = 9
+    x0 = torch.randn(B, Nq, 64, device="cuda") * 0.5
+    y0 = x0 if Nq == Nk else torch.randn(B, Nk, 64, device="cuda") * 0.5
+    n = torch.randint(1, Nk + 1, (B,), device="cuda")
+    mask = (torch.arange(Nk, device="cuda")[None, :] < n[:, None]).float().unsqueeze(2) if masked else None
+    w = torch.randn(B, Nq, 64, device="cuda")
+    res = []
+    try:
+        for fused in (False, True):
+            gapt.MAB.fused = fused
+            m.zero_grad()
+            x = x0.clone().requires_grad_(True)
+            y = x if Nq == Nk else y0.clone().requires_grad_(True)
+            out = m(x, y, mask)
+            (out * w).sum().backward()
+            res.append([out.detach(), x.grad, None if y is x else y.grad] + [p.grad.clone() for p in m.parameters()])
+    finally:
+        gapt.MAB.fused = True
+    names = ["out", "dx", "dy"] + [k for k, _ in m.named_parameters()]
+    for name, a, b in zip(names, res[1], res[0]):
+        if a is None:
+            continue
+        close(a, b, 2e-4 if name == "out" else 1e-3, f"fused MAB {name} Nq={Nq} Nk={Nk}")
+
+
+def test_fused_mab_dropout_is_consistent():
+    """With dropout (p = 0.5 in both the block and its feed-forward layer) the backward must regenerate the forward's
+    masks: directional finite difference of the fixed-mask function vs <grad, direction>; and the keep rate."""
+    import mpgan_b200.ops as O
+    from mpgan_b200 import gapt
+    O.set_precision(0)
+    torch.manual_seed(7)
+    lin = dict(leaky_relu_alpha=0.2, dropout_p=0.5, batch_norm=False, spectral_norm=False)
+    m = gapt.MAB(64, 4, ff_layers=[], final_linear=False, dropout_p=0.5, linear_args=lin).cuda().train()
+    B, N = 64, 30
+    x = (torch.randn(B, N, 64, device="cuda") * 0.5).requires_grad_(True)
+    w = torch.randn(B, N, 64, device="cuda")
+    d = torch.randn(B, N, 64, device="cuda")
+    cnt = O._seed_counter
+
+    def f(xx):
+        O._seed_counter = cnt      # replay the same dropout streams
+        return (m(xx, xx, None) * w).sum()
+
+    out = m(x, x, None)
+    keep = float((out != 0).float().mean())
+    # out = Dropout(h + f): kept by the last dropout (1/2) and not the sum of two dropped terms (h and f are each zero
+    # with probability 1/2 from their own dropouts) -> 1/2 * 3/4
+    assert abs(keep - 0.375) < 0.02, keep
+    O._seed_counter = cnt
+    loss = f(x)
+    loss.backward()
+    eps = 1e-2
+    with torch.no_grad():
+        fd = (float(f(x + eps * d)) - float(f(x - eps * d))) / (2 * eps)
+    an = float((x.grad * d).sum())
+    assert abs(fd - an) <= 2e-2 * max(1.0, abs(an)), (fd, an)
