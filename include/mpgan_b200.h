@@ -256,10 +256,13 @@ int mpg_mab_bwd(const float* x, int ldx, const float* y, int ldy, const float* k
  * stream with the same n / ctas: the kernel waits (system-scope flags, bounded spin) until every peer's gradients
  * are complete, sums them in rank order, applies p -= lr * g / (sqrt(sq) + eps) with g = sum / world and
  * sq = alpha * sq + (1 - alpha) * g^2, and returns only after every peer has finished reading this rank's
- * gradients.  ctas <= the SM count (all CTAs must be co-resident).  Graph-capturable (the epoch lives on the device). */
+ * gradients.  grads_multicast (optional): the NVLink-SHARP multicast address of the gradient buffers; the sum is then
+ * ONE multimem.ld_reduce per 16 bytes, reduced inside the NVSwitch, instead of `world` peer loads.  ctas <= the SM
+ * count (all CTAs must be co-resident).  Graph-capturable (the epoch lives on the device). */
 size_t mpg_peer_flag_words(int ctas, int world);
-int mpg_allreduce_rmsprop(float* p, float* sq, const void* const* peer_grads, void* const* peer_flags, size_t n, int rank,
-                          int world, int ctas, float lr, float alpha, float eps, void* stream);
+int mpg_allreduce_rmsprop(float* p, float* sq, const void* const* peer_grads, void* const* peer_flags,
+                          const void* grads_multicast, size_t n, int rank, int world, int ctas, float lr, float alpha,
+                          float eps, void* stream);
 
 #ifdef __cplusplus
 }

@@ -732,13 +732,16 @@ int mpg_mab_bwd(const float* x, int ldx, const float* y, int ldy, const float* k
 
 size_t mpg_peer_flag_words(int ctas, int world) { return peer_flag_words(ctas, world); }
 
-int mpg_allreduce_rmsprop(float* p, float* sq, const void* const* peer_grads, void* const* peer_flags, size_t n, int rank,
-                          int world, int ctas, float lr, float alpha, float eps, void* stream) {
+int mpg_allreduce_rmsprop(float* p, float* sq, const void* const* peer_grads, void* const* peer_flags,
+                          const void* grads_multicast, size_t n, int rank, int world, int ctas, float lr, float alpha,
+                          float eps, void* stream) {
   MPG_CHECK(peer_grads != nullptr && peer_flags != nullptr, "allreduce_rmsprop: null pointer table");
   MPG_CHECK(world >= 2 && world <= MPG_PEER_MAX, "allreduce_rmsprop: world size must be in [2, %d]", MPG_PEER_MAX);
   PeerArgs a;
   memset(&a, 0, sizeof(a));
   a.p = p; a.sq = sq; a.n = n; a.rank = rank; a.world = world; a.lr = lr; a.alpha = alpha; a.eps = eps;
+  a.grads_mc = reinterpret_cast<const float*>(grads_multicast);
+  MPG_CHECK((reinterpret_cast<uintptr_t>(grads_multicast) & 15) == 0, "allreduce_rmsprop: unaligned multicast pointer");
   for (int r = 0; r < world; ++r) {
     a.grads[r] = reinterpret_cast<const float*>(peer_grads[r]);
     a.flags[r] = reinterpret_cast<unsigned*>(peer_flags[r]);

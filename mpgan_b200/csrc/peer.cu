@@ -8,7 +8,8 @@
 //   1. arrive:  flags[p][A, c, me] += 1 on every peer p (release, system scope), then wait until my own
 //      flags[me][A, c, p] reach this call's epoch for every p (acquire): rank p's kernel is running, so the backward
 //      kernels that produced its gradients -- earlier in its stream -- have completed.
-//   2. g = sum_r grads[r][i] in RANK ORDER (so every rank computes bit-identical sums, hence bit-identical weights),
+//   2. (grads_mc != null: g = multimem.ld_reduce over the multicast mapping -- the NVSwitch sums the ranks' buffers,
+//      each rank reads 1.4 MB instead of W x 1.4 MB; else:)  g = sum_r grads[r][i] in RANK ORDER (so every rank computes bit-identical sums, hence bit-identical weights),
 //      read from the peers with 16-byte system-scope loads; sq = a sq + (1-a) (g/W)^2; p -= lr (g/W) / (sqrt(sq) + eps).
 //      The 1.4 MB buffers make the one-shot form (every rank reads everything: (W-1) x 1.4 MB over NVLink) cheaper
 //      than a reduce-scatter + all-gather pair.
@@ -33,6 +34,13 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* addr) {
 __device__ __forceinline__ float4 ld_sys_v4(const float* addr) {
   float4 v;
   asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(addr) : "memory");
+  return v;
+}
+// sum over all ranks of the 16 bytes at this multicast address, reduced inside the NVSwitch (NVLink SHARP)
+__device__ __forceinline__ float4 ld_reduce_mc_v4(const float* mc_addr) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc_addr) : "memory");
   return v;
 }
 __device__ __forceinline__ float ld_sys(const float* addr) {
@@ -89,13 +97,19 @@ __global__ void __launch_bounds__(PEER_THREADS) allreduce_rmsprop_kernel(PeerArg
       idx[u] = base + ((size_t)u * PEER_THREADS + threadIdx.x) * 4;
       g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    for (int r = 0; r < a.world; ++r) {   // rank order: bit-identical sums on every rank
-      float4 v[PEER_UNROLL];
+    if (a.grads_mc != nullptr) {   // in-switch reduction: every rank reads the buffer ONCE instead of world times
 #pragma unroll
       for (int u = 0; u < PEER_UNROLL; ++u)
-        v[u] = idx[u] + 4 <= hi ? ld_sys_v4(a.grads[r] + idx[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (idx[u] + 4 <= hi) g[u] = ld_reduce_mc_v4(a.grads_mc + idx[u]);
+    } else {
+      for (int r = 0; r < a.world; ++r) {   // rank order: bit-identical sums on every rank
+        float4 v[PEER_UNROLL];
 #pragma unroll
-      for (int u = 0; u < PEER_UNROLL; ++u) { g[u].x += v[u].x; g[u].y += v[u].y; g[u].z += v[u].z; g[u].w += v[u].w; }
+        for (int u = 0; u < PEER_UNROLL; ++u)
+          v[u] = idx[u] + 4 <= hi ? ld_sys_v4(a.grads[r] + idx[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < PEER_UNROLL; ++u) { g[u].x += v[u].x; g[u].y += v[u].y; g[u].z += v[u].z; g[u].w += v[u].w; }
+      }
     }
 #pragma unroll
     for (int u = 0; u < PEER_UNROLL; ++u) {

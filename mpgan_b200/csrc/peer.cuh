@@ -8,6 +8,8 @@ struct PeerArgs {
   float* sq;                      // local RMSprop accumulators
   const float* grads[MPG_PEER_MAX];   // every rank's flat gradient buffer (symmetric memory), as mapped on this GPU
   unsigned* flags[MPG_PEER_MAX];      // every rank's flag block (symmetric memory, zero-initialised)
+  const float* grads_mc;              // optional NVLink-SHARP multicast address of the gradient buffers: one
+                                      // multimem.ld_reduce returns the sum over all ranks, reduced in the switch
   size_t n;
   int rank, world;
   float lr, alpha, eps;

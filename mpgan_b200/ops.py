@@ -1016,11 +1016,12 @@ def rmsprop_(p_flat, g_flat, sq_flat, lr, alpha=0.99, eps=1e-8, gscale=1.0):
                              float(alpha), float(eps), float(gscale), _lib.stream()), "mpg_rmsprop")
 
 
-def allreduce_rmsprop_(p_flat, sq_flat, grad_ptrs, flag_ptrs, rank, world, ctas, lr, alpha=0.99, eps=1e-8):
+def allreduce_rmsprop_(p_flat, sq_flat, grad_ptrs, flag_ptrs, rank, world, ctas, lr, alpha=0.99, eps=1e-8, multicast=None):
     """Fused data-parallel update (mpg_allreduce_rmsprop): ``grad_ptrs`` / ``flag_ptrs`` are ctypes arrays of the
-    ranks' peer-mapped gradient buffers and flag blocks."""
+    ranks' peer-mapped gradient buffers and flag blocks; ``multicast``: the buffers' multicast address (int) or None."""
     L = _lib.lib()
-    _lib.check(L.mpg_allreduce_rmsprop(_lib.ptr(p_flat), _lib.ptr(sq_flat), grad_ptrs, flag_ptrs, p_flat.numel(), int(rank),
+    _lib.check(L.mpg_allreduce_rmsprop(_lib.ptr(p_flat), _lib.ptr(sq_flat), grad_ptrs, flag_ptrs, multicast or None,
+                                       p_flat.numel(), int(rank),
                                        int(world), int(ctas), float(lr), float(alpha), float(eps), _lib.stream()),
                "mpg_allreduce_rmsprop")
 

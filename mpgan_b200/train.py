@@ -97,10 +97,23 @@ class PeerReducer:
         self._handles = (handles[0], hf)
         self.grad_ptrs = (C.c_void_p * self.world)(*[int(p) for p in handles[0].buffer_ptrs])
         self.flag_ptrs = (C.c_void_p * self.world)(*[int(p) for p in hf.buffer_ptrs])
+        # NVLink-SHARP multicast mapping of the gradient buffers (in-switch reduction): measured on 8 B200s the
+        # one-shot peer-load form loses to NCCL (every rank reads 8 x 1.4 MB), so from MULTICAST_MIN_WORLD ranks on the
+        # kernel sums with multimem.ld_reduce when the fabric offers it
+        self.multicast = None
+        try:
+            mc = int(handles[0].multicast_ptr)
+            if mc and self.world >= self.MULTICAST_MIN_WORLD and self.use_multicast:
+                self.multicast = mc
+        except Exception:
+            self.multicast = None
+
+    MULTICAST_MIN_WORLD = int(__import__('os').environ.get('MPG_MULTICAST_MIN_WORLD', '4'))
+    use_multicast = True
 
     def step(self, opt):
         ops.allreduce_rmsprop_(self.fp.flat, opt.square_avg, self.grad_ptrs, self.flag_ptrs, self.rank, self.world,
-                               self.CTAS, opt.lr, opt.alpha, opt.eps)
+                               self.CTAS, opt.lr, opt.alpha, opt.eps, multicast=self.multicast)
 
 
 def get_gen_noise(batch_size, num_particles, latent_node_size, sd=0.2, device="cuda", generator=None):
@@ -181,7 +194,8 @@ class GANTrainer:
         if world > 1 and fused_allreduce and next(G.parameters()).is_cuda:
             try:
                 self.peerG, self.peerD = PeerReducer(G, process_group), PeerReducer(D, process_group)
-                self.collective = "fused peer-memory all-reduce + RMSprop (mpg_allreduce_rmsprop)"
+                self.collective = "fused peer-memory all-reduce + RMSprop (mpg_allreduce_rmsprop, " + (
+                    "multimem.ld_reduce in-switch sums)" if self.peerG.multicast else "one-shot peer loads)")
             except Exception as e:   # no peer access / symmetric memory unavailable
                 self.peerG = self.peerD = None
                 self.collective = f"ncclAllReduce + RMSprop kernel (peer memory unavailable: {type(e).__name__})"

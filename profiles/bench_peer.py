@@ -39,14 +39,19 @@ def timeit(fn, iters=200):
 
 
 res = {}
-for ctas in (2, 4, 8, 16, 32, 64):
+for mc in (False, True):
+  train.PeerReducer.use_multicast = mc
+  train.PeerReducer.MULTICAST_MIN_WORLD = 2
+  for ctas in ((8, 16, 32, 64, 128) if mc else (16, 32, 64, 128)):
     # every CTA count needs its own flag block layout: rebuild the reducer's flags
     train.PeerReducer.CTAS = ctas
     D2 = presets.mp_discriminator().to(dev)
     p2 = train.PeerReducer(D2, None)
     o2 = train.FusedRMSprop(p2.fp, 3e-5)
     p2.fp.grad.normal_()
-    res[f"fused_ctas{ctas}"] = timeit(lambda: p2.step(o2))
+    if mc and p2.multicast is None:
+        continue
+    res[f"fused_{'multimem' if mc else 'peer_loads'}_ctas{ctas}"] = timeit(lambda: p2.step(o2))
 g = torch.randn(n, device=dev)
 p = torch.randn(n, device=dev)
 sq = torch.zeros(n, device=dev)
