@@ -178,21 +178,27 @@ int mpg_residual_dropout_bwd(const float* dout, float* dx, size_t rows, int cols
  * entry (:354-363).  mpg_edge_nbr_fwd / _bwd: the fused edge network of mpg_edge_fwd / _bwd with receiver i
  * aggregating over its k listed senders only (mask = the listed sender's mask, mean = 1/k); ef_mode 1 feeds the
  * distance (to the scaled sender when knn_scale != 0) as the pair feature.  fp32 SIMT kernels.  With nbr == NULL
- * mpg_edge_nbr_bwd is the fully connected backward on the fp32 kernels; dmask (optional, [B*N], overwritten) receives
- * the gradient w.r.t. the mask multiplier: dmask[b,j] = scale * sum_i <fe(x_i | x_j), dagg[b,i]>. */
+ * both are the fully connected op on the fp32 kernels; dmask (optional, [B*N], overwritten) receives the gradient
+ * w.r.t. the mask multiplier: dmask[b,j] = scale * sum_i <fe(x_i | x_j), dagg[b,i]>.  lc (optional, [B, H0]): the
+ * first-layer contribution of the conditioning columns (clabels / mask_fne_np, :247-253), Lc = cond W0c^T; pair row r
+ * of the [B*N*K] edge list adds lc[r % B] (the reference's `.repeat` pairs row r with jet r % B); dlc [B, H0]
+ * (overwritten) receives its gradient. */
 int mpg_knn_select(const float* x, int ldx, const float* mask, int B, int N, int nd, int k, int self_loops, int* idx,
                    void* stream);
-int mpg_edge_nbr_fwd(const int* nbr, int K, int knn_scale, const float* x, int ldx, const float* mask, const float* w0,
-                     const float* b0, const float* w1, const float* b1, const float* w2, const float* b2, int B, int N,
-                     int F, int H0, int H1, int H2, int ef_mode, int nd, int mean, float alpha, float p_drop,
+int mpg_edge_nbr_fwd(const int* nbr, int K, int knn_scale, const float* lc, const float* x, int ldx, const float* mask,
+                     const float* w0, const float* b0, const float* w1, const float* b1, const float* w2, const float* b2,
+                     int B, int N, int F, int H0, int H1, int H2, int ef_mode, int nd, int mean, float alpha, float p_drop,
                      uint64_t seed, const uint64_t* seed_dev, void* workspace, size_t workspace_bytes, float* agg,
                      void* stream);
-int mpg_edge_nbr_bwd(const int* nbr, int K, int knn_scale, const float* x, int ldx, const float* mask, const float* w0,
-                     const float* b0, const float* w1, const float* b1, const float* w2, const float* b2, int B, int N,
-                     int F, int H0, int H1, int H2, int ef_mode, int nd, int mean, float alpha, float p_drop,
+int mpg_edge_nbr_bwd(const int* nbr, int K, int knn_scale, const float* lc, const float* x, int ldx, const float* mask,
+                     const float* w0, const float* b0, const float* w1, const float* b1, const float* w2, const float* b2,
+                     int B, int N, int F, int H0, int H1, int H2, int ef_mode, int nd, int mean, float alpha, float p_drop,
                      uint64_t seed, const uint64_t* seed_dev, void* workspace, size_t workspace_bytes, const float* dagg,
-                     float* dx, int lddx, float* dmask, float* dw0, float* db0, float* dw1, float* db1, float* dw2,
-                     float* db2, void* stream);
+                     float* dx, int lddx, float* dmask, float* dlc, float* dw0, float* db0, float* dw1, float* db1,
+                     float* dw2, float* db2, void* stream);
+/* out[r, :F] = x[r, :], out[r, F + t] = cond[r % B, t]: the node network's conditioning columns (labels / particle
+ * count, mpgan/model.py:270-276; the reference's `.repeat(num_nodes, 1)` gives row r the entry r % B). */
+int mpg_cond_columns(const float* x, int ldx, const float* cond, int C, float* out, size_t rows, int F, int B, void* stream);
 
 /* ---- second-order products of the fused edge op: double backward for WGAN-GP (train.py:286-324) -----------------
  * fe is piecewise linear, so with u [B*N, F] the cotangent the double backward receives for mpg_edge_bwd's dx output,

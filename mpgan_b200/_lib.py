@@ -60,10 +60,11 @@ _SIGS = {
     "mpg_residual_dropout_fwd": (C.c_int, [_f, _f, _f, _sz, _i, _fl, _u64, _f, _u32, _f]),
     "mpg_residual_dropout_bwd": (C.c_int, [_f, _f, _sz, _i, _fl, _u64, _f, _u32, _f]),
     "mpg_knn_select": (C.c_int, [_f, _i, _f, _i, _i, _i, _i, _i, _f, _f]),
-    "mpg_edge_nbr_fwd": (C.c_int, [_f, _i, _i, _f, _i, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _i,
+    "mpg_edge_nbr_fwd": (C.c_int, [_f, _i, _i, _f, _f, _i, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _i,
                                    _fl, _fl, _u64, _f, _f, _sz, _f, _f]),
-    "mpg_edge_nbr_bwd": (C.c_int, [_f, _i, _i, _f, _i, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _i,
-                                   _fl, _fl, _u64, _f, _f, _sz, _f, _f, _i, _f, _f, _f, _f, _f, _f, _f, _f]),
+    "mpg_edge_nbr_bwd": (C.c_int, [_f, _i, _i, _f, _f, _i, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _i,
+                                   _fl, _fl, _u64, _f, _f, _sz, _f, _f, _i, _f, _f, _f, _f, _f, _f, _f, _f, _f]),
+    "mpg_cond_columns": (C.c_int, [_f, _i, _f, _i, _f, _sz, _i, _i, _f]),
     "mpg_edge_bwd2_workspace_bytes": (C.c_size_t, [_i] * 6),
     "mpg_edge_bwd2": (C.c_int, [_f, _i, _f, _i, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _fl, _fl, _u64,
                                 _f, _f, _sz, _f, _f, _f, _f, _f, _f, _f]),

@@ -100,7 +100,10 @@ struct EdgeExtra {
   int K = 0;
   int knn_scale = 0;
   float* dmask = nullptr;
-  bool any() const { return nbr != nullptr || dmask != nullptr; }
+  const float* lc = nullptr;
+  float* dlc = nullptr;
+  bool fp32_only = false;   // entry points that always run the fp32 kernels
+  bool any() const { return fp32_only || nbr != nullptr || dmask != nullptr || lc != nullptr; }
 };
 
 int edge_common(EdgeArgs& a, EdgeWs& w, const float* x, int ldx, const float* mask, const float* w0,
@@ -332,9 +335,10 @@ static int edge_fwd_impl(const EdgeExtra& ex, const float* x, int ldx, const flo
   EdgeWs w;
   bool use_tc = false;
   if (edge_common(a, w, x, ldx, mask, w0, b0, w1, b1, w2, b2, B, N, F, H0, H1, H2, ef_mode, nd, mean, alpha,
-                  p_drop, seed, seed_dev, ex.nbr ? 0 : precision, workspace, workspace_bytes, &use_tc, s, true))
+                  p_drop, seed, seed_dev, ex.any() ? 0 : precision, workspace, workspace_bytes, &use_tc, s, true))
     return 1;
   a.agg = agg;
+  a.Lc = ex.lc;
   if (ex.nbr != nullptr) {
     MPG_CHECK(ex.K > 0 && ex.K <= N, "edge_nbr: need 0 < K <= N (K = %d, N = %d)", ex.K, N);
     a.nbr = ex.nbr; a.K = ex.K; a.knn_scale = ex.knn_scale;
@@ -352,14 +356,14 @@ int mpg_edge_fwd(const float* x, int ldx, const float* mask, const float* w0, co
                        p_drop, seed, seed_dev, precision, workspace, workspace_bytes, agg, stream);
 }
 
-int mpg_edge_nbr_fwd(const int* nbr, int K, int knn_scale, const float* x, int ldx, const float* mask, const float* w0,
-                     const float* b0, const float* w1, const float* b1, const float* w2, const float* b2, int B, int N,
-                     int F, int H0, int H1, int H2, int ef_mode, int nd, int mean, float alpha, float p_drop,
+int mpg_edge_nbr_fwd(const int* nbr, int K, int knn_scale, const float* lc, const float* x, int ldx, const float* mask,
+                     const float* w0, const float* b0, const float* w1, const float* b1, const float* w2, const float* b2,
+                     int B, int N, int F, int H0, int H1, int H2, int ef_mode, int nd, int mean, float alpha, float p_drop,
                      uint64_t seed, const uint64_t* seed_dev, void* workspace, size_t workspace_bytes, float* agg,
                      void* stream) {
-  MPG_CHECK(nbr != nullptr, "edge_nbr_fwd: null neighbour list");
   EdgeExtra ex;
-  ex.nbr = nbr; ex.K = K; ex.knn_scale = knn_scale;
+  ex.fp32_only = true;
+  ex.nbr = nbr; ex.K = K; ex.knn_scale = knn_scale; ex.lc = lc;
   return edge_fwd_impl(ex, x, ldx, mask, w0, b0, w1, b1, w2, b2, B, N, F, H0, H1, H2, ef_mode, nd, mean, alpha, p_drop,
                        seed, seed_dev, 0, workspace, workspace_bytes, agg, stream);
 }
@@ -383,6 +387,11 @@ static int edge_bwd_impl(const EdgeExtra& ex, const void* saved, size_t saved_by
     MPG_CHECK(ex.K > 0 && ex.K <= N, "edge_nbr: need 0 < K <= N (K = %d, N = %d)", ex.K, N);
     a.nbr = ex.nbr; a.K = ex.K; a.knn_scale = ex.knn_scale;
     if (mean) a.out_scale = 1.f / (float)ex.K;
+  }
+  a.Lc = ex.lc;
+  if (ex.lc != nullptr && ex.dlc != nullptr) {
+    a.dLc = ex.dlc;
+    MPG_CUDA(cudaMemsetAsync(ex.dlc, 0, (size_t)B * H0 * sizeof(float), s));
   }
   if (ex.dmask != nullptr) {
     MPG_CHECK(mask != nullptr, "edge_bwd: a mask gradient needs a mask");
@@ -458,14 +467,15 @@ int mpg_edge_bwd(const float* x, int ldx, const float* mask, const float* w0, co
                        dw1, db1, dw2, db2, stream);
 }
 
-int mpg_edge_nbr_bwd(const int* nbr, int K, int knn_scale, const float* x, int ldx, const float* mask, const float* w0,
-                     const float* b0, const float* w1, const float* b1, const float* w2, const float* b2, int B, int N,
-                     int F, int H0, int H1, int H2, int ef_mode, int nd, int mean, float alpha, float p_drop,
+int mpg_edge_nbr_bwd(const int* nbr, int K, int knn_scale, const float* lc, const float* x, int ldx, const float* mask,
+                     const float* w0, const float* b0, const float* w1, const float* b1, const float* w2, const float* b2,
+                     int B, int N, int F, int H0, int H1, int H2, int ef_mode, int nd, int mean, float alpha, float p_drop,
                      uint64_t seed, const uint64_t* seed_dev, void* workspace, size_t workspace_bytes, const float* dagg,
-                     float* dx, int lddx, float* dmask, float* dw0, float* db0, float* dw1, float* db1, float* dw2,
-                     float* db2, void* stream) {
+                     float* dx, int lddx, float* dmask, float* dlc, float* dw0, float* db0, float* dw1, float* db1,
+                     float* dw2, float* db2, void* stream) {
   EdgeExtra ex;
-  ex.nbr = nbr; ex.K = K; ex.knn_scale = knn_scale; ex.dmask = dmask;
+  ex.fp32_only = true;
+  ex.nbr = nbr; ex.K = K; ex.knn_scale = knn_scale; ex.dmask = dmask; ex.lc = lc; ex.dlc = dlc;
   return edge_bwd_impl(ex, nullptr, 0, x, ldx, mask, w0, b0, w1, b1, w2, b2, B, N, F, H0, H1, H2, ef_mode, nd, mean, alpha,
                        p_drop, seed, seed_dev, 0, workspace, workspace_bytes, dagg, dx, lddx, dw0, db0, dw1, db1, dw2, db2,
                        stream);
@@ -656,6 +666,10 @@ int mpg_gen_postprocess(const float* jets, int ldj, float* out, int ldo, size_t 
   return launch_gen_postprocess(jets, ldj, out, ldo, rows, c, use_mask, (cudaStream_t)stream);
 }
 
+int mpg_cond_columns(const float* x, int ldx, const float* cond, int C, float* out, size_t rows, int F, int B, void* stream) {
+  MPG_CHECK(C > 0 && F > 0 && B > 0, "cond_columns: bad sizes");
+  return launch_cond_columns(x, ldx, cond, C, out, rows, F, B, (cudaStream_t)stream);
+}
 int mpg_split_mask_bwd(const float* dmask, float* dx, int ldx, size_t rows, void* stream) {
   return launch_split_mask_bwd(dmask, dx, ldx, rows, (cudaStream_t)stream);
 }

@@ -39,6 +39,11 @@ struct EdgeArgs {
   int K;                 // senders per receiver (N when nbr is null)
   int knn_scale;         // scale masked senders in the distance feature (kNN with a mask)
   float* dmask;          // optional [B*N]: d/d(mask), accumulated with atomics (zeroed by the caller)
+  // conditioning columns of the edge network (clabels / mask_fne_np, mpgan/model.py:247-253): pair row r of the
+  // [B*N*K, .] edge input gets cond[r % B] (the reference's .repeat quirk), i.e. the first layer gains
+  // Lc[r % B] = W0c cond[r % B].  Lc [B, H0]; dLc [B, H0] (zeroed by the caller) receives its gradient.
+  const float* Lc;
+  float* dLc;
   // second-order ("tangent") mode of the backward kernel, see mpg_edge_bwd2: Pt/Qt = first layer applied to the
   // direction u (no bias); tagg [B*N, H2] and gmask [B*N] (zeroed by the caller) are outputs; dW1/dW2 receive the
   // second-order weight gradients, dP/dQ the ordinary first-order ones

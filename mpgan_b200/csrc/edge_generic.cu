@@ -111,6 +111,7 @@ __device__ __forceinline__ void build_h0(const EdgeArgs& a, const ChunkCtx& c, c
     if (r < c.nvalid) {
       v = Pi[k] + a.Q[((size_t)c.b * a.N + c.sj[r]) * a.H0 + k];
       for (int e = 0; e < a.n_ef; ++e) v = fmaf(efs[e * RS + r], a.Wef[(size_t)k * a.ldwef + e], v);
+      if (a.Lc != nullptr) v += a.Lc[(size_t)((c.pair0 + c.j0 + r) % (uint64_t)a.B) * a.H0 + k];
       v = lrelu(v, a.alpha);
       if (a.drop.p > 0.f) v = edge_keep(a, 0, c.pair0 + c.j0 + r, k) ? v * a.drop.scale : 0.f;
     }
@@ -387,7 +388,10 @@ __global__ void __launch_bounds__(NTHR) edge_bwd_generic(EdgeArgs a) {
       const int k = idx % a.H0, r = idx / a.H0;
       if (r < c.nvalid) {
         const float v = dH0s[k * RS + r];
-        if (v != 0.f) atomicAdd(a.dQ + ((size_t)c.b * a.N + c.sj[r]) * a.H0 + k, v);
+        if (v != 0.f) {
+          atomicAdd(a.dQ + ((size_t)c.b * a.N + c.sj[r]) * a.H0 + k, v);
+          if (a.dLc != nullptr) atomicAdd(a.dLc + (size_t)((c.pair0 + c.j0 + r) % (uint64_t)a.B) * a.H0 + k, v);
+        }
       }
     }
     if (!TAN && a.n_ef > 0) {

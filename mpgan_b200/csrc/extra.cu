@@ -24,6 +24,17 @@ __global__ void gen_postprocess_kernel(const float* __restrict__ jets, int ldj, 
   }
 }
 
+// ---- node-network conditioning columns: out[r] = (x[r] | cond[r % B]) -------------------------------------------------
+__global__ void cond_columns_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ cond, int C,
+                                    float* __restrict__ out, size_t rows, int F, int B) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int ldo = F + C;
+  if (idx >= rows * ldo) return;
+  const size_t r = idx / ldo;
+  const int c = (int)(idx % ldo);
+  out[idx] = c < F ? x[r * ldx + c] : cond[(r % B) * C + (c - F)];
+}
+
 // ---- d(mask = x[..., -1] + 0.5)/dx: zero everywhere but the last column ------------------------------------------
 __global__ void split_mask_bwd_kernel(const float* __restrict__ dmask, float* __restrict__ dx, int ldx, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -143,6 +154,13 @@ int launch_gen_postprocess(const float* jets, int ldj, float* out, int ldo, size
                            cudaStream_t s) {
   if (rows == 0) return 0;
   gen_postprocess_kernel<<<cdiv((long long)rows, 256), 256, 0, s>>>(jets, ldj, out, ldo, rows, c, use_mask);
+  MPG_LAUNCH_CHECK();
+  return 0;
+}
+int launch_cond_columns(const float* x, int ldx, const float* cond, int C, float* out, size_t rows, int F, int B,
+                        cudaStream_t s) {
+  if (rows == 0) return 0;
+  cond_columns_kernel<<<cdiv((long long)(rows * (F + C)), 256), 256, 0, s>>>(x, ldx, cond, C, out, rows, F, B);
   MPG_LAUNCH_CHECK();
   return 0;
 }

@@ -113,8 +113,6 @@ class MPLayer(nn.Module):
         super().__init__()
         if int_diffs:
             raise NotImplementedError("int_diffs is not implemented in the reference either")
-        if clabels or mask_fne_np:
-            raise NotImplementedError("clabels / mask_fne_np conditioning columns are not supported")
         if len(fe_layers) != 3:
             raise NotImplementedError("the fused edge kernel is built for a 3-layer edge network")
 
@@ -185,14 +183,31 @@ class MPLayer(nn.Module):
         w1, b1 = fe.layer_params(1)
         w2, b2 = fe.layer_params(2)
         p = fe.dropout_p if self.training else 0.0
-        if self.fully_connected:
+        ncond = self.clabels + int(self.mask_fne_np)
+        cond = lc = None
+        if ncond:
+            # conditioning columns (reference :247-253, 270-276): labels[:, :clabels] and / or the particle count, fed to
+            # BOTH networks.  The reference builds them with .repeat, which pairs row r of the edge / node list with jet
+            # r % B -- reproduced as is.  In the edge network they only shift the first layer: Lc = cond W0c^T.
+            assert not (self.clabels and labels is None), "need ``labels`` tensor if using ``clabels`` option"
+            assert not (self.mask_fne_np and num_jet_particles is None), \
+                "need ``num_jet_particles`` tensor if using ``mask_fne_np`` option"
+            parts = ([labels[:, :self.clabels]] if self.clabels else []) + \
+                ([num_jet_particles.reshape(batch_size, 1)] if self.mask_fne_np else [])
+            cond = torch.cat(parts, 1).detach().float().contiguous()
+            nmain = w0.shape[1] - ncond
+            lc = ops.linear(cond, w0[:, nmain:], None, False, 0.0, 0.0)
+            w0 = w0[:, :nmain]
+        if self.fully_connected and lc is None:
             agg = ops.edge_aggregate(x, mask if use_mask else None, w0, b0, w1, b1, w2, b2, ef_mode=self._ef_mode,
                                      nd=self._nd, mean=not self.sum, alpha=fe.leaky_relu_alpha, p_drop=p)
         else:
             m = mask if use_mask else None
-            nbr = ops.knn_select(x, m, self.num_knn, self._nd, self.self_loops)
+            nbr = None if self.fully_connected else ops.knn_select(x, m, self.num_knn, self._nd, self.self_loops)
             agg = ops.edge_aggregate_knn(x, m, nbr, w0, b0, w1, b1, w2, b2, ef_mode=self._ef_mode, nd=self._nd,
-                                         mean=not self.sum, alpha=fe.leaky_relu_alpha, p_drop=p)
+                                         mean=not self.sum, alpha=fe.leaky_relu_alpha, p_drop=p, lc=lc)
+        if cond is not None:
+            x = ops.cond_columns(x, cond)      # (x | cond) for the node network
         fn = self.fn
         pn = fn.dropout_p if self.training else 0.0
         if len(fn.net) == 3 and fn.final_linear and ops.node_net_supported(
@@ -260,6 +275,10 @@ class MPNet(nn.Module):
                                           **mp_args, **linear_args))
         self.mp_layers.append(MPLayer(hidden_node_size, fe_layers, fn_layers, self.output_node_size,
                                       **mp_args, **linear_args))
+        # The reference's conditioning columns pair row r of its flattened lists with jet r % B: the result then depends
+        # on the order of jets and particles, so the layout permutations (real particles first; jets by count in the
+        # trainer) must stay off for such networks.
+        self.order_dependent = any(l.clabels or l.mask_fne_np for l in self.mp_layers)
 
     def forward(self, x: Tensor, labels: Tensor = None) -> Tensor:
         if not x.is_cuda:
@@ -267,7 +286,7 @@ class MPNet(nn.Module):
         x = self._pre_mp(x, labels)
         x, use_mask, mask, num_jet_particles = self._get_mask(x, labels, **self.mask_args)
         idx = None
-        if use_mask and self.sort_particles and x.shape[1] > 1 and not mask.requires_grad:
+        if use_mask and self.sort_particles and x.shape[1] > 1 and not mask.requires_grad and not self.order_dependent:
             # (a mask that carries a gradient -- D differentiated w.r.t. its input's mask channel -- keeps its layout)
             # Real particles first inside every jet.  The layers are permutation-equivariant over particles
             # (fully connected, sum / mean aggregation), so this only changes the layout: a generated jet's real
@@ -395,13 +414,14 @@ class MPDiscriminator(MPNet):
                   mask_fnd_np: bool = False, **mask_args):
         mask = None
         use_mask = mask_manual or mask_learn or mask_c or mask_learn_sep
-        if mask_fne_np:
-            raise NotImplementedError("mask_fne_np is not supported")
         if use_mask or mask_fnd_np:
             mask = ops.split_mask(x)          # x[:, :, -1:] + 0.5, a real-valued multiplier (differentiable)
         if use_mask:
             x = x[:, :, :-1]                  # strided view: the kernels take a row stride, no copy
-        return x, use_mask, mask, None
+        njp = None
+        if mask_fne_np:                       # reference :886-887: mean of the mask over particles, a conditioning value
+            njp = ops.masked_pool(mask.detach(), None, True)
+        return x, use_mask, mask, njp
 
     def __repr__(self):
         dea_str = f",\nFND = {self.fnd_layer}" if self.dea else ""

@@ -217,7 +217,7 @@ class LinearFn(torch.autograd.Function):
         M = int(x2.numel() // x2.shape[-1]) if x2.shape[-1] else 0
         K, N = x2.shape[-1], w.shape[0]
         w = w.contiguous()
-        b = b.contiguous()
+        b = None if b is None else b.contiguous()
         y = torch.empty(*lead, N, device=x.device, dtype=torch.float32)
         if seed is None:
             seed = next_seed() if p_drop > 0 else 0
@@ -396,9 +396,9 @@ class EdgeAggFn(torch.autograd.Function):
             # the mask multiplier itself needs a gradient (D differentiated w.r.t. its input's mask channel): the fp32
             # kernels compute it next to dx
             dmask = torch.empty(B, N, device=dagg.device, dtype=torch.float32)
-            _lib.check(L.mpg_edge_nbr_bwd(None, 0, 0, _lib.ptr(x3), ldx, _lib.ptr(m), *[_lib.ptr(t) for t in (w0, b0, w1, b1, w2, b2)],
+            _lib.check(L.mpg_edge_nbr_bwd(None, 0, 0, None, _lib.ptr(x3), ldx, _lib.ptr(m), *[_lib.ptr(t) for t in (w0, b0, w1, b1, w2, b2)],
                                           B, N, F, H0, H1, H2, ef_mode, nd, mean, alpha, p, seed, sptr, ws.data_ptr(), ws_bytes,
-                                          _lib.ptr(dagg), _lib.ptr(dx), F, _lib.ptr(dmask), *[_lib.ptr(g) for g in grads],
+                                          _lib.ptr(dagg), _lib.ptr(dx), F, _lib.ptr(dmask), None, *[_lib.ptr(g) for g in grads],
                                           _lib.stream()), "mpg_edge_nbr_bwd")
             dmask = dmask.view(ctx.mask_shape)
         else:
@@ -448,9 +448,9 @@ class EdgeAggBwdFn(torch.autograd.Function):
         grads = [torch.zeros_like(t) for t in ws_] if need_w else [None] * 6
         dmask = torch.empty(B, N, device=dev, dtype=torch.float32) if need_mask else None
         if need_mask:
-            _lib.check(L.mpg_edge_nbr_bwd(None, 0, 0, _lib.ptr(x3), ldx, _lib.ptr(m), *[_lib.ptr(t) for t in ws_], B, N, F,
+            _lib.check(L.mpg_edge_nbr_bwd(None, 0, 0, None, _lib.ptr(x3), ldx, _lib.ptr(m), *[_lib.ptr(t) for t in ws_], B, N, F,
                                           H0, H1, H2, ef_mode, nd, mean, alpha, p, seed, sptr, ws.data_ptr(), ws_bytes,
-                                          _lib.ptr(dagg), _lib.ptr(dx), F, _lib.ptr(dmask), *[_lib.ptr(g) for g in grads],
+                                          _lib.ptr(dagg), _lib.ptr(dx), F, _lib.ptr(dmask), None, *[_lib.ptr(g) for g in grads],
                                           _lib.stream()), "mpg_edge_nbr_bwd")
         else:
             _lib.check(L.mpg_edge_bwd(_lib.ptr(x3), ldx, _lib.ptr(m), *[_lib.ptr(t) for t in ws_], B, N, F, H0, H1, H2,
@@ -1174,14 +1174,17 @@ def knn_select(x, mask, k: int, nd: int, self_loops: bool = True):
 
 
 class EdgeNbrFn(torch.autograd.Function):
-    """agg[b,i] = scale * sum_m mask[b, nbr[b,i,m]] fe(x_i | x_nbr | [dist]) over the listed neighbours."""
+    """agg[b,i] = scale * sum_m mask[b, nbr[b,i,m]] fe(x_i | x_nbr | [dist] | [cond]) over the listed neighbours
+    (``nbr`` None: all particles of the jet) on the fp32 kernels; ``lc`` [B, H0]: first-layer contribution of the
+    conditioning columns (see mpg_edge_nbr_fwd)."""
 
     @staticmethod
-    def forward(ctx, x, mask, nbr, w0, b0, w1, b1, w2, b2, ef_mode, nd, mean, alpha, p_drop):
+    def forward(ctx, x, mask, nbr, lc, w0, b0, w1, b1, w2, b2, ef_mode, nd, mean, alpha, p_drop):
         L = _lib.lib()
         x3, ldx = _rows(x)
         B, N, F = x3.shape
-        K = nbr.shape[2]
+        K = N if nbr is None else nbr.shape[2]
+        lc = None if lc is None else lc.contiguous()
         H0, H1, H2 = w0.shape[0], w1.shape[0], w2.shape[0]
         ws_bytes = L.mpg_edge_workspace_bytes(B, N, F, H0, H1, H2)
         ws = torch.empty(ws_bytes, device=x.device, dtype=torch.uint8)
@@ -1189,12 +1192,12 @@ class EdgeNbrFn(torch.autograd.Function):
         m = None if mask is None else mask.reshape(B, N).contiguous()
         ws_ = [t.contiguous() for t in (w0, b0, w1, b1, w2, b2)]
         seed = next_seed() if p_drop > 0 else 0
-        scale = int(m is not None)
-        _lib.check(L.mpg_edge_nbr_fwd(_lib.ptr(nbr), K, scale, _lib.ptr(x3), ldx, _lib.ptr(m), *[_lib.ptr(t) for t in ws_],
+        scale = int(m is not None and nbr is not None)
+        _lib.check(L.mpg_edge_nbr_fwd(_lib.ptr(nbr), K, scale, _lib.ptr(lc), _lib.ptr(x3), ldx, _lib.ptr(m), *[_lib.ptr(t) for t in ws_],
                                       B, N, F, H0, H1, H2, int(ef_mode), int(nd), int(mean), float(alpha), float(p_drop),
                                       seed, _seed_ptr(), ws.data_ptr(), ws_bytes, _lib.ptr(agg), _lib.stream()),
                    "mpg_edge_nbr_fwd")
-        ctx.save_for_backward(x3, m, nbr, *ws_)
+        ctx.save_for_backward(x3, m, nbr, lc, *ws_)
         ctx.params = (w0, b0, w1, b1, w2, b2)
         ctx.cfg = (ldx, B, N, F, K, H0, H1, H2, int(ef_mode), int(nd), int(mean), float(alpha), float(p_drop), seed,
                    scale, _seed_ptr())
@@ -1204,14 +1207,15 @@ class EdgeNbrFn(torch.autograd.Function):
     @once_differentiable
     def backward(ctx, dagg):
         L = _lib.lib()
-        x3, m, nbr, w0, b0, w1, b1, w2, b2 = ctx.saved_tensors
+        x3, m, nbr, lc, w0, b0, w1, b1, w2, b2 = ctx.saved_tensors
         ldx, B, N, F, K, H0, H1, H2, ef_mode, nd, mean, alpha, p, seed, scale, sptr = ctx.cfg
         dagg = dagg.contiguous()
         ws_bytes = L.mpg_edge_workspace_bytes(B, N, F, H0, H1, H2)
         ws = torch.empty(ws_bytes, device=dagg.device, dtype=torch.uint8)
         dx = torch.empty(B, N, F, device=dagg.device, dtype=torch.float32)
-        want_w = _want_wgrad(ctx, 3, 9)
-        sinks = [_grad_sink(q) for q in ctx.params] if (want_w and all(ctx.needs_input_grad[3:9])) else [None] * 6
+        dlc = torch.empty(B, H0, device=dagg.device, dtype=torch.float32) if (lc is not None and ctx.needs_input_grad[3]) else None
+        want_w = _want_wgrad(ctx, 4, 10)
+        sinks = [_grad_sink(q) for q in ctx.params] if (want_w and all(ctx.needs_input_grad[4:10])) else [None] * 6
         direct = all(g is not None for g in sinks)
         if direct:
             grads = sinks
@@ -1219,17 +1223,42 @@ class EdgeNbrFn(torch.autograd.Function):
             grads = [torch.zeros_like(t) for t in (w0, b0, w1, b1, w2, b2)]
         else:
             grads = [None] * 6
-        _lib.check(L.mpg_edge_nbr_bwd(_lib.ptr(nbr), K, scale, _lib.ptr(x3), ldx, _lib.ptr(m),
+        _lib.check(L.mpg_edge_nbr_bwd(_lib.ptr(nbr), K, scale, _lib.ptr(lc), _lib.ptr(x3), ldx, _lib.ptr(m),
                                       *[_lib.ptr(t) for t in (w0, b0, w1, b1, w2, b2)], B, N, F, H0, H1, H2, ef_mode, nd,
                                       mean, alpha, p, seed, sptr, ws.data_ptr(), ws_bytes, _lib.ptr(dagg), _lib.ptr(dx), F,
-                                      None, *[_lib.ptr(g) for g in grads], _lib.stream()), "mpg_edge_nbr_bwd")
+                                      None, _lib.ptr(dlc), *[_lib.ptr(g) for g in grads], _lib.stream()), "mpg_edge_nbr_bwd")
         if direct:
             grads = [None] * 6
-        return (dx, None, None, *grads, None, None, None, None, None)
+        return (dx, None, None, dlc, *grads, None, None, None, None, None)
 
 
-def edge_aggregate_knn(x, mask, nbr, w0, b0, w1, b1, w2, b2, ef_mode=0, nd=0, mean=False, alpha=0.2, p_drop=0.0):
-    return EdgeNbrFn.apply(x, mask, nbr, w0, b0, w1, b1, w2, b2, ef_mode, nd, mean, alpha, p_drop)
+def edge_aggregate_knn(x, mask, nbr, w0, b0, w1, b1, w2, b2, ef_mode=0, nd=0, mean=False, alpha=0.2, p_drop=0.0, lc=None):
+    """``nbr`` None + ``lc``: the fully connected op with conditioning columns (fp32 kernels)."""
+    return EdgeNbrFn.apply(x, mask, nbr, lc, w0, b0, w1, b1, w2, b2, ef_mode, nd, mean, alpha, p_drop)
+
+
+class CondColsFn(torch.autograd.Function):
+    """(x | cond[r % B]) for the node network's input (mpgan/model.py:270-276); the conditioning values are data."""
+
+    @staticmethod
+    def forward(ctx, x, cond):
+        L = _lib.lib()
+        x3, ldx = _rows(x)
+        B, N, F = x3.shape
+        c = cond.detach().contiguous().float()
+        out = torch.empty(B, N, F + c.shape[1], device=x.device, dtype=torch.float32)
+        _lib.check(L.mpg_cond_columns(_lib.ptr(x3), ldx, _lib.ptr(c), c.shape[1], _lib.ptr(out), B * N, F, B, _lib.stream()),
+                   "mpg_cond_columns")
+        ctx.F = F
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        return dout[..., :ctx.F], None
+
+
+def cond_columns(x, cond):
+    return CondColsFn.apply(x, cond)
 
 
 # --------------------------------------------------------------------------------------------------

@@ -182,7 +182,7 @@ class GANTrainer:
         # kernels then holds jets with (nearly) the same padding, and the (tile, sender) steps whose sender is
         # padded in ALL of the tile's jets -- which the kernels drop -- go from ~5-30 % to ~50 % of the steps
         # for n ~ U{1..N}.
-        self.sort_by_count = sort_by_count
+        self.sort_by_count = sort_by_count and not (getattr(G, "order_dependent", False) or getattr(D, "order_dependent", False))
         world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         if world_override is not None:
             world = int(world_override)
@@ -407,6 +407,10 @@ def generate(G, labels, num_particles, latent_node_size=32, sd=0.2, noise=None):
     """G(noise, labels) with the jets processed in order of particle count (fewer live edge-kernel steps, see
     GANTrainer.sort_by_count) and returned in the caller's order."""
     B = labels.shape[0]
+    if getattr(G, "order_dependent", False):   # conditioning columns depend on the jet order (model.MPNet)
+        if noise is None:
+            noise = get_gen_noise(B, num_particles, latent_node_size, sd, labels.device)
+        return G(noise, labels)
     pos = ops.batch_order(labels)
     if noise is None:
         noise = get_gen_noise(B, num_particles, latent_node_size, sd, labels.device)

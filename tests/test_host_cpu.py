@@ -159,12 +159,12 @@ def test_unsupported_options_fail_loudly():
     with pytest.raises(NotImplementedError):
         LinearNet([8], input_size=4, batch_norm=True)
     with pytest.raises(NotImplementedError):
-        MPLayer(3, [96, 160, 192], [256, 256], 32, clabels=1)
-    with pytest.raises(NotImplementedError):
         presets.mp_generator(mask_learn=True)
     with pytest.raises(ValueError):   # kNN feeds ONE distance column; the reference dies with a shape error here
         MPLayer(3, [96, 160, 192], [256, 256], 32, fully_connected=False, pos_diffs=True, delta_coords=True, delta_r=True)
-    # supported since round 2: kNN message passing, GAPT LayerNorm (reference parameter names)
+    # supported since round 2: kNN message passing, conditioning columns, GAPT LayerNorm (reference parameter names)
+    assert MPLayer(3, [96, 160, 192], [256, 256], 32, clabels=2, mask_fne_np=True).fe.net[0].weight.shape == (96, 9)
+    assert presets.mp_discriminator(clabels=1).order_dependent and not presets.mp_discriminator().order_dependent
     l = MPLayer(3, [96, 160, 192], [256, 256], 32, fully_connected=False, num_knn=5, pos_diffs=True, all_ef=False)
     assert (l._ef_mode, l._nd, l.num_ef) == (1, 2, 1) and l.fe.net[0].weight.shape == (96, 7)
     g = presets.gapt_generator(layer_norm_gen=True)
