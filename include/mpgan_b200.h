@@ -238,6 +238,8 @@ int mpg_layernorm_bwd(const float* dy, const float* x, const float* w, const flo
  * same pointer for self attention); w_in [3E, E] / b_in [3E] = nn.MultiheadAttention.in_proj_*, w_out / b_out =
  * out_proj, w_ff / b_ff = ff.net.0 (ff_layers = []).  Supported (mpg_mab_supported): E = 64, 4 heads, Nq, Nk <= 32 --
  * SAB, ISAB (10 inducing points) and PMA (1 seed) on 30-particle jets.  p_res = MAB's dropout, p_ff = the LinearNet's.
+ * precision 0: fp32 SIMT arithmetic; 1: the five projections (and their gradients) on TF32 mma.sync tiles, fp32
+ * accumulate, attention core in fp32.
  * The forward leaves q [B*Nq,E], kv [B*Nk,2E], o, h, f [B*Nq,E] for the backward, which recomputes the attention
  * probabilities, overwrites dx (and dy when y != x) and ACCUMULATES the six parameter gradients (all or none). */
 int mpg_mab_supported(int E, int heads, int Nq, int Nk);
@@ -245,14 +247,14 @@ size_t mpg_mab_workspace_bytes(int B);
 int mpg_mab_fwd(const float* x, int ldx, const float* y, int ldy, const float* key_mask, const float* w_in,
                 const float* b_in, const float* w_out, const float* b_out, const float* w_ff, const float* b_ff, int B,
                 int Nq, int Nk, int E, int heads, float alpha, float p_res, float p_ff, uint64_t seed,
-                const uint64_t* seed_dev, void* workspace, size_t workspace_bytes, float* q, float* kv, float* o, float* h,
-                float* f, float* out, void* stream);
+                const uint64_t* seed_dev, int precision, void* workspace, size_t workspace_bytes, float* q, float* kv,
+                float* o, float* h, float* f, float* out, void* stream);
 int mpg_mab_bwd(const float* x, int ldx, const float* y, int ldy, const float* key_mask, const float* w_in,
                 const float* b_in, const float* w_out, const float* b_out, const float* w_ff, const float* b_ff, int B,
                 int Nq, int Nk, int E, int heads, float alpha, float p_res, float p_ff, uint64_t seed,
-                const uint64_t* seed_dev, void* workspace, size_t workspace_bytes, const float* q, const float* kv,
-                const float* o, const float* h, const float* f, const float* dout, float* dx, float* dy, float* dw_in,
-                float* db_in, float* dw_out, float* db_out, float* dw_ff, float* db_ff, void* stream);
+                const uint64_t* seed_dev, int precision, void* workspace, size_t workspace_bytes, const float* q,
+                const float* kv, const float* o, const float* h, const float* f, const float* dout, float* dx, float* dy,
+                float* dw_in, float* db_in, float* dw_out, float* db_out, float* dw_ff, float* db_ff, void* stream);
 
 /* ---- data-parallel update: one-shot gradient all-reduce fused with RMSprop over NVLink peer memory ------------------
  * (replaces DataParallel's gradient reduction, setup_training.py:1418-1421, + torch.optim.RMSprop, :1511-1513.)

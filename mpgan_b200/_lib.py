@@ -76,10 +76,10 @@ _SIGS = {
     "mpg_layernorm_bwd": (C.c_int, [_f, _f, _f, _f, _f, _f, _f, _f, _sz, _i, _f]),
     "mpg_mab_supported": (C.c_int, [_i, _i, _i, _i]),
     "mpg_mab_workspace_bytes": (C.c_size_t, [_i]),
-    "mpg_mab_fwd": (C.c_int, [_f, _i, _f, _i, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _fl, _fl, _fl, _u64, _f, _f,
-                              _sz, _f, _f, _f, _f, _f, _f, _f]),
-    "mpg_mab_bwd": (C.c_int, [_f, _i, _f, _i, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _fl, _fl, _fl, _u64, _f, _f,
-                              _sz, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f]),
+    "mpg_mab_fwd": (C.c_int, [_f, _i, _f, _i, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _fl, _fl, _fl, _u64, _f, _i,
+                              _f, _sz, _f, _f, _f, _f, _f, _f, _f]),
+    "mpg_mab_bwd": (C.c_int, [_f, _i, _f, _i, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _fl, _fl, _fl, _u64, _f, _i,
+                              _f, _sz, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f]),
     "mpg_peer_flag_words": (C.c_size_t, [_i, _i]),
     "mpg_allreduce_rmsprop": (C.c_int, [_f, _f, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _f, _sz, _i, _i, _i, _fl,
                                         _fl, _fl, _f]),

@@ -711,22 +711,22 @@ static int mab_args(MabArgs& a, const float* x, int ldx, const float* y, int ldy
 int mpg_mab_fwd(const float* x, int ldx, const float* y, int ldy, const float* key_mask, const float* w_in,
                 const float* b_in, const float* w_out, const float* b_out, const float* w_ff, const float* b_ff, int B,
                 int Nq, int Nk, int E, int heads, float alpha, float p_res, float p_ff, uint64_t seed,
-                const uint64_t* seed_dev, void* workspace, size_t workspace_bytes, float* q, float* kv, float* o, float* h,
-                float* f, float* out, void* stream) {
+                const uint64_t* seed_dev, int precision, void* workspace, size_t workspace_bytes, float* q, float* kv,
+                float* o, float* h, float* f, float* out, void* stream) {
   MabArgs a;
   if (mab_args(a, x, ldx, y, ldy, key_mask, w_in, b_in, w_out, b_out, w_ff, b_ff, B, Nq, Nk, E, heads, alpha, p_res, p_ff,
                seed, seed_dev, q, kv, o, h, f, out))
     return 1;
   MPG_CHECK(out != nullptr && workspace != nullptr && workspace_bytes >= mab_workspace_bytes(B), "mab_fwd: workspace too small");
-  return launch_mab_fwd(a, workspace, (cudaStream_t)stream);
+  return launch_mab_fwd(a, workspace, precision, (cudaStream_t)stream);
 }
 
 int mpg_mab_bwd(const float* x, int ldx, const float* y, int ldy, const float* key_mask, const float* w_in,
                 const float* b_in, const float* w_out, const float* b_out, const float* w_ff, const float* b_ff, int B,
                 int Nq, int Nk, int E, int heads, float alpha, float p_res, float p_ff, uint64_t seed,
-                const uint64_t* seed_dev, void* workspace, size_t workspace_bytes, const float* q, const float* kv,
-                const float* o, const float* h, const float* f, const float* dout, float* dx, float* dy, float* dw_in,
-                float* db_in, float* dw_out, float* db_out, float* dw_ff, float* db_ff, void* stream) {
+                const uint64_t* seed_dev, int precision, void* workspace, size_t workspace_bytes, const float* q,
+                const float* kv, const float* o, const float* h, const float* f, const float* dout, float* dx, float* dy,
+                float* dw_in, float* db_in, float* dw_out, float* db_out, float* dw_ff, float* db_ff, void* stream) {
   MabArgs a;
   if (mab_args(a, x, ldx, y, ldy, key_mask, w_in, b_in, w_out, b_out, w_ff, b_ff, B, Nq, Nk, E, heads, alpha, p_res, p_ff,
                seed, seed_dev, const_cast<float*>(q), const_cast<float*>(kv), const_cast<float*>(o), const_cast<float*>(h),
@@ -741,7 +741,7 @@ int mpg_mab_bwd(const float* x, int ldx, const float* y, int ldy, const float* k
   memset(&g, 0, sizeof(g));
   g.dout = dout; g.dx = dx; g.dy = dy;
   g.dw_in = dw_in; g.db_in = db_in; g.dw_out = dw_out; g.db_out = db_out; g.dw_ff = dw_ff; g.db_ff = db_ff;
-  return launch_mab_bwd(a, g, workspace, (cudaStream_t)stream);
+  return launch_mab_bwd(a, g, workspace, precision, (cudaStream_t)stream);
 }
 
 size_t mpg_peer_flag_words(int ctas, int world) { return peer_flag_words(ctas, world); }

@@ -21,6 +21,6 @@ struct MabGrads {
 };
 bool mab_supported(int E, int heads, int Nq, int Nk);
 size_t mab_workspace_bytes(int B);
-int launch_mab_fwd(const MabArgs& a, void* workspace, cudaStream_t s);
-int launch_mab_bwd(const MabArgs& a, MabGrads g, void* workspace, cudaStream_t s);
+int launch_mab_fwd(const MabArgs& a, void* workspace, int precision, cudaStream_t s);
+int launch_mab_bwd(const MabArgs& a, MabGrads g, void* workspace, int precision, cudaStream_t s);
 }  // namespace mpg

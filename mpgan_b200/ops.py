@@ -1311,12 +1311,13 @@ class MabFn(torch.autograd.Function):
         o, h, f, out = (torch.empty(B, Nq, E, device=dev, dtype=torch.float32) for _ in range(4))
         seed = next_seed() if (p_res > 0 or p_ff > 0) else 0
         _lib.check(L.mpg_mab_fwd(_lib.ptr(x3), ldx, _lib.ptr(y3), ldy, _lib.ptr(km), *[_lib.ptr(t) for t in ws_], B, Nq, Nk,
-                                 E, int(heads), float(alpha), float(p_res), float(p_ff), seed, _seed_ptr(), ws.data_ptr(),
-                                 ws_bytes, _lib.ptr(q), _lib.ptr(kv), _lib.ptr(o), _lib.ptr(h), _lib.ptr(f), _lib.ptr(out),
-                                 _lib.stream()), "mpg_mab_fwd")
+                                 E, int(heads), float(alpha), float(p_res), float(p_ff), seed, _seed_ptr(), _PRECISION,
+                                 ws.data_ptr(), ws_bytes, _lib.ptr(q), _lib.ptr(kv), _lib.ptr(o), _lib.ptr(h), _lib.ptr(f),
+                                 _lib.ptr(out), _lib.stream()), "mpg_mab_fwd")
         ctx.save_for_backward(x3, y3 if not self_attn else None, km, q, kv, o, h, f, *ws_)
         ctx.params = (w_in, b_in, w_out, b_out, w_ff, b_ff)
-        ctx.cfg = (ldx, ldy, B, Nq, Nk, E, int(heads), float(alpha), float(p_res), float(p_ff), seed, _seed_ptr(), self_attn)
+        ctx.cfg = (ldx, ldy, B, Nq, Nk, E, int(heads), float(alpha), float(p_res), float(p_ff), seed, _seed_ptr(), self_attn,
+                   _PRECISION)
         return out
 
     @staticmethod
@@ -1324,7 +1325,7 @@ class MabFn(torch.autograd.Function):
     def backward(ctx, dout):
         L = _lib.lib()
         x3, y3, km, q, kv, o, h, f, *ws_ = ctx.saved_tensors
-        ldx, ldy, B, Nq, Nk, E, heads, alpha, p_res, p_ff, seed, sptr, self_attn = ctx.cfg
+        ldx, ldy, B, Nq, Nk, E, heads, alpha, p_res, p_ff, seed, sptr, self_attn, prec = ctx.cfg
         if self_attn:
             y3 = x3
         dev = dout.device
@@ -1347,7 +1348,7 @@ class MabFn(torch.autograd.Function):
         else:
             grads = [None] * 6
         _lib.check(L.mpg_mab_bwd(_lib.ptr(x3), ldx, _lib.ptr(y3), ldy, _lib.ptr(km), *[_lib.ptr(t) for t in ws_], B, Nq, Nk,
-                                 E, heads, alpha, p_res, p_ff, seed, sptr, ws.data_ptr(), ws_bytes, _lib.ptr(q), _lib.ptr(kv),
+                                 E, heads, alpha, p_res, p_ff, seed, sptr, prec, ws.data_ptr(), ws_bytes, _lib.ptr(q), _lib.ptr(kv),
                                  _lib.ptr(o), _lib.ptr(h), _lib.ptr(f), _lib.ptr(dout), _lib.ptr(dx), _lib.ptr(dy),
                                  *[_lib.ptr(g) for g in grads], _lib.stream()), "mpg_mab_bwd")
         if direct:

@@ -244,12 +244,15 @@ def test_batch_order_large_batch():
         assert torch.equal(pos, ref), B
 
 
+@pytest.mark.parametrize("prec", [0, 1])
 @pytest.mark.parametrize("Nq,Nk,masked", [(30, 30, True), (10, 30, True), (30, 10, False), (1, 30, True), (17, 17, False)])
-def test_fused_mab_matches_per_op_path(Nq, Nk, masked):
+def test_fused_mab_matches_per_op_path(Nq, Nk, masked, prec):
     """ops.MabFn (one kernel per direction) against the per-op path (projection GEMMs + attention core + residual
-    kernels, itself pinned to the reference by the GAPT goldens): forward, input and all parameter gradients."""
+    kernels, itself pinned to the reference by the GAPT goldens): forward, input and all parameter gradients.
+    precision 0: fp32 SIMT kernel vs 3xTF32 GEMMs; precision 1: TF32 mma.sync kernel vs TF32 GEMMs (both round their
+    operands to TF32, in different places: 5e-3 forward, 2e-2 relative L2 on gradients)."""
     from mpgan_b200 import gapt, ops
-    ops.set_precision(0)
+    ops.set_precision(prec)
     torch.manual_seed(100 + Nq + Nk)
     lin = dict(leaky_relu_alpha=0.2, dropout_p=0.0, batch_norm=False, spectral_norm=False)
     m = gapt.MAB(64, 4, ff_layers=[], final_linear=False, dropout_p=0.0, linear_args=lin).cuda().train()
@@ -275,7 +278,12 @@ def test_fused_mab_matches_per_op_path(Nq, Nk, masked):
     for name, a, b in zip(names, res[1], res[0]):
         if a is None:
             continue
-        close(a, b, 2e-4 if name == "out" else 1e-3, f"fused MAB {name} Nq={Nq} Nk={Nk}")
+        if prec == 0:
+            close(a, b, 2e-4 if name == "out" else 1e-3, f"fused MAB {name} Nq={Nq} Nk={Nk}")
+        elif name == "out":
+            close(a, b, 5e-3, f"fused MAB {name} Nq={Nq} Nk={Nk}")
+        else:
+            assert rel_l2(a, b) <= 2e-2, f"fused MAB {name} Nq={Nq} Nk={Nk}: rel L2 {rel_l2(a, b):.3e}"
 
 
 def test_fused_mab_dropout_is_consistent():
@@ -335,3 +343,35 @@ def test_conditioning_columns_golden(golden):
             close(dict(layer.named_parameters())[k].grad, g, 2e-3, f"{name} {k}")
         done += 1
     assert done >= 6
+
+
+def test_fused_mab_tensor_core_matches_simt_with_dropout():
+    """The TF32 mma.sync kernel (precision 1) against the fp32 SIMT kernel (precision 0) of the same fused block WITH
+    dropout 0.5 and the same seed: identical keep masks (one draws them per row cooperatively, the other per element)
+    and the same arithmetic up to TF32 operand rounding -- forward, input and parameter gradients."""
+    import mpgan_b200.ops as O
+    from mpgan_b200 import gapt
+    torch.manual_seed(11)
+    lin = dict(leaky_relu_alpha=0.2, dropout_p=0.5, batch_norm=False, spectral_norm=False)
+    m = gapt.MAB(64, 4, ff_layers=[], final_linear=False, dropout_p=0.5, linear_args=lin).cuda().train()
+    for Nq, Nk in ((30, 30), (10, 30)):
+        B = 40
+        x0 = torch.randn(B, Nq, 64, device="cuda") * 0.5
+        y0 = x0 if Nq == Nk else torch.randn(B, Nk, 64, device="cuda") * 0.5
+        n = torch.randint(1, Nk + 1, (B,), device="cuda")
+        mask = (torch.arange(Nk, device="cuda")[None, :] < n[:, None]).float().unsqueeze(2)
+        w = torch.randn(B, Nq, 64, device="cuda")
+        res = []
+        for prec in (0, 1):
+            O.set_precision(prec)
+            O._seed_counter = 777
+            m.zero_grad()
+            x = x0.clone().requires_grad_(True)
+            y = x if Nq == Nk else y0.clone().requires_grad_(True)
+            out = m(x, y, mask)
+            (out * w).sum().backward()
+            res.append([out.detach(), x.grad] + [p.grad.clone() for p in m.parameters()])
+        assert torch.equal(res[0][0] == 0, res[1][0] == 0), "the two kernels must drop the same elements"
+        close(res[1][0], res[0][0], 5e-3, "out")
+        for a, b in zip(res[1][1:], res[0][1:]):
+            assert rel_l2(a, b) <= 2e-2, rel_l2(a, b)
