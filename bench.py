@@ -271,16 +271,17 @@ def run_reference(args, name, wl):
     import torch
     N, kind = wl["N"], wl["kind"]
     B_sample = cpu_sample_size(wl)
-    # bounded: time one probe step, then shrink the per-step sample until warmup + steps fit ~3.5 minutes
+    # bounded: time one probe step, then cut the step count, then the per-step sample, until the run fits ~3.5 minutes
     warm, reps = max(0, args.warmup), max(1, args.steps)
     probe_B = max(1, min(B_sample, 32))
     sec_probe, cores, how = reference_step_time(wl, probe_B, 1, 0)
     budget = 210.0
-    while B_sample > 8 and sec_probe / probe_B * B_sample * (warm + reps) > budget:
+    per_step = lambda: sec_probe / probe_B * B_sample
+    if per_step() * (warm + reps) > budget:   # keep the GPU arm's batch, run fewer steps of it (said in steps / warmup)
+        warm = min(warm, 2)
+        reps = min(reps, max(5, int(budget / per_step()) - warm))
+    while B_sample > 8 and per_step() * (warm + reps) > budget:   # a step of the full batch is too long: bounded sample
         B_sample //= 2
-    if sec_probe / probe_B * B_sample * (warm + reps) > budget:   # still too long: fewer steps of the same sample
-        reps = max(2, int(budget / (sec_probe / probe_B * B_sample)) - 1)
-        warm = 1
     sec, cores, how = reference_step_time(wl, B_sample, reps, warm)
     val = B_sample / sec
     what = "unmodified reference (oracle/_ref: train.train_D + train.train_G, torch.optim.RMSprop)" if how == "reference" \
