@@ -75,14 +75,15 @@ EdgeWs carve_edge_ws(void* base, int B, int N, int F, int H0, int H1, int H2) {
     return r;
   };
   const size_t BN = (size_t)B * N;
-  w.P = take(BN * H0);
+  const size_t BNT = (BN + 127) / 128 * 128;   // P / dP may be stored per 128-row tile (EdgeArgs::p_tiled)
+  w.P = take(BNT * H0);
   w.Q = take(BN * H0);
   w.W1t = take((size_t)H0 * H1);
   w.W2t = take((size_t)H1 * H2);
   w.tc = p + off;
   off += align_up(edge_tc_persist_bytes(B, N, H0, H1, H2));
   w.persist = off;
-  w.dP = take(BN * H0);     // dP and dQ are adjacent: one memset clears both
+  w.dP = take(BNT * H0);    // dP and dQ are adjacent: one memset clears both
   w.dQ = take(BN * H0);
   w.dxef = take(BN * F);
   // sink for the weight gradients of a dx-only backward on the generic path (never read)
@@ -140,10 +141,13 @@ int edge_common(EdgeArgs& a, EdgeWs& w, const float* x, int ldx, const float* ma
   a.drop = make_drop(p_drop, seed, seed_dev);
   const bool precise = precision == 0;
   *use_tc = !precise && edge_tc_supported(a);
+  // both ends of P / dP are the pq kernels and the tcgen05 kernels: tile-major storage (the backward takes the same
+  // decision from the same arguments, so a saved forward workspace is read the way it was written)
+  a.p_tiled = (*use_tc && (edge_tc_features() & 2) && pq_supported(F, H0)) ? 1 : 0;
   if (saved != nullptr) return 0;
   // factorised first layer: W0 [x_i ; x_j ; ef] = Wa x_i + Wb x_j + Wef ef   (node-level GEMMs)
   if (pq_supported(F, H0)) {
-    if (launch_pq_fwd(x, ldx, w0, a.ldwef, b0, w.P, w.Q, B * N, F, H0, s)) return 1;
+    if (launch_pq_fwd(x, ldx, w0, a.ldwef, b0, w.P, w.Q, B * N, F, H0, s, a.p_tiled != 0)) return 1;
   } else {
     GemmEpi e;
     e.bias = b0;
@@ -435,7 +439,7 @@ static int edge_bwd_impl(const EdgeExtra& ex, const void* saved, size_t saved_by
   const bool precise = precision == 0;
   // node-level tail of the factorised first layer
   if (pq_supported(F, H0)) {
-    if (launch_pq_bwd(w.dP, w.dQ, x, ldx, w0, a.ldwef, dx, lddx, dw0, db0, (int)BN, F, H0, s)) return 1;
+    if (launch_pq_bwd(w.dP, w.dQ, x, ldx, w0, a.ldwef, dx, lddx, dw0, db0, (int)BN, F, H0, s, a.p_tiled != 0)) return 1;
   } else {
     GemmEpi acc;
     acc.accumulate = 1;

@@ -11,6 +11,11 @@ struct EdgeArgs {
   // factorised first layer (node level): P = x*Wa^T + b0, Q = x*Wb^T   [B*N, H0]
   const float* P;
   const float* Q;
+  // p_tiled: P and dP are stored per 128-row tile as [column group k/4][row in tile][4] (the order in which the
+  // tcgen05 kernels' threads -- one per row -- read them: a warp's 32 rows x 16 bytes are contiguous); only set when
+  // both ends (pq kernels and tcgen05 edge kernels) run, with both buffers rounded up to whole tiles.  Q/dQ stay
+  // row-major (they are copied a row at a time).
+  int p_tiled;
   // optional pair features (pos_diffs): ef_mode bit0 = distance column, bit1 = difference columns
   const float* x;        // [B*N, F] node features, row stride ldx
   int ldx;
@@ -61,9 +66,13 @@ int launch_transpose(const float* in, int rows, int cols, float* out, cudaStream
 // node-level ends of the factorised first layer (edge_node.cu)
 bool pq_supported(int F, int H0);
 int launch_pq_fwd(const float* x, int ldx, const float* W0, int ldw, const float* b0, float* P, float* Q, int BN,
-                  int F, int H0, cudaStream_t stream);
+                  int F, int H0, cudaStream_t stream, bool p_tiled = false);
 int launch_pq_bwd(const float* dP, const float* dQ, const float* x, int ldx, const float* W0, int ldw, float* dx,
-                  int lddx, float* dW0, float* db0, int BN, int F, int H0, cudaStream_t stream);
+                  int lddx, float* dW0, float* db0, int BN, int F, int H0, cudaStream_t stream, bool p_tiled = false);
+// element (row r, column k) of a tiled P / dP buffer (EdgeArgs::p_tiled), H0 columns, 128-row tiles
+__host__ __device__ inline size_t p_tiled_index(size_t r, int k, int H0) {
+  return (r >> 7) * 128 * (size_t)H0 + ((size_t)(k >> 2) * 128 + (r & 127)) * 4 + (k & 3);
+}
 
 // tcgen05 path (edge_tc.cu): default architecture only
 int edge_tc_features();

@@ -26,7 +26,7 @@ __device__ __forceinline__ void load_w_t(float* Ws, const float* __restrict__ W0
 
 __global__ void __launch_bounds__(NT) pq_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ W0,
                                                     int ldw, const float* __restrict__ b0, float* __restrict__ P,
-                                                    float* __restrict__ Q, int BN, int F, int H0) {
+                                                    float* __restrict__ Q, int BN, int F, int H0, int p_tiled) {
   extern __shared__ float sm[];
   const int H0P = H0 + 1, FP = F + 1;
   float* Ws = sm;                       // [2F][H0P]
@@ -53,10 +53,11 @@ __global__ void __launch_bounds__(NT) pq_fwd_kernel(const float* __restrict__ x,
       for (int i = 0; i < 4; ++i) acc[i] = fmaf(xs[(rg * 4 + i) * FP + f], wv, acc[i]);
     }
     float* dst = c < H0 ? P : Q;
+    const bool tiled = p_tiled && c < H0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int r = r0 + rg * 4 + i;
-      if (r < BN) dst[(size_t)r * H0 + k] = acc[i];
+      if (r < BN) dst[tiled ? p_tiled_index(r, k, H0) : (size_t)r * H0 + k] = acc[i];
     }
   }
 }
@@ -67,7 +68,7 @@ __global__ void __launch_bounds__(NT) pq_fwd_kernel(const float* __restrict__ x,
 __global__ void __launch_bounds__(NT) pq_bwd_kernel(const float* __restrict__ dP, const float* __restrict__ dQ,
                                                     const float* __restrict__ x, int ldx, const float* __restrict__ W0,
                                                     int ldw, float* __restrict__ dx, int lddx, float* __restrict__ dW0,
-                                                    float* __restrict__ db0, int BN, int F, int H0) {
+                                                    float* __restrict__ db0, int BN, int F, int H0, int p_tiled) {
   extern __shared__ __align__(16) float sm[];
   const int H0P = H0 + 4, FP = F + 1, DP = 2 * H0 + 4;   // H0 % 4 == 0 (launcher): rows stay 16-byte aligned
   float* Ws = sm;                          // [2F][H0P]   Ws[c][k] = W0[k][c]
@@ -79,11 +80,27 @@ __global__ void __launch_bounds__(NT) pq_bwd_kernel(const float* __restrict__ dP
     const int r = idx / F, f = idx % F;
     xs[r * FP + f] = r0 + r < BN ? x[(size_t)(r0 + r) * ldx + f] : 0.f;
   }
-  for (int idx = threadIdx.x; idx < BWD_ROWS * 2 * H0; idx += NT) {
-    const int r = idx / (2 * H0), c = idx % (2 * H0);
-    float v = 0.f;
-    if (r0 + r < BN) v = c < H0 ? dP[(size_t)(r0 + r) * H0 + c] : dQ[(size_t)(r0 + r) * H0 + c - H0];
-    ds[r * DP + c] = v;
+  if (p_tiled) {   // dP: 16-byte column groups, 64 consecutive rows of a group are contiguous; dQ: row-major
+    const int ng = H0 / 4;
+    for (int idx = threadIdx.x; idx < ng * BWD_ROWS; idx += NT) {
+      const int g = idx / BWD_ROWS, r = idx % BWD_ROWS;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r0 + r < BN) v = *reinterpret_cast<const float4*>(dP + p_tiled_index(r0 + r, 4 * g, H0));
+      *reinterpret_cast<float4*>(ds + r * DP + 4 * g) = v;
+    }
+    for (int idx = threadIdx.x; idx < BWD_ROWS * ng; idx += NT) {
+      const int r = idx / ng, g = idx % ng;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r0 + r < BN) v = *reinterpret_cast<const float4*>(dQ + (size_t)(r0 + r) * H0 + 4 * g);
+      *reinterpret_cast<float4*>(ds + r * DP + H0 + 4 * g) = v;
+    }
+  } else {
+    for (int idx = threadIdx.x; idx < BWD_ROWS * 2 * H0; idx += NT) {
+      const int r = idx / (2 * H0), c = idx % (2 * H0);
+      float v = 0.f;
+      if (r0 + r < BN) v = c < H0 ? dP[(size_t)(r0 + r) * H0 + c] : dQ[(size_t)(r0 + r) * H0 + c - H0];
+      ds[r * DP + c] = v;
+    }
   }
   __syncthreads();
   // ---- dx[r][f] = sum_k dP[r][k] Wa[k][f] + dQ[r][k] Wb[k][f]: 8 rows (independent accumulators) per thread ----
@@ -156,19 +173,19 @@ size_t bwd_smem(int F, int H0) {
 bool pq_supported(int F, int H0) { return F >= 1 && F <= 64 && H0 >= 8 && H0 <= 128 && H0 % 8 == 0; }
 
 int launch_pq_fwd(const float* x, int ldx, const float* W0, int ldw, const float* b0, float* P, float* Q, int BN,
-                  int F, int H0, cudaStream_t stream) {
+                  int F, int H0, cudaStream_t stream, bool p_tiled) {
   const size_t smem = fwd_smem(F, H0);
   MPG_CUDA(cudaFuncSetAttribute(pq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  pq_fwd_kernel<<<cdiv(BN, FWD_ROWS), NT, smem, stream>>>(x, ldx, W0, ldw, b0, P, Q, BN, F, H0);
+  pq_fwd_kernel<<<cdiv(BN, FWD_ROWS), NT, smem, stream>>>(x, ldx, W0, ldw, b0, P, Q, BN, F, H0, p_tiled ? 1 : 0);
   MPG_LAUNCH_CHECK();
   return 0;
 }
 
 int launch_pq_bwd(const float* dP, const float* dQ, const float* x, int ldx, const float* W0, int ldw, float* dx,
-                  int lddx, float* dW0, float* db0, int BN, int F, int H0, cudaStream_t stream) {
+                  int lddx, float* dW0, float* db0, int BN, int F, int H0, cudaStream_t stream, bool p_tiled) {
   const size_t smem = bwd_smem(F, H0);
   MPG_CUDA(cudaFuncSetAttribute(pq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  pq_bwd_kernel<<<cdiv(BN, BWD_ROWS), NT, smem, stream>>>(dP, dQ, x, ldx, W0, ldw, dx, lddx, dW0, db0, BN, F, H0);
+  pq_bwd_kernel<<<cdiv(BN, BWD_ROWS), NT, smem, stream>>>(dP, dQ, x, ldx, W0, ldw, dx, lddx, dW0, db0, BN, F, H0, p_tiled ? 1 : 0);
   MPG_LAUNCH_CHECK();
   return 0;
 }

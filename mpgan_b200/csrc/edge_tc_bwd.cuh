@@ -127,12 +127,17 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + OFF_BARS + 192);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  MPG_TP(0);
   const long long total_steps = *t.total_steps;
   const long long g0 = total_steps * blockIdx.x / gridDim.x;
   const long long g1 = total_steps * (blockIdx.x + 1) / gridDim.x;
   const int nsteps = (int)(g1 - g0);
   const int2* steps = t.steps + g0;   // this CTA's (tile, sender) list
   const int N = a.N, BN = a.B * a.N;
+  // every thread fetches the first record itself: the load is in flight under the barrier / TMEM set-up, and the
+  // epilogue threads can start their first tile's row loads without waiting for the loader's first stage
+  int2 first = make_int2(0, 0);
+  if (nsteps > 0) first = __ldg(steps);
 
   if (threadIdx.x == 0) {
     mbar_init(bar0 + BwdBars::w, 1);
@@ -150,6 +155,7 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  MPG_TP(1);
 
   if (warp >= 16) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(F_REGS_CTL));
@@ -165,7 +171,7 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
         mbar_expect_tx_elect(ubar + BwdBars::w, W1_BYTES);
         bulk_g2s_elect(ub + OFF_W1, t.w1img, W1_BYTES, ubar + BwdBars::w);
       }
-      int2 ts = steps[0];
+      int2 ts = first;
       for (int it = 0; it < nsteps; ++it) {
         const int2 ts_next = steps[it + 1 < nsteps ? it + 1 : it];   // in flight while this step's copies are issued
         const int st = it % QS;
@@ -177,15 +183,16 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
         const uint32_t bar = ubar + BwdBars::q + 8 * st;
         const uint32_t dst = ub + OFF_QR + (uint32_t)st * F_QSTAGE;
         // stage header (tile, sender, the sender's mask in each jet of the tile): see edge_tc_fwd.cuh
-        if (lane < nj) {
-          const float mv = a.mask ? __ldg(a.mask + (size_t)(j0 + lane) * N + q_s) : 1.f;
-          asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst + F_QHDR + 8 + 4 * (uint32_t)lane), "f"(mv) : "memory");
-        }
+        // the mask load and the row copies are in flight together; the header is stored and the barrier's own
+        // arrival (with the byte count) comes last, so the phase cannot complete before the header is visible
+        float mv = 1.f;
+        if (lane < nj && a.mask) mv = __ldg(a.mask + (size_t)(j0 + lane) * N + q_s);
+        for (int j = 0; j < nj; ++j)
+          bulk_g2s_elect(dst + (uint32_t)j * F_QROW, a.Q + ((size_t)(j0 + j) * N + q_s) * K0, F_QROW, bar);
+        if (lane < nj) asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst + F_QHDR + 8 + 4 * (uint32_t)lane), "f"(mv) : "memory");
         if (lane == 0) asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(dst + F_QHDR), "r"(q_tile), "r"(q_s) : "memory");
         __syncwarp();
         mbar_expect_tx_elect(bar, (uint32_t)nj * F_QROW);
-        for (int j = 0; j < nj; ++j)
-          bulk_g2s_elect(dst + (uint32_t)j * F_QROW, a.Q + ((size_t)(j0 + j) * N + q_s) * K0, F_QROW, bar);
         ts = ts_next;
       }
     } else if (warp == 16 && nsteps > 0) {
@@ -344,6 +351,7 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
   } else {
     // =============================== epilogue warps ====================================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(F_REGS_EPI));
+    MPG_TP(8);
     if (nsteps == 0) {   // no work (fewer live steps than CTAs): this CTA's part of its slab must still be defined
       float* slab = t.wslab + (size_t)blockIdx.x * SLAB_FLOATS;
       for (int i = (CH ? SLAB_DW1 : SLAB_DW2) + threadIdx.x; i < (CH ? SLAB_DW2 : SLAB_FLOATS); i += F_NEPI) slab[i] = 0.f;
@@ -402,29 +410,35 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
           st_zero_chunk(sH0 + swz_chunk(row, 120, A_BLK));
         }
       };
+      auto tile_rows = [&](int tile) {   // this thread's row of `tile`: index, stage offsets, its P values
+        h_loaded = tile;
+        const int r = tile * TILE + row;
+        const int rc = r < BN ? r : BN - 1;
+        h_r = rc;
+        h_valid = r < BN;
+        const uint32_t jl = (uint32_t)(rc / N - (tile * TILE) / N);
+        h_moff = F_QHDR + 8 + 4 * jl;
+        h_qoff = jl * F_QROW + (uint32_t)q * 32u;
+        // row-major: 8 floats at column 32c + 8q; tiled (EdgeArgs::p_tiled): column groups 8c + 2q (+1), the warp's 32
+        // rows of one group contiguous (rows past the end read the last row, like the row-major form)
+        const float* p = a.p_tiled ? a.P + (size_t)tile * TILE * K0 + ((size_t)(2 * q) * TILE + (rc - tile * TILE)) * 4
+                                   : a.P + (size_t)rc * K0 + q * 8;
+        const int cs = a.p_tiled ? 8 * TILE * 4 : 32, hs = a.p_tiled ? TILE * 4 : 4;
+#pragma unroll
+        for (int c = 0; c < Q0 / 8; ++c) {
+          const float4 v0 = __ldg(reinterpret_cast<const float4*>(p + cs * c));
+          const float4 v1 = __ldg(reinterpret_cast<const float4*>(p + cs * c + hs));
+          Preg[8 * c] = v0.x; Preg[8 * c + 1] = v0.y; Preg[8 * c + 2] = v0.z; Preg[8 * c + 3] = v0.w;
+          Preg[8 * c + 4] = v1.x; Preg[8 * c + 5] = v1.y; Preg[8 * c + 6] = v1.z; Preg[8 * c + 7] = v1.w;
+        }
+      };
       auto build_h0 = [&](int it) {
         mbar_wait(bar0 + BwdBars::q + 8 * (it % QS), (it / QS) & 1);
+        if (it == 0) MPG_TP(12);
         const uint32_t stage = sQ + (uint32_t)(it % QS) * F_QSTAGE;
         int h_tile, h_s;
         asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(h_tile), "=r"(h_s) : "r"(stage + F_QHDR));
-        if (h_tile != h_loaded) {
-          h_loaded = h_tile;
-          const int r = h_tile * TILE + row;
-          const int rc = r < BN ? r : BN - 1;
-          h_r = rc;
-          h_valid = r < BN;
-          const uint32_t jl = (uint32_t)(rc / N - (h_tile * TILE) / N);
-          h_moff = F_QHDR + 8 + 4 * jl;
-          h_qoff = jl * F_QROW + (uint32_t)q * 32u;
-          const float* p = a.P + (size_t)rc * K0 + q * 8;
-#pragma unroll
-          for (int c = 0; c < Q0 / 8; ++c) {
-            const float4 v0 = __ldg(reinterpret_cast<const float4*>(p + 32 * c));
-            const float4 v1 = __ldg(reinterpret_cast<const float4*>(p + 32 * c + 4));
-            Preg[8 * c] = v0.x; Preg[8 * c + 1] = v0.y; Preg[8 * c + 2] = v0.z; Preg[8 * c + 3] = v0.w;
-            Preg[8 * c + 4] = v1.x; Preg[8 * c + 5] = v1.y; Preg[8 * c + 6] = v1.z; Preg[8 * c + 7] = v1.w;
-          }
-        }
+        if (h_tile != h_loaded) tile_rows(h_tile);
         {
           float mv;
           asm volatile("ld.shared.f32 %0, [%1];" : "=f"(mv) : "r"(stage + h_moff));
@@ -465,22 +479,35 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
       // DW2 builds two steps ahead: records of steps it+1 (p1_*) and it+2 (n_*)
       int p1_tile = -1, p1_s = 0;
       float p1_m = 0.f;
+      const bool dagg32 = (reinterpret_cast<uintptr_t>(a.dagg) & 31) == 0;
       auto enter_tile = [&]() {   // rows of the tile the current step belongs to; their dAgg
         const int r = c_tile * TILE + row;
         c_valid = r < BN;
         c_r = c_valid ? r : BN - 1;
         const float* dg = a.dagg + (size_t)c_r * N2 + q * 8;
+        if (dagg32) {   // 32-byte loads (see ldg256)
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+          for (int h = 0; h < 2; ++h)
 #pragma unroll
-          for (int c = 0; c < QH / 8; ++c) {
-            const float4 v0 = __ldg(reinterpret_cast<const float4*>(dg + h * NH2 + 32 * c));
-            const float4 v1 = __ldg(reinterpret_cast<const float4*>(dg + h * NH2 + 32 * c + 4));
-            dAggp[h * (QH / 2) + 4 * c] = pack_bf16(v0.x, v0.y);
-            dAggp[h * (QH / 2) + 4 * c + 1] = pack_bf16(v0.z, v0.w);
-            dAggp[h * (QH / 2) + 4 * c + 2] = pack_bf16(v1.x, v1.y);
-            dAggp[h * (QH / 2) + 4 * c + 3] = pack_bf16(v1.z, v1.w);
-          }
+            for (int c = 0; c < QH / 8; ++c) {
+              float v[8];
+              ldg256(dg + h * NH2 + 32 * c, v);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) dAggp[h * (QH / 2) + 4 * c + e] = pack_bf16(v[2 * e], v[2 * e + 1]);
+            }
+        } else {
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int c = 0; c < QH / 8; ++c) {
+              const float4 v0 = __ldg(reinterpret_cast<const float4*>(dg + h * NH2 + 32 * c));
+              const float4 v1 = __ldg(reinterpret_cast<const float4*>(dg + h * NH2 + 32 * c + 4));
+              dAggp[h * (QH / 2) + 4 * c] = pack_bf16(v0.x, v0.y);
+              dAggp[h * (QH / 2) + 4 * c + 1] = pack_bf16(v0.z, v0.w);
+              dAggp[h * (QH / 2) + 4 * c + 2] = pack_bf16(v1.x, v1.y);
+              dAggp[h * (QH / 2) + 4 * c + 3] = pack_bf16(v1.z, v1.w);
+            }
+        }
       };
       if (CH) {
 #pragma unroll
@@ -498,15 +525,18 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
           }
         }
       }
-      if (CH) {   // the first tile's constant-1 / one-hot columns must be in place before build_h0(0) releases M1(0)
-        mbar_wait(bar0 + BwdBars::q, 0);
-        int t0;
-        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(t0) : "r"(sQ + F_QHDR));
-        write_onehot(t0);
-      }
-      build_h0(0);
-      c_tile = n_tile; c_s = n_s; c_m = n_m;
+      // the first tile's P and dAgg rows are requested before the loader's first stage is waited for (one memory
+      // round trip under the other)
+      MPG_TP(9);
+      tile_rows(first.x);
+      c_tile = first.x;
       enter_tile();
+      MPG_TP(10);
+      if (CH) write_onehot(first.x);   // constant-1 / one-hot columns: in place before build_h0(0) releases M1(0)
+      MPG_TP(11);
+      build_h0(0);
+      MPG_TP(13);
+      c_tile = n_tile; c_s = n_s; c_m = n_m;
       s0 = s0_next;
       k0w = k0w_next;
       if (!CH && nsteps > 1) {   // DW2: layer 1 runs one step ahead
@@ -529,6 +559,7 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
         }
       };
 
+      MPG_TP(2);
       for (int it = 0; it < nsteps; ++it) {
         const uint32_t par = it & 1;
         const float mfac = c_m;
@@ -756,11 +787,14 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
             c_m = n_m;
             if (c_first) {
               if (c_valid) {
-                float* dst = a.dP + (size_t)c_r * K0 + q * 8;
+                // (layouts as in tile_rows: tiled dP makes each warp-wide reduction 512 contiguous bytes)
+                float* dst = a.p_tiled ? a.dP + (size_t)c_tile * TILE * K0 + ((size_t)(2 * q) * TILE + row) * 4
+                                       : a.dP + (size_t)c_r * K0 + q * 8;
+                const int cs = a.p_tiled ? 8 * TILE * 4 : 32, hs = a.p_tiled ? TILE * 4 : 4;
 #pragma unroll
                 for (int c = 0; c < Q0; c += 4)
-                  red_add_v4(dst + 32 * (c >> 3) + (c & 7), dPacc[c] * sc_g0, dPacc[c + 1] * sc_g0, dPacc[c + 2] * sc_g0,
-                             dPacc[c + 3] * sc_g0);
+                  red_add_v4(dst + cs * (c >> 3) + hs * ((c >> 2) & 1), dPacc[c] * sc_g0, dPacc[c + 1] * sc_g0,
+                             dPacc[c + 2] * sc_g0, dPacc[c + 3] * sc_g0);
               }
 #pragma unroll
               for (int c = 0; c < Q0; ++c) dPacc[c] = 0.f;
@@ -787,10 +821,13 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
       }
 
       // ---- drain -----------------------------------------------------------------------------------------------------------
+      MPG_TP(3);
       if constexpr (CH) {
         mbar_wait(bar0 + BwdBars::doneE, (nsteps - 1) & 1);
         tc_fence_after();
+        MPG_TP(4);
         dq_readout();
+        MPG_TP(5);
         // dW1^T accumulator: lane = H0' column k0 (< 96: dW1[:, k0]; 96: db1), column n1 = 32c + 8q + e
         float* slab = t.wslab + (size_t)blockIdx.x * SLAB_FLOATS;
         float v[Q1];
@@ -827,8 +864,10 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
     }
   }
 
+  MPG_TP(6);
   tc_fence_before();
   __syncthreads();
+  MPG_TP(7);
   if (warp == 16) tmem_dealloc(tmem, TMEM_COLS);
 }
 

@@ -289,6 +289,14 @@ __device__ __forceinline__ void st_ones_chunk(uint32_t addr) {   // {1, 1, 0, 0,
 __device__ __forceinline__ void st_zero_chunk(uint32_t addr) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(addr), "r"(0u));
 }
+// 32 contiguous bytes (32-byte aligned) of read-only global memory in one instruction: the epilogue threads read their
+// rows with one row per lane, so every warp-wide load touches 32 different lines -- half as many instructions, half as
+// many L1 wavefronts as two 16-byte loads
+__device__ __forceinline__ void ldg256(const float* p, float (&v)[8]) {
+  asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+      : "l"(p));
+}
 // keep bit `b` (0..127) of a 128-bit Philox draw as an all-ones / all-zeros word
 __device__ __forceinline__ uint32_t keep_mask(const u4& bits, int b) {
   const uint32_t w = (b >> 5) == 0 ? bits.x : ((b >> 5) == 1 ? bits.y : ((b >> 5) == 2 ? bits.z : bits.w));

@@ -107,6 +107,10 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
   const int nsteps = (int)(g1 - g0);
   const int2* steps = t.steps + g0;   // this CTA's (tile, sender) list
   const int N = a.N, BN = a.B * a.N;
+  // every thread fetches the first record itself: the load is in flight under the barrier / TMEM set-up, and the
+  // epilogue threads can start their first tile's row loads without waiting for the loader's first stage
+  int2 first = make_int2(0, 0);
+  if (nsteps > 0) first = __ldg(steps);
   MPG_TP(0);
 
   if (threadIdx.x == 0) {
@@ -139,7 +143,7 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
       mbar_expect_tx_elect(bar_w, W1_BYTES + W2_BYTES);
       bulk_g2s_elect(sW1, t.w1img, W1_BYTES, bar_w);
       bulk_g2s_elect(sW2, t.w2img, W2_BYTES, bar_w);
-      int2 ts = steps[0];
+      int2 ts = first;
       for (int it = 0; it < nsteps; ++it) {
         const int2 ts_next = steps[it + 1 < nsteps ? it + 1 : it];   // in flight while this step's copies are issued
         // stage it % F_QS is free once every builder thread has read the rows of step it - F_QS
@@ -152,15 +156,16 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
         const uint32_t dst = sQ + (uint32_t)(it & (F_QS - 1)) * F_QSTAGE;
         // header: the step and the sender's mask in each jet of the tile, so that no epilogue thread touches global
         // memory per step (the loader runs F_QS steps ahead: its own loads are off everybody's critical path)
-        if (lane < nj) {
-          const float mv = a.mask ? __ldg(a.mask + (size_t)(j0 + lane) * N + q_s) : 1.f;
-          asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst + F_QHDR + 8 + 4 * (uint32_t)lane), "f"(mv) : "memory");
-        }
+        // the mask load and the row copies are in flight together; the header is stored and the barrier's own
+        // arrival (with the byte count) comes last, so the phase cannot complete before the header is visible
+        float mv = 1.f;
+        if (lane < nj && a.mask) mv = __ldg(a.mask + (size_t)(j0 + lane) * N + q_s);
+        for (int j = 0; j < nj; ++j)
+          bulk_g2s_elect(dst + (uint32_t)j * F_QROW, a.Q + ((size_t)(j0 + j) * N + q_s) * K0, F_QROW, bar);
+        if (lane < nj) asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst + F_QHDR + 8 + 4 * (uint32_t)lane), "f"(mv) : "memory");
         if (lane == 0) asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(dst + F_QHDR), "r"(q_tile), "r"(q_s) : "memory");
         __syncwarp();
         mbar_expect_tx_elect(bar, (uint32_t)nj * F_QROW);
-        for (int j = 0; j < nj; ++j)
-          bulk_g2s_elect(dst + (uint32_t)j * F_QROW, a.Q + ((size_t)(j0 + j) * N + q_s) * K0, F_QROW, bar);
         ts = ts_next;
       }
     } else if (warp == 16 && nsteps > 0) {
@@ -283,29 +288,34 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
     // built during iteration it, so three are live
     int s_tile[3] = {0, 0, 0}, s_snd[3] = {0, 0, 0}, s_row[3] = {0, 0, 0};
     float s_m[3] = {0.f, 0.f, 0.f};
+    auto tile_rows = [&](int tile) {   // this thread's row of `tile`: index, stage offsets, its P values
+      h_loaded = tile;
+      const int r = tile * TILE + row;
+      const int rc = r < BN ? r : BN - 1;
+      h_r = rc;
+      h_valid = r < BN;
+      const uint32_t jl = (uint32_t)(rc / N - (tile * TILE) / N);
+      h_moff = F_QHDR + 8 + 4 * jl;
+      h_qoff = jl * F_QROW + (uint32_t)q * 32u;
+      // row-major: 8 floats at column 32c + 8q; tiled (EdgeArgs::p_tiled): column groups 8c + 2q (+1), the warp's 32
+      // rows of one group contiguous (rows past the end read the last row, like the row-major form)
+      const float* p = a.p_tiled ? a.P + (size_t)tile * TILE * K0 + ((size_t)(2 * q) * TILE + (rc - tile * TILE)) * 4
+                                 : a.P + (size_t)rc * K0 + q * 8;
+      const int cs = a.p_tiled ? 8 * TILE * 4 : 32, hs = a.p_tiled ? TILE * 4 : 4;
+#pragma unroll
+      for (int c = 0; c < Q0 / 8; ++c) {
+        const float4 v0 = __ldg(reinterpret_cast<const float4*>(p + cs * c));
+        const float4 v1 = __ldg(reinterpret_cast<const float4*>(p + cs * c + hs));
+        Preg[8 * c] = v0.x; Preg[8 * c + 1] = v0.y; Preg[8 * c + 2] = v0.z; Preg[8 * c + 3] = v0.w;
+        Preg[8 * c + 4] = v1.x; Preg[8 * c + 5] = v1.y; Preg[8 * c + 6] = v1.z; Preg[8 * c + 7] = v1.w;
+      }
+    };
     auto build_h0 = [&](int it) {
       mbar_wait(bar_q + 8 * (it & (F_QS - 1)), (it / F_QS) & 1);
       const uint32_t stage = sQ + (uint32_t)(it & (F_QS - 1)) * F_QSTAGE;
       int h_tile, h_s;
       asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(h_tile), "=r"(h_s) : "r"(stage + F_QHDR));
-      if (h_tile != h_loaded) {
-        h_loaded = h_tile;
-        const int r = h_tile * TILE + row;
-        const int rc = r < BN ? r : BN - 1;
-        h_r = rc;
-        h_valid = r < BN;
-        const uint32_t jl = (uint32_t)(rc / N - (h_tile * TILE) / N);
-        h_moff = F_QHDR + 8 + 4 * jl;
-        h_qoff = jl * F_QROW + (uint32_t)q * 32u;
-        const float* p = a.P + (size_t)rc * K0 + q * 8;
-#pragma unroll
-        for (int c = 0; c < Q0 / 8; ++c) {
-          const float4 v0 = __ldg(reinterpret_cast<const float4*>(p + 32 * c));
-          const float4 v1 = __ldg(reinterpret_cast<const float4*>(p + 32 * c + 4));
-          Preg[8 * c] = v0.x; Preg[8 * c + 1] = v0.y; Preg[8 * c + 2] = v0.z; Preg[8 * c + 3] = v0.w;
-          Preg[8 * c + 4] = v1.x; Preg[8 * c + 5] = v1.y; Preg[8 * c + 6] = v1.z; Preg[8 * c + 7] = v1.w;
-        }
-      }
+      if (h_tile != h_loaded) tile_rows(h_tile);
       {
         float mv;
         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(mv) : "r"(stage + h_moff));
@@ -378,6 +388,7 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
     uint32_t kz = 0, kwd = 0;   // layer-2 keep words of the step whose E1 ran last (consumed one iteration later)
 
     MPG_TP(2);
+    tile_rows(first.x);   // the first tile's P rows are requested before the loader's first stage is waited for
     build_h0(0);
     rotate();
     rotate();              // record of step 0 -> slot 0
