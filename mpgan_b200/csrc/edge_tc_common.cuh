@@ -289,6 +289,12 @@ __device__ __forceinline__ void st_ones_chunk(uint32_t addr) {   // {1, 1, 0, 0,
 __device__ __forceinline__ void st_zero_chunk(uint32_t addr) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(addr), "r"(0u));
 }
+// global[dst .. dst+bytes) += shared[src .. src+bytes) as fp32, asynchronously (bulk_group completion); 16-byte aligned
+// addresses and size.  Issued by one thread.
+__device__ __forceinline__ void bulk_reduce_add_f32(float* dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst), "r"(src_smem),
+               "r"(bytes) : "memory");
+}
 // 32 contiguous bytes (32-byte aligned) of read-only global memory in one instruction: the epilogue threads read their
 // rows with one row per lane, so every warp-wide load touches 32 different lines -- half as many instructions, half as
 // many L1 wavefronts as two 16-byte loads

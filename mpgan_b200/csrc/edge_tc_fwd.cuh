@@ -42,8 +42,12 @@ constexpr uint32_t F_QHDR = F_QJ * F_QROW;   // stage header: int tile, int send
 constexpr uint32_t F_QSTAGE = F_QHDR + 64;
 constexpr int F_NEPIW = 16;                  // epilogue warps = arrivals per barrier phase
 constexpr uint32_t F_OFF_Q = OFF_H1;                       // 147456 (no H1 tile in shared memory)
-constexpr uint32_t F_OFF_BAR = F_OFF_Q + F_QS * F_QSTAGE;  // 211968
-constexpr uint32_t F_SMEM = F_OFF_BAR + 256 + 1024;
+constexpr uint32_t F_OFF_BAR = F_OFF_Q + F_QS * F_QSTAGE;  // 163072
+// staging for the accumulator flush: per TMEM lane quarter (4 warps, 32 rows) one D2 half of every row, padded rows
+// (conflict-free 16-byte accesses both ways).  Threads own rows, global memory wants lines: see flush()
+constexpr uint32_t F_STG_ROW = N2 * 4 + 16;                // 784 bytes: one agg row + pad
+constexpr uint32_t F_OFF_STG = F_OFF_BAR + 256;
+constexpr uint32_t F_SMEM = F_OFF_STG + 4 * 16 * F_STG_ROW + 1024;   // 214528: 16 rows per lane quarter and round
 constexpr uint32_t F_D1_COL = 0, F_D2LO_COL = 320, F_D2HI_COL = 416;
 constexpr int NH2 = N2 / 2;                  // 96: columns of one D2 half
 constexpr int QH = NH2 / NQ;                 // 24: columns of a D2 half owned by one thread
@@ -354,22 +358,45 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
     };
 
     // ---- tile state: `cur` = tile of step `it` (mask / dropout rows), `acc` = tile the accumulators belong to
-    int acc_tile = 0, acc_row = 0;
-    bool acc_valid = false;
+    int acc_tile = 0;
     float e_m = 0.f;      // mask multiplier of the step whose E2 is pending
     const float fl_scale = a.out_scale * (DROP ? 2.f : 1.f) * 0.5f * (1.f + a.alpha);
+    // A thread holds one row's 8-column chunks: 12 reductions of 16 bytes per thread, 6144 per CTA and flush, all
+    // CTAs at once at the end of the kernel (~6.5 k clk per flush, bound by the L2 reduction rate of 16-byte packets).
+    // Instead the rows go to shared memory (padded: conflict-free) and one bulk reduce-add per row (768 contiguous
+    // bytes, cp.reduce.async.bulk) adds them to agg asynchronously: 16 rows per lane quarter and round, each of the
+    // quarter's four warps issues four of them.
     auto flush = [&]() {
-      if (acc_valid) {
-        float* dst = a.agg + (size_t)acc_row * N2 + q * 8;
+      const int g = warp & 3;
+      const uint32_t stg = base + F_OFF_STG + (uint32_t)g * (16u * F_STG_ROW);
+      const int grow0 = acc_tile * TILE + g * 32;
+#pragma unroll 1
+      for (int rd = 0; rd < 2; ++rd) {
+        if ((lane >> 4) == rd) {
+          const uint32_t dst = stg + (uint32_t)(lane & 15) * F_STG_ROW + (uint32_t)(8 * q) * 4u;
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+          for (int h = 0; h < 2; ++h)
 #pragma unroll
-          for (int c = 0; c < QH / 8; ++c)
+            for (int c = 0; c < QH / 8; ++c)
 #pragma unroll
-            for (int e = 0; e < 8; e += 4) {
-              const float* v = acc + h * QH + 8 * c + e;
-              red_add_v4(dst + h * NH2 + 32 * c + e, v[0] * fl_scale, v[1] * fl_scale, v[2] * fl_scale, v[3] * fl_scale);
-            }
+              for (int e = 0; e < 8; e += 4) {
+                const float* v = acc + h * QH + 8 * c + e;
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(dst + (uint32_t)(h * NH2 + 32 * c + e) * 4u),
+                             "f"(v[0] * fl_scale), "f"(v[1] * fl_scale), "f"(v[2] * fl_scale), "f"(v[3] * fl_scale) : "memory");
+              }
+        }
+        fence_async_smem();                 // generic-proxy writes -> visible to the bulk (async proxy) reads
+        named_bar_sync(1 + g, 128);
+        if (lane == 0) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = 4 * q + i, grow = grow0 + 16 * rd + rr;
+            if (grow < BN) bulk_reduce_add_f32(a.agg + (size_t)grow * N2, stg + (uint32_t)rr * F_STG_ROW, N2 * 4);
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // rows read: the staging may be rewritten
+        }
+        named_bar_sync(1 + g, 128);
       }
 #pragma unroll
       for (int c = 0; c < 2 * QH; ++c) acc[c] = 0.f;
@@ -393,8 +420,6 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
     rotate();
     rotate();              // record of step 0 -> slot 0
     acc_tile = s_tile[0];
-    acc_row = s_row[0];
-    acc_valid = acc_tile * TILE + row < BN;
     MPG_TP(3);
     if (nsteps > 1) {
       mbar_wait(bar_d1, 0);   // M1(0) done: the H0' tile may be overwritten
@@ -458,8 +483,6 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
         if (cur_tile != acc_tile) {   // step it-1 was the last one of its tile
           flush();
           acc_tile = cur_tile;
-          acc_row = cur_row;
-          acc_valid = cur_tile * TILE + row < BN;
         }
       }
       e_m = m_cur;          // multiplier of step `it` (its E2 runs in the next iteration)
@@ -483,6 +506,7 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
     e2_half(F_D2HI_COL, acc + QH, kwd);
     MPG_TP(5);
     flush();
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // this thread's reductions have been performed
     MPG_TP(6);
     }
   }

@@ -22,6 +22,12 @@
 namespace mpg {
 namespace {
 
+__device__ __forceinline__ void stg256(float* p, const float (&v)[8]) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+
+
 #define MPG_TC_WRAPPERS_ONLY
 #include "edge_tc_common.cuh"   // PTX wrappers (mbarrier, bulk copies, tcgen05 alloc/commit/ld/st), umma_desc
 
@@ -476,14 +482,23 @@ __global__ void __launch_bounds__(FN_THREADS, 1) fn_tc_kernel(FnTcArgs t) {
           }
         }
       }
+      // a thread owns a row: every warp-wide store touches 32 lines, so one 32-byte store where alignment allows
       if (c0 + 7 < t.Na && t.vec_oa) {
         float* o = t.outa + (size_t)grow * t.ldoa + c0;
-        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        if (t.vec_oa == 2) {
+          stg256(o, v);
+        } else {
+          *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        }
       } else if (c0 >= t.Na && c0 + 7 < NC && t.vec_ob) {
         float* o = t.outb + (size_t)grow * t.ldob + (c0 - t.Na);
-        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        if (t.vec_ob == 2) {
+          stg256(o, v);
+        } else {
+          *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        }
       } else {
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -770,8 +785,11 @@ int launch_fn_tc(FnTcArgs t, bool bwd, const float* w0, const float* w1, const f
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   t.vec_a = (t.a != nullptr) && (t.lda % 4 == 0) && (t.Ka % 4 == 0) && al16(t.a);
   t.vec_b = (t.b != nullptr) && (t.ldb % 4 == 0) && (t.Ka % 4 == 0) && (t.Kb % 4 == 0) && al16(t.b);
-  t.vec_oa = (t.outa != nullptr) && (t.ldoa % 4 == 0) && al16(t.outa);
+  auto al32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
+  t.vec_oa = (t.outa != nullptr) && (t.ldoa % 4 == 0) && al16(t.outa);               // 2: 32-byte stores allowed
   t.vec_ob = (t.outb != nullptr) && (t.ldob % 4 == 0) && (t.Na % 8 == 0) && al16(t.outb);
+  if (t.vec_oa && t.ldoa % 8 == 0 && al32(t.outa)) t.vec_oa = 2;
+  if (t.vec_ob && t.ldob % 8 == 0 && al32(t.outb)) t.vec_ob = 2;
   fn_image_kernel<<<cdiv(chunks, 256), 256, 0, stream>>>(jobs);
   MPG_LAUNCH_CHECK();
   const int grid = cdiv(t.M, 128);
