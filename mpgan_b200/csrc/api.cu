@@ -146,8 +146,12 @@ int edge_common(EdgeArgs& a, EdgeWs& w, const float* x, int ldx, const float* ma
   a.p_tiled = (*use_tc && (edge_tc_features() & 2) && pq_supported(F, H0)) ? 1 : 0;
   if (saved != nullptr) return 0;
   // factorised first layer: W0 [x_i ; x_j ; ef] = Wa x_i + Wb x_j + Wef ef   (node-level GEMMs)
-  if (pq_supported(F, H0)) {
-    if (launch_pq_fwd(x, ldx, w0, a.ldwef, b0, w.P, w.Q, B * N, F, H0, s, a.p_tiled != 0)) return 1;
+  a.pq_deferred = a.p_tiled;
+  a.b0 = b0;
+  if (a.pq_deferred) {
+    // computed by the tcgen05 launcher's set-up kernel
+  } else if (pq_supported(F, H0)) {
+    if (launch_pq_fwd(x, ldx, w0, a.ldwef, b0, w.P, w.Q, B * N, F, H0, s, false)) return 1;
   } else {
     GemmEpi e;
     e.bias = b0;

@@ -16,6 +16,10 @@ struct EdgeArgs {
   // both ends (pq kernels and tcgen05 edge kernels) run, with both buffers rounded up to whole tiles.  Q/dQ stay
   // row-major (they are copied a row at a time).
   int p_tiled;
+  // set together with p_tiled: P / Q have NOT been computed yet -- the tcgen05 launcher's set-up kernel does it (next to
+  // the weight images and the work list, one launch) from x, W0 (= Wef - 2F, row stride ldwef) and b0
+  int pq_deferred;
+  const float* b0;
   // optional pair features (pos_diffs): ef_mode bit0 = distance column, bit1 = difference columns
   const float* x;        // [B*N, F] node features, row stride ldx
   int ldx;

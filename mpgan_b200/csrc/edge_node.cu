@@ -7,12 +7,11 @@
 // launches + a column sum (~20 us each, latency-bound).  One fp32 SIMT kernel per direction does the
 // same work from shared memory in a few microseconds, exactly (no TF32 rounding).
 // Reference: first Linear of fe applied to cat(x_i, x_j), mpgan/model.py:77-83, 294-311.
-#include "edge.cuh"
+#include "edge_node.cuh"
 
 namespace mpg {
 namespace {
 
-constexpr int FWD_ROWS = 32;     // rows per block, forward
 constexpr int BWD_ROWS = 64;     // rows per block, backward (two blocks per SM)
 constexpr int NT = 256;
 
@@ -24,42 +23,9 @@ __device__ __forceinline__ void load_w_t(float* Ws, const float* __restrict__ W0
   }
 }
 
-__global__ void __launch_bounds__(NT) pq_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ W0,
-                                                    int ldw, const float* __restrict__ b0, float* __restrict__ P,
-                                                    float* __restrict__ Q, int BN, int F, int H0, int p_tiled) {
-  extern __shared__ float sm[];
-  const int H0P = H0 + 1, FP = F + 1;
-  float* Ws = sm;                       // [2F][H0P]
-  float* xs = Ws + 2 * F * H0P;         // [FWD_ROWS][FP]
-  const int r0 = blockIdx.x * FWD_ROWS;
-  load_w_t(Ws, W0, ldw, F, H0, H0P);
-  for (int idx = threadIdx.x; idx < FWD_ROWS * F; idx += NT) {
-    const int r = idx / F, f = idx % F;
-    xs[r * FP + f] = r0 + r < BN ? x[(size_t)(r0 + r) * ldx + f] : 0.f;
-  }
-  __syncthreads();
-  // thread -> output column c of [P | Q] (c < 2*H0), 4 rows at a time
-  for (int idx = threadIdx.x; idx < 2 * H0 * (FWD_ROWS / 4); idx += NT) {
-    const int c = idx % (2 * H0), rg = idx / (2 * H0);
-    const int k = c < H0 ? c : c - H0;
-    const float* w = Ws + (c < H0 ? 0 : F) * H0P + k;
-    float acc[4];
-    const float bias = c < H0 ? b0[k] : 0.f;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) acc[i] = bias;
-    for (int f = 0; f < F; ++f) {
-      const float wv = w[f * H0P];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) acc[i] = fmaf(xs[(rg * 4 + i) * FP + f], wv, acc[i]);
-    }
-    float* dst = c < H0 ? P : Q;
-    const bool tiled = p_tiled && c < H0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = r0 + rg * 4 + i;
-      if (r < BN) dst[tiled ? p_tiled_index(r, k, H0) : (size_t)r * H0 + k] = acc[i];
-    }
-  }
+__global__ void __launch_bounds__(PQ_NT) pq_fwd_kernel(PqFwdArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  pq_fwd_tile(a, blockIdx.x, sm);
 }
 
 // dx, dW0[:, :2F] += [dP^T x | dQ^T x], db0 += column sums of dP.  Shared-memory bandwidth (one warp load per
@@ -163,20 +129,24 @@ __global__ void __launch_bounds__(NT) pq_bwd_kernel(const float* __restrict__ dP
   }
 }
 
-size_t fwd_smem(int F, int H0) { return (size_t)(2 * F * (H0 + 1) + FWD_ROWS * (F + 1)) * sizeof(float); }
 size_t bwd_smem(int F, int H0) {
   return (size_t)(2 * F * (H0 + 4) + BWD_ROWS * (F + 1) + BWD_ROWS * (2 * H0 + 4)) * sizeof(float);
 }
 
 }  // namespace
 
-bool pq_supported(int F, int H0) { return F >= 1 && F <= 64 && H0 >= 8 && H0 <= 128 && H0 % 8 == 0; }
+bool pq_supported(int F, int H0) {
+  return F >= 1 && F <= 64 && H0 >= 8 && H0 <= 128 && H0 % 8 == 0 && pq_fwd_smem(F, H0) <= 227 * 1024;
+}
 
 int launch_pq_fwd(const float* x, int ldx, const float* W0, int ldw, const float* b0, float* P, float* Q, int BN,
                   int F, int H0, cudaStream_t stream, bool p_tiled) {
-  const size_t smem = fwd_smem(F, H0);
+  MPG_CHECK((reinterpret_cast<uintptr_t>(P) & 15) == 0 && (reinterpret_cast<uintptr_t>(Q) & 15) == 0,
+            "pq_fwd: P / Q must be 16-byte aligned");
+  const size_t smem = pq_fwd_smem(F, H0);
   MPG_CUDA(cudaFuncSetAttribute(pq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  pq_fwd_kernel<<<cdiv(BN, FWD_ROWS), NT, smem, stream>>>(x, ldx, W0, ldw, b0, P, Q, BN, F, H0, p_tiled ? 1 : 0);
+  PqFwdArgs a{x, ldx, W0, ldw, b0, P, Q, BN, F, H0, p_tiled ? 1 : 0};
+  pq_fwd_kernel<<<cdiv(BN, PQ_ROWS), PQ_NT, smem, stream>>>(a);
   MPG_LAUNCH_CHECK();
   return 0;
 }

@@ -1,7 +1,9 @@
 // tcgen05 / TMEM edge network for the default MPGAN architecture (fe = 96 -> 160 -> 192): host-side
 // launchers.  Kernels: edge_tc_fwd.cuh (forward), edge_tc_bwd.cuh (backward by recompute); shared PTX
 // wrappers, tile layouts and the weight-image kernel: edge_tc_common.cuh.
-#include "edge.cuh"
+#include <cstdlib>
+
+#include "edge_node.cuh"
 
 namespace mpg {
 namespace {
@@ -93,11 +95,36 @@ static int tc_prepare(const EdgeArgs& a, void* persist, void* scratch, bool reus
     const float s = (a.drop.p > 0.f ? 2.f : 1.f) * 0.5f * (1.f + a.alpha);
     const size_t agg_floats = zero_agg != nullptr ? (size_t)a.B * a.N * N2 : 0;   // N2 % 4 == 0; torch buffers are 16-byte aligned
     MPG_CHECK((reinterpret_cast<uintptr_t>(zero_agg) & 15) == 0, "edge_tc: agg must be 16-byte aligned");
-    edge_prepare_kernel<<<cdiv(N1 * 128 + N2 * 192, 256), 256, 0, stream>>>(
-        a.W1, a.b1, a.W2, a.b2, s, img, img + W1_BYTES, total, reinterpret_cast<float4*>(zero_agg), agg_floats / 4);
+    PqFwdArgs pq{};
+    int nb_pq = 0;
+    const long long BNl = (long long)a.B * a.N;
+    // The set-up kernel's last block builds the work list when that is quick (a warp per tile and 32 senders: ~0.15 us
+    // each on one SM); larger problems use the many-block kernel after it.  MPG_STEP_LIST_MAX_UNITS: test knob.
+    long long list_max = 384;
+    if (const char* e = getenv("MPG_STEP_LIST_MAX_UNITS")) list_max = atoll(e);
+    const bool list_in_block = (long long)t.num_tiles * ((a.N + 31) / 32) <= list_max &&
+                               step_list_smem(BNl, a.N) <= 160 * 1024;
+    size_t smem = list_in_block ? step_list_smem(BNl, a.N) : 0;
+    if (a.pq_deferred) {   // P / Q of this call: first layer's node-level ends (edge_node.cuh)
+      pq = PqFwdArgs{a.x, a.ldx, a.Wef - 2 * a.F, a.ldwef, a.b0, const_cast<float*>(a.P), const_cast<float*>(a.Q),
+                     (int)BNl, a.F, a.H0, a.p_tiled};
+      nb_pq = cdiv(BNl, PQ_ROWS);
+      if (pq_fwd_smem(a.F, a.H0) > smem) smem = pq_fwd_smem(a.F, a.H0);
+    }
+    const int nb_prep = cdiv(N1 * 128 + N2 * 192, 256);
+    PrepArgs pr{a.W1, a.b1, a.W2, a.b2, s, img, img + W1_BYTES, reinterpret_cast<float4*>(zero_agg), agg_floats / 4};
+    int stride = (int)(t.num_tiles * 0.381966f) | 1;   // ~ golden-ratio step: consecutive slots are far apart
+    auto gcd = [](int x, int y) { while (y) { const int r = x % y; x = y; y = r; } return x; };
+    while (stride > 1 && gcd(stride, t.num_tiles) != 1) stride -= 2;
+    if (stride < 1) stride = 1;
+    ListArgs ls{a.mask, a.B, a.N, t.num_tiles, const_cast<int2*>(t.steps), total, list_in_block ? 1 : 0, stride};
+    MPG_CUDA(cudaFuncSetAttribute(edge_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    edge_setup_kernel<<<nb_pq + nb_prep + (list_in_block ? 1 : 0), 256, smem, stream>>>(pq, nb_pq, pr, nb_prep, ls);
     MPG_LAUNCH_CHECK();
-    step_list_kernel<<<cdiv(t.num_tiles, 8), 256, 0, stream>>>(a.mask, a.B, a.N, t.num_tiles, const_cast<int2*>(t.steps), total);
-    MPG_LAUNCH_CHECK();
+    if (!list_in_block) {
+      step_list_kernel<<<cdiv(t.num_tiles, 8), 256, 0, stream>>>(a.mask, a.B, a.N, t.num_tiles, const_cast<int2*>(t.steps), total);
+      MPG_LAUNCH_CHECK();
+    }
   }
   // the number of live steps is only known on the device: one CTA per SM, CTAs without steps exit at once
   const long long max_steps = (long long)t.num_tiles * a.N;

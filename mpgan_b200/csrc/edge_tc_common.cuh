@@ -332,42 +332,145 @@ struct TcArgs {
 // weight images: img[n][k] (K-major, SW128) = bf16(scale * W[n][k]) for k < K, bias_hi / bias_lo at
 // k = K, K+1, zero elsewhere.
 // ---------------------------------------------------------------------------------------------------
-// Both weight images of a call, the work-list counter and (forward) the zero fill of the aggregate the kernel
-// accumulates into with reductions: one launch instead of two image kernels and a memset node.
-__global__ void edge_prepare_kernel(const float* __restrict__ W1, const float* __restrict__ b1,
-                                    const float* __restrict__ W2, const float* __restrict__ b2, float scale,
-                                    uint8_t* __restrict__ img1, uint8_t* __restrict__ img2, int* __restrict__ total,
-                                    float4* __restrict__ agg4, size_t agg_n4) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx == 0) *total = 0;   // the work-list counter of the step_list_kernel that follows
+// One set-up launch per call: blocks [0, nb_pq) compute P / Q (pq_fwd_tile), the next nb_prep blocks write both
+// weight images and (forward) zero-fill the aggregate the edge kernel accumulates into with reductions, the last
+// block builds the work list.
+struct PrepArgs {
+  const float* W1; const float* b1; const float* W2; const float* b2;
+  float scale;
+  uint8_t* img1; uint8_t* img2;
+  float4* agg4; size_t agg_n4;
+};
+__device__ __forceinline__ void edge_prepare_block(const PrepArgs& p, int blk, int nblk) {
+  const int idx = blk * 256 + threadIdx.x;
   constexpr int E1 = N1 * 128, E2 = N2 * 192;
   if (idx < E1 + E2) {
     const bool first = idx < E1;
     const int j = first ? idx : idx - E1;
     const int Kpad = first ? 128 : 192, K = first ? K0 : N1, Nout = first ? N1 : N2;
-    const float* W = first ? W1 : W2;
-    const float* bias = first ? b1 : b2;
-    uint8_t* img = first ? img1 : img2;
+    const float* W = first ? p.W1 : p.W2;
+    const float* bias = first ? p.b1 : p.b2;
+    uint8_t* img = first ? p.img1 : p.img2;
     const int n = j / Kpad, k = j % Kpad;
     float v = 0.f;
-    if (k < K) v = W[(size_t)n * K + k] * scale;
+    if (k < K) v = W[(size_t)n * K + k] * p.scale;
     else if (k == K) v = bias[n];
     else if (k == K + 1) v = bias[n] - __bfloat162float(__float2bfloat16_rn(bias[n]));
     const uint32_t off = (uint32_t)(k >> 6) * (uint32_t)Nout * 128u + (uint32_t)n * 128u +
                          ((((uint32_t)(k & 63) >> 3) ^ ((uint32_t)n & 7u)) << 4) + (uint32_t)(k & 7) * 2u;
     *reinterpret_cast<__nv_bfloat16*>(img + off) = __float2bfloat16_rn(v);
   }
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = idx; i < agg_n4; i += stride) agg4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const size_t stride = (size_t)nblk * 256;
+  for (size_t i = idx; i < p.agg_n4; i += stride) p.agg4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // ---------------------------------------------------------------------------------------------------
 // Work list.  A step (128-receiver tile, sender index s) whose sender rows are masked in every jet the
 // tile touches contributes exactly zero to the aggregate and to every gradient: it is dropped here, so
-// padded particles cost nothing.  One warp per tile: ballots compact its live senders (ascending), one
-// atomicAdd reserves the tile's contiguous slice of the list (tiles land in arbitrary order; only the
-// grouping by tile matters to the kernels).  *total must be zero on entry (edge_prepare_kernel does it).
+// padded particles cost nothing.  One block: a warp per tile counts its live senders (ballots), a scan over
+// the tiles of a chunk gives every tile its slice, the warps write the slices (tile-major, sender ascending).
 // ---------------------------------------------------------------------------------------------------
+struct ListArgs {
+  const float* mask; int B, N, num_tiles;
+  int2* steps; int* total;
+  int in_block;   // 1: the set-up kernel's last block builds the list; 0: step_list_kernel does (very large batches)
+  // list slot i holds tile (i * stride) % num_tiles, stride coprime to num_tiles: batches arrive sorted by particle
+  // count, and a CTA (a contiguous slice of the list) whose tiles all have few live senders would spend its time on
+  // tile changes (~2 steps each) while the others wait -- interleaving long and short tiles balances the slices
+  int stride;
+};
+constexpr int LIST_CHUNK = 512;    // tiles per scan chunk
+// shared memory of step_list_block: scan counters, the live-sender words of a chunk's tiles, one byte per four mask
+// elements
+__host__ __device__ inline size_t step_list_smem(long long BN, int N) {
+  return (size_t)(LIST_CHUNK + 8) * sizeof(int) + (size_t)LIST_CHUNK * ((N + 31) / 32) * sizeof(uint32_t) +
+         (size_t)((BN + 3) / 4 + 15) / 16 * 16;
+}
+__device__ __forceinline__ void step_list_block(const ListArgs& l, int* cnt /* shared, step_list_smem bytes */) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int BN = l.B * l.N, N = l.N, R = (N + 31) / 32;
+  uint32_t* live = reinterpret_cast<uint32_t*>(cnt + LIST_CHUNK + 8);   // [LIST_CHUNK][R] live-sender bits of a tile
+  uint8_t* nib = reinterpret_cast<uint8_t*>(live + LIST_CHUNK * R);     // bit (i & 3) of nib[i >> 2]: mask[i] != 0
+  if (l.mask != nullptr) {   // one coalesced pass over the mask; everything below reads shared memory only
+    const int n4 = BN >> 2;
+    if ((reinterpret_cast<uintptr_t>(l.mask) & 15) == 0) {
+      const float4* m4 = reinterpret_cast<const float4*>(l.mask);
+#pragma unroll 4
+      for (int i = threadIdx.x; i < n4; i += 256) {
+        const float4 v = __ldg(m4 + i);
+        nib[i] = (uint8_t)((v.x != 0.f) | ((v.y != 0.f) << 1) | ((v.z != 0.f) << 2) | ((v.w != 0.f) << 3));
+      }
+    } else {
+      for (int i = threadIdx.x; i < n4; i += 256) {
+        const float* m = l.mask + 4 * (size_t)i;
+        nib[i] = (uint8_t)((m[0] != 0.f) | ((m[1] != 0.f) << 1) | ((m[2] != 0.f) << 2) | ((m[3] != 0.f) << 3));
+      }
+    }
+    if (threadIdx.x == 0 && (BN & 3)) {
+      uint8_t v = 0;
+      for (int e = 0; e < (BN & 3); ++e) v |= (uint8_t)((l.mask[4 * (size_t)n4 + e] != 0.f) << e);
+      nib[n4] = v;
+    }
+    __syncthreads();
+  }
+  auto tile_of = [&](int slot) { return (int)(((long long)slot * l.stride) % l.num_tiles); };
+  int base = 0;
+  for (int t0 = 0; t0 < l.num_tiles; t0 += LIST_CHUNK) {
+    const int nt = min(LIST_CHUNK, l.num_tiles - t0);
+    for (int i = warp; i < nt; i += 8) {   // a warp per tile: live-sender words and their count
+      const int tile = tile_of(t0 + i);
+      const int j0 = (tile * TILE) / N, j1 = min(tile * TILE + TILE - 1, BN - 1) / N;
+      int count = 0;
+      for (int r = 0; r < R; ++r) {
+        const int s = 32 * r + lane;
+        bool any = false;
+        if (s < N) {
+          any = l.mask == nullptr;
+          if (!any)
+            for (int j = j0; j <= j1; ++j) {
+              const int e = j * N + s;
+              any |= (nib[e >> 2] >> (e & 3)) & 1;
+            }
+        }
+        const uint32_t b = __ballot_sync(0xffffffffu, any);
+        if (lane == 0) live[i * R + r] = b;
+        count += __popc(b);
+      }
+      if (lane == 0) cnt[i] = count;
+    }
+    __syncthreads();
+    if (warp == 0) {   // exclusive scan of cnt[0, nt) in place, chunk total -> cnt[LIST_CHUNK]
+      int run = 0;
+      for (int i0 = 0; i0 < nt; i0 += 32) {
+        const int v = i0 + lane < nt ? cnt[i0 + lane] : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int u = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += u;
+        }
+        if (i0 + lane < nt) cnt[i0 + lane] = run + inc - v;
+        run += __shfl_sync(0xffffffffu, inc, 31);
+      }
+      if (lane == 0) cnt[LIST_CHUNK] = run;
+    }
+    __syncthreads();
+    for (int i = warp; i < nt; i += 8) {   // the tile's slice: senders ascending
+      int off = base + cnt[i];
+      const int tile = tile_of(t0 + i);
+      for (int r = 0; r < R; ++r) {
+        const uint32_t b = live[i * R + r];
+        if ((b >> lane) & 1u) l.steps[off + __popc(b & ((1u << lane) - 1u))] = make_int2(tile, 32 * r + lane);
+        off += __popc(b);
+      }
+    }
+    base += cnt[LIST_CHUNK];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *l.total = base;
+}
+// the same list from many blocks (one warp per tile, slices reserved with an atomic: tiles land in arbitrary order,
+// only the grouping by tile matters to the kernels); *total must be zero on entry (the set-up kernel does it)
 __global__ void __launch_bounds__(256) step_list_kernel(const float* __restrict__ mask, int B, int N, int num_tiles,
                                                         int2* __restrict__ steps, int* __restrict__ total) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -393,6 +496,19 @@ __global__ void __launch_bounds__(256) step_list_kernel(const float* __restrict_
     const uint32_t b = __ballot_sync(0xffffffffu, f);
     if (f) steps[off + __popc(b & ((1u << lane) - 1u))] = make_int2(tile, s0 + lane);
     off += __popc(b);
+  }
+}
+
+__global__ void __launch_bounds__(256) edge_setup_kernel(PqFwdArgs pq, int nb_pq, PrepArgs pr, int nb_prep, ListArgs ls) {
+  extern __shared__ __align__(16) float setup_sm[];
+  const int b = blockIdx.x;
+  if (b < nb_pq) {
+    pq_fwd_tile(pq, b, setup_sm);
+  } else if (b < nb_pq + nb_prep) {
+    if (!ls.in_block && b == nb_pq && threadIdx.x == 0) *ls.total = 0;   // counter of the step_list_kernel that follows
+    edge_prepare_block(pr, b - nb_pq, nb_prep);
+  } else {
+    step_list_block(ls, reinterpret_cast<int*>(setup_sm));
   }
 }
 #endif  // MPG_TC_WRAPPERS_ONLY

@@ -338,6 +338,35 @@ def test_edge_tc_vs_fp32_kernel(B, N, p):
         close(r1, r0, 2e-2 if name == "agg" else 6e-2, f"edge {name} B={B} N={N} p={p}")
 
 
+@pytest.mark.parametrize("list_kernel", [False, True])
+def test_edge_tc_work_list_paths(list_kernel, monkeypatch):
+    """The work list (which (tile, sender) steps run) built inside the set-up kernel from shared-memory mask bits and
+    by the stand-alone many-block kernel (very large batches; forced here through MPG_STEP_LIST_MAX_UNITS): same
+    result as the fp32 kernels for a mask with holes (not a prefix), odd sizes and an unaligned element count."""
+    import mpgan_b200.ops as O
+    monkeypatch.setenv("MPG_STEP_LIST_MAX_UNITS", "0" if list_kernel else "100000")
+    torch.manual_seed(77)
+    B, N, F = 37, 19, 32            # B*N = 703: not a multiple of 4, tiles span up to 8 jets
+    x0 = torch.randn(B, N, F, device="cuda") * 0.5
+    mask = (torch.rand(B, N, 1, device="cuda") < 0.4).float()
+    mask[3] = 0                      # a jet without particles
+    mask[:, 5] = 0                   # a sender index dead in every jet: its steps must be dropped everywhere
+    ws0 = []
+    for i, o in ((2 * F, 96), (96, 160), (160, 192)):
+        ws0 += [torch.randn(o, i, device="cuda") / i ** 0.5, torch.randn(o, device="cuda") * 0.1]
+    dagg = torch.randn(B, N, 192, device="cuda")
+    res = []
+    for prec in (0, 1):
+        O.set_precision(prec)
+        x = x0.clone().requires_grad_(True)
+        ws = [w.clone().requires_grad_(True) for w in ws0]
+        agg = O.edge_aggregate(x, mask, *ws, p_drop=0.0)
+        agg.backward(dagg)
+        res.append([agg.detach(), x.grad] + [w.grad for w in ws])
+    for name, r0, r1 in zip(["agg", "dx", "dW0", "db0", "dW1", "db1", "dW2", "db2"], res[0], res[1]):
+        close(r1, r0, 2e-2 if name == "agg" else 6e-2, f"edge {name} (work list, list_kernel={list_kernel})")
+
+
 def _fn_reference(agg, x, ws, alpha):
     """fp32 torch restatement of LinearNet(final_linear)(cat(agg, x)) (mpgan/model.py:70-85, 268-279), p = 0."""
     w0, b0, w1, b1, w2, b2 = ws

@@ -83,8 +83,10 @@ def test_graph_replay_matches_eager_steps(golden, prec):
         assert moved > 1e-3, "the steps must change the weights"
         diff = float((res["eager"][i] - res["graph"][i]).norm())
         assert diff <= (0.05 if prec == 0 else 0.15) * moved, (name, diff, moved)   # measured 0.10 at precision 1
-    # RMSprop's running mean of squared D gradients (measured 1.0e-3 at precision 1: the same bf16 re-rounding drift)
-    assert rel_l2(res["graph"][3], res["eager"][3]) <= (1e-3 if prec == 0 else 5e-3), rel_l2(res["graph"][3], res["eager"][3])
+    # RMSprop's running mean of squared D gradients.  precision 1: the aggregate is summed with fp32 reductions whose
+    # order differs from run to run; one ulp there can flip a bf16 rounding downstream, so two runs of the SAME mode
+    # differ by 1e-3 .. 6e-3 (measured over 10 repetitions, two clusters) -- the bound is that run-to-run spread
+    assert rel_l2(res["graph"][3], res["eager"][3]) <= (1e-3 if prec == 0 else 1e-2), rel_l2(res["graph"][3], res["eager"][3])
 
 
 def test_graph_replay_fresh_noise_and_dropout(golden):
