@@ -175,7 +175,7 @@ int launch_edge_tc_bwd(const EdgeArgs& a, void* persist, void* scratch, bool reu
     if (wgrad && launch_bwd_one<BWD_DW2, false>(t, grid, D_SMEM, stream)) return 1;
   }
   if (wgrad) {
-    wgrad_reduce_kernel<<<cdiv(SLAB_FLOATS, 256), 256, 0, stream>>>(t.wslab, grid, a.dW1, a.db1, a.dW2, a.db2);
+    wgrad_reduce_kernel<<<cdiv(SLAB_FLOATS / 4, WR_COLS), WR_COLS * WR_PARTS, 0, stream>>>(t.wslab, grid, a.dW1, a.db1, a.dW2, a.db2);
     MPG_LAUNCH_CHECK();
   }
   return 0;

@@ -871,17 +871,42 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
   if (warp == 16) tmem_dealloc(tmem, TMEM_COLS);
 }
 
-// dW1 / db1 / dW2 / db2 += sum over the CTAs' slabs (coalesced: consecutive threads, consecutive elements)
-__global__ void wgrad_reduce_kernel(const float* __restrict__ slabs, int nslabs, float* __restrict__ dW1,
-                                    float* __restrict__ db1, float* __restrict__ dW2, float* __restrict__ db2) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= SLAB_FLOATS) return;
-  float s = 0.f;
-  for (int c = 0; c < nslabs; ++c) s += slabs[(size_t)c * SLAB_FLOATS + i];
-  float* dst;
-  if (i < SLAB_DB1) dst = dW1 + i;
-  else if (i < SLAB_DW2) dst = db1 + (i - SLAB_DB1);
-  else if (i < SLAB_DB2) dst = dW2 + ((i - SLAB_DW2) % N2) * N1 + (i - SLAB_DW2) / N2;   // slab holds dW2 transposed
-  else dst = db2 + (i - SLAB_DB2);
-  *dst += s;
+// dW1 / db1 / dW2 / db2 += sum over the CTAs' slabs.  27 MB of slabs at N = 30: the loop over slabs must keep many
+// loads in flight, so a block is 32 float4 columns x 8 slab groups (slab c goes to group c % 8), ~19 independent
+// 16-byte loads per thread; the groups are combined in a fixed order (deterministic).
+constexpr int WR_COLS = 32, WR_PARTS = 8;
+__global__ void __launch_bounds__(WR_COLS * WR_PARTS) wgrad_reduce_kernel(const float* __restrict__ slabs, int nslabs,
+                                                                          float* __restrict__ dW1, float* __restrict__ db1,
+                                                                          float* __restrict__ dW2, float* __restrict__ db2) {
+  static_assert(SLAB_FLOATS % 4 == 0, "slabs are read as float4");
+  __shared__ float4 part[WR_PARTS][WR_COLS];
+  const int lane = threadIdx.x & (WR_COLS - 1), p = threadIdx.x / WR_COLS;
+  const int c4 = blockIdx.x * WR_COLS + lane;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c4 < SLAB_FLOATS / 4) {
+#pragma unroll 4
+    for (int c = p; c < nslabs; c += WR_PARTS) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(slabs + (size_t)c * SLAB_FLOATS) + c4);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+  }
+  part[p][lane] = s;
+  __syncthreads();
+  if (p != 0 || c4 >= SLAB_FLOATS / 4) return;
+#pragma unroll
+  for (int k = 1; k < WR_PARTS; ++k) {
+    const float4 v = part[k][lane];
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  const float sv[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int i = 4 * c4 + e;
+    float* dst;
+    if (i < SLAB_DB1) dst = dW1 + i;
+    else if (i < SLAB_DW2) dst = db1 + (i - SLAB_DB1);
+    else if (i < SLAB_DB2) dst = dW2 + ((i - SLAB_DW2) % N2) * N1 + (i - SLAB_DW2) / N2;   // slab holds dW2 transposed
+    else dst = db2 + (i - SLAB_DB2);
+    *dst += sv[e];
+  }
 }

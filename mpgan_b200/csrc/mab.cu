@@ -485,12 +485,10 @@ __device__ __forceinline__ void mma8(float (&c)[4], const uint32_t (&a)[4], cons
 
 // C[32 x 8*NTW*8] = A[32 x K] * W^T,  W [n][k] (B operand column-major = rows of W).  Warp w owns n-tiles
 // w*NTW .. w*NTW+NTW-1; acc[mi][nt][..] follows the m16n8 accumulator layout (row g / g+8, columns 2t, 2t+1).
-// (rows > 16 ? both 16-row m-tiles : the first one only -- ISAB's 10 inducing points, PMA's single seed)
 template <int NTW>
 __device__ __forceinline__ void mma_AWt(float (&acc)[2][NTW][4], const float* __restrict__ A, const float* __restrict__ W,
-                                        int K, int rows) {
+                                        int K) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-  const bool two = rows > 16;
 #pragma unroll
   for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
@@ -502,7 +500,6 @@ __device__ __forceinline__ void mma_AWt(float (&acc)[2][NTW][4], const float* __
     uint32_t a[2][4];
 #pragma unroll
     for (int mi = 0; mi < 2; ++mi) {
-      if (mi == 1 && !two) break;
       const float* ap = A + (mi * 16 + g) * LDT + k0 + t;
       a[mi][0] = tf32(ap[0]); a[mi][1] = tf32(ap[8 * LDT]); a[mi][2] = tf32(ap[4]); a[mi][3] = tf32(ap[8 * LDT + 4]);
     }
@@ -511,15 +508,14 @@ __device__ __forceinline__ void mma_AWt(float (&acc)[2][NTW][4], const float* __
       const float* bp = W + ((warp * NTW + nt) * 8 + g) * LDT + k0 + t;
       const uint32_t b[2] = {__float_as_uint(bp[0]), __float_as_uint(bp[4])};   // weights were rounded at load time
       mma8(acc[0][nt], a[0], b);
-      if (two) mma8(acc[1][nt], a[1], b);
+      mma8(acc[1][nt], a[1], b);
     }
   }
 }
 // C[32 x 64] = A[32 x K] * W,  W [k][n] (reduction index = row of W): dX = dZ W.  Warp w owns n-tile w.
 __device__ __forceinline__ void mma_AW(float (&acc)[2][1][4], const float* __restrict__ A, const float* __restrict__ W,
-                                       int K, int rows) {
+                                       int K) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-  const bool two = rows > 16;
 #pragma unroll
   for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
@@ -530,7 +526,6 @@ __device__ __forceinline__ void mma_AW(float (&acc)[2][1][4], const float* __res
     const uint32_t b[2] = {__float_as_uint(bp[0]), __float_as_uint(bp[4 * LDT])};
 #pragma unroll
     for (int mi = 0; mi < 2; ++mi) {
-      if (mi == 1 && !two) break;
       const float* ap = A + (mi * 16 + g) * LDT + k0 + t;
       const uint32_t a[4] = {tf32(ap[0]), tf32(ap[8 * LDT]), tf32(ap[4]), tf32(ap[8 * LDT + 4])};
       mma8(acc[mi][0], a, b);
@@ -538,12 +533,10 @@ __device__ __forceinline__ void mma_AW(float (&acc)[2][1][4], const float* __res
   }
 }
 // dW[64 x 64] += Z^T X over the 32 rows: dW[m][n] = sum_i Z[i][m] X[i][n].  Warp w owns n-tile w, all four m-tiles.
-__device__ __forceinline__ void mma_ZtX(float (&acc)[4][4], const float* __restrict__ Z, const float* __restrict__ X,
-                                        int rows) {
+__device__ __forceinline__ void mma_ZtX(float (&acc)[4][4], const float* __restrict__ Z, const float* __restrict__ X) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
 #pragma unroll
   for (int k0 = 0; k0 < RMAX; k0 += 8) {
-    if (k0 >= rows) break;   // the tiles' rows beyond `rows` are zero
     const float* bp = X + (k0 + t) * LDT + warp * 8 + g;
     const uint32_t b[2] = {tf32(bp[0]), tf32(bp[4 * LDT])};
 #pragma unroll
@@ -737,7 +730,7 @@ __global__ void __launch_bounds__(NT, 1) mab_fwd_tc_kernel(MabArgs a) {
     const float* Ys = self ? X : Yb + buf * TILE_F;
     {   // Q = x Wq^T + bq
       float acc[2][1][4];
-      mma_AWt<1>(acc, X, W, E, Nq);
+      mma_AWt<1>(acc, X, W, E);
       for_acc<1>(acc, [&](int i, int n, float& v) {
         const float o = i < Nq ? v + bias[n] : 0.f;
         Q[i * LDT + n] = o;
@@ -746,7 +739,7 @@ __global__ void __launch_bounds__(NT, 1) mab_fwd_tc_kernel(MabArgs a) {
     }
     {   // K | V = y Wkv^T + bkv
       float acc[2][2][4];
-      mma_AWt<2>(acc, Ys, W + E * LDT, E, Nk);
+      mma_AWt<2>(acc, Ys, W + E * LDT, E);
       for_acc<2>(acc, [&](int i, int n, float& v) {
         const float o = i < Nk ? v + bias[E + n] : 0.f;
         (n < E ? Kt : V)[i * LDT + (n & (E - 1))] = o;
@@ -779,7 +772,7 @@ __global__ void __launch_bounds__(NT, 1) mab_fwd_tc_kernel(MabArgs a) {
     for (int idx = threadIdx.x; idx < Nq * E; idx += NT) a.o[rq * E + idx] = O[(idx >> 6) * LDT + (idx & 63)];
     {   // h = Dropout(x + o Wout^T + bout)
       float acc[2][1][4];
-      mma_AWt<1>(acc, O, W + 3 * E * LDT, E, Nq);
+      mma_AWt<1>(acc, O, W + 3 * E * LDT, E);
       for_acc<1>(acc, [&](int i, int n, float& v) {
         float o = 0.f;
         if (i < Nq) {
@@ -793,7 +786,7 @@ __global__ void __launch_bounds__(NT, 1) mab_fwd_tc_kernel(MabArgs a) {
     __syncthreads();
     {   // out = Dropout(h + Dropout(lrelu(h Wff^T + bff)))
       float acc[2][1][4];
-      mma_AWt<1>(acc, Hh, W + 4 * E * LDT, E, Nq);
+      mma_AWt<1>(acc, Hh, W + 4 * E * LDT, E);
       for_acc<1>(acc, [&](int i, int n, float& v) {
         if (i < Nq) {
           float f = lrelu(v + bias[4 * E + n], a.alpha);
@@ -891,11 +884,11 @@ __global__ void __launch_bounds__(NT, 1) mab_bwd_tc_kernel(MabArgs a, MabGrads g
     __syncthreads();
     const float* Ys = self ? X : Y;
     // ---- feed-forward: dWff += dz^T h, dbff, da = (g + dz Wff) * keep48 -----------------------------------------------
-    mma_ZtX(gWf, Ff, Hh, Nq);
+    mma_ZtX(gWf, Ff, Hh);
     if (threadIdx.x < E) gbf += colsum(Ff, threadIdx.x);
     {
       float acc[2][1][4];
-      mma_AW(acc, Ff, W + 4 * E * LDT, E, Nq);
+      mma_AW(acc, Ff, W + 4 * E * LDT, E);
       for_acc<1>(acc, [&](int i, int n, float& v) {
         float o = 0.f;
         if (i < Nq) {
@@ -907,11 +900,11 @@ __global__ void __launch_bounds__(NT, 1) mab_bwd_tc_kernel(MabArgs a, MabGrads g
     }
     __syncthreads();
     // ---- out_proj: dWout += da^T o, dbout, do = da Wout -> Ff --------------------------------------------------------------
-    mma_ZtX(gWo, A, Oo, Nq);
+    mma_ZtX(gWo, A, Oo);
     if (threadIdx.x < E) gbo += colsum(A, threadIdx.x);
     {
       float acc[2][1][4];
-      mma_AW(acc, A, W + 3 * E * LDT, E, Nq);
+      mma_AW(acc, A, W + 3 * E * LDT, E);
       __syncthreads();   // dz (Ff) has been read by everyone (dWff product above, this product's operand is A)
       for_acc<1>(acc, [&](int i, int n, float& v) { Ff[i * LDT + n] = i < Nq ? v : 0.f; });
     }
@@ -988,15 +981,15 @@ __global__ void __launch_bounds__(NT, 1) mab_bwd_tc_kernel(MabArgs a, MabGrads g
     }
     __syncthreads();
     // ---- in_proj: weight / bias gradients, dx = da + dq Wq, dy = dk Wk + dv Wv ----------------------------------------------
-    mma_ZtX(gWq, dQ, X, Nq);
-    mma_ZtX(gWk, dK, Ys, Nk);
-    mma_ZtX(gWv, dV, Ys, Nk);
+    mma_ZtX(gWq, dQ, X);
+    mma_ZtX(gWk, dK, Ys);
+    mma_ZtX(gWv, dV, Ys);
     if (threadIdx.x < 3 * E) gbin += colsum(threadIdx.x < E ? dQ : (threadIdx.x < 2 * E ? dK : dV), threadIdx.x & (E - 1));
     {
       float ax[2][1][4], ak[2][1][4], av[2][1][4];
-      mma_AW(ax, dQ, W, E, Nq);
-      mma_AW(ak, dK, W + E * LDT, E, Nk);
-      mma_AW(av, dV, W + 2 * E * LDT, E, Nk);
+      mma_AW(ax, dQ, W, E);
+      mma_AW(ak, dK, W + E * LDT, E);
+      mma_AW(av, dV, W + 2 * E * LDT, E);
       const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gg = lane >> 2, t = lane & 3;
 #pragma unroll
       for (int mi = 0; mi < 2; ++mi)
