@@ -108,9 +108,11 @@ __host__ __device__ __forceinline__ uint32_t drop_word32(const DropCfg& d, uint3
 // The tcgen05 kernels give one thread one pair row x one column "quarter" q of every fe layer, where
 // quarter q is the set of 8-column chunks 4c + q (columns 32c + 8q + [0, 8), c = 0, 1, ...); layer 2 is
 // handled as two halves of H2/2 columns with the same chunking inside each half.  Element i = 8c + e of
-// a thread's slice is column 32c + 8q + e.  Two Philox draws per (pair, quarter) cover the slices:
-// draw 0 -> layer 0 (consumed when the H0 tile is built, two pipeline steps before the rest), draw 1 ->
-// words x,y: layer 1; word z: layer 2 low half; word w: high half.  Inside a 32-bit word, element i
+// a thread's slice is column 32c + 8q + e.  Draw 1 of (pair, quarter) -> words x,y: layer 1; word z: layer 2 low
+// half; word w: high half.  Layer 0: for the default widths (H0 <= 96, H1 <= 160: edge_drop_compact) its 24 bits
+// are bits 0..5 of every byte of word y -- layer 1's elements 32..39 only use bits 6,7 there -- i.e. the layer-0
+// keep word is y << 2 and ONE Philox draw per (pair, quarter) serves all three layers (the draw is the largest
+// single item of the dropout cost in the tcgen05 epilogues); wider layers take layer 0 from draw 0.  Inside a 32-bit word, element i
 // uses bit edge_drop_bitpos(i & 31): the order in which byte-permutes with sign replication (PRMT)
 // turn a word into packed bf16x2 / fp32 keep masks.  The generic kernel evaluates the same function
 // element-wise.
@@ -121,6 +123,7 @@ __host__ __device__ __forceinline__ u4 edge_drop_bits(uint64_t seed, uint64_t pa
   return philox4x32_10((uint32_t)pair, (uint32_t)(pair >> 32), 0xED6E0000u | quarter, draw, (uint32_t)seed,
                        (uint32_t)(seed >> 32));
 }
+__host__ __device__ __forceinline__ bool edge_drop_compact(int H0, int H1) { return H0 <= 96 && H1 <= 160; }
 __host__ __device__ __forceinline__ uint32_t edge_drop_bitpos(int e) {   // e in [0, 32)
   return 8u * (2u * ((uint32_t)(e >> 1) & 1u) + ((uint32_t)e & 1u)) + 7u - (uint32_t)(e >> 2);
 }
@@ -129,6 +132,10 @@ __host__ __device__ __forceinline__ bool edge_drop_keep(uint64_t seed, uint64_t 
   const int cc = layer == 2 ? col % (H2 / 2) : col;      // column inside the slice's tile (half)
   const int q = (cc >> 3) & 3;
   const int i = 8 * (cc >> 5) + (cc & 7);
+  if (layer == 0 && edge_drop_compact(H0, H1)) {
+    const u4 r = edge_drop_bits(seed, pair, (uint32_t)q, 1u);
+    return (r.y >> (edge_drop_bitpos(i) - 2u)) & 1u;
+  }
   const uint32_t draw = layer == 0 ? 0u : 1u;
   const int wsel = layer == 2 ? 2 + col / (H2 / 2) : (i >> 5);
   const u4 r = edge_drop_bits(seed, pair, (uint32_t)q, draw);

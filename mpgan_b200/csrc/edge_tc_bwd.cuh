@@ -389,6 +389,7 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
       // record of the step whose H0' was built last (tile, sender, this row's mask multiplier)
       int n_tile = -1, n_s = 0;
       float n_m = 0.f;
+      u4 n_kb{0, 0, 0, 0};                    // DROP: that step's Philox draw (layer 0 = y << 2; x,y: layer 1; z,w: layer 2)
       auto write_onehot = [&](int tile) {   // CHAIN: constant-1 columns 96,97 and one-hot jet columns 98+j of the H0' tile
         if (q == 0) {
           const int r = tile * TILE + row;
@@ -444,7 +445,10 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
           asm volatile("ld.shared.f32 %0, [%1];" : "=f"(mv) : "r"(stage + h_moff));
           n_tile = h_tile; n_s = h_s; n_m = h_valid ? mv : 0.f;
         }
-        if (DROP) k0w_next = edge_drop_bits(drop.seed, (uint64_t)h_r * N + h_s, q, 0).x;
+        if (DROP) {
+          n_kb = edge_drop_bits(drop.seed, (uint64_t)h_r * N + h_s, q, 1);
+          k0w_next = n_kb.y << 2;
+        }
         const uint32_t qa = stage + h_qoff;
         s0_next = 0;
 #pragma unroll
@@ -479,6 +483,7 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
       // DW2 builds two steps ahead: records of steps it+1 (p1_*) and it+2 (n_*)
       int p1_tile = -1, p1_s = 0;
       float p1_m = 0.f;
+      u4 kb{0, 0, 0, 0}, p1_kb{0, 0, 0, 0};   // draws of the current step / of step it+1 (DW2)
       const bool dagg32 = (reinterpret_cast<uintptr_t>(a.dagg) & 31) == 0;
       auto enter_tile = [&]() {   // rows of the tile the current step belongs to; their dAgg
         const int r = c_tile * TILE + row;
@@ -537,12 +542,13 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
       build_h0(0);
       MPG_TP(13);
       c_tile = n_tile; c_s = n_s; c_m = n_m;
+      kb = n_kb;
       s0 = s0_next;
       k0w = k0w_next;
       if (!CH && nsteps > 1) {   // DW2: layer 1 runs one step ahead
         mbar_wait(bar0 + BwdBars::doneA, 0);
         build_h0(1);
-        p1_tile = n_tile; p1_s = n_s; p1_m = n_m;
+        p1_tile = n_tile; p1_s = n_s; p1_m = n_m; p1_kb = n_kb;
       }
 
       int p_j0 = 0, p_nj = 0, p_s = 0;   // CHAIN: the step whose per-jet dQ sums sit in RB[0,96)
@@ -563,8 +569,6 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
       for (int it = 0; it < nsteps; ++it) {
         const uint32_t par = it & 1;
         const float mfac = c_m;
-        u4 kb{0, 0, 0, 0};
-        if (DROP) kb = edge_drop_bits(drop.seed, (uint64_t)c_r * N + c_s, q, 1);
 
         // ---- E1: D1 -> H1' (+ sign words): chunks 0..2, then 3..4 (24 / 16 live values) -----------------------------
         uint32_t s1[2] = {0, 0};
@@ -776,6 +780,7 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
           MPG_TRW(it, 10);
           s0 = s0_next;
           k0w = k0w_next;
+          kb = n_kb;                          // draw of step it+1 (build_h0(it + 1) ran above)
           // remember where this step's dQ sums belong, then advance
           p_j0 = (c_tile * TILE) / N;
           p_nj = min(c_tile * TILE + TILE - 1, BN - 1) / N - p_j0 + 1;
@@ -815,7 +820,8 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
               c_tile = p1_tile;
               enter_tile();
             }
-            p1_tile = n_tile; p1_s = n_s; p1_m = n_m;
+            kb = p1_kb;
+            p1_tile = n_tile; p1_s = n_s; p1_m = n_m; p1_kb = n_kb;
           }
         }
       }

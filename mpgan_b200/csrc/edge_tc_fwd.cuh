@@ -292,6 +292,7 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
     // built during iteration it, so three are live
     int s_tile[3] = {0, 0, 0}, s_snd[3] = {0, 0, 0}, s_row[3] = {0, 0, 0};
     float s_m[3] = {0.f, 0.f, 0.f};
+    u4 s_kb[3] = {};   // DROP: the step's Philox draw (layer 0 = y << 2, consumed at once; the rest two steps later)
     auto tile_rows = [&](int tile) {   // this thread's row of `tile`: index, stage offsets, its P values
       h_loaded = tile;
       const int r = tile * TILE + row;
@@ -326,7 +327,10 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
         s_tile[2] = h_tile; s_snd[2] = h_s; s_row[2] = h_r; s_m[2] = h_valid ? mv : 0.f;
       }
       uint32_t kw = 0;
-      if (DROP) kw = edge_drop_bits(drop.seed, (uint64_t)h_r * N + h_s, q, 0).x;
+      if (DROP) {
+        s_kb[2] = edge_drop_bits(drop.seed, (uint64_t)h_r * N + h_s, q, 1);
+        kw = s_kb[2].y << 2;
+      }
       const uint32_t qa = stage + h_qoff;
 #pragma unroll
       for (int c = 0; c < Q0 / 8; ++c) {
@@ -354,7 +358,10 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
     };
     auto rotate = [&]() {   // records of steps it+1, it+2 become those of it, it+1
 #pragma unroll
-      for (int i = 0; i < 2; ++i) { s_tile[i] = s_tile[i + 1]; s_snd[i] = s_snd[i + 1]; s_row[i] = s_row[i + 1]; s_m[i] = s_m[i + 1]; }
+      for (int i = 0; i < 2; ++i) {
+        s_tile[i] = s_tile[i + 1]; s_snd[i] = s_snd[i + 1]; s_row[i] = s_row[i + 1]; s_m[i] = s_m[i + 1];
+        if (DROP) s_kb[i] = s_kb[i + 1];
+      }
     };
 
     // ---- tile state: `cur` = tile of step `it` (mask / dropout rows), `acc` = tile the accumulators belong to
@@ -407,9 +414,12 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
       tmem_ld8x3(tl + dcol, v);
 #pragma unroll
       for (int e = 0; e < QH; ++e) {
-        float m = e_m;
-        if (DROP) m = __uint_as_float(__float_as_uint(m) & keep_one(kw, e));
-        ac[e] = fmaf(lrelu_g(v[e], cg), m, ac[e]);
+        const float g = lrelu_g(v[e], cg);
+        if (DROP) {   // a compile-time bit of the keep word: one predicate-setting LOP3 + a predicated FFMA
+          if (kw & (1u << edge_drop_bitpos(e))) ac[e] = fmaf(g, e_m, ac[e]);
+        } else {
+          ac[e] = fmaf(g, e_m, ac[e]);
+        }
       }
     };
     uint32_t kz = 0, kwd = 0;   // layer-2 keep words of the step whose E1 ran last (consumed one iteration later)
@@ -425,6 +435,7 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
       mbar_wait(bar_d1, 0);   // M1(0) done: the H0' tile may be overwritten
       build_h0(1);
       s_tile[1] = s_tile[2]; s_snd[1] = s_snd[2]; s_row[1] = s_row[2]; s_m[1] = s_m[2];
+      if (DROP) s_kb[1] = s_kb[2];
     }
 
     for (int it = 0; it < nsteps; ++it) {
@@ -442,10 +453,7 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
       }
       // ---- E1(it): D1 -> H1' ---------------------------------------------------------------------
       uint32_t kx = 0, ky = 0, kz_n = 0, kw_n = 0;
-      if (DROP) {
-        const u4 b = edge_drop_bits(drop.seed, (uint64_t)cur_row * N + cur_s, q, 1);
-        kx = b.x; ky = b.y; kz_n = b.z; kw_n = b.w;
-      }
+      if (DROP) { kx = s_kb[0].x; ky = s_kb[0].y; kz_n = s_kb[0].z; kw_n = s_kb[0].w; }   // drawn when H0'(it) was built
       mbar_wait(bar_d1 + 8 * (it & 1), (it >> 1) & 1);
       MPG_TR(it, 3);
       tc_fence_after();
