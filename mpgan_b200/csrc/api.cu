@@ -443,7 +443,7 @@ static int edge_bwd_impl(const EdgeExtra& ex, const void* saved, size_t saved_by
   const bool precise = precision == 0;
   // node-level tail of the factorised first layer
   if (pq_supported(F, H0)) {
-    if (launch_pq_bwd(w.dP, w.dQ, x, ldx, w0, a.ldwef, dx, lddx, dw0, db0, (int)BN, F, H0, s, a.p_tiled != 0)) return 1;
+    if (launch_pq_bwd(w.dP, w.dQ, x, ldx, w0, a.ldwef, dx, lddx, dw0, db0, (int)BN, F, H0, s, a.p_tiled != 0, tc_bwd)) return 1;
   } else {
     GemmEpi acc;
     acc.accumulate = 1;

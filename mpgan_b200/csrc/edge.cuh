@@ -72,7 +72,8 @@ bool pq_supported(int F, int H0);
 int launch_pq_fwd(const float* x, int ldx, const float* W0, int ldw, const float* b0, float* P, float* Q, int BN,
                   int F, int H0, cudaStream_t stream, bool p_tiled = false);
 int launch_pq_bwd(const float* dP, const float* dQ, const float* x, int ldx, const float* W0, int ldw, float* dx,
-                  int lddx, float* dW0, float* db0, int BN, int F, int H0, cudaStream_t stream, bool p_tiled = false);
+                  int lddx, float* dW0, float* db0, int BN, int F, int H0, cudaStream_t stream, bool p_tiled = false,
+                  bool tf32 = false);   // tf32: TF32 tensor-core products (precision 1)
 // element (row r, column k) of a tiled P / dP buffer (EdgeArgs::p_tiled), H0 columns, 128-row tiles
 __host__ __device__ inline size_t p_tiled_index(size_t r, int k, int H0) {
   return (r >> 7) * 128 * (size_t)H0 + ((size_t)(k >> 2) * 128 + (r & 127)) * 4 + (k & 3);

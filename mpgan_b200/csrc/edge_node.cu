@@ -129,6 +129,109 @@ __global__ void __launch_bounds__(NT) pq_bwd_kernel(const float* __restrict__ dP
   }
 }
 
+// ---- the same products on tensor cores (precision 1: TF32 mma.sync.m16n8k8, fp32 accumulation) -------------------------
+// The fp32 kernel above is FMA-bound (1.6 MFMA per 64-row block); here the block is bound by its loads.
+//   dx[64 x F]    = [dP | dQ][64 x 2*H0] * [Wa ; Wb][2*H0 x F]        16-row x 8-column tiles, K = 2*H0
+//   dW0[2*H0 x F] += [dP | dQ]^T[2*H0 x 64] * x[64 x F]               K = the block's 64 rows
+// Operand tiles sit in shared memory with row pitches that keep the fragment loads conflict-free (or 2-way).
+__device__ __forceinline__ uint32_t to_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__host__ __device__ inline int pq_f8(int F) { return (F + 7) & ~7; }
+size_t bwd_tc_smem(int F, int H0) {
+  const int F8 = pq_f8(F);
+  return (size_t)(2 * F8 * (H0 + 4) + BWD_ROWS * (F8 + 8) + BWD_ROWS * (2 * H0 + 4)) * sizeof(float);
+}
+__global__ void __launch_bounds__(NT) pq_bwd_tc_kernel(const float* __restrict__ dP, const float* __restrict__ dQ,
+                                                       const float* __restrict__ x, int ldx, const float* __restrict__ W0,
+                                                       int ldw, float* __restrict__ dx, int lddx, float* __restrict__ dW0,
+                                                       float* __restrict__ db0, int BN, int F, int H0, int p_tiled) {
+  extern __shared__ __align__(16) float sm[];
+  const int F8 = pq_f8(F), H0P = H0 + 4, FP = F8 + 8, DP = 2 * H0 + 4;
+  float* Ws = sm;                          // [2*F8][H0P]  Ws[h*F8 + f][k] = W0[k][h*F + f], zero rows for f >= F
+  float* ds = Ws + 2 * F8 * H0P;           // [BWD_ROWS][DP]  row = [dP | dQ]
+  float* xs = ds + BWD_ROWS * DP;          // [BWD_ROWS][FP]  zero columns for f >= F
+  const int r0 = blockIdx.x * BWD_ROWS;
+  for (int idx = threadIdx.x; idx < 2 * F8 * H0; idx += NT) {
+    const int k = idx / (2 * F8), c = idx % (2 * F8), h = c >= F8 ? 1 : 0, f = c - h * F8;
+    Ws[c * H0P + k] = f < F ? W0[(size_t)k * ldw + h * F + f] : 0.f;
+  }
+  for (int idx = threadIdx.x; idx < BWD_ROWS * F8; idx += NT) {
+    const int r = idx / F8, f = idx % F8;
+    xs[r * FP + f] = (r0 + r < BN && f < F) ? x[(size_t)(r0 + r) * ldx + f] : 0.f;
+  }
+  const int ng = H0 / 4;
+  for (int idx = threadIdx.x; idx < ng * BWD_ROWS; idx += NT) {
+    const int g = idx / BWD_ROWS, r = idx % BWD_ROWS;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r0 + r < BN)
+      v = *reinterpret_cast<const float4*>(dP + (p_tiled ? p_tiled_index(r0 + r, 4 * g, H0) : (size_t)(r0 + r) * H0 + 4 * g));
+    *reinterpret_cast<float4*>(ds + r * DP + 4 * g) = v;
+  }
+  for (int idx = threadIdx.x; idx < BWD_ROWS * ng; idx += NT) {
+    const int r = idx / ng, g = idx % ng;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r0 + r < BN) v = *reinterpret_cast<const float4*>(dQ + (size_t)(r0 + r) * H0 + 4 * g);
+    *reinterpret_cast<float4*>(ds + r * DP + H0 + 4 * g) = v;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int nnt = F8 / 8;                  // 8-column tiles of the F axis
+  // ---- dx: (BWD_ROWS / 16) x nnt tiles over the warps ---------------------------------------------------------------
+  for (int tile = warp; tile < (BWD_ROWS / 16) * nnt; tile += NT / 32) {
+    const int m0 = (tile / nnt) * 16, n0 = (tile % nnt) * 8;
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int h = 0; h < 2; ++h) {
+      const float* A = ds + h * H0;                       // dP or dQ columns
+      const float* B = Ws + (size_t)(h * F8 + n0 + g) * H0P;   // B[k][n] = Ws[n][k]
+      for (int k0 = 0; k0 < H0; k0 += 8) {
+        const uint32_t a[4] = {to_tf32(A[(m0 + g) * DP + k0 + t]), to_tf32(A[(m0 + g + 8) * DP + k0 + t]),
+                               to_tf32(A[(m0 + g) * DP + k0 + t + 4]), to_tf32(A[(m0 + g + 8) * DP + k0 + t + 4])};
+        const uint32_t b[2] = {to_tf32(B[k0 + t]), to_tf32(B[k0 + t + 4])};
+        mma_tf32(c, a, b);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int r = r0 + m0 + g + 8 * (e >> 1), f = n0 + 2 * t + (e & 1);
+      if (r < BN && f < F) dx[(size_t)r * lddx + f] = c[e];
+    }
+  }
+  if (dW0 == nullptr) return;   // input gradient only
+  // ---- dW0: (2*H0 / 16) x nnt tiles; A[m = column of [dP | dQ]][k = row] is ds read transposed ---------------------------
+  for (int tile = warp; tile < (2 * H0 / 16) * nnt; tile += NT / 32) {
+    const int m0 = (tile / nnt) * 16, n0 = (tile % nnt) * 8;
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+    for (int k0 = 0; k0 < BWD_ROWS; k0 += 8) {
+      const uint32_t a[4] = {to_tf32(ds[(k0 + t) * DP + m0 + g]), to_tf32(ds[(k0 + t) * DP + m0 + g + 8]),
+                             to_tf32(ds[(k0 + t + 4) * DP + m0 + g]), to_tf32(ds[(k0 + t + 4) * DP + m0 + g + 8])};
+      const uint32_t b[2] = {to_tf32(xs[(k0 + t) * FP + n0 + g]), to_tf32(xs[(k0 + t + 4) * FP + n0 + g])};
+      mma_tf32(c, a, b);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int dc = m0 + g + 8 * (e >> 1), f = n0 + 2 * t + (e & 1);   // column of [dP | dQ], input feature
+      if (f < F) {
+        const int k = dc < H0 ? dc : dc - H0;
+        atomicAdd(dW0 + (size_t)k * ldw + (dc < H0 ? f : F + f), c[e]);
+      }
+    }
+  }
+  for (int k = threadIdx.x; k < H0; k += NT) {
+    float acc = 0.f;
+    for (int r = 0; r < BWD_ROWS; ++r) acc += ds[r * DP + k];
+    atomicAdd(db0 + k, acc);
+  }
+}
+
 size_t bwd_smem(int F, int H0) {
   return (size_t)(2 * F * (H0 + 4) + BWD_ROWS * (F + 1) + BWD_ROWS * (2 * H0 + 4)) * sizeof(float);
 }
@@ -152,7 +255,15 @@ int launch_pq_fwd(const float* x, int ldx, const float* W0, int ldw, const float
 }
 
 int launch_pq_bwd(const float* dP, const float* dQ, const float* x, int ldx, const float* W0, int ldw, float* dx,
-                  int lddx, float* dW0, float* db0, int BN, int F, int H0, cudaStream_t stream, bool p_tiled) {
+                  int lddx, float* dW0, float* db0, int BN, int F, int H0, cudaStream_t stream, bool p_tiled, bool tf32) {
+  if (tf32 && H0 % 16 == 0) {
+    const size_t smem = bwd_tc_smem(F, H0);
+    MPG_CUDA(cudaFuncSetAttribute(pq_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pq_bwd_tc_kernel<<<cdiv(BN, BWD_ROWS), NT, smem, stream>>>(dP, dQ, x, ldx, W0, ldw, dx, lddx, dW0, db0, BN, F, H0,
+                                                               p_tiled ? 1 : 0);
+    MPG_LAUNCH_CHECK();
+    return 0;
+  }
   const size_t smem = bwd_smem(F, H0);
   MPG_CUDA(cudaFuncSetAttribute(pq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   pq_bwd_kernel<<<cdiv(BN, BWD_ROWS), NT, smem, stream>>>(dP, dQ, x, ldx, W0, ldw, dx, lddx, dW0, db0, BN, F, H0, p_tiled ? 1 : 0);
