@@ -159,28 +159,46 @@ __global__ void __launch_bounds__(NT) pq_bwd_tc_kernel(const float* __restrict__
   float* ds = Ws + 2 * F8 * H0P;           // [BWD_ROWS][DP]  row = [dP | dQ]
   float* xs = ds + BWD_ROWS * DP;          // [BWD_ROWS][FP]  zero columns for f >= F
   const int r0 = blockIdx.x * BWD_ROWS;
-  for (int idx = threadIdx.x; idx < 2 * F8 * H0; idx += NT) {
-    const int k = idx / (2 * F8), c = idx % (2 * F8), h = c >= F8 ? 1 : 0, f = c - h * F8;
-    Ws[c * H0P + k] = f < F ? W0[(size_t)k * ldw + h * F + f] : 0.f;
-  }
-  for (int idx = threadIdx.x; idx < BWD_ROWS * F8; idx += NT) {
-    const int r = idx / F8, f = idx % F8;
-    xs[r * FP + f] = (r0 + r < BN && f < F) ? x[(size_t)(r0 + r) * ldx + f] : 0.f;
-  }
   const int ng = H0 / 4;
-  for (int idx = threadIdx.x; idx < ng * BWD_ROWS; idx += NT) {
-    const int g = idx / BWD_ROWS, r = idx % BWD_ROWS;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r0 + r < BN)
-      v = *reinterpret_cast<const float4*>(dP + (p_tiled ? p_tiled_index(r0 + r, 4 * g, H0) : (size_t)(r0 + r) * H0 + 4 * g));
-    *reinterpret_cast<float4*>(ds + r * DP + 4 * g) = v;
+  {   // gradient rows first (the largest item), 16 bytes per load, every load of a thread in flight together
+    constexpr int U = 6;
+    for (int i0 = threadIdx.x; i0 < 2 * ng * BWD_ROWS; i0 += NT * U) {
+      float4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int idx = i0 + u * NT;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (idx < ng * BWD_ROWS) {                       // dP: tiled -> 64 consecutive rows of a column group are contiguous
+          const int g = idx / BWD_ROWS, r = idx % BWD_ROWS;
+          if (r0 + r < BN)
+            v[u] = *reinterpret_cast<const float4*>(dP + (p_tiled ? p_tiled_index(r0 + r, 4 * g, H0) : (size_t)(r0 + r) * H0 + 4 * g));
+        } else if (idx < 2 * ng * BWD_ROWS) {            // dQ: row-major
+          const int j = idx - ng * BWD_ROWS, r = j / ng, g = j % ng;
+          if (r0 + r < BN) v[u] = *reinterpret_cast<const float4*>(dQ + (size_t)(r0 + r) * H0 + 4 * g);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int idx = i0 + u * NT;
+        if (idx < ng * BWD_ROWS) {
+          const int g = idx / BWD_ROWS, r = idx % BWD_ROWS;
+          *reinterpret_cast<float4*>(ds + r * DP + 4 * g) = v[u];
+        } else if (idx < 2 * ng * BWD_ROWS) {
+          const int j = idx - ng * BWD_ROWS, r = j / ng, g = j % ng;
+          *reinterpret_cast<float4*>(ds + r * DP + H0 + 4 * g) = v[u];
+        }
+      }
+    }
   }
-  for (int idx = threadIdx.x; idx < BWD_ROWS * ng; idx += NT) {
-    const int r = idx / ng, g = idx % ng;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r0 + r < BN) v = *reinterpret_cast<const float4*>(dQ + (size_t)(r0 + r) * H0 + 4 * g);
-    *reinterpret_cast<float4*>(ds + r * DP + H0 + 4 * g) = v;
-  }
+  batched_fill<8, NT>(2 * F8 * H0,
+      [&](int idx) {
+        const int k = idx / (2 * F8), c = idx % (2 * F8), h = c >= F8 ? 1 : 0, f = c - h * F8;
+        return f < F ? W0[(size_t)k * ldw + h * F + f] : 0.f;
+      },
+      [&](int idx, float v) { const int k = idx / (2 * F8), c = idx % (2 * F8); Ws[c * H0P + k] = v; });
+  batched_fill<8, NT>(BWD_ROWS * F8,
+      [&](int idx) { const int r = idx / F8, f = idx % F8; return (r0 + r < BN && f < F) ? x[(size_t)(r0 + r) * ldx + f] : 0.f; },
+      [&](int idx, float v) { const int r = idx / F8, f = idx % F8; xs[r * FP + f] = v; });
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int nnt = F8 / 8;                  // 8-column tiles of the F axis
@@ -249,7 +267,7 @@ int launch_pq_fwd(const float* x, int ldx, const float* W0, int ldw, const float
   const size_t smem = pq_fwd_smem(F, H0);
   MPG_CUDA(cudaFuncSetAttribute(pq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   PqFwdArgs a{x, ldx, W0, ldw, b0, P, Q, BN, F, H0, p_tiled ? 1 : 0};
-  pq_fwd_kernel<<<cdiv(BN, PQ_ROWS), PQ_NT, smem, stream>>>(a);
+  pq_fwd_kernel<<<2 * cdiv(BN, PQ_ROWS), PQ_NT, smem, stream>>>(a);
   MPG_LAUNCH_CHECK();
   return 0;
 }

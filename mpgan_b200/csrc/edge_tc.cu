@@ -108,7 +108,7 @@ static int tc_prepare(const EdgeArgs& a, void* persist, void* scratch, bool reus
     if (a.pq_deferred) {   // P / Q of this call: first layer's node-level ends (edge_node.cuh)
       pq = PqFwdArgs{a.x, a.ldx, a.Wef - 2 * a.F, a.ldwef, a.b0, const_cast<float*>(a.P), const_cast<float*>(a.Q),
                      (int)BNl, a.F, a.H0, a.p_tiled};
-      nb_pq = cdiv(BNl, PQ_ROWS);
+      nb_pq = 2 * cdiv(BNl, PQ_ROWS);   // a block per (128-row tile, P | Q)
       if (pq_fwd_smem(a.F, a.H0) > smem) smem = pq_fwd_smem(a.F, a.H0);
     }
     const int nb_prep = cdiv(N1 * 128 + N2 * 192, 256);

@@ -332,7 +332,7 @@ struct TcArgs {
 // weight images: img[n][k] (K-major, SW128) = bf16(scale * W[n][k]) for k < K, bias_hi / bias_lo at
 // k = K, K+1, zero elsewhere.
 // ---------------------------------------------------------------------------------------------------
-// One set-up launch per call: blocks [0, nb_pq) compute P / Q (pq_fwd_tile), the next nb_prep blocks write both
+// One set-up launch per call: blocks [0, nb_pq) compute P / Q (pq_fwd_tile: job = 2 * tile + output), the next nb_prep blocks write both
 // weight images and (forward) zero-fill the aggregate the edge kernel accumulates into with reductions, the last
 // block builds the work list.
 struct PrepArgs {
