@@ -213,6 +213,17 @@ int mpg_edge_bwd2(const float* x, int ldx, const float* u, int ldu, const float*
                   size_t workspace_bytes, const float* dagg, float* tagg, float* gmask, float* dw0, float* dw1, float* dw2,
                   void* stream);
 
+/* ---- receiver compaction (tcgen05 edge path; exact for the discriminator, mpgan/model.py:810-822,881-884: padded
+ * particles are masked as senders and multiplied by the mask at the pooling, so nothing they receive is ever used).
+ * mpg_compact_map writes the map (mpg_compact_map_ints(B, N) ints; `scratch`: B ints) that packs the rows with
+ * mask != 0 into 128-row tiles; mpg_edge_set_compaction(map) makes THIS THREAD's following mpg_edge_fwd / mpg_edge_bwd /
+ * mpg_edge_bwd_saved calls build their tiles from it (NULL: off).  Tensors keep their padded [B*N, .] layout; rows
+ * outside every tile get agg = 0 and dx = 0.  Ignored on the fp32 path.  Do not use for a generator (its padded rows are
+ * part of its output, mpgan/model.py:723-752). */
+size_t mpg_compact_map_ints(int B, int N);
+int mpg_compact_map(const float* mask, int B, int N, int* cmap, int* scratch, void* stream);
+int mpg_edge_set_compaction(const int* cmap);
+
 /* ---- mask-channel gradients (the discriminator's mask = x[..., -1] + 0.5 is differentiable, mpgan/model.py:881) --
  * mpg_split_mask_bwd: dx [rows, ldx] = 0 except dx[r, ldx-1] = dmask[r];  mpg_pool_dmask: dmask[b,i] = scale *
  * <h[b,i,:], dout[b,:]> (gradient of the masked sum pool w.r.t. the mask). */

@@ -68,6 +68,9 @@ _SIGS = {
     "mpg_edge_bwd2_workspace_bytes": (C.c_size_t, [_i] * 6),
     "mpg_edge_bwd2": (C.c_int, [_f, _i, _f, _i, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _fl, _fl, _u64,
                                 _f, _f, _sz, _f, _f, _f, _f, _f, _f, _f]),
+    "mpg_compact_map_ints": (C.c_size_t, [_i, _i]),
+    "mpg_compact_map": (C.c_int, [_f, _i, _i, _f, _f, _f]),
+    "mpg_edge_set_compaction": (C.c_int, [_f]),
     "mpg_split_mask_bwd": (C.c_int, [_f, _f, _i, _sz, _f]),
     "mpg_pool_dmask": (C.c_int, [_f, _f, _f, _i, _i, _i, _fl, _f]),
     "mpg_gen_postprocess": (C.c_int, [_f, _i, _f, _i, _sz, _i, C.POINTER(C.c_float), C.POINTER(C.c_float),

@@ -75,7 +75,8 @@ EdgeWs carve_edge_ws(void* base, int B, int N, int F, int H0, int H1, int H2) {
     return r;
   };
   const size_t BN = (size_t)B * N;
-  const size_t BNT = (BN + 127) / 128 * 128;   // P / dP may be stored per 128-row tile (EdgeArgs::p_tiled)
+  // P / dP may be stored per 128-row tile (EdgeArgs::p_tiled), of the compacted tile space when receivers are compacted
+  const size_t BNT = (size_t)compact_tiles_max(B, N) * 128;
   w.P = take(BNT * H0);
   w.Q = take(BN * H0);
   w.W1t = take((size_t)H0 * H1);
@@ -106,6 +107,9 @@ struct EdgeExtra {
   bool fp32_only = false;   // entry points that always run the fp32 kernels
   bool any() const { return fp32_only || nbr != nullptr || dmask != nullptr || lc != nullptr; }
 };
+
+// receiver compaction map of this thread's next edge calls (mpg_edge_set_compaction); null: off
+static thread_local const int* g_cmap = nullptr;
 
 int edge_common(EdgeArgs& a, EdgeWs& w, const float* x, int ldx, const float* mask, const float* w0,
                 const float* b0, const float* w1, const float* b1, const float* w2, const float* b2, int B, int N,
@@ -144,10 +148,20 @@ int edge_common(EdgeArgs& a, EdgeWs& w, const float* x, int ldx, const float* ma
   // both ends of P / dP are the pq kernels and the tcgen05 kernels: tile-major storage (the backward takes the same
   // decision from the same arguments, so a saved forward workspace is read the way it was written)
   a.p_tiled = (*use_tc && (edge_tc_features() & 2) && pq_supported(F, H0)) ? 1 : 0;
-  if (saved != nullptr) return 0;
+  if (saved != nullptr) {
+    if (a.p_tiled && g_cmap != nullptr) {   // the forward that filled `saved` ran compacted: same map
+      a.cmap = g_cmap;
+      a.ctiles_max = compact_tiles_max(B, N);
+    }
+    return 0;
+  }
   // factorised first layer: W0 [x_i ; x_j ; ef] = Wa x_i + Wb x_j + Wef ef   (node-level GEMMs)
   a.pq_deferred = a.p_tiled;
   a.b0 = b0;
+  if (a.p_tiled && g_cmap != nullptr) {   // receiver compaction requested for this thread's edge calls (tcgen05 path only)
+    a.cmap = g_cmap;
+    a.ctiles_max = compact_tiles_max(B, N);
+  }
   if (a.pq_deferred) {
     // computed by the tcgen05 launcher's set-up kernel
   } else if (pq_supported(F, H0)) {
@@ -443,7 +457,11 @@ static int edge_bwd_impl(const EdgeExtra& ex, const void* saved, size_t saved_by
   const bool precise = precision == 0;
   // node-level tail of the factorised first layer
   if (pq_supported(F, H0)) {
-    if (launch_pq_bwd(w.dP, w.dQ, x, ldx, w0, a.ldwef, dx, lddx, dw0, db0, (int)BN, F, H0, s, a.p_tiled != 0, tc_bwd)) return 1;
+    if (a.cmap != nullptr)   // rows outside every tile (padded particles) get no gradient
+      MPG_CUDA(cudaMemset2DAsync(dx, (size_t)lddx * sizeof(float), 0, (size_t)F * sizeof(float), BN, s));
+    if (launch_pq_bwd(w.dP, w.dQ, x, ldx, w0, a.ldwef, dx, lddx, dw0, db0, (int)BN, F, H0, s, a.p_tiled != 0, tc_bwd,
+                      tc_bwd ? a.cmap : nullptr, a.ctiles_max))
+      return 1;
   } else {
     GemmEpi acc;
     acc.accumulate = 1;
@@ -677,6 +695,15 @@ int mpg_gen_postprocess(const float* jets, int ldj, float* out, int ldo, size_t 
 int mpg_cond_columns(const float* x, int ldx, const float* cond, int C, float* out, size_t rows, int F, int B, void* stream) {
   MPG_CHECK(C > 0 && F > 0 && B > 0, "cond_columns: bad sizes");
   return launch_cond_columns(x, ldx, cond, C, out, rows, F, B, (cudaStream_t)stream);
+}
+size_t mpg_compact_map_ints(int B, int N) { return compact_map_ints(B, N); }
+int mpg_compact_map(const float* mask, int B, int N, int* cmap, int* scratch, void* stream) {
+  MPG_CHECK(mask != nullptr && cmap != nullptr && scratch != nullptr && B > 0 && N > 0, "compact_map: bad arguments");
+  return launch_compact_map(mask, B, N, cmap, scratch, (cudaStream_t)stream);
+}
+int mpg_edge_set_compaction(const int* cmap) {
+  g_cmap = cmap;
+  return 0;
 }
 int mpg_split_mask_bwd(const float* dmask, float* dx, int ldx, size_t rows, void* stream) {
   return launch_split_mask_bwd(dmask, dx, ldx, rows, (cudaStream_t)stream);

@@ -20,6 +20,16 @@ struct EdgeArgs {
   // the weight images and the work list, one launch) from x, W0 (= Wef - 2F, row stride ldwef) and b0
   int pq_deferred;
   const float* b0;
+  // Receiver compaction (tcgen05 path, opt-in: mpg_edge_set_compaction): tiles are built from the rows whose mask is
+  // non-zero only, so padded particles cost nothing as RECEIVERS either (they already cost nothing as senders).  Every
+  // global tensor keeps its padded [B*N, .] layout; `cmap` (device, written by mpg_compact_map) says which padded row
+  // each of a tile's 128 lanes stands for.  Rows that are in no tile keep agg = 0 / dx = 0: exact for a network whose
+  // padded particles are dropped downstream (the discriminator: masked as senders, multiplied by the mask at the
+  // pooling, mpgan/model.py:810-822,881-884) -- not for the generator, whose padded rows are part of its output.
+  //   cmap[0] = number of tiles, cmap[2 + t] = first jet of tile t, cmap[2 + T + t] = jets it spans (<= 10),
+  //   cmap[2 + 2T + 128 t + lane] = padded row (b*N + i) or -1, T = ctiles_max
+  const int* cmap;
+  int ctiles_max;
   // optional pair features (pos_diffs): ef_mode bit0 = distance column, bit1 = difference columns
   const float* x;        // [B*N, F] node features, row stride ldx
   int ldx;
@@ -73,7 +83,15 @@ int launch_pq_fwd(const float* x, int ldx, const float* W0, int ldw, const float
                   int F, int H0, cudaStream_t stream, bool p_tiled = false);
 int launch_pq_bwd(const float* dP, const float* dQ, const float* x, int ldx, const float* W0, int ldw, float* dx,
                   int lddx, float* dW0, float* db0, int BN, int F, int H0, cudaStream_t stream, bool p_tiled = false,
-                  bool tf32 = false);   // tf32: TF32 tensor-core products (precision 1)
+                  bool tf32 = false,    // tf32: TF32 tensor-core products (precision 1)
+                  const int* cmap = nullptr, int ctiles_max = 0);   // receiver compaction (EdgeArgs::cmap)
+// compaction helpers (host + device)
+__host__ __device__ inline int compact_tiles_max(long long B, long long N) {   // full tiles + jet-capped tiles + 1
+  return (int)((B * N + 127) / 128 + (B + 9) / 10 + 1);
+}
+__host__ __device__ inline size_t compact_map_ints(long long B, long long N) {
+  return 2 + (size_t)compact_tiles_max(B, N) * (2 + 128);
+}
 // element (row r, column k) of a tiled P / dP buffer (EdgeArgs::p_tiled), H0 columns, 128-row tiles
 __host__ __device__ inline size_t p_tiled_index(size_t r, int k, int H0) {
   return (r >> 7) * 128 * (size_t)H0 + ((size_t)(k >> 2) * 128 + (r & 127)) * 4 + (k & 3);

@@ -152,8 +152,17 @@ size_t bwd_tc_smem(int F, int H0) {
 __global__ void __launch_bounds__(NT) pq_bwd_tc_kernel(const float* __restrict__ dP, const float* __restrict__ dQ,
                                                        const float* __restrict__ x, int ldx, const float* __restrict__ W0,
                                                        int ldw, float* __restrict__ dx, int lddx, float* __restrict__ dW0,
-                                                       float* __restrict__ db0, int BN, int F, int H0, int p_tiled) {
+                                                       float* __restrict__ db0, int BN, int F, int H0, int p_tiled,
+                                                       const int* __restrict__ cmap, int ctiles_max) {
   extern __shared__ __align__(16) float sm[];
+  __shared__ int rmap[BWD_ROWS];           // padded row of each of the block's rows (-1: none)
+  {
+    const int pos0 = blockIdx.x * BWD_ROWS;   // receiver compaction: positions in the compacted tile space
+    if (cmap != nullptr && pos0 >= cmap[0] * 128) return;   // (block-uniform)
+    for (int r = threadIdx.x; r < BWD_ROWS; r += NT)
+      rmap[r] = cmap != nullptr ? cmap[2 + 2 * ctiles_max + pos0 + r] : (pos0 + r < BN ? pos0 + r : -1);
+    __syncthreads();
+  }
   const int F8 = pq_f8(F), H0P = H0 + 4, FP = F8 + 8, DP = 2 * H0 + 4;
   float* Ws = sm;                          // [2*F8][H0P]  Ws[h*F8 + f][k] = W0[k][h*F + f], zero rows for f >= F
   float* ds = Ws + 2 * F8 * H0P;           // [BWD_ROWS][DP]  row = [dP | dQ]
@@ -170,11 +179,11 @@ __global__ void __launch_bounds__(NT) pq_bwd_tc_kernel(const float* __restrict__
         v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (idx < ng * BWD_ROWS) {                       // dP: tiled -> 64 consecutive rows of a column group are contiguous
           const int g = idx / BWD_ROWS, r = idx % BWD_ROWS;
-          if (r0 + r < BN)
-            v[u] = *reinterpret_cast<const float4*>(dP + (p_tiled ? p_tiled_index(r0 + r, 4 * g, H0) : (size_t)(r0 + r) * H0 + 4 * g));
-        } else if (idx < 2 * ng * BWD_ROWS) {            // dQ: row-major
+          if (rmap[r] >= 0)   // tiled dP is indexed by the position in the (compacted) tile space
+            v[u] = *reinterpret_cast<const float4*>(dP + (p_tiled ? p_tiled_index(r0 + r, 4 * g, H0) : (size_t)rmap[r] * H0 + 4 * g));
+        } else if (idx < 2 * ng * BWD_ROWS) {            // dQ: row-major, padded rows
           const int j = idx - ng * BWD_ROWS, r = j / ng, g = j % ng;
-          if (r0 + r < BN) v[u] = *reinterpret_cast<const float4*>(dQ + (size_t)(r0 + r) * H0 + 4 * g);
+          if (rmap[r] >= 0) v[u] = *reinterpret_cast<const float4*>(dQ + (size_t)rmap[r] * H0 + 4 * g);
         }
       }
 #pragma unroll
@@ -197,7 +206,7 @@ __global__ void __launch_bounds__(NT) pq_bwd_tc_kernel(const float* __restrict__
       },
       [&](int idx, float v) { const int k = idx / (2 * F8), c = idx % (2 * F8); Ws[c * H0P + k] = v; });
   batched_fill<8, NT>(BWD_ROWS * F8,
-      [&](int idx) { const int r = idx / F8, f = idx % F8; return (r0 + r < BN && f < F) ? x[(size_t)(r0 + r) * ldx + f] : 0.f; },
+      [&](int idx) { const int r = idx / F8, f = idx % F8; return (rmap[r] >= 0 && f < F) ? x[(size_t)rmap[r] * ldx + f] : 0.f; },
       [&](int idx, float v) { const int r = idx / F8, f = idx % F8; xs[r * FP + f] = v; });
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -218,8 +227,8 @@ __global__ void __launch_bounds__(NT) pq_bwd_tc_kernel(const float* __restrict__
     }
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const int r = r0 + m0 + g + 8 * (e >> 1), f = n0 + 2 * t + (e & 1);
-      if (r < BN && f < F) dx[(size_t)r * lddx + f] = c[e];
+      const int r = rmap[m0 + g + 8 * (e >> 1)], f = n0 + 2 * t + (e & 1);
+      if (r >= 0 && f < F) dx[(size_t)r * lddx + f] = c[e];
     }
   }
   if (dW0 == nullptr) return;   // input gradient only
@@ -266,19 +275,22 @@ int launch_pq_fwd(const float* x, int ldx, const float* W0, int ldw, const float
             "pq_fwd: P / Q must be 16-byte aligned");
   const size_t smem = pq_fwd_smem(F, H0);
   MPG_CUDA(cudaFuncSetAttribute(pq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  PqFwdArgs a{x, ldx, W0, ldw, b0, P, Q, BN, F, H0, p_tiled ? 1 : 0};
+  PqFwdArgs a{x, ldx, W0, ldw, b0, P, Q, BN, F, H0, p_tiled ? 1 : 0, nullptr, 0};
   pq_fwd_kernel<<<2 * cdiv(BN, PQ_ROWS), PQ_NT, smem, stream>>>(a);
   MPG_LAUNCH_CHECK();
   return 0;
 }
 
 int launch_pq_bwd(const float* dP, const float* dQ, const float* x, int ldx, const float* W0, int ldw, float* dx,
-                  int lddx, float* dW0, float* db0, int BN, int F, int H0, cudaStream_t stream, bool p_tiled, bool tf32) {
+                  int lddx, float* dW0, float* db0, int BN, int F, int H0, cudaStream_t stream, bool p_tiled, bool tf32,
+                  const int* cmap, int ctiles_max) {
+  MPG_CHECK(cmap == nullptr || (tf32 && H0 % 16 == 0 && p_tiled), "pq_bwd: receiver compaction needs the tensor-core form");
   if (tf32 && H0 % 16 == 0) {
     const size_t smem = bwd_tc_smem(F, H0);
     MPG_CUDA(cudaFuncSetAttribute(pq_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pq_bwd_tc_kernel<<<cdiv(BN, BWD_ROWS), NT, smem, stream>>>(dP, dQ, x, ldx, W0, ldw, dx, lddx, dW0, db0, BN, F, H0,
-                                                               p_tiled ? 1 : 0);
+    const int grid = cmap != nullptr ? ctiles_max * (128 / BWD_ROWS) : cdiv(BN, BWD_ROWS);
+    pq_bwd_tc_kernel<<<grid, NT, smem, stream>>>(dP, dQ, x, ldx, W0, ldw, dx, lddx, dW0, db0, BN, F, H0, p_tiled ? 1 : 0,
+                                                 cmap, ctiles_max);
     MPG_LAUNCH_CHECK();
     return 0;
   }

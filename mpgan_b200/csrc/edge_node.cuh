@@ -13,6 +13,7 @@ struct PqFwdArgs {
   const float* b0;
   float* P; float* Q;
   int BN, F, H0, p_tiled;
+  const int* cmap; int ctiles_max;   // receiver compaction (EdgeArgs::cmap): P tiles follow the map, Q stays per padded row
 };
 constexpr int PQ_ROWS = 128, PQ_NT = 256;
 
@@ -50,12 +51,19 @@ __device__ __forceinline__ void pq_fwd_tile(const PqFwdArgs& a, int job, float* 
   float* xs = Ws + F * H0P;              // [128][FP]
   float* st = xs + PQ_ROWS * FP;         // [128][H0P]  staging of a row-major output
   const int r0 = tile * PQ_ROWS;
+  const bool mapped = a.cmap != nullptr && h == 0;      // P of a compacted tile: lane r stands for padded row map[r]
+  if (mapped ? tile >= a.cmap[0] : r0 >= BN) return;    // (block-uniform)
+  const int* map = mapped ? a.cmap + 2 + 2 * a.ctiles_max + tile * PQ_ROWS : nullptr;
   // (eight independent loads in flight per thread: a load -> store loop exposes one memory latency per iteration)
   batched_fill<8, PQ_NT>(F * H0,
       [&](int idx) { const int k = idx / F, f = idx % F; return a.W0[(size_t)k * a.ldw + h * F + f]; },
       [&](int idx, float v) { const int k = idx / F, f = idx % F; Ws[f * H0P + k] = v; });
   batched_fill<8, PQ_NT>(PQ_ROWS * F,
-      [&](int idx) { const int r = idx / F, f = idx % F; return r0 + r < BN ? a.x[(size_t)(r0 + r) * a.ldx + f] : 0.f; },
+      [&](int idx) {
+        const int r = idx / F, f = idx % F;
+        const int gr = mapped ? map[r] : (r0 + r < BN ? r0 + r : -1);
+        return gr >= 0 ? a.x[(size_t)gr * a.ldx + f] : 0.f;
+      },
       [&](int idx, float v) { const int r = idx / F, f = idx % F; xs[r * FP + f] = v; });
   __syncthreads();
   const int ra = threadIdx.x & 63, rb = ra + 64, qt = threadIdx.x >> 6;
@@ -81,7 +89,7 @@ __device__ __forceinline__ void pq_fwd_tile(const PqFwdArgs& a, int job, float* 
     for (int i = 0; i < 2; ++i) {
       const int rl = i ? rb : ra;
       if (direct) {
-        if (r0 + rl < BN) {
+        if (mapped || r0 + rl < BN) {   // (mapped: every lane of the tile gets a finite P, rows or not)
           float* p = a.P + p_tiled_index((size_t)(r0 + rl), k0, H0);
           *reinterpret_cast<float4*>(p) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
           *reinterpret_cast<float4*>(p + 4 * PQ_ROWS) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);

@@ -45,7 +45,7 @@ bool edge_tc_supported(const EdgeArgs& a) {
 }
 
 static size_t tc_sbits_bytes(int B, int N) {   // backward: one uint2 per (step, epilogue thread)
-  const long long tiles = ((long long)B * N + TILE - 1) / TILE;
+  const long long tiles = compact_tiles_max(B, N);   // (covers the uncompacted ceil(B*N / 128) too)
   return (size_t)tiles * N * F_NEPI * sizeof(uint2);
 }
 
@@ -57,7 +57,7 @@ static int tc_num_sms() {
 static size_t tc_slab_bytes() { return (size_t)tc_num_sms() * SLAB_FLOATS * sizeof(float); }
 
 static size_t tc_steps_bytes(int B, int N) {   // work list: int2 per (tile, sender) + the total
-  const long long tiles = ((long long)B * N + TILE - 1) / TILE;
+  const long long tiles = compact_tiles_max(B, N);
   return ((size_t)tiles * N * sizeof(int2) + 256 + 255) & ~(size_t)255;
 }
 
@@ -90,7 +90,7 @@ static int tc_prepare(const EdgeArgs& a, void* persist, void* scratch, bool reus
     t.wslab = reinterpret_cast<float*>(q + ((tc_sbits_bytes(a.B, a.N) + 255) & ~(size_t)255));
   }
   const long long BN = (long long)a.B * a.N;
-  t.num_tiles = (int)((BN + TILE - 1) / TILE);
+  t.num_tiles = a.cmap ? a.ctiles_max : (int)((BN + TILE - 1) / TILE);   // compaction: upper bound (actual count on the device)
   if (!reuse) {   // images and work list of this (weights, mask): the backward of the same call finds them here
     const float s = (a.drop.p > 0.f ? 2.f : 1.f) * 0.5f * (1.f + a.alpha);
     const size_t agg_floats = zero_agg != nullptr ? (size_t)a.B * a.N * N2 : 0;   // N2 % 4 == 0; torch buffers are 16-byte aligned
@@ -107,8 +107,8 @@ static int tc_prepare(const EdgeArgs& a, void* persist, void* scratch, bool reus
     size_t smem = list_in_block ? step_list_smem(BNl, a.N) : 0;
     if (a.pq_deferred) {   // P / Q of this call: first layer's node-level ends (edge_node.cuh)
       pq = PqFwdArgs{a.x, a.ldx, a.Wef - 2 * a.F, a.ldwef, a.b0, const_cast<float*>(a.P), const_cast<float*>(a.Q),
-                     (int)BNl, a.F, a.H0, a.p_tiled};
-      nb_pq = 2 * cdiv(BNl, PQ_ROWS);   // a block per (128-row tile, P | Q)
+                     (int)BNl, a.F, a.H0, a.p_tiled, a.cmap, a.ctiles_max};
+      nb_pq = 2 * (a.cmap ? a.ctiles_max : cdiv(BNl, PQ_ROWS));   // a block per (128-row tile, P | Q)
       if (pq_fwd_smem(a.F, a.H0) > smem) smem = pq_fwd_smem(a.F, a.H0);
     }
     const int nb_prep = cdiv(N1 * 128 + N2 * 192, 256);
@@ -117,12 +117,13 @@ static int tc_prepare(const EdgeArgs& a, void* persist, void* scratch, bool reus
     auto gcd = [](int x, int y) { while (y) { const int r = x % y; x = y; y = r; } return x; };
     while (stride > 1 && gcd(stride, t.num_tiles) != 1) stride -= 2;
     if (stride < 1) stride = 1;
-    ListArgs ls{a.mask, a.B, a.N, t.num_tiles, const_cast<int2*>(t.steps), total, list_in_block ? 1 : 0, stride};
+    ListArgs ls{a.mask, a.B, a.N, t.num_tiles, const_cast<int2*>(t.steps), total, list_in_block ? 1 : 0, stride, a.cmap, a.ctiles_max};
     MPG_CUDA(cudaFuncSetAttribute(edge_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     edge_setup_kernel<<<nb_pq + nb_prep + (list_in_block ? 1 : 0), 256, smem, stream>>>(pq, nb_pq, pr, nb_prep, ls);
     MPG_LAUNCH_CHECK();
     if (!list_in_block) {
-      step_list_kernel<<<cdiv(t.num_tiles, 8), 256, 0, stream>>>(a.mask, a.B, a.N, t.num_tiles, const_cast<int2*>(t.steps), total);
+      step_list_kernel<<<cdiv(t.num_tiles, 8), 256, 0, stream>>>(a.mask, a.B, a.N, t.num_tiles, const_cast<int2*>(t.steps), total,
+                                                                 a.cmap, a.ctiles_max);
       MPG_LAUNCH_CHECK();
     }
   }

@@ -177,9 +177,8 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
         const int st = it % QS;
         if (it >= QS) mbar_wait(ubar + BwdBars::qe + 8 * st, (it / QS - 1) & 1);
         const int q_tile = ts.x, q_s = ts.y;
-        const int j0 = (q_tile * TILE) / N;
-        const int rl = min(q_tile * TILE + TILE - 1, BN - 1);
-        const int nj = rl / N - j0 + 1;
+        int j0, nj;
+        tile_jets(a, q_tile, j0, nj);
         const uint32_t bar = ubar + BwdBars::q + 8 * st;
         const uint32_t dst = ub + OFF_QR + (uint32_t)st * F_QSTAGE;
         // stage header (tile, sender, the sender's mask in each jet of the tile): see edge_tc_fwd.cuh
@@ -392,13 +391,15 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
       u4 n_kb{0, 0, 0, 0};                    // DROP: that step's Philox draw (layer 0 = y << 2; x,y: layer 1; z,w: layer 2)
       auto write_onehot = [&](int tile) {   // CHAIN: constant-1 columns 96,97 and one-hot jet columns 98+j of the H0' tile
         if (q == 0) {
-          const int r = tile * TILE + row;
-          const int js = (r < BN ? r : BN - 1) / N - (tile * TILE) / N;   // 0 .. F_QJ-1
+          int tj0, tnj;
+          tile_jets(a, tile, tj0, tnj);
+          const int r = tile_row(a, tile, row);
+          const int js = r >= 0 ? r / N - tj0 : 0;   // 0 .. F_QJ-1
           uint32_t w[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) w[i] = 0u;
           w[0] = 0x3F803F80u;
-          if (r < BN) {
+          if (r >= 0) {
 #pragma unroll
             for (int i = 1; i < 8; ++i)
               if (i == ((2 + js) >> 1)) w[i] = 0x3F80u << (16 * (js & 1));
@@ -413,16 +414,20 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
       };
       auto tile_rows = [&](int tile) {   // this thread's row of `tile`: index, stage offsets, its P values
         h_loaded = tile;
-        const int r = tile * TILE + row;
-        const int rc = r < BN ? r : BN - 1;
+        int tj0, tnj;
+        tile_jets(a, tile, tj0, tnj);
+        const int r = tile_row(a, tile, row);               // padded row of this lane, -1: none
+        h_valid = r >= 0;
+        // lanes without a row compute on a row that exists (their mask multiplier is 0)
+        const int rc = h_valid ? r : (a.cmap ? tj0 * N : BN - 1);
         h_r = rc;
-        h_valid = r < BN;
-        const uint32_t jl = (uint32_t)(rc / N - (tile * TILE) / N);
+        const uint32_t jl = (uint32_t)(rc / N - tj0);
         h_moff = F_QHDR + 8 + 4 * jl;
         h_qoff = jl * F_QROW + (uint32_t)q * 32u;
         // row-major: 8 floats at column 32c + 8q; tiled (EdgeArgs::p_tiled): column groups 8c + 2q (+1), the warp's 32
-        // rows of one group contiguous (rows past the end read the last row, like the row-major form)
-        const float* p = a.p_tiled ? a.P + (size_t)tile * TILE * K0 + ((size_t)(2 * q) * TILE + (rc - tile * TILE)) * 4
+        // rows of one group contiguous, indexed by the lane's position in the tile
+        const int prow = (a.cmap || h_valid) ? row : rc - tile * TILE;
+        const float* p = a.p_tiled ? a.P + (size_t)tile * TILE * K0 + ((size_t)(2 * q) * TILE + prow) * 4
                                    : a.P + (size_t)rc * K0 + q * 8;
         const int cs = a.p_tiled ? 8 * TILE * 4 : 32, hs = a.p_tiled ? TILE * 4 : 4;
 #pragma unroll
@@ -486,9 +491,9 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
       u4 kb{0, 0, 0, 0}, p1_kb{0, 0, 0, 0};   // draws of the current step / of step it+1 (DW2)
       const bool dagg32 = (reinterpret_cast<uintptr_t>(a.dagg) & 31) == 0;
       auto enter_tile = [&]() {   // rows of the tile the current step belongs to; their dAgg
-        const int r = c_tile * TILE + row;
-        c_valid = r < BN;
-        c_r = c_valid ? r : BN - 1;
+        const int r = tile_row(a, c_tile, row);
+        c_valid = r >= 0;
+        c_r = c_valid ? r : (a.cmap ? a.cmap[2 + c_tile] * N : BN - 1);
         const float* dg = a.dagg + (size_t)c_r * N2 + q * 8;
         if (dagg32) {   // 32-byte loads (see ldg256)
 #pragma unroll
@@ -782,8 +787,7 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
           k0w = k0w_next;
           kb = n_kb;                          // draw of step it+1 (build_h0(it + 1) ran above)
           // remember where this step's dQ sums belong, then advance
-          p_j0 = (c_tile * TILE) / N;
-          p_nj = min(c_tile * TILE + TILE - 1, BN - 1) / N - p_j0 + 1;
+          tile_jets(a, c_tile, p_j0, p_nj);
           p_s = c_s;
           {   // advance; flush dP when the next step belongs to another tile (or there is none)
             const int2 nx = it + 1 < nsteps ? make_int2(n_tile, n_s) : make_int2(-1, 0);   // build_h0(it + 1) ran above

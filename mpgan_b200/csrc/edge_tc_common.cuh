@@ -315,6 +315,28 @@ __device__ __forceinline__ float apply_keep(float x, uint32_t mask) { return __u
 // Everything below is specific to the edge-network kernels; fn_tc.cu includes this header for the PTX wrappers
 // above only (MPG_TC_WRAPPERS_ONLY).
 #ifndef MPG_TC_WRAPPERS_ONLY
+// ---- tile geometry: 128 consecutive padded rows, or (EdgeArgs::cmap) the rows listed by the compaction map -------------
+__device__ __forceinline__ int tile_count(const EdgeArgs& a) {
+  return a.cmap ? a.cmap[0] : (a.B * a.N + TILE - 1) / TILE;
+}
+// padded row (b*N + i) that lane `row` of `tile` stands for, -1 for none
+__device__ __forceinline__ int tile_row(const EdgeArgs& a, int tile, int row) {
+  if (a.cmap) return a.cmap[2 + 2 * a.ctiles_max + tile * TILE + row];
+  const int r = tile * TILE + row;
+  return r < a.B * a.N ? r : -1;
+}
+// first jet of the tile and the number of jets it spans
+__device__ __forceinline__ void tile_jets(const EdgeArgs& a, int tile, int& j0, int& nj) {
+  if (a.cmap) {
+    j0 = a.cmap[2 + tile];
+    nj = a.cmap[2 + a.ctiles_max + tile];
+  } else {
+    const int BN = a.B * a.N;
+    j0 = (tile * TILE) / a.N;
+    nj = min(tile * TILE + TILE - 1, BN - 1) / a.N - j0 + 1;
+  }
+}
+
 struct TcArgs {
   EdgeArgs a;
   const uint8_t* w1img;   // pre-swizzled bf16 images (edge_prepare_kernel)
@@ -378,6 +400,7 @@ struct ListArgs {
   // count, and a CTA (a contiguous slice of the list) whose tiles all have few live senders would spend its time on
   // tile changes (~2 steps each) while the others wait -- interleaving long and short tiles balances the slices
   int stride;
+  const int* cmap; int ctiles_max;   // receiver compaction (EdgeArgs): tile count and jets per tile come from the map
 };
 constexpr int LIST_CHUNK = 512;    // tiles per scan chunk
 // shared memory of step_list_block: scan counters, the live-sender words of a chunk's tiles, one byte per four mask
@@ -413,13 +436,28 @@ __device__ __forceinline__ void step_list_block(const ListArgs& l, int* cnt /* s
     }
     __syncthreads();
   }
-  auto tile_of = [&](int slot) { return (int)(((long long)slot * l.stride) % l.num_tiles); };
+  const int num_tiles = l.cmap ? l.cmap[0] : l.num_tiles;
+  int stride = l.stride;
+  if (l.cmap) {   // the tile count is only known here: same choice of stride as the host makes
+    stride = (int)(num_tiles * 0.381966f) | 1;
+    auto gcd = [](int x, int y) { while (y) { const int r = x % y; x = y; y = r; } return x; };
+    while (stride > 1 && gcd(stride, num_tiles) != 1) stride -= 2;
+    if (stride < 1) stride = 1;
+  }
+  auto tile_of = [&](int slot) { return (int)(((long long)slot * stride) % num_tiles); };
   int base = 0;
-  for (int t0 = 0; t0 < l.num_tiles; t0 += LIST_CHUNK) {
-    const int nt = min(LIST_CHUNK, l.num_tiles - t0);
+  for (int t0 = 0; t0 < num_tiles; t0 += LIST_CHUNK) {
+    const int nt = min(LIST_CHUNK, num_tiles - t0);
     for (int i = warp; i < nt; i += 8) {   // a warp per tile: live-sender words and their count
       const int tile = tile_of(t0 + i);
-      const int j0 = (tile * TILE) / N, j1 = min(tile * TILE + TILE - 1, BN - 1) / N;
+      int j0, j1;
+      if (l.cmap) {
+        j0 = l.cmap[2 + tile];
+        j1 = j0 + l.cmap[2 + l.ctiles_max + tile] - 1;
+      } else {
+        j0 = (tile * TILE) / N;
+        j1 = min(tile * TILE + TILE - 1, BN - 1) / N;
+      }
       int count = 0;
       for (int r = 0; r < R; ++r) {
         const int s = 32 * r + lane;
@@ -472,13 +510,20 @@ __device__ __forceinline__ void step_list_block(const ListArgs& l, int* cnt /* s
 // the same list from many blocks (one warp per tile, slices reserved with an atomic: tiles land in arbitrary order,
 // only the grouping by tile matters to the kernels); *total must be zero on entry (the set-up kernel does it)
 __global__ void __launch_bounds__(256) step_list_kernel(const float* __restrict__ mask, int B, int N, int num_tiles,
-                                                        int2* __restrict__ steps, int* __restrict__ total) {
+                                                        int2* __restrict__ steps, int* __restrict__ total,
+                                                        const int* __restrict__ cmap, int ctiles_max) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x * 8 + warp;
-  if (tile >= num_tiles) return;
+  if (tile >= (cmap ? cmap[0] : num_tiles)) return;
   const int BN = B * N;
-  const int j0 = (tile * TILE) / N;
-  const int j1 = min(tile * TILE + TILE - 1, BN - 1) / N;
+  int j0, j1;
+  if (cmap) {
+    j0 = cmap[2 + tile];
+    j1 = j0 + cmap[2 + ctiles_max + tile] - 1;
+  } else {
+    j0 = (tile * TILE) / N;
+    j1 = min(tile * TILE + TILE - 1, BN - 1) / N;
+  }
   auto active = [&](int s) {
     if (s >= N) return false;
     if (mask == nullptr) return true;

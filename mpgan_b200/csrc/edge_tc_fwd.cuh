@@ -153,9 +153,8 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
         // stage it % F_QS is free once every builder thread has read the rows of step it - F_QS
         if (it >= F_QS) mbar_wait(bar_qe + 8 * (it & (F_QS - 1)), (it / F_QS - 1) & 1);
         const int q_tile = ts.x, q_s = ts.y;
-        const int j0 = (q_tile * TILE) / N;
-        const int rl = min(q_tile * TILE + TILE - 1, BN - 1);
-        const int nj = rl / N - j0 + 1;
+        int j0, nj;
+        tile_jets(a, q_tile, j0, nj);
         const uint32_t bar = bar_q + 8 * (it & (F_QS - 1));
         const uint32_t dst = sQ + (uint32_t)(it & (F_QS - 1)) * F_QSTAGE;
         // header: the step and the sender's mask in each jet of the tile, so that no epilogue thread touches global
@@ -295,16 +294,20 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
     u4 s_kb[3] = {};   // DROP: the step's Philox draw (layer 0 = y << 2, consumed at once; the rest two steps later)
     auto tile_rows = [&](int tile) {   // this thread's row of `tile`: index, stage offsets, its P values
       h_loaded = tile;
-      const int r = tile * TILE + row;
-      const int rc = r < BN ? r : BN - 1;
+      int tj0, tnj;
+      tile_jets(a, tile, tj0, tnj);
+      const int r = tile_row(a, tile, row);                 // padded row of this lane, -1: none
+      h_valid = r >= 0;
+      // lanes without a row compute on a row that exists (their mask multiplier is 0): the last one / the tile's first jet
+      const int rc = h_valid ? r : (a.cmap ? tj0 * N : BN - 1);
       h_r = rc;
-      h_valid = r < BN;
-      const uint32_t jl = (uint32_t)(rc / N - (tile * TILE) / N);
+      const uint32_t jl = (uint32_t)(rc / N - tj0);
       h_moff = F_QHDR + 8 + 4 * jl;
       h_qoff = jl * F_QROW + (uint32_t)q * 32u;
       // row-major: 8 floats at column 32c + 8q; tiled (EdgeArgs::p_tiled): column groups 8c + 2q (+1), the warp's 32
-      // rows of one group contiguous (rows past the end read the last row, like the row-major form)
-      const float* p = a.p_tiled ? a.P + (size_t)tile * TILE * K0 + ((size_t)(2 * q) * TILE + (rc - tile * TILE)) * 4
+      // rows of one group contiguous, indexed by the lane's position in the tile (lanes without a row: any lane's)
+      const int prow = (a.cmap || h_valid) ? row : rc - tile * TILE;
+      const float* p = a.p_tiled ? a.P + (size_t)tile * TILE * K0 + ((size_t)(2 * q) * TILE + prow) * 4
                                  : a.P + (size_t)rc * K0 + q * 8;
       const int cs = a.p_tiled ? 8 * TILE * 4 : 32, hs = a.p_tiled ? TILE * 4 : 4;
 #pragma unroll
@@ -376,7 +379,7 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
     auto flush = [&]() {
       const int g = warp & 3;
       const uint32_t stg = base + F_OFF_STG + (uint32_t)g * (16u * F_STG_ROW);
-      const int grow0 = acc_tile * TILE + g * 32;
+      const int lrow0 = g * 32;             // first lane (tile row) of this lane quarter
 #pragma unroll 1
       for (int rd = 0; rd < 2; ++rd) {
         if ((lane >> 4) == rd) {
@@ -397,8 +400,8 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
         if (lane == 0) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const int rr = 4 * q + i, grow = grow0 + 16 * rd + rr;
-            if (grow < BN) bulk_reduce_add_f32(a.agg + (size_t)grow * N2, stg + (uint32_t)rr * F_STG_ROW, N2 * 4);
+            const int rr = 4 * q + i, grow = tile_row(a, acc_tile, lrow0 + 16 * rd + rr);
+            if (grow >= 0) bulk_reduce_add_f32(a.agg + (size_t)grow * N2, stg + (uint32_t)rr * F_STG_ROW, N2 * 4);
           }
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // rows read: the staging may be rewritten

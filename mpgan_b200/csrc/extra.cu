@@ -1,5 +1,6 @@
 // Small HBM / latency-bound kernels added in round 2 (see extra.cuh).
 #include "extra.cuh"
+#include "edge.cuh"
 
 namespace mpg {
 namespace {
@@ -164,6 +165,95 @@ int launch_cond_columns(const float* x, int ldx, const float* cond, int C, float
   MPG_LAUNCH_CHECK();
   return 0;
 }
+// ---- receiver compaction map (EdgeArgs::cmap, edge.cuh) -------------------------------------------------------------
+// One block.  (1) a thread per jet counts its unmasked particles; (2) thread 0 places the jets one after the other in
+// the compacted row space -- a 128-row tile may touch at most MAXJ consecutive jets (the Q ring of the edge kernels
+// holds one row per jet), so when the next jet would be the (MAXJ+1)-th of its tile the rest of the tile stays empty;
+// (3) a thread per jet writes its rows' padded indices, a thread per tile the tile's jet span.
+constexpr int CMAP_MAXJ = 10;
+constexpr size_t CMAP_SMEM_MAX = 160 * 1024;   // counts / start positions and the mask bits live in shared memory up to here
+__host__ __device__ inline size_t cmap_smem(long long B, long long N) {
+  return (size_t)B * sizeof(int) + (size_t)((B * N + 3) / 4 + 15) / 16 * 16;
+}
+__global__ void __launch_bounds__(256) compact_map_kernel(const float* __restrict__ mask, int B, int N, int* __restrict__ cmap,
+                                                          int tmax, int* __restrict__ start_g /* [B] scratch */, int in_smem) {
+  extern __shared__ int cm_sm[];
+  int* start = in_smem ? cm_sm : start_g;   // count, then first position of every jet
+  uint8_t* nib = reinterpret_cast<uint8_t*>(cm_sm + B);   // in_smem: bit (i & 3) of nib[i >> 2] = mask[i] != 0
+  int* tile_j0 = cmap + 2;
+  int* tile_nj = cmap + 2 + tmax;
+  int* rowmap = cmap + 2 + 2 * tmax;
+  const int BN = B * N;
+  for (int i = threadIdx.x; i < tmax * 128; i += blockDim.x) rowmap[i] = -1;
+  for (int t = threadIdx.x; t < tmax; t += blockDim.x) { tile_j0[t] = 0; tile_nj[t] = 1; }
+  if (in_smem) {   // one coalesced pass over the mask, eight loads in flight per thread
+    const int n4 = (BN + 3) >> 2;
+    for (int i0 = threadIdx.x; i0 < n4; i0 += blockDim.x * 8) {
+      uint8_t v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * blockDim.x;
+        v[u] = 0;
+        if (i < n4) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (4 * i + e < BN) v[u] |= (uint8_t)((mask[4 * (size_t)i + e] != 0.f) << e);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * blockDim.x;
+        if (i < n4) nib[i] = v[u];
+      }
+    }
+    __syncthreads();
+  }
+  auto live = [&](int e) { return in_smem ? ((nib[e >> 2] >> (e & 3)) & 1) != 0 : mask[e] != 0.f; };
+  for (int j = threadIdx.x; j < B; j += blockDim.x) {
+    int n = 0;
+    for (int i = 0; i < N; ++i) n += live(j * N + i);
+    start[j] = n;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int pos = 0, first = -1;            // next free position; first jet of the tile `pos` lies in (-1: tile still empty)
+    for (int j = 0; j < B; ++j) {
+      const int n = start[j];
+      if (n == 0) { start[j] = -1; continue; }
+      if ((pos & 127) == 0) first = -1;
+      if (first >= 0 && j - first + 1 > CMAP_MAXJ) { pos = (pos + 127) & ~127; first = -1; }
+      if (first < 0) { first = j; tile_j0[pos >> 7] = j; }
+      tile_nj[pos >> 7] = j - first + 1;
+      start[j] = pos;
+      const int end = pos + n;
+      for (int t = (pos >> 7) + 1; t <= ((end - 1) >> 7); ++t) {   // the jet runs on: it is the first jet of those tiles
+        first = j;
+        tile_j0[t] = j;
+        tile_nj[t] = 1;
+      }
+      pos = end;
+    }
+    cmap[0] = (pos + 127) >> 7;
+    cmap[1] = pos;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < B; j += blockDim.x) {
+    int p = start[j];
+    if (p < 0) continue;
+    for (int i = 0; i < N; ++i)
+      if (live(j * N + i)) rowmap[p++] = j * N + i;
+  }
+}
+
+int launch_compact_map(const float* mask, int B, int N, int* cmap, int* scratch, cudaStream_t s) {
+  const bool in_smem = cmap_smem(B, N) <= CMAP_SMEM_MAX;
+  const size_t smem = in_smem ? cmap_smem(B, N) : 0;
+  MPG_CUDA(cudaFuncSetAttribute(compact_map_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CMAP_SMEM_MAX));
+  compact_map_kernel<<<1, 256, smem, s>>>(mask, B, N, cmap, compact_tiles_max(B, N), scratch, in_smem ? 1 : 0);
+  MPG_LAUNCH_CHECK();
+  return 0;
+}
+
 int launch_split_mask_bwd(const float* dmask, float* dx, int ldx, size_t rows, cudaStream_t s) {
   if (rows == 0) return 0;
   const size_t n = rows * (size_t)ldx;

@@ -11,6 +11,7 @@ int launch_gen_postprocess(const float* jets, int ldj, float* out, int ldo, size
                            cudaStream_t s);
 int launch_cond_columns(const float* x, int ldx, const float* cond, int C, float* out, size_t rows, int F, int B,
                         cudaStream_t s);
+int launch_compact_map(const float* mask, int B, int N, int* cmap, int* scratch, cudaStream_t s);
 int launch_split_mask_bwd(const float* dmask, float* dx, int ldx, size_t rows, cudaStream_t s);
 int launch_pool_dmask(const float* h, const float* dout, float* dmask, int B, int N, int C, float scale, cudaStream_t s);
 int launch_layernorm_fwd(const float* x, const float* w, const float* b, float* y, float* mean, float* rstd, size_t rows,

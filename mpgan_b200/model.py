@@ -295,8 +295,15 @@ class MPNet(nn.Module):
             idx, mask_sorted = ops.particle_order(mask)       # idx[b, i] = new position of particle i
             x = ops.permute_rows(x, idx, 0)
             mask_orig, mask = mask, mask_sorted
-        for i in range(self.mp_iters):
-            x = self.mp_layers[i](x, use_mask, mask, labels, num_jet_particles)
+        cmap = None
+        if (use_mask and self.compact_receivers and ops.get_precision() == 1 and not mask.requires_grad
+                and not self.order_dependent and all(l.fully_connected for l in self.mp_layers)):
+            # Padded particles are dropped downstream (masked as senders, multiplied by the mask at the pooling):
+            # the edge kernels need not compute what they RECEIVE either.  One map per call, shared by the layers.
+            cmap = ops.compact_map(mask)
+        with ops.receiver_compaction(cmap):
+            for i in range(self.mp_iters):
+                x = self.mp_layers[i](x, use_mask, mask, labels, num_jet_particles)
         if idx is not None and not self._pool_is_order_free():
             x = ops.permute_rows(x, idx, 1)                    # back to the caller's particle order
             mask = mask_orig
@@ -304,6 +311,7 @@ class MPNet(nn.Module):
         return self._tail(x, mask)
 
     sort_particles = True     # class-level switch (tests compare both layouts)
+    compact_receivers = False  # only networks that drop their padded particles downstream may switch this on
 
     def _pool_is_order_free(self) -> bool:
         """True if ``_post_mp`` reduces over particles (then the permutation need not be undone)."""
@@ -398,6 +406,8 @@ class MPDiscriminator(MPNet):
         if dea:
             self.fnd_layer = LinearNet(fnd, input_size=self.hidden_node_size + int(mask_fnd_np), output_size=1,
                                        final_linear=True, **self.linear_args)
+
+    compact_receivers = True   # reference :810-822,881-884: x * mask before the pooling, mask on the sender axis
 
     def _pool_is_order_free(self) -> bool:
         return True   # masked sum / mean over particles (with or without the fnd head)

@@ -176,18 +176,24 @@ def _pair_flops(B, N, Ha, Hb):
     return 2.0 * B * N * N * Ha * Hb
 
 
-def edge_active_fraction(mask, B, N):
-    """Share of the (128-receiver tile, sender) steps the tcgen05 kernels execute: a step is dropped when
-    the sender is masked in every jet the tile touches (csrc/edge_tc_common.cuh: step_list_kernel).
-    Reporting helper (synchronises); not on the compute path."""
+def edge_active_fraction(mask, B, N, cmap=None):
+    """Share of the (128-receiver tile, sender) steps of the padded problem the tcgen05 kernels execute: a step is
+    dropped when the sender is masked in every jet the tile touches (csrc/edge_tc_common.cuh: step_list_block); with a
+    receiver compaction map the tiles are the map's.  Reporting helper (synchronises); not on the compute path."""
     if mask is None:
         return 1.0
     m = (mask.reshape(B, N) != 0).to(torch.int32)
     BN = B * N
     tiles = (BN + 127) // 128
-    r0 = torch.arange(tiles, device=m.device) * 128
-    j0 = r0 // N
-    j1 = torch.clamp(r0 + 127, max=BN - 1) // N
+    if cmap is not None:
+        tmax = (int(cmap.numel()) - 2) // 130
+        nt = int(cmap[0].item())
+        j0 = cmap[2:2 + nt].long()
+        j1 = j0 + cmap[2 + tmax:2 + tmax + nt].long() - 1
+    else:
+        r0 = torch.arange(tiles, device=m.device) * 128
+        j0 = r0 // N
+        j1 = torch.clamp(r0 + 127, max=BN - 1) // N
     cs = torch.cat((torch.zeros(1, N, dtype=torch.int32, device=m.device), m.cumsum(0).to(torch.int32)), 0)
     act = (cs[j1 + 1] - cs[j0]) > 0
     return float(act.sum().item()) / float(tiles * N)
@@ -327,6 +333,52 @@ def linear(x, w, b, act: bool, alpha: float, p_drop: float, rng_stream: int = 16
 # --------------------------------------------------------------------------------------------------
 # fused edge network + aggregation
 # --------------------------------------------------------------------------------------------------
+_CMAP = None            # receiver compaction map of the edge calls inside ``receiver_compaction`` (int32 tensor or None)
+
+
+def compact_map(mask):
+    """Map that packs the particles with mask != 0 into the 128-row tiles of the tcgen05 edge kernels
+    (``mpg_compact_map``): padded particles then cost nothing as receivers either.  ``mask`` [B, N(, 1)]."""
+    L = _lib.lib()
+    B, N = int(mask.shape[0]), int(mask.shape[1])
+    m = mask.detach().reshape(B, N).contiguous().float()
+    cmap = torch.empty(int(L.mpg_compact_map_ints(B, N)), device=m.device, dtype=torch.int32)
+    scratch = torch.empty(B, device=m.device, dtype=torch.int32)
+    _lib.check(L.mpg_compact_map(_lib.ptr(m), B, N, _lib.ptr(cmap), _lib.ptr(scratch), _lib.stream()), "mpg_compact_map")
+    return cmap
+
+
+class receiver_compaction:
+    """``with receiver_compaction(cmap):`` the fused edge ops inside build their tiles from ``cmap`` (None: no-op).
+    Exact only where padded particles are dropped downstream (the discriminator); see include/mpgan_b200.h."""
+
+    def __init__(self, cmap):
+        self.cmap = cmap
+
+    def __enter__(self):
+        global _CMAP
+        self.prev, _CMAP = _CMAP, self.cmap
+
+    def __exit__(self, *exc):
+        global _CMAP
+        _CMAP = self.prev
+
+
+class _compaction_for_call:
+    """Arms / disarms the library's thread-local map around one C call."""
+
+    def __init__(self, cmap):
+        self.cmap = cmap
+
+    def __enter__(self):
+        if self.cmap is not None:
+            _lib.lib().mpg_edge_set_compaction(_lib.ptr(self.cmap))
+
+    def __exit__(self, *exc):
+        if self.cmap is not None:
+            _lib.lib().mpg_edge_set_compaction(None)
+
+
 class EdgeAggFn(torch.autograd.Function):
     """agg[b,i] = scale * sum_j mask[b,j] fe(x_i | x_j | ef_ij); mpgan/model.py:256-267,284-317."""
 
@@ -343,9 +395,12 @@ class EdgeAggFn(torch.autograd.Function):
         m = None if mask is None else mask.reshape(B, N).contiguous()
         ws_ = [t.contiguous() for t in (w0, b0, w1, b1, w2, b2)]
         seed = next_seed() if p_drop > 0 else 0
-        frac = edge_active_fraction(m, B, N) if _profile is not None else 1.0
+        cmap = _CMAP if (m is not None and _PRECISION == 1 and ef_mode == 0) else None
+        ctx.cmap = cmap
+        frac = edge_active_fraction(m, B, N, cmap) if _profile is not None else 1.0
         with _Timed("edge_fwd", edge_flops(B, N, F, H0, H1, H2),
-                    [(1, "edge_tc_fwd_kernel", _pair_flops(B, N, H0, H1) + _pair_flops(B, N, H1, H2))], frac):
+                    [(1, "edge_tc_fwd_kernel", _pair_flops(B, N, H0, H1) + _pair_flops(B, N, H1, H2))], frac), \
+                _compaction_for_call(cmap):
             _lib.check(L.mpg_edge_fwd(_lib.ptr(x3), ldx, _lib.ptr(m), *[_lib.ptr(t) for t in ws_], B, N, F, H0, H1,
                                       H2, int(ef_mode), int(nd), int(mean), float(alpha), float(p_drop), seed,
                                       _seed_ptr(), _PRECISION, ws.data_ptr(), ws_bytes, _lib.ptr(agg),
@@ -402,10 +457,11 @@ class EdgeAggFn(torch.autograd.Function):
                                           _lib.stream()), "mpg_edge_nbr_bwd")
             dmask = dmask.view(ctx.mask_shape)
         else:
-            frac = edge_active_fraction(m, B, N) if _profile is not None else 1.0
+            frac = edge_active_fraction(m, B, N, getattr(ctx, "cmap", None)) if _profile is not None else 1.0
             with _Timed("edge_bwd", 2.0 * edge_flops(B, N, F, H0, H1, H2),
                         [(2, "edge_tc_bwd_chain_kernel", 2 * _pair_flops(B, N, H0, H1) + _pair_flops(B, N, H1, H2)),
-                         (3, "edge_tc_bwd_dw2_kernel", _pair_flops(B, N, H1, H2))], frac):
+                         (3, "edge_tc_bwd_dw2_kernel", _pair_flops(B, N, H1, H2))], frac), \
+                    _compaction_for_call(getattr(ctx, "cmap", None)):
                 args = (_lib.ptr(x3), ldx, _lib.ptr(m), *[_lib.ptr(t) for t in (w0, b0, w1, b1, w2, b2)], B, N, F, H0, H1,
                         H2, ef_mode, nd, mean, alpha, p, seed, sptr, prec, ws.data_ptr(), ws_bytes, _lib.ptr(dagg),
                         _lib.ptr(dx), F, *[_lib.ptr(g) for g in grads], _lib.stream())

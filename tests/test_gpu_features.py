@@ -385,3 +385,100 @@ def test_fused_mab_tensor_core_matches_simt_with_dropout():
         close(res[1][0], res[0][0], 5e-3, "out")
         for a, b in zip(res[1][1:], res[0][1:]):
             assert rel_l2(a, b) <= 2e-2, rel_l2(a, b)
+
+
+def _ragged_inputs(B, N, seed, zero_jets=()):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    n = torch.randint(1, N + 1, (B,), device="cuda", generator=g)
+    for j in zero_jets:
+        n[j] = 0
+    mask = (torch.arange(N, device="cuda")[None, :] < n[:, None]).float()
+    x = (torch.rand(B, N, 3, device="cuda", generator=g) - 0.5) * mask.unsqueeze(2)
+    return torch.cat((x, mask.unsqueeze(2) - 0.5), 2), n
+
+
+@pytest.mark.parametrize("B,N", [(37, 30), (300, 30), (20, 150), (64, 17)])
+def test_compaction_map_invariants(B, N):
+    """mpg_compact_map: every unmasked particle appears exactly once, in order; a tile spans at most 10 jets and its
+    (first jet, jet count) entries cover exactly the jets of its rows."""
+    from mpgan_b200 import ops
+    x, n = _ragged_inputs(B, N, 5 + B, zero_jets=(1, B - 1))
+    mask = x[..., 3] + 0.5
+    mask[2, 0] = 0            # a hole: masks need not be prefixes
+    cmap = ops.compact_map(mask).cpu()
+    tmax = (cmap.numel() - 2) // 130
+    nt = int(cmap[0])
+    rows = cmap[2 + 2 * tmax:2 + 2 * tmax + nt * 128].view(nt, 128)
+    want = torch.nonzero(mask.reshape(-1).cpu() != 0).flatten()
+    got = rows[rows >= 0]
+    assert torch.equal(got.long(), want), "rows of the map = the unmasked particles, in order"
+    assert int(cmap[1]) >= want.numel() and nt <= tmax
+    for t in range(nt):
+        r = rows[t][rows[t] >= 0]
+        assert r.numel() > 0
+        j0, nj = int(cmap[2 + t]), int(cmap[2 + tmax + t])
+        assert j0 == int(r[0]) // N and j0 + nj - 1 == int(r[-1]) // N and 1 <= nj <= 10
+
+
+@pytest.mark.parametrize("p_drop", [0.0, 0.5])
+def test_receiver_compaction_is_exact_for_the_discriminator(golden, p_drop):
+    """MPDiscriminator with receiver compaction (padded particles skipped as receivers, the default at precision 1)
+    against the same network without it, on a ragged batch with empty jets: output, every parameter gradient and the
+    input gradient (zero on padded rows either way).  Same bf16 arithmetic per particle pair; only the order of the
+    fp32 sums differs.  reference semantics: mpgan/model.py:810-822,881-884."""
+    from mpgan_b200 import ops, presets
+    import mpgan_b200.model as M
+    ops.set_precision(1)
+    x, n = _ragged_inputs(96, 30, 11, zero_jets=(7,))
+    labels = (n.float() / 30).unsqueeze(1)
+    res = []
+    for compact in (False, True):
+        torch.manual_seed(0)
+        D = presets.mp_discriminator(disc_dropout=p_drop).cuda().train()
+        M.MPDiscriminator.compact_receivers = compact
+        try:
+            ops._seed_counter = 977
+            xi = x.clone().requires_grad_(True)
+            xi_in = torch.cat((xi[..., :3], xi[..., 3:].detach()), 2)   # the mask channel carries no gradient here
+            out = D(xi_in, labels)
+            out.square().sum().backward()
+            res.append((out.detach(), xi.grad.clone(), {k: p.grad.clone() for k, p in D.named_parameters()}))
+        finally:
+            M.MPDiscriminator.compact_receivers = True
+    (o0, gx0, gp0), (o1, gx1, gp1) = res
+    close(o1, o0, 2e-3, "D output")
+    print("dx rel_l2", rel_l2(gx1, gx0), "max-abs rel", rel(gx1, gx0))
+    assert rel_l2(gx1, gx0) <= 5e-3, ("D input gradient", rel_l2(gx1, gx0), rel(gx1, gx0))
+    pad = (x[..., 3] < 0)
+    assert float(gx1[..., :3][pad].abs().max()) == 0.0, "padded particles get no gradient"
+    for k in gp0:
+        assert rel_l2(gp1[k], gp0[k]) <= 5e-3, (k, rel_l2(gp1[k], gp0[k]))
+
+
+@pytest.mark.parametrize("p_drop", [0.0, 0.5])
+def test_receiver_compaction_edge_op(p_drop):
+    """The fused edge op alone, compacted vs not, same dropout seed: aggregate of the unmasked receivers, input
+    gradient and weight gradients (the incoming gradient is zero on padded receivers, as it is inside D)."""
+    from mpgan_b200 import ops
+    ops.set_precision(1)
+    B, N, F = 70, 30, 32
+    g = torch.Generator(device="cuda").manual_seed(3)
+    n = torch.randint(1, N + 1, (B,), device="cuda", generator=g)
+    mask = (torch.arange(N, device="cuda")[None, :] < n[:, None]).float().unsqueeze(2)
+    x0 = torch.randn(B, N, F, device="cuda", generator=g) * 0.5
+    ws0 = []
+    for i, o in ((2 * F, 96), (96, 160), (160, 192)):
+        ws0 += [torch.randn(o, i, device="cuda", generator=g) / i ** 0.5, torch.randn(o, device="cuda", generator=g) * 0.1]
+    dagg = torch.randn(B, N, 192, device="cuda", generator=g) * mask
+    cmap = ops.compact_map(mask)
+    res = []
+    for cm in (None, cmap):
+        ops._seed_counter = 31337
+        x = x0.clone().requires_grad_(True)
+        ws = [w.clone().requires_grad_(True) for w in ws0]
+        with ops.receiver_compaction(cm):
+            agg = ops.edge_aggregate(x, mask, *ws, p_drop=p_drop)
+        agg.backward(dagg)
+        res.append([agg.detach() * mask, x.grad] + [w.grad for w in ws])
+    for name, r0, r1 in zip(["agg", "dx", "dW0", "db0", "dW1", "db1", "dW2", "db2"], res[0], res[1]):
+        assert rel_l2(r1, r0) <= 2e-3, (name, p_drop, rel_l2(r1, r0), rel(r1, r0))
