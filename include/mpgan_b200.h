@@ -215,7 +215,7 @@ int mpg_edge_bwd2(const float* x, int ldx, const float* u, int ldu, const float*
 
 /* ---- receiver compaction (tcgen05 edge path; exact for the discriminator, mpgan/model.py:810-822,881-884: padded
  * particles are masked as senders and multiplied by the mask at the pooling, so nothing they receive is ever used).
- * mpg_compact_map writes the map (mpg_compact_map_ints(B, N) ints; `scratch`: B ints) that packs the rows with
+ * mpg_compact_map writes the map (mpg_compact_map_ints(B, N) ints; `scratch`: 2B + 8 ints) that packs the rows with
  * mask != 0 into 128-row tiles; mpg_edge_set_compaction(map) makes THIS THREAD's following mpg_edge_fwd / mpg_edge_bwd /
  * mpg_edge_bwd_saved calls build their tiles from it (NULL: off).  Tensors keep their padded [B*N, .] layout; rows
  * outside every tile get agg = 0 and dx = 0.  Ignored on the fp32 path.  Do not use for a generator (its padded rows are

@@ -86,8 +86,8 @@ int launch_pq_bwd(const float* dP, const float* dQ, const float* x, int ldx, con
                   bool tf32 = false,    // tf32: TF32 tensor-core products (precision 1)
                   const int* cmap = nullptr, int ctiles_max = 0);   // receiver compaction (EdgeArgs::cmap)
 // compaction helpers (host + device)
-__host__ __device__ inline int compact_tiles_max(long long B, long long N) {   // full tiles + jet-capped tiles + 1
-  return (int)((B * N + 127) / 128 + (B + 9) / 10 + 1);
+__host__ __device__ inline int compact_tiles_max(long long B, long long N) {   // every jet is max(n, 15) <= max(N, 15) wide
+  return (int)((B * (N > 15 ? N : 15) + 127) / 128);
 }
 __host__ __device__ inline size_t compact_map_ints(long long B, long long N) {
   return 2 + (size_t)compact_tiles_max(B, N) * (2 + 128);

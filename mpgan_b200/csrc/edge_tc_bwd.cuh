@@ -172,13 +172,13 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
         bulk_g2s_elect(ub + OFF_W1, t.w1img, W1_BYTES, ubar + BwdBars::w);
       }
       int2 ts = first;
+      int l_tile = -1, j0 = 0, nj = 1;   // jets of the tile whose steps are being loaded
       for (int it = 0; it < nsteps; ++it) {
         const int2 ts_next = steps[it + 1 < nsteps ? it + 1 : it];   // in flight while this step's copies are issued
         const int st = it % QS;
         if (it >= QS) mbar_wait(ubar + BwdBars::qe + 8 * st, (it / QS - 1) & 1);
         const int q_tile = ts.x, q_s = ts.y;
-        int j0, nj;
-        tile_jets(a, q_tile, j0, nj);
+        if (q_tile != l_tile) { tile_jets(a, q_tile, j0, nj); l_tile = q_tile; }
         const uint32_t bar = ubar + BwdBars::q + 8 * st;
         const uint32_t dst = ub + OFF_QR + (uint32_t)st * F_QSTAGE;
         // stage header (tile, sender, the sender's mask in each jet of the tile): see edge_tc_fwd.cuh
@@ -482,7 +482,7 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
       };
 
       // ---- state of the current step ------------------------------------------------------------------------
-      int c_tile = 0, c_s = 0, c_r = 0;
+      int c_tile = 0, c_s = 0, c_r = 0, c_j0 = 0, c_nj = 1;   // current step's tile, sender, this lane's row, the tile's jets
       float c_m = 0.f;                        // mask multiplier of the current step (0 for rows past the end)
       bool c_valid = false, c_first = true;   // c_first: first step of its tile inside this CTA's range
       // DW2 builds two steps ahead: records of steps it+1 (p1_*) and it+2 (n_*)
@@ -492,8 +492,9 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
       const bool dagg32 = (reinterpret_cast<uintptr_t>(a.dagg) & 31) == 0;
       auto enter_tile = [&]() {   // rows of the tile the current step belongs to; their dAgg
         const int r = tile_row(a, c_tile, row);
+        tile_jets(a, c_tile, c_j0, c_nj);
         c_valid = r >= 0;
-        c_r = c_valid ? r : (a.cmap ? a.cmap[2 + c_tile] * N : BN - 1);
+        c_r = c_valid ? r : (a.cmap ? c_j0 * N : BN - 1);
         const float* dg = a.dagg + (size_t)c_r * N2 + q * 8;
         if (dagg32) {   // 32-byte loads (see ldg256)
 #pragma unroll
@@ -787,7 +788,7 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_bwd_kernel(TcArgs t) {
           k0w = k0w_next;
           kb = n_kb;                          // draw of step it+1 (build_h0(it + 1) ran above)
           // remember where this step's dQ sums belong, then advance
-          tile_jets(a, c_tile, p_j0, p_nj);
+          p_j0 = c_j0; p_nj = c_nj;
           p_s = c_s;
           {   // advance; flush dP when the next step belongs to another tile (or there is none)
             const int2 nx = it + 1 < nsteps ? make_int2(n_tile, n_s) : make_int2(-1, 0);   // build_h0(it + 1) ran above

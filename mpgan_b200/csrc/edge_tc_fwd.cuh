@@ -148,13 +148,13 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
       bulk_g2s_elect(sW1, t.w1img, W1_BYTES, bar_w);
       bulk_g2s_elect(sW2, t.w2img, W2_BYTES, bar_w);
       int2 ts = first;
+      int l_tile = -1, j0 = 0, nj = 1;   // jets of the tile whose steps are being loaded
       for (int it = 0; it < nsteps; ++it) {
         const int2 ts_next = steps[it + 1 < nsteps ? it + 1 : it];   // in flight while this step's copies are issued
         // stage it % F_QS is free once every builder thread has read the rows of step it - F_QS
         if (it >= F_QS) mbar_wait(bar_qe + 8 * (it & (F_QS - 1)), (it / F_QS - 1) & 1);
         const int q_tile = ts.x, q_s = ts.y;
-        int j0, nj;
-        tile_jets(a, q_tile, j0, nj);
+        if (q_tile != l_tile) { tile_jets(a, q_tile, j0, nj); l_tile = q_tile; }
         const uint32_t bar = bar_q + 8 * (it & (F_QS - 1));
         const uint32_t dst = sQ + (uint32_t)(it & (F_QS - 1)) * F_QSTAGE;
         // header: the step and the sender's mask in each jet of the tile, so that no epilogue thread touches global
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
       {
         float mv;
         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(mv) : "r"(stage + h_moff));
-        s_tile[2] = h_tile; s_snd[2] = h_s; s_row[2] = h_r; s_m[2] = h_valid ? mv : 0.f;
+        s_tile[2] = h_tile; s_snd[2] = h_s; s_row[2] = h_valid ? h_r : -1; s_m[2] = h_valid ? mv : 0.f;
       }
       uint32_t kw = 0;
       if (DROP) {
@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
     };
 
     // ---- tile state: `cur` = tile of step `it` (mask / dropout rows), `acc` = tile the accumulators belong to
-    int acc_tile = 0;
+    int acc_tile = 0, acc_R = -1;   // tile the accumulators belong to; this lane's padded row in it (-1: none)
     float e_m = 0.f;      // mask multiplier of the step whose E2 is pending
     const float fl_scale = a.out_scale * (DROP ? 2.f : 1.f) * 0.5f * (1.f + a.alpha);
     // A thread holds one row's 8-column chunks: 12 reductions of 16 bytes per thread, 6144 per CTA and flush, all
@@ -379,7 +379,6 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
     auto flush = [&]() {
       const int g = warp & 3;
       const uint32_t stg = base + F_OFF_STG + (uint32_t)g * (16u * F_STG_ROW);
-      const int lrow0 = g * 32;             // first lane (tile row) of this lane quarter
 #pragma unroll 1
       for (int rd = 0; rd < 2; ++rd) {
         if ((lane >> 4) == rd) {
@@ -397,11 +396,14 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
         }
         fence_async_smem();                 // generic-proxy writes -> visible to the bulk (async proxy) reads
         named_bar_sync(1 + g, 128);
+        int grow[4];   // padded rows of the four staged rows this warp issues (each lane knows its own: acc_R)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) grow[i] = __shfl_sync(0xffffffffu, acc_R, 16 * rd + 4 * q + i);
         if (lane == 0) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const int rr = 4 * q + i, grow = tile_row(a, acc_tile, lrow0 + 16 * rd + rr);
-            if (grow >= 0) bulk_reduce_add_f32(a.agg + (size_t)grow * N2, stg + (uint32_t)rr * F_STG_ROW, N2 * 4);
+            const int rr = 4 * q + i;
+            if (grow[i] >= 0) bulk_reduce_add_f32(a.agg + (size_t)grow[i] * N2, stg + (uint32_t)rr * F_STG_ROW, N2 * 4);
           }
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // rows read: the staging may be rewritten
@@ -433,6 +435,7 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
     rotate();
     rotate();              // record of step 0 -> slot 0
     acc_tile = s_tile[0];
+    acc_R = s_row[0];
     MPG_TP(3);
     if (nsteps > 1) {
       mbar_wait(bar_d1, 0);   // M1(0) done: the H0' tile may be overwritten
@@ -494,6 +497,7 @@ __global__ void __launch_bounds__(F_NTHR, 1) edge_tc_fwd_kernel(TcArgs t) {
         if (cur_tile != acc_tile) {   // step it-1 was the last one of its tile
           flush();
           acc_tile = cur_tile;
+          acc_R = cur_row;
         }
       }
       e_m = m_cur;          // multiplier of step `it` (its E2 runs in the next iteration)

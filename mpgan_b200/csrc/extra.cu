@@ -166,26 +166,28 @@ int launch_cond_columns(const float* x, int ldx, const float* cond, int C, float
   return 0;
 }
 // ---- receiver compaction map (EdgeArgs::cmap, edge.cuh) -------------------------------------------------------------
-// One block.  (1) a thread per jet counts its unmasked particles; (2) thread 0 places the jets one after the other in
-// the compacted row space -- a 128-row tile may touch at most MAXJ consecutive jets (the Q ring of the edge kernels
-// holds one row per jet), so when the next jet would be the (MAXJ+1)-th of its tile the rest of the tile stays empty;
-// (3) a thread per jet writes its rows' padded indices, a thread per tile the tile's jet span.
-constexpr int CMAP_MAXJ = 10;
-constexpr size_t CMAP_SMEM_MAX = 160 * 1024;   // counts / start positions and the mask bits live in shared memory up to here
+// One block, everything parallel.  Jet j gets max(n_j, CMAP_MINW) consecutive positions of the compacted row space (its
+// n_j unmasked particles first, in order; the rest stays empty): with every jet at least 15 positions wide a 128-row
+// tile touches at most floor(126 / 15) + 2 = 10 jets -- the bound of the edge kernels' Q ring -- and the positions are
+// an exclusive prefix sum (a sequential "open a new tile at the 11th jet" rule packs a little tighter for batches of
+// tiny jets but costs ~50 us on one thread).  Tile t's jet span comes from two binary searches over the positions.
+constexpr int CMAP_MINW = 15;
+constexpr size_t CMAP_SMEM_MAX = 160 * 1024;   // positions, counts and the mask bits live in shared memory up to here
 __host__ __device__ inline size_t cmap_smem(long long B, long long N) {
-  return (size_t)B * sizeof(int) + (size_t)((B * N + 3) / 4 + 15) / 16 * 16;
+  return (size_t)(2 * B + 8) * sizeof(int) + (size_t)((B * N + 3) / 4 + 15) / 16 * 16;
 }
 __global__ void __launch_bounds__(256) compact_map_kernel(const float* __restrict__ mask, int B, int N, int* __restrict__ cmap,
-                                                          int tmax, int* __restrict__ start_g /* [B] scratch */, int in_smem) {
+                                                          int tmax, int* __restrict__ scratch_g /* [2B + 8] */, int in_smem) {
   extern __shared__ int cm_sm[];
-  int* start = in_smem ? cm_sm : start_g;   // count, then first position of every jet
-  uint8_t* nib = reinterpret_cast<uint8_t*>(cm_sm + B);   // in_smem: bit (i & 3) of nib[i >> 2] = mask[i] != 0
+  int* start = in_smem ? cm_sm : scratch_g;   // first position of every jet
+  int* cnt = start + B;                       // unmasked particles of every jet
+  uint8_t* nib = reinterpret_cast<uint8_t*>(cm_sm + 2 * B + 8);   // in_smem: bit (i & 3) of nib[i >> 2] = mask[i] != 0
+  __shared__ int wsum[8], s_total;
   int* tile_j0 = cmap + 2;
   int* tile_nj = cmap + 2 + tmax;
   int* rowmap = cmap + 2 + 2 * tmax;
-  const int BN = B * N;
+  const int BN = B * N, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < tmax * 128; i += blockDim.x) rowmap[i] = -1;
-  for (int t = threadIdx.x; t < tmax; t += blockDim.x) { tile_j0[t] = 0; tile_nj[t] = 1; }
   if (in_smem) {   // one coalesced pass over the mask, eight loads in flight per thread
     const int n4 = (BN + 3) >> 2;
     for (int i0 = threadIdx.x; i0 < n4; i0 += blockDim.x * 8) {
@@ -209,43 +211,66 @@ __global__ void __launch_bounds__(256) compact_map_kernel(const float* __restric
     __syncthreads();
   }
   auto live = [&](int e) { return in_smem ? ((nib[e >> 2] >> (e & 3)) & 1) != 0 : mask[e] != 0.f; };
-  for (int j = threadIdx.x; j < B; j += blockDim.x) {
+  // counts and widths: thread t owns jets [t*K, t*K + K)
+  const int K = (B + (int)blockDim.x - 1) / (int)blockDim.x;
+  const int ja = min(B, (int)threadIdx.x * K), jb = min(B, ja + K);
+  int mine = 0;
+  for (int j = ja; j < jb; ++j) {
     int n = 0;
     for (int i = 0; i < N; ++i) n += live(j * N + i);
-    start[j] = n;
+    cnt[j] = n;
+    mine += max(n, CMAP_MINW);
   }
+  // block-wide exclusive scan of the per-thread widths
+  int inc = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += u;
+  }
+  if (lane == 31) wsum[warp] = inc;
   __syncthreads();
   if (threadIdx.x == 0) {
-    int pos = 0, first = -1;            // next free position; first jet of the tile `pos` lies in (-1: tile still empty)
-    for (int j = 0; j < B; ++j) {
-      const int n = start[j];
-      if (n == 0) { start[j] = -1; continue; }
-      if ((pos & 127) == 0) first = -1;
-      if (first >= 0 && j - first + 1 > CMAP_MAXJ) { pos = (pos + 127) & ~127; first = -1; }
-      if (first < 0) { first = j; tile_j0[pos >> 7] = j; }
-      tile_nj[pos >> 7] = j - first + 1;
-      start[j] = pos;
-      const int end = pos + n;
-      for (int t = (pos >> 7) + 1; t <= ((end - 1) >> 7); ++t) {   // the jet runs on: it is the first jet of those tiles
-        first = j;
-        tile_j0[t] = j;
-        tile_nj[t] = 1;
-      }
-      pos = end;
-    }
-    cmap[0] = (pos + 127) >> 7;
-    cmap[1] = pos;
+    int run = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { const int v = wsum[w]; wsum[w] = run; run += v; }
+    s_total = run;
+    cmap[0] = (run + 127) >> 7;
+    cmap[1] = run;
   }
   __syncthreads();
-  for (int j = threadIdx.x; j < B; j += blockDim.x) {
-    int p = start[j];
-    if (p < 0) continue;
+  int pos = wsum[warp] + inc - mine;
+  for (int j = ja; j < jb; ++j) {
+    start[j] = pos;
+    int p = pos;
     for (int i = 0; i < N; ++i)
       if (live(j * N + i)) rowmap[p++] = j * N + i;
+    pos += max(cnt[j], CMAP_MINW);
+  }
+  __syncthreads();
+  // jets of every tile: those with an unmasked particle at a position inside [128 t, 128 t + 127]
+  const int ntile = (s_total + 127) >> 7;
+  for (int t = threadIdx.x; t < tmax; t += blockDim.x) {
+    int j0 = 0, nj = 0;
+    if (t < ntile) {
+      const int a = t * 128, b = a + 127;
+      auto last_le = [&](int v) {   // last jet whose first position is <= v (start is non-decreasing, start[0] = 0)
+        int lo = 0, hi = B - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (start[mid] <= v) lo = mid; else hi = mid - 1; }
+        return lo;
+      };
+      int lo = last_le(a), hi = last_le(b);
+      if (start[lo] + cnt[lo] <= a) ++lo;                 // its particles end before the tile begins
+      while (lo <= hi && cnt[lo] == 0) ++lo;
+      while (hi >= lo && cnt[hi] == 0) --hi;
+      if (lo <= hi) { j0 = lo; nj = hi - lo + 1; }
+    }
+    tile_j0[t] = j0;
+    tile_nj[t] = nj;
   }
 }
 
 int launch_compact_map(const float* mask, int B, int N, int* cmap, int* scratch, cudaStream_t s) {
+  // (`scratch`, 2B + 8 ints, is only touched by very large batches whose positions do not fit shared memory)
   const bool in_smem = cmap_smem(B, N) <= CMAP_SMEM_MAX;
   const size_t smem = in_smem ? cmap_smem(B, N) : 0;
   MPG_CUDA(cudaFuncSetAttribute(compact_map_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CMAP_SMEM_MAX));

@@ -343,7 +343,7 @@ def compact_map(mask):
     B, N = int(mask.shape[0]), int(mask.shape[1])
     m = mask.detach().reshape(B, N).contiguous().float()
     cmap = torch.empty(int(L.mpg_compact_map_ints(B, N)), device=m.device, dtype=torch.int32)
-    scratch = torch.empty(B, device=m.device, dtype=torch.int32)
+    scratch = torch.empty(2 * B + 8, device=m.device, dtype=torch.int32)
     _lib.check(L.mpg_compact_map(_lib.ptr(m), B, N, _lib.ptr(cmap), _lib.ptr(scratch), _lib.stream()), "mpg_compact_map")
     return cmap
 

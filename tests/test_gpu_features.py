@@ -399,8 +399,8 @@ def _ragged_inputs(B, N, seed, zero_jets=()):
 
 @pytest.mark.parametrize("B,N", [(37, 30), (300, 30), (20, 150), (64, 17)])
 def test_compaction_map_invariants(B, N):
-    """mpg_compact_map: every unmasked particle appears exactly once, in order; a tile spans at most 10 jets and its
-    (first jet, jet count) entries cover exactly the jets of its rows."""
+    """mpg_compact_map: every unmasked particle appears exactly once, in order (each jet is given max(n, 15) positions);
+    a tile spans at most 10 jets and its (first jet, jet count) entries cover exactly the jets of its rows."""
     from mpgan_b200 import ops
     x, n = _ragged_inputs(B, N, 5 + B, zero_jets=(1, B - 1))
     mask = x[..., 3] + 0.5
@@ -415,8 +415,10 @@ def test_compaction_map_invariants(B, N):
     assert int(cmap[1]) >= want.numel() and nt <= tmax
     for t in range(nt):
         r = rows[t][rows[t] >= 0]
-        assert r.numel() > 0
         j0, nj = int(cmap[2 + t]), int(cmap[2 + tmax + t])
+        if r.numel() == 0:          # a tile of padding only (runs of empty jets): no jets, no steps
+            assert nj == 0
+            continue
         assert j0 == int(r[0]) // N and j0 + nj - 1 == int(r[-1]) // N and 1 <= nj <= 10
 
 
