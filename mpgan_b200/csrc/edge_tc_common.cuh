@@ -354,9 +354,9 @@ struct TcArgs {
 // weight images: img[n][k] (K-major, SW128) = bf16(scale * W[n][k]) for k < K, bias_hi / bias_lo at
 // k = K, K+1, zero elsewhere.
 // ---------------------------------------------------------------------------------------------------
-// One set-up launch per call: blocks [0, nb_pq) compute P / Q (pq_fwd_tile: job = 2 * tile + output), the next nb_prep blocks write both
-// weight images and (forward) zero-fill the aggregate the edge kernel accumulates into with reductions, the last
-// block builds the work list.
+// One set-up launch per call: block 0 builds the work list, the next nb_pq blocks compute P / Q (pq_fwd_tile: job =
+// 2 * tile + output), the remaining nb_prep blocks write both
+// weight images and (forward) zero-fill the aggregate the edge kernel accumulates into with reductions.
 struct PrepArgs {
   const float* W1; const float* b1; const float* W2; const float* b2;
   float scale;
@@ -546,14 +546,17 @@ __global__ void __launch_bounds__(256) step_list_kernel(const float* __restrict_
 
 __global__ void __launch_bounds__(256) edge_setup_kernel(PqFwdArgs pq, int nb_pq, PrepArgs pr, int nb_prep, ListArgs ls) {
   extern __shared__ __align__(16) float setup_sm[];
-  const int b = blockIdx.x;
-  if (b < nb_pq) {
+  // the work-list block goes first: it is the longest single block (one SM walks every tile), so it must not wait for
+  // a free slot behind hundreds of others
+  const int nb_list = ls.in_block ? 1 : 0;
+  const int b = (int)blockIdx.x - nb_list;
+  if (b < 0) {
+    step_list_block(ls, reinterpret_cast<int*>(setup_sm));
+  } else if (b < nb_pq) {
     pq_fwd_tile(pq, b, setup_sm);
-  } else if (b < nb_pq + nb_prep) {
+  } else {
     if (!ls.in_block && b == nb_pq && threadIdx.x == 0) *ls.total = 0;   // counter of the step_list_kernel that follows
     edge_prepare_block(pr, b - nb_pq, nb_prep);
-  } else {
-    step_list_block(ls, reinterpret_cast<int*>(setup_sm));
   }
 }
 #endif  // MPG_TC_WRAPPERS_ONLY
