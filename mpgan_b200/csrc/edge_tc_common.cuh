@@ -339,7 +339,7 @@ __device__ __forceinline__ void tile_jets(const EdgeArgs& a, int tile, int& j0, 
 
 struct TcArgs {
   EdgeArgs a;
-  const uint8_t* w1img;   // pre-swizzled bf16 images (edge_prepare_kernel)
+  const uint8_t* w1img;   // pre-swizzled bf16 images (edge_setup_kernel: edge_prepare_block)
   const uint8_t* w2img;
   uint2* sbits;           // backward: sign bits of D2, one uint2 per (step, epilogue thread)
   float* wslab;           // backward: per-CTA weight-gradient partials (edge_tc_bwd.cuh: SLAB_*)

@@ -28,9 +28,14 @@
 // E2lo/E2hi(s-1) and H0'(s+2) are produced under M2(s) / M1(s+1).
 // TMEM: D1a [0,160) D1b [160,320) D2lo [320,416) D2hi [416,512).
 //
-// Dropout (p = 0.5): Philox bits as laid out in common.cuh (edge_drop_*), applied to the packed bf16
-// words (layers 0/1) or to the mask multiplier (layer 2) through PRMT sign-replication masks; the 2x
+// Dropout (p = 0.5): Philox bits as laid out in common.cuh (edge_drop_*: one draw per pair and column quarter,
+// made when H0' is built and carried with the step record), applied to the packed bf16 words (layers 0/1)
+// through PRMT sign-replication masks or as the predicate of the accumulating FFMA (layer 2); the 2x
 // scale of layers 0/1 is folded into the next weight image, the last one into the flush.
+// Tiles: 128 consecutive rows of [B*N], or the rows the receiver-compaction map lists (tile_row / tile_jets,
+// edge_tc_common.cuh).  Per-row global traffic (P on entering a tile, the aggregate flush) is organised so that
+// a warp -- one row per lane -- touches contiguous memory: tile-major P, flush through shared memory + bulk
+// reduce-add.
 
 constexpr int F_NEPI = 512;                  // epilogue threads
 constexpr int F_NTHR = F_NEPI + 128;         // + control warpgroup (warp 16: MMA issuer, warp 17: TMA loader)
