@@ -406,6 +406,9 @@ def test_compaction_map_invariants(B, N):
     mask = x[..., 3] + 0.5
     mask[2, 0] = 0            # a hole: masks need not be prefixes
     cmap = ops.compact_map(mask).cpu()
+    from compact_ref import compact_map_ref, as_cmap      # the numpy restatement of the layout rule: exact agreement
+    want_map = torch.from_numpy(as_cmap(compact_map_ref(mask.cpu().numpy())))
+    assert torch.equal(cmap, want_map), "device map != reference map"
     tmax = (cmap.numel() - 2) // 130
     nt = int(cmap[0])
     rows = cmap[2 + 2 * tmax:2 + 2 * tmax + nt * 128].view(nt, 128)

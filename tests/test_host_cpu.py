@@ -207,3 +207,44 @@ def test_rank_shard_covers_all_samples():
         spans = [train.rank_shard(n, r, w) for r in range(w)]
         assert spans[0][0] == 0 and spans[-1][1] == n
         assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+def test_compaction_map_reference_properties():
+    """The layout rule of mpg_compact_map (numpy restatement, tests/compact_ref.py): every unmasked particle once, in
+    order; with every jet at least 15 positions wide no 128-row tile touches more than 10 jets (the bound of the edge
+    kernels' Q ring), for any mix of tiny, empty and full jets; and the executed-step count ops.edge_active_fraction
+    derives from a map equals a direct count."""
+    import numpy as np
+    import torch
+    from compact_ref import compact_map_ref, as_cmap
+    from mpgan_b200 import ops
+    rng = np.random.default_rng(0)
+    for B, N, kind in [(64, 30, "uniform"), (200, 30, "tiny"), (33, 150, "uniform"), (50, 17, "holes"), (40, 30, "empty")]:
+        if kind == "tiny":
+            n = rng.integers(0, 4, B)
+        elif kind == "empty":
+            n = np.where(rng.random(B) < 0.5, 0, rng.integers(1, N + 1, B))
+        else:
+            n = rng.integers(1, N + 1, B)
+        mask = (np.arange(N)[None, :] < n[:, None]).astype(np.float32)
+        if kind == "holes":
+            mask *= rng.random((B, N)) < 0.7
+        ref = compact_map_ref(mask)
+        rows = ref["rowmap"][ref["rowmap"] >= 0]
+        assert np.array_equal(rows, np.nonzero(mask.reshape(-1))[0])
+        assert ref["tiles"] <= ref["tmax"] and ref["tile_nj"].max() <= 10
+        for t in range(ref["tiles"]):
+            r = ref["rowmap"][t * 128:(t + 1) * 128]
+            r = r[r >= 0]
+            if r.size:
+                assert ref["tile_j0"][t] == r[0] // N and ref["tile_j0"][t] + ref["tile_nj"][t] - 1 == r[-1] // N
+            else:
+                assert ref["tile_nj"][t] == 0
+        # executed (tile, sender) steps: sender s of a tile is live if any of the tile's jets has it unmasked
+        steps = 0
+        for t in range(ref["tiles"]):
+            j0, nj = int(ref["tile_j0"][t]), int(ref["tile_nj"][t])
+            if nj:
+                steps += int((mask[j0:j0 + nj] != 0).any(0).sum())
+        frac = ops.edge_active_fraction(torch.from_numpy(mask), B, N, torch.from_numpy(as_cmap(ref)))
+        assert abs(frac - steps / (((B * N + 127) // 128) * N)) < 1e-12
