@@ -523,7 +523,9 @@ def measure(name, wl, args, env, with_baselines):
                        "particles_per_jet": "all N real" if all_real else "n ~ U{1..N} (padded rows masked); every rank's "
                                             "shard has the same particle-count multiset (fixed per-GPU work)",
                        "batch_order": "jets ordered by particle count inside each batch (GANTrainer.sort_by_count / "
-                                      "train.generate); fully padded (tile, sender) steps are dropped by the kernels",
+                                      "train.generate); fully padded (tile, sender) steps are dropped by the kernels; the "
+                                      "discriminator's edge tiles hold unmasked particles only (receiver compaction, exact: "
+                                      "DESIGN.md 4.1)",
                        "l2": "flushed between timed steps (256 MiB write)",
                        "precision": ("TF32 projections, fp32 attention core" if gapt else
                                      "bf16 tcgen05 edge network, TF32 node GEMMs, fp32 accumulate"), "parallelism": f"dp{world}",
